@@ -1,0 +1,178 @@
+/*
+ * rvb.h -- C ABI of librvb.so, the sm_100a (B200) kernels behind reconvat_b200.
+ *
+ * The reference (KinWaiCheuk/ReconVAT) is 100 % Python and has no FFI of its
+ * own: its hot path is a sequence of ATen calls.  Each entry point below
+ * replaces the ATen call sequence cited next to it (paths relative to the
+ * reference tree); reconvat_b200/_lib.py binds them with ctypes and
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to float32 unless stated otherwise;
+ *     all memory is owned by the caller (PyTorch tensors); the library keeps
+ *     no global state besides a cache of TMA descriptors keyed by
+ *     (pointer, shape);
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work
+ *     on it (no host synchronisation);
+ *   - return value: 0 = enqueued; negative = error (RVB_ERR_*), message via
+ *     rvb_last_error() (thread-local).  Nothing throws across the boundary;
+ *   - device-side anomalies (NaN/Inf in r_adv) are reported through a
+ *     caller-owned device int (`status_flag`), never by aborting the kernel.
+ */
+#ifndef RVB_H_
+#define RVB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVB_ABI_VERSION 1
+
+#define RVB_OK 0
+#define RVB_ERR_ARG (-1)    /* bad argument (shape / alignment / unsupported combination) */
+#define RVB_ERR_CUDA (-2)   /* a CUDA runtime / driver call failed */
+#define RVB_ERR_LAUNCH (-3) /* kernel launch failed */
+
+typedef void* rvb_stream_t;
+
+int rvb_abi_version(void);
+const char* rvb_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py: gpu_launches) */
+int64_t rvb_launch_count(void);
+
+/* ------------------------------------------------------------------ front-end */
+
+/* pad modes of STFT.forward, model/Spectrogram.py:209-218 */
+#define RVB_PAD_REFLECT 0  /* center=True, pad_mode='reflect'  (nn.ReflectionPad1d(n_fft//2)) */
+#define RVB_PAD_CONSTANT 1 /* center=True, pad_mode='constant' (nn.ConstantPad1d(n_fft//2, 0)) */
+#define RVB_PAD_NONE 2     /* center=False */
+
+/*
+ * K0  pad + hop-blocking + tf32 hi/lo split.
+ * Replaces: the caller-side trim `audio[:, :-1]` (model/self_attention_VAT.py:1100,1112,1296 --
+ * express it through n_samples / audio_ld) and `padding(x)` (model/Spectrogram.py:216-218).
+ * Writes two planes [n_seg][rows_per_seg][hop]: sig_hi = tf32(p), sig_lo = tf32(p - sig_hi),
+ * where p is the padded signal laid out in non-overlapping hop-sized rows, so that sample n of
+ * frame t is plane[(t + n / hop) * hop + n % hop]; positions past the padded length are zero.
+ */
+int rvb_pad_split(const float* audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int pad_mode,
+                  float* sig_hi, float* sig_lo, int rows_per_seg, int hop, rvb_stream_t stream);
+
+/* epilogues of the STFT contraction, model/Spectrogram.py:226-237 and :458 */
+#define RVB_EPI_POWER 0     /* (sqrt(re^2+im^2))^2   out0[b][k][t]     (:227,231 then **2.0 at :458) */
+#define RVB_EPI_MAGNITUDE 1 /* sqrt(re^2+im^2)       out0[b][k][t]     (:227,231) */
+#define RVB_EPI_COMPLEX 2   /* (re, -im)             out0[b][k][t][2]  (:234) */
+#define RVB_EPI_PHASE 3     /* atan2(-im + 0.0, re)  out0[b][k][t]     (:237) */
+#define RVB_EPI_POWER_P 4   /* sqrt(re^2+im^2)^power out0[b][k][t]     (general `power`, :458) */
+
+/*
+ * K1  STFT as a dense contraction on tcgen05 tensor cores, 3xTF32 (hi*hi + hi*lo + lo*hi, fp32
+ * accumulators in TMEM), TMA-staged operands.
+ * Replaces: `conv1d(x, wsin, stride)` + `conv1d(x, wcos, stride)` (model/Spectrogram.py:219-220),
+ * the magnitude (:226-231) and `** self.power` (:458) or the Complex / Phase formats (:234,237).
+ *   sig_hi/lo   planes from rvb_pad_split
+ *   basis_hi/lo [n_basis_rows][n_fft] row-major, tf32 hi/lo split of the windowed Fourier basis,
+ *               rows grouped in tiles of 256: rows [256j, 256j+128) = wcos bins [128j, 128j+128),
+ *               rows [256j+128, 256j+256) = wsin of the same bins  (n_basis_rows % 256 == 0)
+ *   out0        n_out_bins rows per segment; the kernel writes bins [0, min(n_out_bins, n_basis_rows/2))
+ * Constraints: n_fft % 32 == 0, hop % 32 == 0, all pointers 128-byte aligned.
+ */
+int rvb_stft_gemm(const float* sig_hi, const float* sig_lo, int n_seg, int rows_per_seg, int hop, int n_frames,
+                  const float* basis_hi, const float* basis_lo, int n_basis_rows, int n_fft, int epilogue,
+                  float power, float* out0, int n_out_bins, rvb_stream_t stream);
+
+/*
+ * K1b  one frequency bin in plain fp32 FMA (used for the Nyquist bin, which would otherwise cost a
+ * whole extra 256-column tile).  Same epilogues / output indexing as rvb_stft_gemm; `wcos_row`,
+ * `wsin_row` are the fp32 windowed basis rows of that bin (model/Spectrogram.py:162-164).
+ */
+int rvb_stft_bin(const float* sig_hi, const float* sig_lo, int n_seg, int rows_per_seg, int hop, int n_frames,
+                 const float* wcos_row, const float* wsin_row, int n_fft, int bin, int epilogue, float power,
+                 float* out0, int n_out_bins, rvb_stream_t stream);
+
+#define RVB_LAYOUT_BINS_MAJOR 0 /* out[b][m][t]  -- what MelSpectrogram.forward returns (:460) */
+#define RVB_LAYOUT_TIME_MAJOR 1 /* out[b][t][m]  -- after `.transpose(-1,-2)` (self_attention_VAT.py:1104) */
+
+/*
+ * K2  banded Mel projection (+ optional log compression and per-segment min/max).
+ * Replaces: `torch.matmul(self.mel_basis, spec)` (model/Spectrogram.py:460),
+ * `torch.log(spec + 1e-5)` (model/self_attention_VAT.py:1102) and the two reductions of
+ * Normalization('imagewise') (model/utils.py:96-97).
+ * The filterbank is passed in banded form: bin k feeds band band0[k] with weight w0[k] and band
+ * band0[k]+1 with weight w1[k] (triangular filters overlap pairwise; band0 non-decreasing in k).
+ *   power     [n_seg][n_bins][n_frames]
+ *   log_offset < 0: no log;  >= 0: out = logf(mel + log_offset)
+ *   minmax    NULL, or uint32 [n_seg][2] receiving order-preserving keys of (min, max) of `out`
+ *             per segment (decoded by rvb_normalise); the call zeroes it first.
+ */
+int rvb_mel_project(const float* power, int n_seg, int n_bins, int n_frames, const int32_t* band0,
+                    const float* w0, const float* w1, int k_begin, int k_end, int n_mels, float log_offset,
+                    int layout, float* out, uint32_t* minmax, rvb_stream_t stream);
+
+/*
+ * Per-segment min/max keys of an arbitrary [n_seg][n_per_seg] tensor
+ * (model/utils.py:96-97 when Normalization is used on its own).
+ */
+int rvb_minmax(const float* x, int n_seg, int64_t n_per_seg, uint32_t* minmax, rvb_stream_t stream);
+
+/*
+ * K3  y = (x - min) / (max - min) per segment, in place when y == x
+ * (model/utils.py:100; no epsilon: a constant image gives NaN exactly as the reference).
+ */
+int rvb_normalise(const float* x, float* y, int n_seg, int64_t n_per_seg, const uint32_t* minmax,
+                  rvb_stream_t stream);
+
+/* ------------------------------------------------------------------ VAT loop */
+
+/*
+ * V1  x_adv = clamp(x + xi * d / ||d||_row, 0, 1)      rows of `row_len` (229) floats.
+ * Replaces: `_l2_normalize(d)` + `XI * .` + `(x + r).clamp(0,1)`
+ * (model/self_attention_VAT.py:176-177, :240-246; model/UNet_onset.py:130-131;
+ *  model/onset_frame_VAT.py:182-183; model/VAT.py:27-28 with do_clamp = 0).
+ */
+int rvb_vat_perturb(const float* x, const float* d, float* x_adv, int64_t n_rows, int row_len, float xi,
+                    int do_clamp, rvb_stream_t stream);
+
+/*
+ * V2  grad = gscale * (p - y) / max((1 - p) * p, 1e-12) / n   (d mean-BCE / d p, ATen's formula).
+ * Replaces: the backward of `F.binary_cross_entropy(y_pred, y_ref)`
+ * (model/self_attention_VAT.py:182-183).  `gscale_dev` is an optional device scalar (upstream grad).
+ */
+int rvb_bce_grad(const float* p, const float* y, float* grad, int64_t n, const float* gscale_dev, float gscale,
+                 rvb_stream_t stream);
+
+/*
+ * V3  power-iteration backward + finalisation, one pass over (g, d, x):
+ *   n = ||d||, dhat = d/n, m = [0 <= x + xi*dhat <= 1], gd = xi * g * m
+ *   d' = scale * (gd / n - d * sum(gd * d) / n^3)                 (== d.grad * scale)
+ *   dhat' = d'/||d'||, r_adv = eps * dhat', x_adv = clamp(x + r_adv, 0, 1)
+ * Replaces: autograd through clamp/add/mul/div/norm, `d.grad.detach()*1e10`,
+ * `eps*_l2_normalize(d)`, the NaN asserts, `(x + r_adv).clamp(0,1)` and the recomputed
+ * `_l2_normalize(d)` (model/self_attention_VAT.py:183-202 and siblings).
+ * status_flag (device int, caller zeroes): bit0 = NaN in r_adv, bit1 = Inf in r_adv.
+ */
+int rvb_vat_finalize(const float* g, const float* d, const float* x, float* r_adv, float* x_adv, float* d_hat,
+                     int64_t n_rows, int row_len, float xi, float eps, float scale, int do_clamp,
+                     int32_t* status_flag, rvb_stream_t stream);
+
+/*
+ * V3b finalisation only (n_power == 0: the random direction is used as is):
+ *   dhat = d/||d||, r_adv = eps*dhat, x_adv = clamp(x + r_adv)     (:188-194 with d = randn)
+ */
+int rvb_vat_direct(const float* d, const float* x, float* r_adv, float* x_adv, float* d_hat, int64_t n_rows,
+                   int row_len, float eps, int do_clamp, int32_t* status_flag, rvb_stream_t stream);
+
+/*
+ * V4  loss = mean( -(y*max(log p,-100) + (1-y)*max(log1p(-p),-100)) ), deterministic two-level sum.
+ * Replaces: `F.binary_cross_entropy(y_pred, y_ref)` forward (model/self_attention_VAT.py:200).
+ * workspace: >= RVB_BCE_WORKSPACE_FLOATS floats, zero-initialised once by the caller (self-cleaning).
+ */
+#define RVB_BCE_WORKSPACE_FLOATS 1032
+int rvb_bce_mean(const float* p, const float* y, int64_t n, float* loss, float* workspace, rvb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVB_H_ */

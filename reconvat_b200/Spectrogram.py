@@ -1,0 +1,284 @@
+"""Drop-in for ``nnAudio.Spectrogram`` (== the reference's vendored model/Spectrogram.py) limited to
+the classes on the hot path: ``STFT`` (model/Spectrogram.py:22-316) and ``MelSpectrogram``
+(model/Spectrogram.py:319-466).  Same constructor arguments, same registered buffers
+(``wsin``, ``wcos``, ``window_mask``, ``mel_basis`` -- checkpoint compatible, transcribe_files.py:71
+loads strictly), same output shapes and formats; the arithmetic runs in librvb.so:
+
+    pad + hop-block + tf32 split  ->  tcgen05 3xTF32 contraction (+ magnitude / power / complex /
+    phase epilogue)  ->  banded Mel  [-> log -> per-segment min/max -> normalise, fused extension]
+
+Scope cuts, all raising instead of silently computing something else: ``trainable*=True`` (no
+config of the reference uses it), ``STFT.inverse`` / the other nnAudio transforms,
+CPU tensors (there is no fallback path).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, basis
+
+__all__ = ["STFT", "MelSpectrogram"]
+
+
+def _ceil_div(a, b):
+    return -(-a // b)
+
+
+class STFT(nn.Module):
+    """model/Spectrogram.py:22-237.  ``forward(x, output_format=None)``:
+    ``Magnitude`` -> (B, F, T); ``Complex`` -> (B, F, T, 2) holding (re, -im); ``Phase`` -> (B, F, T)."""
+
+    def __init__(self, n_fft=2048, win_length=None, freq_bins=None, hop_length=None, window='hann',
+                 freq_scale='no', center=True, pad_mode='reflect', iSTFT=False,
+                 fmin=50, fmax=6000, sr=22050, trainable=False,
+                 output_format="Complex", verbose=True):
+        super().__init__()
+        if trainable:
+            raise NotImplementedError("reconvat_b200.STFT: trainable=True (autograd through the Fourier basis, "
+                                      "model/Spectrogram.py:170-174) is outside the accelerated hot path")
+        if win_length is None:
+            win_length = n_fft
+        if hop_length is None:
+            hop_length = int(win_length // 4)
+        self.output_format = output_format
+        self.trainable = trainable
+        self.stride = hop_length
+        self.center = center
+        self.pad_mode = pad_mode
+        self.n_fft = n_fft
+        self.freq_bins = freq_bins
+        self.pad_amount = self.n_fft // 2
+        self.window = window
+        self.win_length = win_length
+        self.iSTFT = iSTFT
+
+        kernel_sin, kernel_cos, self.bins2freq, self.bin_list, window_mask = basis.fourier_basis(
+            n_fft, win_length=win_length, freq_bins=freq_bins, window=window, freq_scale=freq_scale,
+            fmin=fmin, fmax=fmax, sr=sr)
+        kernel_sin = torch.from_numpy(kernel_sin).unsqueeze(1)        # (F, 1, n_fft)
+        kernel_cos = torch.from_numpy(kernel_cos).unsqueeze(1)
+        if iSTFT:   # kept only so that state_dict keys match; inverse() is not accelerated
+            self.register_buffer('kernel_sin_inv', torch.cat((kernel_sin, -kernel_sin[1:-1].flip(0)), 0).unsqueeze(-1))
+            self.register_buffer('kernel_cos_inv', torch.cat((kernel_cos, kernel_cos[1:-1].flip(0)), 0).unsqueeze(-1))
+        window_mask = torch.from_numpy(window_mask)
+        # float32 product, as model/Spectrogram.py:162-164
+        self.register_buffer('wsin', kernel_sin * window_mask)
+        self.register_buffer('wcos', kernel_cos * window_mask)
+        self.register_buffer('window_mask', window_mask.unsqueeze(0).unsqueeze(-1))
+        self._tables = None          # device operand planes, rebuilt lazily from wsin/wcos
+        self._tables_key = None
+        if verbose:
+            print("STFT kernels created (reconvat_b200, tcgen05 3xTF32 contraction)")
+
+    # -- device tables ------------------------------------------------------------------
+    def _device_tables(self):
+        key = (self.wsin.device, self.wsin._version, self.wcos._version, self.wsin.data_ptr())
+        if self._tables is None or self._tables_key != key:
+            if not self.wsin.is_cuda:
+                raise _lib.RvbError("reconvat_b200.STFT: module is on %s; move it to a CUDA device "
+                                    "(there is no CPU path)" % self.wsin.device)
+            wcos = self.wcos[:, 0, :].detach().cpu().numpy()
+            wsin = self.wsin[:, 0, :].detach().cpu().numpy()
+            hi, lo, n_gemm, leftover = basis.gemm_operand(wcos, wsin)
+            dev = self.wsin.device
+            self._tables = dict(basis_hi=torch.from_numpy(hi).to(dev), basis_lo=torch.from_numpy(lo).to(dev),
+                                n_gemm_bins=n_gemm, leftover=leftover, n_bins=wcos.shape[0])
+            self._tables_key = key
+        return self._tables
+
+    def _apply(self, fn, *args, **kwargs):
+        self._tables = None
+        return super()._apply(fn, *args, **kwargs)
+
+    # -- geometry -----------------------------------------------------------------------
+    def _geometry(self, num_samples):
+        if self.center:
+            if self.pad_mode == 'reflect':
+                if num_samples < self.pad_amount:
+                    raise AssertionError("Signal length shorter than reflect padding length (n_fft // 2).")
+                if num_samples == self.pad_amount:
+                    # the reference reaches nn.ReflectionPad1d, which refuses pad >= length
+                    raise RuntimeError("Padding size should be less than the corresponding input dimension, but got: "
+                                       "padding (%d, %d) at dimension 2 of input [1, 1, %d]"
+                                       % (self.pad_amount, self.pad_amount, num_samples))
+                mode = _lib.PAD_REFLECT
+            elif self.pad_mode == 'constant':
+                mode = _lib.PAD_CONSTANT
+            else:
+                raise ValueError("pad_mode must be 'reflect' or 'constant'")
+            padded = num_samples + 2 * self.pad_amount
+        else:
+            mode, padded = _lib.PAD_NONE, num_samples
+        if padded < self.n_fft:
+            raise RuntimeError("Calculated padded input size per channel: (%d). Kernel size: (%d). "
+                               "Kernel size can't be greater than actual input size" % (padded, self.n_fft))
+        n_frames = (padded - self.n_fft) // self.stride + 1
+        rows = _ceil_div(padded, self.stride)
+        return mode, n_frames, rows
+
+    def _planes(self, x):
+        """x: (B,1,L) CUDA float32 -> (sig_hi, sig_lo, n_frames, rows_per_seg)."""
+        if not x.is_cuda:
+            raise _lib.RvbError("reconvat_b200.STFT: input is on %s; there is no CPU path" % x.device)
+        if x.requires_grad:
+            raise NotImplementedError("reconvat_b200.STFT: gradients w.r.t. the waveform are not provided")
+        if x.dtype != torch.float32:
+            raise _lib.RvbError("reconvat_b200.STFT: expected float32 audio, got %s" % x.dtype)
+        if self.stride % 32 != 0 or self.n_fft % 32 != 0:
+            raise NotImplementedError("reconvat_b200.STFT: hop_length and n_fft must be multiples of 32 "
+                                      "(got hop=%d, n_fft=%d)" % (self.stride, self.n_fft))
+        B, _, L = x.shape
+        x2 = x[:, 0, :]
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        mode, n_frames, rows = self._geometry(L)
+        # tail boxes of the last segment run past the planes: TMA zero-fills out-of-bounds rows
+        sig = torch.empty((2, B * rows, self.stride), dtype=torch.float32, device=x.device)
+        _lib.call("rvb_pad_split", _lib.ptr(x2), x2.stride(0) if B > 1 else L, B, L, self.pad_amount, mode,
+                  sig[0].data_ptr(), sig[1].data_ptr(), rows, self.stride)
+        return sig, n_frames, rows
+
+    def _contract(self, sig, B, n_frames, rows, epilogue, power, out, n_out_bins):
+        tb = self._device_tables()
+        _lib.call("rvb_stft_gemm", sig[0].data_ptr(), sig[1].data_ptr(), B, rows, self.stride, n_frames,
+                  tb["basis_hi"].data_ptr(), tb["basis_lo"].data_ptr(), tb["basis_hi"].shape[0], self.n_fft,
+                  epilogue, float(power), _lib.ptr(out), n_out_bins)
+        for k in tb["leftover"]:
+            if k < n_out_bins:
+                _lib.call("rvb_stft_bin", sig[0].data_ptr(), sig[1].data_ptr(), B, rows, self.stride, n_frames,
+                          self.wcos[k, 0].data_ptr(), self.wsin[k, 0].data_ptr(), self.n_fft, k, epilogue,
+                          float(power), _lib.ptr(out), n_out_bins)
+
+    def forward(self, x, output_format=None):
+        output_format = output_format or self.output_format
+        self.num_samples = x.shape[-1]
+        x = basis.broadcast_dim(x)
+        sig, n_frames, rows = self._planes(x)
+        B = x.shape[0]
+        F = self._device_tables()["n_bins"]
+        if output_format == 'Magnitude':
+            out = torch.empty((B, F, n_frames), dtype=torch.float32, device=x.device)
+            self._contract(sig, B, n_frames, rows, _lib.EPI_MAGNITUDE, 1.0, out, F)
+        elif output_format == 'Complex':
+            out = torch.empty((B, F, n_frames, 2), dtype=torch.float32, device=x.device)
+            self._contract(sig, B, n_frames, rows, _lib.EPI_COMPLEX, 1.0, out, F)
+        elif output_format == 'Phase':
+            out = torch.empty((B, F, n_frames), dtype=torch.float32, device=x.device)
+            self._contract(sig, B, n_frames, rows, _lib.EPI_PHASE, 1.0, out, F)
+        else:
+            return None          # the reference falls through its if/elif chain the same way
+        return out
+
+    def inverse(self, *args, **kwargs):
+        raise NotImplementedError("reconvat_b200.STFT.inverse: iSTFT is outside the accelerated hot path "
+                                  "(SURVEY.md section 2, row 1b)")
+
+    def extra_repr(self):
+        return 'n_fft={}, Fourier Kernel size={}, iSTFT={}, trainable={}'.format(
+            self.n_fft, (*self.wsin.shape,), self.iSTFT, self.trainable)
+
+
+class MelSpectrogram(nn.Module):
+    """model/Spectrogram.py:319-466.  ``forward(x)`` -> (B, n_mels, T) Mel power spectrogram.
+
+    Extension (not in the reference): :meth:`normalised_log_mel` runs the rest of the front-end of
+    ``UNet.run_on_batch`` (model/self_attention_VAT.py:1100-1104) fused on the device.
+    """
+
+    def __init__(self, sr=22050, n_fft=2048, n_mels=128, hop_length=512,
+                 window='hann', center=True, pad_mode='reflect', power=2.0, htk=False,
+                 fmin=0.0, fmax=None, norm=1, trainable_mel=False, trainable_STFT=False,
+                 verbose=True, **kwargs):
+        super().__init__()
+        if trainable_mel or trainable_STFT:
+            raise NotImplementedError("reconvat_b200.MelSpectrogram: trainable_mel / trainable_STFT "
+                                      "(model/Spectrogram.py:430-433) are outside the accelerated hot path")
+        self.stride = hop_length
+        self.center = center
+        self.pad_mode = pad_mode
+        self.n_fft = n_fft
+        self.power = power
+        self.trainable_mel = trainable_mel
+        self.trainable_STFT = trainable_STFT
+        self.stft = STFT(n_fft=n_fft, freq_bins=None, hop_length=hop_length, window=window,
+                         freq_scale='no', center=center, pad_mode=pad_mode, sr=sr, trainable=trainable_STFT,
+                         output_format="Magnitude", verbose=verbose, **kwargs)
+        mel_basis = basis.mel_filterbank(sr, n_fft, n_mels, fmin, fmax, htk=htk, norm=norm)
+        self.register_buffer('mel_basis', torch.from_numpy(mel_basis))
+        self._bands = None
+        self._bands_key = None
+        if verbose:
+            print("Mel filter created (reconvat_b200, banded projection)")
+
+    def _apply(self, fn, *args, **kwargs):
+        self._bands = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def _band_tables(self):
+        key = (self.mel_basis.device, self.mel_basis._version, self.mel_basis.data_ptr())
+        if self._bands is None or self._bands_key != key:
+            band0, w0, w1, k_begin, k_end = basis.banded_filterbank(self.mel_basis.detach().cpu().numpy())
+            dev = self.mel_basis.device
+            self._bands = dict(band0=torch.from_numpy(band0).to(dev), w0=torch.from_numpy(w0).to(dev),
+                               w1=torch.from_numpy(w1).to(dev), k_begin=k_begin, k_end=k_end)
+            self._bands_key = key
+        return self._bands
+
+    def _power_spectrogram(self, x):
+        """(B,1,L) -> power (B, n_pow_bins, T) holding (sqrt(re^2+im^2))**power for every bin the
+        filterbank reads (model/Spectrogram.py:458)."""
+        sig, n_frames, rows = self.stft._planes(x)
+        B = x.shape[0]
+        bands = self._band_tables()
+        n_pow_bins = bands["k_end"]                          # bins >= k_end carry zero weight: never stored
+        power = torch.empty((B, n_pow_bins, n_frames), dtype=torch.float32, device=x.device)
+        if float(self.power) == 2.0:
+            epi = _lib.EPI_POWER
+        elif float(self.power) == 1.0:
+            epi = _lib.EPI_MAGNITUDE
+        else:
+            epi = _lib.EPI_POWER_P
+        self.stft._contract(sig, B, n_frames, rows, epi, self.power, power, n_pow_bins)
+        return power, n_frames, bands
+
+    def forward(self, x):
+        x = basis.broadcast_dim(x)
+        power, n_frames, bands = self._power_spectrogram(x)
+        B, n_pow_bins, _ = power.shape
+        n_mels = self.mel_basis.shape[0]
+        out = torch.empty((B, n_mels, n_frames), dtype=torch.float32, device=x.device)
+        _lib.call("rvb_mel_project", power.data_ptr(), B, n_pow_bins, n_frames, bands["band0"].data_ptr(),
+                  bands["w0"].data_ptr(), bands["w1"].data_ptr(), bands["k_begin"], bands["k_end"], n_mels,
+                  -1.0, _lib.LAYOUT_BINS_MAJOR, out.data_ptr(), None)
+        return out
+
+    def normalised_log_mel(self, audio, trim_last=True, log_offset=1e-5, channel_dim=True, normalise=True,
+                           return_minmax=False):
+        """Fused front-end of ``UNet.run_on_batch`` (model/self_attention_VAT.py:1100-1104, 1112-1121):
+
+            spec = self(audio[:, :-1]); spec = log(spec + 1e-5)
+            spec = Normalization('imagewise').transform(spec); spec = spec.transpose(-1,-2).unsqueeze(1)
+
+        Returns a contiguous (B, 1, T, n_mels) tensor ((B, T, n_mels) when ``channel_dim=False``, the
+        O&F convention of model/onset_frame_VAT.py:647-651).  ``audio`` is (B, L) / (L) / (B,1,L).
+        """
+        x = basis.broadcast_dim(audio)
+        if trim_last:
+            x = x[:, :, :-1]                                  # a view; the kernel takes the row stride
+        power, n_frames, bands = self._power_spectrogram(x)
+        B, n_pow_bins, _ = power.shape
+        n_mels = self.mel_basis.shape[0]
+        out = torch.empty((B, n_frames, n_mels), dtype=torch.float32, device=x.device)
+        minmax = torch.empty((B, 2), dtype=torch.int32, device=x.device) if normalise else None
+        _lib.call("rvb_mel_project", power.data_ptr(), B, n_pow_bins, n_frames, bands["band0"].data_ptr(),
+                  bands["w0"].data_ptr(), bands["w1"].data_ptr(), bands["k_begin"], bands["k_end"], n_mels,
+                  float(log_offset), _lib.LAYOUT_TIME_MAJOR, out.data_ptr(),
+                  minmax.data_ptr() if normalise else None)
+        if normalise:
+            _lib.call("rvb_normalise", out.data_ptr(), out.data_ptr(), B, n_frames * n_mels, minmax.data_ptr())
+        out = out.unsqueeze(1) if channel_dim else out
+        return (out, minmax) if return_minmax else out
+
+    def extra_repr(self):
+        return 'Mel filter banks size = {}, trainable_mel={}'.format(
+            (*self.mel_basis.shape,), self.trainable_mel, self.trainable_STFT)

@@ -1,0 +1,267 @@
+"""Drop-ins for the reference's VAT modules, backed by the fused row kernels of librvb.so.
+
+The reference has the same loop five times with small differences; one core implements it and the
+named classes only fix the flavour (constructor signature, call convention, scale, return arity):
+
+==========================  ==========================================  =================================
+class here                  replaces                                    differences
+==========================  ==========================================  =================================
+``stepwise_VAT_vatpy``      model/VAT.py:9-40                           no clamp, no scale, 2-tuple
+``stepwise_VAT``            model/self_attention_VAT.py:101-145         ``model(x)``, no scale, 3-tuple
+``UNet_VAT``                model/self_attention_VAT.py:147-202         ``model.transcriber(x)``, *1e10
+``onset_frame_VAT``         model/self_attention_VAT.py:204-238         3-tuple model output, 2-tuple
+``UNet_VAT_onset``          model/UNet_onset.py:101-162                 frame+onset heads, dict loss
+``stepwise_VAT_onf``        model/onset_frame_VAT.py:158-207            3-D x, frame head = output[2]
+==========================  ==========================================  =================================
+
+What changes relative to the reference's op sequence (results identical within the stated tolerances):
+* ``x_adv`` is made a leaf and the model's backward is driven with ``torch.autograd.grad`` seeded by
+  our BCE-gradient kernel, so autograd no longer walks clamp/add/mul/div/norm and never computes
+  weight gradients that ``model.zero_grad()`` would throw away (model/self_attention_VAT.py:183-185);
+* the chain rule through the row normalisation and the clamp mask, the ``*1e10``, the second
+  normalisation, ``eps`` scaling, the clamp of ``x + r_adv`` and the recomputed ``_l2_normalize(d)``
+  are one kernel (``rvb_vat_finalize``);
+* the two host-synchronising NaN asserts (:189-190) become a device flag: it is checked (and raises
+  the reference's AssertionError) at the next call, on ``check()``, or immediately with
+  ``strict=True`` / ``RVB_STRICT_NAN=1``.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+__all__ = ["stepwise_VAT_vatpy", "stepwise_VAT", "UNet_VAT", "onset_frame_VAT", "UNet_VAT_onset",
+           "stepwise_VAT_onf", "bce_mean", "l2_normalize"]
+
+
+def _rows(x):
+    return x.numel() // x.shape[-1], x.shape[-1]
+
+
+def _check_input(x):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise _lib.RvbError("reconvat_b200 VAT needs a CUDA tensor (got %s); there is no CPU path"
+                            % (x.device if isinstance(x, torch.Tensor) else type(x)))
+    if x.dtype != torch.float32:
+        raise _lib.RvbError("reconvat_b200 VAT needs float32, got %s" % x.dtype)
+    return x if x.is_contiguous() else x.contiguous()     # the reference hands over a transposed view
+
+
+class _BCEMean(torch.autograd.Function):
+    """``F.binary_cross_entropy(p, y)`` (mean) with our forward and backward kernels.  ``y`` is a label
+    (no gradient), exactly as y_ref in the VAT loop."""
+
+    @staticmethod
+    def forward(ctx, p, y, workspace):
+        p = p.contiguous()
+        y = y.contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=p.device)
+        _lib.call("rvb_bce_mean", _lib.ptr(p), _lib.ptr(y), p.numel(), loss.data_ptr(), workspace.data_ptr())
+        ctx.save_for_backward(p, y)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        p, y = ctx.saved_tensors
+        grad = torch.empty_like(p)
+        go = grad_out.contiguous().to(torch.float32)
+        _lib.call("rvb_bce_grad", p.data_ptr(), y.data_ptr(), grad.data_ptr(), p.numel(), go.data_ptr(), 1.0)
+        return grad, None, None
+
+
+_workspaces = {}
+
+
+def _workspace(device):
+    ws = _workspaces.get(device)
+    if ws is None:
+        ws = torch.zeros(_lib.BCE_WORKSPACE_FLOATS, dtype=torch.float32, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+def bce_mean(p, y):
+    """Differentiable (w.r.t. ``p``) mean binary cross entropy on the device kernels."""
+    if p.shape != y.shape:
+        raise ValueError("Using a target size ({}) that is different to the input size ({}) is deprecated. "
+                         "Please ensure they have the same size.".format(y.shape, p.shape))
+    return _BCEMean.apply(p, y.detach(), _workspace(p.device))
+
+
+def _bce_grad(p, y):
+    """d mean-BCE / d p as a plain tensor (seeds the model's backward in the power iteration)."""
+    p = p.detach().contiguous()
+    y = y.detach().contiguous()
+    grad = torch.empty_like(p)
+    _lib.call("rvb_bce_grad", _lib.ptr(p), _lib.ptr(y), grad.data_ptr(), p.numel(), None, 1.0)
+    return grad
+
+
+def l2_normalize(d):
+    """``_l2_normalize(d, binwise=False)`` (model/self_attention_VAT.py:240-246) as one kernel."""
+    d = _check_input(d)
+    n_rows, row_len = _rows(d)
+    out = torch.empty_like(d)
+    scratch = torch.empty_like(d)
+    _lib.call("rvb_vat_direct", d.data_ptr(), d.data_ptr(), scratch.data_ptr(), scratch.data_ptr(), out.data_ptr(),
+              n_rows, row_len, 1.0, 0, None)
+    return out
+
+
+class _VATCore(nn.Module):
+    # flavour knobs, overridden by the named subclasses
+    _use_transcriber = False       # model.transcriber(x) vs model(x)
+    _heads = (0,)                  # indices of the model outputs that enter the divergence
+    _scale = 1.0                   # d.grad multiplier (1e10 in the UNet / O&F flavours)
+    _clamp = True                  # (x + r).clamp(0, 1)
+    _n_returns = 3
+    _dict_loss = None              # names of the per-head losses when the loss is returned as a dict
+    _nan_message = ("r_adv has nan, d min={dmin} d max={dmax} d mean={dmean} please debug tune down the XI for VAT")
+
+    def _init_common(self, XI, epsilon, n_power, KL_Div=False, binwise=False, strict=None):
+        self.n_power = n_power
+        self.XI = XI
+        self.epsilon = epsilon
+        self.KL_Div = KL_Div
+        self.binwise = binwise
+        self.strict = bool(int(os.environ.get("RVB_STRICT_NAN", "0"))) if strict is None else strict
+        self._pending = None       # (flag tensor, pinned host copy, event)
+        if KL_Div:
+            raise NotImplementedError("reconvat_b200 VAT: KL_Div=True (binary_kl_div, model/self_attention_VAT.py:"
+                                      "248-255) is not on any shipped configuration; SURVEY.md section 8 row f4")
+        if binwise:
+            raise NotImplementedError("reconvat_b200 VAT: binwise=True is never selected by the reference "
+                                      "(hard-wired False, model/self_attention_VAT.py:159)")
+        if n_power not in (0, 1):
+            raise NotImplementedError("reconvat_b200 VAT: n_power=%r -- the reference itself fails for n_power > 1 "
+                                      "(d.grad is None on the second iteration, model/self_attention_VAT.py:184)"
+                                      % (n_power,))
+
+    # -- deferred NaN / Inf assertion ---------------------------------------------------------
+    def check(self):
+        """Raise the reference's AssertionError if the previous call produced NaN/Inf in r_adv."""
+        if self._pending is None:
+            return
+        host, event = self._pending
+        self._pending = None
+        event.synchronize()
+        if int(host.item()) != 0:
+            raise AssertionError(self._nan_message.format(dmin="nan", dmax="nan", dmean="nan"))
+
+    def _model_outputs(self, model, x):
+        out = model.transcriber(x) if self._use_transcriber else model(x)
+        return [out[i] for i in self._heads]
+
+    def forward(self, model, x):
+        self.check()
+        x = _check_input(x).detach()
+        n_rows, row_len = _rows(x)
+        with torch.no_grad():
+            y_ref = [y.detach() for y in self._model_outputs(model, x)]   # labels, no grad (…:163-164)
+
+        d = torch.randn_like(x)                                           # same global Philox stream (…:172)
+        flag = torch.zeros((), dtype=torch.int32, device=x.device)
+        r_adv = torch.empty_like(x)
+        x_adv2 = torch.empty_like(x)
+        d_hat = torch.empty_like(x)
+        if self.n_power == 1:
+            x_adv = torch.empty_like(x)
+            _lib.call("rvb_vat_perturb", x.data_ptr(), d.data_ptr(), x_adv.data_ptr(), n_rows, row_len,
+                      float(self.XI), int(self._clamp))
+            x_adv.requires_grad_(True)
+            with torch.enable_grad():
+                y_pred = self._model_outputs(model, x_adv)
+                seeds = [_bce_grad(p, y) for p, y in zip(y_pred, y_ref)]  # d(sum of mean BCEs)/dp (…:182)
+                (g,) = torch.autograd.grad(y_pred, [x_adv], seeds)        # model backward only (…:183)
+            model.zero_grad()                                             # side effect kept (…:185)
+            _lib.call("rvb_vat_finalize", g.contiguous().data_ptr(), d.data_ptr(), x.data_ptr(), r_adv.data_ptr(),
+                      x_adv2.data_ptr(), d_hat.data_ptr(), n_rows, row_len, float(self.XI), float(self.epsilon),
+                      float(self._scale), int(self._clamp), flag.data_ptr())
+        else:
+            _lib.call("rvb_vat_direct", d.data_ptr(), x.data_ptr(), r_adv.data_ptr(), x_adv2.data_ptr(),
+                      d_hat.data_ptr(), n_rows, row_len, float(self.epsilon), int(self._clamp), flag.data_ptr())
+
+        host = torch.empty((), dtype=torch.int32, pin_memory=True)
+        host.copy_(flag, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record()
+        self._pending = (host, event)
+        if self.strict:
+            self.check()
+
+        y_pred = self._model_outputs(model, x_adv2)                       # graph to the parameters kept (…:195)
+        losses = [bce_mean(p, y) for p, y in zip(y_pred, y_ref)]          # (…:200)
+        if self._dict_loss is not None:
+            vat_loss = dict(zip(self._dict_loss, losses))
+        else:
+            vat_loss = losses[0]
+        if self._n_returns == 2:
+            return vat_loss, r_adv
+        return vat_loss, r_adv, d_hat
+
+
+class stepwise_VAT_vatpy(_VATCore):
+    """model/VAT.py:9-40 -- ``stepwise_VAT(XI, epsilon, n_power)``; no clamp, returns (vat_loss, r_adv)."""
+    _clamp = False
+    _n_returns = 2
+
+    def __init__(self, XI, epsilon, n_power, strict=None):
+        super().__init__()
+        self._init_common(XI, epsilon, n_power, strict=strict)
+
+
+class stepwise_VAT(_VATCore):
+    """model/self_attention_VAT.py:101-145 -- ``stepwise_VAT(XI, epsilon, n_power, KL_Div, binwise=False)``."""
+
+    def __init__(self, XI, epsilon, n_power, KL_Div, binwise=False, strict=None):
+        super().__init__()
+        self._init_common(XI, epsilon, n_power, KL_Div, binwise, strict)
+
+
+class UNet_VAT(_VATCore):
+    """model/self_attention_VAT.py:147-202 -- ``UNet_VAT(XI, epsilon, n_power, KL_Div, reconstruction=False)``."""
+    _use_transcriber = True
+    _scale = 1e10
+
+    def __init__(self, XI, epsilon, n_power, KL_Div, reconstruction=False, strict=None):
+        super().__init__()
+        self._init_common(XI, epsilon, n_power, KL_Div, False, strict)
+        self.reconstruction = reconstruction
+
+
+class onset_frame_VAT(_VATCore):
+    """model/self_attention_VAT.py:204-238 -- ``onset_frame_VAT(XI, epsilon, n_power)``; the model returns a
+    3-tuple whose first element is the posterior; returns (vat_loss, r_adv)."""
+    _n_returns = 2
+
+    def __init__(self, XI, epsilon, n_power, strict=None):
+        super().__init__()
+        self._init_common(XI, epsilon, n_power, strict=strict)
+
+
+class UNet_VAT_onset(_VATCore):
+    """model/UNet_onset.py:101-162 -- frame and onset posteriors, loss returned as {'frame','onset'}."""
+    _use_transcriber = True
+    _heads = (0, 1)
+    _scale = 1e10
+    _dict_loss = ("frame", "onset")
+
+    def __init__(self, XI, epsilon, n_power, KL_Div, reconstruction=False, strict=None):
+        super().__init__()
+        self._init_common(XI, epsilon, n_power, KL_Div, False, strict)
+        self.reconstruction = reconstruction
+
+
+class stepwise_VAT_onf(_VATCore):
+    """model/onset_frame_VAT.py:158-207 -- ``stepwise_VAT(XI, epsilon, n_power, KL_Div)`` of the Onsets&Frames
+    baseline: x is (B, T, F), the model returns (onset, activation, frame) and only ``frame`` enters the loss;
+    the third return is ``_l2_normalize(d*1e8)`` == ``_l2_normalize(d)`` away from overflow."""
+    _heads = (2,)
+    _scale = 1e10
+    _nan_message = "r_adv contains nan"
+
+    def __init__(self, XI, epsilon, n_power, KL_Div, strict=None):
+        super().__init__()
+        self._init_common(XI, epsilon, n_power, KL_Div, False, strict)

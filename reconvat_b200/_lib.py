@@ -1,0 +1,96 @@
+"""ctypes binding of librvb.so (the C ABI declared in include/rvb.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (or ``make -C
+reconvat_b200/csrc``).  There is NO fallback: if the shared object is missing,
+or a tensor is not a CUDA float32 tensor, the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "librvb.so")
+
+_c_p = ctypes.c_void_p          # device pointers and the stream travel as integers
+_i32, _i64, _f32 = ctypes.c_int, ctypes.c_int64, ctypes.c_float
+
+# name -> argtypes; mirrors include/rvb.h one to one (tests/test_abi.py checks the header against this)
+SIGNATURES = {
+    "rvb_pad_split": [_c_p, _i64, _i32, _i32, _i32, _i32, _c_p, _c_p, _i32, _i32, _c_p],
+    "rvb_stft_gemm": [_c_p, _c_p, _i32, _i32, _i32, _i32, _c_p, _c_p, _i32, _i32, _i32, _f32, _c_p, _i32, _c_p],
+    "rvb_stft_bin": [_c_p, _c_p, _i32, _i32, _i32, _i32, _c_p, _c_p, _i32, _i32, _i32, _f32, _c_p, _i32, _c_p],
+    "rvb_mel_project": [_c_p, _i32, _i32, _i32, _c_p, _c_p, _c_p, _i32, _i32, _i32, _f32, _i32, _c_p, _c_p, _c_p],
+    "rvb_minmax": [_c_p, _i32, _i64, _c_p, _c_p],
+    "rvb_normalise": [_c_p, _c_p, _i32, _i64, _c_p, _c_p],
+    "rvb_vat_perturb": [_c_p, _c_p, _c_p, _i64, _i32, _f32, _i32, _c_p],
+    "rvb_bce_grad": [_c_p, _c_p, _c_p, _i64, _c_p, _f32, _c_p],
+    "rvb_vat_finalize": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i64, _i32, _f32, _f32, _f32, _i32, _c_p, _c_p],
+    "rvb_vat_direct": [_c_p, _c_p, _c_p, _c_p, _c_p, _i64, _i32, _f32, _i32, _c_p, _c_p],
+    "rvb_bce_mean": [_c_p, _c_p, _i64, _c_p, _c_p, _c_p],
+}
+ABI_VERSION = 1
+BCE_WORKSPACE_FLOATS = 1032
+
+PAD_REFLECT, PAD_CONSTANT, PAD_NONE = 0, 1, 2
+EPI_POWER, EPI_MAGNITUDE, EPI_COMPLEX, EPI_PHASE, EPI_POWER_P = 0, 1, 2, 3, 4
+LAYOUT_BINS_MAJOR, LAYOUT_TIME_MAJOR = 0, 1
+
+_lib = None
+
+
+class RvbError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen librvb.so (works without a GPU: the CUDA driver is only touched by the first launch)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "reconvat_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C reconvat_b200/csrc`. There is no CPU / PyTorch fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.rvb_abi_version.restype = ctypes.c_int
+    lib.rvb_last_error.restype = ctypes.c_char_p
+    lib.rvb_launch_count.restype = ctypes.c_int64
+    if lib.rvb_abi_version() != ABI_VERSION:
+        raise ImportError("reconvat_b200: librvb.so has ABI %d, the Python side expects %d -- rebuild"
+                          % (lib.rvb_abi_version(), ABI_VERSION))
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def launch_count():
+    """Kernels launched by librvb.so in this process so far (bench.py reports the delta)."""
+    return int(load().rvb_launch_count())
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t, dtype=torch.float32):
+    """Device pointer of a CUDA tensor; refuses anything the kernels cannot read."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RvbError("reconvat_b200 kernels need CUDA tensors (got %s); there is no CPU path"
+                       % (t.device if isinstance(t, torch.Tensor) else type(t)))
+    if t.dtype != dtype:
+        raise RvbError("expected %s, got %s" % (dtype, t.dtype))
+    return t.data_ptr()
+
+
+def call(name, *args):
+    """Invoke an entry point on the current PyTorch stream; raise RvbError on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args, _stream())
+    if rc != 0:
+        raise RvbError("%s failed (%d): %s" % (name, rc, lib.rvb_last_error().decode("utf-8", "replace")))

@@ -1,0 +1,179 @@
+"""Host-side builders for the tables the kernels consume.
+
+* windowed Fourier basis  == what nnAudio 0.2.0 ``create_fourier_kernels`` + the window multiply at
+  model/Spectrogram.py:133-164 produce (float64 evaluation, float32 storage, float32 window product);
+* Slaney / HTK triangular Mel filterbank == ``nnAudio.librosa_functions.mel`` as called at
+  model/Spectrogram.py:421, and its banded form (every FFT bin feeds at most two adjacent bands);
+* tf32 hi/lo operand planes in the row order the tcgen05 contraction expects.
+
+Pure numpy; the results are registered as module buffers (same names/shapes as the reference, so
+checkpoints interchange) plus non-persistent device tables.
+"""
+import numpy as np
+from scipy.signal import get_window
+
+GEMM_TILE_BINS = 128      # one 256-row operand tile = 128 cos rows + 128 sin rows of the same bins
+
+
+def broadcast_dim(x):
+    """(L) / (B,L) / (B,1,L) -> (B,1,L); ValueError otherwise (nnAudio.utils.broadcast_dim)."""
+    if x.dim() == 2:
+        return x[:, None, :]
+    if x.dim() == 1:
+        return x[None, None, :]
+    if x.dim() == 3:
+        return x
+    raise ValueError("Only support input with shape = (batch, len) or shape = (len)")
+
+
+def fourier_basis(n_fft, win_length=None, freq_bins=None, window="hann", freq_scale="no", fmin=50, fmax=6000,
+                  sr=22050):
+    """Returns (kernel_sin, kernel_cos, bins2freq, binslist, window_mask): float32 un-windowed tables
+    (F, n_fft) and the float32 window centre-padded to n_fft."""
+    if freq_bins is None:
+        freq_bins = n_fft // 2 + 1
+    if win_length is None:
+        win_length = n_fft
+    s = np.arange(0, n_fft, 1.0)
+    k = np.arange(freq_bins, dtype=np.float64)
+    if freq_scale == "no":
+        bins = k
+    elif freq_scale == "linear":
+        start_bin = fmin * n_fft / sr
+        scaling_ind = (fmax - fmin) * (n_fft / sr) / freq_bins
+        bins = k * scaling_ind + start_bin
+    elif freq_scale == "log":
+        start_bin = fmin * n_fft / sr
+        scaling_ind = np.log(fmax / fmin) / freq_bins
+        bins = np.exp(k * scaling_ind) * start_bin
+    else:
+        raise ValueError("Please select the correct frequency scale, 'linear' or 'log'")
+    bins2freq = bins * sr / n_fft
+    arg = (2 * np.pi * bins)[:, None] * s[None, :] / n_fft           # ((2*pi*k)*s)/n_fft in float64
+    kernel_sin = np.sin(arg).astype(np.float32)
+    kernel_cos = np.cos(arg).astype(np.float32)
+    w = get_window(window, int(win_length), fftbins=True)
+    lpad = (n_fft - len(w)) // 2
+    if lpad < 0:
+        raise ValueError("Target size ({:d}) must be at least input size ({:d})".format(n_fft, len(w)))
+    window_mask = np.pad(w, (lpad, n_fft - len(w) - lpad)).astype(np.float32)
+    return kernel_sin, kernel_cos, list(bins2freq), list(bins), window_mask
+
+
+# ---------------------------------------------------------------- Mel
+def _hz_to_mel(f, htk):
+    f = np.asarray(f, dtype=np.float64)
+    if htk:
+        return 2595.0 * np.log10(1.0 + f / 700.0)
+    f_sp = 200.0 / 3
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    lin = f / f_sp
+    logp = min_log_mel + np.log(np.maximum(f, 1e-300) / min_log_hz) / logstep
+    return np.where(f >= min_log_hz, logp, lin)
+
+
+def _mel_to_hz(m, htk):
+    m = np.asarray(m, dtype=np.float64)
+    if htk:
+        return 700.0 * (10.0 ** (m / 2595.0) - 1.0)
+    f_sp = 200.0 / 3
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def mel_filterbank(sr, n_fft, n_mels=128, fmin=0.0, fmax=None, htk=False, norm=1):
+    """float32 (n_mels, 1 + n_fft//2) triangular filters, area-normalised for norm == 1."""
+    if fmax is None:
+        fmax = float(sr) / 2
+    if norm is not None and norm != 1 and norm != np.inf:
+        raise ValueError("Unsupported norm: {}".format(repr(norm)))
+    n_mels = int(n_mels)
+    n_bins = 1 + n_fft // 2
+    fftfreqs = np.linspace(0, float(sr) / 2, n_bins, endpoint=True)
+    edges = _mel_to_hz(np.linspace(_hz_to_mel(fmin, htk), _hz_to_mel(fmax, htk), n_mels + 2), htk)
+    fdiff = np.diff(edges)
+    ramps = edges[:, None] - fftfreqs[None, :]
+    lower = -ramps[:-2] / fdiff[:-1, None]
+    upper = ramps[2:] / fdiff[1:, None]
+    weights = np.maximum(0, np.minimum(lower, upper)).astype(np.float32)
+    if norm == 1:
+        enorm = 2.0 / (edges[2:n_mels + 2] - edges[:n_mels])
+        weights = (weights.astype(np.float64) * enorm[:, None]).astype(np.float32)
+    return weights
+
+
+def banded_filterbank(mel_basis):
+    """Dense (n_mels, F) -> (band0 int32[F], w0 f32[F], w1 f32[F], k_begin, k_end).
+
+    Bin k contributes w0[k] to band band0[k] and w1[k] to band band0[k]+1.  Raises ValueError when
+    the matrix is not a pairwise-overlapping filterbank (a column with non-adjacent or more than two
+    non-zeros, or band indices that decrease with k) -- e.g. a trained dense ``mel_basis``.
+    """
+    mb = np.asarray(mel_basis, dtype=np.float32)
+    n_mels, F = mb.shape
+    band0 = np.zeros(F, np.int32)
+    w0 = np.zeros(F, np.float32)
+    w1 = np.zeros(F, np.float32)
+    nzcols = np.flatnonzero((mb != 0).any(0))
+    if len(nzcols) == 0:
+        raise ValueError("mel_basis is all zero")
+    k_begin, k_end = int(nzcols[0]), int(nzcols[-1]) + 1
+    prev = 0
+    for k in range(k_begin, k_end):
+        rows = np.flatnonzero(mb[:, k])
+        if len(rows) == 0:
+            band0[k] = prev
+        elif len(rows) == 1:
+            r = int(rows[0])
+            # keep band0 non-decreasing: a lone weight may sit in either slot of the (band0, band0+1) pair
+            if r == prev + 1:
+                band0[k], w1[k] = prev, mb[r, k]
+            else:
+                band0[k], w0[k] = r, mb[r, k]
+        elif len(rows) == 2 and rows[1] == rows[0] + 1:
+            band0[k], w0[k], w1[k] = int(rows[0]), mb[rows[0], k], mb[rows[1], k]
+        else:
+            raise ValueError("mel_basis column %d has non-zeros in rows %s: not a banded triangular "
+                             "filterbank; the fused Mel kernel cannot represent it" % (k, rows.tolist()))
+        if band0[k] < prev:
+            raise ValueError("mel_basis band order decreases at bin %d" % k)
+        prev = int(band0[k])
+    return band0, w0, w1, k_begin, k_end
+
+
+# ---------------------------------------------------------------- tf32 operand planes
+def tf32_round(x):
+    """Round-to-nearest (ties away) fp32 -> tf32, identical to PTX cvt.rna.tf32.f32 for finite values."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def tf32_split(x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    hi = tf32_round(x)
+    lo = tf32_round(x - hi)
+    return hi, lo
+
+
+def gemm_operand(wcos, wsin):
+    """(F, n_fft) float32 windowed bases -> (basis_hi, basis_lo, n_gemm_bins, leftover_bins).
+
+    Rows are grouped in 256-row tiles: [128 cos rows | 128 sin rows] of the same 128 bins, so that one
+    accumulator tile holds re and im of the same bins.  When F % 128 == 1 (the usual n_fft/2+1) the
+    last bin is left to the scalar single-bin kernel instead of costing a whole extra tile.
+    """
+    F, n_fft = wcos.shape
+    n_gemm = F - 1 if (F % GEMM_TILE_BINS == 1 and F > 1) else F
+    leftover = list(range(n_gemm, F))
+    n_tiles = (n_gemm + GEMM_TILE_BINS - 1) // GEMM_TILE_BINS
+    mat = np.zeros((n_tiles * 2 * GEMM_TILE_BINS, n_fft), np.float32)
+    for j in range(n_tiles):
+        lo_bin, hi_bin = j * GEMM_TILE_BINS, min((j + 1) * GEMM_TILE_BINS, n_gemm)
+        mat[256 * j:256 * j + (hi_bin - lo_bin)] = wcos[lo_bin:hi_bin]
+        mat[256 * j + 128:256 * j + 128 + (hi_bin - lo_bin)] = wsin[lo_bin:hi_bin]
+    hi, lo = tf32_split(mat)
+    return hi, lo, n_gemm, leftover

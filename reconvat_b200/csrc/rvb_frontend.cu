@@ -1,0 +1,368 @@
+// HBM-bound front-end kernels around the STFT contraction:
+//   K0 pad + hop-blocking + tf32 split     (model/Spectrogram.py:209-218)
+//   K1b single frequency bin in fp32       (Nyquist bin of model/Spectrogram.py:219-220)
+//   K2 banded Mel + log + min/max          (model/Spectrogram.py:460, self_attention_VAT.py:1102, utils.py:96-97)
+//   K3 imagewise normalise                 (model/utils.py:100)
+#include "rvb_common.cuh"
+
+namespace rvb {
+
+extern void count_launch();
+
+// ------------------------------------------------------------------ K0
+// One thread produces 4 consecutive plane samples (float4 stores; float4 loads in the interior).
+__device__ __forceinline__ float padded_sample(const float* __restrict__ a, int64_t i, int n, int pad, int mode) {
+  // i: index into the padded signal of length n + 2*pad (or n when mode == NONE)
+  int64_t j = i - pad;
+  if (mode == RVB_PAD_NONE) j = i;
+  if (j < 0) {
+    if (mode != RVB_PAD_REFLECT) return 0.f;
+    j = -j;                                   // ReflectionPad1d: edge sample not repeated
+  } else if (j >= n) {
+    if (mode != RVB_PAD_REFLECT) return 0.f;
+    j = 2 * (int64_t)(n - 1) - j;
+  }
+  return __ldg(a + j);
+}
+
+__global__ void __launch_bounds__(256)
+pad_split_kernel(const float* __restrict__ audio, int64_t audio_ld, int n_samples, int pad, int mode,
+                 float* __restrict__ sig_hi, float* __restrict__ sig_lo, int64_t plane_per_seg) {
+  const int b = blockIdx.y;
+  const float* a = audio + (int64_t)b * audio_ld;
+  const int64_t padded = (mode == RVB_PAD_NONE) ? n_samples : (int64_t)n_samples + 2 * pad;
+  const int64_t off = (mode == RVB_PAD_NONE) ? 0 : pad;
+  const bool src_vec = ((reinterpret_cast<uintptr_t>(a) & 15u) == 0) && ((off & 3) == 0);
+  for (int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < plane_per_seg;
+       i4 += (int64_t)gridDim.x * blockDim.x * 4) {
+    float v[4];
+    const int64_t j0 = i4 - off;
+    if (src_vec && j0 >= 0 && j0 + 3 < n_samples) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(a + j0));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int64_t i = i4 + e;
+        v[e] = (i < padded) ? padded_sample(a, i, n_samples, pad, mode) : 0.f;
+      }
+    }
+    float4 hi, lo;
+    hi.x = to_tf32(v[0]); lo.x = to_tf32(v[0] - hi.x);
+    hi.y = to_tf32(v[1]); lo.y = to_tf32(v[1] - hi.y);
+    hi.z = to_tf32(v[2]); lo.z = to_tf32(v[2] - hi.z);
+    hi.w = to_tf32(v[3]); lo.w = to_tf32(v[3] - hi.w);
+    const int64_t o = (int64_t)b * plane_per_seg + i4;
+    *reinterpret_cast<float4*>(sig_hi + o) = hi;
+    *reinterpret_cast<float4*>(sig_lo + o) = lo;
+  }
+}
+
+// ------------------------------------------------------------------ K1b
+// One warp per frame: plain fp32 dot products of the frame with one basis row pair.
+__global__ void __launch_bounds__(256)
+stft_bin_kernel(const float* __restrict__ sig_hi, const float* __restrict__ sig_lo, int n_seg, int rows_per_seg,
+                int hop, int n_frames, const float* __restrict__ wcos_row, const float* __restrict__ wsin_row,
+                int n_fft, int bin, int epilogue, float power, float* __restrict__ out0, int n_out_bins) {
+  const int lane = threadIdx.x & 31;
+  const int64_t frame = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (frame >= (int64_t)n_seg * n_frames) return;
+  const int b = (int)(frame / n_frames), t = (int)(frame % n_frames);
+  const int64_t base = ((int64_t)b * rows_per_seg + t) * hop;   // frame t starts at plane sample t*hop
+  float re = 0.f, im = 0.f;
+  for (int n = lane; n < n_fft; n += 32) {
+    float s = __ldg(sig_hi + base + n) + __ldg(sig_lo + base + n);
+    re = fmaf(s, __ldg(wcos_row + n), re);
+    im = fmaf(s, __ldg(wsin_row + n), im);
+  }
+  re = warp_sum(re);
+  im = warp_sum(im);
+  if (lane == 0) stft_store(epilogue, power, re, im, out0, ((int64_t)b * n_out_bins + bin) * n_frames + t);
+}
+
+// ------------------------------------------------------------------ K2
+// Block = 32 consecutive frames of one segment x all bins.  Warp w walks bin chunk w in increasing k;
+// lane <-> frame, so every load is one coalesced 128-byte line of power[b][k][t0..t0+31].
+// Two rotating register accumulators follow the (band0, band0+1) pair of the current bin.  A finished
+// band goes to the smem tile with a plain store, except the first two bands a warp finishes: those may
+// be shared with the previous chunk and are parked in a per-warp edge slot; warp 0 folds the edge
+// slots into the tile in fixed order afterwards (no atomics, bit-reproducible).  The tile is then
+// log-compressed, min/max-reduced and written in either layout with coalesced stores.
+constexpr int kMelWarps = 8;
+constexpr int kMelFrames = 32;
+
+struct MelEmit {
+  float* tile;        // [n_mels][33]
+  float* edge;        // [2][32] of this warp
+  int* edge_band;     // [2] of this warp
+  int n_emit, n_mels, lane, warp;
+  __device__ __forceinline__ void operator()(int band, float v) {
+    if (band >= n_mels) return;
+    if (warp > 0 && n_emit < 2) {
+      edge[n_emit * 32 + lane] = v;
+      if (lane == 0) edge_band[n_emit] = band;
+    } else {
+      tile[band * 33 + lane] = v;
+    }
+    ++n_emit;
+  }
+};
+
+__global__ void __launch_bounds__(kMelWarps* kWarp)
+mel_project_kernel(const float* __restrict__ power, int n_bins, int n_frames, const int32_t* __restrict__ band0,
+                   const float* __restrict__ w0, const float* __restrict__ w1, int k_begin, int k_end, int n_mels,
+                   float log_offset, int layout, float* __restrict__ out, uint32_t* __restrict__ minmax) {
+  extern __shared__ float smem[];
+  float* tile = smem;                                   // [n_mels][33]
+  __shared__ float edge[kMelWarps][2][32];
+  __shared__ int edge_band[kMelWarps][2];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kMelFrames;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < n_mels * 33; i += blockDim.x) tile[i] = 0.f;
+  if (threadIdx.x < kMelWarps * 2) edge_band[threadIdx.x >> 1][threadIdx.x & 1] = -1;
+  __syncthreads();
+
+  const int nk = k_end - k_begin;
+  const int chunk = (nk + kMelWarps - 1) / kMelWarps;
+  const int ks = k_begin + warp * chunk;
+  const int ke = min(ks + chunk, k_end);
+  const int t = t0 + lane;
+  const bool tv = t < n_frames;
+  const float* src = power + ((int64_t)b * n_bins) * n_frames + (tv ? t : 0);
+
+  if (ks < ke) {
+    MelEmit emit{tile, &edge[warp][0][0], &edge_band[warp][0], 0, n_mels, lane, warp};
+    float acc_a = 0.f, acc_b = 0.f;
+    int cur = __ldg(band0 + ks);
+    constexpr int U = 8;
+    for (int k = ks; k < ke; k += U) {
+      float pv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) pv[u] = (tv && k + u < ke) ? __ldg(src + (int64_t)(k + u) * n_frames) : 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k + u < ke) {
+          const int j = __ldg(band0 + k + u);
+          if (j != cur) {                                 // warp-uniform
+            emit(cur, acc_a);
+            if (j == cur + 1) {
+              acc_a = acc_b;
+            } else {
+              emit(cur + 1, acc_b);
+              acc_a = 0.f;
+            }
+            acc_b = 0.f;
+            cur = j;
+          }
+          acc_a = fmaf(__ldg(w0 + k + u), pv[u], acc_a);
+          acc_b = fmaf(__ldg(w1 + k + u), pv[u], acc_b);
+        }
+      }
+    }
+    emit(cur, acc_a);
+    emit(cur + 1, acc_b);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < kMelWarps; ++w)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int band = edge_band[w][e];
+        if (band >= 0) tile[band * 33 + lane] += edge[w][e][lane];
+      }
+  }
+  __syncthreads();
+
+  float vmax = -INFINITY, vmin = INFINITY;
+  bool seen_nan = false;
+  const int nt = min(kMelFrames, n_frames - t0);
+  if (layout == RVB_LAYOUT_TIME_MAJOR) {
+    // out[b][t][m]: consecutive threads -> consecutive m of one frame (contiguous n_mels floats)
+    float* dst = out + ((int64_t)b * n_frames + t0) * n_mels;
+    for (int i = threadIdx.x; i < nt * n_mels; i += blockDim.x) {
+      const int tt = i / n_mels, m = i - tt * n_mels;
+      float v = tile[m * 33 + tt];
+      if (log_offset >= 0.f) v = logf(v + log_offset);
+      dst[i] = v;
+      vmax = fmaxf(vmax, v); vmin = fminf(vmin, v); seen_nan |= isnan(v);
+    }
+  } else {
+    // out[b][m][t]: consecutive threads -> consecutive t of one band
+    for (int i = threadIdx.x; i < n_mels * kMelFrames; i += blockDim.x) {
+      const int m = i >> 5, tt = i & 31;
+      if (tt < nt) {
+        float v = tile[m * 33 + tt];
+        if (log_offset >= 0.f) v = logf(v + log_offset);
+        out[((int64_t)b * n_mels + m) * n_frames + t0 + tt] = v;
+        vmax = fmaxf(vmax, v); vmin = fminf(vmin, v); seen_nan |= isnan(v);
+      }
+    }
+  }
+  if (minmax) {
+    // torch.max / torch.min propagate NaN: encode it as the largest key on both sides.
+    unsigned kmax = seen_nan ? 0xffffffffu : f2key(vmax);
+    unsigned kmin = seen_nan ? 0xffffffffu : f2key(-vmin);
+    kmax = warp_max_u32(kmax);
+    kmin = warp_max_u32(kmin);
+    __shared__ unsigned red[2][kMelWarps];
+    if (lane == 0) { red[0][warp] = kmin; red[1][warp] = kmax; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      unsigned k = 0;
+#pragma unroll
+      for (int w = 0; w < kMelWarps; ++w) k = max(k, red[threadIdx.x][w]);
+      atomicMax(minmax + 2 * b + threadIdx.x, k);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ min/max of an arbitrary tensor
+__global__ void __launch_bounds__(256)
+minmax_kernel(const float* __restrict__ x, int64_t n_per_seg, uint32_t* __restrict__ minmax) {
+  const int b = blockIdx.y;
+  const float* p = x + (int64_t)b * n_per_seg;
+  float vmax = -INFINITY, vmin = INFINITY;
+  bool seen_nan = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_seg; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = __ldg(p + i);
+    vmax = fmaxf(vmax, v); vmin = fminf(vmin, v); seen_nan |= isnan(v);
+  }
+  unsigned kmax = warp_max_u32(seen_nan ? 0xffffffffu : f2key(vmax));
+  unsigned kmin = warp_max_u32(seen_nan ? 0xffffffffu : f2key(-vmin));
+  __shared__ unsigned red[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = kmin; red[1][warp] = kmax; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    unsigned k = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) k = max(k, red[threadIdx.x][w]);
+    atomicMax(minmax + 2 * b + threadIdx.x, k);
+  }
+}
+
+// ------------------------------------------------------------------ K3
+__device__ __forceinline__ void decode_minmax(const uint32_t* __restrict__ minmax, int b, float& mn, float& mx) {
+  const unsigned kmin = __ldg(minmax + 2 * b), kmax = __ldg(minmax + 2 * b + 1);
+  if (kmin == 0xffffffffu || kmax == 0xffffffffu) {
+    mn = mx = __int_as_float(0x7fc00000);
+  } else {
+    mn = -key2f(kmin);
+    mx = key2f(kmax);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+normalise_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n_per_seg,
+                 const uint32_t* __restrict__ minmax, int vec_ok) {
+  const int b = blockIdx.y;
+  float mn, mx;
+  decode_minmax(minmax, b, mn, mx);
+  const float den = mx - mn;                              // (x_max - x_min), utils.py:100
+  const float* p = x + (int64_t)b * n_per_seg;
+  float* q = y + (int64_t)b * n_per_seg;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec_ok) {
+    const int64_t n4 = n_per_seg >> 2;
+    for (int64_t j = i; j < n4; j += stride) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(p) + j);
+      v.x = (v.x - mn) / den; v.y = (v.y - mn) / den; v.z = (v.z - mn) / den; v.w = (v.w - mn) / den;
+      reinterpret_cast<float4*>(q)[j] = v;
+    }
+    for (int64_t j = (n4 << 2) + i; j < n_per_seg; j += stride) q[j] = (__ldg(p + j) - mn) / den;
+  } else {
+    for (int64_t j = i; j < n_per_seg; j += stride) q[j] = (__ldg(p + j) - mn) / den;
+  }
+}
+
+}  // namespace rvb
+
+using namespace rvb;
+
+extern "C" int rvb_pad_split(const float* audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int pad_mode,
+                             float* sig_hi, float* sig_lo, int rows_per_seg, int hop, rvb_stream_t stream) {
+  RVB_REQUIRE(audio && sig_hi && sig_lo, "rvb_pad_split: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_samples > 0 && hop > 0 && rows_per_seg > 0, "rvb_pad_split: bad shape");
+  RVB_REQUIRE(pad_mode >= RVB_PAD_REFLECT && pad_mode <= RVB_PAD_NONE, "rvb_pad_split: bad pad_mode %d", pad_mode);
+  RVB_REQUIRE(hop % 4 == 0, "rvb_pad_split: hop %d must be a multiple of 4", hop);
+  RVB_REQUIRE((reinterpret_cast<uintptr_t>(sig_hi) & 15u) == 0 && (reinterpret_cast<uintptr_t>(sig_lo) & 15u) == 0,
+              "rvb_pad_split: planes must be 16-byte aligned");
+  if (pad_mode == RVB_PAD_REFLECT) {
+    // model/Spectrogram.py:214-215 raises for n < pad; ReflectionPad1d itself needs pad < n.
+    RVB_REQUIRE(n_samples > pad, "rvb_pad_split: reflect padding %d needs more than %d samples", pad, n_samples);
+  }
+  const int64_t padded = (pad_mode == RVB_PAD_NONE) ? n_samples : (int64_t)n_samples + 2 * pad;
+  const int64_t plane = (int64_t)rows_per_seg * hop;
+  RVB_REQUIRE(plane >= padded, "rvb_pad_split: rows_per_seg*hop = %lld < padded length %lld", (long long)plane,
+              (long long)padded);
+  int64_t bx = (plane / 4 + 255) / 256;
+  if (bx > 1024) bx = 1024;
+  dim3 grid((unsigned)bx, (unsigned)n_seg);
+  pad_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(audio, audio_ld, n_samples, pad, pad_mode, sig_hi, sig_lo,
+                                                           plane);
+  count_launch();
+  return check_launch("pad_split_kernel");
+}
+
+extern "C" int rvb_stft_bin(const float* sig_hi, const float* sig_lo, int n_seg, int rows_per_seg, int hop,
+                            int n_frames, const float* wcos_row, const float* wsin_row, int n_fft, int bin,
+                            int epilogue, float power, float* out0, int n_out_bins, rvb_stream_t stream) {
+  RVB_REQUIRE(sig_hi && sig_lo && wcos_row && wsin_row && out0, "rvb_stft_bin: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_frames > 0 && bin >= 0 && bin < n_out_bins, "rvb_stft_bin: bad shape");
+  RVB_REQUIRE(epilogue >= RVB_EPI_POWER && epilogue <= RVB_EPI_POWER_P, "rvb_stft_bin: bad epilogue %d", epilogue);
+  RVB_REQUIRE((int64_t)(n_frames - 1) * hop + n_fft <= (int64_t)rows_per_seg * hop, "rvb_stft_bin: plane too short");
+  const int64_t frames = (int64_t)n_seg * n_frames;
+  stft_bin_kernel<<<(unsigned)((frames + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      sig_hi, sig_lo, n_seg, rows_per_seg, hop, n_frames, wcos_row, wsin_row, n_fft, bin, epilogue, power, out0,
+      n_out_bins);
+  count_launch();
+  return check_launch("stft_bin_kernel");
+}
+
+extern "C" int rvb_mel_project(const float* power, int n_seg, int n_bins, int n_frames, const int32_t* band0,
+                               const float* w0, const float* w1, int k_begin, int k_end, int n_mels,
+                               float log_offset, int layout, float* out, uint32_t* minmax, rvb_stream_t stream) {
+  RVB_REQUIRE(power && band0 && w0 && w1 && out, "rvb_mel_project: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_frames > 0 && n_mels > 0, "rvb_mel_project: bad shape");
+  RVB_REQUIRE(0 <= k_begin && k_begin < k_end && k_end <= n_bins, "rvb_mel_project: bad bin range [%d,%d) of %d",
+              k_begin, k_end, n_bins);
+  RVB_REQUIRE(layout == RVB_LAYOUT_BINS_MAJOR || layout == RVB_LAYOUT_TIME_MAJOR, "rvb_mel_project: bad layout");
+  const size_t smem = (size_t)n_mels * 33 * sizeof(float);
+  RVB_REQUIRE(smem <= 200 * 1024, "rvb_mel_project: n_mels %d too large", n_mels);
+  if (minmax) RVB_CUDA(cudaMemsetAsync(minmax, 0, sizeof(uint32_t) * 2 * n_seg, (cudaStream_t)stream));
+  if (smem > 48 * 1024)
+    RVB_CUDA(cudaFuncSetAttribute(mel_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((n_frames + kMelFrames - 1) / kMelFrames), (unsigned)n_seg);
+  mel_project_kernel<<<grid, kMelWarps * kWarp, smem, (cudaStream_t)stream>>>(
+      power, n_bins, n_frames, band0, w0, w1, k_begin, k_end, n_mels, log_offset, layout, out, minmax);
+  count_launch();
+  return check_launch("mel_project_kernel");
+}
+
+extern "C" int rvb_minmax(const float* x, int n_seg, int64_t n_per_seg, uint32_t* minmax, rvb_stream_t stream) {
+  RVB_REQUIRE(x && minmax, "rvb_minmax: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_per_seg > 0, "rvb_minmax: bad shape");
+  RVB_CUDA(cudaMemsetAsync(minmax, 0, sizeof(uint32_t) * 2 * n_seg, (cudaStream_t)stream));
+  int64_t bx = (n_per_seg + 256 * 8 - 1) / (256 * 8);
+  if (bx > 296) bx = 296;
+  dim3 grid((unsigned)bx, (unsigned)n_seg);
+  minmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n_per_seg, minmax);
+  count_launch();
+  return check_launch("minmax_kernel");
+}
+
+extern "C" int rvb_normalise(const float* x, float* y, int n_seg, int64_t n_per_seg, const uint32_t* minmax,
+                             rvb_stream_t stream) {
+  RVB_REQUIRE(x && y && minmax, "rvb_normalise: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_per_seg > 0, "rvb_normalise: bad shape");
+  const int vec = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0) &&
+                  (n_per_seg % 4 == 0);
+  int64_t bx = (n_per_seg + 256 * 8 - 1) / (256 * 8);
+  if (bx > 296) bx = 296;
+  dim3 grid((unsigned)bx, (unsigned)n_seg);
+  normalise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, n_per_seg, minmax, vec);
+  count_launch();
+  return check_launch("normalise_kernel");
+}

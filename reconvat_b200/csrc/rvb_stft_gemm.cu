@@ -1,0 +1,418 @@
+// K1: the STFT as one dense contraction on 5th-generation tensor cores (sm_100a).
+//
+//   D[frame, col] = sum_n  p[hop*frame + n] * basis[col, n]          (model/Spectrogram.py:219-220)
+//
+// * M = frames (B*T), N = basis rows (cos|sin interleaved per 128-bin tile), K = n_fft.
+// * 3xTF32: operands are pre-split into tf32 hi/lo planes; each K-step issues hi*hi + hi*lo + lo*hi
+//   with fp32 accumulation in TMEM (error ~2^-21 per product, inside the 1e-4 log-Mel budget; a
+//   single TF32 pass is 2.3e-3 off on white noise and 1.7e-2 on tonal input -- see DESIGN.md).
+// * A is never materialised as frames: hop | n_fft-block arithmetic makes K-slice [kk, kk+32) of frame
+//   t the 32 floats at column kk%hop of row t + kk/hop of the hop-blocked signal plane, so a
+//   128-frame x 32-sample operand tile is ONE 2-D TMA box over non-overlapping rows.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+//   warps 2..5 = epilogue (TMEM -> registers -> re^2+im^2 etc. -> coalesced global stores).
+//   smem ring (full/empty mbarriers) between producer and MMA; two 256-column TMEM accumulators
+//   (tmem_full/tmem_empty mbarriers) so the epilogue of unit i overlaps the MMAs of unit i+1.
+// * Persistent: grid = min(#units, #SMs); unit = (128-frame tile, 256-column tile), n fastest.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "rvb_common.cuh"
+
+namespace rvb {
+
+extern void count_launch();
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 32;                       // fp32 elements = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;                         // tf32
+constexpr int STAGES = 2;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
+constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 4;   // 32 KB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // hi+lo of both operands: 96 KB
+constexpr int BAR_BYTES = 128;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + slack for 1024-byte alignment
+constexpr int ACC_COLS = BLOCK_N;                 // fp32 accumulator columns per stage
+constexpr int TMEM_COLS = 512;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+
+struct GemmParams {
+  int n_seg, rows_per_seg, hop, n_frames, n_fft;
+  int tiles_per_seg, m_tiles, n_tiles;
+  int epilogue, n_out_bins, n_store_bins;
+  float power;
+  float* out0;
+  int* dbg_status;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must become a trap, never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* dbg_status, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((it & 0x3ff) == 0x3ff) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) {     // 4 s
+        if (dbg_status) atomicExch(dbg_status, code);
+        __threadfence_system();
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t smem_dst, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (tile base 1024-byte aligned):
+//   bits [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 = 1024>>4
+//   | [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  const uint32_t lo = ((smem_addr >> 4) & 0x3fffu) | (1u << 16);
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+// kind::tf32 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), both K-major,
+// N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+stft_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto s_a_hi = [&](int s) { return smem_base + s * STAGE_BYTES; };
+  auto s_a_lo = [&](int s) { return smem_base + s * STAGE_BYTES + A_TILE_BYTES; };
+  auto s_b_hi = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * A_TILE_BYTES; };
+  auto s_b_lo = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * A_TILE_BYTES + B_TILE_BYTES; };
+  auto bar_full = [&](int s) { return bar_base + 8 * s; };
+  auto bar_empty = [&](int s) { return bar_base + 8 * (STAGES + s); };
+  auto bar_tmem_full = [&](int a) { return bar_base + 8 * (2 * STAGES + a); };
+  auto bar_tmem_empty = [&](int a) { return bar_base + 8 * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8 * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;   // warp-uniform
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b_hi);
+    tma_prefetch_desc(&tm_b_lo);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tmem_full(a), 1);
+      mbar_init(bar_tmem_empty(a), 4);          // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  const int n_units = p.m_tiles * p.n_tiles;
+  const int num_kb = p.n_fft / BLOCK_K;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
+        const int b = m_tile / p.tiles_per_seg;
+        const int t0 = (m_tile - b * p.tiles_per_seg) * BLOCK_M;
+        const int row0 = b * p.rows_per_seg + t0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty(stage), phase ^ 1u, p.dbg_status, 1);
+          mbar_expect_tx(bar_full(stage), STAGE_BYTES);
+          const int kk = kb * BLOCK_K;
+          const int col = kk % p.hop, row = row0 + kk / p.hop;
+          tma_load_2d(&tm_a_hi, s_a_hi(stage), bar_full(stage), col, row);
+          tma_load_2d(&tm_a_lo, s_a_lo(stage), bar_full(stage), col, row);
+          tma_load_2d(&tm_b_hi, s_b_hi(stage), bar_full(stage), kk, n_tile * BLOCK_N);
+          tma_load_2d(&tm_b_lo, s_b_lo(stage), bar_full(stage), kk, n_tile * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        mbar_wait(bar_tmem_empty(acc), acc_phase ^ 1u, p.dbg_status, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full(stage), phase, p.dbg_status, 3);
+          tc_fence_after();
+          const uint64_t da_hi = make_sw128_desc(s_a_hi(stage));
+          const uint64_t da_lo = make_sw128_desc(s_a_lo(stage));
+          const uint64_t db_hi = make_sw128_desc(s_b_hi(stage));
+          const uint64_t db_lo = make_sw128_desc(s_b_lo(stage));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)(k * UMMA_K * 4 >> 4);      // +32 bytes inside the swizzle row
+            umma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, (kb | k) != 0);
+            umma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+            umma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+          }
+          umma_commit(bar_empty(stage));            // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(bar_tmem_full(acc));            // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
+      const int b = m_tile / p.tiles_per_seg;
+      const int t = (m_tile - b * p.tiles_per_seg) * BLOCK_M + row;
+      const bool t_ok = t < p.n_frames;
+      mbar_wait(bar_tmem_full(acc), acc_phase, p.dbg_status, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t re[32], im[32];
+        tmem_ld32(taddr + c * 32, re);
+        tmem_ld32(taddr + 128 + c * 32, im);
+        tmem_ld_wait();
+        const int k0 = n_tile * 128 + c * 32;
+        if (t_ok) {
+          const int64_t base = ((int64_t)b * p.n_out_bins + k0) * p.n_frames + t;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (k0 + i < p.n_store_bins)
+              stft_store(p.epilogue, p.power, __uint_as_float(re[i]), __uint_as_float(im[i]), p.out0,
+                         base + (int64_t)i * p.n_frames);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tmem_empty(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+// 2-D fp32 row-major tensor [rows][cols] -> tiled map with a (box_cols x box_rows) box, 128-byte swizzle.
+static int make_map_2d(CUtensorMap* out, const float* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
+                       uint32_t box_rows) {
+  using Key = std::tuple<const void*, uint64_t, uint64_t, uint32_t, uint32_t>;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  const Key key{base, cols, rows, box_cols, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return RVB_OK;
+    }
+  }
+  auto encode = get_encode_fn();
+  if (!encode) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return RVB_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (cols=%llu rows=%llu box=%ux%u)", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, box_cols, box_rows);
+    return RVB_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 256) cache.clear();
+  cache[key] = *out;
+  return RVB_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace rvb
+
+using namespace rvb;
+
+extern "C" int rvb_stft_gemm(const float* sig_hi, const float* sig_lo, int n_seg, int rows_per_seg, int hop,
+                             int n_frames, const float* basis_hi, const float* basis_lo, int n_basis_rows, int n_fft,
+                             int epilogue, float power, float* out0, int n_out_bins, rvb_stream_t stream) {
+  RVB_REQUIRE(sig_hi && sig_lo && basis_hi && basis_lo && out0, "rvb_stft_gemm: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_frames > 0 && rows_per_seg > 0, "rvb_stft_gemm: bad shape");
+  RVB_REQUIRE(n_fft % BLOCK_K == 0 && n_fft >= BLOCK_K, "rvb_stft_gemm: n_fft %d must be a multiple of %d", n_fft,
+              BLOCK_K);
+  RVB_REQUIRE(hop % BLOCK_K == 0 && hop >= BLOCK_K, "rvb_stft_gemm: hop %d must be a multiple of %d", hop, BLOCK_K);
+  RVB_REQUIRE(n_basis_rows % BLOCK_N == 0 && n_basis_rows > 0, "rvb_stft_gemm: n_basis_rows %d must be a multiple of %d",
+              n_basis_rows, BLOCK_N);
+  RVB_REQUIRE(epilogue >= RVB_EPI_POWER && epilogue <= RVB_EPI_POWER_P, "rvb_stft_gemm: bad epilogue %d", epilogue);
+  RVB_REQUIRE((int64_t)(n_frames - 1) * hop + n_fft <= (int64_t)rows_per_seg * hop,
+              "rvb_stft_gemm: %d frames of %d samples do not fit %d rows of %d", n_frames, n_fft, rows_per_seg, hop);
+  for (const void* ptr : {(const void*)sig_hi, (const void*)sig_lo, (const void*)basis_hi, (const void*)basis_lo})
+    RVB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 127u) == 0, "rvb_stft_gemm: operands must be 128-byte aligned");
+  RVB_REQUIRE(n_out_bins > 0, "rvb_stft_gemm: n_out_bins must be positive");
+
+  CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+  const uint64_t a_rows = (uint64_t)n_seg * rows_per_seg;
+  int rc;
+  if ((rc = make_map_2d(&tm_a_hi, sig_hi, hop, a_rows, BLOCK_K, BLOCK_M)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_a_lo, sig_lo, hop, a_rows, BLOCK_K, BLOCK_M)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_b_hi, basis_hi, n_fft, n_basis_rows, BLOCK_K, BLOCK_N)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_b_lo, basis_lo, n_fft, n_basis_rows, BLOCK_K, BLOCK_N)) != RVB_OK) return rc;
+
+  GemmParams p;
+  p.n_seg = n_seg; p.rows_per_seg = rows_per_seg; p.hop = hop; p.n_frames = n_frames; p.n_fft = n_fft;
+  p.tiles_per_seg = (n_frames + BLOCK_M - 1) / BLOCK_M;
+  p.m_tiles = p.tiles_per_seg * n_seg;
+  p.n_tiles = n_basis_rows / BLOCK_N;
+  p.epilogue = epilogue; p.n_out_bins = n_out_bins;
+  p.n_store_bins = n_out_bins < n_basis_rows / 2 ? n_out_bins : n_basis_rows / 2;
+  p.power = power; p.out0 = out0; p.dbg_status = nullptr;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    RVB_CUDA(cudaFuncSetAttribute(stft_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
+  const int grid = (int)(n_units < num_sms() ? n_units : num_sms());
+  stft_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p);
+  count_launch();
+  return check_launch("stft_gemm_kernel");
+}

@@ -1,0 +1,207 @@
+"""GPU parity of the Mel front-end (through the C ABI / module surface) against the reference-generated
+golden vectors and the CPU oracle.  Tolerance (BASELINE.json, made precise in SURVEY.md 8d):
+log-Mel  max |delta| / max(|ref|, 1) <= 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+LOGMEL_TOL = 1e-4
+MEL_KW = dict(sr=16000, win_length=2048, n_mels=229, hop_length=512, fmin=30, fmax=8000,
+              trainable_mel=False, trainable_STFT=False, verbose=False)
+
+
+def relerr(a, b):
+    return float((np.abs(a - b) / np.maximum(np.abs(b), 1)).max())
+
+
+@pytest.fixture(scope="module")
+def R():
+    import reconvat_b200
+    return reconvat_b200
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def mel(R, dev):
+    return R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+
+
+def test_pad_split_bit_exact(R, dev):
+    from reconvat_b200 import basis, synth
+    a = torch.from_numpy(synth.to_float(np.stack([synth.white_int16(16385, 1), synth.music_int16(16385, 2)])))
+    for mode, pad in ((0, 1024), (1, 1024), (2, 0)):
+        x = a[:, :-1]
+        L = x.shape[1]
+        padded = L + 2 * pad
+        rows = -(-padded // 512)
+        sig = torch.full((2, 2 * rows, 512), float("nan"), device=dev)
+        xd = a.to(dev)[:, :-1]                               # non-contiguous view, row stride L+1
+        R._lib.call("rvb_pad_split", xd.data_ptr(), xd.stride(0), 2, L, pad, mode, sig[0].data_ptr(),
+                    sig[1].data_ptr(), rows, 512)
+        p = x.numpy() if mode == 2 else np.pad(x.numpy(), [(0, 0), (pad, pad)], mode="reflect" if mode == 0 else "constant")
+        pp = np.zeros((2, rows * 512), np.float32)
+        pp[:, :p.shape[1]] = p
+        hi, lo = basis.tf32_split(pp)
+        assert np.array_equal(sig[0].cpu().numpy().reshape(2, -1), hi)
+        assert np.array_equal(sig[1].cpu().numpy().reshape(2, -1), lo)
+
+
+def test_frontend_short_golden(mel, dev, golden):
+    from reconvat_b200 import synth
+    g = golden["frontend_short"]
+    a = torch.from_numpy(synth.to_float(g["audio_int16"])).to(dev)
+    mp = mel(a[:, :-1])                                        # the module surface: (B, n_mels, T) Mel power
+    assert mp.shape == (5, 229, 33) and mp.dtype == torch.float32
+    lm = torch.log(mp + 1e-5).cpu().numpy()                    # the caller's log (self_attention_VAT.py:1102)
+    assert relerr(lm, g["log_mel"]) < LOGMEL_TOL
+    spec = mel.normalised_log_mel(a).cpu().numpy()             # fused extension
+    ok = ~np.isnan(g["spec"])
+    assert np.array_equal(np.isnan(spec), ~ok)                 # all-zero audio -> NaN image, like the reference
+    assert np.abs(spec[ok] - g["spec"][ok]).max() < LOGMEL_TOL
+    assert spec.shape == (5, 1, 33, 229)
+
+
+def test_frontend_full_segment_golden(mel, dev, golden):
+    from reconvat_b200 import synth
+    g = golden["frontend_full"]
+    a16 = np.stack([synth.white_int16(synth.SEGMENT_SAMPLES, int(g["seeds"][0])),
+                    synth.music_int16(synth.SEGMENT_SAMPLES, int(g["seeds"][1]))])
+    a = torch.from_numpy(synth.to_float(a16)).to(dev)
+    lm = torch.log(mel(a[:, :-1]) + 1e-5).cpu().numpy()
+    assert lm.shape == (2, 229, 640)
+    assert relerr(lm, g["log_mel"]) < LOGMEL_TOL
+    spec, mm = mel.normalised_log_mel(a, return_minmax=True)
+    spec = spec.cpu().numpy()
+    assert spec.shape == (2, 1, 640, 229)
+    assert np.abs(spec.reshape(2, -1)[:, ::7] - g["spec_stride7"]).max() < LOGMEL_TOL
+    assert spec.min() == 0.0 and spec.max() == 1.0             # exact 0 and 1 present (utils.py:100)
+    onf = mel.normalised_log_mel(a, channel_dim=False)         # O&F convention (B, T, F)
+    assert onf.shape == (2, 640, 229) and torch.equal(onf, torch.from_numpy(spec[:, 0]).to(dev))
+
+
+def test_frontend_min_length_and_errors(mel, dev, golden):
+    from reconvat_b200 import synth
+    g = golden["frontend_minlen"]
+    a = torch.from_numpy(synth.to_float(g["audio_int16"])).to(dev)
+    mp = mel(a[:, :-1]).cpu().numpy()
+    assert mp.shape == (1, 229, 3)
+    assert relerr(np.log(mp + 1e-5), np.log(g["mel_power"] + 1e-5)) < LOGMEL_TOL
+    with pytest.raises(AssertionError, match="shorter than reflect padding"):
+        mel(torch.zeros(1, 1000, device=dev))                  # Spectrogram.py:214-215
+    with pytest.raises(ValueError):
+        mel(torch.zeros(1, 1, 1, 4000, device=dev))            # broadcast_dim
+    import reconvat_b200
+    with pytest.raises(reconvat_b200._lib.RvbError):
+        mel(torch.zeros(1, 4000))                              # CPU tensor: no fallback
+    assert mel(torch.rand(5000, device=dev)).shape == (1, 229, 10)        # (L) input
+    assert mel(torch.rand(2, 1, 5000, device=dev)).shape == (2, 229, 10)  # (B,1,L) input
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("default", dict(n_fft=2048, hop_length=512, sr=16000)),
+    ("small", dict(n_fft=512, hop_length=128, sr=16000)),
+    ("hop_default", dict(n_fft=1024, sr=22050)),
+    ("nocenter", dict(n_fft=512, hop_length=256, center=False)),
+    ("constpad", dict(n_fft=512, hop_length=128, pad_mode="constant")),
+    ("win_short", dict(n_fft=512, win_length=400, hop_length=160)),
+    ("hamming", dict(n_fft=512, hop_length=128, window="hamming")),
+])
+def test_stft_formats_golden(R, dev, golden, tag, kw):
+    from reconvat_b200 import synth
+    g = golden["stft_formats"]
+    a = torch.from_numpy(synth.to_float(g["audio_int16"])).to(dev)
+    st = R.Spectrogram.STFT(verbose=False, **kw).to(dev)
+    c = st(a, output_format="Complex").cpu().numpy()
+    ref = g[tag + "_complex"]
+    assert c.shape == ref.shape
+    scale = np.abs(ref).max()
+    assert np.abs(c - ref).max() < 2e-5 * scale
+    m = st(a, output_format="Magnitude").cpu().numpy()
+    assert np.abs(m - g[tag + "_magnitude"]).max() < 2e-5 * scale
+    ph = st(a, output_format="Phase").cpu().numpy()
+    # phase is ill-conditioned where the magnitude is tiny: compare on well-defined bins, modulo 2*pi
+    strong = g[tag + "_magnitude"] > 1e-2 * scale
+    dphi = np.angle(np.exp(1j * (ph - g[tag + "_phase"])))
+    assert np.abs(dphi[strong]).max() < 1e-3
+    assert st(a).shape == ref.shape                            # default output_format="Complex"
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("librosa_default", dict(verbose=False)),
+    ("htk_128", dict(sr=16000, n_fft=1024, n_mels=128, hop_length=256, htk=True, verbose=False)),
+    ("power1", dict(sr=16000, n_fft=512, n_mels=40, hop_length=128, power=1.0, fmin=20, fmax=7000, verbose=False)),
+])
+def test_mel_variants_golden(R, dev, golden, tag, kw):
+    from reconvat_b200 import synth
+    g = golden["mel_variants"]
+    a = torch.from_numpy(synth.to_float(g["audio_int16"])).to(dev)
+    out = R.Spectrogram.MelSpectrogram(**kw).to(dev)(a).cpu().numpy()
+    assert out.shape == g[tag].shape
+    assert relerr(np.log(out + 1e-5), np.log(g[tag] + 1e-5)) < LOGMEL_TOL
+
+
+def test_normalization_golden_bit_exact(R, dev, golden):
+    g = golden["normalization"]
+    out = R.utils.Normalization("imagewise").transform(torch.from_numpy(g["x"]).to(dev)).cpu().numpy()
+    ok = ~np.isnan(g["imagewise"])
+    assert np.array_equal(np.isnan(out), ~ok)                  # constant image -> NaN (no epsilon)
+    assert np.array_equal(out[ok], g["imagewise"][ok])
+
+
+@pytest.mark.parametrize("B", [1, 3, 8])
+def test_frontend_batch_vs_oracle(mel, dev, B):
+    """BASELINE config-2 shape (B=8 x 327 680 samples) against the oracle run on the same inputs."""
+    from oracle.frontend import FrontEndOracle
+    from reconvat_b200 import synth
+    a = synth.segments(B, "mixed", seed=40 + B)
+    fo = FrontEndOracle()
+    spec = mel.normalised_log_mel(torch.from_numpy(a).to(dev)).cpu().numpy()
+    ref = fo.spec_for_model(a)
+    assert spec.shape == ref.shape == (B, 1, 640, 229)
+    assert np.abs(spec - ref).max() < LOGMEL_TOL
+    lm = torch.log(mel(torch.from_numpy(a).to(dev)[:, :-1]) + 1e-5).cpu().numpy()
+    lm64 = fo.log_mel(a[:, :-1].astype(np.float64), np.float64)
+    assert relerr(lm, lm64) < LOGMEL_TOL                       # and against the float64 truth
+
+
+def test_size_independent_properties_full_batch(mel, dev):
+    """Properties that pin the B=32 headline shape without a CPU reference of that size:
+    batch invariance (segment b alone == segment b inside the batch, bit for bit), hop-shift
+    equivariance of interior frames, and homogeneity of the power spectrogram."""
+    from reconvat_b200 import synth
+    a = torch.from_numpy(synth.segments(4, "mixed", seed=70)).to(dev)
+    big = a.repeat(8, 1)                                       # B = 32
+    mp = mel(big[:, :-1])
+    assert mp.shape == (32, 229, 640)
+    for b in (0, 5, 31):
+        assert torch.equal(mp[b], mel(big[b:b + 1, :-1])[0])
+    assert torch.equal(mp[:4], mp[28:])
+    shifted = torch.roll(a, -512, dims=1)
+    ms = mel(shifted[:, :-1])
+    mo = mel(a[:, :-1])
+    # frame t of the shifted signal == frame t+1 of the original, away from the reflected edges
+    assert torch.allclose(ms[:, :, 4:600], mo[:, :, 5:601], rtol=1e-4, atol=1e-6)
+    half = mel(0.5 * a[:, :-1])
+    assert torch.allclose(half, 0.25 * mo, rtol=2e-4, atol=1e-9)
+    spec = mel.normalised_log_mel(big)
+    assert float(spec.min()) == 0.0 and float(spec.max()) == 1.0
+    assert torch.equal(spec[:4], spec[28:])
+
+
+def test_state_dict_interchange(R, dev):
+    """Buffer names/shapes are part of the checkpoint format (transcribe_files.py:71 loads strictly)."""
+    m = R.Spectrogram.MelSpectrogram(**MEL_KW)
+    sd = m.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        "mel_basis": (229, 1025), "stft.wsin": (1025, 1, 2048), "stft.wcos": (1025, 1, 2048),
+        "stft.window_mask": (1, 2048, 1)}
+    m2 = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    m2.load_state_dict(sd, strict=True)
+    x = torch.rand(1, 8192, device=dev)
+    assert torch.equal(m2(x), m.to(dev)(x))
