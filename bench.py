@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the ReconVAT hot path (Mel front-end + VAT step) -- see DESIGN.md "Measurement".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+A step = the hot path over one batch of B synthetic 20.48 s segments per GPU: Mel front-end
+(pad/split, tcgen05 STFT, banded Mel, log, imagewise normalise) + one UNet_VAT call against a stand-in
+transcriber (the real U-Net is the black-box caller, out of scope).  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEG_SECONDS = 20.48
+SEG_SAMPLES = 327680
+T_FRAMES, N_MELS, N_PITCH = 640, 229, 88
+STFT_FLOP_PER_SEG = 2 * 640 * 2050 * 2048                 # dense fp32-equivalent contraction
+N4, P4 = T_FRAMES * N_MELS * 4, T_FRAMES * N_PITCH * 4
+# algorithmic HBM bytes per segment of each HBM-bound kernel (DESIGN.md "Kernels")
+HBM_BYTES_PER_SEG = {
+    "rvb_pad_split": 1310716 + 2 * 1318912,
+    "rvb_mel_project": 1020 * 640 * 4 + N4,
+    "rvb_normalise": 2 * N4,
+    "rvb_vat_perturb": 3 * N4,
+    "rvb_bce_grad": 3 * P4,
+    "rvb_vat_finalize": 6 * N4,
+    "rvb_bce_mean": 2 * P4,
+}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained"),
+                    source="measured")
+    except Exception:
+        return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")   # B200_PROFILING.md
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_audio(n_batches, batch, seed):
+    """n_batches x (batch, SEG_SAMPLES) float32: white and music-like int16-quantised segments.  A few unique
+    segments are generated and circularly shifted to fill the batches (generation is CPU-expensive)."""
+    import numpy as np
+    from reconvat_b200 import synth
+    uniq = [synth.to_float(synth.white_int16(SEG_SAMPLES, seed + 1)), synth.to_float(synth.music_int16(SEG_SAMPLES, seed + 2)),
+            synth.to_float(synth.music_int16(SEG_SAMPLES, seed + 3)), synth.to_float(synth.white_int16(SEG_SAMPLES, seed + 4))]
+    out = []
+    for n in range(n_batches):
+        a = np.empty((batch, SEG_SAMPLES), np.float32)
+        for b in range(batch):
+            a[b] = np.roll(uniq[(n + b) % 4], 4099 * (n * batch + b))
+        out.append(a)
+    return out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port) on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    import torch
+    from oracle.cpu_path import CpuHotPath
+    from reconvat_b200.standin import StandInTranscriber
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = min(args.batch, args.cpu_batch)
+    audio = torch.from_numpy(make_audio(1, sample, 0)[0])
+    model = StandInTranscriber("unet", n_out=N_PITCH, seed=1)
+    path = CpuHotPath()
+    torch.manual_seed(0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        path.step(model, audio)
+    steps = max(1, min(args.steps, args.cpu_steps))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss, rn = path.step(model, audio)
+        loss.item()
+    dt = (time.perf_counter() - t0) / steps
+    value = sample * SEG_SECONDS / dt
+    line = {
+        "impl": "reference", "metric": "audio-sec/s", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Mel+VAT step (front-end + UNet_VAT on a stand-in transcriber), CPU, %d x 20.48 s "
+                               "segments per step (bounded sample of the B=%d workload)" % (sample, args.batch)},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                         "sample": "%d segments x %d steps, oracle/cpu_path.py (the reference's ATen op sequence; the "
+                                   "reference is Python and /root/reference does not travel)" % (sample, steps)},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import reconvat_b200 as R
+    from reconvat_b200.pipeline import HotPathStep
+    from reconvat_b200.standin import StandInTranscriber
+
+    B = args.batch
+    n_rot = max(4, -(-130 * 2 ** 20 // (B * SEG_SAMPLES * 4)))      # rotate inputs over > L2 (126 MB)
+    host = [torch.from_numpy(a).pin_memory() for a in make_audio(n_rot, B, 100 * rank)]
+    dev_audio = [h.to(dev) for h in host]
+    model = StandInTranscriber("unet", n_out=N_PITCH, seed=1).to(dev)
+    step = HotPathStep(model, dev)
+    torch.manual_seed(1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput ("value") ----------------
+    for i in range(args.warmup):
+        step(dev_audio[i % n_rot])
+    step.vat_loss.check()
+    sampler = ClockSampler(local_rank)
+    kernel_names = ["rvb_stft_gemm"] + list(HBM_BYTES_PER_SEG)
+    barrier()
+    sampler.start()
+    log = R._lib.record_events(kernel_names)
+    launches0 = R._lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        vat_loss, r_norm, _, _ = step(dev_audio[i % n_rot])
+    ev1.record()
+    barrier()
+    launches = R._lib.launch_count() - launches0
+    R._lib.record_events(None)
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.summary()
+    step.vat_loss.check()
+    ms_step = ms_total / args.steps
+    value = world * B * SEG_SECONDS / (ms_step * 1e-3)
+
+    # per-kernel durations from the events recorded inside the timed region
+    kms = {n: [s.elapsed_time(e) for s, e in v] for n, v in log.items() if v}
+    kavg = {n: sum(v) / len(v) for n, v in kms.items()}
+
+    # ---------------- end to end from pinned host memory ("e2e") ----------------
+    results = torch.zeros((args.steps, 2), dtype=torch.float32).pin_memory()
+    step.run_host([host[i % n_rot] for i in range(min(args.warmup, 3))], results)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    n_done = step.run_host((host[i % n_rot] for i in range(args.steps)), results)
+    ev1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1)) / n_done
+    e2e_value = world * B * SEG_SECONDS / (e2e_ms * 1e-3)
+    assert torch.isfinite(results).all(), "non-finite VAT loss in the e2e run"
+
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    gemm_ms = kavg.get("rvb_stft_gemm")
+    roofline = None
+    if gemm_ms:
+        achieved = B * STFT_FLOP_PER_SEG / (gemm_ms * 1e-3) / 1e12
+        roofline = {"kernel": "stft_gemm_kernel (rvb_stft_gemm)", "bound": "tensor", "achieved": achieved,
+                    "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"], "traffic": None,
+                    "peak_source": "%s dense bf16 burst (MEASURED_PEAKS.json); the kernel runs kind::tf32 (half the "
+                                   "bf16 rate) and issues 3 MMAs per product (3xTF32), so frac <= 1/6 at a saturated "
+                                   "tensor pipe" % peaks["source"],
+                    "issued_tflops": 3 * B * 2 * 640 * 2048 * 2048 / (gemm_ms * 1e-3) / 1e12,
+                    "ms_per_launch": gemm_ms, "share_of_step": gemm_ms / ms_step}
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                roofline["traffic"] = json.load(f).get("stft_gemm_kernel")
+        except Exception:
+            pass
+    hbm = {}
+    for n, per_seg in HBM_BYTES_PER_SEG.items():
+        if n in kavg:
+            calls_per_step = len(kms[n]) / args.steps
+            gbs = B * per_seg / (kavg[n] * 1e-3) / 1e9
+            hbm[n] = {"ms_per_launch": kavg[n], "launches_per_step": calls_per_step, "achieved_gbs": gbs,
+                      "frac_of_measured_hbm": gbs / peaks["hbm"]}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle.cpu_path import CpuHotPath
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cb = min(B, args.cpu_batch)
+        audio = host[0][:cb].clone()
+        cm = StandInTranscriber("unet", n_out=N_PITCH, seed=1)
+        path = CpuHotPath()
+        path.step(cm, audio)
+        t0 = time.perf_counter()
+        for _ in range(args.cpu_steps):
+            float(path.step(cm, audio)[0])
+        dt = (time.perf_counter() - t0) / args.cpu_steps
+        cpu = {"value": cb * SEG_SECONDS / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+               "sample": "%d segments x %d steps of the same step on the host CPU (oracle/cpu_path.py: the reference's "
+                         "ATen op sequence)" % (cb, args.cpu_steps)}
+
+    line = {
+        "metric": "audio-sec/s", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (STFT: 3xTF32 split operands, f32 accumulate in TMEM)", "data": "synthetic",
+        "config": {"workload": "Mel+VAT step, B=%d x 20.48 s segments per GPU (BASELINE metric shape): Mel front-end + "
+                               "UNet_VAT(XI=1e-6, eps=2) against a stand-in transcriber" % B,
+                   "batch_per_gpu": B, "segment_samples": SEG_SAMPLES, "parallelism": "segments sharded, dp%d, no "
+                   "collective on the path" % world,
+                   "cache": "inputs rotated over %d batches = %.0f MB > 126 MB L2" % (n_rot, n_rot * B * SEG_SAMPLES * 4 / 1e6)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": B * SEG_SAMPLES * 4,
+                "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / n_done,
+                "api": "reconvat_b200.pipeline.HotPathStep.run_host (pinned host audio in, (vat_loss, r_norm) out; "
+                       "copy of batch i+1 overlapped with the kernels of batch i)"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "hbm_kernels": hbm,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=32, help="segments per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-batch", type=int, default=8, help="segments per CPU-baseline step")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1:
+        # convenience: relaunch under torchrun so that `python bench.py --gpus N` works on its own
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511")] + sys.argv
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -122,6 +122,14 @@ def main():
         "onf": (ref.onset_frame_VAT.stepwise_VAT, dict(XI=1e-6, epsilon=0.1, n_power=1, KL_Div=False), "onf", 3),
         "unet_kl": (ref.self_attention_VAT.UNet_VAT, dict(XI=1e-6, epsilon=2, n_power=1, KL_Div=True), "unet", 4),
     }
+    # With the shipped XI=1e-6 the perturbed and clean posteriors differ at fp32 rounding level, so g
+    # (and hence r_adv) is only reproducible on the same device with the same kernels: those cases pin
+    # the kernels with g injected.  The "_xi01" twins (XI=0.1) are well conditioned and pin whole modules
+    # across devices.
+    for tag in list(vat_cases):
+        cls, kw, conv, xdim = vat_cases[tag]
+        if not kw.get("KL_Div"):
+            vat_cases[tag + "_xi01"] = (cls, dict(kw, XI=0.1), conv, xdim)
     out = {"x": xs, "P": np.array(P)}
     for tag, (cls, kw, conv, xdim) in vat_cases.items():
         model = StandInTranscriber(conv, n_in=F, n_out=P, seed=3)

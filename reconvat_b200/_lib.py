@@ -88,9 +88,28 @@ def ptr(t, dtype=torch.float32):
     return t.data_ptr()
 
 
+# Optional per-entry-point CUDA-event timing (bench.py's roofline numbers): {name: [(start, end), ...]}
+_event_log = None
+
+
+def record_events(names):
+    """Start recording (start, end) CUDA events around every call of the given entry points on the
+    launching stream; returns the log dict.  ``record_events(None)`` stops recording."""
+    global _event_log
+    _event_log = None if names is None else {n: [] for n in names}
+    return _event_log
+
+
 def call(name, *args):
     """Invoke an entry point on the current PyTorch stream; raise RvbError on a non-zero status."""
     lib = load()
+    log = _event_log.get(name) if _event_log is not None else None
+    if log is not None:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
     rc = getattr(lib, name)(*args, _stream())
+    if log is not None:
+        end.record()
+        log.append((start, end))
     if rc != 0:
         raise RvbError("%s failed (%d): %s" % (name, rc, lib.rvb_last_error().decode("utf-8", "replace")))

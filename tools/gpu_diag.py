@@ -27,7 +27,8 @@ def stage_vat():
     d = torch.randn_like(x)
     g = torch.randn_like(x) * 1e-7
     xa = torch.empty_like(x, device=dev)
-    _lib.call("rvb_vat_perturb", x.to(dev).data_ptr(), d.to(dev).data_ptr(), xa.data_ptr(), 4 * 640, 229, 1e-6, 1)
+    xd0, dd0 = x.to(dev), d.to(dev)
+    _lib.call("rvb_vat_perturb", xd0.data_ptr(), dd0.data_ptr(), xa.data_ptr(), 4 * 640, 229, 1e-6, 1)
     ref = OV.perturb(x, d, 1e-6)
     print("perturb max abs err", float((xa.cpu() - ref).abs().max()))
     xd, dd, gd = x.to(dev), d.to(dev), g.to(dev)
@@ -41,11 +42,12 @@ def stage_vat():
     print("finalize x_adv abs err", float((xa2.cpu() - xa_ref).abs().max()), "dhat", float((dh.cpu() - dh_ref).abs().max()))
     p = torch.sigmoid(torch.randn(4, 640, 88) * 3); y = torch.sigmoid(torch.randn(4, 640, 88) * 3)
     gr = torch.empty_like(p, device=dev)
-    _lib.call("rvb_bce_grad", p.to(dev).data_ptr(), y.to(dev).data_ptr(), gr.data_ptr(), p.numel(), None, 1.0)
+    pd, yd = p.to(dev), y.to(dev)
+    _lib.call("rvb_bce_grad", pd.data_ptr(), yd.data_ptr(), gr.data_ptr(), p.numel(), None, 1.0)
     ref = OV.bce_mean_grad(p, y)
     print("bce_grad rel-to-max err", float((gr.cpu() - ref).abs().max() / ref.abs().max()))
     ws = torch.zeros(_lib.BCE_WORKSPACE_FLOATS, device=dev); loss = torch.zeros((), device=dev)
-    _lib.call("rvb_bce_mean", p.to(dev).data_ptr(), y.to(dev).data_ptr(), p.numel(), loss.data_ptr(), ws.data_ptr())
+    _lib.call("rvb_bce_mean", pd.data_ptr(), yd.data_ptr(), p.numel(), loss.data_ptr(), ws.data_ptr())
     print("bce_mean", loss.item(), OV.bce_mean(p, y).item())
 
 
