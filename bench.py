@@ -65,7 +65,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(f)
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         self.stop_flag.set()
@@ -95,18 +95,27 @@ def make_audio(n_batches, batch, seed):
     return out
 
 
+def make_model(args, batch, dev):
+    """The black-box network the VAT loop calls.  'injected' (default): precomputed posteriors and input
+    gradient, zero kernels -- the step then contains the hot path only (SURVEY.md 8d headline definition).
+    'standin': a frame-wise linear+sigmoid transcriber run by PyTorch (adds cuBLAS/ATen launches that are the
+    caller's, not ours)."""
+    from reconvat_b200.standin import InjectedTranscriber, StandInTranscriber
+    m = InjectedTranscriber(batch, seed=7) if args.model == "injected" else StandInTranscriber("unet", n_out=N_PITCH, seed=1)
+    return m if dev is None else m.to(dev)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (oracle port) on the host cores, rank 0 only."""
     if rank != 0:
         return
     import torch
     from oracle.cpu_path import CpuHotPath
-    from reconvat_b200.standin import StandInTranscriber
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sample = min(args.batch, args.cpu_batch)
     audio = torch.from_numpy(make_audio(1, sample, 0)[0])
-    model = StandInTranscriber("unet", n_out=N_PITCH, seed=1)
+    model = make_model(args, sample, None)
     path = CpuHotPath()
     torch.manual_seed(0)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -122,8 +131,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "audio-sec/s", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Mel+VAT step (front-end + UNet_VAT on a stand-in transcriber), CPU, %d x 20.48 s "
-                               "segments per step (bounded sample of the B=%d workload)" % (sample, args.batch)},
+        "config": {"workload": "Mel+VAT step (front-end + UNet_VAT, network = %s), CPU, %d x 20.48 s "
+                               "segments per step (bounded sample of the B=%d workload)" % (args.model, sample, args.batch)},
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
                          "sample": "%d segments x %d steps, oracle/cpu_path.py (the reference's ATen op sequence; the "
                                    "reference is Python and /root/reference does not travel)" % (sample, steps)},
@@ -145,13 +154,12 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     import reconvat_b200 as R
     from reconvat_b200.pipeline import HotPathStep
-    from reconvat_b200.standin import StandInTranscriber
 
     B = args.batch
     n_rot = max(4, -(-130 * 2 ** 20 // (B * SEG_SAMPLES * 4)))      # rotate inputs over > L2 (126 MB)
     host = [torch.from_numpy(a).pin_memory() for a in make_audio(n_rot, B, 100 * rank)]
     dev_audio = [h.to(dev) for h in host]
-    model = StandInTranscriber("unet", n_out=N_PITCH, seed=1).to(dev)
+    model = make_model(args, B, dev)
     step = HotPathStep(model, dev)
     torch.manual_seed(1234 + rank)
 
@@ -186,7 +194,6 @@ def run_ours(args, rank, local_rank, world):
     launches = R._lib.launch_count() - launches0
     R._lib.record_events(None)
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    clocks = sampler.summary()
     step.vat_loss.check()
     ms_step = ms_total / args.steps
     value = world * B * SEG_SECONDS / (ms_step * 1e-3)
@@ -205,6 +212,7 @@ def run_ours(args, rank, local_rank, world):
     ev1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.summary()                               # sampled across both timed regions
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1)) / n_done
     e2e_value = world * B * SEG_SECONDS / (e2e_ms * 1e-3)
     assert torch.isfinite(results).all(), "non-finite VAT loss in the e2e run"
@@ -243,12 +251,12 @@ def run_ours(args, rank, local_rank, world):
         torch.set_num_threads(cores)
         cb = min(B, args.cpu_batch)
         audio = host[0][:cb].clone()
-        cm = StandInTranscriber("unet", n_out=N_PITCH, seed=1)
+        cm = make_model(args, cb, None)
         path = CpuHotPath()
         path.step(cm, audio)
         t0 = time.perf_counter()
         for _ in range(args.cpu_steps):
-            float(path.step(cm, audio)[0])
+            path.step(cm, audio)[0].item()
         dt = (time.perf_counter() - t0) / args.cpu_steps
         cpu = {"value": cb * SEG_SECONDS / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
                "sample": "%d segments x %d steps of the same step on the host CPU (oracle/cpu_path.py: the reference's "
@@ -259,7 +267,8 @@ def run_ours(args, rank, local_rank, world):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (STFT: 3xTF32 split operands, f32 accumulate in TMEM)", "data": "synthetic",
         "config": {"workload": "Mel+VAT step, B=%d x 20.48 s segments per GPU (BASELINE metric shape): Mel front-end + "
-                               "UNet_VAT(XI=1e-6, eps=2) against a stand-in transcriber" % B,
+                               "UNet_VAT(XI=1e-6, eps=2); network = %s" % (B, "injected posteriors and input gradient "
+                               "(hot path only)" if args.model == "injected" else "stand-in linear transcriber (PyTorch)"),
                    "batch_per_gpu": B, "segment_samples": SEG_SAMPLES, "parallelism": "segments sharded, dp%d, no "
                    "collective on the path" % world,
                    "cache": "inputs rotated over %d batches = %.0f MB > 126 MB L2" % (n_rot, n_rot * B * SEG_SAMPLES * 4 / 1e6)},
@@ -279,13 +288,15 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32, help="segments per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=8, help="segments per CPU-baseline step")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="injected", choices=["injected", "standin"],
+                    help="the black-box network the VAT loop calls (see make_model)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

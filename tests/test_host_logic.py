@@ -1,0 +1,190 @@
+"""CPU tests of the host-side logic: basis builders (bit-exact against the reference-generated golden
+tables), banded filterbank, tf32 split, module surface / state dict, geometry and error behaviour,
+the install() seam, the no-CPU-fallback rule, the injected transcriber."""
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import reconvat_b200 as R
+from reconvat_b200 import basis
+
+MEL_KW = dict(sr=16000, win_length=2048, n_mels=229, hop_length=512, fmin=30, fmax=8000,
+              trainable_mel=False, trainable_STFT=False, verbose=False)
+
+
+def test_basis_bit_exact_vs_reference_golden(golden):
+    g = golden["basis_16k"]
+    m = R.Spectrogram.MelSpectrogram(**MEL_KW)
+    rows = g["rows"]
+    assert np.array_equal(m.stft.wsin[rows, 0].numpy(), g["wsin_rows"])
+    assert np.array_equal(m.stft.wcos[rows, 0].numpy(), g["wcos_rows"])
+    assert np.array_equal(m.stft.window_mask.numpy().reshape(-1), g["window_mask"])
+    assert np.isclose(m.stft.wcos.double().abs().sum().item(), g["wcos_abs64"], rtol=1e-12)
+    assert np.isclose(m.stft.wsin.double().abs().sum().item(), g["wsin_abs64"], rtol=1e-12)
+    mb = np.zeros(tuple(g["mel_shape"]), np.float32)
+    mb[g["mel_nz_m"], g["mel_nz_k"]] = g["mel_nz_v"]
+    assert np.array_equal(m.mel_basis.numpy(), mb)
+
+
+def test_basis_independent_of_the_oracle_restatement():
+    from oracle import nnaudio_restate as NR
+    for kw in (dict(sr=22050, n_fft=2048, n_mels=128), dict(sr=16000, n_fft=1024, n_mels=128, htk=True),
+               dict(sr=16000, n_fft=512, n_mels=40, fmin=20, fmax=7000)):
+        assert np.array_equal(basis.mel_filterbank(**kw), NR.mel(**kw))
+    for fs in ("no", "linear", "log"):
+        a = basis.fourier_basis(512, freq_bins=100, freq_scale=fs, fmin=50, fmax=6000, sr=22050)
+        b = NR.create_fourier_kernels(512, freq_bins=100, freq_scale=fs, fmin=50, fmax=6000, sr=22050, verbose=False)
+        assert np.array_equal(a[0], b[0][:, 0]) and np.array_equal(a[1], b[1][:, 0]) and np.array_equal(a[4], b[4])
+
+
+def test_banded_filterbank_roundtrip_and_rejection():
+    mb = basis.mel_filterbank(16000, 2048, 229, 30, 8000)
+    band0, w0, w1, kb, ke = basis.banded_filterbank(mb)
+    assert (kb, ke) == (4, 1024) and np.all(np.diff(band0[kb:ke]) >= 0)
+    dense = np.zeros_like(mb)
+    for k in range(kb, ke):
+        if w0[k]:
+            dense[band0[k], k] = w0[k]
+        if w1[k]:
+            dense[band0[k] + 1, k] = w1[k]
+    assert np.array_equal(dense, mb)
+    assert int((mb != 0).sum()) == 2025 and int((mb != 0).sum(0).max()) == 2
+    bad = mb.copy()
+    bad[100, 50] = 1.0                                   # third, non-adjacent weight in a column
+    with pytest.raises(ValueError, match="not a banded"):
+        basis.banded_filterbank(bad)
+
+
+def test_tf32_split_reconstructs_to_2_pow_minus_21():
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(100000) * np.exp(rng.uniform(-20, 5, 100000))).astype(np.float32)
+    hi, lo = basis.tf32_split(x)
+    assert np.all((hi.view(np.uint32) & 0x1FFF) == 0) and np.all((lo.view(np.uint32) & 0x1FFF) == 0)
+    rel = np.abs((hi.astype(np.float64) + lo) - x) / np.abs(x)
+    assert rel.max() < 2.0 ** -21
+    # ties round away from zero, like cvt.rna.tf32.f32
+    t = np.array([1.0 + 2.0 ** -11, -(1.0 + 2.0 ** -11)], np.float32)
+    assert np.array_equal(basis.tf32_round(t), np.array([1.0 + 2.0 ** -10, -(1.0 + 2.0 ** -10)], np.float32))
+
+
+def test_gemm_operand_layout():
+    rng = np.random.default_rng(1)
+    wc = rng.standard_normal((257, 512)).astype(np.float32)
+    ws = rng.standard_normal((257, 512)).astype(np.float32)
+    hi, lo, n_gemm, left = basis.gemm_operand(wc, ws)
+    assert hi.shape == (512, 512) and n_gemm == 256 and left == [256]
+    full = hi.astype(np.float64) + lo
+    assert np.allclose(full[0:128], wc[0:128], rtol=1e-6) and np.allclose(full[128:256], ws[0:128], rtol=1e-6)
+    assert np.allclose(full[256:384], wc[128:256], rtol=1e-6) and np.allclose(full[384:512], ws[128:256], rtol=1e-6)
+    hi, lo, n_gemm, left = basis.gemm_operand(wc[:100], ws[:100])
+    assert hi.shape == (256, 512) and n_gemm == 100 and left == [] and not hi[100:128].any() and not hi[228:].any()
+
+
+def test_module_surface_and_state_dict():
+    m = R.Spectrogram.MelSpectrogram(**MEL_KW)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {
+        "mel_basis": (229, 1025), "stft.wsin": (1025, 1, 2048), "stft.wcos": (1025, 1, 2048),
+        "stft.window_mask": (1, 2048, 1)}
+    assert m.stft.stride == 512 and m.stft.pad_amount == 1024 and m.power == 2.0
+    s = R.Spectrogram.STFT(n_fft=1024, verbose=False)          # hop defaults to win_length // 4
+    assert s.stride == 256 and s.wsin.shape == (513, 1, 1024) and s.output_format == "Complex"
+    si = R.Spectrogram.STFT(n_fft=512, iSTFT=True, verbose=False)
+    assert si.kernel_sin_inv.shape == (512, 1, 512, 1)
+    for kw in (dict(trainable=True),):
+        with pytest.raises(NotImplementedError):
+            R.Spectrogram.STFT(verbose=False, **kw)
+    with pytest.raises(NotImplementedError):
+        R.Spectrogram.MelSpectrogram(trainable_mel=True, verbose=False)
+    with pytest.raises(NotImplementedError):
+        s.inverse(None)
+
+
+def test_geometry_matches_conv1d_arithmetic():
+    s = R.Spectrogram.STFT(n_fft=2048, hop_length=512, verbose=False)
+    assert s._geometry(327679) == (0, 640, 644)
+    assert s._geometry(1025)[1] == 3
+    with pytest.raises(AssertionError, match="shorter than reflect padding"):
+        s._geometry(1000)
+    with pytest.raises(RuntimeError, match="Padding size should be less"):
+        s._geometry(1024)
+    nc = R.Spectrogram.STFT(n_fft=512, hop_length=256, center=False, verbose=False)
+    assert nc._geometry(8192) == (2, 31, 32)
+    with pytest.raises(RuntimeError, match="Kernel size"):
+        nc._geometry(300)
+
+
+def test_no_cpu_fallback_anywhere():
+    m = R.Spectrogram.MelSpectrogram(**MEL_KW)
+    with pytest.raises(R._lib.RvbError, match="no CPU path"):
+        m(torch.zeros(1, 4096))
+    with pytest.raises(R._lib.RvbError, match="no CPU path"):
+        m.normalised_log_mel(torch.zeros(1, 4096))
+    with pytest.raises(R._lib.RvbError, match="no CPU path"):
+        R.utils.Normalization("imagewise").transform(torch.zeros(1, 4, 4))
+    with pytest.raises(R._lib.RvbError, match="no CPU path"):
+        R.VAT.UNet_VAT(1e-6, 2.0, 1, False)(None, torch.zeros(1, 1, 4, 229))
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 1, 1, 4096))
+    # the product never imports the oracle
+    import os
+    pkg = os.path.dirname(R.__file__)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(root, f)).read().replace("oracle/cpu_path", ""), f
+
+
+def test_install_rebinds_the_reference_modules(monkeypatch):
+    fake = {}
+    for name in ("model", "model.VAT", "model.self_attention_VAT", "model.UNet_onset", "model.onset_frame_VAT"):
+        mod = types.ModuleType(name)
+        fake[name] = mod
+        monkeypatch.setitem(sys.modules, name, mod)
+    fake["model"].stepwise_VAT = object
+    fake["model.self_attention_VAT"].Normalization = object
+    fake["model.self_attention_VAT"].Spectrogram = types.ModuleType("nnAudio.Spectrogram")
+    for k in ("nnAudio", "nnAudio.Spectrogram", "nnAudio.utils", "nnAudio.librosa_functions"):
+        monkeypatch.delitem(sys.modules, k, raising=False)
+    done = R.install()
+    import nnAudio
+    from nnAudio import Spectrogram as S
+    assert S is R.Spectrogram and nnAudio.Spectrogram.MelSpectrogram is R.Spectrogram.MelSpectrogram
+    assert fake["model.self_attention_VAT"].UNet_VAT is R.VAT.UNet_VAT
+    assert fake["model.self_attention_VAT"].stepwise_VAT is R.VAT.stepwise_VAT
+    assert fake["model.UNet_onset"].UNet_VAT is R.VAT.UNet_VAT_onset
+    assert fake["model.onset_frame_VAT"].stepwise_VAT is R.VAT.stepwise_VAT_onf
+    assert fake["model.VAT"].stepwise_VAT is R.VAT.stepwise_VAT_vatpy
+    assert fake["model.self_attention_VAT"].Normalization is R.utils.Normalization
+    assert fake["model.self_attention_VAT"].Spectrogram is R.Spectrogram
+    assert fake["model"].stepwise_VAT is R.VAT.stepwise_VAT
+    assert ("model.UNet_onset", "UNet_VAT") in done
+    from nnAudio.utils import create_fourier_kernels
+    from nnAudio.librosa_functions import mel
+    assert create_fourier_kernels(512, freq_scale="no")[0].shape == (257, 1, 512) and mel(16000, 512).shape == (128, 257)
+
+
+def test_vat_constructor_signatures_mirror_the_reference():
+    V = R.VAT
+    assert V.stepwise_VAT_vatpy(1e-6, 2, 1).epsilon == 2
+    assert V.stepwise_VAT(1e-6, 2, 1, False, binwise=False).XI == 1e-6
+    assert V.UNet_VAT(1e-6, 2, 1, False, reconstruction=True).reconstruction is True
+    assert V.UNet_VAT_onset(1e-6, 2, 1, False)._dict_loss == ("frame", "onset")
+    assert V.stepwise_VAT_onf(1e-6, 0.1, 1, False)._heads == (2,)
+    assert V.onset_frame_VAT(1e-6, 2, 1)._n_returns == 2
+    for bad in (dict(n_power=2, KL_Div=False), dict(n_power=1, KL_Div=True)):
+        with pytest.raises(NotImplementedError):
+            V.UNet_VAT(1e-6, 2, **bad)
+
+
+def test_injected_transcriber_drives_the_reference_op_sequence_on_cpu():
+    from oracle.cpu_path import CpuHotPath
+    from reconvat_b200.standin import InjectedTranscriber
+    m = InjectedTranscriber(1, frames=6, seed=3)
+    x = torch.rand(1, 1, 6, 229)
+    torch.manual_seed(0)
+    loss, r_adv, dhat = CpuHotPath().vat(m, x)
+    assert torch.allclose(r_adv.norm(dim=-1), torch.full((1, 1, 6), 2.0), rtol=1e-5)
+    assert torch.isfinite(loss)
