@@ -84,6 +84,41 @@ int rvb_stft_gemm(const float* sig_hi, const float* sig_lo, int n_seg, int rows_
                   float power, float* out0, int n_out_bins, rvb_stream_t stream);
 
 /*
+ * K0f  pad + frame + FOLD + tf32 hi/lo split, for windows that are symmetric about n_fft/2
+ * (w[n] == w[n_fft-n]; true for every periodic scipy window at win_length == n_fft, checked on the host).
+ * For a real frame p[0..N) the windowed Fourier basis satisfies wcos[k][N-n] = wcos[k][n] and
+ * wsin[k][N-n] = -wsin[k][n], so
+ *     re[k] = w[0] p[0] + sum_{n=1}^{N/2} wcos[k][n] e[n],   e[n] = p[n] + p[N-n]  (e[N/2] = p[N/2])
+ *     im[k] =             sum_{n=1}^{N/2-1} wsin[k][n] o[n], o[n] = p[n] - p[N-n]
+ * which halves the contraction length (model/Spectrogram.py:219-220 computes the same sums unfolded).
+ * Writes the operand planes a_hi/a_lo as [2][n_seg*n_frames][n_fft/2]: plane 0 = e, plane 1 = o
+ * (column c <-> n = c+1; o's last column is 0), each split as hi = tf32(v), lo = tf32(v - hi) with the
+ * rounding error of the fp32 add recovered (TwoSum), and optionally p0[frame] = p[0] (needed when w[0] != 0).
+ */
+int rvb_fold_split(const float* audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int pad_mode, int n_fft,
+                   int hop, int n_frames, float* a_hi, float* a_lo, float* p0, rvb_stream_t stream);
+
+/*
+ * K1f  the folded STFT contraction on tcgen05 (two K = n_fft/2 chains per tile: e x cos -> re, o x sin -> im).
+ *   a_hi/a_lo     planes from rvb_fold_split
+ *   basis_hi/lo   [2][n_bins_pad][n_fft/2] row-major: plane 0 = folded cos rows, plane 1 = folded sin rows
+ *                 (n_bins_pad % 128 == 0)
+ *   p0, w0        optional rank-1 term re += w0 * p0[frame] (pass NULL / 0 when the window starts at 0)
+ * Same epilogues and output indexing as rvb_stft_gemm.
+ */
+int rvb_stft_gemm_folded(const float* a_hi, const float* a_lo, int n_seg, int n_frames, int n_fft,
+                         const float* basis_hi, const float* basis_lo, int n_bins_pad, const float* p0, float w0,
+                         int epilogue, float power, float* out0, int n_out_bins, rvb_stream_t stream);
+
+/*
+ * K1fb  one frequency bin from the folded planes in plain fp32 FMA (Nyquist bin of the STFT module).
+ * wc_row / ws_row: that bin's folded fp32 basis rows (n_fft/2 floats each).
+ */
+int rvb_stft_bin_folded(const float* a_hi, const float* a_lo, int n_seg, int n_frames, int n_fft,
+                        const float* wc_row, const float* ws_row, const float* p0, float w0, int bin, int epilogue,
+                        float power, float* out0, int n_out_bins, rvb_stream_t stream);
+
+/*
  * K1b  one frequency bin in plain fp32 FMA (used for the Nyquist bin, which would otherwise cost a
  * whole extra 256-column tile).  Same epilogues / output indexing as rvb_stft_gemm; `wcos_row`,
  * `wsin_row` are the fp32 windowed basis rows of that bin (model/Spectrogram.py:162-164).

@@ -11,6 +11,8 @@ Scope cuts, all raising instead of silently computing something else: ``trainabl
 config of the reference uses it), ``STFT.inverse`` / the other nnAudio transforms,
 CPU tensors (there is no fallback path).
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -79,11 +81,18 @@ class STFT(nn.Module):
                                     "(there is no CPU path)" % self.wsin.device)
             wcos = self.wcos[:, 0, :].detach().cpu().numpy()
             wsin = self.wsin[:, 0, :].detach().cpu().numpy()
-            hi, lo, n_gemm, leftover = basis.gemm_operand(wcos, wsin)
             dev = self.wsin.device
-            self._tables = dict(basis_hi=torch.from_numpy(hi).to(dev), basis_lo=torch.from_numpy(lo).to(dev),
-                                n_gemm_bins=n_gemm, leftover=leftover, n_bins=wcos.shape[0])
-            self._tables_key = key
+            tb = dict(n_bins=wcos.shape[0], fold=None, direct=None)
+            fold = None if os.environ.get("RVB_NO_FOLD") else basis.fold_operand(wcos, wsin)
+            if fold is not None:
+                for k in ("basis_hi", "basis_lo", "left_cos", "left_sin"):
+                    fold[k] = torch.from_numpy(np.ascontiguousarray(fold[k])).to(dev)
+                tb["fold"] = fold
+            else:
+                hi, lo, n_gemm, leftover = basis.gemm_operand(wcos, wsin)
+                tb["direct"] = dict(basis_hi=torch.from_numpy(hi).to(dev), basis_lo=torch.from_numpy(lo).to(dev),
+                                    n_gemm_bins=n_gemm, leftover=leftover)
+            self._tables, self._tables_key = tb, key
         return self._tables
 
     def _apply(self, fn, *args, **kwargs):
@@ -116,57 +125,80 @@ class STFT(nn.Module):
         rows = _ceil_div(padded, self.stride)
         return mode, n_frames, rows
 
-    def _planes(self, x):
-        """x: (B,1,L) CUDA float32 -> (sig_hi, sig_lo, n_frames, rows_per_seg)."""
+    def _check_input(self, x):
         if not x.is_cuda:
             raise _lib.RvbError("reconvat_b200.STFT: input is on %s; there is no CPU path" % x.device)
         if x.requires_grad:
             raise NotImplementedError("reconvat_b200.STFT: gradients w.r.t. the waveform are not provided")
         if x.dtype != torch.float32:
             raise _lib.RvbError("reconvat_b200.STFT: expected float32 audio, got %s" % x.dtype)
-        if self.stride % 32 != 0 or self.n_fft % 32 != 0:
-            raise NotImplementedError("reconvat_b200.STFT: hop_length and n_fft must be multiples of 32 "
-                                      "(got hop=%d, n_fft=%d)" % (self.stride, self.n_fft))
-        B, _, L = x.shape
         x2 = x[:, 0, :]
-        if x2.stride(-1) != 1:
-            x2 = x2.contiguous()
+        return x2 if x2.stride(-1) == 1 else x2.contiguous()
+
+    def n_frames(self, num_samples):
+        return self._geometry(num_samples)[1]
+
+    def _spectrum(self, x, epilogue, power, make_out):
+        """x: (B,1,L) CUDA float32.  Runs pad/frame/split + the tcgen05 contraction with the given epilogue.
+        ``make_out(B, n_frames)`` -> (out tensor, n_out_bins).  Returns (out, n_frames)."""
+        x2 = self._check_input(x)
+        B, L = x2.shape
+        ld = x2.stride(0) if B > 1 else L
         mode, n_frames, rows = self._geometry(L)
+        out, n_out_bins = make_out(B, n_frames)
+        tb = self._device_tables()
+        if tb["fold"] is not None:
+            fd = tb["fold"]
+            half, M = self.n_fft // 2, B * n_frames
+            planes = torch.empty((2, 2, M, half), dtype=torch.float32, device=x.device)    # [hi|lo][e|o][frame][c]
+            p0 = torch.empty((M,), dtype=torch.float32, device=x.device) if fd["w0"] != 0.0 else None
+            _lib.call("rvb_fold_split", _lib.ptr(x2), ld, B, L, self.pad_amount, mode, self.n_fft, self.stride,
+                      n_frames, planes[0].data_ptr(), planes[1].data_ptr(), None if p0 is None else p0.data_ptr())
+            _lib.call("rvb_stft_gemm_folded", planes[0].data_ptr(), planes[1].data_ptr(), B, n_frames, self.n_fft,
+                      fd["basis_hi"].data_ptr(), fd["basis_lo"].data_ptr(), fd["n_bins_pad"],
+                      None if p0 is None else p0.data_ptr(), fd["w0"], epilogue, float(power), _lib.ptr(out),
+                      n_out_bins)
+            for i, k in enumerate(fd["leftover"]):
+                if k < n_out_bins:
+                    _lib.call("rvb_stft_bin_folded", planes[0].data_ptr(), planes[1].data_ptr(), B, n_frames,
+                              self.n_fft, fd["left_cos"][i].data_ptr(), fd["left_sin"][i].data_ptr(),
+                              None if p0 is None else p0.data_ptr(), fd["w0"], k, epilogue, float(power),
+                              _lib.ptr(out), n_out_bins)
+            return out, n_frames
+        # unfolded contraction (non-symmetric window / non-integer bin scale)
+        if self.stride % 32 != 0 or self.n_fft % 32 != 0:
+            raise NotImplementedError("reconvat_b200.STFT: for a basis that is not symmetric about n_fft/2, hop_length "
+                                      "and n_fft must be multiples of 32 (got hop=%d, n_fft=%d)" % (self.stride, self.n_fft))
+        dr = tb["direct"]
         # tail boxes of the last segment run past the planes: TMA zero-fills out-of-bounds rows
         sig = torch.empty((2, B * rows, self.stride), dtype=torch.float32, device=x.device)
-        _lib.call("rvb_pad_split", _lib.ptr(x2), x2.stride(0) if B > 1 else L, B, L, self.pad_amount, mode,
-                  sig[0].data_ptr(), sig[1].data_ptr(), rows, self.stride)
-        return sig, n_frames, rows
-
-    def _contract(self, sig, B, n_frames, rows, epilogue, power, out, n_out_bins):
-        tb = self._device_tables()
+        _lib.call("rvb_pad_split", _lib.ptr(x2), ld, B, L, self.pad_amount, mode, sig[0].data_ptr(),
+                  sig[1].data_ptr(), rows, self.stride)
         _lib.call("rvb_stft_gemm", sig[0].data_ptr(), sig[1].data_ptr(), B, rows, self.stride, n_frames,
-                  tb["basis_hi"].data_ptr(), tb["basis_lo"].data_ptr(), tb["basis_hi"].shape[0], self.n_fft,
+                  dr["basis_hi"].data_ptr(), dr["basis_lo"].data_ptr(), dr["basis_hi"].shape[0], self.n_fft,
                   epilogue, float(power), _lib.ptr(out), n_out_bins)
-        for k in tb["leftover"]:
+        for k in dr["leftover"]:
             if k < n_out_bins:
                 _lib.call("rvb_stft_bin", sig[0].data_ptr(), sig[1].data_ptr(), B, rows, self.stride, n_frames,
                           self.wcos[k, 0].data_ptr(), self.wsin[k, 0].data_ptr(), self.n_fft, k, epilogue,
                           float(power), _lib.ptr(out), n_out_bins)
+        return out, n_frames
 
     def forward(self, x, output_format=None):
         output_format = output_format or self.output_format
         self.num_samples = x.shape[-1]
         x = basis.broadcast_dim(x)
-        sig, n_frames, rows = self._planes(x)
-        B = x.shape[0]
-        F = self._device_tables()["n_bins"]
+        F = self.wsin.shape[0]
+        dev = x.device
         if output_format == 'Magnitude':
-            out = torch.empty((B, F, n_frames), dtype=torch.float32, device=x.device)
-            self._contract(sig, B, n_frames, rows, _lib.EPI_MAGNITUDE, 1.0, out, F)
+            epi, shape = _lib.EPI_MAGNITUDE, lambda B, T: (B, F, T)
         elif output_format == 'Complex':
-            out = torch.empty((B, F, n_frames, 2), dtype=torch.float32, device=x.device)
-            self._contract(sig, B, n_frames, rows, _lib.EPI_COMPLEX, 1.0, out, F)
+            epi, shape = _lib.EPI_COMPLEX, lambda B, T: (B, F, T, 2)
         elif output_format == 'Phase':
-            out = torch.empty((B, F, n_frames), dtype=torch.float32, device=x.device)
-            self._contract(sig, B, n_frames, rows, _lib.EPI_PHASE, 1.0, out, F)
+            epi, shape = _lib.EPI_PHASE, lambda B, T: (B, F, T)
         else:
             return None          # the reference falls through its if/elif chain the same way
+        out, _ = self._spectrum(x, epi, 1.0, lambda B, T: (torch.empty(shape(B, T), dtype=torch.float32, device=dev), F))
         return out
 
     def inverse(self, *args, **kwargs):
@@ -227,18 +259,18 @@ class MelSpectrogram(nn.Module):
     def _power_spectrogram(self, x):
         """(B,1,L) -> power (B, n_pow_bins, T) holding (sqrt(re^2+im^2))**power for every bin the
         filterbank reads (model/Spectrogram.py:458)."""
-        sig, n_frames, rows = self.stft._planes(x)
-        B = x.shape[0]
         bands = self._band_tables()
         n_pow_bins = bands["k_end"]                          # bins >= k_end carry zero weight: never stored
-        power = torch.empty((B, n_pow_bins, n_frames), dtype=torch.float32, device=x.device)
         if float(self.power) == 2.0:
             epi = _lib.EPI_POWER
         elif float(self.power) == 1.0:
             epi = _lib.EPI_MAGNITUDE
         else:
             epi = _lib.EPI_POWER_P
-        self.stft._contract(sig, B, n_frames, rows, epi, self.power, power, n_pow_bins)
+        dev = x.device
+        power, n_frames = self.stft._spectrum(
+            x, epi, self.power,
+            lambda B, T: (torch.empty((B, n_pow_bins, T), dtype=torch.float32, device=dev), n_pow_bins))
         return power, n_frames, bands
 
     def forward(self, x):

@@ -177,3 +177,53 @@ def gemm_operand(wcos, wsin):
         mat[256 * j + 128:256 * j + 128 + (hi_bin - lo_bin)] = wsin[lo_bin:hi_bin]
     hi, lo = tf32_split(mat)
     return hi, lo, n_gemm, leftover
+
+
+def tf32_split64(x64):
+    """float64 values -> (hi, lo) float32 tf32 planes with hi + lo == x to ~2^-22 relative."""
+    x64 = np.asarray(x64, dtype=np.float64)
+    hi = tf32_round(x64.astype(np.float32))
+    lo = tf32_round((x64 - hi.astype(np.float64)).astype(np.float32))
+    return hi, lo
+
+
+def fold_operand(wcos, wsin, tol=2.5e-7):
+    """Folded operand for windows symmetric about n_fft/2, or None when the basis is not symmetric
+    (short / non-periodic windows, non-integer 'linear' / 'log' bin scales).
+
+    With wcos[k][N-n] == wcos[k][n] and wsin[k][N-n] == -wsin[k][n] (to fp32 rounding),
+        re[k] = w[0] p[0] + sum_{c=0}^{N/2-1} Bc[k][c] e[c],  e[c] = p[c+1] + p[N-c-1]  (e[N/2-1] = p[N/2])
+        im[k] =             sum_{c=0}^{N/2-1} Bs[k][c] o[c],  o[c] = p[c+1] - p[N-c-1]  (o[N/2-1] = 0)
+    Bc / Bs average the two mirror entries in float64 (they differ by at most an fp32 ulp).
+    Returns dict(basis_hi, basis_lo [2*n_bins_pad, N/2] f32; n_bins_pad; n_gemm_bins; leftover; w0;
+    left_cos, left_sin: folded fp32 rows of the leftover bins).
+    """
+    F, N = wcos.shape
+    if N % 64 != 0:
+        return None
+    half = N // 2
+    c64, s64 = wcos.astype(np.float64), wsin.astype(np.float64)
+    fwd = slice(1, half)                       # n = 1 .. N/2-1
+    mirror = slice(N - 1, half, -1)            # N-n = N-1 .. N/2+1
+    scale = max(float(np.abs(c64).max()), 1e-30)
+    if np.abs(c64[:, fwd] - c64[:, mirror]).max() > tol * scale or np.abs(s64[:, fwd] + s64[:, mirror]).max() > tol * scale:
+        return None
+    if np.abs(s64[:, 0]).max() > tol * scale or np.abs(s64[:, half]).max() > tol * scale:
+        return None
+    w0 = float(wcos[0, 0])
+    if np.abs(c64[:, 0] - w0).max() > tol * scale:     # the n = 0 term must be the same for every bin
+        return None
+    bc = np.empty((F, half), np.float64)
+    bs = np.zeros((F, half), np.float64)
+    bc[:, :half - 1] = 0.5 * (c64[:, fwd] + c64[:, mirror])
+    bc[:, half - 1] = c64[:, half]
+    bs[:, :half - 1] = 0.5 * (s64[:, fwd] - s64[:, mirror])
+    n_gemm = F - 1 if (F % GEMM_TILE_BINS == 1 and F > 1) else F
+    leftover = list(range(n_gemm, F))
+    n_bins_pad = -(-n_gemm // GEMM_TILE_BINS) * GEMM_TILE_BINS
+    mat = np.zeros((2 * n_bins_pad, half), np.float64)
+    mat[:n_gemm] = bc[:n_gemm]
+    mat[n_bins_pad:n_bins_pad + n_gemm] = bs[:n_gemm]
+    hi, lo = tf32_split64(mat)
+    return dict(basis_hi=hi, basis_lo=lo, n_bins_pad=n_bins_pad, n_gemm_bins=n_gemm, leftover=leftover, w0=w0,
+                left_cos=bc[n_gemm:].astype(np.float32), left_sin=bs[n_gemm:].astype(np.float32))

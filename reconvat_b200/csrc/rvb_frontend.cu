@@ -58,6 +58,55 @@ pad_split_kernel(const float* __restrict__ audio, int64_t audio_ld, int n_sample
   }
 }
 
+// ------------------------------------------------------------------ K0f
+// One block per frame (grid-stride): the frame's n_fft samples are staged in smem with coalesced,
+// reflect-aware loads, then thread i produces columns i, i+256, ... of the e and o planes (coalesced 4-byte
+// stores, conflict-free smem reads).  Each audio sample is read by the 4 frames that overlap it: L2 hits.
+__device__ __forceinline__ void split_sum(float a, float b, float& hi, float& lo) {
+  const float s = a + b;
+  const float bb = s - a;
+  const float err = (a - (s - bb)) + (b - bb);            // TwoSum: a + b == s + err exactly
+  hi = to_tf32(s);
+  lo = to_tf32((s - hi) + err);
+}
+
+__global__ void __launch_bounds__(256)
+fold_split_kernel(const float* __restrict__ audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int mode,
+                  int n_fft, int hop, int n_frames, float* __restrict__ a_hi, float* __restrict__ a_lo,
+                  float* __restrict__ p0) {
+  extern __shared__ float frame[];                         // n_fft floats
+  const int half = n_fft >> 1;
+  const int64_t n_rows = (int64_t)n_seg * n_frames;
+  const int64_t padded = (mode == RVB_PAD_NONE) ? n_samples : (int64_t)n_samples + 2 * pad;
+  for (int64_t f = blockIdx.x; f < n_rows; f += gridDim.x) {
+    const int b = (int)(f / n_frames), t = (int)(f - (int64_t)b * n_frames);
+    const float* a = audio + (int64_t)b * audio_ld;
+    const int64_t start = (int64_t)t * hop;
+    __syncthreads();                                       // previous iteration's readers are done
+    for (int i = threadIdx.x; i < n_fft; i += blockDim.x) {
+      const int64_t pi = start + i;
+      frame[i] = (pi < padded) ? padded_sample(a, pi, n_samples, pad, mode) : 0.f;
+    }
+    __syncthreads();
+    float* e_hi = a_hi + f * half;
+    float* e_lo = a_lo + f * half;
+    float* o_hi = a_hi + (n_rows + f) * half;
+    float* o_lo = a_lo + (n_rows + f) * half;
+    for (int c = threadIdx.x; c < half; c += blockDim.x) {
+      const int n = c + 1;
+      const float x = frame[n];
+      const float y = (n < half) ? frame[n_fft - n] : 0.f;  // n == n_fft/2 pairs with itself: e = p, o = 0
+      float h, l;
+      split_sum(x, y, h, l);
+      e_hi[c] = h; e_lo[c] = l;
+      split_sum(x, -y, h, l);
+      if (n == half) { h = 0.f; l = 0.f; }
+      o_hi[c] = h; o_lo[c] = l;
+    }
+    if (p0 && threadIdx.x == 0) p0[f] = frame[0];
+  }
+}
+
 // ------------------------------------------------------------------ K1b
 // One warp per frame: plain fp32 dot products of the frame with one basis row pair.
 __global__ void __launch_bounds__(256)
@@ -304,6 +353,30 @@ extern "C" int rvb_pad_split(const float* audio, int64_t audio_ld, int n_seg, in
                                                            plane);
   count_launch();
   return check_launch("pad_split_kernel");
+}
+
+extern "C" int rvb_fold_split(const float* audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int pad_mode,
+                              int n_fft, int hop, int n_frames, float* a_hi, float* a_lo, float* p0,
+                              rvb_stream_t stream) {
+  RVB_REQUIRE(audio && a_hi && a_lo, "rvb_fold_split: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_samples > 0 && hop > 0 && n_frames > 0, "rvb_fold_split: bad shape");
+  RVB_REQUIRE(n_fft >= 64 && n_fft % 64 == 0 && n_fft <= 32768, "rvb_fold_split: n_fft %d must be a multiple of 64", n_fft);
+  RVB_REQUIRE(pad_mode >= RVB_PAD_REFLECT && pad_mode <= RVB_PAD_NONE, "rvb_fold_split: bad pad_mode %d", pad_mode);
+  if (pad_mode == RVB_PAD_REFLECT)
+    RVB_REQUIRE(n_samples > pad, "rvb_fold_split: reflect padding %d needs more than %d samples", pad, n_samples);
+  const int64_t padded = (pad_mode == RVB_PAD_NONE) ? n_samples : (int64_t)n_samples + 2 * pad;
+  RVB_REQUIRE((int64_t)(n_frames - 1) * hop + n_fft <= padded, "rvb_fold_split: %d frames do not fit %lld samples",
+              n_frames, (long long)padded);
+  const int64_t n_rows = (int64_t)n_seg * n_frames;
+  const size_t smem = (size_t)n_fft * sizeof(float);
+  if (smem > 48 * 1024)
+    RVB_CUDA(cudaFuncSetAttribute(fold_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t cap = 148 * 8 * 4;
+  const unsigned grid = (unsigned)(n_rows < cap ? n_rows : cap);
+  fold_split_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(audio, audio_ld, n_seg, n_samples, pad, pad_mode, n_fft,
+                                                               hop, n_frames, a_hi, a_lo, p0);
+  count_launch();
+  return check_launch("fold_split_kernel");
 }
 
 extern "C" int rvb_stft_bin(const float* sig_hi, const float* sig_lo, int n_seg, int rows_per_seg, int hop,

@@ -304,6 +304,211 @@ stft_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------- folded kernel (K1f)
+// Same pipeline skeleton; differences from stft_gemm_kernel:
+//  * the K loop runs two chains back to back: chain 0 = e x folded-cos -> accumulator columns [0,128) (re),
+//    chain 1 = o x folded-sin -> columns [128,256) (im); each chain is K = n_fft/2 long, so the MMA work is
+//    half of the unfolded contraction;
+//  * operands are plain row-major matrices (frames are materialised by fold_split_kernel): A box = 128 rows x
+//    32 floats at row chain*M + m_tile*128, B box = 128 rows at row chain*n_bins_pad + n_tile*128;
+//  * stage = A_hi, A_lo, B_hi, B_lo of 16 KB each = 64 KB -> 3 stages; MMAs are 128 x 128 x 8;
+//  * M is the flattened frame index (tiles may straddle segments; the epilogue maps row -> (b, t)).
+constexpr int F_BLOCK_N = 128;
+constexpr int F_STAGES = 3;
+constexpr int F_TILE_BYTES = 128 * BLOCK_K * 4;         // 16 KB (A and B tiles are both 128 rows)
+constexpr int F_STAGE_BYTES = 4 * F_TILE_BYTES;         // 64 KB
+constexpr int F_SMEM_BYTES = F_STAGES * F_STAGE_BYTES + BAR_BYTES + 1024;
+
+struct FoldParams {
+  int n_frames;               // frames per segment (T)
+  int64_t m_rows;             // n_seg * n_frames
+  int n_bins_pad, half;       // rows per basis plane, n_fft / 2
+  int m_tiles, n_tiles;
+  int epilogue, n_out_bins, n_store_bins;
+  float power, w0;
+  const float* p0;
+  float* out0;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                      const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                      const FoldParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + F_STAGES * F_STAGE_BYTES;
+  auto s_tile = [&](int s, int which) { return smem_base + s * F_STAGE_BYTES + which * F_TILE_BYTES; };   // 0 A_hi 1 A_lo 2 B_hi 3 B_lo
+  auto bar_full = [&](int s) { return bar_base + 8 * s; };
+  auto bar_empty = [&](int s) { return bar_base + 8 * (F_STAGES + s); };
+  auto bar_tmem_full = [&](int a) { return bar_base + 8 * (2 * F_STAGES + a); };
+  auto bar_tmem_empty = [&](int a) { return bar_base + 8 * (2 * F_STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8 * (2 * F_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b_hi);
+    tma_prefetch_desc(&tm_b_lo);
+    for (int s = 0; s < F_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tmem_full(a), 1);
+      mbar_init(bar_tmem_empty(a), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  const int n_units = p.m_tiles * p.n_tiles;
+  const int kb_per_chain = p.half / BLOCK_K;
+  const int num_kb = 2 * kb_per_chain;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int chain = kb >= kb_per_chain;
+          const int kk = (kb - chain * kb_per_chain) * BLOCK_K;
+          const int a_row = (int)(chain * p.m_rows) + m_tile * BLOCK_M;
+          const int b_row = chain * p.n_bins_pad + n_tile * F_BLOCK_N;
+          mbar_wait(bar_empty(stage), phase ^ 1u, nullptr, 1);
+          mbar_expect_tx(bar_full(stage), F_STAGE_BYTES);
+          tma_load_2d(&tm_a_hi, s_tile(stage, 0), bar_full(stage), kk, a_row);
+          tma_load_2d(&tm_a_lo, s_tile(stage, 1), bar_full(stage), kk, a_row);
+          tma_load_2d(&tm_b_hi, s_tile(stage, 2), bar_full(stage), kk, b_row);
+          tma_load_2d(&tm_b_lo, s_tile(stage, 3), bar_full(stage), kk, b_row);
+          if (++stage == F_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, F_BLOCK_N);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        mbar_wait(bar_tmem_empty(acc), acc_phase ^ 1u, nullptr, 2);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int chain = kb >= kb_per_chain;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + chain * F_BLOCK_N);
+          const bool first_kb = (kb == 0) || (kb == kb_per_chain);
+          mbar_wait(bar_full(stage), phase, nullptr, 3);
+          tc_fence_after();
+          const uint64_t da_hi = make_sw128_desc(s_tile(stage, 0));
+          const uint64_t da_lo = make_sw128_desc(s_tile(stage, 1));
+          const uint64_t db_hi = make_sw128_desc(s_tile(stage, 2));
+          const uint64_t db_lo = make_sw128_desc(s_tile(stage, 3));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)(k * UMMA_K * 4 >> 4);
+            // small cross terms first: while the accumulator is still small their truncation costs nothing
+            umma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
+            umma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+            umma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+          }
+          umma_commit(bar_empty(stage));
+          if (++stage == F_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(bar_tmem_full(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
+      const int64_t f = (int64_t)m_tile * BLOCK_M + row;        // flattened frame index
+      const bool f_ok = f < p.m_rows;
+      const int b = f_ok ? (int)(f / p.n_frames) : 0;
+      const int t = f_ok ? (int)(f - (int64_t)b * p.n_frames) : 0;
+      const float re0 = (p.p0 != nullptr && f_ok) ? p.w0 * __ldg(p.p0 + f) : 0.f;
+      mbar_wait(bar_tmem_full(acc), acc_phase, nullptr, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t re[32], im[32];
+        tmem_ld32(taddr + c * 32, re);
+        tmem_ld32(taddr + 128 + c * 32, im);
+        tmem_ld_wait();
+        const int k0 = n_tile * 128 + c * 32;
+        if (f_ok) {
+          const int64_t base = ((int64_t)b * p.n_out_bins + k0) * p.n_frames + t;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (k0 + i < p.n_store_bins)
+              stft_store(p.epilogue, p.power, __uint_as_float(re[i]) + re0, __uint_as_float(im[i]), p.out0,
+                         base + (int64_t)i * p.n_frames);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tmem_empty(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// Single bin from the folded planes (Nyquist bin of the STFT module): warp per frame, fp32 FMA.
+__global__ void __launch_bounds__(256)
+stft_bin_fold_kernel(const float* __restrict__ a_hi, const float* __restrict__ a_lo, int64_t m_rows, int n_frames,
+                     int half, const float* __restrict__ wc_row, const float* __restrict__ ws_row,
+                     const float* __restrict__ p0, float w0, int bin, int epilogue, float power,
+                     float* __restrict__ out0, int n_out_bins) {
+  const int lane = threadIdx.x & 31;
+  const int64_t f = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (f >= m_rows) return;
+  const float* e_hi = a_hi + f * half;
+  const float* e_lo = a_lo + f * half;
+  const float* o_hi = a_hi + (m_rows + f) * half;
+  const float* o_lo = a_lo + (m_rows + f) * half;
+  float re = 0.f, im = 0.f;
+  for (int c = lane; c < half; c += 32) {
+    re = fmaf(__ldg(e_hi + c) + __ldg(e_lo + c), __ldg(wc_row + c), re);
+    im = fmaf(__ldg(o_hi + c) + __ldg(o_lo + c), __ldg(ws_row + c), im);
+  }
+  re = warp_sum(re);
+  im = warp_sum(im);
+  if (lane == 0) {
+    if (p0) re += w0 * __ldg(p0 + f);
+    const int b = (int)(f / n_frames), t = (int)(f - (int64_t)b * n_frames);
+    stft_store(epilogue, power, re, im, out0, ((int64_t)b * n_out_bins + bin) * n_frames + t);
+  }
+}
+
 // ---------------------------------------------------------------- host side
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -415,4 +620,66 @@ extern "C" int rvb_stft_gemm(const float* sig_hi, const float* sig_lo, int n_seg
   stft_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p);
   count_launch();
   return check_launch("stft_gemm_kernel");
+}
+
+extern "C" int rvb_stft_gemm_folded(const float* a_hi, const float* a_lo, int n_seg, int n_frames, int n_fft,
+                                    const float* basis_hi, const float* basis_lo, int n_bins_pad, const float* p0,
+                                    float w0, int epilogue, float power, float* out0, int n_out_bins,
+                                    rvb_stream_t stream) {
+  RVB_REQUIRE(a_hi && a_lo && basis_hi && basis_lo && out0, "rvb_stft_gemm_folded: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_frames > 0, "rvb_stft_gemm_folded: bad shape");
+  RVB_REQUIRE(n_fft % (2 * BLOCK_K) == 0 && n_fft >= 2 * BLOCK_K, "rvb_stft_gemm_folded: n_fft %d must be a multiple of %d",
+              n_fft, 2 * BLOCK_K);
+  RVB_REQUIRE(n_bins_pad % F_BLOCK_N == 0 && n_bins_pad > 0, "rvb_stft_gemm_folded: n_bins_pad %d must be a multiple of %d",
+              n_bins_pad, F_BLOCK_N);
+  RVB_REQUIRE(epilogue >= RVB_EPI_POWER && epilogue <= RVB_EPI_POWER_P, "rvb_stft_gemm_folded: bad epilogue %d", epilogue);
+  RVB_REQUIRE(n_out_bins > 0, "rvb_stft_gemm_folded: n_out_bins must be positive");
+  for (const void* ptr : {(const void*)a_hi, (const void*)a_lo, (const void*)basis_hi, (const void*)basis_lo})
+    RVB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 127u) == 0, "rvb_stft_gemm_folded: operands must be 128-byte aligned");
+  const int half = n_fft / 2;
+  const int64_t m_rows = (int64_t)n_seg * n_frames;
+  RVB_REQUIRE(2 * m_rows < (1ll << 31), "rvb_stft_gemm_folded: too many frames");
+
+  CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+  int rc;
+  if ((rc = make_map_2d(&tm_a_hi, a_hi, half, 2 * m_rows, BLOCK_K, BLOCK_M)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_a_lo, a_lo, half, 2 * m_rows, BLOCK_K, BLOCK_M)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_b_hi, basis_hi, half, 2 * (uint64_t)n_bins_pad, BLOCK_K, F_BLOCK_N)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_b_lo, basis_lo, half, 2 * (uint64_t)n_bins_pad, BLOCK_K, F_BLOCK_N)) != RVB_OK) return rc;
+
+  FoldParams p;
+  p.n_frames = n_frames; p.m_rows = m_rows; p.n_bins_pad = n_bins_pad; p.half = half;
+  p.m_tiles = (int)((m_rows + BLOCK_M - 1) / BLOCK_M);
+  p.n_tiles = n_bins_pad / F_BLOCK_N;
+  p.epilogue = epilogue; p.n_out_bins = n_out_bins;
+  p.n_store_bins = n_out_bins < n_bins_pad ? n_out_bins : n_bins_pad;
+  p.power = power; p.w0 = w0; p.p0 = (w0 != 0.f) ? p0 : nullptr; p.out0 = out0;
+  RVB_REQUIRE(w0 == 0.f || p0 != nullptr, "rvb_stft_gemm_folded: w0 != 0 needs p0");
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
+  const int grid = (int)(n_units < num_sms() ? n_units : num_sms());
+  stft_gemm_fold_kernel<<<grid, NUM_THREADS, F_SMEM_BYTES, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo, tm_b_hi,
+                                                                                      tm_b_lo, p);
+  count_launch();
+  return check_launch("stft_gemm_fold_kernel");
+}
+
+extern "C" int rvb_stft_bin_folded(const float* a_hi, const float* a_lo, int n_seg, int n_frames, int n_fft,
+                                   const float* wc_row, const float* ws_row, const float* p0, float w0, int bin,
+                                   int epilogue, float power, float* out0, int n_out_bins, rvb_stream_t stream) {
+  RVB_REQUIRE(a_hi && a_lo && wc_row && ws_row && out0, "rvb_stft_bin_folded: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_frames > 0 && bin >= 0 && bin < n_out_bins, "rvb_stft_bin_folded: bad shape");
+  RVB_REQUIRE(epilogue >= RVB_EPI_POWER && epilogue <= RVB_EPI_POWER_P, "rvb_stft_bin_folded: bad epilogue %d", epilogue);
+  RVB_REQUIRE(w0 == 0.f || p0 != nullptr, "rvb_stft_bin_folded: w0 != 0 needs p0");
+  const int64_t m_rows = (int64_t)n_seg * n_frames;
+  stft_bin_fold_kernel<<<(unsigned)((m_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      a_hi, a_lo, m_rows, n_frames, n_fft / 2, wc_row, ws_row, (w0 != 0.f) ? p0 : nullptr, w0, bin, epilogue, power,
+      out0, n_out_bins);
+  count_launch();
+  return check_launch("stft_bin_fold_kernel");
 }

@@ -31,7 +31,7 @@ def lib():
 
 def test_header_and_library_agree(lib):
     decls = _declared()
-    assert len(decls) >= 14
+    assert len(decls) >= 17
     out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line and "rvb_" in line}
     assert exported == set(decls), (exported ^ set(decls))

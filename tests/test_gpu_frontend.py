@@ -27,9 +27,41 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.fixture(scope="module")
-def mel(R, dev):
-    return R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+@pytest.fixture(scope="module", params=["folded", "direct"])
+def mel(R, dev, request):
+    """Both contraction kernels: the folded one (symmetric window, default) and the unfolded one."""
+    import os
+    m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    if request.param == "direct":
+        os.environ["RVB_NO_FOLD"] = "1"
+    try:
+        tb = m.stft._device_tables()                          # tables are built here, under the env switch
+    finally:
+        os.environ.pop("RVB_NO_FOLD", None)
+    assert (tb["fold"] is None) == (request.param == "direct")
+    return m
+
+
+def test_fold_split_matches_numpy(R, dev):
+    """e = p[n] + p[N-n], o = p[n] - p[N-n] (hi + lo reconstructs them to 2^-21), p0 = p[0]."""
+    from reconvat_b200 import synth
+    a = torch.from_numpy(synth.to_float(np.stack([synth.white_int16(16385, 1), synth.music_int16(16385, 2)])))
+    xd = a.to(dev)[:, :-1]
+    L, N, hop, T = 16384, 2048, 512, 33
+    planes = torch.full((2, 2, 2 * T, N // 2), float("nan"), device=dev)
+    p0 = torch.empty(2 * T, device=dev)
+    R._lib.call("rvb_fold_split", xd.data_ptr(), xd.stride(0), 2, L, 1024, 0, N, hop, T, planes[0].data_ptr(),
+                planes[1].data_ptr(), p0.data_ptr())
+    p = np.pad(a[:, :-1].numpy().astype(np.float64), [(0, 0), (1024, 1024)], mode="reflect")
+    fr = np.lib.stride_tricks.sliding_window_view(p, N, axis=1)[:, ::hop].reshape(2 * T, N)
+    e = np.empty((2 * T, N // 2)); o = np.zeros((2 * T, N // 2))
+    e[:, :-1] = fr[:, 1:N // 2] + fr[:, N - 1:N // 2:-1]; e[:, -1] = fr[:, N // 2]
+    o[:, :-1] = fr[:, 1:N // 2] - fr[:, N - 1:N // 2:-1]
+    got = planes.cpu().numpy().astype(np.float64)
+    assert np.abs(got[0, 0] + got[1, 0] - e).max() < 2.0 ** -20
+    assert np.abs(got[0, 1] + got[1, 1] - o).max() < 2.0 ** -20
+    assert np.all((planes.cpu().numpy().view(np.uint32) & 0x1FFF) == 0)      # every plane value is a tf32 number
+    assert np.array_equal(p0.cpu().numpy(), fr[:, 0].astype(np.float32))
 
 
 def test_pad_split_bit_exact(R, dev):
@@ -112,11 +144,16 @@ def test_frontend_min_length_and_errors(mel, dev, golden):
     ("win_short", dict(n_fft=512, win_length=400, hop_length=160)),
     ("hamming", dict(n_fft=512, hop_length=128, window="hamming")),
 ])
-def test_stft_formats_golden(R, dev, golden, tag, kw):
+@pytest.mark.parametrize("path", ["auto", "direct"])
+def test_stft_formats_golden(R, dev, golden, tag, kw, path, monkeypatch):
     from reconvat_b200 import synth
     g = golden["stft_formats"]
     a = torch.from_numpy(synth.to_float(g["audio_int16"])).to(dev)
+    if path == "direct":
+        monkeypatch.setenv("RVB_NO_FOLD", "1")
     st = R.Spectrogram.STFT(verbose=False, **kw).to(dev)
+    folded = st._device_tables()["fold"] is not None
+    assert folded == (path == "auto")                          # every golden STFT config has a symmetric basis
     c = st(a, output_format="Complex").cpu().numpy()
     ref = g[tag + "_complex"]
     assert c.shape == ref.shape
@@ -130,6 +167,26 @@ def test_stft_formats_golden(R, dev, golden, tag, kw):
     dphi = np.angle(np.exp(1j * (ph - g[tag + "_phase"])))
     assert np.abs(dphi[strong]).max() < 1e-3
     assert st(a).shape == ref.shape                            # default output_format="Complex"
+
+
+def test_non_symmetric_basis_takes_the_unfolded_kernel(R, dev):
+    """'linear' / 'log' bin scales are not symmetric about n_fft/2: the module must pick the direct kernel."""
+    from oracle import nnaudio_restate as NR
+    from reconvat_b200 import synth
+    a = synth.to_float(np.stack([synth.white_int16(8192, 41), synth.music_int16(8192, 42)]))
+    for fs in ("linear", "log"):
+        kw = dict(n_fft=512, hop_length=128, freq_bins=100, freq_scale=fs, fmin=50, fmax=6000, sr=16000)
+        st = R.Spectrogram.STFT(verbose=False, **kw).to(dev)
+        c = st(torch.from_numpy(a).to(dev), output_format="Complex").cpu().numpy()
+        assert st._device_tables()["fold"] is None
+        ks, kc, _, _, wm = NR.create_fourier_kernels(512, freq_bins=100, freq_scale=fs, fmin=50, fmax=6000, sr=16000,
+                                                     verbose=False)
+        p = np.pad(a.astype(np.float64), [(0, 0), (256, 256)], mode="reflect")
+        fr = np.lib.stride_tricks.sliding_window_view(p, 512, axis=1)[:, ::128]
+        re = np.einsum("btn,kn->bkt", fr, (kc[:, 0] * wm).astype(np.float64))
+        im = np.einsum("btn,kn->bkt", fr, (ks[:, 0] * wm).astype(np.float64))
+        scale = np.abs(re).max()
+        assert np.abs(c[..., 0] - re).max() < 2e-5 * scale and np.abs(c[..., 1] + im).max() < 2e-5 * scale
 
 
 @pytest.mark.parametrize("tag,kw", [

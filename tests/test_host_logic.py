@@ -83,6 +83,27 @@ def test_gemm_operand_layout():
     assert hi.shape == (256, 512) and n_gemm == 100 and left == [] and not hi[100:128].any() and not hi[228:].any()
 
 
+def test_fold_operand_reproduces_the_unfolded_sums():
+    ks, kc, _, _, wm = basis.fourier_basis(512, window="hamming")          # w[0] = 0.08: exercises the p0 term
+    wcos, wsin = kc * wm[None], ks * wm[None]
+    fd = basis.fold_operand(wcos, wsin)
+    assert fd is not None and fd["n_bins_pad"] == 256 and fd["leftover"] == [256] and abs(fd["w0"] - 0.08) < 1e-6
+    rng = np.random.default_rng(0)
+    p = rng.standard_normal(512)
+    e = np.empty(256); o = np.zeros(256)
+    e[:-1] = p[1:256] + p[511:256:-1]; e[-1] = p[256]
+    o[:-1] = p[1:256] - p[511:256:-1]
+    B = fd["basis_hi"].astype(np.float64) + fd["basis_lo"]
+    re, im = B[:256] @ e + fd["w0"] * p[0], B[256:] @ o
+    assert np.abs(re - wcos[:256].astype(np.float64) @ p).max() < 1e-5
+    assert np.abs(im - wsin[:256].astype(np.float64) @ p).max() < 1e-5
+    assert abs(fd["left_cos"][0].astype(np.float64) @ e + fd["w0"] * p[0] - wcos[256].astype(np.float64) @ p) < 1e-5
+    # not symmetric about n_fft/2 -> no fold
+    ks, kc, _, _, wm = basis.fourier_basis(512, freq_bins=100, freq_scale="linear")
+    assert basis.fold_operand(kc * wm[None], ks * wm[None]) is None
+    assert basis.fold_operand(wcos[:, :500], wsin[:, :500]) is None        # n_fft not a multiple of 64
+
+
 def test_module_surface_and_state_dict():
     m = R.Spectrogram.MelSpectrogram(**MEL_KW)
     assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {

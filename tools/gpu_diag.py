@@ -114,6 +114,56 @@ def stage_gemm():
         print("  sample got/ref re[0, :4, :4]:\n", c[0, :4, :4, 0], "\n", re64[0, :4, :4])
 
 
+def stage_bias():
+    """Signed error of the contraction against float64 truth (tensor-core accumulate truncation)."""
+    fo = FrontEndOracle()
+    a = synth.to_float(np.stack([synth.white_int16(16385, 1), synth.music_int16(16385, 2)]))
+    re64, im64 = fo.stft(a[:, :-1].astype(np.float64), np.float64)
+    for label, env in (("folded", None), ("direct", "1")):
+        if env:
+            os.environ["RVB_NO_FOLD"] = env
+        st = R.Spectrogram.STFT(n_fft=2048, hop_length=512, sr=16000, verbose=False).to(dev)
+        c = st(torch.from_numpy(a).to(dev)[:, :-1], output_format="Complex").cpu().numpy().astype(np.float64)
+        os.environ.pop("RVB_NO_FOLD", None)
+        big = np.abs(re64) > 0.1 * np.abs(re64).max()
+        rel = (c[..., 0] - re64)[big] / re64[big]
+        scale = np.abs(re64).max()
+        print("%s: max|err|/scale re %.3e im %.3e ; signed rel err on large bins: mean %.3e  std %.3e"
+              % (label, np.abs(c[..., 0] - re64).max() / scale, np.abs(c[..., 1] + im64).max() / scale, rel.mean(), rel.std()))
+
+
+def stage_weak():
+    """Where does the log-Mel error live?  Error of re/im by magnitude decade, folded vs direct, on a full
+    music-like segment; and the worst log-Mel cell of each path."""
+    fo = FrontEndOracle()
+    a = synth.segments(2, "mixed", seed=3)[1:2]                  # the music-like one
+    re64, im64 = fo.stft(a[:, :-1].astype(np.float64), np.float64)
+    mag = np.sqrt(re64 ** 2 + im64 ** 2)[:, :1024]
+    scale = mag.max()
+    lm64 = fo.log_mel(a[:, :-1].astype(np.float64), np.float64)
+    for label, env in (("folded", None), ("direct", "1")):
+        if env:
+            os.environ["RVB_NO_FOLD"] = env
+        st = R.Spectrogram.STFT(n_fft=2048, hop_length=512, sr=16000, verbose=False).to(dev)
+        mel = R.Spectrogram.MelSpectrogram(sr=16000, win_length=2048, n_mels=229, hop_length=512, fmin=30, fmax=8000,
+                                           verbose=False).to(dev)
+        ad = torch.from_numpy(a).to(dev)
+        c = st(ad[:, :-1], output_format="Complex").cpu().numpy().astype(np.float64)[:, :1024]
+        lm = np.log(mel(ad[:, :-1]).cpu().numpy().astype(np.float64) + 1e-5)
+        os.environ.pop("RVB_NO_FOLD", None)
+        err = np.sqrt((c[..., 0] - re64[:, :1024]) ** 2 + (c[..., 1] + im64[:, :1024]) ** 2)
+        print("-- %s" % label)
+        for lo_, hi_ in ((1e-7, 1e-5), (1e-5, 1e-4), (1e-4, 1e-3), (1e-3, 1e-2), (1e-2, 1e-1), (1e-1, 1.01)):
+            m = (mag >= lo_ * scale) & (mag < hi_ * scale)
+            if m.any():
+                print("   |X|/scale in [%.0e,%.0e): n=%8d  rms err/scale %.2e  max err/scale %.2e  max err/|X| %.2e"
+                      % (lo_, hi_, m.sum(), np.sqrt((err[m] ** 2).mean()) / scale, err[m].max() / scale, (err[m] / mag[m]).max()))
+        e = np.abs(lm - lm64) / np.maximum(np.abs(lm64), 1)
+        b, mm, t = np.unravel_index(e.argmax(), e.shape)
+        print("   worst log-Mel cell: band %d frame %d  err %.3e  value %.4f (truth %.4f)" % (mm, t, e.max(), lm[b, mm, t], lm64[b, mm, t]))
+        print("   log-Mel err percentiles 50/99/99.9/max: %s" % np.percentile(e, [50, 99, 99.9, 100]))
+
+
 def stage_frontend():
     fo = FrontEndOracle()
     a = synth.segments(2, "mixed", seed=3)
@@ -148,7 +198,7 @@ def stage_timing():
 
 
 if __name__ == "__main__":
-    stages = sys.argv[1:] or ["vat", "pad", "mel", "gemm", "frontend", "timing"]
+    stages = sys.argv[1:] or ["vat", "pad", "mel", "gemm", "bias", "frontend", "timing"]
     for s in stages:
         print("==== %s ====" % s, flush=True)
         try:
