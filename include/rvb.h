@@ -66,6 +66,8 @@ int rvb_pad_split(const float* audio, int64_t audio_ld, int n_seg, int n_samples
 #define RVB_EPI_COMPLEX 2   /* (re, -im)             out0[b][k][t][2]  (:234) */
 #define RVB_EPI_PHASE 3     /* atan2(-im + 0.0, re)  out0[b][k][t]     (:237) */
 #define RVB_EPI_POWER_P 4   /* sqrt(re^2+im^2)^power out0[b][k][t]     (general `power`, :458) */
+/* OR-ed onto a single-float epilogue: write out0[b][t][k] (time-major, what rvb_mel_project reads) */
+#define RVB_EPI_TIME_MAJOR 0x10
 
 /*
  * K1  STFT as a dense contraction on tcgen05 tensor cores, 3xTF32 (hi*hi + hi*lo + lo*hi, fp32
@@ -133,17 +135,19 @@ int rvb_stft_bin(const float* sig_hi, const float* sig_lo, int n_seg, int rows_p
 /*
  * K2  banded Mel projection (+ optional log compression and per-segment min/max).
  * Replaces: `torch.matmul(self.mel_basis, spec)` (model/Spectrogram.py:460),
- * `torch.log(spec + 1e-5)` (model/self_attention_VAT.py:1102) and the two reductions of
- * Normalization('imagewise') (model/utils.py:96-97).
- * The filterbank is passed in banded form: bin k feeds band band0[k] with weight w0[k] and band
- * band0[k]+1 with weight w1[k] (triangular filters overlap pairwise; band0 non-decreasing in k).
- *   power     [n_seg][n_bins][n_frames]
+ * `torch.log(spec + 1e-5)` (model/self_attention_VAT.py:1102), the two reductions of
+ * Normalization('imagewise') (model/utils.py:96-97) and, with RVB_LAYOUT_TIME_MAJOR, the
+ * `.transpose(-1,-2)` (model/self_attention_VAT.py:1104).
+ * The filterbank is passed by rows: band m reads bins [band_lo[m], band_lo[m] + band_len[m]) with weights
+ * band_w[j][m], j < band_len[m] (band_w is [max_len][n_mels], band fastest): any filterbank whose rows have
+ * contiguous support.
+ *   power     [n_seg * n_frames][n_bins], time-major (RVB_EPI_TIME_MAJOR epilogue of the contraction)
  *   log_offset < 0: no log;  >= 0: out = logf(mel + log_offset)
  *   minmax    NULL, or uint32 [n_seg][2] receiving order-preserving keys of (min, max) of `out`
  *             per segment (decoded by rvb_normalise); the call zeroes it first.
  */
-int rvb_mel_project(const float* power, int n_seg, int n_bins, int n_frames, const int32_t* band0,
-                    const float* w0, const float* w1, int k_begin, int k_end, int n_mels, float log_offset,
+int rvb_mel_project(const float* power, int n_seg, int n_frames, int n_bins, const int32_t* band_lo,
+                    const int32_t* band_len, const float* band_w, int max_len, int n_mels, float log_offset,
                     int layout, float* out, uint32_t* minmax, rvb_stream_t stream);
 
 /*

@@ -249,18 +249,20 @@ class MelSpectrogram(nn.Module):
     def _band_tables(self):
         key = (self.mel_basis.device, self.mel_basis._version, self.mel_basis.data_ptr())
         if self._bands is None or self._bands_key != key:
-            band0, w0, w1, k_begin, k_end = basis.banded_filterbank(self.mel_basis.detach().cpu().numpy())
+            lo, ln, w, k_end = basis.band_rows(self.mel_basis.detach().cpu().numpy())
             dev = self.mel_basis.device
-            self._bands = dict(band0=torch.from_numpy(band0).to(dev), w0=torch.from_numpy(w0).to(dev),
-                               w1=torch.from_numpy(w1).to(dev), k_begin=k_begin, k_end=k_end)
+            self._bands = dict(lo=torch.from_numpy(lo).to(dev), len=torch.from_numpy(ln).to(dev),
+                               w=torch.from_numpy(w).to(dev), max_len=w.shape[0], k_end=k_end)
             self._bands_key = key
         return self._bands
 
     def _power_spectrogram(self, x):
-        """(B,1,L) -> power (B, n_pow_bins, T) holding (sqrt(re^2+im^2))**power for every bin the
+        """(B,1,L) -> power (B, T, n_pow_bins), time-major, holding (sqrt(re^2+im^2))**power for every bin the
         filterbank reads (model/Spectrogram.py:458)."""
         bands = self._band_tables()
-        n_pow_bins = bands["k_end"]                          # bins >= k_end carry zero weight: never stored
+        n_pow_bins = -(-bands["k_end"] // 4) * 4             # bins >= k_end carry zero weight; pad to 16 bytes
+        if n_pow_bins > self.mel_basis.shape[1]:
+            n_pow_bins = bands["k_end"]
         if float(self.power) == 2.0:
             epi = _lib.EPI_POWER
         elif float(self.power) == 1.0:
@@ -269,19 +271,21 @@ class MelSpectrogram(nn.Module):
             epi = _lib.EPI_POWER_P
         dev = x.device
         power, n_frames = self.stft._spectrum(
-            x, epi, self.power,
-            lambda B, T: (torch.empty((B, n_pow_bins, T), dtype=torch.float32, device=dev), n_pow_bins))
+            x, epi | _lib.EPI_TIME_MAJOR, self.power,
+            lambda B, T: (torch.empty((B, T, n_pow_bins), dtype=torch.float32, device=dev), n_pow_bins))
         return power, n_frames, bands
+
+    def _project(self, power, n_frames, bands, log_offset, layout, out, minmax):
+        B, _, n_pow_bins = power.shape
+        _lib.call("rvb_mel_project", power.data_ptr(), B, n_frames, n_pow_bins, bands["lo"].data_ptr(),
+                  bands["len"].data_ptr(), bands["w"].data_ptr(), bands["max_len"], self.mel_basis.shape[0],
+                  float(log_offset), layout, out.data_ptr(), None if minmax is None else minmax.data_ptr())
 
     def forward(self, x):
         x = basis.broadcast_dim(x)
         power, n_frames, bands = self._power_spectrogram(x)
-        B, n_pow_bins, _ = power.shape
-        n_mels = self.mel_basis.shape[0]
-        out = torch.empty((B, n_mels, n_frames), dtype=torch.float32, device=x.device)
-        _lib.call("rvb_mel_project", power.data_ptr(), B, n_pow_bins, n_frames, bands["band0"].data_ptr(),
-                  bands["w0"].data_ptr(), bands["w1"].data_ptr(), bands["k_begin"], bands["k_end"], n_mels,
-                  -1.0, _lib.LAYOUT_BINS_MAJOR, out.data_ptr(), None)
+        out = torch.empty((power.shape[0], self.mel_basis.shape[0], n_frames), dtype=torch.float32, device=x.device)
+        self._project(power, n_frames, bands, -1.0, _lib.LAYOUT_BINS_MAJOR, out, None)
         return out
 
     def normalised_log_mel(self, audio, trim_last=True, log_offset=1e-5, channel_dim=True, normalise=True,
@@ -298,14 +302,10 @@ class MelSpectrogram(nn.Module):
         if trim_last:
             x = x[:, :, :-1]                                  # a view; the kernel takes the row stride
         power, n_frames, bands = self._power_spectrogram(x)
-        B, n_pow_bins, _ = power.shape
-        n_mels = self.mel_basis.shape[0]
+        B, n_mels = power.shape[0], self.mel_basis.shape[0]
         out = torch.empty((B, n_frames, n_mels), dtype=torch.float32, device=x.device)
         minmax = torch.empty((B, 2), dtype=torch.int32, device=x.device) if normalise else None
-        _lib.call("rvb_mel_project", power.data_ptr(), B, n_pow_bins, n_frames, bands["band0"].data_ptr(),
-                  bands["w0"].data_ptr(), bands["w1"].data_ptr(), bands["k_begin"], bands["k_end"], n_mels,
-                  float(log_offset), _lib.LAYOUT_TIME_MAJOR, out.data_ptr(),
-                  minmax.data_ptr() if normalise else None)
+        self._project(power, n_frames, bands, log_offset, _lib.LAYOUT_TIME_MAJOR, out, minmax)
         if normalise:
             _lib.call("rvb_normalise", out.data_ptr(), out.data_ptr(), B, n_frames * n_mels, minmax.data_ptr())
         out = out.unsqueeze(1) if channel_dim else out

@@ -23,7 +23,7 @@ SIGNATURES = {
     "rvb_stft_gemm_folded": [_c_p, _c_p, _i32, _i32, _i32, _c_p, _c_p, _i32, _c_p, _f32, _i32, _f32, _c_p, _i32, _c_p],
     "rvb_stft_bin_folded": [_c_p, _c_p, _i32, _i32, _i32, _c_p, _c_p, _c_p, _f32, _i32, _i32, _f32, _c_p, _i32, _c_p],
     "rvb_stft_bin": [_c_p, _c_p, _i32, _i32, _i32, _i32, _c_p, _c_p, _i32, _i32, _i32, _f32, _c_p, _i32, _c_p],
-    "rvb_mel_project": [_c_p, _i32, _i32, _i32, _c_p, _c_p, _c_p, _i32, _i32, _i32, _f32, _i32, _c_p, _c_p, _c_p],
+    "rvb_mel_project": [_c_p, _i32, _i32, _i32, _c_p, _c_p, _c_p, _i32, _i32, _f32, _i32, _c_p, _c_p, _c_p],
     "rvb_minmax": [_c_p, _i32, _i64, _c_p, _c_p],
     "rvb_normalise": [_c_p, _c_p, _i32, _i64, _c_p, _c_p],
     "rvb_vat_perturb": [_c_p, _c_p, _c_p, _i64, _i32, _f32, _i32, _c_p],
@@ -37,6 +37,7 @@ BCE_WORKSPACE_FLOATS = 1032
 
 PAD_REFLECT, PAD_CONSTANT, PAD_NONE = 0, 1, 2
 EPI_POWER, EPI_MAGNITUDE, EPI_COMPLEX, EPI_PHASE, EPI_POWER_P = 0, 1, 2, 3, 4
+EPI_TIME_MAJOR = 0x10
 LAYOUT_BINS_MAJOR, LAYOUT_TIME_MAJOR = 0, 1
 
 _lib = None

@@ -145,6 +145,33 @@ def banded_filterbank(mel_basis):
     return band0, w0, w1, k_begin, k_end
 
 
+def band_rows(mel_basis, max_len=256):
+    """Dense (n_mels, F) -> (band_lo int32[n_mels], band_len int32[n_mels], band_w f32[L, n_mels], k_end).
+
+    Row m reads bins [band_lo[m], band_lo[m] + band_len[m]) with weights band_w[:band_len[m], m] (interior zeros
+    are kept as zero weights; the table is stored support-position-major so that a warp of bands reads it
+    coalesced).  Raises ValueError when a row's support is wider than ``max_len`` bins, e.g. a trained dense
+    ``mel_basis`` -- that is not a banded filterbank and the fused Mel kernel would crawl on it."""
+    mb = np.asarray(mel_basis, dtype=np.float32)
+    n_mels, F = mb.shape
+    lo = np.zeros(n_mels, np.int32)
+    ln = np.zeros(n_mels, np.int32)
+    for m in range(n_mels):
+        nz = np.flatnonzero(mb[m])
+        if len(nz):
+            lo[m], ln[m] = nz[0], nz[-1] - nz[0] + 1
+    L = int(ln.max())
+    if L == 0:
+        raise ValueError("mel_basis is all zero")
+    if L > max_len:
+        raise ValueError("mel_basis row support of %d bins exceeds %d: not a banded filterbank; the fused Mel "
+                         "kernel cannot represent it" % (L, max_len))
+    w = np.zeros((L, n_mels), np.float32)
+    for m in range(n_mels):
+        w[:ln[m], m] = mb[m, lo[m]:lo[m] + ln[m]]
+    return lo, ln, w, int((lo + ln).max())
+
+
 # ---------------------------------------------------------------- tf32 operand planes
 def tf32_round(x):
     """Round-to-nearest (ties away) fp32 -> tf32, identical to PTX cvt.rna.tf32.f32 for finite values."""

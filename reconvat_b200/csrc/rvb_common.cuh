@@ -33,6 +33,12 @@ int check_launch(const char* what);           // cudaGetLastError -> RVB_ERR_LAU
     }                                                                                    \
   } while (0)
 
+inline bool epilogue_ok(int e) {
+  const int epi = e & 0xf;
+  return (e & ~(0xf | RVB_EPI_TIME_MAJOR)) == 0 && epi >= RVB_EPI_POWER && epi <= RVB_EPI_POWER_P &&
+         !((e & RVB_EPI_TIME_MAJOR) && epi == RVB_EPI_COMPLEX);
+}
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -74,20 +80,52 @@ __device__ __forceinline__ float to_tf32(float v) {
   return __uint_as_float(r);
 }
 
-// ---- STFT output formats, shared by the tcgen05 contraction and the single-bin kernel ----
+// ---- STFT output formats, shared by the tcgen05 contractions and the single-bin kernels ----
+// Single-float formats (power / magnitude / phase / power_p) may carry RVB_EPI_TIME_MAJOR:
+//   bin-major  out0[(b*n_out_bins + k)*T + t]      what STFT.forward returns
+//   time-major out0[(b*T + t)*n_out_bins + k]      what the Mel kernel reads (16-byte stores per thread)
+__device__ __forceinline__ float stft_value(int epi, float power, float re, float im) {
+  if (epi == RVB_EPI_PHASE) return atan2f(-im + 0.0f, re);             // Spectrogram.py:237
+  float mag = sqrtf(re * re + im * im);                                 // Spectrogram.py:227,231
+  if (epi == RVB_EPI_POWER) mag = mag * mag;                            // **2.0 (Spectrogram.py:458)
+  else if (epi == RVB_EPI_POWER_P) mag = powf(mag, power);
+  return mag;
+}
 __device__ __forceinline__ void stft_store(int epilogue, float power, float re, float im, float* __restrict__ out0,
-                                           int64_t idx /* (b*n_out_bins + k)*T + t */) {
-  if (epilogue == RVB_EPI_COMPLEX) {
-    reinterpret_cast<float2*>(out0)[idx] = make_float2(re, -im);        // Spectrogram.py:234
-  } else if (epilogue == RVB_EPI_PHASE) {
-    out0[idx] = atan2f(-im + 0.0f, re);                                 // Spectrogram.py:237
+                                           int b, int k, int t, int n_out_bins, int n_frames) {
+  const int epi = epilogue & 0xf;
+  if (epi == RVB_EPI_COMPLEX) {
+    reinterpret_cast<float2*>(out0)[((int64_t)b * n_out_bins + k) * n_frames + t] = make_float2(re, -im);   // :234
+  } else if (epilogue & RVB_EPI_TIME_MAJOR) {
+    out0[((int64_t)b * n_frames + t) * n_out_bins + k] = stft_value(epi, power, re, im);
   } else {
-    float mag = sqrtf(re * re + im * im);                               // Spectrogram.py:227,231
-    if (epilogue == RVB_EPI_POWER) mag = mag * mag;                     // **2.0 (Spectrogram.py:458)
-    else if (epilogue == RVB_EPI_POWER_P) mag = powf(mag, power);
-    out0[idx] = mag;
+    out0[((int64_t)b * n_out_bins + k) * n_frames + t] = stft_value(epi, power, re, im);
   }
 }
 
+// Epilogue of one accumulator chunk: 32 consecutive bins [k0, k0+32) of frame (b, t) held by one thread.
+__device__ __forceinline__ void stft_store_chunk(int epilogue, float power, const uint32_t (&re)[32],
+                                                 const uint32_t (&im)[32], float re_add, float* __restrict__ out0, int b,
+                                                 int k0, int t, int n_out_bins, int n_store_bins, int n_frames) {
+  const int epi = epilogue & 0xf;
+  if ((epilogue & RVB_EPI_TIME_MAJOR) && epi != RVB_EPI_COMPLEX && k0 + 32 <= n_store_bins && (n_out_bins & 3) == 0) {
+    float4* dst = reinterpret_cast<float4*>(out0 + ((int64_t)b * n_frames + t) * n_out_bins + k0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 v;
+      v.x = stft_value(epi, power, __uint_as_float(re[4 * i + 0]) + re_add, __uint_as_float(im[4 * i + 0]));
+      v.y = stft_value(epi, power, __uint_as_float(re[4 * i + 1]) + re_add, __uint_as_float(im[4 * i + 1]));
+      v.z = stft_value(epi, power, __uint_as_float(re[4 * i + 2]) + re_add, __uint_as_float(im[4 * i + 2]));
+      v.w = stft_value(epi, power, __uint_as_float(re[4 * i + 3]) + re_add, __uint_as_float(im[4 * i + 3]));
+      dst[i] = v;
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (k0 + i < n_store_bins)
+      stft_store(epilogue, power, __uint_as_float(re[i]) + re_add, __uint_as_float(im[i]), out0, b, k0 + i, t, n_out_bins,
+                 n_frames);
+}
 
 }  // namespace rvb

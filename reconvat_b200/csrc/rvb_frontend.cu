@@ -59,49 +59,70 @@ pad_split_kernel(const float* __restrict__ audio, int64_t audio_ld, int n_sample
 }
 
 // ------------------------------------------------------------------ K0f
-// One block per frame (grid-stride): the frame's n_fft samples are staged in smem with coalesced,
-// reflect-aware loads, then thread i produces columns i, i+256, ... of the e and o planes (coalesced 4-byte
-// stores, conflict-free smem reads).  Each audio sample is read by the 4 frames that overlap it: L2 hits.
-__device__ __forceinline__ void split_sum(float a, float b, float& hi, float& lo) {
-  const float s = a + b;
-  const float bb = s - a;
-  const float err = (a - (s - bb)) + (b - bb);            // TwoSum: a + b == s + err exactly
-  hi = to_tf32(s);
-  lo = to_tf32((s - hi) + err);
+// One block per frame (grid-stride).  The frame's n_fft samples are staged in smem (float4 loads for
+// interior frames, reflect-aware scalar loads at the segment edges), shifted by 3 floats so that the forward
+// run p[c+1 .. c+4] of a 4-column group is one aligned LDS.128.  Each thread then emits 4 consecutive columns
+// of the e and o planes as 16-byte stores.  Each audio sample is read by the 4 frames that overlap it: L2 hits.
+// The fp32 add/sub rounds at 2^-24, below the 2^-22 of the tf32 split (and exact for int16-derived audio).
+__device__ __forceinline__ void split2(float v, float& hi, float& lo) {
+  hi = to_tf32(v);
+  lo = to_tf32(v - hi);
 }
 
 __global__ void __launch_bounds__(256)
 fold_split_kernel(const float* __restrict__ audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int mode,
                   int n_fft, int hop, int n_frames, float* __restrict__ a_hi, float* __restrict__ a_lo,
                   float* __restrict__ p0) {
-  extern __shared__ float frame[];                         // n_fft floats
+  extern __shared__ __align__(16) float frame_s[];         // frame_s[i + 3] = p[i], i in [0, n_fft)
+  float* frame = frame_s + 3;
   const int half = n_fft >> 1;
   const int64_t n_rows = (int64_t)n_seg * n_frames;
   const int64_t padded = (mode == RVB_PAD_NONE) ? n_samples : (int64_t)n_samples + 2 * pad;
+  const int off = (mode == RVB_PAD_NONE) ? 0 : pad;
   for (int64_t f = blockIdx.x; f < n_rows; f += gridDim.x) {
     const int b = (int)(f / n_frames), t = (int)(f - (int64_t)b * n_frames);
     const float* a = audio + (int64_t)b * audio_ld;
-    const int64_t start = (int64_t)t * hop;
+    const int64_t start = (int64_t)t * hop;                // index of p[0] in the padded signal
+    const int64_t j0 = start - off;                        // ... and in the audio row
     __syncthreads();                                       // previous iteration's readers are done
-    for (int i = threadIdx.x; i < n_fft; i += blockDim.x) {
-      const int64_t pi = start + i;
-      frame[i] = (pi < padded) ? padded_sample(a, pi, n_samples, pad, mode) : 0.f;
+    const bool interior = j0 >= 0 && j0 + n_fft <= n_samples && ((j0 & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(a) & 15u) == 0);
+    if (interior) {
+      const float4* src = reinterpret_cast<const float4*>(a + j0);
+      for (int i = threadIdx.x; i < (n_fft >> 2); i += blockDim.x) {
+        const float4 v = __ldg(src + i);
+        frame[4 * i + 0] = v.x; frame[4 * i + 1] = v.y; frame[4 * i + 2] = v.z; frame[4 * i + 3] = v.w;
+      }
+    } else {
+      for (int i = threadIdx.x; i < n_fft; i += blockDim.x) {
+        const int64_t pi = start + i;
+        frame[i] = (pi < padded) ? padded_sample(a, pi, n_samples, pad, mode) : 0.f;
+      }
     }
     __syncthreads();
-    float* e_hi = a_hi + f * half;
-    float* e_lo = a_lo + f * half;
-    float* o_hi = a_hi + (n_rows + f) * half;
-    float* o_lo = a_lo + (n_rows + f) * half;
-    for (int c = threadIdx.x; c < half; c += blockDim.x) {
-      const int n = c + 1;
-      const float x = frame[n];
-      const float y = (n < half) ? frame[n_fft - n] : 0.f;  // n == n_fft/2 pairs with itself: e = p, o = 0
-      float h, l;
-      split_sum(x, y, h, l);
-      e_hi[c] = h; e_lo[c] = l;
-      split_sum(x, -y, h, l);
-      if (n == half) { h = 0.f; l = 0.f; }
-      o_hi[c] = h; o_lo[c] = l;
+    float4* e_hi = reinterpret_cast<float4*>(a_hi + f * half);
+    float4* e_lo = reinterpret_cast<float4*>(a_lo + f * half);
+    float4* o_hi = reinterpret_cast<float4*>(a_hi + (n_rows + f) * half);
+    float4* o_lo = reinterpret_cast<float4*>(a_lo + (n_rows + f) * half);
+    for (int q = threadIdx.x; q < (half >> 2); q += blockDim.x) {
+      const int c = q << 2;                                // columns c .. c+3  <->  n = c+1 .. c+4
+      const float4 x = *reinterpret_cast<const float4*>(frame_s + c + 4);        // p[c+1 .. c+4]
+      float y[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] = frame[n_fft - (c + 1 + i)];              // p[N-n]
+      if (c + 4 == half) y[3] = 0.f;                       // n == N/2 pairs with itself: e = p, o = 0
+      const float xs[4] = {x.x, x.y, x.z, x.w};
+      float eh[4], el[4], oh[4], ol[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        split2(xs[i] + y[i], eh[i], el[i]);
+        split2(xs[i] - y[i], oh[i], ol[i]);
+      }
+      if (c + 4 == half) { oh[3] = 0.f; ol[3] = 0.f; }
+      e_hi[q] = make_float4(eh[0], eh[1], eh[2], eh[3]);
+      e_lo[q] = make_float4(el[0], el[1], el[2], el[3]);
+      o_hi[q] = make_float4(oh[0], oh[1], oh[2], oh[3]);
+      o_lo[q] = make_float4(ol[0], ol[1], ol[2], ol[3]);
     }
     if (p0 && threadIdx.x == 0) p0[f] = frame[0];
   }
@@ -126,141 +147,100 @@ stft_bin_kernel(const float* __restrict__ sig_hi, const float* __restrict__ sig_
   }
   re = warp_sum(re);
   im = warp_sum(im);
-  if (lane == 0) stft_store(epilogue, power, re, im, out0, ((int64_t)b * n_out_bins + bin) * n_frames + t);
+  if (lane == 0) stft_store(epilogue, power, re, im, out0, b, bin, t, n_out_bins, n_frames);
 }
 
 // ------------------------------------------------------------------ K2
-// Block = 32 consecutive frames of one segment x all bins.  Warp w walks bin chunk w in increasing k;
-// lane <-> frame, so every load is one coalesced 128-byte line of power[b][k][t0..t0+31].
-// Two rotating register accumulators follow the (band0, band0+1) pair of the current bin.  A finished
-// band goes to the smem tile with a plain store, except the first two bands a warp finishes: those may
-// be shared with the previous chunk and are parked in a per-warp edge slot; warp 0 folds the edge
-// slots into the tile in fixed order afterwards (no atomics, bit-reproducible).  The tile is then
-// log-compressed, min/max-reduced and written in either layout with coalesced stores.
-constexpr int kMelWarps = 8;
-constexpr int kMelFrames = 32;
+// Input: power[frame][bin] time-major (the GEMM epilogue writes it that way with 16-byte stores).
+// Block = kMelFR consecutive frames of one segment: their rows (kMelFR x n_bins floats, contiguous in HBM)
+// are staged in smem with coalesced float4 loads; then thread <-> Mel band: it holds its band's weights in
+// registers and walks its contiguous bin support in the smem rows (loop bound = longest support in the
+// warp, so low-frequency warps finish in a few steps).  Output is coalesced in the time-major layout
+// (thread <-> band) and sector-complete in the bin-major one.  log and the per-segment min/max keys are fused.
+constexpr int kMelFR = 8;
+constexpr int kMelThreads = 256;
 
-struct MelEmit {
-  float* tile;        // [n_mels][33]
-  float* edge;        // [2][32] of this warp
-  int* edge_band;     // [2] of this warp
-  int n_emit, n_mels, lane, warp;
-  __device__ __forceinline__ void operator()(int band, float v) {
-    if (band >= n_mels) return;
-    if (warp > 0 && n_emit < 2) {
-      edge[n_emit * 32 + lane] = v;
-      if (lane == 0) edge_band[n_emit] = band;
-    } else {
-      tile[band * 33 + lane] = v;
-    }
-    ++n_emit;
-  }
-};
-
-__global__ void __launch_bounds__(kMelWarps* kWarp)
-mel_project_kernel(const float* __restrict__ power, int n_bins, int n_frames, const int32_t* __restrict__ band0,
-                   const float* __restrict__ w0, const float* __restrict__ w1, int k_begin, int k_end, int n_mels,
+__global__ void __launch_bounds__(kMelThreads)
+mel_project_kernel(const float* __restrict__ power, int n_frames, int n_bins, const int32_t* __restrict__ band_lo,
+                   const int32_t* __restrict__ band_len, const float* __restrict__ band_w, int max_len, int n_mels,
                    float log_offset, int layout, float* __restrict__ out, uint32_t* __restrict__ minmax) {
-  extern __shared__ float smem[];
-  float* tile = smem;                                   // [n_mels][33]
-  __shared__ float edge[kMelWarps][2][32];
-  __shared__ int edge_band[kMelWarps][2];
+  extern __shared__ __align__(16) float rows[];            // [kMelFR][n_bins]
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * kMelFrames;
+  const int t0 = blockIdx.x * kMelFR;
+  const int nfr = min(kMelFR, n_frames - t0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < n_mels * 33; i += blockDim.x) tile[i] = 0.f;
-  if (threadIdx.x < kMelWarps * 2) edge_band[threadIdx.x >> 1][threadIdx.x & 1] = -1;
-  __syncthreads();
-
-  const int nk = k_end - k_begin;
-  const int chunk = (nk + kMelWarps - 1) / kMelWarps;
-  const int ks = k_begin + warp * chunk;
-  const int ke = min(ks + chunk, k_end);
-  const int t = t0 + lane;
-  const bool tv = t < n_frames;
-  const float* src = power + ((int64_t)b * n_bins) * n_frames + (tv ? t : 0);
-
-  if (ks < ke) {
-    MelEmit emit{tile, &edge[warp][0][0], &edge_band[warp][0], 0, n_mels, lane, warp};
-    float acc_a = 0.f, acc_b = 0.f;
-    int cur = __ldg(band0 + ks);
-    constexpr int U = 8;
-    for (int k = ks; k < ke; k += U) {
-      float pv[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) pv[u] = (tv && k + u < ke) ? __ldg(src + (int64_t)(k + u) * n_frames) : 0.f;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (k + u < ke) {
-          const int j = __ldg(band0 + k + u);
-          if (j != cur) {                                 // warp-uniform
-            emit(cur, acc_a);
-            if (j == cur + 1) {
-              acc_a = acc_b;
-            } else {
-              emit(cur + 1, acc_b);
-              acc_a = 0.f;
-            }
-            acc_b = 0.f;
-            cur = j;
-          }
-          acc_a = fmaf(__ldg(w0 + k + u), pv[u], acc_a);
-          acc_b = fmaf(__ldg(w1 + k + u), pv[u], acc_b);
-        }
-      }
-    }
-    emit(cur, acc_a);
-    emit(cur + 1, acc_b);
-  }
-  __syncthreads();
-  if (warp == 0) {
-    for (int w = 1; w < kMelWarps; ++w)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int band = edge_band[w][e];
-        if (band >= 0) tile[band * 33 + lane] += edge[w][e][lane];
-      }
+  const float* src = power + ((int64_t)b * n_frames + t0) * n_bins;
+  const int n_val = nfr * n_bins;
+  if ((n_bins & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(rows);
+    for (int i = threadIdx.x; i < (n_val >> 2); i += kMelThreads) d4[i] = __ldg(s4 + i);
+  } else {
+    for (int i = threadIdx.x; i < n_val; i += kMelThreads) rows[i] = __ldg(src + i);
   }
   __syncthreads();
 
   float vmax = -INFINITY, vmin = INFINITY;
   bool seen_nan = false;
-  const int nt = min(kMelFrames, n_frames - t0);
-  if (layout == RVB_LAYOUT_TIME_MAJOR) {
-    // out[b][t][m]: consecutive threads -> consecutive m of one frame (contiguous n_mels floats)
-    float* dst = out + ((int64_t)b * n_frames + t0) * n_mels;
-    for (int i = threadIdx.x; i < nt * n_mels; i += blockDim.x) {
-      const int tt = i / n_mels, m = i - tt * n_mels;
-      float v = tile[m * 33 + tt];
-      if (log_offset >= 0.f) v = logf(v + log_offset);
-      dst[i] = v;
-      vmax = fmaxf(vmax, v); vmin = fminf(vmin, v); seen_nan |= isnan(v);
+  for (int m0 = 0; m0 < n_mels; m0 += kMelThreads) {
+    const int m = m0 + threadIdx.x;
+    const bool m_ok = m < n_mels;
+    const int lo = m_ok ? __ldg(band_lo + m) : 0;
+    const int len = m_ok ? __ldg(band_len + m) : 0;
+    int wlen = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wlen = max(wlen, __shfl_xor_sync(kFull, wlen, o));
+    float acc[kMelFR];
+#pragma unroll
+    for (int fr = 0; fr < kMelFR; ++fr) acc[fr] = 0.f;
+    const float* base = rows + lo;
+    const float* wcol = band_w + (m_ok ? m : 0);           // weights are stored [j][band]: coalesced, L1-resident
+    for (int j = 0; j < wlen; ++j) {                       // warp-uniform bound = longest support in the warp
+      const bool in = j < len;
+      const float w = in ? __ldg(wcol + (int64_t)j * n_mels) : 0.f;
+      const int jj = in ? j : 0;                           // stay inside the row; the weight is 0 there
+#pragma unroll
+      for (int fr = 0; fr < kMelFR; ++fr) acc[fr] = fmaf(w, base[fr * n_bins + jj], acc[fr]);
     }
-  } else {
-    // out[b][m][t]: consecutive threads -> consecutive t of one band
-    for (int i = threadIdx.x; i < n_mels * kMelFrames; i += blockDim.x) {
-      const int m = i >> 5, tt = i & 31;
-      if (tt < nt) {
-        float v = tile[m * 33 + tt];
-        if (log_offset >= 0.f) v = logf(v + log_offset);
-        out[((int64_t)b * n_mels + m) * n_frames + t0 + tt] = v;
-        vmax = fmaxf(vmax, v); vmin = fminf(vmin, v); seen_nan |= isnan(v);
+    if (m_ok) {
+#pragma unroll
+      for (int fr = 0; fr < kMelFR; ++fr) {
+        if (fr < nfr) {
+          float v = acc[fr];
+          if (log_offset >= 0.f) v = logf(v + log_offset);
+          acc[fr] = v;
+          vmax = fmaxf(vmax, v); vmin = fminf(vmin, v); seen_nan |= isnan(v);
+        }
+      }
+      if (layout == RVB_LAYOUT_TIME_MAJOR) {
+        float* dst = out + ((int64_t)b * n_frames + t0) * n_mels + m;
+#pragma unroll
+        for (int fr = 0; fr < kMelFR; ++fr)
+          if (fr < nfr) dst[(int64_t)fr * n_mels] = acc[fr];
+      } else {
+        float* dst = out + ((int64_t)b * n_mels + m) * n_frames + t0;
+        if (nfr == kMelFR && (n_frames & 3) == 0) {
+          reinterpret_cast<float4*>(dst)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          reinterpret_cast<float4*>(dst)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        } else {
+#pragma unroll
+          for (int fr = 0; fr < kMelFR; ++fr)
+            if (fr < nfr) dst[fr] = acc[fr];
+        }
       }
     }
   }
   if (minmax) {
     // torch.max / torch.min propagate NaN: encode it as the largest key on both sides.
-    unsigned kmax = seen_nan ? 0xffffffffu : f2key(vmax);
-    unsigned kmin = seen_nan ? 0xffffffffu : f2key(-vmin);
-    kmax = warp_max_u32(kmax);
-    kmin = warp_max_u32(kmin);
-    __shared__ unsigned red[2][kMelWarps];
+    unsigned kmax = warp_max_u32(seen_nan ? 0xffffffffu : f2key(vmax));
+    unsigned kmin = warp_max_u32(seen_nan ? 0xffffffffu : f2key(-vmin));
+    __shared__ unsigned red[2][kMelThreads / 32];
     if (lane == 0) { red[0][warp] = kmin; red[1][warp] = kmax; }
     __syncthreads();
     if (threadIdx.x < 2) {
       unsigned k = 0;
 #pragma unroll
-      for (int w = 0; w < kMelWarps; ++w) k = max(k, red[threadIdx.x][w]);
+      for (int w2 = 0; w2 < kMelThreads / 32; ++w2) k = max(k, red[threadIdx.x][w2]);
       atomicMax(minmax + 2 * b + threadIdx.x, k);
     }
   }
@@ -359,6 +339,8 @@ extern "C" int rvb_fold_split(const float* audio, int64_t audio_ld, int n_seg, i
                               int n_fft, int hop, int n_frames, float* a_hi, float* a_lo, float* p0,
                               rvb_stream_t stream) {
   RVB_REQUIRE(audio && a_hi && a_lo, "rvb_fold_split: null pointer");
+  RVB_REQUIRE((reinterpret_cast<uintptr_t>(a_hi) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a_lo) & 15u) == 0,
+              "rvb_fold_split: planes must be 16-byte aligned");
   RVB_REQUIRE(n_seg > 0 && n_samples > 0 && hop > 0 && n_frames > 0, "rvb_fold_split: bad shape");
   RVB_REQUIRE(n_fft >= 64 && n_fft % 64 == 0 && n_fft <= 32768, "rvb_fold_split: n_fft %d must be a multiple of 64", n_fft);
   RVB_REQUIRE(pad_mode >= RVB_PAD_REFLECT && pad_mode <= RVB_PAD_NONE, "rvb_fold_split: bad pad_mode %d", pad_mode);
@@ -368,7 +350,7 @@ extern "C" int rvb_fold_split(const float* audio, int64_t audio_ld, int n_seg, i
   RVB_REQUIRE((int64_t)(n_frames - 1) * hop + n_fft <= padded, "rvb_fold_split: %d frames do not fit %lld samples",
               n_frames, (long long)padded);
   const int64_t n_rows = (int64_t)n_seg * n_frames;
-  const size_t smem = (size_t)n_fft * sizeof(float);
+  const size_t smem = (size_t)(n_fft + 4) * sizeof(float);
   if (smem > 48 * 1024)
     RVB_CUDA(cudaFuncSetAttribute(fold_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t cap = 148 * 8 * 4;
@@ -384,7 +366,7 @@ extern "C" int rvb_stft_bin(const float* sig_hi, const float* sig_lo, int n_seg,
                             int epilogue, float power, float* out0, int n_out_bins, rvb_stream_t stream) {
   RVB_REQUIRE(sig_hi && sig_lo && wcos_row && wsin_row && out0, "rvb_stft_bin: null pointer");
   RVB_REQUIRE(n_seg > 0 && n_frames > 0 && bin >= 0 && bin < n_out_bins, "rvb_stft_bin: bad shape");
-  RVB_REQUIRE(epilogue >= RVB_EPI_POWER && epilogue <= RVB_EPI_POWER_P, "rvb_stft_bin: bad epilogue %d", epilogue);
+  RVB_REQUIRE(epilogue_ok(epilogue), "rvb_stft_bin: bad epilogue %d", epilogue);
   RVB_REQUIRE((int64_t)(n_frames - 1) * hop + n_fft <= (int64_t)rows_per_seg * hop, "rvb_stft_bin: plane too short");
   const int64_t frames = (int64_t)n_seg * n_frames;
   stft_bin_kernel<<<(unsigned)((frames + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
@@ -394,22 +376,22 @@ extern "C" int rvb_stft_bin(const float* sig_hi, const float* sig_lo, int n_seg,
   return check_launch("stft_bin_kernel");
 }
 
-extern "C" int rvb_mel_project(const float* power, int n_seg, int n_bins, int n_frames, const int32_t* band0,
-                               const float* w0, const float* w1, int k_begin, int k_end, int n_mels,
-                               float log_offset, int layout, float* out, uint32_t* minmax, rvb_stream_t stream) {
-  RVB_REQUIRE(power && band0 && w0 && w1 && out, "rvb_mel_project: null pointer");
-  RVB_REQUIRE(n_seg > 0 && n_frames > 0 && n_mels > 0, "rvb_mel_project: bad shape");
-  RVB_REQUIRE(0 <= k_begin && k_begin < k_end && k_end <= n_bins, "rvb_mel_project: bad bin range [%d,%d) of %d",
-              k_begin, k_end, n_bins);
+extern "C" int rvb_mel_project(const float* power, int n_seg, int n_frames, int n_bins, const int32_t* band_lo,
+                               const int32_t* band_len, const float* band_w, int max_len, int n_mels, float log_offset,
+                               int layout, float* out, uint32_t* minmax, rvb_stream_t stream) {
+  RVB_REQUIRE(power && band_lo && band_len && band_w && out, "rvb_mel_project: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_frames > 0 && n_mels > 0 && n_bins > 0, "rvb_mel_project: bad shape");
+  RVB_REQUIRE(max_len > 0 && max_len <= n_bins, "rvb_mel_project: bad max_len %d", max_len);
   RVB_REQUIRE(layout == RVB_LAYOUT_BINS_MAJOR || layout == RVB_LAYOUT_TIME_MAJOR, "rvb_mel_project: bad layout");
-  const size_t smem = (size_t)n_mels * 33 * sizeof(float);
-  RVB_REQUIRE(smem <= 200 * 1024, "rvb_mel_project: n_mels %d too large", n_mels);
+  const size_t smem = (size_t)kMelFR * n_bins * sizeof(float);
+  RVB_REQUIRE(smem <= 200 * 1024, "rvb_mel_project: n_bins %d too large", n_bins);
   if (minmax) RVB_CUDA(cudaMemsetAsync(minmax, 0, sizeof(uint32_t) * 2 * n_seg, (cudaStream_t)stream));
   if (smem > 48 * 1024)
     RVB_CUDA(cudaFuncSetAttribute(mel_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)((n_frames + kMelFrames - 1) / kMelFrames), (unsigned)n_seg);
-  mel_project_kernel<<<grid, kMelWarps * kWarp, smem, (cudaStream_t)stream>>>(
-      power, n_bins, n_frames, band0, w0, w1, k_begin, k_end, n_mels, log_offset, layout, out, minmax);
+  dim3 grid((unsigned)((n_frames + kMelFR - 1) / kMelFR), (unsigned)n_seg);
+  mel_project_kernel<<<grid, kMelThreads, smem, (cudaStream_t)stream>>>(power, n_frames, n_bins, band_lo, band_len,
+                                                                       band_w, max_len, n_mels, log_offset, layout, out,
+                                                                       minmax);
   count_launch();
   return check_launch("mel_project_kernel");
 }

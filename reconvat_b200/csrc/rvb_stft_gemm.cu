@@ -278,15 +278,8 @@ stft_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         tmem_ld32(taddr + 128 + c * 32, im);
         tmem_ld_wait();
         const int k0 = n_tile * 128 + c * 32;
-        if (t_ok) {
-          const int64_t base = ((int64_t)b * p.n_out_bins + k0) * p.n_frames + t;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (k0 + i < p.n_store_bins)
-              stft_store(p.epilogue, p.power, __uint_as_float(re[i]), __uint_as_float(im[i]), p.out0,
-                         base + (int64_t)i * p.n_frames);
-          }
-        }
+        if (t_ok)
+          stft_store_chunk(p.epilogue, p.power, re, im, 0.f, p.out0, b, k0, t, p.n_out_bins, p.n_store_bins, p.n_frames);
       }
       tc_fence_before();
       __syncwarp();
@@ -456,15 +449,8 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
         tmem_ld32(taddr + 128 + c * 32, im);
         tmem_ld_wait();
         const int k0 = n_tile * 128 + c * 32;
-        if (f_ok) {
-          const int64_t base = ((int64_t)b * p.n_out_bins + k0) * p.n_frames + t;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (k0 + i < p.n_store_bins)
-              stft_store(p.epilogue, p.power, __uint_as_float(re[i]) + re0, __uint_as_float(im[i]), p.out0,
-                         base + (int64_t)i * p.n_frames);
-          }
-        }
+        if (f_ok)
+          stft_store_chunk(p.epilogue, p.power, re, im, re0, p.out0, b, k0, t, p.n_out_bins, p.n_store_bins, p.n_frames);
       }
       tc_fence_before();
       __syncwarp();
@@ -505,7 +491,7 @@ stft_bin_fold_kernel(const float* __restrict__ a_hi, const float* __restrict__ a
   if (lane == 0) {
     if (p0) re += w0 * __ldg(p0 + f);
     const int b = (int)(f / n_frames), t = (int)(f - (int64_t)b * n_frames);
-    stft_store(epilogue, power, re, im, out0, ((int64_t)b * n_out_bins + bin) * n_frames + t);
+    stft_store(epilogue, power, re, im, out0, b, bin, t, n_out_bins, n_frames);
   }
 }
 
@@ -586,7 +572,7 @@ extern "C" int rvb_stft_gemm(const float* sig_hi, const float* sig_lo, int n_seg
   RVB_REQUIRE(hop % BLOCK_K == 0 && hop >= BLOCK_K, "rvb_stft_gemm: hop %d must be a multiple of %d", hop, BLOCK_K);
   RVB_REQUIRE(n_basis_rows % BLOCK_N == 0 && n_basis_rows > 0, "rvb_stft_gemm: n_basis_rows %d must be a multiple of %d",
               n_basis_rows, BLOCK_N);
-  RVB_REQUIRE(epilogue >= RVB_EPI_POWER && epilogue <= RVB_EPI_POWER_P, "rvb_stft_gemm: bad epilogue %d", epilogue);
+  RVB_REQUIRE(epilogue_ok(epilogue), "rvb_stft_gemm: bad epilogue %d", epilogue);
   RVB_REQUIRE((int64_t)(n_frames - 1) * hop + n_fft <= (int64_t)rows_per_seg * hop,
               "rvb_stft_gemm: %d frames of %d samples do not fit %d rows of %d", n_frames, n_fft, rows_per_seg, hop);
   for (const void* ptr : {(const void*)sig_hi, (const void*)sig_lo, (const void*)basis_hi, (const void*)basis_lo})
@@ -632,7 +618,7 @@ extern "C" int rvb_stft_gemm_folded(const float* a_hi, const float* a_lo, int n_
               n_fft, 2 * BLOCK_K);
   RVB_REQUIRE(n_bins_pad % F_BLOCK_N == 0 && n_bins_pad > 0, "rvb_stft_gemm_folded: n_bins_pad %d must be a multiple of %d",
               n_bins_pad, F_BLOCK_N);
-  RVB_REQUIRE(epilogue >= RVB_EPI_POWER && epilogue <= RVB_EPI_POWER_P, "rvb_stft_gemm_folded: bad epilogue %d", epilogue);
+  RVB_REQUIRE(epilogue_ok(epilogue), "rvb_stft_gemm_folded: bad epilogue %d", epilogue);
   RVB_REQUIRE(n_out_bins > 0, "rvb_stft_gemm_folded: n_out_bins must be positive");
   for (const void* ptr : {(const void*)a_hi, (const void*)a_lo, (const void*)basis_hi, (const void*)basis_lo})
     RVB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 127u) == 0, "rvb_stft_gemm_folded: operands must be 128-byte aligned");
@@ -674,7 +660,7 @@ extern "C" int rvb_stft_bin_folded(const float* a_hi, const float* a_lo, int n_s
                                    int epilogue, float power, float* out0, int n_out_bins, rvb_stream_t stream) {
   RVB_REQUIRE(a_hi && a_lo && wc_row && ws_row && out0, "rvb_stft_bin_folded: null pointer");
   RVB_REQUIRE(n_seg > 0 && n_frames > 0 && bin >= 0 && bin < n_out_bins, "rvb_stft_bin_folded: bad shape");
-  RVB_REQUIRE(epilogue >= RVB_EPI_POWER && epilogue <= RVB_EPI_POWER_P, "rvb_stft_bin_folded: bad epilogue %d", epilogue);
+  RVB_REQUIRE(epilogue_ok(epilogue), "rvb_stft_bin_folded: bad epilogue %d", epilogue);
   RVB_REQUIRE(w0 == 0.f || p0 != nullptr, "rvb_stft_bin_folded: w0 != 0 needs p0");
   const int64_t m_rows = (int64_t)n_seg * n_frames;
   stft_bin_fold_kernel<<<(unsigned)((m_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(

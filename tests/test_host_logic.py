@@ -58,6 +58,22 @@ def test_banded_filterbank_roundtrip_and_rejection():
         basis.banded_filterbank(bad)
 
 
+def test_band_rows_roundtrip_and_rejection():
+    mb = basis.mel_filterbank(16000, 2048, 229, 30, 8000)
+    lo, ln, w, k_end = basis.band_rows(mb)
+    assert k_end == 1024 and w.shape == (27, 229) and int(ln.max()) == 27 and int(lo.min()) == 4
+    dense = np.zeros_like(mb)
+    for m in range(229):
+        dense[m, lo[m]:lo[m] + ln[m]] = w[:ln[m], m]
+    assert np.array_equal(dense, mb)
+    wide = mb.copy()
+    wide[0, 900] = 1.0                                    # support of 897 bins: not banded
+    with pytest.raises(ValueError, match="not a banded"):
+        basis.band_rows(wide)
+    for kw in (dict(sr=22050, n_fft=2048, n_mels=128), dict(sr=16000, n_fft=1024, n_mels=128, htk=True)):
+        assert basis.band_rows(basis.mel_filterbank(**kw))[2].shape[0] <= 64
+
+
 def test_tf32_split_reconstructs_to_2_pow_minus_21():
     rng = np.random.default_rng(0)
     x = (rng.standard_normal(100000) * np.exp(rng.uniform(-20, 5, 100000))).astype(np.float32)

@@ -69,18 +69,18 @@ def stage_pad():
 def stage_mel():
     fo = FrontEndOracle()
     rng = np.random.default_rng(0)
-    P = (rng.standard_normal((3, 1024, 70)).astype(np.float32) ** 2) * 50
-    band0, w0, w1, kb, ke = basis.banded_filterbank(fo.mel_basis)
+    P = (rng.standard_normal((3, 70, 1024)).astype(np.float32) ** 2) * 50          # time-major [b][t][k]
+    lo, ln, w, k_end = basis.band_rows(fo.mel_basis)
     t = lambda v: torch.from_numpy(v).to(dev)
-    Pd, b0d, w0d, w1d = t(P), t(band0), t(w0), t(w1)
+    Pd, lod, lnd, wd = t(P), t(lo), t(ln), t(w)
+    ref = np.einsum("mk,btk->bmt", fo.mel_basis[:, :1024].astype(np.float64), P.astype(np.float64))
     out = torch.empty((3, 229, 70), device=dev)
-    _lib.call("rvb_mel_project", Pd.data_ptr(), 3, 1024, 70, b0d.data_ptr(), w0d.data_ptr(), w1d.data_ptr(), kb, ke,
+    _lib.call("rvb_mel_project", Pd.data_ptr(), 3, 70, 1024, lod.data_ptr(), lnd.data_ptr(), wd.data_ptr(), w.shape[0],
               229, -1.0, 0, out.data_ptr(), None)
-    ref = np.einsum("mk,bkt->bmt", fo.mel_basis[:, :1024].astype(np.float64), P.astype(np.float64))
     print("mel bins-major rel err", float((np.abs(out.cpu().numpy() - ref) / np.abs(ref).max()).max()))
     out2 = torch.empty((3, 70, 229), device=dev)
     mm = torch.empty((3, 2), dtype=torch.int32, device=dev)
-    _lib.call("rvb_mel_project", Pd.data_ptr(), 3, 1024, 70, b0d.data_ptr(), w0d.data_ptr(), w1d.data_ptr(), kb, ke,
+    _lib.call("rvb_mel_project", Pd.data_ptr(), 3, 70, 1024, lod.data_ptr(), lnd.data_ptr(), wd.data_ptr(), w.shape[0],
               229, 1e-5, 1, out2.data_ptr(), mm.data_ptr())
     lref = np.log(ref + 1e-5).transpose(0, 2, 1)
     print("logmel time-major err", relerr(out2.cpu().numpy(), lref))
