@@ -27,7 +27,8 @@ N4, P4 = T_FRAMES * N_MELS * 4, T_FRAMES * N_PITCH * 4
 # algorithmic HBM bytes per segment of each HBM-bound kernel (DESIGN.md "Kernels")
 HBM_BYTES_PER_SEG = {
     "rvb_pad_split": 1310716 + 2 * 1318912,
-    "rvb_fold_split": 1310716 + 4 * 640 * 1024 * 4,       # R audio, W e/o hi/lo operand planes
+    "rvb_fold_split": 1310716 + 4 * 640 * 1024 * 4,       # R audio, W e/o hi/lo tf32 operand planes
+    "rvb_fold_split_f16": 1310716 + 4 * 640 * 1024 * 2 + 640 * 4,   # R audio, W e/o hi/lo fp16 planes + row scales
     "rvb_mel_project": 1020 * 640 * 4 + N4,
     "rvb_normalise": 2 * N4,
     "rvb_vat_perturb": 3 * N4,
@@ -181,7 +182,7 @@ def run_ours(args, rank, local_rank, world):
         step(dev_audio[i % n_rot])
     step.vat_loss.check()
     sampler = ClockSampler(local_rank)
-    kernel_names = ["rvb_stft_gemm", "rvb_stft_gemm_folded"] + list(HBM_BYTES_PER_SEG)
+    kernel_names = ["rvb_stft_gemm", "rvb_stft_gemm_folded", "rvb_stft_gemm_folded_f16"] + list(HBM_BYTES_PER_SEG)
     barrier()
     sampler.start()
     log = R._lib.record_events(kernel_names)
@@ -221,22 +222,26 @@ def run_ours(args, rank, local_rank, world):
     if rank != 0:
         return
     peaks = load_peaks()
-    folded = "rvb_stft_gemm_folded" in kavg
-    gemm_name = "rvb_stft_gemm_folded" if folded else "rvb_stft_gemm"
+    f16 = "rvb_stft_gemm_folded_f16" in kavg
+    folded = f16 or "rvb_stft_gemm_folded" in kavg
+    gemm_name = "rvb_stft_gemm_folded_f16" if f16 else ("rvb_stft_gemm_folded" if folded else "rvb_stft_gemm")
     gemm_ms = kavg.get(gemm_name)
     roofline = None
     if gemm_ms:
         # algorithmic FLOPs: the dense contraction as the reference computes it, whichever kernel ran;
-        # issued: 3 tf32 MMAs per product, K halved by the fold
+        # issued: 3 MMAs per product (hi*hi + hi*lo + lo*hi), K halved by the fold
         achieved = B * STFT_FLOP_PER_SEG / (gemm_ms * 1e-3) / 1e12
         issued = 3 * B * 2 * 640 * 2048 * (1024 if folded else 2048) / (gemm_ms * 1e-3) / 1e12
-        kname = "stft_gemm_fold_kernel" if folded else "stft_gemm_kernel"
+        kname = ("stft_gemm_fold_kernel<f16>" if f16 else "stft_gemm_fold_kernel<tf32>") if folded else "stft_gemm_kernel"
+        pipe_peak = peaks["bf16"] if f16 else peaks["bf16"] / 2
         roofline = {"kernel": "%s (%s)" % (kname, gemm_name), "bound": "tensor", "achieved": achieved,
                     "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"], "traffic": None,
-                    "peak_source": "%s dense bf16 burst (MEASURED_PEAKS.json); the kernel runs kind::tf32 (half the "
-                                   "bf16 rate) with 3 MMAs per product (3xTF32) and, folded, half the contraction "
-                                   "length: frac <= %s at a saturated tensor pipe" % (peaks["source"], "1/3" if folded else "1/6"),
-                    "issued_tflops": issued, "issued_frac_of_tf32_peak": issued / (peaks["bf16"] / 2),
+                    "peak_source": "%s dense bf16 burst (MEASURED_PEAKS.json); the kernel runs %s with 3 MMAs per "
+                                   "product and%s: frac <= %s at a saturated tensor pipe"
+                                   % (peaks["source"], "kind::f16 (the bf16 rate)" if f16 else "kind::tf32 (half the bf16 rate)",
+                                      ", folded, half the contraction length" if folded else " the full contraction length",
+                                      "2/3" if f16 else ("1/3" if folded else "1/6")),
+                    "issued_tflops": issued, "issued_frac_of_pipe_peak": issued / pipe_peak,
                     "ms_per_launch": gemm_ms, "share_of_step": gemm_ms / ms_step}
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -272,7 +277,7 @@ def run_ours(args, rank, local_rank, world):
     line = {
         "metric": "audio-sec/s", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 (STFT: 3xTF32 split operands, f32 accumulate in TMEM)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32 (STFT: 3x%s split operands, f32 accumulate in TMEM)" % ("FP16" if f16 else "TF32"), "data": "synthetic",
         "config": {"workload": "Mel+VAT step, B=%d x 20.48 s segments per GPU (BASELINE metric shape): Mel front-end + "
                                "UNet_VAT(XI=1e-6, eps=2); network = %s" % (B, "injected posteriors and input gradient "
                                "(hot path only)" if args.model == "injected" else "stand-in linear transcriber (PyTorch)"),

@@ -121,6 +121,29 @@ int rvb_stft_bin_folded(const float* a_hi, const float* a_lo, int n_seg, int n_f
                         float power, float* out0, int n_out_bins, rvb_stream_t stream);
 
 /*
+ * K0h / K1h / K1hb  the fp16 flavour of the folded contraction (3xFP16: hi*hi + hi*lo + lo*hi with fp32
+ * accumulation in TMEM).  fp16 has tf32's 11 significant bits, so the split carries the same 22 operand bits as
+ * 3xTF32 while `tcgen05.mma.kind::f16` runs at twice the `kind::tf32` rate.  Its 5-bit exponent is handled by
+ * power-of-two block scaling: rvb_fold_split_f16 scales each frame row so that its largest |e|,|o| lies in
+ * [2^14, 2^15) and writes row_scale_inv[frame] = 2^-s; the host scales the basis the same way
+ * (basis_scale_inv); the epilogue multiplies the accumulator by row_scale_inv * basis_scale_inv (exact).
+ *   a_hi/a_lo    IEEE binary16 planes [2][n_seg*n_frames][n_fft/2] (plane 0 = e, plane 1 = o), 128-byte aligned
+ *   basis_hi/lo  IEEE binary16 [2][n_bins_pad][n_fft/2]
+ * Replaces the same reference lines as rvb_fold_split / rvb_stft_gemm_folded / rvb_stft_bin_folded
+ * (model/Spectrogram.py:209-231, :458).  Constraint: n_fft % 128 == 0.
+ */
+int rvb_fold_split_f16(const float* audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int pad_mode,
+                       int n_fft, int hop, int n_frames, void* a_hi, void* a_lo, float* row_scale_inv, float* p0,
+                       rvb_stream_t stream);
+int rvb_stft_gemm_folded_f16(const void* a_hi, const void* a_lo, const float* row_scale_inv, int n_seg, int n_frames,
+                             int n_fft, const void* basis_hi, const void* basis_lo, float basis_scale_inv,
+                             int n_bins_pad, const float* p0, float w0, int epilogue, float power, float* out0,
+                             int n_out_bins, rvb_stream_t stream);
+int rvb_stft_bin_folded_f16(const void* a_hi, const void* a_lo, const float* row_scale_inv, int n_seg, int n_frames,
+                            int n_fft, const float* wc_row, const float* ws_row, const float* p0, float w0, int bin,
+                            int epilogue, float power, float* out0, int n_out_bins, rvb_stream_t stream);
+
+/*
  * K1b  one frequency bin in plain fp32 FMA (used for the Nyquist bin, which would otherwise cost a
  * whole extra 256-column tile).  Same epilogues / output indexing as rvb_stft_gemm; `wcos_row`,
  * `wsin_row` are the fp32 windowed basis rows of that bin (model/Spectrogram.py:162-164).

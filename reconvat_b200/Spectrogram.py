@@ -83,7 +83,11 @@ class STFT(nn.Module):
             wsin = self.wsin[:, 0, :].detach().cpu().numpy()
             dev = self.wsin.device
             tb = dict(n_bins=wcos.shape[0], fold=None, direct=None)
-            fold = None if os.environ.get("RVB_NO_FOLD") else basis.fold_operand(wcos, wsin)
+            # RVB_STFT_OPERAND=tf32 keeps the 3xTF32 planes (half the MMA rate; kept for A/B measurements)
+            operand = os.environ.get("RVB_STFT_OPERAND", "f16")
+            fold = None if os.environ.get("RVB_NO_FOLD") else basis.fold_operand(wcos, wsin, operand=operand)
+            if fold is None and operand == "f16" and not os.environ.get("RVB_NO_FOLD"):
+                fold = basis.fold_operand(wcos, wsin, operand="tf32")       # n_fft % 128 != 0
             if fold is not None:
                 for k in ("basis_hi", "basis_lo", "left_cos", "left_sin"):
                     fold[k] = torch.from_numpy(np.ascontiguousarray(fold[k])).to(dev)
@@ -150,8 +154,25 @@ class STFT(nn.Module):
         if tb["fold"] is not None:
             fd = tb["fold"]
             half, M = self.n_fft // 2, B * n_frames
-            planes = torch.empty((2, 2, M, half), dtype=torch.float32, device=x.device)    # [hi|lo][e|o][frame][c]
             p0 = torch.empty((M,), dtype=torch.float32, device=x.device) if fd["w0"] != 0.0 else None
+            p0_ptr = None if p0 is None else p0.data_ptr()
+            if fd["operand"] == "f16":
+                planes = torch.empty((2, 2, M, half), dtype=torch.float16, device=x.device)  # [hi|lo][e|o][frame][c]
+                row_inv = torch.empty((M,), dtype=torch.float32, device=x.device)
+                _lib.call("rvb_fold_split_f16", _lib.ptr(x2), ld, B, L, self.pad_amount, mode, self.n_fft, self.stride,
+                          n_frames, planes[0].data_ptr(), planes[1].data_ptr(), row_inv.data_ptr(), p0_ptr)
+                _lib.call("rvb_stft_gemm_folded_f16", planes[0].data_ptr(), planes[1].data_ptr(), row_inv.data_ptr(),
+                          B, n_frames, self.n_fft, fd["basis_hi"].data_ptr(), fd["basis_lo"].data_ptr(),
+                          fd["scale_inv"], fd["n_bins_pad"], p0_ptr, fd["w0"], epilogue, float(power), _lib.ptr(out),
+                          n_out_bins)
+                for i, k in enumerate(fd["leftover"]):
+                    if k < n_out_bins:
+                        _lib.call("rvb_stft_bin_folded_f16", planes[0].data_ptr(), planes[1].data_ptr(),
+                                  row_inv.data_ptr(), B, n_frames, self.n_fft, fd["left_cos"][i].data_ptr(),
+                                  fd["left_sin"][i].data_ptr(), p0_ptr, fd["w0"], k, epilogue, float(power),
+                                  _lib.ptr(out), n_out_bins)
+                return out, n_frames
+            planes = torch.empty((2, 2, M, half), dtype=torch.float32, device=x.device)    # [hi|lo][e|o][frame][c]
             _lib.call("rvb_fold_split", _lib.ptr(x2), ld, B, L, self.pad_amount, mode, self.n_fft, self.stride,
                       n_frames, planes[0].data_ptr(), planes[1].data_ptr(), None if p0 is None else p0.data_ptr())
             _lib.call("rvb_stft_gemm_folded", planes[0].data_ptr(), planes[1].data_ptr(), B, n_frames, self.n_fft,

@@ -214,7 +214,19 @@ def tf32_split64(x64):
     return hi, lo
 
 
-def fold_operand(wcos, wsin, tol=2.5e-7):
+def f16_split64(x64):
+    """float64 values -> (hi, lo, scale_inv): IEEE binary16 planes of x * 2^s with hi + lo == x * 2^s to 2^-22
+    relative (2^-25 absolute where lo is subnormal), s chosen so that max|x| 2^s lies in [2^14, 2^15)."""
+    x64 = np.asarray(x64, dtype=np.float64)
+    mx = float(np.abs(x64).max())
+    s = 14 - int(np.floor(np.log2(mx))) if mx > 0 else 0
+    xs = np.ldexp(x64, s)
+    hi = xs.astype(np.float16)
+    lo = (xs - hi.astype(np.float64)).astype(np.float16)
+    return hi, lo, float(np.ldexp(1.0, -s))
+
+
+def fold_operand(wcos, wsin, tol=2.5e-7, operand="tf32"):
     """Folded operand for windows symmetric about n_fft/2, or None when the basis is not symmetric
     (short / non-periodic windows, non-integer 'linear' / 'log' bin scales).
 
@@ -222,11 +234,12 @@ def fold_operand(wcos, wsin, tol=2.5e-7):
         re[k] = w[0] p[0] + sum_{c=0}^{N/2-1} Bc[k][c] e[c],  e[c] = p[c+1] + p[N-c-1]  (e[N/2-1] = p[N/2])
         im[k] =             sum_{c=0}^{N/2-1} Bs[k][c] o[c],  o[c] = p[c+1] - p[N-c-1]  (o[N/2-1] = 0)
     Bc / Bs average the two mirror entries in float64 (they differ by at most an fp32 ulp).
-    Returns dict(basis_hi, basis_lo [2*n_bins_pad, N/2] f32; n_bins_pad; n_gemm_bins; leftover; w0;
-    left_cos, left_sin: folded fp32 rows of the leftover bins).
+    Returns dict(basis_hi, basis_lo [2*n_bins_pad, N/2]; n_bins_pad; n_gemm_bins; leftover; w0;
+    left_cos, left_sin: folded fp32 rows of the leftover bins; scale_inv).  ``operand`` selects the split:
+    "tf32" -> float32 planes (scale_inv 1), "f16" -> block-scaled float16 planes (see :func:`f16_split64`).
     """
     F, N = wcos.shape
-    if N % 64 != 0:
+    if N % (128 if operand == "f16" else 64) != 0:
         return None
     half = N // 2
     c64, s64 = wcos.astype(np.float64), wsin.astype(np.float64)
@@ -251,6 +264,12 @@ def fold_operand(wcos, wsin, tol=2.5e-7):
     mat = np.zeros((2 * n_bins_pad, half), np.float64)
     mat[:n_gemm] = bc[:n_gemm]
     mat[n_bins_pad:n_bins_pad + n_gemm] = bs[:n_gemm]
-    hi, lo = tf32_split64(mat)
+    if operand == "f16":
+        hi, lo, scale_inv = f16_split64(mat)
+    elif operand == "tf32":
+        (hi, lo), scale_inv = tf32_split64(mat), 1.0
+    else:
+        raise ValueError("operand must be 'f16' or 'tf32'")
     return dict(basis_hi=hi, basis_lo=lo, n_bins_pad=n_bins_pad, n_gemm_bins=n_gemm, leftover=leftover, w0=w0,
-                left_cos=bc[n_gemm:].astype(np.float32), left_sin=bs[n_gemm:].astype(np.float32))
+                left_cos=bc[n_gemm:].astype(np.float32), left_sin=bs[n_gemm:].astype(np.float32),
+                scale_inv=scale_inv, operand=operand)

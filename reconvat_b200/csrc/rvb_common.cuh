@@ -1,5 +1,6 @@
 // Shared device/host helpers for the reconvat_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -104,19 +105,21 @@ __device__ __forceinline__ void stft_store(int epilogue, float power, float re, 
 }
 
 // Epilogue of one accumulator chunk: 32 consecutive bins [k0, k0+32) of frame (b, t) held by one thread.
+// `scale` undoes the power-of-two operand scaling of the fp16 contraction (1 for tf32 operands: exact either way).
 __device__ __forceinline__ void stft_store_chunk(int epilogue, float power, const uint32_t (&re)[32],
-                                                 const uint32_t (&im)[32], float re_add, float* __restrict__ out0, int b,
-                                                 int k0, int t, int n_out_bins, int n_store_bins, int n_frames) {
+                                                 const uint32_t (&im)[32], float scale, float re_add,
+                                                 float* __restrict__ out0, int b, int k0, int t, int n_out_bins,
+                                                 int n_store_bins, int n_frames) {
   const int epi = epilogue & 0xf;
   if ((epilogue & RVB_EPI_TIME_MAJOR) && epi != RVB_EPI_COMPLEX && k0 + 32 <= n_store_bins && (n_out_bins & 3) == 0) {
     float4* dst = reinterpret_cast<float4*>(out0 + ((int64_t)b * n_frames + t) * n_out_bins + k0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 v;
-      v.x = stft_value(epi, power, __uint_as_float(re[4 * i + 0]) + re_add, __uint_as_float(im[4 * i + 0]));
-      v.y = stft_value(epi, power, __uint_as_float(re[4 * i + 1]) + re_add, __uint_as_float(im[4 * i + 1]));
-      v.z = stft_value(epi, power, __uint_as_float(re[4 * i + 2]) + re_add, __uint_as_float(im[4 * i + 2]));
-      v.w = stft_value(epi, power, __uint_as_float(re[4 * i + 3]) + re_add, __uint_as_float(im[4 * i + 3]));
+      v.x = stft_value(epi, power, __uint_as_float(re[4 * i + 0]) * scale + re_add, __uint_as_float(im[4 * i + 0]) * scale);
+      v.y = stft_value(epi, power, __uint_as_float(re[4 * i + 1]) * scale + re_add, __uint_as_float(im[4 * i + 1]) * scale);
+      v.z = stft_value(epi, power, __uint_as_float(re[4 * i + 2]) * scale + re_add, __uint_as_float(im[4 * i + 2]) * scale);
+      v.w = stft_value(epi, power, __uint_as_float(re[4 * i + 3]) * scale + re_add, __uint_as_float(im[4 * i + 3]) * scale);
       dst[i] = v;
     }
     return;
@@ -124,8 +127,8 @@ __device__ __forceinline__ void stft_store_chunk(int epilogue, float power, cons
 #pragma unroll
   for (int i = 0; i < 32; ++i)
     if (k0 + i < n_store_bins)
-      stft_store(epilogue, power, __uint_as_float(re[i]) + re_add, __uint_as_float(im[i]), out0, b, k0 + i, t, n_out_bins,
-                 n_frames);
+      stft_store(epilogue, power, __uint_as_float(re[i]) * scale + re_add, __uint_as_float(im[i]) * scale, out0, b, k0 + i,
+                 t, n_out_bins, n_frames);
 }
 
 }  // namespace rvb

@@ -128,6 +128,110 @@ fold_split_kernel(const float* __restrict__ audio, int64_t audio_ld, int n_seg, 
   }
 }
 
+// ------------------------------------------------------------------ K0h
+// fp16 flavour of K0f for the 3xFP16 contraction.  fp16 carries tf32's 11 significant bits but only a 5-bit
+// exponent, so each frame row is block-scaled: s = 14 - floor(log2(max(|e|,|o|))) puts the row maximum in
+// [2^14, 2^15) (fp16 overflows at 65504), hi = fp16(v 2^s), lo = fp16(v 2^s - hi).  lo keeps its full 11 bits while
+// |v 2^s| >= 2^-3, i.e. over 18 binades below the row maximum; under that it rounds on the fp16 subnormal grid,
+// an absolute 2^-25 (2^-39 of the row maximum).  row_scale_inv[frame] = 2^-s is applied by the GEMM epilogue.
+__device__ __forceinline__ void fold4(const float* __restrict__ frame_s, const float* __restrict__ frame, int n_fft,
+                                      int half, int c, float (&e)[4], float (&o)[4]) {
+  const float4 x = *reinterpret_cast<const float4*>(frame_s + c + 4);            // p[c+1 .. c+4]
+  const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float y = frame[n_fft - (c + 1 + i)];                                  // p[N-n]
+    e[i] = xs[i] + y;
+    o[i] = xs[i] - y;
+  }
+  if (c + 4 == half) { e[3] = xs[3]; o[3] = 0.f; }                               // n == N/2 pairs with itself
+}
+
+__global__ void __launch_bounds__(256)
+fold_split_f16_kernel(const float* __restrict__ audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int mode,
+                      int n_fft, int hop, int n_frames, __half* __restrict__ a_hi, __half* __restrict__ a_lo,
+                      float* __restrict__ row_scale_inv, float* __restrict__ p0) {
+  extern __shared__ __align__(16) float frame_s[];         // frame_s[i + 3] = p[i], i in [0, n_fft)
+  __shared__ float red[8];
+  float* frame = frame_s + 3;
+  const int half = n_fft >> 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n_rows = (int64_t)n_seg * n_frames;
+  const int64_t padded = (mode == RVB_PAD_NONE) ? n_samples : (int64_t)n_samples + 2 * pad;
+  const int off = (mode == RVB_PAD_NONE) ? 0 : pad;
+  for (int64_t f = blockIdx.x; f < n_rows; f += gridDim.x) {
+    const int b = (int)(f / n_frames), t = (int)(f - (int64_t)b * n_frames);
+    const float* a = audio + (int64_t)b * audio_ld;
+    const int64_t start = (int64_t)t * hop;
+    const int64_t j0 = start - off;
+    __syncthreads();                                       // previous iteration's readers (frame, red) are done
+    const bool interior = j0 >= 0 && j0 + n_fft <= n_samples && ((j0 & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(a) & 15u) == 0);
+    if (interior) {
+      const float4* src = reinterpret_cast<const float4*>(a + j0);
+      for (int i = threadIdx.x; i < (n_fft >> 2); i += blockDim.x) {
+        const float4 v = __ldg(src + i);
+        frame[4 * i + 0] = v.x; frame[4 * i + 1] = v.y; frame[4 * i + 2] = v.z; frame[4 * i + 3] = v.w;
+      }
+    } else {
+      for (int i = threadIdx.x; i < n_fft; i += blockDim.x) {
+        const int64_t pi = start + i;
+        frame[i] = (pi < padded) ? padded_sample(a, pi, n_samples, pad, mode) : 0.f;
+      }
+    }
+    __syncthreads();
+    float mx = 0.f;
+    for (int q = threadIdx.x; q < (half >> 2); q += blockDim.x) {
+      float e[4], o[4];
+      fold4(frame_s, frame, n_fft, half, q << 2, e, o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(e[i]), fabsf(o[i])));   // fmaxf drops NaN: s stays finite
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    // floor(log2(mx)) from the exponent field (subnormal rows: treat as 2^-126); all-zero rows: s = 0
+    int s = 0;
+    if (mx > 0.f) {
+      int ex = (int)((__float_as_uint(mx) >> 23) & 0xff) - 127;
+      ex = max(-126, min(ex, 127));
+      s = max(-126, min(14 - ex, 126));
+    }
+    const float sc = __uint_as_float((unsigned)(s + 127) << 23);          // 2^s, exact
+    __half* e_hi = a_hi + f * half;
+    __half* e_lo = a_lo + f * half;
+    __half* o_hi = a_hi + (n_rows + f) * half;
+    __half* o_lo = a_lo + (n_rows + f) * half;
+    for (int q = threadIdx.x; q < (half >> 2); q += blockDim.x) {
+      float e[4], o[4];
+      fold4(frame_s, frame, n_fft, half, q << 2, e, o);
+      __half eh[4], el[4], oh[4], ol[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float ev = e[i] * sc, ov = o[i] * sc;
+        eh[i] = __float2half_rn(ev); el[i] = __float2half_rn(ev - __half2float(eh[i]));
+        oh[i] = __float2half_rn(ov); ol[i] = __float2half_rn(ov - __half2float(oh[i]));
+      }
+      auto pack = [](const __half (&h)[4]) {
+        uint2 r;
+        r.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+        r.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+        return r;
+      };
+      reinterpret_cast<uint2*>(e_hi)[q] = pack(eh);
+      reinterpret_cast<uint2*>(e_lo)[q] = pack(el);
+      reinterpret_cast<uint2*>(o_hi)[q] = pack(oh);
+      reinterpret_cast<uint2*>(o_lo)[q] = pack(ol);
+    }
+    if (threadIdx.x == 0) {
+      row_scale_inv[f] = __uint_as_float((unsigned)(127 - s) << 23);      // 2^-s
+      if (p0) p0[f] = frame[0];
+    }
+  }
+}
+
 // ------------------------------------------------------------------ K1b
 // One warp per frame: plain fp32 dot products of the frame with one basis row pair.
 __global__ void __launch_bounds__(256)
@@ -359,6 +463,34 @@ extern "C" int rvb_fold_split(const float* audio, int64_t audio_ld, int n_seg, i
                                                                hop, n_frames, a_hi, a_lo, p0);
   count_launch();
   return check_launch("fold_split_kernel");
+}
+
+extern "C" int rvb_fold_split_f16(const float* audio, int64_t audio_ld, int n_seg, int n_samples, int pad,
+                                  int pad_mode, int n_fft, int hop, int n_frames, void* a_hi, void* a_lo,
+                                  float* row_scale_inv, float* p0, rvb_stream_t stream) {
+  RVB_REQUIRE(audio && a_hi && a_lo && row_scale_inv, "rvb_fold_split_f16: null pointer");
+  RVB_REQUIRE((reinterpret_cast<uintptr_t>(a_hi) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a_lo) & 15u) == 0,
+              "rvb_fold_split_f16: planes must be 16-byte aligned");
+  RVB_REQUIRE(n_seg > 0 && n_samples > 0 && hop > 0 && n_frames > 0, "rvb_fold_split_f16: bad shape");
+  RVB_REQUIRE(n_fft >= 128 && n_fft % 128 == 0 && n_fft <= 32768, "rvb_fold_split_f16: n_fft %d must be a multiple of 128",
+              n_fft);
+  RVB_REQUIRE(pad_mode >= RVB_PAD_REFLECT && pad_mode <= RVB_PAD_NONE, "rvb_fold_split_f16: bad pad_mode %d", pad_mode);
+  if (pad_mode == RVB_PAD_REFLECT)
+    RVB_REQUIRE(n_samples > pad, "rvb_fold_split_f16: reflect padding %d needs more than %d samples", pad, n_samples);
+  const int64_t padded = (pad_mode == RVB_PAD_NONE) ? n_samples : (int64_t)n_samples + 2 * pad;
+  RVB_REQUIRE((int64_t)(n_frames - 1) * hop + n_fft <= padded, "rvb_fold_split_f16: %d frames do not fit %lld samples",
+              n_frames, (long long)padded);
+  const int64_t n_rows = (int64_t)n_seg * n_frames;
+  const size_t smem = (size_t)(n_fft + 4) * sizeof(float);
+  if (smem > 48 * 1024)
+    RVB_CUDA(cudaFuncSetAttribute(fold_split_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t cap = 148 * 8 * 4;
+  const unsigned grid = (unsigned)(n_rows < cap ? n_rows : cap);
+  fold_split_f16_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
+      audio, audio_ld, n_seg, n_samples, pad, pad_mode, n_fft, hop, n_frames, static_cast<__half*>(a_hi),
+      static_cast<__half*>(a_lo), row_scale_inv, p0);
+  count_launch();
+  return check_launch("fold_split_f16_kernel");
 }
 
 extern "C" int rvb_stft_bin(const float* sig_hi, const float* sig_lo, int n_seg, int rows_per_seg, int hop,

@@ -118,17 +118,28 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   return (uint64_t)lo | ((uint64_t)hi << 32);
 }
-// kind::tf32 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), both K-major,
-// N>>3 at bits 17-22, M>>4 at bits 24-28.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// Instruction descriptor: D=f32 (bits 4-5 = 1), A and B formats at bits 7-9 / 10-12 (0 = f16, 2 = tf32), both
+// K-major, N>>3 at bits 17-22, M>>4 at bits 24-28.
+constexpr uint32_t FMT_F16 = 0, FMT_TF32 = 2;
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) { return make_idesc(m, n, FMT_TF32); }
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -279,7 +290,7 @@ stft_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         tmem_ld_wait();
         const int k0 = n_tile * 128 + c * 32;
         if (t_ok)
-          stft_store_chunk(p.epilogue, p.power, re, im, 0.f, p.out0, b, k0, t, p.n_out_bins, p.n_store_bins, p.n_frames);
+          stft_store_chunk(p.epilogue, p.power, re, im, 1.f, 0.f, p.out0, b, k0, t, p.n_out_bins, p.n_store_bins, p.n_frames);
       }
       tc_fence_before();
       __syncwarp();
@@ -305,7 +316,14 @@ stft_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 //  * operands are plain row-major matrices (frames are materialised by fold_split_kernel): A box = 128 rows x
 //    32 floats at row chain*M + m_tile*128, B box = 128 rows at row chain*n_bins_pad + n_tile*128;
 //  * stage = A_hi, A_lo, B_hi, B_lo of 16 KB each = 64 KB -> 3 stages; MMAs are 128 x 128 x 8;
-//  * M is the flattened frame index (tiles may straddle segments; the epilogue maps row -> (b, t)).
+//  * M is the flattened frame index (tiles may straddle segments; the epilogue maps row -> (b, t));
+//  * kF16 = true: operands are fp16 hi/lo planes (3xFP16: hi*hi + hi*lo + lo*hi, the same 22 operand bits as
+//    3xTF32, at twice the MMA rate).  fp16 has tf32's mantissa but a 5-bit exponent, so the planes are
+//    block-scaled by powers of two: every A row so that its largest element lies in [2^14, 2^15), the basis as
+//    a whole likewise; elements whose lo part falls into the fp16 subnormals keep an ABSOLUTE error of 2^-25
+//    in scaled units (2^-39 of the row maximum), far below the fp32 accumulation error.  The epilogue
+//    multiplies by row_scale_inv[frame] * basis_scale_inv (exact).  A 128-byte swizzle row is 64 halves and
+//    one MMA covers K = 16, so a stage carries twice the contraction length of the tf32 stage.
 constexpr int F_BLOCK_N = 128;
 constexpr int F_STAGES = 3;
 constexpr int F_TILE_BYTES = 128 * BLOCK_K * 4;         // 16 KB (A and B tiles are both 128 rows)
@@ -321,8 +339,11 @@ struct FoldParams {
   float power, w0;
   const float* p0;
   float* out0;
+  const float* row_scale_inv;   // fp16 operands only: per-frame 2^-s_row
+  float basis_scale_inv;        // fp16 operands only: 2^-s_basis
 };
 
+template <bool kF16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -367,8 +388,9 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
 
+  constexpr int kBlockK = kF16 ? 2 * BLOCK_K : BLOCK_K;     // elements per 128-byte swizzle row
   const int n_units = p.m_tiles * p.n_tiles;
-  const int kb_per_chain = p.half / BLOCK_K;
+  const int kb_per_chain = p.half / kBlockK;
   const int num_kb = 2 * kb_per_chain;
 
   if (warp == 0) {
@@ -379,7 +401,7 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
         const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           const int chain = kb >= kb_per_chain;
-          const int kk = (kb - chain * kb_per_chain) * BLOCK_K;
+          const int kk = (kb - chain * kb_per_chain) * kBlockK;
           const int a_row = (int)(chain * p.m_rows) + m_tile * BLOCK_M;
           const int b_row = chain * p.n_bins_pad + n_tile * F_BLOCK_N;
           mbar_wait(bar_empty(stage), phase ^ 1u, nullptr, 1);
@@ -395,7 +417,7 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, F_BLOCK_N);
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, F_BLOCK_N, kF16 ? FMT_F16 : FMT_TF32);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -413,11 +435,17 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
           const uint64_t db_lo = make_sw128_desc(s_tile(stage, 3));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adv = (uint64_t)(k * UMMA_K * 4 >> 4);
+            const uint64_t adv = (uint64_t)(k * UMMA_K * 4 >> 4);     // one MMA consumes 32 bytes of the row
             // small cross terms first: while the accumulator is still small their truncation costs nothing
-            umma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
-            umma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
-            umma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+            if constexpr (kF16) {
+              umma_f16(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
+              umma_f16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+              umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
+              umma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+              umma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+            }
           }
           umma_commit(bar_empty(stage));
           if (++stage == F_STAGES) { stage = 0; phase ^= 1u; }
@@ -439,6 +467,7 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
       const int b = f_ok ? (int)(f / p.n_frames) : 0;
       const int t = f_ok ? (int)(f - (int64_t)b * p.n_frames) : 0;
       const float re0 = (p.p0 != nullptr && f_ok) ? p.w0 * __ldg(p.p0 + f) : 0.f;
+      const float scale = (kF16 && f_ok) ? __ldg(p.row_scale_inv + f) * p.basis_scale_inv : 1.f;
       mbar_wait(bar_tmem_full(acc), acc_phase, nullptr, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
@@ -450,7 +479,8 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
         tmem_ld_wait();
         const int k0 = n_tile * 128 + c * 32;
         if (f_ok)
-          stft_store_chunk(p.epilogue, p.power, re, im, re0, p.out0, b, k0, t, p.n_out_bins, p.n_store_bins, p.n_frames);
+          stft_store_chunk(p.epilogue, p.power, re, im, scale, re0, p.out0, b, k0, t, p.n_out_bins, p.n_store_bins,
+                           p.n_frames);
       }
       tc_fence_before();
       __syncwarp();
@@ -469,26 +499,32 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
 }
 
 // Single bin from the folded planes (Nyquist bin of the STFT module): warp per frame, fp32 FMA.
+// T = float (tf32 planes) or __half (fp16 planes, row-scaled: row_scale_inv undoes the scaling).
+template <typename T>
 __global__ void __launch_bounds__(256)
-stft_bin_fold_kernel(const float* __restrict__ a_hi, const float* __restrict__ a_lo, int64_t m_rows, int n_frames,
-                     int half, const float* __restrict__ wc_row, const float* __restrict__ ws_row,
-                     const float* __restrict__ p0, float w0, int bin, int epilogue, float power,
-                     float* __restrict__ out0, int n_out_bins) {
+stft_bin_fold_kernel(const T* __restrict__ a_hi, const T* __restrict__ a_lo, const float* __restrict__ row_scale_inv,
+                     int64_t m_rows, int n_frames, int half, const float* __restrict__ wc_row,
+                     const float* __restrict__ ws_row, const float* __restrict__ p0, float w0, int bin, int epilogue,
+                     float power, float* __restrict__ out0, int n_out_bins) {
   const int lane = threadIdx.x & 31;
   const int64_t f = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (f >= m_rows) return;
-  const float* e_hi = a_hi + f * half;
-  const float* e_lo = a_lo + f * half;
-  const float* o_hi = a_hi + (m_rows + f) * half;
-  const float* o_lo = a_lo + (m_rows + f) * half;
+  const T* e_hi = a_hi + f * half;
+  const T* e_lo = a_lo + f * half;
+  const T* o_hi = a_hi + (m_rows + f) * half;
+  const T* o_lo = a_lo + (m_rows + f) * half;
   float re = 0.f, im = 0.f;
   for (int c = lane; c < half; c += 32) {
-    re = fmaf(__ldg(e_hi + c) + __ldg(e_lo + c), __ldg(wc_row + c), re);
-    im = fmaf(__ldg(o_hi + c) + __ldg(o_lo + c), __ldg(ws_row + c), im);
+    re = fmaf((float)e_hi[c] + (float)e_lo[c], __ldg(wc_row + c), re);
+    im = fmaf((float)o_hi[c] + (float)o_lo[c], __ldg(ws_row + c), im);
   }
   re = warp_sum(re);
   im = warp_sum(im);
   if (lane == 0) {
+    if (row_scale_inv) {
+      const float sc = __ldg(row_scale_inv + f);
+      re *= sc; im *= sc;
+    }
     if (p0) re += w0 * __ldg(p0 + f);
     const int b = (int)(f / n_frames), t = (int)(f - (int64_t)b * n_frames);
     stft_store(epilogue, power, re, im, out0, b, bin, t, n_out_bins, n_frames);
@@ -509,13 +545,14 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-// 2-D fp32 row-major tensor [rows][cols] -> tiled map with a (box_cols x box_rows) box, 128-byte swizzle.
-static int make_map_2d(CUtensorMap* out, const float* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
-                       uint32_t box_rows) {
-  using Key = std::tuple<const void*, uint64_t, uint64_t, uint32_t, uint32_t>;
+// 2-D row-major tensor [rows][cols] of fp32 (elem_bytes 4) or fp16 (2) -> tiled map with a
+// (box_cols x box_rows) box, 128-byte swizzle.
+static int make_map_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
+                       uint32_t box_rows, int elem_bytes = 4) {
+  using Key = std::tuple<const void*, uint64_t, uint64_t, uint32_t, uint32_t, int>;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
-  const Key key{base, cols, rows, box_cols, box_rows};
+  const Key key{base, cols, rows, box_cols, box_rows, elem_bytes};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -530,10 +567,11 @@ static int make_map_2d(CUtensorMap* out, const float* base, uint64_t cols, uint6
     return RVB_ERR_CUDA;
   }
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * sizeof(float)};
+  cuuint64_t gstride[1] = {cols * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estride[2] = {1, 1};
-  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
+  CUresult r = encode(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                      const_cast<void*>(base), gdim, gstride, box, estride,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -608,30 +646,35 @@ extern "C" int rvb_stft_gemm(const float* sig_hi, const float* sig_lo, int n_seg
   return check_launch("stft_gemm_kernel");
 }
 
-extern "C" int rvb_stft_gemm_folded(const float* a_hi, const float* a_lo, int n_seg, int n_frames, int n_fft,
-                                    const float* basis_hi, const float* basis_lo, int n_bins_pad, const float* p0,
-                                    float w0, int epilogue, float power, float* out0, int n_out_bins,
-                                    rvb_stream_t stream) {
-  RVB_REQUIRE(a_hi && a_lo && basis_hi && basis_lo && out0, "rvb_stft_gemm_folded: null pointer");
-  RVB_REQUIRE(n_seg > 0 && n_frames > 0, "rvb_stft_gemm_folded: bad shape");
-  RVB_REQUIRE(n_fft % (2 * BLOCK_K) == 0 && n_fft >= 2 * BLOCK_K, "rvb_stft_gemm_folded: n_fft %d must be a multiple of %d",
-              n_fft, 2 * BLOCK_K);
-  RVB_REQUIRE(n_bins_pad % F_BLOCK_N == 0 && n_bins_pad > 0, "rvb_stft_gemm_folded: n_bins_pad %d must be a multiple of %d",
+template <bool kF16>
+static int launch_folded(const char* who, const void* a_hi, const void* a_lo, const float* row_scale_inv, int n_seg,
+                         int n_frames, int n_fft, const void* basis_hi, const void* basis_lo, float basis_scale_inv,
+                         int n_bins_pad, const float* p0, float w0, int epilogue, float power, float* out0,
+                         int n_out_bins, rvb_stream_t stream) {
+  constexpr int kBlockK = kF16 ? 2 * BLOCK_K : BLOCK_K;
+  constexpr int kElem = kF16 ? 2 : 4;
+  RVB_REQUIRE(a_hi && a_lo && basis_hi && basis_lo && out0, "%s: null pointer", who);
+  RVB_REQUIRE(!kF16 || row_scale_inv, "%s: null row_scale_inv", who);
+  RVB_REQUIRE(n_seg > 0 && n_frames > 0, "%s: bad shape", who);
+  RVB_REQUIRE(n_fft % (2 * kBlockK) == 0 && n_fft >= 2 * kBlockK, "%s: n_fft %d must be a multiple of %d", who, n_fft,
+              2 * kBlockK);
+  RVB_REQUIRE(n_bins_pad % F_BLOCK_N == 0 && n_bins_pad > 0, "%s: n_bins_pad %d must be a multiple of %d", who,
               n_bins_pad, F_BLOCK_N);
-  RVB_REQUIRE(epilogue_ok(epilogue), "rvb_stft_gemm_folded: bad epilogue %d", epilogue);
-  RVB_REQUIRE(n_out_bins > 0, "rvb_stft_gemm_folded: n_out_bins must be positive");
-  for (const void* ptr : {(const void*)a_hi, (const void*)a_lo, (const void*)basis_hi, (const void*)basis_lo})
-    RVB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 127u) == 0, "rvb_stft_gemm_folded: operands must be 128-byte aligned");
+  RVB_REQUIRE(epilogue_ok(epilogue), "%s: bad epilogue %d", who, epilogue);
+  RVB_REQUIRE(n_out_bins > 0, "%s: n_out_bins must be positive", who);
+  RVB_REQUIRE(w0 == 0.f || p0 != nullptr, "%s: w0 != 0 needs p0", who);
+  for (const void* ptr : {a_hi, a_lo, basis_hi, basis_lo})
+    RVB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 127u) == 0, "%s: operands must be 128-byte aligned", who);
   const int half = n_fft / 2;
   const int64_t m_rows = (int64_t)n_seg * n_frames;
-  RVB_REQUIRE(2 * m_rows < (1ll << 31), "rvb_stft_gemm_folded: too many frames");
+  RVB_REQUIRE(2 * m_rows < (1ll << 31), "%s: too many frames", who);
 
   CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
   int rc;
-  if ((rc = make_map_2d(&tm_a_hi, a_hi, half, 2 * m_rows, BLOCK_K, BLOCK_M)) != RVB_OK) return rc;
-  if ((rc = make_map_2d(&tm_a_lo, a_lo, half, 2 * m_rows, BLOCK_K, BLOCK_M)) != RVB_OK) return rc;
-  if ((rc = make_map_2d(&tm_b_hi, basis_hi, half, 2 * (uint64_t)n_bins_pad, BLOCK_K, F_BLOCK_N)) != RVB_OK) return rc;
-  if ((rc = make_map_2d(&tm_b_lo, basis_lo, half, 2 * (uint64_t)n_bins_pad, BLOCK_K, F_BLOCK_N)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_a_hi, a_hi, half, 2 * m_rows, kBlockK, BLOCK_M, kElem)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_a_lo, a_lo, half, 2 * m_rows, kBlockK, BLOCK_M, kElem)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_b_hi, basis_hi, half, 2 * (uint64_t)n_bins_pad, kBlockK, F_BLOCK_N, kElem)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_b_lo, basis_lo, half, 2 * (uint64_t)n_bins_pad, kBlockK, F_BLOCK_N, kElem)) != RVB_OK) return rc;
 
   FoldParams p;
   p.n_frames = n_frames; p.m_rows = m_rows; p.n_bins_pad = n_bins_pad; p.half = half;
@@ -640,32 +683,67 @@ extern "C" int rvb_stft_gemm_folded(const float* a_hi, const float* a_lo, int n_
   p.epilogue = epilogue; p.n_out_bins = n_out_bins;
   p.n_store_bins = n_out_bins < n_bins_pad ? n_out_bins : n_bins_pad;
   p.power = power; p.w0 = w0; p.p0 = (w0 != 0.f) ? p0 : nullptr; p.out0 = out0;
-  RVB_REQUIRE(w0 == 0.f || p0 != nullptr, "rvb_stft_gemm_folded: w0 != 0 needs p0");
+  p.row_scale_inv = row_scale_inv; p.basis_scale_inv = basis_scale_inv;
 
   static bool attr_set = false;
   if (!attr_set) {
-    RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+    RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_kernel<kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
     attr_set = true;
   }
   const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
   const int grid = (int)(n_units < num_sms() ? n_units : num_sms());
-  stft_gemm_fold_kernel<<<grid, NUM_THREADS, F_SMEM_BYTES, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo, tm_b_hi,
-                                                                                      tm_b_lo, p);
+  stft_gemm_fold_kernel<kF16><<<grid, NUM_THREADS, F_SMEM_BYTES, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo, tm_b_hi,
+                                                                                            tm_b_lo, p);
   count_launch();
-  return check_launch("stft_gemm_fold_kernel");
+  return check_launch(kF16 ? "stft_gemm_fold_kernel<f16>" : "stft_gemm_fold_kernel<tf32>");
+}
+
+extern "C" int rvb_stft_gemm_folded(const float* a_hi, const float* a_lo, int n_seg, int n_frames, int n_fft,
+                                    const float* basis_hi, const float* basis_lo, int n_bins_pad, const float* p0,
+                                    float w0, int epilogue, float power, float* out0, int n_out_bins,
+                                    rvb_stream_t stream) {
+  return launch_folded<false>("rvb_stft_gemm_folded", a_hi, a_lo, nullptr, n_seg, n_frames, n_fft, basis_hi, basis_lo,
+                              1.f, n_bins_pad, p0, w0, epilogue, power, out0, n_out_bins, stream);
+}
+
+extern "C" int rvb_stft_gemm_folded_f16(const void* a_hi, const void* a_lo, const float* row_scale_inv, int n_seg,
+                                        int n_frames, int n_fft, const void* basis_hi, const void* basis_lo,
+                                        float basis_scale_inv, int n_bins_pad, const float* p0, float w0, int epilogue,
+                                        float power, float* out0, int n_out_bins, rvb_stream_t stream) {
+  return launch_folded<true>("rvb_stft_gemm_folded_f16", a_hi, a_lo, row_scale_inv, n_seg, n_frames, n_fft, basis_hi,
+                             basis_lo, basis_scale_inv, n_bins_pad, p0, w0, epilogue, power, out0, n_out_bins, stream);
+}
+
+template <typename T>
+static int launch_bin_folded(const char* who, const T* a_hi, const T* a_lo, const float* row_scale_inv, int n_seg,
+                             int n_frames, int n_fft, const float* wc_row, const float* ws_row, const float* p0,
+                             float w0, int bin, int epilogue, float power, float* out0, int n_out_bins,
+                             rvb_stream_t stream) {
+  RVB_REQUIRE(a_hi && a_lo && wc_row && ws_row && out0, "%s: null pointer", who);
+  RVB_REQUIRE(n_seg > 0 && n_frames > 0 && bin >= 0 && bin < n_out_bins, "%s: bad shape", who);
+  RVB_REQUIRE(epilogue_ok(epilogue), "%s: bad epilogue %d", who, epilogue);
+  RVB_REQUIRE(w0 == 0.f || p0 != nullptr, "%s: w0 != 0 needs p0", who);
+  const int64_t m_rows = (int64_t)n_seg * n_frames;
+  stft_bin_fold_kernel<T><<<(unsigned)((m_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      a_hi, a_lo, row_scale_inv, m_rows, n_frames, n_fft / 2, wc_row, ws_row, (w0 != 0.f) ? p0 : nullptr, w0, bin,
+      epilogue, power, out0, n_out_bins);
+  count_launch();
+  return check_launch("stft_bin_fold_kernel");
 }
 
 extern "C" int rvb_stft_bin_folded(const float* a_hi, const float* a_lo, int n_seg, int n_frames, int n_fft,
                                    const float* wc_row, const float* ws_row, const float* p0, float w0, int bin,
                                    int epilogue, float power, float* out0, int n_out_bins, rvb_stream_t stream) {
-  RVB_REQUIRE(a_hi && a_lo && wc_row && ws_row && out0, "rvb_stft_bin_folded: null pointer");
-  RVB_REQUIRE(n_seg > 0 && n_frames > 0 && bin >= 0 && bin < n_out_bins, "rvb_stft_bin_folded: bad shape");
-  RVB_REQUIRE(epilogue_ok(epilogue), "rvb_stft_bin_folded: bad epilogue %d", epilogue);
-  RVB_REQUIRE(w0 == 0.f || p0 != nullptr, "rvb_stft_bin_folded: w0 != 0 needs p0");
-  const int64_t m_rows = (int64_t)n_seg * n_frames;
-  stft_bin_fold_kernel<<<(unsigned)((m_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      a_hi, a_lo, m_rows, n_frames, n_fft / 2, wc_row, ws_row, (w0 != 0.f) ? p0 : nullptr, w0, bin, epilogue, power,
-      out0, n_out_bins);
-  count_launch();
-  return check_launch("stft_bin_fold_kernel");
+  return launch_bin_folded<float>("rvb_stft_bin_folded", a_hi, a_lo, nullptr, n_seg, n_frames, n_fft, wc_row, ws_row,
+                                  p0, w0, bin, epilogue, power, out0, n_out_bins, stream);
+}
+
+extern "C" int rvb_stft_bin_folded_f16(const void* a_hi, const void* a_lo, const float* row_scale_inv, int n_seg,
+                                       int n_frames, int n_fft, const float* wc_row, const float* ws_row,
+                                       const float* p0, float w0, int bin, int epilogue, float power, float* out0,
+                                       int n_out_bins, rvb_stream_t stream) {
+  RVB_REQUIRE(row_scale_inv, "rvb_stft_bin_folded_f16: null row_scale_inv");
+  return launch_bin_folded<__half>("rvb_stft_bin_folded_f16", static_cast<const __half*>(a_hi),
+                                   static_cast<const __half*>(a_lo), row_scale_inv, n_seg, n_frames, n_fft, wc_row,
+                                   ws_row, p0, w0, bin, epilogue, power, out0, n_out_bins, stream);
 }

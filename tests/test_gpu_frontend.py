@@ -27,18 +27,24 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.fixture(scope="module", params=["folded", "direct"])
+@pytest.fixture(scope="module", params=["folded_f16", "folded_tf32", "direct"])
 def mel(R, dev, request):
-    """Both contraction kernels: the folded one (symmetric window, default) and the unfolded one."""
+    """All three contraction kernels: folded 3xFP16 (symmetric window, the default), folded 3xTF32, and the
+    unfolded 3xTF32 one."""
     import os
     m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
     if request.param == "direct":
         os.environ["RVB_NO_FOLD"] = "1"
+    if request.param == "folded_tf32":
+        os.environ["RVB_STFT_OPERAND"] = "tf32"
     try:
-        tb = m.stft._device_tables()                          # tables are built here, under the env switch
+        tb = m.stft._device_tables()                          # tables are built here, under the env switches
     finally:
         os.environ.pop("RVB_NO_FOLD", None)
+        os.environ.pop("RVB_STFT_OPERAND", None)
     assert (tb["fold"] is None) == (request.param == "direct")
+    if tb["fold"] is not None:
+        assert tb["fold"]["operand"] == request.param[len("folded_"):]
     return m
 
 
@@ -62,6 +68,54 @@ def test_fold_split_matches_numpy(R, dev):
     assert np.abs(got[0, 1] + got[1, 1] - o).max() < 2.0 ** -20
     assert np.all((planes.cpu().numpy().view(np.uint32) & 0x1FFF) == 0)      # every plane value is a tf32 number
     assert np.array_equal(p0.cpu().numpy(), fr[:, 0].astype(np.float32))
+
+
+def test_fold_split_f16_matches_numpy(R, dev):
+    """Block-scaled fp16 planes: (hi + lo) * row_scale_inv reconstructs e / o to 2^-21 of the row maximum, the
+    scaled row maximum sits in [2^14, 2^15), all-zero rows get scale 1 -- for quiet, normal and loud audio."""
+    from reconvat_b200 import synth
+    base = synth.to_float(np.stack([synth.white_int16(16385, 1), synth.music_int16(16385, 2), synth.white_int16(16385, 3),
+                                    synth.music_int16(16385, 4), synth.white_int16(16385, 5)]))
+    base[2] *= 3e-6; base[3] *= 700.0; base[4, :9000] = 0.0                # quiet, loud, partly silent
+    a = torch.from_numpy(base)
+    xd = a.to(dev)[:, :-1]
+    nb, L, N, hop, T = 5, 16384, 2048, 512, 33
+    planes = torch.full((2, 2, nb * T, N // 2), float("nan"), dtype=torch.float16, device=dev)
+    inv = torch.empty(nb * T, device=dev)
+    p0 = torch.empty(nb * T, device=dev)
+    R._lib.call("rvb_fold_split_f16", xd.data_ptr(), xd.stride(0), nb, L, 1024, 0, N, hop, T, planes[0].data_ptr(),
+                planes[1].data_ptr(), inv.data_ptr(), p0.data_ptr())
+    p = np.pad(a[:, :-1].numpy(), [(0, 0), (1024, 1024)], mode="reflect")
+    fr = np.lib.stride_tricks.sliding_window_view(p, N, axis=1)[:, ::hop].reshape(nb * T, N)
+    e = np.empty((nb * T, N // 2), np.float32); o = np.zeros((nb * T, N // 2), np.float32)
+    e[:, :-1] = fr[:, 1:N // 2] + fr[:, N - 1:N // 2:-1]; e[:, -1] = fr[:, N // 2]      # fp32 adds, as the kernel
+    o[:, :-1] = fr[:, 1:N // 2] - fr[:, N - 1:N // 2:-1]
+    got = planes.cpu().numpy().astype(np.float64)
+    assert np.isfinite(got).all()
+    inv = inv.cpu().numpy().astype(np.float64)
+    rmax = np.maximum(np.abs(e).max(1), np.abs(o).max(1)).astype(np.float64)
+    zero = rmax == 0
+    assert zero.any() and np.all(inv[zero] == 1.0)
+    assert np.all(np.log2(inv) == np.round(np.log2(inv)))                  # exact powers of two
+    smax = rmax[~zero] / inv[~zero]
+    assert smax.min() >= 2.0 ** 14 and smax.max() < 2.0 ** 15
+    for plane, want in ((0, e), (1, o)):
+        rec = (got[0, plane] + got[1, plane]) * inv[:, None]
+        assert (np.abs(rec - want) <= 2.0 ** -21 * rmax[:, None]).all()
+    assert np.array_equal(p0.cpu().numpy(), fr[:, 0])
+
+
+def test_frontend_amplitude_range(R, dev):
+    """Quiet (-110 dB), loud (x700) and partly silent audio through the block-scaled fp16 contraction."""
+    from oracle.frontend import FrontEndOracle
+    from reconvat_b200 import synth
+    a = synth.to_float(np.stack([synth.music_int16(16385, 11), synth.white_int16(16385, 12), synth.music_int16(16385, 13)]))
+    a[0] *= 3e-6; a[1] *= 700.0; a[2, 4000:12000] = 0.0
+    m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    assert m.stft._device_tables()["fold"]["operand"] == "f16"
+    lm = torch.log(m(torch.from_numpy(a).to(dev)[:, :-1]) + 1e-5).cpu().numpy()
+    ref = FrontEndOracle().log_mel(a[:, :-1].astype(np.float64), np.float64)
+    assert relerr(lm, ref) < LOGMEL_TOL
 
 
 def test_pad_split_bit_exact(R, dev):
@@ -144,16 +198,20 @@ def test_frontend_min_length_and_errors(mel, dev, golden):
     ("win_short", dict(n_fft=512, win_length=400, hop_length=160)),
     ("hamming", dict(n_fft=512, hop_length=128, window="hamming")),
 ])
-@pytest.mark.parametrize("path", ["auto", "direct"])
+@pytest.mark.parametrize("path", ["auto", "tf32", "direct"])
 def test_stft_formats_golden(R, dev, golden, tag, kw, path, monkeypatch):
     from reconvat_b200 import synth
     g = golden["stft_formats"]
     a = torch.from_numpy(synth.to_float(g["audio_int16"])).to(dev)
     if path == "direct":
         monkeypatch.setenv("RVB_NO_FOLD", "1")
+    if path == "tf32":
+        monkeypatch.setenv("RVB_STFT_OPERAND", "tf32")
     st = R.Spectrogram.STFT(verbose=False, **kw).to(dev)
-    folded = st._device_tables()["fold"] is not None
-    assert folded == (path == "auto")                          # every golden STFT config has a symmetric basis
+    fold = st._device_tables()["fold"]
+    assert (fold is not None) == (path != "direct")            # every golden STFT config has a symmetric basis
+    if fold is not None:
+        assert fold["operand"] == ("tf32" if path == "tf32" else "f16")
     c = st(a, output_format="Complex").cpu().numpy()
     ref = g[tag + "_complex"]
     assert c.shape == ref.shape

@@ -74,6 +74,24 @@ def test_band_rows_roundtrip_and_rejection():
         assert basis.band_rows(basis.mel_filterbank(**kw))[2].shape[0] <= 64
 
 
+def test_f16_fold_operand_is_block_scaled_and_reconstructs():
+    ks, kc, _, _, win = basis.fourier_basis(2048, sr=16000)
+    wcos, wsin = kc * win, ks * win
+    f16 = basis.fold_operand(wcos, wsin, operand="f16")
+    t32 = basis.fold_operand(wcos, wsin, operand="tf32")
+    assert f16["basis_hi"].dtype == np.float16 and f16["basis_lo"].dtype == np.float16
+    assert f16["basis_hi"].shape == t32["basis_hi"].shape == (2048, 1024)
+    hi = f16["basis_hi"].astype(np.float64)
+    assert np.isfinite(hi).all() and 2.0 ** 14 <= np.abs(hi).max() <= 2.0 ** 15
+    assert np.log2(f16["scale_inv"]) == round(np.log2(f16["scale_inv"]))
+    rec16 = (hi + f16["basis_lo"].astype(np.float64)) * f16["scale_inv"]
+    rec32 = t32["basis_hi"].astype(np.float64) + t32["basis_lo"].astype(np.float64)
+    # both splits carry 22 bits: they agree to 2^-21 of the element, or 2^-38 absolute where the fp16 lo is subnormal
+    assert (np.abs(rec16 - rec32) <= 2.0 ** -21 * np.abs(rec32) + 2.0 ** -38).all()
+    with pytest.raises(ValueError):
+        basis.fold_operand(wcos, wsin, operand="bf16")
+
+
 def test_tf32_split_reconstructs_to_2_pow_minus_21():
     rng = np.random.default_rng(0)
     x = (rng.standard_normal(100000) * np.exp(rng.uniform(-20, 5, 100000))).astype(np.float32)
