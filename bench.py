@@ -29,6 +29,7 @@ HBM_BYTES_PER_SEG = {
     "rvb_pad_split": 1310716 + 2 * 1318912,
     "rvb_fold_split": 1310716 + 4 * 640 * 1024 * 4,       # R audio, W e/o hi/lo tf32 operand planes
     "rvb_fold_split_f16": 1310716 + 4 * 640 * 1024 * 2 + 640 * 4,   # R audio, W e/o hi/lo fp16 planes + row scales
+    "rvb_fold_split_f16_pcm16": 1310716 // 2 + 4 * 640 * 1024 * 2 + 640 * 4,
     "rvb_mel_project": 1020 * 640 * 4 + N4,
     "rvb_normalise": 2 * N4,
     "rvb_vat_perturb": 3 * N4,
@@ -81,20 +82,29 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def make_audio(n_batches, batch, seed):
-    """n_batches x (batch, SEG_SAMPLES) float32: white and music-like int16-quantised segments.  A few unique
-    segments are generated and circularly shifted to fill the batches (generation is CPU-expensive)."""
+def make_audio(n_batches, batch, seed, pcm16=False):
+    """n_batches x (batch, SEG_SAMPLES): white and music-like segments, PCM int16 as the dataset stores them
+    (model/dataset.py:62) or already converted to float32.  A few unique segments are generated and circularly
+    shifted to fill the batches (generation is CPU-expensive)."""
     import numpy as np
     from reconvat_b200 import synth
-    uniq = [synth.to_float(synth.white_int16(SEG_SAMPLES, seed + 1)), synth.to_float(synth.music_int16(SEG_SAMPLES, seed + 2)),
-            synth.to_float(synth.music_int16(SEG_SAMPLES, seed + 3)), synth.to_float(synth.white_int16(SEG_SAMPLES, seed + 4))]
+    uniq = [synth.white_int16(SEG_SAMPLES, seed + 1), synth.music_int16(SEG_SAMPLES, seed + 2),
+            synth.music_int16(SEG_SAMPLES, seed + 3), synth.white_int16(SEG_SAMPLES, seed + 4)]
+    if not pcm16:
+        uniq = [synth.to_float(u) for u in uniq]
     out = []
     for n in range(n_batches):
-        a = np.empty((batch, SEG_SAMPLES), np.float32)
+        a = np.empty((batch, SEG_SAMPLES), np.int16 if pcm16 else np.float32)
         for b in range(batch):
             a[b] = np.roll(uniq[(n + b) % 4], 4099 * (n * batch + b))
         out.append(a)
     return out
+
+
+def to_float_cpu(audio):
+    """The dataset's conversion on the host (model/dataset.py:62); part of the CPU arm when the input is PCM16."""
+    import torch
+    return audio.float().div_(32768.0) if audio.dtype == torch.int16 else audio
 
 
 def make_model(args, batch, dev):
@@ -116,16 +126,16 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sample = min(args.batch, args.cpu_batch)
-    audio = torch.from_numpy(make_audio(1, sample, 0)[0])
+    audio = torch.from_numpy(make_audio(1, sample, 0, pcm16=args.input == "pcm16")[0])
     model = make_model(args, sample, None)
     path = CpuHotPath()
     torch.manual_seed(0)
     for _ in range(max(1, min(args.warmup, 2))):
-        path.step(model, audio)
+        path.step(model, to_float_cpu(audio))
     steps = max(1, min(args.steps, args.cpu_steps))
     t0 = time.perf_counter()
     for _ in range(steps):
-        loss, rn = path.step(model, audio)
+        loss, rn = path.step(model, to_float_cpu(audio))
         loss.item()
     dt = (time.perf_counter() - t0) / steps
     value = sample * SEG_SECONDS / dt
@@ -134,7 +144,8 @@ def run_reference(args, rank, world):
         "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "Mel+VAT step (front-end + UNet_VAT, network = %s), CPU, %d x 20.48 s "
-                               "segments per step (bounded sample of the B=%d workload)" % (args.model, sample, args.batch)},
+                               "segments per step (bounded sample of the B=%d workload), input %s"
+                               % (args.model, sample, args.batch, args.input)},
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
                          "sample": "%d segments x %d steps, oracle/cpu_path.py (the reference's ATen op sequence; the "
                                    "reference is Python and /root/reference does not travel)" % (sample, steps)},
@@ -158,8 +169,9 @@ def run_ours(args, rank, local_rank, world):
     from reconvat_b200.pipeline import HotPathStep
 
     B = args.batch
-    n_rot = max(4, -(-130 * 2 ** 20 // (B * SEG_SAMPLES * 4)))      # rotate inputs over > L2 (126 MB)
-    host = [torch.from_numpy(a).pin_memory() for a in make_audio(n_rot, B, 100 * rank)]
+    pcm16 = args.input == "pcm16"
+    n_rot = max(4, -(-130 * 2 ** 20 // (B * SEG_SAMPLES * (2 if pcm16 else 4))))   # rotate inputs over > L2 (126 MB)
+    host = [torch.from_numpy(a).pin_memory() for a in make_audio(n_rot, B, 100 * rank, pcm16=pcm16)]
     dev_audio = [h.to(dev) for h in host]
     model = make_model(args, B, dev)
     step = HotPathStep(model, dev)
@@ -181,36 +193,55 @@ def run_ours(args, rank, local_rank, world):
     for i in range(args.warmup):
         step(dev_audio[i % n_rot])
     step.vat_loss.check()
+    if not args.no_graphs:
+        step.capture(dev_audio)                              # one CUDA graph of the whole step per input buffer
+        for i in range(args.warmup):
+            step.replay(i % n_rot)
     sampler = ClockSampler(local_rank)
-    kernel_names = ["rvb_stft_gemm", "rvb_stft_gemm_folded", "rvb_stft_gemm_folded_f16"] + list(HBM_BYTES_PER_SEG)
     barrier()
     sampler.start()
-    log = R._lib.record_events(kernel_names)
     launches0 = R._lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i in range(args.steps):
-        vat_loss, r_norm, _, _ = step(dev_audio[i % n_rot])
+    if args.no_graphs:
+        for i in range(args.steps):
+            step(dev_audio[i % n_rot])
+    else:
+        for i in range(args.steps):
+            step.replay(i % n_rot)
     ev1.record()
     barrier()
-    launches = R._lib.launch_count() - launches0
-    R._lib.record_events(None)
+    launches = (R._lib.launch_count() - launches0) if args.no_graphs else step.kernels_per_graph * args.steps
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    step.vat_loss.check()
+    step.check()
     ms_step = ms_total / args.steps
     value = world * B * SEG_SECONDS / (ms_step * 1e-3)
 
-    # per-kernel durations from the events recorded inside the timed region
+    # per-kernel durations: the same K steps launched eagerly with CUDA events around every entry point, on the
+    # launching stream (events cannot be read back from inside a replayed graph)
+    kernel_names = ["rvb_stft_gemm", "rvb_stft_gemm_folded", "rvb_stft_gemm_folded_f16"] + list(HBM_BYTES_PER_SEG)
+    barrier()
+    log = R._lib.record_events(kernel_names)
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    for i in range(args.steps):
+        step(dev_audio[i % n_rot])
+    ev3.record()
+    barrier()
+    R._lib.record_events(None)
+    step.vat_loss.check()
+    eager_ms_step = ev2.elapsed_time(ev3) / args.steps
     kms = {n: [s.elapsed_time(e) for s, e in v] for n, v in log.items() if v}
     kavg = {n: sum(v) / len(v) for n, v in kms.items()}
 
     # ---------------- end to end from pinned host memory ("e2e") ----------------
     results = torch.zeros((args.steps, 2), dtype=torch.float32).pin_memory()
-    step.run_host([host[i % n_rot] for i in range(3)], torch.zeros((3, 2), dtype=torch.float32).pin_memory())
+    step.run_host([host[i % n_rot] for i in range(3)], torch.zeros((3, 2), dtype=torch.float32).pin_memory(),
+                  use_graphs=not args.no_graphs)
     barrier()
     t0 = time.perf_counter()
     ev0.record()
-    n_done = step.run_host((host[i % n_rot] for i in range(args.steps)), results)
+    n_done = step.run_host((host[i % n_rot] for i in range(args.steps)), results, use_graphs=not args.no_graphs)
     ev1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -265,10 +296,10 @@ def run_ours(args, rank, local_rank, world):
         audio = host[0][:cb].clone()
         cm = make_model(args, cb, None)
         path = CpuHotPath()
-        path.step(cm, audio)
+        path.step(cm, to_float_cpu(audio))
         t0 = time.perf_counter()
         for _ in range(args.cpu_steps):
-            path.step(cm, audio)[0].item()
+            path.step(cm, to_float_cpu(audio))[0].item()
         dt = (time.perf_counter() - t0) / args.cpu_steps
         cpu = {"value": cb * SEG_SECONDS / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
                "sample": "%d segments x %d steps of the same step on the host CPU (oracle/cpu_path.py: the reference's "
@@ -283,13 +314,19 @@ def run_ours(args, rank, local_rank, world):
                                "(hot path only)" if args.model == "injected" else "stand-in linear transcriber (PyTorch)"),
                    "batch_per_gpu": B, "segment_samples": SEG_SAMPLES, "parallelism": "segments sharded, dp%d, no "
                    "collective on the path" % world,
-                   "cache": "inputs rotated over %d batches = %.0f MB > 126 MB L2" % (n_rot, n_rot * B * SEG_SAMPLES * 4 / 1e6)},
+                   "input": "PCM int16 as the dataset stores it (model/dataset.py:62), scaled by 1/32768 on the device"
+                            if pcm16 else "float32 in [-1, 1)",
+                   "cache": "inputs rotated over %d batches = %.0f MB > 126 MB L2"
+                            % (n_rot, n_rot * B * SEG_SAMPLES * (2 if pcm16 else 4) / 1e6),
+                   "launch": "eager" if args.no_graphs else "CUDA graph replay, one graph of the whole step per input "
+                             "buffer (%d librvb kernels per graph)" % step.kernels_per_graph},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": B * SEG_SAMPLES * 4,
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": B * SEG_SAMPLES * (2 if pcm16 else 4),
                 "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / n_done,
                 "api": "reconvat_b200.pipeline.HotPathStep.run_host (pinned host audio in, (vat_loss, r_norm) out; "
-                       "copy of batch i+1 overlapped with the kernels of batch i)"},
+                       "copy of batch i+1 overlapped with the kernels of batch i%s)" % ("" if args.no_graphs else "; graph replay")},
         "gpu_launches": launches,
+        "eager_ms_per_step": eager_ms_step,
         "roofline": roofline,
         "hbm_kernels": hbm,
         "cpu_baseline": cpu,
@@ -307,6 +344,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8, help="segments per CPU-baseline step")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--input", default="pcm16", choices=["pcm16", "f32"],
+                    help="audio format handed to the front-end: the dataset's PCM int16 (default) or float32")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--model", default="injected", choices=["injected", "standin"],
                     help="the black-box network the VAT loop calls (see make_model)")
     args = ap.parse_args()

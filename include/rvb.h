@@ -135,6 +135,11 @@ int rvb_stft_bin_folded(const float* a_hi, const float* a_lo, int n_seg, int n_f
 int rvb_fold_split_f16(const float* audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int pad_mode,
                        int n_fft, int hop, int n_frames, void* a_hi, void* a_lo, float* row_scale_inv, float* p0,
                        rvb_stream_t stream);
+/* PCM16 input as the dataset stores it: sample = pcm * gain with gain = 1/32768 (model/dataset.py:62,
+ * `audio.float().div_(32768.0)`; exact in fp32).  Halves the host->device bytes of the front-end. */
+int rvb_fold_split_f16_pcm16(const int16_t* audio, int64_t audio_ld, float gain, int n_seg, int n_samples, int pad,
+                             int pad_mode, int n_fft, int hop, int n_frames, void* a_hi, void* a_lo,
+                             float* row_scale_inv, float* p0, rvb_stream_t stream);
 int rvb_stft_gemm_folded_f16(const void* a_hi, const void* a_lo, const float* row_scale_inv, int n_seg, int n_frames,
                              int n_fft, const void* basis_hi, const void* basis_lo, float basis_scale_inv,
                              int n_bins_pad, const float* p0, float w0, int epilogue, float power, float* out0,

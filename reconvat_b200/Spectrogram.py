@@ -134,8 +134,8 @@ class STFT(nn.Module):
             raise _lib.RvbError("reconvat_b200.STFT: input is on %s; there is no CPU path" % x.device)
         if x.requires_grad:
             raise NotImplementedError("reconvat_b200.STFT: gradients w.r.t. the waveform are not provided")
-        if x.dtype != torch.float32:
-            raise _lib.RvbError("reconvat_b200.STFT: expected float32 audio, got %s" % x.dtype)
+        if x.dtype not in (torch.float32, torch.int16):
+            raise _lib.RvbError("reconvat_b200.STFT: expected float32 (or PCM int16) audio, got %s" % x.dtype)
         x2 = x[:, 0, :]
         return x2 if x2.stride(-1) == 1 else x2.contiguous()
 
@@ -147,10 +147,14 @@ class STFT(nn.Module):
         ``make_out(B, n_frames)`` -> (out tensor, n_out_bins).  Returns (out, n_frames)."""
         x2 = self._check_input(x)
         B, L = x2.shape
-        ld = x2.stride(0) if B > 1 else L
         mode, n_frames, rows = self._geometry(L)
         out, n_out_bins = make_out(B, n_frames)
         tb = self._device_tables()
+        pcm16 = x2.dtype == torch.int16
+        if pcm16 and not (tb["fold"] is not None and tb["fold"]["operand"] == "f16"):
+            x2 = x2.to(torch.float32).div_(32768.0)          # model/dataset.py:62; only the fp16 fold reads PCM16 itself
+            pcm16 = False
+        ld = x2.stride(0) if B > 1 else L
         if tb["fold"] is not None:
             fd = tb["fold"]
             half, M = self.n_fft // 2, B * n_frames
@@ -159,8 +163,14 @@ class STFT(nn.Module):
             if fd["operand"] == "f16":
                 planes = torch.empty((2, 2, M, half), dtype=torch.float16, device=x.device)  # [hi|lo][e|o][frame][c]
                 row_inv = torch.empty((M,), dtype=torch.float32, device=x.device)
-                _lib.call("rvb_fold_split_f16", _lib.ptr(x2), ld, B, L, self.pad_amount, mode, self.n_fft, self.stride,
-                          n_frames, planes[0].data_ptr(), planes[1].data_ptr(), row_inv.data_ptr(), p0_ptr)
+                if pcm16:
+                    _lib.call("rvb_fold_split_f16_pcm16", _lib.ptr(x2, torch.int16), ld, 1.0 / 32768.0, B, L,
+                              self.pad_amount, mode, self.n_fft, self.stride, n_frames, planes[0].data_ptr(),
+                              planes[1].data_ptr(), row_inv.data_ptr(), p0_ptr)
+                else:
+                    _lib.call("rvb_fold_split_f16", _lib.ptr(x2), ld, B, L, self.pad_amount, mode, self.n_fft,
+                              self.stride, n_frames, planes[0].data_ptr(), planes[1].data_ptr(), row_inv.data_ptr(),
+                              p0_ptr)
                 _lib.call("rvb_stft_gemm_folded_f16", planes[0].data_ptr(), planes[1].data_ptr(), row_inv.data_ptr(),
                           B, n_frames, self.n_fft, fd["basis_hi"].data_ptr(), fd["basis_lo"].data_ptr(),
                           fd["scale_inv"], fd["n_bins_pad"], p0_ptr, fd["w0"], epilogue, float(power), _lib.ptr(out),
@@ -317,7 +327,8 @@ class MelSpectrogram(nn.Module):
             spec = Normalization('imagewise').transform(spec); spec = spec.transpose(-1,-2).unsqueeze(1)
 
         Returns a contiguous (B, 1, T, n_mels) tensor ((B, T, n_mels) when ``channel_dim=False``, the
-        O&F convention of model/onset_frame_VAT.py:647-651).  ``audio`` is (B, L) / (L) / (B,1,L).
+        O&F convention of model/onset_frame_VAT.py:647-651).  ``audio`` is (B, L) / (L) / (B,1,L), float32 or
+        the dataset's PCM int16 (then scaled by 1/32768 on the device, model/dataset.py:62).
         """
         x = basis.broadcast_dim(audio)
         if trim_last:

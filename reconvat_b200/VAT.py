@@ -127,7 +127,9 @@ class _VATCore(nn.Module):
         self.KL_Div = KL_Div
         self.binwise = binwise
         self.strict = bool(int(os.environ.get("RVB_STRICT_NAN", "0"))) if strict is None else strict
-        self._pending = None       # (flag tensor, pinned host copy, event)
+        self._pending = None       # (pinned host copy of the NaN flag, event) of the previous eager call
+        self._host_flag = None     # persistent pinned int32 (allocated once: no per-call cudaHostAlloc)
+        self.last_flag = None      # device flag of the latest call (what a captured CUDA graph leaves behind)
         if KL_Div:
             raise NotImplementedError("reconvat_b200 VAT: KL_Div=True (binary_kl_div, model/self_attention_VAT.py:"
                                       "248-255) is not on any shipped configuration; SURVEY.md section 8 row f4")
@@ -140,14 +142,20 @@ class _VATCore(nn.Module):
                                       % (n_power,))
 
     # -- deferred NaN / Inf assertion ---------------------------------------------------------
-    def check(self):
-        """Raise the reference's AssertionError if the previous call produced NaN/Inf in r_adv."""
-        if self._pending is None:
+    def check(self, flag=None):
+        """Raise the reference's AssertionError if the previous call produced NaN/Inf in r_adv.
+        ``flag``: a device flag to test instead (e.g. ``last_flag`` after replaying a captured graph; this
+        synchronises with the device)."""
+        if flag is not None:
+            bad = int(flag.item()) != 0
+        elif self._pending is not None:
+            host, event = self._pending
+            self._pending = None
+            event.synchronize()
+            bad = int(host.item()) != 0
+        else:
             return
-        host, event = self._pending
-        self._pending = None
-        event.synchronize()
-        if int(host.item()) != 0:
+        if bad:
             raise AssertionError(self._nan_message.format(dmin="nan", dmax="nan", dmean="nan"))
 
     def _model_outputs(self, model, x):
@@ -155,8 +163,9 @@ class _VATCore(nn.Module):
         return [out[i] for i in self._heads]
 
     def forward(self, model, x):
-        self.check()
         x = _check_input(x).detach()
+        if not torch.cuda.is_current_stream_capturing():
+            self.check()
         n_rows, row_len = _rows(x)
         with torch.no_grad():
             y_ref = [y.detach() for y in self._model_outputs(model, x)]   # labels, no grad (…:163-164)
@@ -183,13 +192,17 @@ class _VATCore(nn.Module):
             _lib.call("rvb_vat_direct", d.data_ptr(), x.data_ptr(), r_adv.data_ptr(), x_adv2.data_ptr(),
                       d_hat.data_ptr(), n_rows, row_len, float(self.epsilon), int(self._clamp), flag.data_ptr())
 
-        host = torch.empty((), dtype=torch.int32, pin_memory=True)
-        host.copy_(flag, non_blocking=True)
-        event = torch.cuda.Event()
-        event.record()
-        self._pending = (host, event)
-        if self.strict:
-            self.check()
+        self.last_flag = flag
+        if not torch.cuda.is_current_stream_capturing():
+            # inside a CUDA-graph capture there is no host round trip: the owner of the graph tests last_flag
+            if self._host_flag is None:
+                self._host_flag = torch.empty((), dtype=torch.int32, pin_memory=True)
+            self._host_flag.copy_(flag, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record()
+            self._pending = (self._host_flag, event)
+            if self.strict:
+                self.check()
 
         y_pred = self._model_outputs(model, x_adv2)                       # graph to the parameters kept (…:195)
         losses = [bce_mean(p, y) for p, y in zip(y_pred, y_ref)]          # (…:200)

@@ -85,12 +85,23 @@ __device__ __forceinline__ float to_tf32(float v) {
 // Single-float formats (power / magnitude / phase / power_p) may carry RVB_EPI_TIME_MAJOR:
 //   bin-major  out0[(b*n_out_bins + k)*T + t]      what STFT.forward returns
 //   time-major out0[(b*T + t)*n_out_bins + k]      what the Mel kernel reads (16-byte stores per thread)
-__device__ __forceinline__ float stft_value(int epi, float power, float re, float im) {
+// RVB_EPI_POWER is evaluated as re^2 + im^2: the reference's sqrt followed by **2.0 (Spectrogram.py:227,231,458)
+// returns that value to within 1 ulp, and the IEEE sqrt sequence (MUFU + Newton + slow-path branch, x128 per
+// thread and tile) made the tensor-core epilogue instruction-fetch bound (profiles/r01c).
+static __device__ __noinline__ float stft_value_slow(int epi, float power, float re, float im) {
   if (epi == RVB_EPI_PHASE) return atan2f(-im + 0.0f, re);             // Spectrogram.py:237
-  float mag = sqrtf(re * re + im * im);                                 // Spectrogram.py:227,231
-  if (epi == RVB_EPI_POWER) mag = mag * mag;                            // **2.0 (Spectrogram.py:458)
-  else if (epi == RVB_EPI_POWER_P) mag = powf(mag, power);
-  return mag;
+  return powf(sqrtf(re * re + im * im), power);                         // general `power` (Spectrogram.py:458)
+}
+template <int kEpi>
+__device__ __forceinline__ float stft_value_t(float power, float re, float im) {
+  if constexpr (kEpi == RVB_EPI_POWER) return fmaf(re, re, im * im);
+  else if constexpr (kEpi == RVB_EPI_MAGNITUDE) return sqrtf(re * re + im * im);   // Spectrogram.py:227,231
+  else return stft_value_slow(kEpi, power, re, im);
+}
+__device__ __forceinline__ float stft_value(int epi, float power, float re, float im) {
+  if (epi == RVB_EPI_POWER) return stft_value_t<RVB_EPI_POWER>(power, re, im);
+  if (epi == RVB_EPI_MAGNITUDE) return stft_value_t<RVB_EPI_MAGNITUDE>(power, re, im);
+  return stft_value_slow(epi, power, re, im);
 }
 __device__ __forceinline__ void stft_store(int epilogue, float power, float re, float im, float* __restrict__ out0,
                                            int b, int k, int t, int n_out_bins, int n_frames) {
@@ -106,29 +117,66 @@ __device__ __forceinline__ void stft_store(int epilogue, float power, float re, 
 
 // Epilogue of one accumulator chunk: 32 consecutive bins [k0, k0+32) of frame (b, t) held by one thread.
 // `scale` undoes the power-of-two operand scaling of the fp16 contraction (1 for tf32 operands: exact either way).
+// One compact code path per (format, layout): the dispatch is per chunk, never per value.
+template <int kEpi, bool kTimeMajor>
+__device__ __forceinline__ void stft_store_chunk_t(float power, const uint32_t (&re)[32], const uint32_t (&im)[32],
+                                                   float scale, float re_add, float* __restrict__ out0, int b, int k0,
+                                                   int t, int n_out_bins, int n_store_bins, int n_frames) {
+  if constexpr (kTimeMajor) {
+    float* row = out0 + ((int64_t)b * n_frames + t) * n_out_bins + k0;
+    if (k0 + 32 <= n_store_bins && (n_out_bins & 3) == 0) {
+      float4* dst = reinterpret_cast<float4*>(row);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 v;
+        v.x = stft_value_t<kEpi>(power, fmaf(__uint_as_float(re[4 * i + 0]), scale, re_add), __uint_as_float(im[4 * i + 0]) * scale);
+        v.y = stft_value_t<kEpi>(power, fmaf(__uint_as_float(re[4 * i + 1]), scale, re_add), __uint_as_float(im[4 * i + 1]) * scale);
+        v.z = stft_value_t<kEpi>(power, fmaf(__uint_as_float(re[4 * i + 2]), scale, re_add), __uint_as_float(im[4 * i + 2]) * scale);
+        v.w = stft_value_t<kEpi>(power, fmaf(__uint_as_float(re[4 * i + 3]), scale, re_add), __uint_as_float(im[4 * i + 3]) * scale);
+        dst[i] = v;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (k0 + i < n_store_bins)
+          row[i] = stft_value_t<kEpi>(power, fmaf(__uint_as_float(re[i]), scale, re_add), __uint_as_float(im[i]) * scale);
+    }
+  } else {
+    const int64_t base = ((int64_t)b * n_out_bins + k0) * n_frames + t;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (k0 + i < n_store_bins) {
+        const float r = fmaf(__uint_as_float(re[i]), scale, re_add), m = __uint_as_float(im[i]) * scale;
+        if constexpr (kEpi == RVB_EPI_COMPLEX)
+          reinterpret_cast<float2*>(out0)[base + (int64_t)i * n_frames] = make_float2(r, -m);    // Spectrogram.py:234
+        else
+          out0[base + (int64_t)i * n_frames] = stft_value_t<kEpi>(power, r, m);
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void stft_store_chunk(int epilogue, float power, const uint32_t (&re)[32],
                                                  const uint32_t (&im)[32], float scale, float re_add,
                                                  float* __restrict__ out0, int b, int k0, int t, int n_out_bins,
                                                  int n_store_bins, int n_frames) {
-  const int epi = epilogue & 0xf;
-  if ((epilogue & RVB_EPI_TIME_MAJOR) && epi != RVB_EPI_COMPLEX && k0 + 32 <= n_store_bins && (n_out_bins & 3) == 0) {
-    float4* dst = reinterpret_cast<float4*>(out0 + ((int64_t)b * n_frames + t) * n_out_bins + k0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 v;
-      v.x = stft_value(epi, power, __uint_as_float(re[4 * i + 0]) * scale + re_add, __uint_as_float(im[4 * i + 0]) * scale);
-      v.y = stft_value(epi, power, __uint_as_float(re[4 * i + 1]) * scale + re_add, __uint_as_float(im[4 * i + 1]) * scale);
-      v.z = stft_value(epi, power, __uint_as_float(re[4 * i + 2]) * scale + re_add, __uint_as_float(im[4 * i + 2]) * scale);
-      v.w = stft_value(epi, power, __uint_as_float(re[4 * i + 3]) * scale + re_add, __uint_as_float(im[4 * i + 3]) * scale);
-      dst[i] = v;
-    }
-    return;
+#define RVB_EPI_CASE(E, TM)                                                                                         \
+  case (E) | ((TM) ? RVB_EPI_TIME_MAJOR : 0):                                                                       \
+    stft_store_chunk_t<E, TM>(power, re, im, scale, re_add, out0, b, k0, t, n_out_bins, n_store_bins, n_frames);   \
+    break;
+  switch (epilogue) {
+    RVB_EPI_CASE(RVB_EPI_POWER, true)
+    RVB_EPI_CASE(RVB_EPI_POWER, false)
+    RVB_EPI_CASE(RVB_EPI_MAGNITUDE, true)
+    RVB_EPI_CASE(RVB_EPI_MAGNITUDE, false)
+    RVB_EPI_CASE(RVB_EPI_COMPLEX, false)
+    RVB_EPI_CASE(RVB_EPI_PHASE, true)
+    RVB_EPI_CASE(RVB_EPI_PHASE, false)
+    RVB_EPI_CASE(RVB_EPI_POWER_P, true)
+    RVB_EPI_CASE(RVB_EPI_POWER_P, false)
+    default: break;
   }
-#pragma unroll
-  for (int i = 0; i < 32; ++i)
-    if (k0 + i < n_store_bins)
-      stft_store(epilogue, power, __uint_as_float(re[i]) * scale + re_add, __uint_as_float(im[i]) * scale, out0, b, k0 + i,
-                 t, n_out_bins, n_frames);
+#undef RVB_EPI_CASE
 }
 
 }  // namespace rvb

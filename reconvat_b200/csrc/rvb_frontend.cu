@@ -11,7 +11,8 @@ extern void count_launch();
 
 // ------------------------------------------------------------------ K0
 // One thread produces 4 consecutive plane samples (float4 stores; float4 loads in the interior).
-__device__ __forceinline__ float padded_sample(const float* __restrict__ a, int64_t i, int n, int pad, int mode) {
+template <typename TIn>
+__device__ __forceinline__ float padded_sample(const TIn* __restrict__ a, int64_t i, int n, int pad, int mode) {
   // i: index into the padded signal of length n + 2*pad (or n when mode == NONE)
   int64_t j = i - pad;
   if (mode == RVB_PAD_NONE) j = i;
@@ -22,7 +23,7 @@ __device__ __forceinline__ float padded_sample(const float* __restrict__ a, int6
     if (mode != RVB_PAD_REFLECT) return 0.f;
     j = 2 * (int64_t)(n - 1) - j;
   }
-  return __ldg(a + j);
+  return (float)__ldg(a + j);
 }
 
 __global__ void __launch_bounds__(256)
@@ -134,65 +135,84 @@ fold_split_kernel(const float* __restrict__ audio, int64_t audio_ld, int n_seg, 
 // [2^14, 2^15) (fp16 overflows at 65504), hi = fp16(v 2^s), lo = fp16(v 2^s - hi).  lo keeps its full 11 bits while
 // |v 2^s| >= 2^-3, i.e. over 18 binades below the row maximum; under that it rounds on the fp16 subnormal grid,
 // an absolute 2^-25 (2^-39 of the row maximum).  row_scale_inv[frame] = 2^-s is applied by the GEMM epilogue.
-__device__ __forceinline__ void fold4(const float* __restrict__ frame_s, const float* __restrict__ frame, int n_fft,
-                                      int half, int c, float (&e)[4], float (&o)[4]) {
-  const float4 x = *reinterpret_cast<const float4*>(frame_s + c + 4);            // p[c+1 .. c+4]
+//
+// Block = kFoldWarps consecutive frames of one segment: their n_fft + (kFoldWarps-1) hop samples are staged once in
+// smem (each sample is used by n_fft/hop frames), then one WARP owns one frame: fold, warp-shuffle max, scale,
+// split, 8-byte stores -- no block barrier after the staging.  smem index = sample index + 3 so that the forward
+// run p[c+1..c+4] is one aligned LDS.128; the mirrored run p[N-c-4..N-c-1] straddles two aligned quads.
+constexpr int kFoldWarps = 8;
+
+__device__ __forceinline__ void fold4(const float* __restrict__ fr /* fr[i + 3] = p[i] */, int n_fft, int half, int c,
+                                      float (&e)[4], float (&o)[4]) {
+  const float4 x = *reinterpret_cast<const float4*>(fr + c + 4);                 // p[c+1 .. c+4]
+  const float4 g0 = *reinterpret_cast<const float4*>(fr + n_fft - c - 4);        // .w = p[N-c-4]
+  const float4 g1 = *reinterpret_cast<const float4*>(fr + n_fft - c);            // p[N-c-3], p[N-c-2], p[N-c-1], -
   const float xs[4] = {x.x, x.y, x.z, x.w};
+  const float ys[4] = {g1.z, g1.y, g1.x, g0.w};                                  // p[N-n], n = c+1 .. c+4
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float y = frame[n_fft - (c + 1 + i)];                                  // p[N-n]
-    e[i] = xs[i] + y;
-    o[i] = xs[i] - y;
+    e[i] = xs[i] + ys[i];
+    o[i] = xs[i] - ys[i];
   }
   if (c + 4 == half) { e[3] = xs[3]; o[3] = 0.f; }                               // n == N/2 pairs with itself
 }
 
-__global__ void __launch_bounds__(256)
-fold_split_f16_kernel(const float* __restrict__ audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int mode,
-                      int n_fft, int hop, int n_frames, __half* __restrict__ a_hi, __half* __restrict__ a_lo,
-                      float* __restrict__ row_scale_inv, float* __restrict__ p0) {
-  extern __shared__ __align__(16) float frame_s[];         // frame_s[i + 3] = p[i], i in [0, n_fft)
-  __shared__ float red[8];
-  float* frame = frame_s + 3;
+// TIn = float, or int16_t for PCM16 audio as the dataset stores it (sample = pcm * gain, gain = 1/32768:
+// model/dataset.py:62 `audio.float().div_(32768.0)`; both steps are exact in fp32).
+template <typename TIn>
+__global__ void __launch_bounds__(kFoldWarps * 32)
+fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gain, int n_seg, int n_samples, int pad,
+                      int mode, int n_fft, int hop, int n_frames, int groups_per_seg, __half* __restrict__ a_hi,
+                      __half* __restrict__ a_lo, float* __restrict__ row_scale_inv, float* __restrict__ p0) {
+  extern __shared__ __align__(16) float span_s[];          // span_s[i + 3] = padded signal at start + i
   const int half = n_fft >> 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n_rows = (int64_t)n_seg * n_frames;
   const int64_t padded = (mode == RVB_PAD_NONE) ? n_samples : (int64_t)n_samples + 2 * pad;
   const int off = (mode == RVB_PAD_NONE) ? 0 : pad;
-  for (int64_t f = blockIdx.x; f < n_rows; f += gridDim.x) {
-    const int b = (int)(f / n_frames), t = (int)(f - (int64_t)b * n_frames);
-    const float* a = audio + (int64_t)b * audio_ld;
-    const int64_t start = (int64_t)t * hop;
-    const int64_t j0 = start - off;
-    __syncthreads();                                       // previous iteration's readers (frame, red) are done
-    const bool interior = j0 >= 0 && j0 + n_fft <= n_samples && ((j0 & 3) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(a) & 15u) == 0);
+  const int span = n_fft + (kFoldWarps - 1) * hop;
+  const int n_groups = n_seg * groups_per_seg;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int b = grp / groups_per_seg;
+    const int t0 = (grp - b * groups_per_seg) * kFoldWarps;
+    const TIn* a = audio + (int64_t)b * audio_ld;
+    const int64_t start = (int64_t)t0 * hop;               // index of the group's first sample in the padded signal
+    const int64_t j0 = start - off;                        // ... and in the audio row
+    __syncthreads();                                       // the previous group's readers are done
+    const bool interior = j0 >= 0 && j0 + span <= n_samples && ((j0 & 3) == 0) && ((span & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(a) & (4 * sizeof(TIn) - 1)) == 0);
     if (interior) {
-      const float4* src = reinterpret_cast<const float4*>(a + j0);
-      for (int i = threadIdx.x; i < (n_fft >> 2); i += blockDim.x) {
-        const float4 v = __ldg(src + i);
-        frame[4 * i + 0] = v.x; frame[4 * i + 1] = v.y; frame[4 * i + 2] = v.z; frame[4 * i + 3] = v.w;
+      for (int i = threadIdx.x; i < (span >> 2); i += blockDim.x) {
+        float* d = span_s + 3 + 4 * i;
+        if constexpr (sizeof(TIn) == 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(a + j0) + i);
+          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        } else {
+          const short4 v = __ldg(reinterpret_cast<const short4*>(a + j0) + i);
+          d[0] = (float)v.x * gain; d[1] = (float)v.y * gain; d[2] = (float)v.z * gain; d[3] = (float)v.w * gain;
+        }
       }
     } else {
-      for (int i = threadIdx.x; i < n_fft; i += blockDim.x) {
+      for (int i = threadIdx.x; i < span; i += blockDim.x) {
         const int64_t pi = start + i;
-        frame[i] = (pi < padded) ? padded_sample(a, pi, n_samples, pad, mode) : 0.f;
+        float v = (pi < padded) ? padded_sample(a, pi, n_samples, pad, mode) : 0.f;
+        if constexpr (sizeof(TIn) != 4) v *= gain;
+        span_s[3 + i] = v;
       }
     }
     __syncthreads();
+    const int t = t0 + warp;
+    if (t >= n_frames) continue;                           // warp-uniform; the barriers above are reached by all
+    const float* fr = span_s + warp * hop;                 // fr[i + 3] = p[i] of frame t
     float mx = 0.f;
-    for (int q = threadIdx.x; q < (half >> 2); q += blockDim.x) {
+    for (int c = lane << 2; c < half; c += 128) {
       float e[4], o[4];
-      fold4(frame_s, frame, n_fft, half, q << 2, e, o);
+      fold4(fr, n_fft, half, c, e, o);
 #pragma unroll
       for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(e[i]), fabsf(o[i])));   // fmaxf drops NaN: s stays finite
     }
     mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < 8; ++w) mx = fmaxf(mx, red[w]);
-    // floor(log2(mx)) from the exponent field (subnormal rows: treat as 2^-126); all-zero rows: s = 0
+    // floor(log2(mx)) from the exponent field (subnormal rows: treated as 2^-126); all-zero rows: s = 0
     int s = 0;
     if (mx > 0.f) {
       int ex = (int)((__float_as_uint(mx) >> 23) & 0xff) - 127;
@@ -200,13 +220,14 @@ fold_split_f16_kernel(const float* __restrict__ audio, int64_t audio_ld, int n_s
       s = max(-126, min(14 - ex, 126));
     }
     const float sc = __uint_as_float((unsigned)(s + 127) << 23);          // 2^s, exact
-    __half* e_hi = a_hi + f * half;
-    __half* e_lo = a_lo + f * half;
-    __half* o_hi = a_hi + (n_rows + f) * half;
-    __half* o_lo = a_lo + (n_rows + f) * half;
-    for (int q = threadIdx.x; q < (half >> 2); q += blockDim.x) {
+    const int64_t f = (int64_t)b * n_frames + t;
+    uint2* e_hi = reinterpret_cast<uint2*>(a_hi + f * half);
+    uint2* e_lo = reinterpret_cast<uint2*>(a_lo + f * half);
+    uint2* o_hi = reinterpret_cast<uint2*>(a_hi + (n_rows + f) * half);
+    uint2* o_lo = reinterpret_cast<uint2*>(a_lo + (n_rows + f) * half);
+    for (int c = lane << 2; c < half; c += 128) {
       float e[4], o[4];
-      fold4(frame_s, frame, n_fft, half, q << 2, e, o);
+      fold4(fr, n_fft, half, c, e, o);
       __half eh[4], el[4], oh[4], ol[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -220,14 +241,15 @@ fold_split_f16_kernel(const float* __restrict__ audio, int64_t audio_ld, int n_s
         r.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
         return r;
       };
-      reinterpret_cast<uint2*>(e_hi)[q] = pack(eh);
-      reinterpret_cast<uint2*>(e_lo)[q] = pack(el);
-      reinterpret_cast<uint2*>(o_hi)[q] = pack(oh);
-      reinterpret_cast<uint2*>(o_lo)[q] = pack(ol);
+      const int q = c >> 2;
+      e_hi[q] = pack(eh);
+      e_lo[q] = pack(el);
+      o_hi[q] = pack(oh);
+      o_lo[q] = pack(ol);
     }
-    if (threadIdx.x == 0) {
+    if (lane == 0) {
       row_scale_inv[f] = __uint_as_float((unsigned)(127 - s) << 23);      // 2^-s
-      if (p0) p0[f] = frame[0];
+      if (p0) p0[f] = fr[3];
     }
   }
 }
@@ -465,32 +487,50 @@ extern "C" int rvb_fold_split(const float* audio, int64_t audio_ld, int n_seg, i
   return check_launch("fold_split_kernel");
 }
 
+template <typename TIn>
+static int launch_fold_split_f16(const char* who, const TIn* audio, int64_t audio_ld, float gain, int n_seg,
+                                 int n_samples, int pad, int pad_mode, int n_fft, int hop, int n_frames, void* a_hi,
+                                 void* a_lo, float* row_scale_inv, float* p0, rvb_stream_t stream) {
+  RVB_REQUIRE(audio && a_hi && a_lo && row_scale_inv, "%s: null pointer", who);
+  RVB_REQUIRE((reinterpret_cast<uintptr_t>(a_hi) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a_lo) & 15u) == 0,
+              "%s: planes must be 16-byte aligned", who);
+  RVB_REQUIRE(n_seg > 0 && n_samples > 0 && hop > 0 && n_frames > 0, "%s: bad shape", who);
+  RVB_REQUIRE(n_fft >= 128 && n_fft % 128 == 0 && n_fft <= 32768, "%s: n_fft %d must be a multiple of 128", who, n_fft);
+  RVB_REQUIRE(pad_mode >= RVB_PAD_REFLECT && pad_mode <= RVB_PAD_NONE, "%s: bad pad_mode %d", who, pad_mode);
+  if (pad_mode == RVB_PAD_REFLECT)
+    RVB_REQUIRE(n_samples > pad, "%s: reflect padding %d needs more than %d samples", who, pad, n_samples);
+  const int64_t padded = (pad_mode == RVB_PAD_NONE) ? n_samples : (int64_t)n_samples + 2 * pad;
+  RVB_REQUIRE((int64_t)(n_frames - 1) * hop + n_fft <= padded, "%s: %d frames do not fit %lld samples", who, n_frames,
+              (long long)padded);
+  RVB_REQUIRE(hop % 4 == 0, "%s: hop %d must be a multiple of 4", who, hop);
+  const size_t smem = (size_t)(n_fft + (kFoldWarps - 1) * (int64_t)hop + 8) * sizeof(float);
+  RVB_REQUIRE(smem <= 200 * 1024, "%s: n_fft %d with hop %d needs %zu bytes of shared memory", who, n_fft, hop, smem);
+  if (smem > 48 * 1024)
+    RVB_CUDA(cudaFuncSetAttribute(fold_split_f16_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int groups_per_seg = (n_frames + kFoldWarps - 1) / kFoldWarps;
+  const int64_t n_groups = (int64_t)n_seg * groups_per_seg;
+  RVB_REQUIRE(n_groups < (1ll << 31), "%s: too many frames", who);
+  const int64_t cap = 148 * 8 * 4;
+  const unsigned grid = (unsigned)(n_groups < cap ? n_groups : cap);
+  fold_split_f16_kernel<TIn><<<grid, kFoldWarps * 32, smem, (cudaStream_t)stream>>>(
+      audio, audio_ld, gain, n_seg, n_samples, pad, pad_mode, n_fft, hop, n_frames, groups_per_seg,
+      static_cast<__half*>(a_hi), static_cast<__half*>(a_lo), row_scale_inv, p0);
+  count_launch();
+  return check_launch("fold_split_f16_kernel");
+}
+
 extern "C" int rvb_fold_split_f16(const float* audio, int64_t audio_ld, int n_seg, int n_samples, int pad,
                                   int pad_mode, int n_fft, int hop, int n_frames, void* a_hi, void* a_lo,
                                   float* row_scale_inv, float* p0, rvb_stream_t stream) {
-  RVB_REQUIRE(audio && a_hi && a_lo && row_scale_inv, "rvb_fold_split_f16: null pointer");
-  RVB_REQUIRE((reinterpret_cast<uintptr_t>(a_hi) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a_lo) & 15u) == 0,
-              "rvb_fold_split_f16: planes must be 16-byte aligned");
-  RVB_REQUIRE(n_seg > 0 && n_samples > 0 && hop > 0 && n_frames > 0, "rvb_fold_split_f16: bad shape");
-  RVB_REQUIRE(n_fft >= 128 && n_fft % 128 == 0 && n_fft <= 32768, "rvb_fold_split_f16: n_fft %d must be a multiple of 128",
-              n_fft);
-  RVB_REQUIRE(pad_mode >= RVB_PAD_REFLECT && pad_mode <= RVB_PAD_NONE, "rvb_fold_split_f16: bad pad_mode %d", pad_mode);
-  if (pad_mode == RVB_PAD_REFLECT)
-    RVB_REQUIRE(n_samples > pad, "rvb_fold_split_f16: reflect padding %d needs more than %d samples", pad, n_samples);
-  const int64_t padded = (pad_mode == RVB_PAD_NONE) ? n_samples : (int64_t)n_samples + 2 * pad;
-  RVB_REQUIRE((int64_t)(n_frames - 1) * hop + n_fft <= padded, "rvb_fold_split_f16: %d frames do not fit %lld samples",
-              n_frames, (long long)padded);
-  const int64_t n_rows = (int64_t)n_seg * n_frames;
-  const size_t smem = (size_t)(n_fft + 4) * sizeof(float);
-  if (smem > 48 * 1024)
-    RVB_CUDA(cudaFuncSetAttribute(fold_split_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t cap = 148 * 8 * 4;
-  const unsigned grid = (unsigned)(n_rows < cap ? n_rows : cap);
-  fold_split_f16_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
-      audio, audio_ld, n_seg, n_samples, pad, pad_mode, n_fft, hop, n_frames, static_cast<__half*>(a_hi),
-      static_cast<__half*>(a_lo), row_scale_inv, p0);
-  count_launch();
-  return check_launch("fold_split_f16_kernel");
+  return launch_fold_split_f16<float>("rvb_fold_split_f16", audio, audio_ld, 1.f, n_seg, n_samples, pad, pad_mode,
+                                      n_fft, hop, n_frames, a_hi, a_lo, row_scale_inv, p0, stream);
+}
+
+extern "C" int rvb_fold_split_f16_pcm16(const int16_t* audio, int64_t audio_ld, float gain, int n_seg, int n_samples,
+                                        int pad, int pad_mode, int n_fft, int hop, int n_frames, void* a_hi,
+                                        void* a_lo, float* row_scale_inv, float* p0, rvb_stream_t stream) {
+  return launch_fold_split_f16<int16_t>("rvb_fold_split_f16_pcm16", audio, audio_ld, gain, n_seg, n_samples, pad,
+                                        pad_mode, n_fft, hop, n_frames, a_hi, a_lo, row_scale_inv, p0, stream);
 }
 
 extern "C" int rvb_stft_bin(const float* sig_hi, const float* sig_lo, int n_seg, int rows_per_seg, int hop,

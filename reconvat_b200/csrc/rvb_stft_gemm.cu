@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -498,6 +499,231 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   }
 }
 
+// ---------------------------------------------------------------- folded kernel, CTA pairs (K1f2)
+// The one-CTA folded kernel moves 64 KB of operands per 12 MMAs and saturates the L2 -> SM path (13.6 TB/s over
+// 148 SMs, profiles/r01c) at 55 % of the tensor pipe.  Here two CTAs of a cluster (one TPC) run
+// tcgen05.mma.cta_group::2 on a 256-frame x 128-bin tile: each CTA stages its own 128 frame rows and only HALF of
+// the basis tile (64 bins), the pair's tensor cores read both halves, so a CTA moves 48 KB per 12 MMAs and the
+// ring is 4 stages deep.  Protocol (cf. the CUTLASS 2-SM kernels):
+//   full[s]        lives in the leader (rank 0): the leader's producer arms it with the bytes of BOTH CTAs, and
+//                  both CTAs' TMA loads (cp.async.bulk.tensor...cta_group::2) complete_tx on it;
+//   empty[s]       one per CTA, released by the leader's tcgen05.commit...multicast::cluster (mask 0b11);
+//   tmem_full[a]   one per CTA, same multicast commit;
+//   tmem_empty[a]  lives in the leader, count 8: four epilogue warps of each CTA arrive (remotely from rank 1).
+// Only the leader's warp 1 issues MMAs; each CTA's epilogue drains its own 128 TMEM lanes.
+constexpr int P_STAGES = 4;
+constexpr int P_A_BYTES = 128 * 128;                    // 128 frame rows x one 128-byte swizzle row
+constexpr int P_B_BYTES = 64 * 128;                     // this CTA's half of the 128 basis rows
+constexpr int P_STAGE_BYTES = 2 * P_A_BYTES + 2 * P_B_BYTES;     // A_hi A_lo B_hi B_lo = 48 KB
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + BAR_BYTES + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* tm, uint32_t smem_dst, uint32_t leader_bar, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                           const FoldParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + P_STAGES * P_STAGE_BYTES;
+  auto s_a = [&](int s, int lo) { return smem_base + s * P_STAGE_BYTES + lo * P_A_BYTES; };
+  auto s_b = [&](int s, int lo) { return smem_base + s * P_STAGE_BYTES + 2 * P_A_BYTES + lo * P_B_BYTES; };
+  auto bar_full = [&](int s) { return bar_base + 8 * s; };
+  auto bar_empty = [&](int s) { return bar_base + 8 * (P_STAGES + s); };
+  auto bar_tmem_full = [&](int a) { return bar_base + 8 * (2 * P_STAGES + a); };
+  auto bar_tmem_empty = [&](int a) { return bar_base + 8 * (2 * P_STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8 * (2 * P_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b_hi);
+    tma_prefetch_desc(&tm_b_lo);
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tmem_full(a), 1);
+      mbar_init(bar_tmem_empty(a), 8);            // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                             // both CTAs' barriers are initialised before any remote signal
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  constexpr int kBlockK = 2 * BLOCK_K;            // 64 halves per 128-byte swizzle row
+  const int n_units = p.m_tiles * p.n_tiles;      // m_tiles counts 256-frame pair tiles here
+  const int kb_per_chain = p.half / kBlockK;
+  const int num_kb = 2 * kb_per_chain;
+  const int unit0 = (int)cluster_id_x(), unit_step = (int)num_clusters_x();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t leader_full0 = map_to_rank(bar_full(0), 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
+        const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int chain = kb >= kb_per_chain;
+          const int kk = (kb - chain * kb_per_chain) * kBlockK;
+          const int a_row = (int)(chain * p.m_rows) + m_tile * 256 + (int)rank * 128;
+          const int b_row = chain * p.n_bins_pad + n_tile * F_BLOCK_N + (int)rank * 64;
+          mbar_wait(bar_empty(stage), phase ^ 1u, nullptr, 1);
+          if (leader) mbar_expect_tx(bar_full(stage), 2 * P_STAGE_BYTES);
+          const uint32_t fb = leader_full0 + 8 * stage;
+          tma_load_2d_pair(&tm_a_hi, s_a(stage, 0), fb, kk, a_row);
+          tma_load_2d_pair(&tm_a_lo, s_a(stage, 1), fb, kk, a_row);
+          tma_load_2d_pair(&tm_b_hi, s_b(stage, 0), fb, kk, b_row);
+          tma_load_2d_pair(&tm_b_lo, s_b(stage, 1), fb, kk, b_row);
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(256, F_BLOCK_N, FMT_F16);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
+        mbar_wait(bar_tmem_empty(acc), acc_phase ^ 1u, nullptr, 2);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int chain = kb >= kb_per_chain;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + chain * F_BLOCK_N);
+          const bool first_kb = (kb == 0) || (kb == kb_per_chain);
+          mbar_wait(bar_full(stage), phase, nullptr, 3);
+          tc_fence_after();
+          const uint64_t da_hi = make_sw128_desc(s_a(stage, 0));
+          const uint64_t da_lo = make_sw128_desc(s_a(stage, 1));
+          const uint64_t db_hi = make_sw128_desc(s_b(stage, 0));
+          const uint64_t db_lo = make_sw128_desc(s_b(stage, 1));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);             // one MMA consumes 32 bytes of the row
+            umma_f16_pair(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
+            umma_f16_pair(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+            umma_f16_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+          }
+          umma_commit_pair(bar_empty(stage));       // frees the slot in both CTAs
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(bar_tmem_full(acc));       // accumulators complete in both CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t leader_tmem_empty0 = map_to_rank(bar_tmem_empty(0), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = unit0; unit < n_units; unit += unit_step) {
+      const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
+      const int64_t f = (int64_t)m_tile * 256 + (int64_t)rank * 128 + row;       // flattened frame index
+      const bool f_ok = f < p.m_rows;
+      const int b = f_ok ? (int)(f / p.n_frames) : 0;
+      const int t = f_ok ? (int)(f - (int64_t)b * p.n_frames) : 0;
+      const float re0 = (p.p0 != nullptr && f_ok) ? p.w0 * __ldg(p.p0 + f) : 0.f;
+      const float scale = f_ok ? __ldg(p.row_scale_inv + f) * p.basis_scale_inv : 1.f;
+      mbar_wait(bar_tmem_full(acc), acc_phase, nullptr, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t re[32], im[32];
+        tmem_ld32(taddr + c * 32, re);
+        tmem_ld32(taddr + 128 + c * 32, im);
+        tmem_ld_wait();
+        const int k0 = n_tile * 128 + c * 32;
+        if (f_ok)
+          stft_store_chunk(p.epilogue, p.power, re, im, scale, re0, p.out0, b, k0, t, p.n_out_bins, p.n_store_bins,
+                           p.n_frames);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                             // the peer may still be reading our smem / signalling our barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // Single bin from the folded planes (Nyquist bin of the STFT module): warp per frame, fp32 FMA.
 // T = float (tf32 planes) or __half (fp16 planes, row-scaled: row_scale_inv undoes the scaling).
 template <typename T>
@@ -685,6 +911,31 @@ static int launch_folded(const char* who, const void* a_hi, const void* a_lo, co
   p.power = power; p.w0 = w0; p.p0 = (w0 != 0.f) ? p0 : nullptr; p.out0 = out0;
   p.row_scale_inv = row_scale_inv; p.basis_scale_inv = basis_scale_inv;
 
+  if constexpr (kF16) {
+    static const bool one_cta = getenv("RVB_GEMM_1CTA") != nullptr;       // A/B switch for measurements
+    if (!one_cta) {
+      // CTA-pair kernel: 256-frame tiles; the A map keeps its 128-row box, the B box shrinks to this CTA's 64 rows
+      if ((rc = make_map_2d(&tm_b_hi, basis_hi, half, 2 * (uint64_t)n_bins_pad, kBlockK, 64, kElem)) != RVB_OK) return rc;
+      if ((rc = make_map_2d(&tm_b_lo, basis_lo, half, 2 * (uint64_t)n_bins_pad, kBlockK, 64, kElem)) != RVB_OK) return rc;
+      p.m_tiles = (int)((m_rows + 255) / 256);
+      static int max_clusters = 0;
+      if (max_clusters == 0) {
+        RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+        cudaLaunchConfig_t qc = {};
+        qc.gridDim = dim3(num_sms() & ~1u); qc.blockDim = dim3(NUM_THREADS); qc.dynamicSmemBytes = P_SMEM_BYTES;
+        int nc = 0;
+        RVB_CUDA(cudaOccupancyMaxActiveClusters(&nc, stft_gemm_fold_pair_kernel, &qc));
+        RVB_REQUIRE(nc > 0, "%s: no CTA pair fits on this device", who);
+        max_clusters = nc < num_sms() / 2 ? nc : num_sms() / 2;
+      }
+      const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
+      const int n_clusters = (int)(n_units < max_clusters ? n_units : max_clusters);
+      stft_gemm_fold_pair_kernel<<<2 * n_clusters, NUM_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo,
+                                                                                                      tm_b_hi, tm_b_lo, p);
+      count_launch();
+      return check_launch("stft_gemm_fold_pair_kernel");
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_kernel<kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));

@@ -1,13 +1,18 @@
 """The hot-path step as one call: front-end + VAT on a batch of audio segments.
 
-``HotPathStep(device)(audio)`` is what ``UNet.run_on_batch`` does before it reaches the network proper
+``HotPathStep(model, device)(audio)`` is what ``UNet.run_on_batch`` does before it reaches the network proper
 (model/self_attention_VAT.py:1098-1106): Mel front-end, log, imagewise normalisation, transpose, then the
-VAT loss against the given transcriber.  ``run_host`` feeds it from pinned host memory with the
-host->device copy of batch i+1 overlapped with the kernels of batch i (copy stream + events).
+VAT loss against the given transcriber.
+
+Launch overhead: the step is ~10 short kernels (plus the caller's network), so eager launches leave the GPU idle
+between them.  ``capture(buffers)`` records the whole step -- our kernels, ``torch.randn_like``, the network and
+its backward -- into one CUDA graph per input buffer; ``replay(i)`` re-launches it with a single driver call.
+``run_host`` feeds the step from pinned host memory with the host->device copy of batch i+1 overlapped with the
+kernels of batch i (copy stream + events), replaying the graphs when they exist.
 """
 import torch
 
-from . import Spectrogram, VAT
+from . import Spectrogram, VAT, _lib
 
 MEL_KW = dict(sr=16000, win_length=2048, n_mels=229, hop_length=512, fmin=30, fmax=8000,
               trainable_mel=False, trainable_STFT=False, verbose=False)   # model/self_attention_VAT.py:1027-1029
@@ -20,6 +25,8 @@ class HotPathStep:
         self.spectrogram = Spectrogram.MelSpectrogram(**MEL_KW).to(self.device)
         self.vat_loss = (vat_cls or VAT.UNet_VAT)(xi, eps, 1, False)
         self._copy_stream = None
+        self._graphs = []              # [(graph, input buffer, outputs, device flag)]
+        self.kernels_per_graph = 0
 
     def __call__(self, audio):
         """audio: (B, L) float32 on the device.  Returns (vat_loss, r_norm_mean, spec, r_adv)."""
@@ -27,7 +34,46 @@ class HotPathStep:
         vat_loss, r_adv, r_norm = self.vat_loss(self.model, spec)
         return vat_loss, r_norm.abs().mean(), spec, r_adv
 
-    def run_host(self, host_batches, results_host):
+    # -- CUDA graphs ------------------------------------------------------------------------
+    def capture(self, buffers, warmup=3):
+        """Record one CUDA graph of the step per device input buffer (the graph reads that buffer in place; refill
+        it with ``copy_`` between replays).  Every graph gets its own memory pool: with a shared pool the outputs
+        of graph j alias intermediates of graph i and are clobbered when i replays (seen on the NaN flag)."""
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):                    # warm-up off the capture: lazy tables, cuBLAS handles, ...
+            for i in range(warmup):
+                self(buffers[i % len(buffers)])
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.vat_loss.check()
+        self._graphs = []
+        for buf in buffers:
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g):
+                out = self(buf)
+                packed = torch.stack((out[0].detach(), out[1]))      # (vat_loss, r_norm_mean): one 8-byte result
+            self.kernels_per_graph = _lib.launch_count() - n0
+            self._graphs.append((g, buf, out + (packed,), self.vat_loss.last_flag))
+        return len(self._graphs)
+
+    def replay(self, i):
+        """Re-launch graph i on the current stream.  Returns (vat_loss, r_norm_mean, spec, r_adv, packed): static
+        tensors that the next replay of the same graph overwrites."""
+        g, _, out, _ = self._graphs[i]
+        g.replay()
+        return out
+
+    def check(self):
+        """NaN/Inf assertion of the reference (model/self_attention_VAT.py:189-190) for the eager path and for every
+        captured graph (synchronises)."""
+        self.vat_loss.check()
+        for _, _, _, flag in self._graphs:
+            self.vat_loss.check(flag)
+
+    # -- host-fed loop ----------------------------------------------------------------------
+    def run_host(self, host_batches, results_host, use_graphs=True):
         """host_batches: iterable of pinned (B, L) float32 CPU tensors; results_host: pinned (n, 2) float32.
         Row i of results_host receives (vat_loss, r_norm_mean) of batch i.  Double-buffered: the copy of
         batch i+1 is issued on a side stream while batch i computes.  Returns the number of batches."""
@@ -35,11 +81,16 @@ class HotPathStep:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         copy = self._copy_stream
-        bufs, ready, freed = [None, None], [None, None], [None, None]
+        graphs = use_graphs and len(self._graphs) >= 2
+        bufs = [self._graphs[0][1], self._graphs[1][1]] if graphs else [None, None]
+        ready, freed = [None, None], [None, None]
         it = iter(host_batches)
 
         def stage(slot, hb):
             if bufs[slot] is None or bufs[slot].shape != hb.shape:
+                if graphs:
+                    raise ValueError("run_host: batch shape %s does not match the captured buffers %s"
+                                     % (tuple(hb.shape), tuple(bufs[slot].shape)))
                 bufs[slot] = torch.empty(hb.shape, dtype=hb.dtype, device=self.device)
             with torch.cuda.stream(copy):
                 if freed[slot] is not None:
@@ -60,11 +111,15 @@ class HotPathStep:
             if nxt is not None:
                 stage(slot ^ 1, nxt)
             main.wait_event(ready[slot])
-            vat_loss, r_norm, _, _ = self(bufs[slot])
+            if graphs:
+                packed = self.replay(slot)[4]
+            else:
+                vat_loss, r_norm, _, _ = self(bufs[slot])
+                packed = torch.stack((vat_loss.detach(), r_norm))
+            results_host[i].copy_(packed, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(main)
             freed[slot] = ev
-            results_host[i].copy_(torch.stack((vat_loss.detach(), r_norm)), non_blocking=True)
             i += 1
             if nxt is None:
                 return i

@@ -118,6 +118,28 @@ def test_frontend_amplitude_range(R, dev):
     assert relerr(lm, ref) < LOGMEL_TOL
 
 
+def test_pcm16_input_is_bit_identical_to_float_input(R, dev):
+    """int16 audio (the dataset's storage format, model/dataset.py:62) through rvb_fold_split_f16_pcm16 gives the same
+    bits as the float path fed pcm/32768; the other contraction paths convert with torch and must agree too."""
+    import os
+    from reconvat_b200 import synth
+    a16 = np.stack([synth.white_int16(16385, 21), synth.music_int16(16385, 22)])
+    ai = torch.from_numpy(a16).to(dev)
+    af = torch.from_numpy(synth.to_float(a16)).to(dev)
+    m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    assert torch.equal(m.normalised_log_mel(ai), m.normalised_log_mel(af))
+    assert torch.equal(m(ai[:, :-1]), m(af[:, :-1]))
+    os.environ["RVB_STFT_OPERAND"] = "tf32"
+    try:
+        m2 = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+        assert m2.stft._device_tables()["fold"]["operand"] == "tf32"
+    finally:
+        os.environ.pop("RVB_STFT_OPERAND", None)
+    assert torch.equal(m2.normalised_log_mel(ai), m2.normalised_log_mel(af))
+    with pytest.raises(R._lib.RvbError):
+        m(ai.to(torch.int32))
+
+
 def test_pad_split_bit_exact(R, dev):
     from reconvat_b200 import basis, synth
     a = torch.from_numpy(synth.to_float(np.stack([synth.white_int16(16385, 1), synth.music_int16(16385, 2)])))
