@@ -31,6 +31,8 @@ HBM_BYTES_PER_SEG = {
     "rvb_fold_split_f16": 1310716 + 4 * 640 * 1024 * 2 + 640 * 4,   # R audio, W e/o hi/lo fp16 planes + row scales
     "rvb_fold_split_f16_pcm16": 1310716 // 2 + 4 * 640 * 1024 * 2 + 640 * 4,
     "rvb_mel_project": 1020 * 640 * 4 + N4,
+    "rvb_logmel_minmax": N4,
+    "rvb_logmel_transpose": 2 * N4,
     "rvb_normalise": 2 * N4,
     "rvb_vat_perturb": 3 * N4,
     "rvb_bce_grad": 3 * P4,
@@ -219,7 +221,8 @@ def run_ours(args, rank, local_rank, world):
 
     # per-kernel durations: the same K steps launched eagerly with CUDA events around every entry point, on the
     # launching stream (events cannot be read back from inside a replayed graph)
-    kernel_names = ["rvb_stft_gemm", "rvb_stft_gemm_folded", "rvb_stft_gemm_folded_f16"] + list(HBM_BYTES_PER_SEG)
+    kernel_names = ["rvb_stft_gemm", "rvb_stft_gemm_folded", "rvb_stft_gemm_folded_f16",
+                    "rvb_stft_mel_folded_f16"] + list(HBM_BYTES_PER_SEG)
     barrier()
     log = R._lib.record_events(kernel_names)
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -253,9 +256,11 @@ def run_ours(args, rank, local_rank, world):
     if rank != 0:
         return
     peaks = load_peaks()
-    f16 = "rvb_stft_gemm_folded_f16" in kavg
+    fused = "rvb_stft_mel_folded_f16" in kavg
+    f16 = fused or "rvb_stft_gemm_folded_f16" in kavg
     folded = f16 or "rvb_stft_gemm_folded" in kavg
-    gemm_name = "rvb_stft_gemm_folded_f16" if f16 else ("rvb_stft_gemm_folded" if folded else "rvb_stft_gemm")
+    gemm_name = ("rvb_stft_mel_folded_f16" if fused else "rvb_stft_gemm_folded_f16" if f16 else
+                 "rvb_stft_gemm_folded" if folded else "rvb_stft_gemm")
     gemm_ms = kavg.get(gemm_name)
     roofline = None
     if gemm_ms:
@@ -263,7 +268,8 @@ def run_ours(args, rank, local_rank, world):
         # issued: 3 MMAs per product (hi*hi + hi*lo + lo*hi), K halved by the fold
         achieved = B * STFT_FLOP_PER_SEG / (gemm_ms * 1e-3) / 1e12
         issued = 3 * B * 2 * 640 * 2048 * (1024 if folded else 2048) / (gemm_ms * 1e-3) / 1e12
-        kname = ("stft_gemm_fold_kernel<f16>" if f16 else "stft_gemm_fold_kernel<tf32>") if folded else "stft_gemm_kernel"
+        kname = ("stft_gemm_fold_pair_kernel%s" % (" + Mel epilogue" if fused else "") if f16 else
+                 "stft_gemm_fold_kernel<tf32>") if folded else "stft_gemm_kernel"
         pipe_peak = peaks["bf16"] if f16 else peaks["bf16"] / 2
         roofline = {"kernel": "%s (%s)" % (kname, gemm_name), "bound": "tensor", "achieved": achieved,
                     "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"], "traffic": None,

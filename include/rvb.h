@@ -157,6 +157,29 @@ int rvb_stft_bin(const float* sig_hi, const float* sig_lo, int n_seg, int rows_p
                  const float* wcos_row, const float* wsin_row, int n_fft, int bin, int epilogue, float power,
                  float* out0, int n_out_bins, rvb_stream_t stream);
 
+/*
+ * K1m  the folded fp16 contraction with the Mel projection fused into its epilogue: the power (or magnitude /
+ * power_p) spectrum never leaves the SM.  Replaces model/Spectrogram.py:219-231, :458 and `torch.matmul(self.mel_basis,
+ * spec)` (:460) for filterbanks in which every bin feeds at most two adjacent bands (all triangular banks).
+ *   spectrum   RVB_EPI_POWER | RVB_EPI_MAGNITUDE | RVB_EPI_POWER_P
+ *   mel_tab    [n_bins_pad][4] float: (w0, w1, band0 as int32 bits, 0): bin k adds w0 P[k] to band band0[k] and
+ *              w1 P[k] to band band0[k]+1; band0 non-decreasing in k; 16-byte aligned
+ *   mel_out    [n_seg][n_mels][n_frames] (what MelSpectrogram.forward returns); zeroed by the call, then accumulated
+ *              with RED.ADD -- at most two partial sums per element when no band straddles more than two 128-bin tiles
+ * K2m  rvb_logmel_minmax: per-segment (min, max) keys of log(mel + log_offset) (model/self_attention_VAT.py:1102,
+ * utils.py:96-97);  rvb_logmel_transpose: out[b][t][m] = (log(mel[b][m][t] + log_offset) - min) / (max - min)
+ * (utils.py:100 and the .transpose(-1,-2) of self_attention_VAT.py:1104; minmax NULL: no normalisation;
+ * log_offset < 0: no log).
+ */
+int rvb_stft_mel_folded_f16(const void* a_hi, const void* a_lo, const float* row_scale_inv, int n_seg, int n_frames,
+                            int n_fft, const void* basis_hi, const void* basis_lo, float basis_scale_inv, int n_bins_pad,
+                            const float* p0, float w0, int spectrum, float power, const float* mel_tab, int n_mels,
+                            float* mel_out, rvb_stream_t stream);
+int rvb_logmel_minmax(const float* mel, int n_seg, int64_t n_per_seg, float log_offset, uint32_t* minmax,
+                      rvb_stream_t stream);
+int rvb_logmel_transpose(const float* mel, int n_seg, int n_mels, int n_frames, float log_offset,
+                         const uint32_t* minmax, float* out, rvb_stream_t stream);
+
 #define RVB_LAYOUT_BINS_MAJOR 0 /* out[b][m][t]  -- what MelSpectrogram.forward returns (:460) */
 #define RVB_LAYOUT_TIME_MAJOR 1 /* out[b][t][m]  -- after `.transpose(-1,-2)` (self_attention_VAT.py:1104) */
 

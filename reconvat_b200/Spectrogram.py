@@ -142,9 +142,11 @@ class STFT(nn.Module):
     def n_frames(self, num_samples):
         return self._geometry(num_samples)[1]
 
-    def _spectrum(self, x, epilogue, power, make_out):
+    def _spectrum(self, x, epilogue, power, make_out, mel_tab=None):
         """x: (B,1,L) CUDA float32.  Runs pad/frame/split + the tcgen05 contraction with the given epilogue.
-        ``make_out(B, n_frames)`` -> (out tensor, n_out_bins).  Returns (out, n_frames)."""
+        ``make_out(B, n_frames)`` -> (out tensor, n_out_bins).  Returns (out, n_frames).
+        ``mel_tab`` (only with the folded fp16 contraction, see :meth:`fused_mel_ok`): fuse the Mel projection;
+        make_out then returns the (B, n_mels, T) tensor and n_mels."""
         x2 = self._check_input(x)
         B, L = x2.shape
         mode, n_frames, rows = self._geometry(L)
@@ -171,6 +173,13 @@ class STFT(nn.Module):
                     _lib.call("rvb_fold_split_f16", _lib.ptr(x2), ld, B, L, self.pad_amount, mode, self.n_fft,
                               self.stride, n_frames, planes[0].data_ptr(), planes[1].data_ptr(), row_inv.data_ptr(),
                               p0_ptr)
+                if mel_tab is not None:
+                    # Mel projection fused into the epilogue: `out` is (B, n_mels, T), the spectrum is never stored
+                    _lib.call("rvb_stft_mel_folded_f16", planes[0].data_ptr(), planes[1].data_ptr(),
+                              row_inv.data_ptr(), B, n_frames, self.n_fft, fd["basis_hi"].data_ptr(),
+                              fd["basis_lo"].data_ptr(), fd["scale_inv"], fd["n_bins_pad"], p0_ptr, fd["w0"], epilogue,
+                              float(power), mel_tab.data_ptr(), n_out_bins, _lib.ptr(out))
+                    return out, n_frames
                 _lib.call("rvb_stft_gemm_folded_f16", planes[0].data_ptr(), planes[1].data_ptr(), row_inv.data_ptr(),
                           B, n_frames, self.n_fft, fd["basis_hi"].data_ptr(), fd["basis_lo"].data_ptr(),
                           fd["scale_inv"], fd["n_bins_pad"], p0_ptr, fd["w0"], epilogue, float(power), _lib.ptr(out),
@@ -214,6 +223,11 @@ class STFT(nn.Module):
                           self.wcos[k, 0].data_ptr(), self.wsin[k, 0].data_ptr(), self.n_fft, k, epilogue,
                           float(power), _lib.ptr(out), n_out_bins)
         return out, n_frames
+
+    def fused_mel_ok(self):
+        """True when the contraction that will run is the folded fp16 one (the only one with the Mel epilogue)."""
+        fd = self._device_tables()["fold"]
+        return fd is not None and fd["operand"] == "f16" and not os.environ.get("RVB_NO_MEL_FUSION")
 
     def forward(self, x, output_format=None):
         output_format = output_format or self.output_format
@@ -270,11 +284,14 @@ class MelSpectrogram(nn.Module):
         self.register_buffer('mel_basis', torch.from_numpy(mel_basis))
         self._bands = None
         self._bands_key = None
+        self._fused = None
+        self._fused_key = None
         if verbose:
             print("Mel filter created (reconvat_b200, banded projection)")
 
     def _apply(self, fn, *args, **kwargs):
         self._bands = None
+        self._fused = None
         return super()._apply(fn, *args, **kwargs)
 
     def _band_tables(self):
@@ -287,6 +304,34 @@ class MelSpectrogram(nn.Module):
             self._bands_key = key
         return self._bands
 
+    def _fused_table(self):
+        """Device table of the fused Mel epilogue, or None when this module must take the two-kernel path."""
+        key = (self.mel_basis.device, self.mel_basis._version, self.mel_basis.data_ptr())
+        if self._fused is None or self._fused_key != key:
+            tab = None
+            if self.stft.fused_mel_ok():
+                fd = self.stft._device_tables()["fold"]
+                mb = self.mel_basis.detach().cpu().numpy()
+                if not any(np.any(mb[:, k] != 0) for k in fd["leftover"]):    # e.g. the Nyquist bin carries no weight
+                    tab = basis.mel_epilogue_table(mb, fd["n_bins_pad"])
+            self._fused = (torch.from_numpy(tab).to(self.mel_basis.device) if tab is not None else None,)
+            self._fused_key = key
+        return self._fused[0]
+
+    def _spectrum_epilogue(self):
+        if float(self.power) == 2.0:
+            return _lib.EPI_POWER
+        if float(self.power) == 1.0:
+            return _lib.EPI_MAGNITUDE
+        return _lib.EPI_POWER_P
+
+    def _mel_fused(self, x, tab):
+        """(B,1,L) -> Mel spectrogram (B, n_mels, T) through the contraction with the fused Mel epilogue."""
+        n_mels, dev = self.mel_basis.shape[0], x.device
+        return self.stft._spectrum(x, self._spectrum_epilogue(), self.power,
+                                   lambda B, T: (torch.empty((B, n_mels, T), dtype=torch.float32, device=dev), n_mels),
+                                   mel_tab=tab)
+
     def _power_spectrogram(self, x):
         """(B,1,L) -> power (B, T, n_pow_bins), time-major, holding (sqrt(re^2+im^2))**power for every bin the
         filterbank reads (model/Spectrogram.py:458)."""
@@ -294,12 +339,7 @@ class MelSpectrogram(nn.Module):
         n_pow_bins = -(-bands["k_end"] // 4) * 4             # bins >= k_end carry zero weight; pad to 16 bytes
         if n_pow_bins > self.mel_basis.shape[1]:
             n_pow_bins = bands["k_end"]
-        if float(self.power) == 2.0:
-            epi = _lib.EPI_POWER
-        elif float(self.power) == 1.0:
-            epi = _lib.EPI_MAGNITUDE
-        else:
-            epi = _lib.EPI_POWER_P
+        epi = self._spectrum_epilogue()
         dev = x.device
         power, n_frames = self.stft._spectrum(
             x, epi | _lib.EPI_TIME_MAJOR, self.power,
@@ -314,6 +354,9 @@ class MelSpectrogram(nn.Module):
 
     def forward(self, x):
         x = basis.broadcast_dim(x)
+        tab = self._fused_table()
+        if tab is not None:
+            return self._mel_fused(x, tab)[0]
         power, n_frames, bands = self._power_spectrogram(x)
         out = torch.empty((power.shape[0], self.mel_basis.shape[0], n_frames), dtype=torch.float32, device=x.device)
         self._project(power, n_frames, bands, -1.0, _lib.LAYOUT_BINS_MAJOR, out, None)
@@ -333,6 +376,19 @@ class MelSpectrogram(nn.Module):
         x = basis.broadcast_dim(audio)
         if trim_last:
             x = x[:, :, :-1]                                  # a view; the kernel takes the row stride
+        tab = self._fused_table()
+        if tab is not None:
+            mel, n_frames = self._mel_fused(x, tab)
+            B, n_mels = mel.shape[0], mel.shape[1]
+            out = torch.empty((B, n_frames, n_mels), dtype=torch.float32, device=x.device)
+            minmax = None
+            if normalise:
+                minmax = torch.empty((B, 2), dtype=torch.int32, device=x.device)
+                _lib.call("rvb_logmel_minmax", mel.data_ptr(), B, n_mels * n_frames, float(log_offset), minmax.data_ptr())
+            _lib.call("rvb_logmel_transpose", mel.data_ptr(), B, n_mels, n_frames, float(log_offset),
+                      None if minmax is None else minmax.data_ptr(), out.data_ptr())
+            out = out.unsqueeze(1) if channel_dim else out
+            return (out, minmax) if return_minmax else out
         power, n_frames, bands = self._power_spectrogram(x)
         B, n_mels = power.shape[0], self.mel_basis.shape[0]
         out = torch.empty((B, n_frames, n_mels), dtype=torch.float32, device=x.device)

@@ -145,6 +145,36 @@ def banded_filterbank(mel_basis):
     return band0, w0, w1, k_begin, k_end
 
 
+def mel_epilogue_table(mel_basis, n_bins_pad, tile=GEMM_TILE_BINS):
+    """Table for the Mel projection fused into the contraction's epilogue: float32 [n_bins_pad, 4] rows
+    (w0, w1, band0 as int32 bits, 0) from :func:`banded_filterbank`, band0 kept non-decreasing over the padding.
+    Returns None when the fused epilogue cannot represent the bank bit-reproducibly: a bin feeding more than two
+    (or non-adjacent) bands, weight on a bin the tiled contraction does not produce (>= n_bins_pad), or a band
+    straddling more than two 128-bin tiles (its partial sums would then be added in a run-dependent order)."""
+    mb = np.asarray(mel_basis, dtype=np.float32)
+    try:
+        band0, w0, w1, k_begin, k_end = banded_filterbank(mb)
+    except ValueError:
+        return None
+    if k_end > n_bins_pad:
+        return None
+    for m in range(mb.shape[0]):
+        nz = np.flatnonzero(mb[m])
+        if len(nz) and nz[-1] // tile - nz[0] // tile > 1:
+            return None
+    tab = np.zeros((n_bins_pad, 4), np.float32)
+    b = np.zeros(n_bins_pad, np.int32)
+    n = min(len(band0), n_bins_pad)
+    b[:n] = band0[:n]
+    b[:k_begin] = band0[k_begin]                    # leading zero-weight bins: stay on the first band
+    b[k_end:] = band0[k_end - 1]                    # trailing ones: stay on the last
+    tab[:n, 0] = w0[:n]
+    tab[:n, 1] = w1[:n]
+    tab[:, 2] = b.view(np.float32)
+    assert np.all(np.diff(b) >= 0)
+    return tab
+
+
 def band_rows(mel_basis, max_len=256):
     """Dense (n_mels, F) -> (band_lo int32[n_mels], band_len int32[n_mels], band_w f32[L, n_mels], k_end).
 

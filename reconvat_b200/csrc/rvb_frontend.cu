@@ -3,6 +3,8 @@
 //   K1b single frequency bin in fp32       (Nyquist bin of model/Spectrogram.py:219-220)
 //   K2 banded Mel + log + min/max          (model/Spectrogram.py:460, self_attention_VAT.py:1102, utils.py:96-97)
 //   K3 imagewise normalise                 (model/utils.py:100)
+#include <cstdlib>
+
 #include "rvb_common.cuh"
 
 namespace rvb {
@@ -159,7 +161,9 @@ __device__ __forceinline__ void fold4(const float* __restrict__ fr /* fr[i + 3] 
 
 // TIn = float, or int16_t for PCM16 audio as the dataset stores it (sample = pcm * gain, gain = 1/32768:
 // model/dataset.py:62 `audio.float().div_(32768.0)`; both steps are exact in fp32).
-template <typename TIn>
+// kIters = n_fft / 256 when the frame's 2 * kIters * 4 folded values per lane fit in registers (the fold is then
+// evaluated once), 0 = generic two-pass evaluation.
+template <typename TIn, int kIters>
 __global__ void __launch_bounds__(kFoldWarps * 32)
 fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gain, int n_seg, int n_samples, int pad,
                       int mode, int n_fft, int hop, int n_frames, int groups_per_seg, __half* __restrict__ a_hi,
@@ -204,12 +208,22 @@ fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gai
     const int t = t0 + warp;
     if (t >= n_frames) continue;                           // warp-uniform; the barriers above are reached by all
     const float* fr = span_s + warp * hop;                 // fr[i + 3] = p[i] of frame t
+    constexpr int kR = kIters > 0 ? kIters : 1;
+    float ev[kR][4], ov[kR][4];
     float mx = 0.f;
-    for (int c = lane << 2; c < half; c += 128) {
-      float e[4], o[4];
-      fold4(fr, n_fft, half, c, e, o);
+    if constexpr (kIters > 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(e[i]), fabsf(o[i])));   // fmaxf drops NaN: s stays finite
+      for (int it = 0; it < kIters; ++it) {
+        fold4(fr, n_fft, half, (lane << 2) + it * 128, ev[it], ov[it]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(ev[it][i]), fabsf(ov[it][i])));
+      }
+    } else {
+      for (int c = lane << 2; c < half; c += 128) {
+        fold4(fr, n_fft, half, c, ev[0], ov[0]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(ev[0][i]), fabsf(ov[0][i])));   // fmaxf drops NaN
+      }
     }
     mx = warp_max(mx);
     // floor(log2(mx)) from the exponent field (subnormal rows: treated as 2^-126); all-zero rows: s = 0
@@ -225,27 +239,30 @@ fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gai
     uint2* e_lo = reinterpret_cast<uint2*>(a_lo + f * half);
     uint2* o_hi = reinterpret_cast<uint2*>(a_hi + (n_rows + f) * half);
     uint2* o_lo = reinterpret_cast<uint2*>(a_lo + (n_rows + f) * half);
-    for (int c = lane << 2; c < half; c += 128) {
-      float e[4], o[4];
-      fold4(fr, n_fft, half, c, e, o);
-      __half eh[4], el[4], oh[4], ol[4];
+    // hi = fp16(v 2^s), lo = fp16(v 2^s - hi), two values per cvt.rn.f16x2
+    auto split4 = [sc](const float (&v)[4], uint2& hi, uint2& lo) {
+      const float a0 = v[0] * sc, a1 = v[1] * sc, a2 = v[2] * sc, a3 = v[3] * sc;
+      const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
+      hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+      lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+    };
+    if constexpr (kIters > 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float ev = e[i] * sc, ov = o[i] * sc;
-        eh[i] = __float2half_rn(ev); el[i] = __float2half_rn(ev - __half2float(eh[i]));
-        oh[i] = __float2half_rn(ov); ol[i] = __float2half_rn(ov - __half2float(oh[i]));
+      for (int it = 0; it < kIters; ++it) {
+        const int q = lane + it * 32;
+        uint2 h, l;
+        split4(ev[it], h, l); e_hi[q] = h; e_lo[q] = l;
+        split4(ov[it], h, l); o_hi[q] = h; o_lo[q] = l;
       }
-      auto pack = [](const __half (&h)[4]) {
-        uint2 r;
-        r.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
-        r.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
-        return r;
-      };
-      const int q = c >> 2;
-      e_hi[q] = pack(eh);
-      e_lo[q] = pack(el);
-      o_hi[q] = pack(oh);
-      o_lo[q] = pack(ol);
+    } else {
+      for (int c = lane << 2; c < half; c += 128) {
+        fold4(fr, n_fft, half, c, ev[0], ov[0]);
+        uint2 h, l;
+        split4(ev[0], h, l); e_hi[c >> 2] = h; e_lo[c >> 2] = l;
+        split4(ov[0], h, l); o_hi[c >> 2] = h; o_lo[c >> 2] = l;
+      }
     }
     if (lane == 0) {
       row_scale_inv[f] = __uint_as_float((unsigned)(127 - s) << 23);      // 2^-s
@@ -397,6 +414,100 @@ minmax_kernel(const float* __restrict__ x, int64_t n_per_seg, uint32_t* __restri
   }
 }
 
+// ------------------------------------------------------------------ K2m: after the fused Mel epilogue
+// log via MUFU.LG2 (absolute error < 2^-21 outside [0.5, 2], 1 ulp inside -- three orders below the 1e-4 log-Mel
+// tolerance): libm's logf is ~25 instructions and made both passes instruction-bound (profiles/r01d).  Both passes
+// use the same function, so the normalised extrema stay exactly 0 and 1.
+// __fmul_rn is never contracted into a following subtract, so both passes round identically.
+__device__ __forceinline__ float fast_log(float x) { return __fmul_rn(__log2f(x), 0.693147182464599609375f); }
+
+// mel[b][m][t] (bins-major, what MelSpectrogram.forward returns) -> per-segment min/max keys of log(mel + offset).
+__global__ void __launch_bounds__(256)
+logmel_minmax_kernel(const float* __restrict__ mel, int64_t n_per_seg, float log_offset, uint32_t* __restrict__ minmax) {
+  const int b = blockIdx.y;
+  const float* p = mel + (int64_t)b * n_per_seg;
+  float vmax = -INFINITY, vmin = INFINITY;
+  bool seen_nan = false;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((n_per_seg & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+    for (int64_t j = i0; j < (n_per_seg >> 2); j += stride) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(p) + j);
+      const float v[4] = {fast_log(q.x + log_offset), fast_log(q.y + log_offset), fast_log(q.z + log_offset), fast_log(q.w + log_offset)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { vmax = fmaxf(vmax, v[e]); vmin = fminf(vmin, v[e]); seen_nan |= isnan(v[e]); }
+    }
+  } else {
+    for (int64_t j = i0; j < n_per_seg; j += stride) {
+      const float v = fast_log(__ldg(p + j) + log_offset);
+      vmax = fmaxf(vmax, v); vmin = fminf(vmin, v); seen_nan |= isnan(v);
+    }
+  }
+  unsigned kmax = warp_max_u32(seen_nan ? 0xffffffffu : f2key(vmax));
+  unsigned kmin = warp_max_u32(seen_nan ? 0xffffffffu : f2key(-vmin));
+  __shared__ unsigned red[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = kmin; red[1][warp] = kmax; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    unsigned k = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) k = max(k, red[threadIdx.x][w]);
+    atomicMax(minmax + 2 * b + threadIdx.x, k);
+  }
+}
+
+__device__ __forceinline__ void decode_minmax(const uint32_t* __restrict__ minmax, int b, float& mn, float& mx);
+
+// mel[b][m][t] -> out[b][t][m] = (log(mel + offset) - min) / (max - min)   (log only when minmax == nullptr):
+// model/self_attention_VAT.py:1102, utils.py:100 and the .transpose(-1,-2) of :1104 in one pass.  Block = 32 frames x
+// ALL bands: 128-byte row reads, and the 32 output rows form one contiguous n_mels*128-byte run (float4 stores).
+constexpr int kTrFrames = 32;
+
+__global__ void __launch_bounds__(256)
+logmel_transpose_kernel(const float* __restrict__ mel, int n_mels, int n_frames, float log_offset,
+                        const uint32_t* __restrict__ minmax, float* __restrict__ out) {
+  extern __shared__ __align__(16) float tile[];            // [kTrFrames][n_mels]: already in output order
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kTrFrames;
+  const int nt = min(kTrFrames, n_frames - t0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float mn = 0.f, den = 1.f;
+  if (minmax) {
+    float mx;
+    decode_minmax(minmax, b, mn, mx);
+    den = mx - mn;                                         // (x_max - x_min), utils.py:100
+  }
+  const float* src = mel + (int64_t)b * n_mels * n_frames + t0;
+  // one warp per band row (32 consecutive frames = 128 bytes); four rows in flight per warp to cover DRAM latency
+  for (int m4 = warp; m4 < n_mels; m4 += 32) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int m = m4 + 8 * u;
+      v[u] = (m < n_mels && lane < nt) ? __ldg(src + (int64_t)m * n_frames + lane) : 1.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int m = m4 + 8 * u;
+      float w = v[u];
+      if (log_offset >= 0.f) w = fast_log(w + log_offset);
+      if (minmax) w = (w - mn) / den;
+      if (m < n_mels && lane < nt) tile[lane * n_mels + m] = w;   // bank = (lane * n_mels + m) % 32: conflict-free, odd n_mels
+    }
+  }
+  __syncthreads();
+  float* dst = out + ((int64_t)b * n_frames + t0) * n_mels;
+  const int n = nt * n_mels;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    for (int i = threadIdx.x; i < (n >> 2); i += 256)
+      reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(tile)[i];
+    for (int i = (n & ~3) + threadIdx.x; i < n; i += 256) dst[i] = tile[i];
+  } else {
+    for (int i = threadIdx.x; i < n; i += 256) dst[i] = tile[i];
+  }
+}
+
 // ------------------------------------------------------------------ K3
 __device__ __forceinline__ void decode_minmax(const uint32_t* __restrict__ minmax, int b, float& mn, float& mx) {
   const unsigned kmin = __ldg(minmax + 2 * b), kmax = __ldg(minmax + 2 * b + 1);
@@ -505,14 +616,20 @@ static int launch_fold_split_f16(const char* who, const TIn* audio, int64_t audi
   RVB_REQUIRE(hop % 4 == 0, "%s: hop %d must be a multiple of 4", who, hop);
   const size_t smem = (size_t)(n_fft + (kFoldWarps - 1) * (int64_t)hop + 8) * sizeof(float);
   RVB_REQUIRE(smem <= 200 * 1024, "%s: n_fft %d with hop %d needs %zu bytes of shared memory", who, n_fft, hop, smem);
+  static const bool regs = getenv("RVB_FOLD_REGS") != nullptr;      // A/B switch for measurements
+  auto kernel = !regs ? fold_split_f16_kernel<TIn, 0>
+              : (n_fft == 2048) ? fold_split_f16_kernel<TIn, 8>
+              : (n_fft == 1024) ? fold_split_f16_kernel<TIn, 4>
+              : (n_fft == 512)  ? fold_split_f16_kernel<TIn, 2>
+                                : fold_split_f16_kernel<TIn, 0>;
   if (smem > 48 * 1024)
-    RVB_CUDA(cudaFuncSetAttribute(fold_split_f16_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int groups_per_seg = (n_frames + kFoldWarps - 1) / kFoldWarps;
   const int64_t n_groups = (int64_t)n_seg * groups_per_seg;
   RVB_REQUIRE(n_groups < (1ll << 31), "%s: too many frames", who);
   const int64_t cap = 148 * 8 * 4;
   const unsigned grid = (unsigned)(n_groups < cap ? n_groups : cap);
-  fold_split_f16_kernel<TIn><<<grid, kFoldWarps * 32, smem, (cudaStream_t)stream>>>(
+  kernel<<<grid, kFoldWarps * 32, smem, (cudaStream_t)stream>>>(
       audio, audio_ld, gain, n_seg, n_samples, pad, pad_mode, n_fft, hop, n_frames, groups_per_seg,
       static_cast<__half*>(a_hi), static_cast<__half*>(a_lo), row_scale_inv, p0);
   count_launch();
@@ -566,6 +683,33 @@ extern "C" int rvb_mel_project(const float* power, int n_seg, int n_frames, int 
                                                                        minmax);
   count_launch();
   return check_launch("mel_project_kernel");
+}
+
+extern "C" int rvb_logmel_minmax(const float* mel, int n_seg, int64_t n_per_seg, float log_offset, uint32_t* minmax,
+                                 rvb_stream_t stream) {
+  RVB_REQUIRE(mel && minmax, "rvb_logmel_minmax: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_per_seg > 0 && log_offset >= 0.f, "rvb_logmel_minmax: bad argument");
+  RVB_CUDA(cudaMemsetAsync(minmax, 0, sizeof(uint32_t) * 2 * n_seg, (cudaStream_t)stream));
+  int64_t bx = (n_per_seg + 256 * 8 - 1) / (256 * 8);
+  if (bx > 296) bx = 296;
+  dim3 grid((unsigned)bx, (unsigned)n_seg);
+  logmel_minmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mel, n_per_seg, log_offset, minmax);
+  count_launch();
+  return check_launch("logmel_minmax_kernel");
+}
+
+extern "C" int rvb_logmel_transpose(const float* mel, int n_seg, int n_mels, int n_frames, float log_offset,
+                                    const uint32_t* minmax, float* out, rvb_stream_t stream) {
+  RVB_REQUIRE(mel && out, "rvb_logmel_transpose: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_mels > 0 && n_frames > 0 && n_seg <= 65535, "rvb_logmel_transpose: bad shape");
+  const size_t smem = (size_t)kTrFrames * n_mels * sizeof(float);
+  RVB_REQUIRE(smem <= 200 * 1024, "rvb_logmel_transpose: n_mels %d too large", n_mels);
+  if (smem > 48 * 1024)
+    RVB_CUDA(cudaFuncSetAttribute(logmel_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((n_frames + kTrFrames - 1) / kTrFrames), (unsigned)n_seg);
+  logmel_transpose_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(mel, n_mels, n_frames, log_offset, minmax, out);
+  count_launch();
+  return check_launch("logmel_transpose_kernel");
 }
 
 extern "C" int rvb_minmax(const float* x, int n_seg, int64_t n_per_seg, uint32_t* minmax, rvb_stream_t stream) {

@@ -329,7 +329,7 @@ constexpr int F_BLOCK_N = 128;
 constexpr int F_STAGES = 3;
 constexpr int F_TILE_BYTES = 128 * BLOCK_K * 4;         // 16 KB (A and B tiles are both 128 rows)
 constexpr int F_STAGE_BYTES = 4 * F_TILE_BYTES;         // 64 KB
-constexpr int F_SMEM_BYTES = F_STAGES * F_STAGE_BYTES + BAR_BYTES + 1024;
+constexpr int F_SMEM_BYTES = F_STAGES * F_STAGE_BYTES + BAR_BYTES + 2 * 128 * 16 /* Mel table slots */ + 1024;
 
 struct FoldParams {
   int n_frames;               // frames per segment (T)
@@ -342,7 +342,118 @@ struct FoldParams {
   float* out0;
   const float* row_scale_inv;   // fp16 operands only: per-frame 2^-s_row
   float basis_scale_inv;        // fp16 operands only: 2^-s_basis
+  int dbg;                      // RVB_DBG experiments (timing only, results invalid): 1 alt acc, 2 no stores, 4 no TMA
+  // fused Mel projection (K1m): when mel_tab != nullptr the epilogue does not store the spectrum at all
+  const float4* mel_tab;        // [n_bins_pad] (w0, w1, band0 as int bits, -): bin k adds w0 P to band0, w1 P to band0+1
+  float* mel_out;               // [n_seg][n_mels][n_frames], zeroed before the launch, accumulated with RED.ADD
+  int n_mels;
 };
+
+// ---- epilogue of one unit (128 frames x 128 bins), shared by the one-CTA and the CTA-pair folded kernels ----
+// Thread <-> frame row, 4 chunks of 32 bins.  Plain mode: format + store the spectrum.  Mel mode: the spectrum value
+// P goes straight into the banded Mel projection.  The filterbank is pairwise overlapping (bin k feeds bands
+// band0[k] and band0[k]+1, band0 non-decreasing), and k is warp-uniform, so two rotating register accumulators
+// follow the band pair of the current bin; a finished band is added to mel_out[b][band][t] with one RED.ADD per
+// thread -- lanes are consecutive frames, so a warp's RED covers 128 contiguous bytes.  A band receives at most two
+// partial sums (one per tile it straddles) on top of the zero fill, so the result does not depend on their order.
+// The loop over the tile's 128 bins is ROLLED, four bins per trip straight out of TMEM (tcgen05.ld ...x4): one
+// epilogue warp runs alone on its scheduler, so straight-line code that overflows the instruction cache costs
+// ~10 cycles per instruction (profiles/r01c: the unrolled variant was 40 % slower than the whole contraction).
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+struct MelAcc {
+  int b0;
+  float acc0, acc1;
+};
+
+// Eight consecutive bins of one frame into the rotating band accumulators.
+template <int kEpi>
+__device__ __forceinline__ void mel_bins8(const FoldParams& p, const uint32_t (&re)[8], const uint32_t (&im)[8],
+                                          const float4* tab, float* __restrict__ col, bool f_ok, float scale,
+                                          float re_add, MelAcc& a) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 e = tab[i];                                       // same address in every lane: LDS broadcast
+    const float v = stft_value_t<kEpi>(p.power, fmaf(__uint_as_float(re[i]), scale, re_add), __uint_as_float(im[i]) * scale);
+    const int band = __float_as_int(e.z);
+    while (a.b0 < band) {                                          // warp-uniform
+      if (f_ok && a.b0 < p.n_mels && a.acc0 != 0.f && !(p.dbg & 8)) atomicAdd(col + (int64_t)a.b0 * p.n_frames, a.acc0);
+      a.acc0 = a.acc1;
+      a.acc1 = 0.f;
+      ++a.b0;
+    }
+    a.acc0 = fmaf(e.x, v, a.acc0);
+    a.acc1 = fmaf(e.y, v, a.acc1);
+  }
+}
+
+// The loop over the tile's 128 bins is ROLLED (eight bins per tcgen05.ld, two register sets so that the load of
+// the next eight is in flight while these are folded in): one epilogue warp runs alone on its scheduler, so
+// straight-line code that overflows the instruction cache costs ~10 cycles per instruction, and a TMEM load issued
+// and awaited in the same trip costs its full latency 32 times per tile (profiles/r01d).
+template <int kEpi>
+__device__ __forceinline__ void mel_unit(const FoldParams& p, uint32_t taddr, const float4* tab /* smem, 128 bins */,
+                                         float* __restrict__ col, bool f_ok, float scale, float re_add) {
+  MelAcc a{__float_as_int(tab[0].z), 0.f, 0.f};
+  uint32_t re0[8], im0[8], re1[8], im1[8];
+  tmem_ld8(taddr, re0);
+  tmem_ld8(taddr + 128, im0);
+#pragma unroll 1
+  for (int j = 0; j < 16; j += 2) {
+    tmem_ld_wait();                                                // set 0 (bins 8j .. 8j+7) has landed
+    tmem_ld8(taddr + 8 * (j + 1), re1);
+    tmem_ld8(taddr + 128 + 8 * (j + 1), im1);
+    mel_bins8<kEpi>(p, re0, im0, tab + 8 * j, col, f_ok, scale, re_add, a);
+    tmem_ld_wait();                                                // set 1
+    if (j + 2 < 16) {
+      tmem_ld8(taddr + 8 * (j + 2), re0);
+      tmem_ld8(taddr + 128 + 8 * (j + 2), im0);
+    }
+    mel_bins8<kEpi>(p, re1, im1, tab + 8 * (j + 1), col, f_ok, scale, re_add, a);
+  }
+  if (f_ok) {
+    if (a.b0 < p.n_mels && a.acc0 != 0.f) atomicAdd(col + (int64_t)a.b0 * p.n_frames, a.acc0);
+    if (a.b0 + 1 < p.n_mels && a.acc1 != 0.f) atomicAdd(col + (int64_t)(a.b0 + 1) * p.n_frames, a.acc1);
+  }
+}
+
+// Mel mode, before waiting for the accumulator: the four epilogue warps copy the tile's 128 table rows (2 KB) into
+// their smem slot (one 16-byte load per thread; a global load per bin would cost an L2 round trip per loop trip).
+// `slot` alternates with the accumulator stage; named barrier 1 orders the copy against every warp's reads, and a
+// slot is rewritten two units later, after all four warps have passed the next unit's barrier.
+constexpr int MEL_TAB_SMEM_BYTES = 2 * 128 * 16;
+__device__ __forceinline__ void mel_stage_table(const FoldParams& p, float4* tab_s, int n_tile, int row, int bar_id) {
+  tab_s[row] = __ldg(p.mel_tab + n_tile * 128 + row);
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+}
+
+__device__ __forceinline__ void fold_epilogue_unit(const FoldParams& p, uint32_t taddr, const float4* tab, bool f_ok,
+                                                   int n_tile, int b, int t, float scale, float re0) {
+  if (p.mel_tab != nullptr) {
+    if (p.dbg & 16) return;
+    float* col = p.mel_out + (int64_t)b * p.n_mels * p.n_frames + t;
+    if (p.epilogue == RVB_EPI_POWER) mel_unit<RVB_EPI_POWER>(p, taddr, tab, col, f_ok, scale, re0);
+    else if (p.epilogue == RVB_EPI_MAGNITUDE) mel_unit<RVB_EPI_MAGNITUDE>(p, taddr, tab, col, f_ok, scale, re0);
+    else mel_unit<RVB_EPI_POWER_P>(p, taddr, tab, col, f_ok, scale, re0);
+    return;
+  }
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t re[32], im[32];
+    tmem_ld32(taddr + c * 32, re);
+    tmem_ld32(taddr + 128 + c * 32, im);
+    tmem_ld_wait();
+    const int k0 = n_tile * 128 + c * 32;
+    if (f_ok && !((p.dbg & 2) && re[0] != 0x7fc12345u))
+      stft_store_chunk(p.epilogue, p.power, re, im, scale, re0, p.out0, b, k0, t, p.n_out_bins, p.n_store_bins,
+                       p.n_frames);
+  }
+}
 
 template <bool kF16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -406,6 +517,7 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
           const int a_row = (int)(chain * p.m_rows) + m_tile * BLOCK_M;
           const int b_row = chain * p.n_bins_pad + n_tile * F_BLOCK_N;
           mbar_wait(bar_empty(stage), phase ^ 1u, nullptr, 1);
+          if (p.dbg & 4) { mbar_arrive(bar_full(stage)); if (++stage == F_STAGES) { stage = 0; phase ^= 1u; } continue; }
           mbar_expect_tx(bar_full(stage), F_STAGE_BYTES);
           tma_load_2d(&tm_a_hi, s_tile(stage, 0), bar_full(stage), kk, a_row);
           tma_load_2d(&tm_a_lo, s_tile(stage, 1), bar_full(stage), kk, a_row);
@@ -439,9 +551,10 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
             const uint64_t adv = (uint64_t)(k * UMMA_K * 4 >> 4);     // one MMA consumes 32 bytes of the row
             // small cross terms first: while the accumulator is still small their truncation costs nothing
             if constexpr (kF16) {
-              umma_f16(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
+              const uint32_t d_x = (p.dbg & 1) ? (d_tmem ^ 256u) : d_tmem;
+              umma_f16(d_x, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
               umma_f16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
-              umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+              umma_f16(d_x, da_hi + adv, db_hi + adv, idesc, 1u);
             } else {
               umma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
               umma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
@@ -469,20 +582,12 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
       const int t = f_ok ? (int)(f - (int64_t)b * p.n_frames) : 0;
       const float re0 = (p.p0 != nullptr && f_ok) ? p.w0 * __ldg(p.p0 + f) : 0.f;
       const float scale = (kF16 && f_ok) ? __ldg(p.row_scale_inv + f) * p.basis_scale_inv : 1.f;
+      float4* tab_s = reinterpret_cast<float4*>(smem_raw + (bar_base - smem_u32(smem_raw)) + BAR_BYTES) + acc * 128;
+      if (p.mel_tab != nullptr) mel_stage_table(p, tab_s, n_tile, row, 1);
       mbar_wait(bar_tmem_full(acc), acc_phase, nullptr, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t re[32], im[32];
-        tmem_ld32(taddr + c * 32, re);
-        tmem_ld32(taddr + 128 + c * 32, im);
-        tmem_ld_wait();
-        const int k0 = n_tile * 128 + c * 32;
-        if (f_ok)
-          stft_store_chunk(p.epilogue, p.power, re, im, scale, re0, p.out0, b, k0, t, p.n_out_bins, p.n_store_bins,
-                           p.n_frames);
-      }
+      fold_epilogue_unit(p, taddr, tab_s, f_ok, n_tile, b, t, scale, re0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tmem_empty(acc));
@@ -512,10 +617,11 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
 //   tmem_empty[a]  lives in the leader, count 8: four epilogue warps of each CTA arrive (remotely from rank 1).
 // Only the leader's warp 1 issues MMAs; each CTA's epilogue drains its own 128 TMEM lanes.
 constexpr int P_STAGES = 4;
+constexpr int P_NUM_THREADS = 64 + 2 * 128;          // TMA warp, MMA warp, two epilogue groups of four warps
 constexpr int P_A_BYTES = 128 * 128;                    // 128 frame rows x one 128-byte swizzle row
 constexpr int P_B_BYTES = 64 * 128;                     // this CTA's half of the 128 basis rows
 constexpr int P_STAGE_BYTES = 2 * P_A_BYTES + 2 * P_B_BYTES;     // A_hi A_lo B_hi B_lo = 48 KB
-constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + BAR_BYTES + 1024;
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + BAR_BYTES + 2 * 128 * 16 /* Mel table slots */ + 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -568,7 +674,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_NUM_THREADS, 1)
 stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                            const FoldParams p) {
@@ -680,12 +786,16 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
     }
     __syncwarp();
   } else {
-    const int quarter = warp & 3;
+    // Two epilogue groups of four warps: group g drains accumulator stage g, i.e. every second unit of this
+    // cluster, so one unit's epilogue may take up to two MMA unit times before the tensor pipe waits for it.
+    const int group = (warp - EPI_WARP0) >> 2;
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
-    const uint32_t leader_tmem_empty0 = map_to_rank(bar_tmem_empty(0), 0);
-    int acc = 0;
+    const uint32_t leader_tmem_empty = map_to_rank(bar_tmem_empty(group), 0);
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(group * ACC_COLS);
+    float4* tab_s = reinterpret_cast<float4*>(smem_raw + (bar_base - smem_u32(smem_raw)) + BAR_BYTES) + group * 128;
     uint32_t acc_phase = 0;
-    for (int unit = unit0; unit < n_units; unit += unit_step) {
+    for (int unit = unit0 + group * unit_step; unit < n_units; unit += 2 * unit_step) {
       const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
       const int64_t f = (int64_t)m_tile * 256 + (int64_t)rank * 128 + row;       // flattened frame index
       const bool f_ok = f < p.m_rows;
@@ -693,24 +803,14 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
       const int t = f_ok ? (int)(f - (int64_t)b * p.n_frames) : 0;
       const float re0 = (p.p0 != nullptr && f_ok) ? p.w0 * __ldg(p.p0 + f) : 0.f;
       const float scale = f_ok ? __ldg(p.row_scale_inv + f) * p.basis_scale_inv : 1.f;
-      mbar_wait(bar_tmem_full(acc), acc_phase, nullptr, 4);
+      if (p.mel_tab != nullptr) mel_stage_table(p, tab_s, n_tile, row, 1 + group);
+      mbar_wait(bar_tmem_full(group), acc_phase, nullptr, 4);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t re[32], im[32];
-        tmem_ld32(taddr + c * 32, re);
-        tmem_ld32(taddr + 128 + c * 32, im);
-        tmem_ld_wait();
-        const int k0 = n_tile * 128 + c * 32;
-        if (f_ok)
-          stft_store_chunk(p.epilogue, p.power, re, im, scale, re0, p.out0, b, k0, t, p.n_out_bins, p.n_store_bins,
-                           p.n_frames);
-      }
+      fold_epilogue_unit(p, taddr, tab_s, f_ok, n_tile, b, t, scale, re0);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8 * acc);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty);
+      acc_phase ^= 1u;
     }
   }
 
@@ -872,15 +972,28 @@ extern "C" int rvb_stft_gemm(const float* sig_hi, const float* sig_lo, int n_seg
   return check_launch("stft_gemm_kernel");
 }
 
+struct MelArgs {
+  const float* tab;   // [n_bins_pad][4]
+  float* out;         // [n_seg][n_mels][n_frames]
+  int n_mels;
+};
+
 template <bool kF16>
 static int launch_folded(const char* who, const void* a_hi, const void* a_lo, const float* row_scale_inv, int n_seg,
                          int n_frames, int n_fft, const void* basis_hi, const void* basis_lo, float basis_scale_inv,
                          int n_bins_pad, const float* p0, float w0, int epilogue, float power, float* out0,
-                         int n_out_bins, rvb_stream_t stream) {
+                         int n_out_bins, rvb_stream_t stream, const MelArgs* mel = nullptr) {
   constexpr int kBlockK = kF16 ? 2 * BLOCK_K : BLOCK_K;
   constexpr int kElem = kF16 ? 2 : 4;
-  RVB_REQUIRE(a_hi && a_lo && basis_hi && basis_lo && out0, "%s: null pointer", who);
+  RVB_REQUIRE(a_hi && a_lo && basis_hi && basis_lo && (out0 || mel), "%s: null pointer", who);
   RVB_REQUIRE(!kF16 || row_scale_inv, "%s: null row_scale_inv", who);
+  if (mel) {
+    RVB_REQUIRE(mel->tab && mel->out && mel->n_mels > 0, "%s: bad Mel arguments", who);
+    RVB_REQUIRE((reinterpret_cast<uintptr_t>(mel->tab) & 15u) == 0, "%s: mel_tab must be 16-byte aligned", who);
+    RVB_REQUIRE(epilogue == RVB_EPI_POWER || epilogue == RVB_EPI_MAGNITUDE || epilogue == RVB_EPI_POWER_P,
+                "%s: the Mel projection takes the power / magnitude / power_p spectrum, got %d", who, epilogue);
+    RVB_CUDA(cudaMemsetAsync(mel->out, 0, sizeof(float) * (size_t)n_seg * mel->n_mels * n_frames, (cudaStream_t)stream));
+  }
   RVB_REQUIRE(n_seg > 0 && n_frames > 0, "%s: bad shape", who);
   RVB_REQUIRE(n_fft % (2 * kBlockK) == 0 && n_fft >= 2 * kBlockK, "%s: n_fft %d must be a multiple of %d", who, n_fft,
               2 * kBlockK);
@@ -910,6 +1023,10 @@ static int launch_folded(const char* who, const void* a_hi, const void* a_lo, co
   p.n_store_bins = n_out_bins < n_bins_pad ? n_out_bins : n_bins_pad;
   p.power = power; p.w0 = w0; p.p0 = (w0 != 0.f) ? p0 : nullptr; p.out0 = out0;
   p.row_scale_inv = row_scale_inv; p.basis_scale_inv = basis_scale_inv;
+  { const char* d = getenv("RVB_DBG"); p.dbg = d ? atoi(d) : 0; }
+  p.mel_tab = mel ? reinterpret_cast<const float4*>(mel->tab) : nullptr;
+  p.mel_out = mel ? mel->out : nullptr;
+  p.n_mels = mel ? mel->n_mels : 0;
 
   if constexpr (kF16) {
     static const bool one_cta = getenv("RVB_GEMM_1CTA") != nullptr;       // A/B switch for measurements
@@ -922,7 +1039,7 @@ static int launch_folded(const char* who, const void* a_hi, const void* a_lo, co
       if (max_clusters == 0) {
         RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
         cudaLaunchConfig_t qc = {};
-        qc.gridDim = dim3(num_sms() & ~1u); qc.blockDim = dim3(NUM_THREADS); qc.dynamicSmemBytes = P_SMEM_BYTES;
+        qc.gridDim = dim3(num_sms() & ~1u); qc.blockDim = dim3(P_NUM_THREADS); qc.dynamicSmemBytes = P_SMEM_BYTES;
         int nc = 0;
         RVB_CUDA(cudaOccupancyMaxActiveClusters(&nc, stft_gemm_fold_pair_kernel, &qc));
         RVB_REQUIRE(nc > 0, "%s: no CTA pair fits on this device", who);
@@ -930,7 +1047,7 @@ static int launch_folded(const char* who, const void* a_hi, const void* a_lo, co
       }
       const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
       const int n_clusters = (int)(n_units < max_clusters ? n_units : max_clusters);
-      stft_gemm_fold_pair_kernel<<<2 * n_clusters, NUM_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo,
+      stft_gemm_fold_pair_kernel<<<2 * n_clusters, P_NUM_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo,
                                                                                                       tm_b_hi, tm_b_lo, p);
       count_launch();
       return check_launch("stft_gemm_fold_pair_kernel");
@@ -963,6 +1080,17 @@ extern "C" int rvb_stft_gemm_folded_f16(const void* a_hi, const void* a_lo, cons
                                         float power, float* out0, int n_out_bins, rvb_stream_t stream) {
   return launch_folded<true>("rvb_stft_gemm_folded_f16", a_hi, a_lo, row_scale_inv, n_seg, n_frames, n_fft, basis_hi,
                              basis_lo, basis_scale_inv, n_bins_pad, p0, w0, epilogue, power, out0, n_out_bins, stream);
+}
+
+extern "C" int rvb_stft_mel_folded_f16(const void* a_hi, const void* a_lo, const float* row_scale_inv, int n_seg,
+                                       int n_frames, int n_fft, const void* basis_hi, const void* basis_lo,
+                                       float basis_scale_inv, int n_bins_pad, const float* p0, float w0, int spectrum,
+                                       float power, const float* mel_tab, int n_mels, float* mel_out,
+                                       rvb_stream_t stream) {
+  const MelArgs mel{mel_tab, mel_out, n_mels};
+  return launch_folded<true>("rvb_stft_mel_folded_f16", a_hi, a_lo, row_scale_inv, n_seg, n_frames, n_fft, basis_hi,
+                             basis_lo, basis_scale_inv, n_bins_pad, p0, w0, spectrum, power, nullptr, n_bins_pad, stream,
+                             &mel);
 }
 
 template <typename T>

@@ -27,24 +27,29 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.fixture(scope="module", params=["folded_f16", "folded_tf32", "direct"])
+@pytest.fixture(scope="module", params=["fused_f16", "folded_f16", "folded_tf32", "direct"])
 def mel(R, dev, request):
-    """All three contraction kernels: folded 3xFP16 (symmetric window, the default), folded 3xTF32, and the
-    unfolded 3xTF32 one."""
+    """Every front-end path: folded 3xFP16 contraction with the Mel projection fused into its epilogue (symmetric
+    window + triangular bank: the default), the same contraction followed by the separate Mel kernel, folded
+    3xTF32, and the unfolded 3xTF32 contraction."""
     import os
     m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
     if request.param == "direct":
         os.environ["RVB_NO_FOLD"] = "1"
     if request.param == "folded_tf32":
         os.environ["RVB_STFT_OPERAND"] = "tf32"
+    if request.param == "folded_f16":
+        os.environ["RVB_NO_MEL_FUSION"] = "1"
     try:
         tb = m.stft._device_tables()                          # tables are built here, under the env switches
+        fused = m._fused_table()
     finally:
-        os.environ.pop("RVB_NO_FOLD", None)
-        os.environ.pop("RVB_STFT_OPERAND", None)
+        for k in ("RVB_NO_FOLD", "RVB_STFT_OPERAND", "RVB_NO_MEL_FUSION"):
+            os.environ.pop(k, None)
     assert (tb["fold"] is None) == (request.param == "direct")
     if tb["fold"] is not None:
-        assert tb["fold"]["operand"] == request.param[len("folded_"):]
+        assert tb["fold"]["operand"] == request.param.split("_")[1]
+    assert (fused is not None) == (request.param == "fused_f16")
     return m
 
 
@@ -138,6 +143,34 @@ def test_pcm16_input_is_bit_identical_to_float_input(R, dev):
     assert torch.equal(m2.normalised_log_mel(ai), m2.normalised_log_mel(af))
     with pytest.raises(R._lib.RvbError):
         m(ai.to(torch.int32))
+
+
+def test_fused_mel_epilogue_matches_separate_kernel_and_is_reproducible(R, dev):
+    """Same contraction, Mel projection in the epilogue (RED.ADD partial sums) vs the separate banded kernel: equal to
+    fp32 summation-order rounding; two runs of the fused path are bit-identical (at most two partials per element)."""
+    import os
+    from reconvat_b200 import synth
+    a = torch.from_numpy(synth.segments(3, "mixed", seed=9)).to(dev)
+    fused = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    os.environ["RVB_NO_MEL_FUSION"] = "1"
+    try:
+        plain = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+        assert plain._fused_table() is None
+    finally:
+        os.environ.pop("RVB_NO_MEL_FUSION", None)
+    assert fused._fused_table() is not None
+    f1, f2, p1 = fused(a[:, :-1]), fused(a[:, :-1]), plain(a[:, :-1])
+    assert f1.shape == p1.shape == (3, 229, 640) and f1.is_contiguous()
+    assert torch.equal(f1, f2)
+    assert float(((f1 - p1).abs() / p1.abs().clamp_min(1e-30)).max()) < 2e-6
+    s1, s2 = fused.normalised_log_mel(a), plain.normalised_log_mel(a)
+    assert s1.shape == s2.shape == (3, 1, 640, 229)
+    assert float((s1 - s2).abs().max()) < 1e-6 and s1.min() == 0.0 and s1.max() == 1.0
+    # a bank the epilogue cannot represent (a bin feeding three bands) falls back to the separate kernel
+    odd = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    odd.mel_basis[5, 60] = 1e-3
+    assert odd._fused_table() is None
+    assert odd(a[:, :-1]).shape == (3, 229, 640)
 
 
 def test_pad_split_bit_exact(R, dev):

@@ -74,6 +74,25 @@ def test_band_rows_roundtrip_and_rejection():
         assert basis.band_rows(basis.mel_filterbank(**kw))[2].shape[0] <= 64
 
 
+def test_mel_epilogue_table_roundtrip_and_rejection():
+    mb = basis.mel_filterbank(16000, 2048, 229, 30, 8000)
+    tab = basis.mel_epilogue_table(mb, 1024)
+    band0 = tab[:, 2].view(np.int32)
+    assert tab.shape == (1024, 4) and np.all(np.diff(band0) >= 0) and band0.max() == 227
+    dense = np.zeros((229, 1024), np.float32)
+    for k in range(1024):
+        if tab[k, 0] != 0:
+            dense[band0[k], k] += tab[k, 0]
+        if tab[k, 1] != 0:
+            dense[band0[k] + 1, k] += tab[k, 1]
+    assert np.array_equal(dense, mb[:, :1024])
+    three = mb.copy(); three[5, 600] = 1e-3                  # bin 600 would feed three bands
+    assert basis.mel_epilogue_table(three, 1024) is None
+    assert basis.mel_epilogue_table(mb, 896) is None         # weight on bins the contraction does not produce
+    wide = basis.mel_filterbank(16000, 2048, 6, 30, 8000)    # bands hundreds of bins wide: > 2 tiles
+    assert basis.mel_epilogue_table(wide, 1024) is None
+
+
 def test_f16_fold_operand_is_block_scaled_and_reconstructs():
     ks, kc, _, _, win = basis.fourier_basis(2048, sr=16000)
     wcos, wsin = kc * win, ks * win
