@@ -41,6 +41,20 @@ def test_graph_replay_matches_eager(setup):
     assert torch.equal(step.replay(0)[2], want)
 
 
+def test_replay_many_on_two_streams(setup):
+    dev, host, step = setup
+    if not step._graphs:
+        step.capture([h.to(dev) for h in host[:2]])
+    want = [step.replay(i)[2].clone() for i in range(2)]
+    for i in range(2):
+        step._graphs[i][2][2].zero_()                          # wipe the static spec outputs
+    step.replay_many([0, 1, 0, 1, 0, 1], streams=2)
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert torch.equal(step._graphs[i][2][2], want[i])
+    step.check()
+
+
 def test_run_host_graph_and_eager_agree(setup):
     dev, host, step = setup
     if not step._graphs:
