@@ -266,6 +266,9 @@ def run_ours(args, rank, local_rank, world):
     e2e_value = world * B * SEG_SECONDS / (e2e_ms * 1e-3)
     assert torch.isfinite(results).all(), "non-finite VAT loss in the e2e run"
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peaks = load_peaks()
