@@ -104,8 +104,8 @@ class STFT(nn.Module):
         return super()._apply(fn, *args, **kwargs)
 
     # -- geometry -----------------------------------------------------------------------
-    def _geometry(self, num_samples):
-        if self.center:
+    def _geometry(self, num_samples, prepadded=False):
+        if self.center and not prepadded:
             if self.pad_mode == 'reflect':
                 if num_samples < self.pad_amount:
                     raise AssertionError("Signal length shorter than reflect padding length (n_fft // 2).")
@@ -142,14 +142,14 @@ class STFT(nn.Module):
     def n_frames(self, num_samples):
         return self._geometry(num_samples)[1]
 
-    def _spectrum(self, x, epilogue, power, make_out, mel_tab=None):
+    def _spectrum(self, x, epilogue, power, make_out, mel_tab=None, prepadded=False):
         """x: (B,1,L) CUDA float32.  Runs pad/frame/split + the tcgen05 contraction with the given epilogue.
         ``make_out(B, n_frames)`` -> (out tensor, n_out_bins).  Returns (out, n_frames).
         ``mel_tab`` (only with the folded fp16 contraction, see :meth:`fused_mel_ok`): fuse the Mel projection;
         make_out then returns the (B, n_mels, T) tensor and n_mels."""
         x2 = self._check_input(x)
         B, L = x2.shape
-        mode, n_frames, rows = self._geometry(L)
+        mode, n_frames, rows = self._geometry(L, prepadded)      # prepadded: x already carries its padding / halo
         out, n_out_bins = make_out(B, n_frames)
         tb = self._device_tables()
         pcm16 = x2.dtype == torch.int16
@@ -325,14 +325,14 @@ class MelSpectrogram(nn.Module):
             return _lib.EPI_MAGNITUDE
         return _lib.EPI_POWER_P
 
-    def _mel_fused(self, x, tab):
+    def _mel_fused(self, x, tab, prepadded=False):
         """(B,1,L) -> Mel spectrogram (B, n_mels, T) through the contraction with the fused Mel epilogue."""
         n_mels, dev = self.mel_basis.shape[0], x.device
         return self.stft._spectrum(x, self._spectrum_epilogue(), self.power,
                                    lambda B, T: (torch.empty((B, n_mels, T), dtype=torch.float32, device=dev), n_mels),
-                                   mel_tab=tab)
+                                   mel_tab=tab, prepadded=prepadded)
 
-    def _power_spectrogram(self, x):
+    def _power_spectrogram(self, x, prepadded=False):
         """(B,1,L) -> power (B, T, n_pow_bins), time-major, holding (sqrt(re^2+im^2))**power for every bin the
         filterbank reads (model/Spectrogram.py:458)."""
         bands = self._band_tables()
@@ -343,7 +343,8 @@ class MelSpectrogram(nn.Module):
         dev = x.device
         power, n_frames = self.stft._spectrum(
             x, epi | _lib.EPI_TIME_MAJOR, self.power,
-            lambda B, T: (torch.empty((B, T, n_pow_bins), dtype=torch.float32, device=dev), n_pow_bins))
+            lambda B, T: (torch.empty((B, T, n_pow_bins), dtype=torch.float32, device=dev), n_pow_bins),
+            prepadded=prepadded)
         return power, n_frames, bands
 
     def _project(self, power, n_frames, bands, log_offset, layout, out, minmax):
@@ -363,7 +364,7 @@ class MelSpectrogram(nn.Module):
         return out
 
     def normalised_log_mel(self, audio, trim_last=True, log_offset=1e-5, channel_dim=True, normalise=True,
-                           return_minmax=False):
+                           return_minmax=False, prepadded=False, reduce_minmax=None):
         """Fused front-end of ``UNet.run_on_batch`` (model/self_attention_VAT.py:1100-1104, 1112-1121):
 
             spec = self(audio[:, :-1]); spec = log(spec + 1e-5)
@@ -372,28 +373,38 @@ class MelSpectrogram(nn.Module):
         Returns a contiguous (B, 1, T, n_mels) tensor ((B, T, n_mels) when ``channel_dim=False``, the
         O&F convention of model/onset_frame_VAT.py:647-651).  ``audio`` is (B, L) / (L) / (B,1,L), float32 or
         the dataset's PCM int16 (then scaled by 1/32768 on the device, model/dataset.py:62).
+
+        Time-sharded inference on one long file (reconvat_b200.transcribe): ``prepadded=True`` says that ``audio`` is a
+        slice of the already reflect-padded signal including its halo (frames start at sample 0, no padding is
+        added), and ``reduce_minmax`` is called on the (B, 2) int32 min/max keys between the two passes so that the
+        caller can all-reduce them over the ranks that hold the other slices (model/self_attention_VAT.py:1302
+        normalises over the whole file).
         """
         x = basis.broadcast_dim(audio)
         if trim_last:
             x = x[:, :, :-1]                                  # a view; the kernel takes the row stride
         tab = self._fused_table()
         if tab is not None:
-            mel, n_frames = self._mel_fused(x, tab)
+            mel, n_frames = self._mel_fused(x, tab, prepadded)
             B, n_mels = mel.shape[0], mel.shape[1]
             out = torch.empty((B, n_frames, n_mels), dtype=torch.float32, device=x.device)
             minmax = None
             if normalise:
                 minmax = torch.empty((B, 2), dtype=torch.int32, device=x.device)
                 _lib.call("rvb_logmel_minmax", mel.data_ptr(), B, n_mels * n_frames, float(log_offset), minmax.data_ptr())
+                if reduce_minmax is not None:
+                    minmax = reduce_minmax(minmax)
             _lib.call("rvb_logmel_transpose", mel.data_ptr(), B, n_mels, n_frames, float(log_offset),
                       None if minmax is None else minmax.data_ptr(), out.data_ptr())
             out = out.unsqueeze(1) if channel_dim else out
             return (out, minmax) if return_minmax else out
-        power, n_frames, bands = self._power_spectrogram(x)
+        power, n_frames, bands = self._power_spectrogram(x, prepadded)
         B, n_mels = power.shape[0], self.mel_basis.shape[0]
         out = torch.empty((B, n_frames, n_mels), dtype=torch.float32, device=x.device)
         minmax = torch.empty((B, 2), dtype=torch.int32, device=x.device) if normalise else None
         self._project(power, n_frames, bands, log_offset, _lib.LAYOUT_TIME_MAJOR, out, minmax)
+        if normalise and reduce_minmax is not None:
+            minmax = reduce_minmax(minmax)
         if normalise:
             _lib.call("rvb_normalise", out.data_ptr(), out.data_ptr(), B, n_frames * n_mels, minmax.data_ptr())
         out = out.unsqueeze(1) if channel_dim else out

@@ -55,3 +55,14 @@ def global_min_max(local_min, local_max):
     bad = flag > 0
     nanv = torch.full_like(mn, float("nan"))
     return torch.where(bad, nanv, mn), torch.where(bad, nanv, mx)
+
+
+def global_minmax_keys(keys, group=None):
+    """All-reduce the (B, 2) int32 min/max keys that ``rvb_logmel_minmax`` / ``rvb_mel_project`` produce.  The keys
+    are order-preserving uint32 images of (-min, max) with NaN mapped to 0xffffffff, so ONE MAX all-reduce yields the
+    whole-file extrema and propagates NaN like torch.min/max -- bit-exact, no float round trip."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return keys
+    wide = keys.to(torch.int64) & 0xFFFFFFFF                 # uint32 value; NCCL / gloo have no uint32 MAX
+    dist.all_reduce(wide, op=dist.ReduceOp.MAX, group=group)
+    return torch.where(wide >= 2 ** 31, wide - 2 ** 32, wide).to(torch.int32)

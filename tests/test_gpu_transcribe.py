@@ -1,0 +1,50 @@
+"""Whole-file inference front-end sharded by time: equals the one-shot module result bit for bit, and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MEL_KW = dict(sr=16000, win_length=2048, n_mels=229, hop_length=512, fmin=30, fmax=8000, verbose=False)
+
+
+def test_time_sharded_file_equals_single_pass_and_oracle():
+    import reconvat_b200 as R
+    from reconvat_b200 import synth, transcribe
+    from oracle.frontend import FrontEndOracle
+    dev = torch.device("cuda:0")
+    L = 700 * 512 + 333                                        # ~22 s, not a multiple of anything
+    a16 = np.concatenate([synth.music_int16(L // 2, 31), synth.white_int16(L - L // 2, 32) // 8])
+    mel = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    whole = mel.normalised_log_mel(torch.from_numpy(a16).to(dev)[None, :])          # (1,1,T,229), module path
+    T = whole.shape[2]
+    one, span = transcribe.whole_file_frontend(mel, torch.from_numpy(a16), 0, 1)
+    assert span == (0, T) and torch.equal(one, whole)
+    ref = FrontEndOracle().spec_for_model(synth.to_float(a16)[None, :])
+    assert np.abs(whole.cpu().numpy() - ref).max() < 1e-4
+    for world in (2, 3, 8):
+        # emulate the ranks one after the other: pass 1 collects every rank's keys, the reduction is a MAX
+        keys = []
+        for r in range(world):
+            transcribe.whole_file_frontend(mel, torch.from_numpy(a16), r, world,
+                                           reduce_keys=lambda k: (keys.append(k.clone()), k)[1])
+        wide = torch.stack([k.to(torch.int64) & 0xFFFFFFFF for k in keys]).max(0).values
+        glob = torch.where(wide >= 2 ** 31, wide - 2 ** 32, wide).to(torch.int32)
+        parts, spans = [], []
+        for r in range(world):
+            s, sp = transcribe.whole_file_frontend(mel, torch.from_numpy(a16), r, world, reduce_keys=lambda k: glob)
+            parts.append(s)
+            spans.append(sp)
+        assert spans[0][0] == 0 and spans[-1][1] == T and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert torch.equal(torch.cat(parts, dim=2), whole)
+
+
+def test_padded_slice_matches_reflection_pad():
+    from reconvat_b200 import transcribe
+    a = torch.arange(50, dtype=torch.float32)
+    want = torch.nn.functional.pad(a[None, None, :], (8, 8), mode="reflect")[0, 0]
+    assert torch.equal(transcribe.padded_slice(a, 0, 66, 8), want)
+    assert torch.equal(transcribe.padded_slice(a, 5, 60, 8), want[5:60])
+    assert np.array_equal(transcribe.padded_slice(a.numpy(), 5, 60, 8), want[5:60].numpy())
+    with pytest.raises(AssertionError):
+        transcribe.padded_slice(a[:5], 0, 21, 8)

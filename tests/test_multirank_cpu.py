@@ -58,9 +58,21 @@ def _worker(rank, world, port, out):
         # (3) whole-file min/max across time shards, NaN-propagating
         mn, mx = parallel.global_min_max(torch.tensor([float(rank) - 3.0]), torch.tensor([float(rank) + 5.0]))
         nmn, nmx = parallel.global_min_max(torch.tensor([float("nan") if rank == 1 else 0.0]), torch.tensor([1.0]))
+        # (4) the same reduction on the kernels' uint32 keys (time-sharded whole-file inference): one MAX all-reduce
+        def key(f):                                           # f2key of rvb_common.cuh
+            b = int(np.float32(f).view(np.uint32))
+            return (~b & 0xFFFFFFFF) if b & 0x80000000 else (b | 0x80000000)
+
+        def as_i32(u):
+            return u - 2 ** 32 if u >= 2 ** 31 else u
+        lo, hi = (-7.5, 0.25) if rank == 0 else (-1.0, 3.5)    # rank 0 holds the minimum, rank 1 the maximum
+        k = torch.tensor([[as_i32(key(-lo)), as_i32(key(hi))], [as_i32(0xFFFFFFFF if rank == 1 else key(2.0)), as_i32(key(1.0))]],
+                         dtype=torch.int32)
+        kk = parallel.global_minmax_keys(k)
+        want = [as_i32(key(7.5)), as_i32(key(3.5)), as_i32(0xFFFFFFFF), as_i32(key(1.0))]
         if rank == 0:
             out.put((torch.cat([got[0][:3], got[1][:2]]).tolist(), t, mn.item(), mx.item(),
-                     bool(torch.isnan(nmn).item()), bool(torch.isnan(nmx).item())))
+                     bool(torch.isnan(nmn).item()), bool(torch.isnan(nmx).item()), kk.flatten().tolist() == want))
     finally:
         dist.destroy_process_group()
 
@@ -75,7 +87,8 @@ def test_two_ranks_gloo():
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
-    gathered, t, mn, mx, nan_mn, nan_mx = q.get()
+    gathered, t, mn, mx, nan_mn, nan_mx, keys_ok = q.get()
+    assert keys_ok
     assert gathered == [1.0, 11.0, 21.0, 31.0, 41.0]
     assert t == 2.0
     assert (mn, mx) == (-3.0, 6.0)
