@@ -262,6 +262,32 @@ int rvb_vat_direct(const float* d, const float* x, float* r_adv, float* x_adv, f
 #define RVB_BCE_WORKSPACE_FLOATS 1032
 int rvb_bce_mean(const float* p, const float* y, int64_t n, float* loss, float* workspace, rvb_stream_t stream);
 
+/*
+ * V2' / V4'  the other divergences of the reference's VAT flavours, same kernels as V2 / V4 (workspace as V4):
+ *   RVB_DIV_BCE  F.binary_cross_entropy(p, y)                        denom = n
+ *   RVB_DIV_BKL  binary_kl_div(p, y) (model/self_attention_VAT.py:248-255, KL_Div=True): both clamped to
+ *                [1e-4, 0.9999], F.kl_div(log [y, 1-y], [p, 1-p], reduction='batchmean')   denom = p.shape[0]
+ *   RVB_DIV_MSE  F.mse_loss(p, y) (model/onset_frame_VAT.py:232, stepwise_VAT_frame_stack)  denom = n
+ * loss = sum / denom;  grad = gscale * gscale_dev[0] * d(sum)/dp / denom.
+ */
+#define RVB_DIV_BCE 0
+#define RVB_DIV_BKL 1
+#define RVB_DIV_MSE 2
+int rvb_div_grad(int kind, const float* p, const float* y, float* grad, int64_t n, double denom,
+                 const float* gscale_dev, float gscale, rvb_stream_t stream);
+int rvb_div_mean(int kind, const float* p, const float* y, int64_t n, double denom, float* loss, float* workspace,
+                 rvb_stream_t stream);
+
+/*
+ * V1b / V3b'  binwise=True flavour of _l2_normalize, d / (|d| + 1e-8) (model/self_attention_VAT.py:242-243;
+ * stepwise_VAT(..., binwise=True)): elementwise, n = number of elements.  g == NULL: n_power == 0 (d is used as is).
+ */
+int rvb_vat_perturb_binwise(const float* x, const float* d, float* x_adv, int64_t n, float xi, int do_clamp,
+                            rvb_stream_t stream);
+int rvb_vat_finalize_binwise(const float* g, const float* d, const float* x, float* r_adv, float* x_adv, float* d_hat,
+                             int64_t n, float xi, float eps, float scale, int do_clamp, int32_t* status_flag,
+                             rvb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

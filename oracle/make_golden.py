@@ -121,6 +121,18 @@ def main():
         "unet_onset": (ref.UNet_onset.UNet_VAT, dict(XI=1e-6, epsilon=2, n_power=1, KL_Div=False), "unet_onset", 4),
         "onf": (ref.onset_frame_VAT.stepwise_VAT, dict(XI=1e-6, epsilon=0.1, n_power=1, KL_Div=False), "onf", 3),
         "unet_kl": (ref.self_attention_VAT.UNet_VAT, dict(XI=1e-6, epsilon=2, n_power=1, KL_Div=True), "unet", 4),
+        # the flavours no shipped script selects
+        "stepwise_sa_kl": (ref.self_attention_VAT.stepwise_VAT, dict(XI=1e-6, epsilon=2, n_power=1, KL_Div=True), "stepwise", 4),
+        "stepwise_sa_binwise": (ref.self_attention_VAT.stepwise_VAT,
+                                dict(XI=1e-6, epsilon=2, n_power=1, KL_Div=False, binwise=True), "stepwise", 4),
+        "onf_kl": (ref.onset_frame_VAT.stepwise_VAT, dict(XI=1e-6, epsilon=0.1, n_power=1, KL_Div=True), "onf", 3),
+        "seg": (ref.Segmentation.Seg_VAT, dict(XI=1e-6, epsilon=2, n_power=1, KL_Div=False), "seg", 4),
+        "stack_activation": (ref.onset_frame_VAT.stepwise_VAT_frame_stack,
+                             dict(XI=1e-6, epsilon=2, n_power=1, VAT_mode="activation"), "stack", 3),
+        "stack_frame": (ref.onset_frame_VAT.stepwise_VAT_frame_stack,
+                        dict(XI=1e-6, epsilon=2, n_power=1, VAT_mode="frame"), "stack", 3),
+        "stack_all": (ref.onset_frame_VAT.stepwise_VAT_frame_stack,
+                      dict(XI=1e-6, epsilon=2, n_power=1, VAT_mode="all"), "stack", 3),
     }
     # With the shipped XI=1e-6 the perturbed and clean posteriors differ at fp32 rounding level, so g
     # (and hence r_adv) is only reproducible on the same device with the same kernels: those cases pin
@@ -128,8 +140,7 @@ def main():
     # across devices.
     for tag in list(vat_cases):
         cls, kw, conv, xdim = vat_cases[tag]
-        if not kw.get("KL_Div"):
-            vat_cases[tag + "_xi01"] = (cls, dict(kw, XI=0.1), conv, xdim)
+        vat_cases[tag + "_xi01"] = (cls, dict(kw, XI=0.1), conv, xdim)
     out = {"x": xs, "P": np.array(P)}
     for tag, (cls, kw, conv, xdim) in vat_cases.items():
         model = StandInTranscriber(conv, n_in=F, n_out=P, seed=3)

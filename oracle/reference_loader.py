@@ -32,7 +32,9 @@ _cached = None
 
 def load_reference():
     """Returns a namespace: .Spectrogram, .utils, .constants, .self_attention_VAT,
-    .UNet_onset, .onset_frame_VAT, .VAT  (the reference's own module objects)."""
+    .UNet_onset, .onset_frame_VAT, .VAT, .Segmentation  (the reference's own module objects).
+    model/Segmentation.py imports matplotlib.pyplot at module level without using it on the VAT path: an empty
+    stand-in module is registered when matplotlib is not installed."""
     global _cached
     if _cached is not None:
         return _cached
@@ -41,7 +43,15 @@ def load_reference():
     from . import nnaudio_restate as R
 
     saved = {k: sys.modules.get(k) for k in
-             ("model", "nnAudio", "nnAudio.utils", "nnAudio.librosa_functions", "nnAudio.Spectrogram")}
+             ("model", "nnAudio", "nnAudio.utils", "nnAudio.librosa_functions", "nnAudio.Spectrogram",
+              "matplotlib", "matplotlib.pyplot")}
+    try:
+        import matplotlib.pyplot  # noqa: F401
+    except Exception:
+        mpl = types.ModuleType("matplotlib")
+        mpl.__path__ = []
+        mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+        sys.modules.update({"matplotlib": mpl, "matplotlib.pyplot": mpl.pyplot})
 
     pkg = types.ModuleType("model")
     pkg.__path__ = [os.path.join(REFERENCE_ROOT, "model")]
@@ -64,7 +74,7 @@ def load_reference():
         ns.Spectrogram = importlib.import_module("model.Spectrogram")
         nna.Spectrogram = ns.Spectrogram
         sys.modules["nnAudio.Spectrogram"] = ns.Spectrogram
-        for name in ("constants", "utils", "VAT", "self_attention_VAT", "UNet_onset", "onset_frame_VAT"):
+        for name in ("constants", "utils", "VAT", "self_attention_VAT", "UNet_onset", "onset_frame_VAT", "Segmentation"):
             setattr(ns, name, importlib.import_module("model." + name))
     finally:
         # leave sys.modules as we found it: the product installs its own

@@ -81,6 +81,70 @@ def binary_kl_div(y_pred, y_ref, lo=1e-4):
     return F.kl_div(p.log(), q, reduction="batchmean")
 
 
+def mse_mean(p, y):
+    """F.mse_loss (onset_frame_VAT.py:232)."""
+    return F.mse_loss(p, y)
+
+
+def l2_normalize_binwise(d):
+    """self_attention_VAT.py:242-243 (binwise=True): d / (|d| + 1e-8), no row coupling."""
+    return d / (torch.abs(d) + 1e-8)
+
+
+def power_grad_binwise_autograd(x, d, g, xi, scale=1.0, clamp=True):
+    """d.grad * scale for binwise=True through torch autograd, as the reference obtains it."""
+    d = d.clone().requires_grad_(True)
+    s = x + xi * l2_normalize_binwise(d)
+    (s.clamp(0, 1) if clamp else s).backward(g)
+    return d.grad.detach() * scale
+
+
+def power_grad_binwise_sequence(x, d, g, xi, scale=1.0, clamp=True):
+    """The same gradient written out as the fp32 op sequence autograd executes -- what the CUDA kernel follows.
+    Mathematically d/dd [d / (|d| + e)] = e / (|d| + e)^2 ~ 1e-8, but autograd forms it as the difference of two
+    O(1) terms, go/b - go*((d/b)/b)*sgn(d) with b = |d| + e, which cancels to fp32 rounding noise: the reference's
+    binwise direction IS that noise, so parity means reproducing the sequence, not the closed form."""
+    b = torch.abs(d) + 1e-8
+    go = g
+    if clamp:
+        s = x + xi * (d / b)
+        go = g * ((s >= 0) & (s <= 1)).to(g.dtype)          # clamp backward
+    gdn = go * xi                                             # mul backward
+    grad_a = gdn / b                                          # div backward w.r.t. the numerator
+    grad_b = -gdn * ((d / b) / b)                             # ... and the denominator (ATen: -grad * ((self/other)/other))
+    return (grad_a + grad_b * torch.sgn(d)) * scale           # abs backward, accumulation
+
+
+def finalize_binwise(x, dprime, eps, clamp=True):
+    dhat = l2_normalize_binwise(dprime)
+    r_adv = eps * dhat
+    s = x + r_adv
+    return r_adv, (s.clamp(0, 1) if clamp else s), dhat
+
+
+def vat_generic(outputs, divergences, x, d, xi, eps, scale=1.0, clamp=True, binwise=False):
+    """The loop shared by every flavour (self_attention_VAT.py:115-145, onset_frame_VAT.py:222-263,
+    Segmentation.py:39-77) with ``d`` injected: ``outputs(x)`` -> list of posteriors, ``divergences`` -> one
+    callable (p, y) -> scalar per posterior; the losses are summed in list order.
+    Returns (list of final losses, r_adv, dhat', g)."""
+    with torch.no_grad():
+        y_ref = outputs(x)
+    norm = l2_normalize_binwise if binwise else l2_normalize
+    x_adv = x + xi * norm(d)
+    x_adv = (x_adv.clamp(0, 1) if clamp else x_adv).detach().requires_grad_(True)
+    loss = sum(f(p, y) for f, p, y in zip(divergences, outputs(x_adv), y_ref))
+    (g,) = torch.autograd.grad(loss, x_adv)
+    if binwise:
+        dprime = power_grad_binwise_sequence(x, d, g, xi, scale, clamp)
+        r_adv, x_adv2, dhat = finalize_binwise(x, dprime, eps, clamp)
+    else:
+        dprime = power_grad_closed_form(x, d, g, xi, scale, clamp)
+        r_adv, x_adv2, dhat = finalize(x, dprime, eps, clamp)
+    with torch.no_grad():
+        final = [f(p, y) for f, p, y in zip(divergences, outputs(x_adv2), y_ref)]
+    return final, r_adv, dhat, g
+
+
 def vat_unet(transcribe, x, d, xi, eps, scale=1e10, clamp=True):
     """Whole UNet_VAT.forward (self_attention_VAT.py:162-202) with ``d``
     injected instead of drawn; ``transcribe(x) -> y`` is the model's frame

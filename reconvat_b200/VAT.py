@@ -12,7 +12,12 @@ class here                  replaces                                    differen
 ``onset_frame_VAT``         model/self_attention_VAT.py:204-238         3-tuple model output, 2-tuple
 ``UNet_VAT_onset``          model/UNet_onset.py:101-162                 frame+onset heads, dict loss
 ``stepwise_VAT_onf``        model/onset_frame_VAT.py:158-207            3-D x, frame head = output[2]
+``stepwise_VAT_frame_stack``  model/onset_frame_VAT.py:209-263          (activation, frame): MSE / BCE / both, *1e20
+``Seg_VAT``                 model/Segmentation.py:22-77                 ``model(x)`` is the posterior itself, *1e10
 ==========================  ==========================================  =================================
+
+``KL_Div=True`` (binary_kl_div, model/self_attention_VAT.py:248-255) and ``binwise=True`` (d / (|d| + 1e-8),
+:242-243) select the matching kernels (``rvb_div_*`` with RVB_DIV_BKL, ``rvb_vat_*_binwise``).
 
 What changes relative to the reference's op sequence (results identical within the stated tolerances):
 * ``x_adv`` is made a leaf and the model's backward is driven with ``torch.autograd.grad`` seeded by
@@ -33,7 +38,8 @@ import torch.nn as nn
 from . import _lib
 
 __all__ = ["stepwise_VAT_vatpy", "stepwise_VAT", "UNet_VAT", "onset_frame_VAT", "UNet_VAT_onset",
-           "stepwise_VAT_onf", "bce_mean", "l2_normalize"]
+           "stepwise_VAT_onf", "stepwise_VAT_frame_stack", "Seg_VAT", "bce_mean", "binary_kl_div", "mse_mean",
+           "l2_normalize"]
 
 
 def _rows(x):
@@ -49,17 +55,20 @@ def _check_input(x):
     return x if x.is_contiguous() else x.contiguous()     # the reference hands over a transposed view
 
 
-class _BCEMean(torch.autograd.Function):
-    """``F.binary_cross_entropy(p, y)`` (mean) with our forward and backward kernels.  ``y`` is a label
+class _DivMean(torch.autograd.Function):
+    """A divergence between posteriors with our forward and backward kernels: ``kind`` BCE
+    (``F.binary_cross_entropy``), BKL (the reference's ``binary_kl_div``) or MSE (``F.mse_loss``); ``y`` is a label
     (no gradient), exactly as y_ref in the VAT loop."""
 
     @staticmethod
-    def forward(ctx, p, y, workspace):
+    def forward(ctx, p, y, workspace, kind, denom):
         p = p.contiguous()
         y = y.contiguous()
         loss = torch.empty((), dtype=torch.float32, device=p.device)
-        _lib.call("rvb_bce_mean", _lib.ptr(p), _lib.ptr(y), p.numel(), loss.data_ptr(), workspace.data_ptr())
+        _lib.call("rvb_div_mean", kind, _lib.ptr(p), _lib.ptr(y), p.numel(), float(denom), loss.data_ptr(),
+                  workspace.data_ptr())
         ctx.save_for_backward(p, y)
+        ctx.kind, ctx.denom = kind, denom
         return loss
 
     @staticmethod
@@ -67,8 +76,9 @@ class _BCEMean(torch.autograd.Function):
         p, y = ctx.saved_tensors
         grad = torch.empty_like(p)
         go = grad_out.contiguous().to(torch.float32)
-        _lib.call("rvb_bce_grad", p.data_ptr(), y.data_ptr(), grad.data_ptr(), p.numel(), go.data_ptr(), 1.0)
-        return grad, None, None
+        _lib.call("rvb_div_grad", ctx.kind, p.data_ptr(), y.data_ptr(), grad.data_ptr(), p.numel(), float(ctx.denom),
+                  go.data_ptr(), 1.0)
+        return grad, None, None, None, None
 
 
 _workspaces = {}
@@ -82,20 +92,41 @@ def _workspace(device):
     return ws
 
 
-def bce_mean(p, y):
-    """Differentiable (w.r.t. ``p``) mean binary cross entropy on the device kernels."""
+def _denom(p, kind):
+    """What the reference divides the summed divergence by: numel for the means, the batch size for
+    ``F.kl_div(..., reduction='batchmean')``."""
+    return p.shape[0] if kind == _lib.DIV_BKL else p.numel()
+
+
+def _divergence(p, y, kind):
     if p.shape != y.shape:
         raise ValueError("Using a target size ({}) that is different to the input size ({}) is deprecated. "
                          "Please ensure they have the same size.".format(y.shape, p.shape))
-    return _BCEMean.apply(p, y.detach(), _workspace(p.device))
+    return _DivMean.apply(p, y.detach(), _workspace(p.device), kind, _denom(p, kind))
 
 
-def _bce_grad(p, y):
-    """d mean-BCE / d p as a plain tensor (seeds the model's backward in the power iteration)."""
+def bce_mean(p, y):
+    """Differentiable (w.r.t. ``p``) mean binary cross entropy on the device kernels."""
+    return _divergence(p, y, _lib.DIV_BCE)
+
+
+def binary_kl_div(y_pred, y_ref):
+    """model/self_attention_VAT.py:248-255 on the device kernels (differentiable w.r.t. ``y_pred``)."""
+    return _divergence(y_pred, y_ref, _lib.DIV_BKL)
+
+
+def mse_mean(p, y):
+    """``F.mse_loss(p, y)`` on the device kernels (differentiable w.r.t. ``p``)."""
+    return _divergence(p, y, _lib.DIV_MSE)
+
+
+def _div_grad(p, y, kind):
+    """d divergence / d p as a plain tensor (seeds the model's backward in the power iteration)."""
     p = p.detach().contiguous()
     y = y.detach().contiguous()
     grad = torch.empty_like(p)
-    _lib.call("rvb_bce_grad", _lib.ptr(p), _lib.ptr(y), grad.data_ptr(), p.numel(), None, 1.0)
+    _lib.call("rvb_div_grad", kind, _lib.ptr(p), _lib.ptr(y), grad.data_ptr(), p.numel(), float(_denom(p, kind)),
+              None, 1.0)
     return grad
 
 
@@ -113,7 +144,8 @@ def l2_normalize(d):
 class _VATCore(nn.Module):
     # flavour knobs, overridden by the named subclasses
     _use_transcriber = False       # model.transcriber(x) vs model(x)
-    _heads = (0,)                  # indices of the model outputs that enter the divergence
+    _heads = (0,)                  # indices of the model outputs that enter the divergence (None: the output itself)
+    _kinds = None                  # divergence per head; None -> BCE, or binary KL when KL_Div=True
     _scale = 1.0                   # d.grad multiplier (1e10 in the UNet / O&F flavours)
     _clamp = True                  # (x + r).clamp(0, 1)
     _n_returns = 3
@@ -130,12 +162,9 @@ class _VATCore(nn.Module):
         self._pending = None       # (pinned host copy of the NaN flag, event) of the previous eager call
         self._host_flag = None     # persistent pinned int32 (allocated once: no per-call cudaHostAlloc)
         self.last_flag = None      # device flag of the latest call (what a captured CUDA graph leaves behind)
-        if KL_Div:
-            raise NotImplementedError("reconvat_b200 VAT: KL_Div=True (binary_kl_div, model/self_attention_VAT.py:"
-                                      "248-255) is not on any shipped configuration; SURVEY.md section 8 row f4")
-        if binwise:
-            raise NotImplementedError("reconvat_b200 VAT: binwise=True is never selected by the reference "
-                                      "(hard-wired False, model/self_attention_VAT.py:159)")
+        if KL_Div and len(self._heads) > 1:
+            raise NotImplementedError("reconvat_b200 VAT: KL_Div=True with two heads -- the reference itself fails "
+                                      "there (NameError: y_pred, model/UNet_onset.py:133-134)")
         if n_power not in (0, 1):
             raise NotImplementedError("reconvat_b200 VAT: n_power=%r -- the reference itself fails for n_power > 1 "
                                       "(d.grad is None on the second iteration, model/self_attention_VAT.py:184)"
@@ -160,7 +189,12 @@ class _VATCore(nn.Module):
 
     def _model_outputs(self, model, x):
         out = model.transcriber(x) if self._use_transcriber else model(x)
-        return [out[i] for i in self._heads]
+        return [out if i is None else out[i] for i in self._heads]
+
+    def _head_kinds(self):
+        if self._kinds is not None:
+            return self._kinds
+        return (_lib.DIV_BKL if self.KL_Div else _lib.DIV_BCE,) * len(self._heads)
 
     def forward(self, model, x):
         x = _check_input(x).detach()
@@ -175,19 +209,33 @@ class _VATCore(nn.Module):
         r_adv = torch.empty_like(x)
         x_adv2 = torch.empty_like(x)
         d_hat = torch.empty_like(x)
+        kinds = self._head_kinds()
         if self.n_power == 1:
             x_adv = torch.empty_like(x)
-            _lib.call("rvb_vat_perturb", x.data_ptr(), d.data_ptr(), x_adv.data_ptr(), n_rows, row_len,
-                      float(self.XI), int(self._clamp))
+            if self.binwise:
+                _lib.call("rvb_vat_perturb_binwise", x.data_ptr(), d.data_ptr(), x_adv.data_ptr(), x.numel(),
+                          float(self.XI), int(self._clamp))
+            else:
+                _lib.call("rvb_vat_perturb", x.data_ptr(), d.data_ptr(), x_adv.data_ptr(), n_rows, row_len,
+                          float(self.XI), int(self._clamp))
             x_adv.requires_grad_(True)
             with torch.enable_grad():
                 y_pred = self._model_outputs(model, x_adv)
-                seeds = [_bce_grad(p, y) for p, y in zip(y_pred, y_ref)]  # d(sum of mean BCEs)/dp (…:182)
+                seeds = [_div_grad(p, y, k) for p, y, k in zip(y_pred, y_ref, kinds)]  # d(sum of divergences)/dp (…:182)
                 (g,) = torch.autograd.grad(y_pred, [x_adv], seeds)        # model backward only (…:183)
             model.zero_grad()                                             # side effect kept (…:185)
-            _lib.call("rvb_vat_finalize", g.contiguous().data_ptr(), d.data_ptr(), x.data_ptr(), r_adv.data_ptr(),
-                      x_adv2.data_ptr(), d_hat.data_ptr(), n_rows, row_len, float(self.XI), float(self.epsilon),
-                      float(self._scale), int(self._clamp), flag.data_ptr())
+            if self.binwise:
+                _lib.call("rvb_vat_finalize_binwise", g.contiguous().data_ptr(), d.data_ptr(), x.data_ptr(),
+                          r_adv.data_ptr(), x_adv2.data_ptr(), d_hat.data_ptr(), x.numel(), float(self.XI),
+                          float(self.epsilon), float(self._scale), int(self._clamp), flag.data_ptr())
+            else:
+                _lib.call("rvb_vat_finalize", g.contiguous().data_ptr(), d.data_ptr(), x.data_ptr(), r_adv.data_ptr(),
+                          x_adv2.data_ptr(), d_hat.data_ptr(), n_rows, row_len, float(self.XI), float(self.epsilon),
+                          float(self._scale), int(self._clamp), flag.data_ptr())
+        elif self.binwise:
+            _lib.call("rvb_vat_finalize_binwise", None, d.data_ptr(), x.data_ptr(), r_adv.data_ptr(), x_adv2.data_ptr(),
+                      d_hat.data_ptr(), x.numel(), float(self.XI), float(self.epsilon), 1.0, int(self._clamp),
+                      flag.data_ptr())
         else:
             _lib.call("rvb_vat_direct", d.data_ptr(), x.data_ptr(), r_adv.data_ptr(), x_adv2.data_ptr(),
                       d_hat.data_ptr(), n_rows, row_len, float(self.epsilon), int(self._clamp), flag.data_ptr())
@@ -205,11 +253,13 @@ class _VATCore(nn.Module):
                 self.check()
 
         y_pred = self._model_outputs(model, x_adv2)                       # graph to the parameters kept (…:195)
-        losses = [bce_mean(p, y) for p, y in zip(y_pred, y_ref)]          # (…:200)
+        losses = [_divergence(p, y, k) for p, y, k in zip(y_pred, y_ref, kinds)]   # (…:200)
         if self._dict_loss is not None:
             vat_loss = dict(zip(self._dict_loss, losses))
         else:
             vat_loss = losses[0]
+            for extra in losses[1:]:
+                vat_loss = vat_loss + extra
         if self._n_returns == 2:
             return vat_loss, r_adv
         return vat_loss, r_adv, d_hat
@@ -278,3 +328,38 @@ class stepwise_VAT_onf(_VATCore):
     def __init__(self, XI, epsilon, n_power, KL_Div, strict=None):
         super().__init__()
         self._init_common(XI, epsilon, n_power, KL_Div, False, strict)
+
+
+class stepwise_VAT_frame_stack(_VATCore):
+    """model/onset_frame_VAT.py:209-263 -- ``stepwise_VAT_frame_stack(XI, epsilon, n_power, VAT_mode)``: the model
+    returns (activation, frame); the divergence is MSE on the activation ('activation'), BCE on the frame posterior
+    ('frame') or their sum ('all'); d.grad is scaled by 1e20; returns (vat_loss, r_adv)."""
+    _scale = 1e20
+    _n_returns = 2
+    _nan_message = "r_adv exploded, please debug tune down the XI for VAT"
+
+    def __init__(self, XI, epsilon, n_power, VAT_mode, strict=None):
+        super().__init__()
+        modes = {"activation": ((0,), (_lib.DIV_MSE,)), "frame": ((1,), (_lib.DIV_BCE,)),
+                 "all": ((1, 0), (_lib.DIV_BCE, _lib.DIV_MSE))}          # dist_frame + dist_activation (:241)
+        if VAT_mode not in modes:
+            # the reference leaves `dist` unbound for any other mode (UnboundLocalError at :243)
+            raise ValueError("VAT_mode must be 'activation', 'frame' or 'all', got %r" % (VAT_mode,))
+        self._heads, self._kinds = modes[VAT_mode]
+        self.VAT_mode = VAT_mode
+        self._init_common(XI, epsilon, n_power, strict=strict)
+
+
+class Seg_VAT(_VATCore):
+    """model/Segmentation.py:22-77 -- ``Seg_VAT(XI, epsilon, n_power, KL_Div, reconstruction=False)``: ``model(x)`` is
+    the posterior itself (no tuple), d.grad * 1e10, returns (vat_loss, r_adv, d_hat)."""
+    _heads = (None,)
+    _scale = 1e10
+
+    def __init__(self, XI, epsilon, n_power, KL_Div, reconstruction=False, strict=None):
+        super().__init__()
+        if KL_Div:
+            raise NotImplementedError("reconvat_b200 Seg_VAT: KL_Div=True -- the reference itself fails there "
+                                      "(NameError: binary_kl_div is not defined in model/Segmentation.py:55)")
+        self._init_common(XI, epsilon, n_power, KL_Div, False, strict)
+        self.reconstruction = reconstruction

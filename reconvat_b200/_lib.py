@@ -39,12 +39,17 @@ SIGNATURES = {
     "rvb_vat_perturb": [_c_p, _c_p, _c_p, _i64, _i32, _f32, _i32, _c_p],
     "rvb_bce_grad": [_c_p, _c_p, _c_p, _i64, _c_p, _f32, _c_p],
     "rvb_vat_finalize": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i64, _i32, _f32, _f32, _f32, _i32, _c_p, _c_p],
+    "rvb_div_grad": [_i32, _c_p, _c_p, _c_p, _i64, ctypes.c_double, _c_p, _f32, _c_p],
+    "rvb_div_mean": [_i32, _c_p, _c_p, _i64, ctypes.c_double, _c_p, _c_p, _c_p],
+    "rvb_vat_perturb_binwise": [_c_p, _c_p, _c_p, _i64, _f32, _i32, _c_p],
+    "rvb_vat_finalize_binwise": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i64, _f32, _f32, _f32, _i32, _c_p, _c_p],
     "rvb_vat_direct": [_c_p, _c_p, _c_p, _c_p, _c_p, _i64, _i32, _f32, _i32, _c_p, _c_p],
     "rvb_bce_mean": [_c_p, _c_p, _i64, _c_p, _c_p, _c_p],
 }
 ABI_VERSION = 1
 BCE_WORKSPACE_FLOATS = 1032
 
+DIV_BCE, DIV_BKL, DIV_MSE = 0, 1, 2
 PAD_REFLECT, PAD_CONSTANT, PAD_NONE = 0, 1, 2
 EPI_POWER, EPI_MAGNITUDE, EPI_COMPLEX, EPI_PHASE, EPI_POWER_P = 0, 1, 2, 3, 4
 EPI_TIME_MAJOR = 0x10

@@ -142,15 +142,86 @@ vat_direct_kernel(const float* __restrict__ d, const float* __restrict__ x, floa
   finalize_row(rd, rx, r_adv, x_adv, d_hat, off, row_len, lane, eps, do_clamp, status_flag);
 }
 
-// ---- V2: d mean-BCE / d p ---------------------------------------------------------------
-__device__ __forceinline__ float bce_grad_one(float p, float y, float s) {
-  return (p - y) / fmaxf((1.f - p) * p, 1e-12f) * s;
-}
+// ---- binwise=True flavour of _l2_normalize: d / (|d| + 1e-8), no row coupling (self_attention_VAT.py:242-243) ----
+// Mathematically d/dd [d / (|d| + e)] = e / (|d| + e)^2 ~ 1e-8, but autograd forms it as the difference of two O(1)
+// terms, go/b - go*((d/b)/b)*sgn(d) with b = |d| + e, which cancels to fp32 rounding noise: the reference's binwise
+// direction IS that noise.  Parity therefore means executing the same IEEE op sequence (ATen's mul / div / abs
+// backward formulas) with contraction disabled (__f*_rn intrinsics are never fused); with the same g the result is
+// bit-identical to the reference's (tests: golden r_adv, torch.equal).
+__device__ __forceinline__ float binwise_norm(float d) { return __fdiv_rn(d, __fadd_rn(fabsf(d), 1e-8f)); }
 
 __global__ void __launch_bounds__(256)
-bce_grad_kernel(const float* __restrict__ p, const float* __restrict__ y, float* __restrict__ grad, int64_t n,
-                const float* __restrict__ gscale_dev, float gscale, int vec_ok) {
-  const float s = (gscale_dev ? __ldg(gscale_dev) : 1.f) * gscale / (float)n;
+vat_perturb_binwise_kernel(const float* __restrict__ x, const float* __restrict__ d, float* __restrict__ x_adv,
+                           int64_t n, float xi, int do_clamp) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float s = __fadd_rn(__ldg(x + i), __fmul_rn(xi, binwise_norm(__ldg(d + i))));
+    x_adv[i] = do_clamp ? clamp01(s) : s;
+  }
+}
+
+// have_g = 1: d' = scale * d.grad (sequence above), then r_adv = eps * d' / (|d'| + 1e-8), x_adv, dhat.
+// have_g = 0 (n_power == 0): d' = d.
+__global__ void __launch_bounds__(256)
+vat_finalize_binwise_kernel(const float* __restrict__ g, const float* __restrict__ d, const float* __restrict__ x,
+                            float* __restrict__ r_adv, float* __restrict__ x_adv, float* __restrict__ d_hat,
+                            int64_t n, float xi, float eps, float scale, int do_clamp, int have_g,
+                            int32_t* status_flag) {
+  unsigned bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float dv = __ldg(d + i), xv = __ldg(x + i);
+    float dp = dv;
+    if (have_g) {
+      const float b = __fadd_rn(fabsf(dv), 1e-8f);
+      const float q = __fdiv_rn(dv, b);
+      float go = __ldg(g + i);
+      if (do_clamp) {
+        const float s = __fadd_rn(xv, __fmul_rn(xi, q));
+        go = (s >= 0.f && s <= 1.f) ? go : 0.f;                         // clamp backward
+      }
+      const float gdn = __fmul_rn(go, xi);                              // mul backward
+      const float grad_a = __fdiv_rn(gdn, b);                           // div backward, numerator
+      const float grad_b = __fmul_rn(-gdn, __fdiv_rn(q, b));            // div backward, denominator
+      const float sgn = (dv > 0.f) ? 1.f : ((dv < 0.f) ? -1.f : dv);    // torch.sgn: 0 -> 0, NaN -> NaN
+      dp = __fmul_rn(__fadd_rn(grad_a, __fmul_rn(grad_b, sgn)), scale);
+    }
+    const float dh = binwise_norm(dp);
+    const float r = __fmul_rn(eps, dh);
+    bad |= (isnan(r) ? 1u : 0u) | (isinf(r) ? 2u : 0u);
+    const float s2 = __fadd_rn(xv, r);
+    r_adv[i] = r;
+    x_adv[i] = do_clamp ? clamp01(s2) : s2;
+    d_hat[i] = dh;
+  }
+  bad = __reduce_or_sync(kFull, bad);
+  if (bad && (threadIdx.x & 31) == 0 && status_flag) atomicOr(status_flag, (int)bad);
+}
+
+// ---- V2: d divergence / d p -------------------------------------------------------------
+// kind: RVB_DIV_BCE   F.binary_cross_entropy(p, y)                      (model/self_attention_VAT.py:182,200)
+//       RVB_DIV_BKL   binary_kl_div(p, y): both clamped to [1e-4, 0.9999], F.kl_div(log [y, 1-y], [p, 1-p],
+//                     'batchmean')                                       (model/self_attention_VAT.py:248-255)
+//       RVB_DIV_MSE   F.mse_loss(p, y)                                   (model/onset_frame_VAT.py:232)
+template <int kKind>
+__device__ __forceinline__ float div_grad_one(float p, float y, float s) {
+  if constexpr (kKind == RVB_DIV_BCE) {
+    return (p - y) / fmaxf((1.f - p) * p, 1e-12f) * s;                    // ATen's binary_cross_entropy_backward
+  } else if constexpr (kKind == RVB_DIV_BKL) {
+    // d/dq0 [q0 (log q0 - log p0) + q1 (log q1 - log p1)], q1 = 1 - q0; torch.clamp passes the gradient on the
+    // closed interval only
+    const float q0 = fminf(fmaxf(p, 1e-4f), 0.9999f), p0 = fminf(fmaxf(y, 1e-4f), 0.9999f);
+    const float q1 = 1.f - q0, p1 = 1.f - p0;
+    const float g = (logf(q0) - logf(p0)) - (logf(q1) - logf(p1));
+    return (p >= 1e-4f && p <= 0.9999f) ? g * s : 0.f;
+  } else {
+    return 2.f * (p - y) * s;
+  }
+}
+
+template <int kKind>
+__global__ void __launch_bounds__(256)
+div_grad_kernel(const float* __restrict__ p, const float* __restrict__ y, float* __restrict__ grad, int64_t n,
+                double denom, const float* __restrict__ gscale_dev, float gscale, int vec_ok) {
+  const float s = (gscale_dev ? __ldg(gscale_dev) : 1.f) * gscale / (float)denom;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (vec_ok) {
@@ -160,29 +231,41 @@ bce_grad_kernel(const float* __restrict__ p, const float* __restrict__ y, float*
     float4* g4 = reinterpret_cast<float4*>(grad);
     for (int64_t j = i; j < n4; j += stride) {
       float4 a = __ldg(p4 + j), b = __ldg(y4 + j), o;
-      o.x = bce_grad_one(a.x, b.x, s);
-      o.y = bce_grad_one(a.y, b.y, s);
-      o.z = bce_grad_one(a.z, b.z, s);
-      o.w = bce_grad_one(a.w, b.w, s);
+      o.x = div_grad_one<kKind>(a.x, b.x, s);
+      o.y = div_grad_one<kKind>(a.y, b.y, s);
+      o.z = div_grad_one<kKind>(a.z, b.z, s);
+      o.w = div_grad_one<kKind>(a.w, b.w, s);
       g4[j] = o;
     }
-    for (int64_t j = (n4 << 2) + i; j < n; j += stride) grad[j] = bce_grad_one(__ldg(p + j), __ldg(y + j), s);
+    for (int64_t j = (n4 << 2) + i; j < n; j += stride) grad[j] = div_grad_one<kKind>(__ldg(p + j), __ldg(y + j), s);
   } else {
-    for (int64_t j = i; j < n; j += stride) grad[j] = bce_grad_one(__ldg(p + j), __ldg(y + j), s);
+    for (int64_t j = i; j < n; j += stride) grad[j] = div_grad_one<kKind>(__ldg(p + j), __ldg(y + j), s);
   }
 }
 
-// ---- V4: mean BCE, deterministic ---------------------------------------------------------
+// ---- V4: divergence value (sum / denom), deterministic -----------------------------------
+template <int kKind>
 __device__ __forceinline__ float bce_one(float p, float y) {
-  // ATen: (y - 1) * max(log1p(-p), -100) - y * max(log(p), -100)
-  return (y - 1.f) * fmaxf(log1pf(-p), -100.f) - y * fmaxf(logf(p), -100.f);
+  if constexpr (kKind == RVB_DIV_BCE) {
+    // ATen: (y - 1) * max(log1p(-p), -100) - y * max(log(p), -100)
+    return (y - 1.f) * fmaxf(log1pf(-p), -100.f) - y * fmaxf(logf(p), -100.f);
+  } else if constexpr (kKind == RVB_DIV_BKL) {
+    // kl_div(input = log [p0, p1], target = [q0, q1]) pointwise: q log q - q input, summed over the pair
+    const float q0 = fminf(fmaxf(p, 1e-4f), 0.9999f), p0 = fminf(fmaxf(y, 1e-4f), 0.9999f);
+    const float q1 = 1.f - q0, p1 = 1.f - p0;
+    return (q0 * logf(q0) - q0 * logf(p0)) + (q1 * logf(q1) - q1 * logf(p1));
+  } else {
+    const float e = p - y;
+    return e * e;
+  }
 }
 
 constexpr int kBceMaxBlocks = 1024;
 
+template <int kKind>
 __global__ void __launch_bounds__(256)
-bce_mean_kernel(const float* __restrict__ p, const float* __restrict__ y, int64_t n, float* __restrict__ loss,
-                float* __restrict__ workspace, int vec_ok) {
+div_mean_kernel(const float* __restrict__ p, const float* __restrict__ y, int64_t n, double denom,
+                float* __restrict__ loss, float* __restrict__ workspace, int vec_ok) {
   __shared__ float warp_part[8];
   __shared__ bool is_last;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -194,11 +277,11 @@ bce_mean_kernel(const float* __restrict__ p, const float* __restrict__ y, int64_
     const float4* y4 = reinterpret_cast<const float4*>(y);
     for (int64_t j = i; j < n4; j += stride) {
       float4 a = __ldg(p4 + j), b = __ldg(y4 + j);
-      acc += (bce_one(a.x, b.x) + bce_one(a.y, b.y)) + (bce_one(a.z, b.z) + bce_one(a.w, b.w));
+      acc += (bce_one<kKind>(a.x, b.x) + bce_one<kKind>(a.y, b.y)) + (bce_one<kKind>(a.z, b.z) + bce_one<kKind>(a.w, b.w));
     }
-    for (int64_t j = (n4 << 2) + i; j < n; j += stride) acc += bce_one(__ldg(p + j), __ldg(y + j));
+    for (int64_t j = (n4 << 2) + i; j < n; j += stride) acc += bce_one<kKind>(__ldg(p + j), __ldg(y + j));
   } else {
-    for (int64_t j = i; j < n; j += stride) acc += bce_one(__ldg(p + j), __ldg(y + j));
+    for (int64_t j = i; j < n; j += stride) acc += bce_one<kKind>(__ldg(p + j), __ldg(y + j));
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
@@ -227,7 +310,7 @@ bce_mean_kernel(const float* __restrict__ p, const float* __restrict__ y, int64_
       __syncthreads();
     }
     if (threadIdx.x == 0) {
-      *loss = (float)(dsum[0] / (double)n);
+      *loss = (float)(dsum[0] / denom);
       *ticket = 0u;   // self-cleaning for the next call on this stream
     }
   }
@@ -299,25 +382,73 @@ static unsigned flat_grid(int64_t n, int per_thread) {
   return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
-extern "C" int rvb_bce_grad(const float* p, const float* y, float* grad, int64_t n, const float* gscale_dev,
-                            float gscale, rvb_stream_t stream) {
-  RVB_REQUIRE(p && y && grad, "rvb_bce_grad: null pointer");
-  RVB_REQUIRE(n >= 0, "rvb_bce_grad: negative size");
+template <typename F>
+static int dispatch_kind(int kind, const char* who, F&& f) {
+  switch (kind) {
+    case RVB_DIV_BCE: return f(std::integral_constant<int, RVB_DIV_BCE>{});
+    case RVB_DIV_BKL: return f(std::integral_constant<int, RVB_DIV_BKL>{});
+    case RVB_DIV_MSE: return f(std::integral_constant<int, RVB_DIV_MSE>{});
+    default: set_error("%s: unknown divergence kind %d", who, kind); return RVB_ERR_ARG;
+  }
+}
+
+extern "C" int rvb_div_grad(int kind, const float* p, const float* y, float* grad, int64_t n, double denom,
+                            const float* gscale_dev, float gscale, rvb_stream_t stream) {
+  RVB_REQUIRE(p && y && grad, "rvb_div_grad: null pointer");
+  RVB_REQUIRE(n >= 0 && denom > 0, "rvb_div_grad: bad size");
   if (n == 0) return RVB_OK;
   const int vec = aligned16(p) && aligned16(y) && aligned16(grad);
-  bce_grad_kernel<<<flat_grid(n, 8), 256, 0, (cudaStream_t)stream>>>(p, y, grad, n, gscale_dev, gscale, vec);
-  count_launch();
-  return check_launch("bce_grad_kernel");
+  return dispatch_kind(kind, "rvb_div_grad", [&](auto k) {
+    div_grad_kernel<decltype(k)::value><<<flat_grid(n, 8), 256, 0, (cudaStream_t)stream>>>(p, y, grad, n, denom,
+                                                                                            gscale_dev, gscale, vec);
+    count_launch();
+    return check_launch("div_grad_kernel");
+  });
+}
+
+extern "C" int rvb_div_mean(int kind, const float* p, const float* y, int64_t n, double denom, float* loss,
+                            float* workspace, rvb_stream_t stream) {
+  RVB_REQUIRE(p && y && loss && workspace, "rvb_div_mean: null pointer");
+  RVB_REQUIRE(n > 0 && denom > 0, "rvb_div_mean: empty input (the reference returns NaN for an empty mean)");
+  unsigned grid = flat_grid(n, 16);
+  if (grid > (unsigned)kBceMaxBlocks) grid = kBceMaxBlocks;
+  const int vec = aligned16(p) && aligned16(y);
+  return dispatch_kind(kind, "rvb_div_mean", [&](auto k) {
+    div_mean_kernel<decltype(k)::value><<<grid, 256, 0, (cudaStream_t)stream>>>(p, y, n, denom, loss, workspace, vec);
+    count_launch();
+    return check_launch("div_mean_kernel");
+  });
+}
+
+extern "C" int rvb_bce_grad(const float* p, const float* y, float* grad, int64_t n, const float* gscale_dev,
+                            float gscale, rvb_stream_t stream) {
+  return rvb_div_grad(RVB_DIV_BCE, p, y, grad, n, (double)(n > 0 ? n : 1), gscale_dev, gscale, stream);
 }
 
 extern "C" int rvb_bce_mean(const float* p, const float* y, int64_t n, float* loss, float* workspace,
                             rvb_stream_t stream) {
-  RVB_REQUIRE(p && y && loss && workspace, "rvb_bce_mean: null pointer");
   RVB_REQUIRE(n > 0, "rvb_bce_mean: empty input (the reference returns NaN for an empty mean)");
-  unsigned grid = flat_grid(n, 16);
-  if (grid > (unsigned)kBceMaxBlocks) grid = kBceMaxBlocks;
-  const int vec = aligned16(p) && aligned16(y);
-  bce_mean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, y, n, loss, workspace, vec);
+  return rvb_div_mean(RVB_DIV_BCE, p, y, n, (double)n, loss, workspace, stream);
+}
+
+extern "C" int rvb_vat_perturb_binwise(const float* x, const float* d, float* x_adv, int64_t n, float xi, int do_clamp,
+                                       rvb_stream_t stream) {
+  RVB_REQUIRE(x && d && x_adv, "rvb_vat_perturb_binwise: null pointer");
+  RVB_REQUIRE(n >= 0, "rvb_vat_perturb_binwise: negative size");
+  if (n == 0) return RVB_OK;
+  vat_perturb_binwise_kernel<<<flat_grid(n, 4), 256, 0, (cudaStream_t)stream>>>(x, d, x_adv, n, xi, do_clamp);
   count_launch();
-  return check_launch("bce_mean_kernel");
+  return check_launch("vat_perturb_binwise_kernel");
+}
+
+extern "C" int rvb_vat_finalize_binwise(const float* g, const float* d, const float* x, float* r_adv, float* x_adv,
+                                        float* d_hat, int64_t n, float xi, float eps, float scale, int do_clamp,
+                                        int32_t* status_flag, rvb_stream_t stream) {
+  RVB_REQUIRE(d && x && r_adv && x_adv && d_hat, "rvb_vat_finalize_binwise: null pointer");
+  RVB_REQUIRE(n >= 0, "rvb_vat_finalize_binwise: negative size");
+  if (n == 0) return RVB_OK;
+  vat_finalize_binwise_kernel<<<flat_grid(n, 4), 256, 0, (cudaStream_t)stream>>>(g, d, x, r_adv, x_adv, d_hat, n, xi, eps,
+                                                                               scale, do_clamp, g != nullptr, status_flag);
+  count_launch();
+  return check_launch("vat_finalize_binwise_kernel");
 }

@@ -25,7 +25,9 @@ _VAT_BINDINGS = {
     "model.self_attention_VAT": {"stepwise_VAT": VAT.stepwise_VAT, "UNet_VAT": VAT.UNet_VAT,
                                  "onset_frame_VAT": VAT.onset_frame_VAT},
     "model.UNet_onset": {"UNet_VAT": VAT.UNet_VAT_onset},
-    "model.onset_frame_VAT": {"stepwise_VAT": VAT.stepwise_VAT_onf},
+    "model.onset_frame_VAT": {"stepwise_VAT": VAT.stepwise_VAT_onf,
+                              "stepwise_VAT_frame_stack": VAT.stepwise_VAT_frame_stack},
+    "model.Segmentation": {"Seg_VAT": VAT.Seg_VAT},
 }
 
 

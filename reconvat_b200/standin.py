@@ -41,13 +41,15 @@ class StandInTranscriber(nn.Module):
     'unet_onset'  transcriber(x) -> (frame, onset, None)     UNet_onset.UNet_Onset
     'stepwise'    model(x)       -> (frame, None)            self_attention_VAT.stepwise_VAT / VAT.py
     'onf'         model(x)       -> (onset, activation, frame)   onset_frame_VAT (x is 3-D)
+    'stack'       model(x)       -> (activation, frame)      onset_frame_VAT.stepwise_VAT_frame_stack
+    'seg'         model(x)       -> frame                    Segmentation.Seg_VAT (the posterior itself)
     """
 
     def __init__(self, convention="unet", n_in=229, n_out=88, seed=0, gain=6.0):
         super().__init__()
         self.convention = convention
         self.frame = _Head(n_in, n_out, 100 + seed, gain)
-        self.onset = _Head(n_in, n_out, 200 + seed, gain) if convention in ("unet_onset", "onf") else None
+        self.onset = _Head(n_in, n_out, 200 + seed, gain) if convention in ("unet_onset", "onf", "stack") else None
         self.captured_grads = None            # set to a list to record dL/dx_adv of grad-requiring inputs
         self.transcriber = self._transcriber if convention in ("unet", "unet_onset") else None
 
@@ -69,6 +71,11 @@ class StandInTranscriber(nn.Module):
             f = self.frame(x)
             o = self.onset(x)
             return o, 0.5 * (o + f), f
+        if self.convention == "stack":
+            f = self.frame(x)
+            return 0.5 * (self.onset(x) + f), f
+        if self.convention == "seg":
+            return self.frame(x)
         raise RuntimeError("call .transcriber(x) for convention %r" % self.convention)
 
 

@@ -46,7 +46,8 @@ def test_ctypes_table_mirrors_header(lib):
     decls = _declared()
     plumbing = {"rvb_abi_version", "rvb_last_error", "rvb_launch_count"}
     assert set(lib.SIGNATURES) == set(decls) - plumbing
-    kinds = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_int64: "int64_t", ctypes.c_float: "float"}
+    kinds = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_int64: "int64_t", ctypes.c_float: "float",
+             ctypes.c_double: "double"}
     for name, argtypes in lib.SIGNATURES.items():
         args = decls[name]
         assert len(args) == len(argtypes), name
@@ -59,6 +60,8 @@ def test_ctypes_table_mirrors_header(lib):
                 assert kinds[t] == "int", (name, a)
             elif a.startswith("float"):
                 assert kinds[t] == "float", (name, a)
+            elif a.startswith("double"):
+                assert kinds[t] == "double", (name, a)
             else:
                 raise AssertionError("unparsed argument %r of %s" % (a, name))
     # no torch / C++ types, only plain pointers and sizes in the declarations (comments stripped)

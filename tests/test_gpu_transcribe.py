@@ -39,6 +39,31 @@ def test_time_sharded_file_equals_single_pass_and_oracle():
         assert torch.equal(torch.cat(parts, dim=2), whole)
 
 
+def test_one_hour_file_over_8_ranks_is_bit_identical():
+    """BASELINE config 5 at full size: 3 600 s = 57.6 M samples = 112 500 frames, time-sharded over 8 ranks."""
+    import reconvat_b200 as R
+    from reconvat_b200 import synth, transcribe
+    dev = torch.device("cuda:0")
+    L = 3600 * 16000
+    a16 = torch.from_numpy(np.tile(synth.music_int16(16000 * 60, 77), 60)[:L])
+    a16[L // 2:] //= 4
+    mel = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    whole, span = transcribe.whole_file_frontend(mel, a16, 0, 1)
+    assert span == (0, 112500) and whole.shape == (1, 1, 112500, 229)
+    assert float(whole.min()) == 0.0 and float(whole.max()) == 1.0        # exact extrema over the whole file
+    keys = []
+    for r in range(8):
+        transcribe.whole_file_frontend(mel, a16, r, 8, reduce_keys=lambda k: (keys.append(k.clone()), k)[1])
+    wide = torch.stack([k.to(torch.int64) & 0xFFFFFFFF for k in keys]).max(0).values
+    glob = torch.where(wide >= 2 ** 31, wide - 2 ** 32, wide).to(torch.int32)
+    f = 0
+    for r in range(8):
+        s, (f0, f1) = transcribe.whole_file_frontend(mel, a16, r, 8, reduce_keys=lambda k: glob)
+        assert f0 == f and torch.equal(s, whole[:, :, f0:f1])
+        f = f1
+    assert f == 112500
+
+
 def test_padded_slice_matches_reflection_pad():
     from reconvat_b200 import transcribe
     a = torch.arange(50, dtype=torch.float32)

@@ -127,6 +127,14 @@ FLAVOURS = {
     "stepwise_vatpy": ("stepwise_VAT_vatpy", dict(epsilon=2, n_power=1), "stepwise", 2.0, 1.0, 0),
     "unet_onset": ("UNet_VAT_onset", dict(epsilon=2, n_power=1, KL_Div=False), "unet_onset", 2.0, 1e10, 1),
     "onf": ("stepwise_VAT_onf", dict(epsilon=0.1, n_power=1, KL_Div=False), "onf", 0.1, 1e10, 1),
+    # flavours no shipped script selects
+    "unet_kl": ("UNet_VAT", dict(epsilon=2, n_power=1, KL_Div=True), "unet", 2.0, 1e10, 1),
+    "stepwise_sa_kl": ("stepwise_VAT", dict(epsilon=2, n_power=1, KL_Div=True), "stepwise", 2.0, 1.0, 1),
+    "onf_kl": ("stepwise_VAT_onf", dict(epsilon=0.1, n_power=1, KL_Div=True), "onf", 0.1, 1e10, 1),
+    "seg": ("Seg_VAT", dict(epsilon=2, n_power=1, KL_Div=False), "seg", 2.0, 1e10, 1),
+    "stack_activation": ("stepwise_VAT_frame_stack", dict(epsilon=2, n_power=1, VAT_mode="activation"), "stack", 2.0, 1e20, 1),
+    "stack_frame": ("stepwise_VAT_frame_stack", dict(epsilon=2, n_power=1, VAT_mode="frame"), "stack", 2.0, 1e20, 1),
+    "stack_all": ("stepwise_VAT_frame_stack", dict(epsilon=2, n_power=1, VAT_mode="all"), "stack", 2.0, 1e20, 1),
 }
 
 
@@ -198,6 +206,69 @@ def test_vat_modules_match_reference_golden(R, dev, golden, base, monkeypatch):
     assert not r_adv.requires_grad and r_adv.shape == x.shape
 
 
+@pytest.mark.parametrize("xi", [1e-6, 0.1])
+def test_binwise_kernels_reproduce_the_reference_bit_for_bit(R, dev, golden, xi):
+    """binwise=True: the reference's d.grad is fp32 cancellation noise (oracle/vat.py:power_grad_binwise_sequence);
+    the kernel executes the same IEEE op sequence, so with the reference's (x, d, g) the outputs are IDENTICAL."""
+    g = golden["vat_flavours"]
+    tag = "stepwise_sa_binwise" + ("" if xi == 1e-6 else "_xi01")
+    x = torch.from_numpy(g["x"]).to(dev)
+    d = torch.from_numpy(g[tag + "_d"]).to(dev)
+    gg = torch.from_numpy(g[tag + "_g"][0]).to(dev).contiguous()
+    r = torch.empty_like(x); xa = torch.empty_like(x); dh = torch.empty_like(x)
+    flag = torch.zeros((), dtype=torch.int32, device=dev)
+    R._lib.call("rvb_vat_finalize_binwise", gg.data_ptr(), d.data_ptr(), x.data_ptr(), r.data_ptr(), xa.data_ptr(),
+                dh.data_ptr(), x.numel(), xi, 2.0, 1.0, 1, flag.data_ptr())
+    assert flag.item() == 0
+    assert torch.equal(r.cpu(), torch.from_numpy(g[tag + "_r_adv"]))
+    assert torch.equal(dh.cpu(), torch.from_numpy(g[tag + "_dhat"]))
+    x1 = torch.empty_like(x)
+    R._lib.call("rvb_vat_perturb_binwise", x.data_ptr(), d.data_ptr(), x1.data_ptr(), x.numel(), xi, 1)
+    want = (x.cpu() + xi * (d.cpu() / (d.cpu().abs() + 1e-8))).clamp(0, 1)
+    assert torch.equal(x1.cpu(), want)
+
+
+def test_binwise_module_and_n_power_zero(R, dev, golden):
+    """Whole module with binwise=True on the GPU network.  g differs from the CPU run at rounding level and the
+    direction amplifies that noise, so only what is well defined is compared: the loss, shapes, |d_hat| <= 1."""
+    from reconvat_b200.standin import StandInTranscriber
+    g = golden["vat_flavours"]
+    x = torch.from_numpy(g["x"]).to(dev)
+    model = StandInTranscriber("stepwise", n_in=229, n_out=int(g["P"]), seed=3).to(dev)
+    vat = R.VAT.stepwise_VAT(0.1, 2, 1, False, binwise=True, strict=True)
+    loss, r_adv, d_hat = vat(model, x)
+    assert r_adv.shape == x.shape and float(d_hat.abs().max()) <= 1.0 and torch.allclose(r_adv, 2.0 * d_hat)
+    assert np.isfinite(loss.item())
+    loss.backward()
+    assert model.frame.weight.grad is not None
+    v0 = R.VAT.stepwise_VAT(0.1, 2, 0, False, binwise=True)
+    torch.manual_seed(5)
+    d = torch.randn_like(x)
+    torch.manual_seed(5)
+    _, r0, dh0 = v0(model, x)
+    assert torch.equal(dh0, d / (d.abs() + 1e-8)) and torch.equal(r0, 2.0 * dh0)
+
+
+def test_divergence_kernels_match_torch(R, dev):
+    """rvb_div_mean / rvb_div_grad for the binary KL (batchmean) and MSE against the reference's torch expressions."""
+    import torch.nn.functional as F
+    from oracle import vat as OV
+    from reconvat_b200 import VAT
+    torch.manual_seed(6)
+    p = torch.sigmoid(torch.randn(3, 40, 88) * 4)
+    y = torch.sigmoid(torch.randn(3, 40, 88) * 4)
+    p[0, 0, :6] = torch.tensor([0.0, 1.0, 1e-4, 0.9999, 5e-5, 0.99995])      # on and beyond the clamp edges
+    for ours, ref in ((VAT.binary_kl_div, OV.binary_kl_div), (VAT.mse_mean, F.mse_loss)):
+        pr = p.clone().requires_grad_(True)
+        lr = ref(pr, y)
+        lr.backward()
+        pd = p.to(dev).requires_grad_(True)
+        lo = ours(pd, y.to(dev))
+        (lo * 2.0).backward()
+        assert abs(lo.item() - lr.item()) <= 2e-6 * abs(lr.item())
+        assert float((pd.grad.cpu() - 2.0 * pr.grad).abs().max() / pr.grad.abs().max()) < 1e-5
+
+
 @pytest.mark.parametrize("xi", [0.1])
 def test_vat_full_size_against_oracle(R, dev, xi):
     """B=4 x 640 x 229 (one BASELINE config-2 half batch): module vs oracle with the same d and network."""
@@ -267,7 +338,11 @@ def test_vat_rejects_what_it_does_not_implement(R, dev):
     with pytest.raises(NotImplementedError):
         R.VAT.UNet_VAT(1e-6, 2.0, 2, False)
     with pytest.raises(NotImplementedError):
-        R.VAT.UNet_VAT(1e-6, 2.0, 1, True)
+        R.VAT.UNet_VAT_onset(1e-6, 2.0, 1, True)      # the reference raises NameError there (UNet_onset.py:133)
+    with pytest.raises(NotImplementedError):
+        R.VAT.Seg_VAT(1e-6, 2.0, 1, True)             # ... and there (Segmentation.py:55)
+    with pytest.raises(ValueError):
+        R.VAT.stepwise_VAT_frame_stack(1e-6, 2.0, 1, "onset")
     vat = R.VAT.UNet_VAT(1e-6, 2.0, 1, False)
     with pytest.raises(R._lib.RvbError):
         vat(None, torch.zeros(1, 1, 4, 229))   # CPU tensor: no fallback

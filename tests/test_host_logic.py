@@ -248,9 +248,15 @@ def test_vat_constructor_signatures_mirror_the_reference():
     assert V.UNet_VAT_onset(1e-6, 2, 1, False)._dict_loss == ("frame", "onset")
     assert V.stepwise_VAT_onf(1e-6, 0.1, 1, False)._heads == (2,)
     assert V.onset_frame_VAT(1e-6, 2, 1)._n_returns == 2
-    for bad in (dict(n_power=2, KL_Div=False), dict(n_power=1, KL_Div=True)):
+    with pytest.raises(NotImplementedError):
+        V.UNet_VAT(1e-6, 2, n_power=2, KL_Div=False)          # the reference fails for n_power > 1
+    assert V.UNet_VAT(1e-6, 2, 1, True).KL_Div is True        # binary_kl_div flavour
+    assert V.stepwise_VAT(1e-6, 2, 1, False, binwise=True).binwise is True
+    assert V.Seg_VAT(1e-6, 2, 1, False, reconstruction=False)._heads == (None,)
+    assert V.stepwise_VAT_frame_stack(1e-6, 2, 1, "all")._scale == 1e20
+    for cls in (V.UNet_VAT_onset, V.Seg_VAT):                 # the reference raises NameError in these two
         with pytest.raises(NotImplementedError):
-            V.UNet_VAT(1e-6, 2, **bad)
+            cls(1e-6, 2, 1, True)
 
 
 def test_injected_transcriber_drives_the_reference_op_sequence_on_cpu():
