@@ -214,6 +214,12 @@ int rvb_minmax(const float* x, int n_seg, int64_t n_per_seg, uint32_t* minmax, r
 int rvb_normalise(const float* x, float* y, int n_seg, int64_t n_per_seg, const uint32_t* minmax,
                   rvb_stream_t stream);
 
+/*
+ * K3f  Normalization('framewise') (model/utils.py:85-92): x, y are [n_seg][n_bins][n_frames]; per (segment, frame)
+ * min / max over the bins, y = (x - min) / (max - min), NaN -> 0.  In place when y == x.
+ */
+int rvb_normalise_framewise(const float* x, float* y, int n_seg, int n_bins, int n_frames, rvb_stream_t stream);
+
 /* ------------------------------------------------------------------ VAT loop */
 
 /*

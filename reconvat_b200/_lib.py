@@ -36,6 +36,7 @@ SIGNATURES = {
     "rvb_mel_project": [_c_p, _i32, _i32, _i32, _c_p, _c_p, _c_p, _i32, _i32, _f32, _i32, _c_p, _c_p, _c_p],
     "rvb_minmax": [_c_p, _i32, _i64, _c_p, _c_p],
     "rvb_normalise": [_c_p, _c_p, _i32, _i64, _c_p, _c_p],
+    "rvb_normalise_framewise": [_c_p, _c_p, _i32, _i32, _i32, _c_p],
     "rvb_vat_perturb": [_c_p, _c_p, _c_p, _i64, _i32, _f32, _i32, _c_p],
     "rvb_bce_grad": [_c_p, _c_p, _c_p, _i64, _c_p, _f32, _c_p],
     "rvb_vat_finalize": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i64, _i32, _f32, _f32, _f32, _i32, _c_p, _c_p],

@@ -543,6 +543,31 @@ normalise_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n_p
   }
 }
 
+// ------------------------------------------------------------------ K3f: Normalization('framewise')
+// model/utils.py:85-92: per (segment, frame) min / max over the bins axis of x[b][bin][frame], (x - min)/(max - min),
+// NaN -> 0 (a constant frame gives 0/0).  Thread <-> frame (lanes are consecutive frames: 128-byte rows), two
+// passes over the bins; torch.max / torch.min propagate NaN, and so does the comparison chain here.
+__global__ void __launch_bounds__(256)
+normalise_framewise_kernel(const float* __restrict__ x, float* __restrict__ y, int n_bins, int n_frames) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_frames) return;
+  const float* p = x + (int64_t)b * n_bins * n_frames + t;
+  float* q = y + (int64_t)b * n_bins * n_frames + t;
+  float mx = -INFINITY, mn = INFINITY;
+  bool nan = false;
+  for (int m = 0; m < n_bins; ++m) {
+    const float v = __ldg(p + (int64_t)m * n_frames);
+    mx = fmaxf(mx, v); mn = fminf(mn, v); nan |= isnan(v);
+  }
+  if (nan) mx = mn = __int_as_float(0x7fc00000);
+  const float den = mx - mn;
+  for (int m = 0; m < n_bins; ++m) {
+    const float o = (__ldg(p + (int64_t)m * n_frames) - mn) / den;
+    q[(int64_t)m * n_frames] = isnan(o) ? 0.f : o;                      // output[torch.isnan(output)] = 0
+  }
+}
+
 }  // namespace rvb
 
 using namespace rvb;
@@ -736,4 +761,14 @@ extern "C" int rvb_normalise(const float* x, float* y, int n_seg, int64_t n_per_
   normalise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, n_per_seg, minmax, vec);
   count_launch();
   return check_launch("normalise_kernel");
+}
+
+extern "C" int rvb_normalise_framewise(const float* x, float* y, int n_seg, int n_bins, int n_frames,
+                                       rvb_stream_t stream) {
+  RVB_REQUIRE(x && y, "rvb_normalise_framewise: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_bins > 0 && n_frames > 0 && n_seg <= 65535, "rvb_normalise_framewise: bad shape");
+  dim3 grid((unsigned)((n_frames + 255) / 256), (unsigned)n_seg);
+  normalise_framewise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, n_bins, n_frames);
+  count_launch();
+  return check_launch("normalise_framewise_kernel");
 }

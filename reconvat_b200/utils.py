@@ -1,6 +1,7 @@
-"""Drop-in for ``model.utils.Normalization`` (model/utils.py:82-106), 'imagewise' mode on the device
-kernels: per-sample min and max over all (bins x frames) values, then (x - min) / (max - min).
-No epsilon, like the reference: a constant image becomes NaN."""
+"""Drop-in for ``model.utils.Normalization`` (model/utils.py:82-106) on the device kernels.  'imagewise' (what every
+shipped script selects): per-sample min and max over all (bins x frames) values, then (x - min) / (max - min); no
+epsilon, like the reference: a constant image becomes NaN.  'framewise': the same per (sample, frame) over the bins,
+with NaN replaced by 0."""
 import torch
 
 from . import _lib
@@ -11,11 +12,7 @@ class Normalization():
         if mode == 'imagewise':
             self.normalize = _imagewise
         elif mode == 'framewise':
-            # model/utils.py:85-92; not selected by any shipped script (all pass mode='imagewise',
-            # train_UNet_VAT.py:19) -> outside the accelerated path, refuse rather than emulate.
-            def normalize(x):
-                raise NotImplementedError("reconvat_b200.Normalization: only mode='imagewise' is accelerated")
-            self.normalize = normalize
+            self.normalize = _framewise
         else:
             print(f'please choose the correct mode')
         self.mode = mode
@@ -24,13 +21,24 @@ class Normalization():
         return self.normalize(x)
 
 
-def _imagewise(x):
+def _check(x, mode):
     if not x.is_cuda or x.dtype != torch.float32:
         raise _lib.RvbError("reconvat_b200.Normalization needs a CUDA float32 tensor (got %s, %s); "
                             "there is no CPU path" % (x.device, x.dtype))
     if x.dim() != 3:
-        raise ValueError("Normalization('imagewise') expects (batch, bins, frames)")
-    xc = x.contiguous()
+        raise ValueError("Normalization(%r) expects (batch, bins, frames)" % mode)
+    return x.contiguous()
+
+
+def _framewise(x):
+    xc = _check(x, 'framewise')
+    out = torch.empty_like(xc)
+    _lib.call("rvb_normalise_framewise", xc.data_ptr(), out.data_ptr(), xc.shape[0], xc.shape[1], xc.shape[2])
+    return out
+
+
+def _imagewise(x):
+    xc = _check(x, 'imagewise')
     B = xc.shape[0]
     n = xc.shape[1] * xc.shape[2]
     minmax = torch.empty((B, 2), dtype=torch.int32, device=x.device)

@@ -322,6 +322,13 @@ def test_normalization_golden_bit_exact(R, dev, golden):
     ok = ~np.isnan(g["imagewise"])
     assert np.array_equal(np.isnan(out), ~ok)                  # constant image -> NaN (no epsilon)
     assert np.array_equal(out[ok], g["imagewise"][ok])
+    # framewise (model/utils.py:85-92): per-frame extrema over the bins, NaN -> 0; bit-exact too
+    fw = R.utils.Normalization("framewise").transform(torch.from_numpy(g["x"]).to(dev)).cpu().numpy()
+    assert np.array_equal(fw, g["framewise"])
+    xn = torch.from_numpy(g["x"]).clone()
+    xn[0, 3, 1] = float("nan")                                 # a NaN poisons its frame's extrema -> the frame becomes 0
+    fwn = R.utils.Normalization("framewise").transform(xn.to(dev)).cpu()
+    assert torch.all(fwn[0, :, 1] == 0) and torch.equal(fwn[1:], torch.from_numpy(g["framewise"])[1:])
 
 
 @pytest.mark.parametrize("B", [1, 3, 8])
