@@ -36,6 +36,8 @@ HBM_BYTES_PER_SEG = {
     "rvb_normalise": 2 * N4,
     "rvb_vat_perturb": 3 * N4,
     "rvb_bce_grad": 3 * P4,
+    "rvb_div_grad": 3 * P4,                                # what the VAT modules call (kind = BCE here)
+    "rvb_div_mean": 2 * P4,
     "rvb_vat_finalize": 6 * N4,
     "rvb_bce_mean": 2 * P4,
 }

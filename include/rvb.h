@@ -162,8 +162,9 @@ int rvb_stft_bin(const float* sig_hi, const float* sig_lo, int n_seg, int rows_p
  * power_p) spectrum never leaves the SM.  Replaces model/Spectrogram.py:219-231, :458 and `torch.matmul(self.mel_basis,
  * spec)` (:460) for filterbanks in which every bin feeds at most two adjacent bands (all triangular banks).
  *   spectrum   RVB_EPI_POWER | RVB_EPI_MAGNITUDE | RVB_EPI_POWER_P
- *   mel_tab    [n_bins_pad][4] float: (w0, w1, band0 as int32 bits, 0): bin k adds w0 P[k] to band band0[k] and
- *              w1 P[k] to band band0[k]+1; band0 non-decreasing in k; 16-byte aligned
+ *   mel_tab    HOST pointer, [n_bins_pad][4] float: (w0, w1, band0 as int32 bits, 0): bin k adds w0 P[k] to band
+ *              band0[k] and w1 P[k] to band band0[k]+1; band0 non-decreasing in k; n_bins_pad <= 1024.  The table is
+ *              read during the call and travels as a 16 KB kernel parameter (constant bank, no shared-memory traffic)
  *   mel_out    [n_seg][n_mels][n_frames] (what MelSpectrogram.forward returns); zeroed by the call, then accumulated
  *              with RED.ADD -- at most two partial sums per element when no band straddles more than two 128-bin tiles
  * K2m  rvb_logmel_minmax: per-segment (min, max) keys of log(mel + log_offset) (model/self_attention_VAT.py:1102,

@@ -178,7 +178,7 @@ class STFT(nn.Module):
                     _lib.call("rvb_stft_mel_folded_f16", planes[0].data_ptr(), planes[1].data_ptr(),
                               row_inv.data_ptr(), B, n_frames, self.n_fft, fd["basis_hi"].data_ptr(),
                               fd["basis_lo"].data_ptr(), fd["scale_inv"], fd["n_bins_pad"], p0_ptr, fd["w0"], epilogue,
-                              float(power), mel_tab.data_ptr(), n_out_bins, _lib.ptr(out))
+                              float(power), mel_tab.ctypes.data, n_out_bins, _lib.ptr(out))
                     return out, n_frames
                 _lib.call("rvb_stft_gemm_folded_f16", planes[0].data_ptr(), planes[1].data_ptr(), row_inv.data_ptr(),
                           B, n_frames, self.n_fft, fd["basis_hi"].data_ptr(), fd["basis_lo"].data_ptr(),
@@ -314,7 +314,8 @@ class MelSpectrogram(nn.Module):
                 mb = self.mel_basis.detach().cpu().numpy()
                 if not any(np.any(mb[:, k] != 0) for k in fd["leftover"]):    # e.g. the Nyquist bin carries no weight
                     tab = basis.mel_epilogue_table(mb, fd["n_bins_pad"])
-            self._fused = (torch.from_numpy(tab).to(self.mel_basis.device) if tab is not None else None,)
+            # host-side table: the C ABI reads it at launch time and passes it as a kernel parameter
+            self._fused = (np.ascontiguousarray(tab) if tab is not None and tab.shape[0] <= 1024 else None,)
             self._fused_key = key
         return self._fused[0]
 

@@ -18,7 +18,9 @@
 #include <cudaTypedefs.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <map>
+#include <type_traits>
 #include <mutex>
 #include <tuple>
 
@@ -329,7 +331,7 @@ constexpr int F_BLOCK_N = 128;
 constexpr int F_STAGES = 3;
 constexpr int F_TILE_BYTES = 128 * BLOCK_K * 4;         // 16 KB (A and B tiles are both 128 rows)
 constexpr int F_STAGE_BYTES = 4 * F_TILE_BYTES;         // 64 KB
-constexpr int F_SMEM_BYTES = F_STAGES * F_STAGE_BYTES + BAR_BYTES + 2 * 128 * 16 /* Mel table slots */ + 1024;
+constexpr int F_SMEM_BYTES = F_STAGES * F_STAGE_BYTES + BAR_BYTES + 1024;
 
 struct FoldParams {
   int n_frames;               // frames per segment (T)
@@ -343,8 +345,7 @@ struct FoldParams {
   const float* row_scale_inv;   // fp16 operands only: per-frame 2^-s_row
   float basis_scale_inv;        // fp16 operands only: 2^-s_basis
   int dbg;                      // RVB_DBG experiments (timing only, results invalid): 1 alt acc, 2 no stores, 4 no TMA
-  // fused Mel projection (K1m): when mel_tab != nullptr the epilogue does not store the spectrum at all
-  const float4* mel_tab;        // [n_bins_pad] (w0, w1, band0 as int bits, -): bin k adds w0 P to band0, w1 P to band0+1
+  // fused Mel projection (K1m, kernels instantiated with a MelTable): the epilogue does not store the spectrum
   float* mel_out;               // [n_seg][n_mels][n_frames], zeroed before the launch, accumulated with RED.ADD
   int n_mels;
 };
@@ -369,20 +370,52 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 struct MelAcc {
   int b0;
   float acc0, acc1;
+  float* cur;        // &mel[b][b0][t]: advanced by one band row per rotation (no 64-bit multiply per flush)
 };
 
 // Eight consecutive bins of one frame into the rotating band accumulators.
-template <int kEpi>
+// kFast (power spectrum, no rank-1 p0 term): the power-of-two operand scale is pulled out of the loop -- the
+// accumulators hold sum w (re^2 + im^2) in scaled units and a finished band is multiplied by scale^2 once.  Scaling by
+// a power of two commutes with every rounding, so the result is bit-identical to scaling each value.
+// The Mel table travels as a 16 KB KERNEL PARAMETER (constant bank): the per-bin lookups are uniform constant
+// loads that never touch shared memory -- the tensor pipe reads smem at its full 128 B/clk (64 wavefronts per
+// 64-cycle MMA), so every LDS in the epilogue comes straight out of the contraction's operand bandwidth (with the
+// table staged in smem the fused kernel was 218 us, profiles/r01e).
+constexpr int kMelTableBins = 1024;
+struct MelTable {
+  float4 e[kMelTableBins];      // (w0, w1, band0 as int bits, -): bin k adds w0 P to band0, w1 P to band0 + 1
+};
+struct NoTable {
+  int unused;
+};
+
+// (Tried out of line to shrink the loop: the call spills the accumulator registers around it, 304 us.)
+__device__ __forceinline__ void mel_flush(float* __restrict__ dst, int band, int n_mels, float v, bool f_ok) {
+  if (f_ok && v != 0.f && band < n_mels) atomicAdd(dst, v);
+}
+
+template <int kEpi, bool kFast>
 __device__ __forceinline__ void mel_bins8(const FoldParams& p, const uint32_t (&re)[8], const uint32_t (&im)[8],
                                           const float4* tab, float* __restrict__ col, bool f_ok, float scale,
                                           float re_add, MelAcc& a) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float4 e = tab[i];                                       // same address in every lane: LDS broadcast
-    const float v = stft_value_t<kEpi>(p.power, fmaf(__uint_as_float(re[i]), scale, re_add), __uint_as_float(im[i]) * scale);
+    const float4 e = tab[i];                                       // constant bank, same index in every lane
+    float v;
+    if constexpr (kFast) {
+      const float r = __uint_as_float(re[i]), m = __uint_as_float(im[i]);
+      v = fmaf(r, r, m * m);
+    } else {
+      v = stft_value_t<kEpi>(p.power, fmaf(__uint_as_float(re[i]), scale, re_add), __uint_as_float(im[i]) * scale);
+    }
     const int band = __float_as_int(e.z);
-    while (a.b0 < band) {                                          // warp-uniform
-      if (f_ok && a.b0 < p.n_mels && a.acc0 != 0.f && !(p.dbg & 8)) atomicAdd(col + (int64_t)a.b0 * p.n_frames, a.acc0);
+    // warp-uniform; NOT unrolled: nvcc otherwise emits four copies of the flush plus remainder logic per bin
+    // (3 200 instructions per loop trip), which no longer fit the instruction cache the epilogue shares with the
+    // MMA-issuing thread
+#pragma unroll 1
+    while (a.b0 < band) {
+      mel_flush(a.cur, a.b0, p.n_mels, kFast ? a.acc0 * (scale * scale) : a.acc0, f_ok);
+      a.cur += p.n_frames;
       a.acc0 = a.acc1;
       a.acc1 = 0.f;
       ++a.b0;
@@ -396,10 +429,11 @@ __device__ __forceinline__ void mel_bins8(const FoldParams& p, const uint32_t (&
 // the next eight is in flight while these are folded in): one epilogue warp runs alone on its scheduler, so
 // straight-line code that overflows the instruction cache costs ~10 cycles per instruction, and a TMEM load issued
 // and awaited in the same trip costs its full latency 32 times per tile (profiles/r01d).
-template <int kEpi>
-__device__ __forceinline__ void mel_unit(const FoldParams& p, uint32_t taddr, const float4* tab /* smem, 128 bins */,
+template <int kEpi, bool kFast>
+__device__ __forceinline__ void mel_unit(const FoldParams& p, uint32_t taddr, const float4* tab /* this tile's 128 bins */,
                                          float* __restrict__ col, bool f_ok, float scale, float re_add) {
-  MelAcc a{__float_as_int(tab[0].z), 0.f, 0.f};
+  MelAcc a{__float_as_int(tab[0].z), 0.f, 0.f, nullptr};
+  a.cur = col + (int64_t)a.b0 * p.n_frames;
   uint32_t re0[8], im0[8], re1[8], im1[8];
   tmem_ld8(taddr, re0);
   tmem_ld8(taddr + 128, im0);
@@ -408,38 +442,30 @@ __device__ __forceinline__ void mel_unit(const FoldParams& p, uint32_t taddr, co
     tmem_ld_wait();                                                // set 0 (bins 8j .. 8j+7) has landed
     tmem_ld8(taddr + 8 * (j + 1), re1);
     tmem_ld8(taddr + 128 + 8 * (j + 1), im1);
-    mel_bins8<kEpi>(p, re0, im0, tab + 8 * j, col, f_ok, scale, re_add, a);
+    if (!(p.dbg & 32) || re0[0] == 0x7fc12345u) mel_bins8<kEpi, kFast>(p, re0, im0, tab + 8 * j, col, f_ok, scale, re_add, a);
     tmem_ld_wait();                                                // set 1
     if (j + 2 < 16) {
       tmem_ld8(taddr + 8 * (j + 2), re0);
       tmem_ld8(taddr + 128 + 8 * (j + 2), im0);
     }
-    mel_bins8<kEpi>(p, re1, im1, tab + 8 * (j + 1), col, f_ok, scale, re_add, a);
+    if (!(p.dbg & 32) || re1[0] == 0x7fc12345u) mel_bins8<kEpi, kFast>(p, re1, im1, tab + 8 * (j + 1), col, f_ok, scale, re_add, a);
   }
-  if (f_ok) {
-    if (a.b0 < p.n_mels && a.acc0 != 0.f) atomicAdd(col + (int64_t)a.b0 * p.n_frames, a.acc0);
-    if (a.b0 + 1 < p.n_mels && a.acc1 != 0.f) atomicAdd(col + (int64_t)(a.b0 + 1) * p.n_frames, a.acc1);
-  }
+  const float s2 = kFast ? scale * scale : 1.f;
+  mel_flush(a.cur, a.b0, p.n_mels, a.acc0 * s2, f_ok);
+  mel_flush(a.cur + p.n_frames, a.b0 + 1, p.n_mels, a.acc1 * s2, f_ok);
 }
 
-// Mel mode, before waiting for the accumulator: the four epilogue warps copy the tile's 128 table rows (2 KB) into
-// their smem slot (one 16-byte load per thread; a global load per bin would cost an L2 round trip per loop trip).
-// `slot` alternates with the accumulator stage; named barrier 1 orders the copy against every warp's reads, and a
-// slot is rewritten two units later, after all four warps have passed the next unit's barrier.
-constexpr int MEL_TAB_SMEM_BYTES = 2 * 128 * 16;
-__device__ __forceinline__ void mel_stage_table(const FoldParams& p, float4* tab_s, int n_tile, int row, int bar_id) {
-  tab_s[row] = __ldg(p.mel_tab + n_tile * 128 + row);
-  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-}
-
-__device__ __forceinline__ void fold_epilogue_unit(const FoldParams& p, uint32_t taddr, const float4* tab, bool f_ok,
+template <typename TabT>
+__device__ __forceinline__ void fold_epilogue_unit(const FoldParams& p, const TabT& tab, uint32_t taddr, bool f_ok,
                                                    int n_tile, int b, int t, float scale, float re0) {
-  if (p.mel_tab != nullptr) {
+  if constexpr (std::is_same<TabT, MelTable>::value) {
     if (p.dbg & 16) return;
+    const float4* tt = tab.e + n_tile * 128;
     float* col = p.mel_out + (int64_t)b * p.n_mels * p.n_frames + t;
-    if (p.epilogue == RVB_EPI_POWER) mel_unit<RVB_EPI_POWER>(p, taddr, tab, col, f_ok, scale, re0);
-    else if (p.epilogue == RVB_EPI_MAGNITUDE) mel_unit<RVB_EPI_MAGNITUDE>(p, taddr, tab, col, f_ok, scale, re0);
-    else mel_unit<RVB_EPI_POWER_P>(p, taddr, tab, col, f_ok, scale, re0);
+    if (p.epilogue == RVB_EPI_POWER && p.p0 == nullptr) mel_unit<RVB_EPI_POWER, true>(p, taddr, tt, col, f_ok, scale, 0.f);
+    else if (p.epilogue == RVB_EPI_POWER) mel_unit<RVB_EPI_POWER, false>(p, taddr, tt, col, f_ok, scale, re0);
+    else if (p.epilogue == RVB_EPI_MAGNITUDE) mel_unit<RVB_EPI_MAGNITUDE, false>(p, taddr, tt, col, f_ok, scale, re0);
+    else mel_unit<RVB_EPI_POWER_P, false>(p, taddr, tt, col, f_ok, scale, re0);
     return;
   }
 #pragma unroll 1
@@ -582,12 +608,10 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
       const int t = f_ok ? (int)(f - (int64_t)b * p.n_frames) : 0;
       const float re0 = (p.p0 != nullptr && f_ok) ? p.w0 * __ldg(p.p0 + f) : 0.f;
       const float scale = (kF16 && f_ok) ? __ldg(p.row_scale_inv + f) * p.basis_scale_inv : 1.f;
-      float4* tab_s = reinterpret_cast<float4*>(smem_raw + (bar_base - smem_u32(smem_raw)) + BAR_BYTES) + acc * 128;
-      if (p.mel_tab != nullptr) mel_stage_table(p, tab_s, n_tile, row, 1);
       mbar_wait(bar_tmem_full(acc), acc_phase, nullptr, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
-      fold_epilogue_unit(p, taddr, tab_s, f_ok, n_tile, b, t, scale, re0);
+      fold_epilogue_unit(p, NoTable{}, taddr, f_ok, n_tile, b, t, scale, re0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tmem_empty(acc));
@@ -621,7 +645,7 @@ constexpr int P_NUM_THREADS = 64 + 2 * 128;          // TMA warp, MMA warp, two 
 constexpr int P_A_BYTES = 128 * 128;                    // 128 frame rows x one 128-byte swizzle row
 constexpr int P_B_BYTES = 64 * 128;                     // this CTA's half of the 128 basis rows
 constexpr int P_STAGE_BYTES = 2 * P_A_BYTES + 2 * P_B_BYTES;     // A_hi A_lo B_hi B_lo = 48 KB
-constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + BAR_BYTES + 2 * 128 * 16 /* Mel table slots */ + 1024;
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + BAR_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -674,10 +698,11 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
+template <typename TabT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_NUM_THREADS, 1)
 stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                           const FoldParams p) {
+                           const FoldParams p, const __grid_constant__ TabT tab) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + P_STAGES * P_STAGE_BYTES;
@@ -726,7 +751,7 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
   const int n_units = p.m_tiles * p.n_tiles;      // m_tiles counts 256-frame pair tiles here
   const int kb_per_chain = p.half / kBlockK;
   const int num_kb = 2 * kb_per_chain;
-  const int unit0 = (int)cluster_id_x(), unit_step = (int)num_clusters_x();
+  const int unit0 = (int)(blockIdx.x >> 1), unit_step = (int)(gridDim.x >> 1);     // cluster id / count (cluster = 2 CTAs)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -793,7 +818,6 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
     const int row = quarter * 32 + lane;
     const uint32_t leader_tmem_empty = map_to_rank(bar_tmem_empty(group), 0);
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(group * ACC_COLS);
-    float4* tab_s = reinterpret_cast<float4*>(smem_raw + (bar_base - smem_u32(smem_raw)) + BAR_BYTES) + group * 128;
     uint32_t acc_phase = 0;
     for (int unit = unit0 + group * unit_step; unit < n_units; unit += 2 * unit_step) {
       const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
@@ -803,10 +827,9 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
       const int t = f_ok ? (int)(f - (int64_t)b * p.n_frames) : 0;
       const float re0 = (p.p0 != nullptr && f_ok) ? p.w0 * __ldg(p.p0 + f) : 0.f;
       const float scale = f_ok ? __ldg(p.row_scale_inv + f) * p.basis_scale_inv : 1.f;
-      if (p.mel_tab != nullptr) mel_stage_table(p, tab_s, n_tile, row, 1 + group);
       mbar_wait(bar_tmem_full(group), acc_phase, nullptr, 4);
       tc_fence_after();
-      fold_epilogue_unit(p, taddr, tab_s, f_ok, n_tile, b, t, scale, re0);
+      fold_epilogue_unit(p, tab, taddr, f_ok, n_tile, b, t, scale, re0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_tmem_empty);
@@ -989,7 +1012,8 @@ static int launch_folded(const char* who, const void* a_hi, const void* a_lo, co
   RVB_REQUIRE(!kF16 || row_scale_inv, "%s: null row_scale_inv", who);
   if (mel) {
     RVB_REQUIRE(mel->tab && mel->out && mel->n_mels > 0, "%s: bad Mel arguments", who);
-    RVB_REQUIRE((reinterpret_cast<uintptr_t>(mel->tab) & 15u) == 0, "%s: mel_tab must be 16-byte aligned", who);
+    RVB_REQUIRE(n_bins_pad <= kMelTableBins, "%s: the Mel table is a %d-bin kernel parameter, got n_bins_pad %d", who,
+                kMelTableBins, n_bins_pad);
     RVB_REQUIRE(epilogue == RVB_EPI_POWER || epilogue == RVB_EPI_MAGNITUDE || epilogue == RVB_EPI_POWER_P,
                 "%s: the Mel projection takes the power / magnitude / power_p spectrum, got %d", who, epilogue);
     RVB_CUDA(cudaMemsetAsync(mel->out, 0, sizeof(float) * (size_t)n_seg * mel->n_mels * n_frames, (cudaStream_t)stream));
@@ -1024,7 +1048,6 @@ static int launch_folded(const char* who, const void* a_hi, const void* a_lo, co
   p.power = power; p.w0 = w0; p.p0 = (w0 != 0.f) ? p0 : nullptr; p.out0 = out0;
   p.row_scale_inv = row_scale_inv; p.basis_scale_inv = basis_scale_inv;
   { const char* d = getenv("RVB_DBG"); p.dbg = d ? atoi(d) : 0; }
-  p.mel_tab = mel ? reinterpret_cast<const float4*>(mel->tab) : nullptr;
   p.mel_out = mel ? mel->out : nullptr;
   p.n_mels = mel ? mel->n_mels : 0;
 
@@ -1037,22 +1060,33 @@ static int launch_folded(const char* who, const void* a_hi, const void* a_lo, co
       p.m_tiles = (int)((m_rows + 255) / 256);
       static int max_clusters = 0;
       if (max_clusters == 0) {
-        RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+        RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_pair_kernel<NoTable>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+        RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_pair_kernel<MelTable>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
         cudaLaunchConfig_t qc = {};
         qc.gridDim = dim3(num_sms() & ~1u); qc.blockDim = dim3(P_NUM_THREADS); qc.dynamicSmemBytes = P_SMEM_BYTES;
         int nc = 0;
-        RVB_CUDA(cudaOccupancyMaxActiveClusters(&nc, stft_gemm_fold_pair_kernel, &qc));
+        RVB_CUDA(cudaOccupancyMaxActiveClusters(&nc, stft_gemm_fold_pair_kernel<MelTable>, &qc));
         RVB_REQUIRE(nc > 0, "%s: no CTA pair fits on this device", who);
         max_clusters = nc < num_sms() / 2 ? nc : num_sms() / 2;
       }
       const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
       const int n_clusters = (int)(n_units < max_clusters ? n_units : max_clusters);
-      stft_gemm_fold_pair_kernel<<<2 * n_clusters, P_NUM_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo,
-                                                                                                      tm_b_hi, tm_b_lo, p);
+      if (mel) {
+        // the table is read on the HOST here and travels in the launch's parameter buffer (a CUDA graph bakes it in)
+        static thread_local MelTable tab;
+        std::memset(&tab, 0, sizeof(tab));
+        std::memcpy(tab.e, mel->tab, sizeof(float4) * (size_t)n_bins_pad);
+        stft_gemm_fold_pair_kernel<MelTable><<<2 * n_clusters, P_NUM_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(
+            tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p, tab);
+      } else {
+        stft_gemm_fold_pair_kernel<NoTable><<<2 * n_clusters, P_NUM_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(
+            tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p, NoTable{0});
+      }
       count_launch();
       return check_launch("stft_gemm_fold_pair_kernel");
     }
   }
+  RVB_REQUIRE(!mel, "%s: the Mel epilogue lives in the CTA-pair kernel (unset RVB_GEMM_1CTA)", who);
   static bool attr_set = false;
   if (!attr_set) {
     RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_kernel<kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
