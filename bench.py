@@ -370,7 +370,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--input", default="pcm16", choices=["pcm16", "f32"],
                     help="audio format handed to the front-end: the dataset's PCM int16 (default) or float32")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=3,
                     help="replay the per-buffer graphs on this many alternating streams (device-resident run)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--model", default="injected", choices=["injected", "standin"],
