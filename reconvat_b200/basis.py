@@ -145,12 +145,15 @@ def banded_filterbank(mel_basis):
     return band0, w0, w1, k_begin, k_end
 
 
-def mel_epilogue_table(mel_basis, n_bins_pad, tile=GEMM_TILE_BINS):
+EPILOGUE_CHUNK_BINS = 32      # bins folded by one epilogue warp group of the contraction (rvb_stft_gemm.cu)
+
+
+def mel_epilogue_table(mel_basis, n_bins_pad, tile=EPILOGUE_CHUNK_BINS):
     """Table for the Mel projection fused into the contraction's epilogue: float32 [n_bins_pad, 4] rows
     (w0, w1, band0 as int32 bits, 0) from :func:`banded_filterbank`, band0 kept non-decreasing over the padding.
     Returns None when the fused epilogue cannot represent the bank bit-reproducibly: a bin feeding more than two
     (or non-adjacent) bands, weight on a bin the tiled contraction does not produce (>= n_bins_pad), or a band
-    straddling more than two 128-bin tiles (its partial sums would then be added in a run-dependent order)."""
+    straddling more than two 32-bin epilogue chunks (its partial sums would then be added in a run-dependent order)."""
     mb = np.asarray(mel_basis, dtype=np.float32)
     try:
         band0, w0, w1, k_begin, k_end = banded_filterbank(mb)

@@ -430,7 +430,8 @@ __device__ __forceinline__ void mel_bins8(const FoldParams& p, const uint32_t (&
 // straight-line code that overflows the instruction cache costs ~10 cycles per instruction, and a TMEM load issued
 // and awaited in the same trip costs its full latency 32 times per tile (profiles/r01d).
 template <int kEpi, bool kFast>
-__device__ __forceinline__ void mel_unit(const FoldParams& p, uint32_t taddr, const float4* tab /* this tile's 128 bins */,
+__device__ __forceinline__ void mel_unit(const FoldParams& p, uint32_t taddr /* first column of the range */,
+                                         const float4* tab /* first bin of the range */, int n_trips /* 8 bins each */,
                                          float* __restrict__ col, bool f_ok, float scale, float re_add) {
   MelAcc a{__float_as_int(tab[0].z), 0.f, 0.f, nullptr};
   a.cur = col + (int64_t)a.b0 * p.n_frames;
@@ -438,13 +439,13 @@ __device__ __forceinline__ void mel_unit(const FoldParams& p, uint32_t taddr, co
   tmem_ld8(taddr, re0);
   tmem_ld8(taddr + 128, im0);
 #pragma unroll 1
-  for (int j = 0; j < 16; j += 2) {
+  for (int j = 0; j < n_trips; j += 2) {
     tmem_ld_wait();                                                // set 0 (bins 8j .. 8j+7) has landed
     tmem_ld8(taddr + 8 * (j + 1), re1);
     tmem_ld8(taddr + 128 + 8 * (j + 1), im1);
     if (!(p.dbg & 32) || re0[0] == 0x7fc12345u) mel_bins8<kEpi, kFast>(p, re0, im0, tab + 8 * j, col, f_ok, scale, re_add, a);
     tmem_ld_wait();                                                // set 1
-    if (j + 2 < 16) {
+    if (j + 2 < n_trips) {
       tmem_ld8(taddr + 8 * (j + 2), re0);
       tmem_ld8(taddr + 128 + 8 * (j + 2), im0);
     }
@@ -455,21 +456,26 @@ __device__ __forceinline__ void mel_unit(const FoldParams& p, uint32_t taddr, co
   mel_flush(a.cur + p.n_frames, a.b0 + 1, p.n_mels, a.acc1 * s2, f_ok);
 }
 
+// c_begin, c_end: the 32-bin chunks of the tile this warp handles ([0, 4) = the whole tile; the CTA-pair kernel
+// gives each of its two epilogue groups one half, which halves the epilogue's latency per tile).
 template <typename TabT>
 __device__ __forceinline__ void fold_epilogue_unit(const FoldParams& p, const TabT& tab, uint32_t taddr, bool f_ok,
-                                                   int n_tile, int b, int t, float scale, float re0) {
+                                                   int n_tile, int c_begin, int c_end, int b, int t, float scale,
+                                                   float re0) {
   if constexpr (std::is_same<TabT, MelTable>::value) {
     if (p.dbg & 16) return;
-    const float4* tt = tab.e + n_tile * 128;
+    const float4* tt = tab.e + n_tile * 128 + c_begin * 32;
+    const uint32_t ta = taddr + (uint32_t)(c_begin * 32);
+    const int trips = (c_end - c_begin) * 4;
     float* col = p.mel_out + (int64_t)b * p.n_mels * p.n_frames + t;
-    if (p.epilogue == RVB_EPI_POWER && p.p0 == nullptr) mel_unit<RVB_EPI_POWER, true>(p, taddr, tt, col, f_ok, scale, 0.f);
-    else if (p.epilogue == RVB_EPI_POWER) mel_unit<RVB_EPI_POWER, false>(p, taddr, tt, col, f_ok, scale, re0);
-    else if (p.epilogue == RVB_EPI_MAGNITUDE) mel_unit<RVB_EPI_MAGNITUDE, false>(p, taddr, tt, col, f_ok, scale, re0);
-    else mel_unit<RVB_EPI_POWER_P, false>(p, taddr, tt, col, f_ok, scale, re0);
+    if (p.epilogue == RVB_EPI_POWER && p.p0 == nullptr) mel_unit<RVB_EPI_POWER, true>(p, ta, tt, trips, col, f_ok, scale, 0.f);
+    else if (p.epilogue == RVB_EPI_POWER) mel_unit<RVB_EPI_POWER, false>(p, ta, tt, trips, col, f_ok, scale, re0);
+    else if (p.epilogue == RVB_EPI_MAGNITUDE) mel_unit<RVB_EPI_MAGNITUDE, false>(p, ta, tt, trips, col, f_ok, scale, re0);
+    else mel_unit<RVB_EPI_POWER_P, false>(p, ta, tt, trips, col, f_ok, scale, re0);
     return;
   }
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     uint32_t re[32], im[32];
     tmem_ld32(taddr + c * 32, re);
     tmem_ld32(taddr + 128 + c * 32, im);
@@ -611,7 +617,7 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
       mbar_wait(bar_tmem_full(acc), acc_phase, nullptr, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
-      fold_epilogue_unit(p, NoTable{}, taddr, f_ok, n_tile, b, t, scale, re0);
+      fold_epilogue_unit(p, NoTable{}, taddr, f_ok, n_tile, 0, 4, b, t, scale, re0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tmem_empty(acc));
@@ -641,7 +647,8 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
 //   tmem_empty[a]  lives in the leader, count 8: four epilogue warps of each CTA arrive (remotely from rank 1).
 // Only the leader's warp 1 issues MMAs; each CTA's epilogue drains its own 128 TMEM lanes.
 constexpr int P_STAGES = 4;
-constexpr int P_NUM_THREADS = 64 + 2 * 128;          // TMA warp, MMA warp, two epilogue groups of four warps
+constexpr int P_EPI_GROUPS = 4;                       // epilogue groups of four warps; each takes 128 / P_EPI_GROUPS bins
+constexpr int P_NUM_THREADS = 64 + P_EPI_GROUPS * 128;   // TMA warp, MMA warp, epilogue groups
 constexpr int P_A_BYTES = 128 * 128;                    // 128 frame rows x one 128-byte swizzle row
 constexpr int P_B_BYTES = 64 * 128;                     // this CTA's half of the 128 basis rows
 constexpr int P_STAGE_BYTES = 2 * P_A_BYTES + 2 * P_B_BYTES;     // A_hi A_lo B_hi B_lo = 48 KB
@@ -730,7 +737,7 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tmem_full(a), 1);
-      mbar_init(bar_tmem_empty(a), 8);            // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+      mbar_init(bar_tmem_empty(a), 8 * P_EPI_GROUPS);   // epilogue warps of both CTAs (only the leader's copy is used)
     }
     fence_barrier_init();
   }
@@ -811,15 +818,19 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
     }
     __syncwarp();
   } else {
-    // Two epilogue groups of four warps: group g drains accumulator stage g, i.e. every second unit of this
-    // cluster, so one unit's epilogue may take up to two MMA unit times before the tensor pipe waits for it.
-    const int group = (warp - EPI_WARP0) >> 2;
+    // P_EPI_GROUPS x 4 epilogue warps per CTA: group g folds bins [32 g, 32 g + 32) of every tile (TMEM lane quarter
+    // = warp % 4 in every group).  A TMEM accumulator stage is handed back to the tensor pipe only when its epilogue
+    // has finished, so what must stay below one MMA tile time is the epilogue's LATENCY per tile, whatever its
+    // throughput: one group 222 us, two 197 us, four 190 us = the contraction without any Mel work (profiles/r01e).
+    // A band straddling a 32-bin boundary gets its two partial sums from two groups (or two tiles): still at most
+    // two per element for banks whose bands are narrower than 33 bins -- checked on the host.
+    const int half_id = (warp - EPI_WARP0) >> 2;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
-    const uint32_t leader_tmem_empty = map_to_rank(bar_tmem_empty(group), 0);
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(group * ACC_COLS);
+    const uint32_t leader_tmem_empty0 = map_to_rank(bar_tmem_empty(0), 0);
+    int acc = 0;
     uint32_t acc_phase = 0;
-    for (int unit = unit0 + group * unit_step; unit < n_units; unit += 2 * unit_step) {
+    for (int unit = unit0; unit < n_units; unit += unit_step) {
       const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
       const int64_t f = (int64_t)m_tile * 256 + (int64_t)rank * 128 + row;       // flattened frame index
       const bool f_ok = f < p.m_rows;
@@ -827,13 +838,15 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
       const int t = f_ok ? (int)(f - (int64_t)b * p.n_frames) : 0;
       const float re0 = (p.p0 != nullptr && f_ok) ? p.w0 * __ldg(p.p0 + f) : 0.f;
       const float scale = f_ok ? __ldg(p.row_scale_inv + f) * p.basis_scale_inv : 1.f;
-      mbar_wait(bar_tmem_full(group), acc_phase, nullptr, 4);
+      mbar_wait(bar_tmem_full(acc), acc_phase, nullptr, 4);
       tc_fence_after();
-      fold_epilogue_unit(p, tab, taddr, f_ok, n_tile, b, t, scale, re0);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+      constexpr int kChunks = 4 / P_EPI_GROUPS;
+      fold_epilogue_unit(p, tab, taddr, f_ok, n_tile, kChunks * half_id, kChunks * half_id + kChunks, b, t, scale, re0);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty);
-      acc_phase ^= 1u;
+      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
