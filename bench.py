@@ -246,9 +246,17 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda._sleep(int(k_steps * max(eager_ms_step, 0.3) * 3e-3 * 1.9e9))      # 3x the eager enqueue time
     for i in range(k_steps):
         step(dev_audio[i % n_rot])
+    # an event pair around nothing, queued behind the same spin: what the pair itself costs on the stream
+    empty = []
+    for _ in range(64):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e1.record()
+        empty.append((e0, e1))
     barrier()
     R._lib.record_events(None)
     step.vat_loss.check()
+    ev_overhead_ms = statistics.median(a.elapsed_time(b) for a, b in empty)
     kms = {n: [s.elapsed_time(e) for s, e in v] for n, v in log.items() if v}
     kavg = {n: sum(v) / len(v) for n, v in kms.items()}
 
@@ -351,6 +359,9 @@ def run_ours(args, rank, local_rank, world):
                        "copy of batch i+1 overlapped with the kernels of batch i%s)" % ("" if args.no_graphs else "; graph replay")},
         "gpu_launches": launches,
         "eager_ms_per_step": eager_ms_step,
+        # an event pair around nothing costs this much on the stream; the per-kernel times below INCLUDE it (they
+        # are upper bounds: the ncu durations in profiles/ are tighter, e.g. 11 us for vat_perturb)
+        "event_pair_overhead_us": ev_overhead_ms * 1e3,
         "roofline": roofline,
         "hbm_kernels": hbm,
         "cpu_baseline": cpu,

@@ -161,9 +161,7 @@ __device__ __forceinline__ void fold4(const float* __restrict__ fr /* fr[i + 3] 
 
 // TIn = float, or int16_t for PCM16 audio as the dataset stores it (sample = pcm * gain, gain = 1/32768:
 // model/dataset.py:62 `audio.float().div_(32768.0)`; both steps are exact in fp32).
-// kIters = n_fft / 256 when the frame's 2 * kIters * 4 folded values per lane fit in registers (the fold is then
-// evaluated once), 0 = generic two-pass evaluation.
-template <typename TIn, int kIters>
+template <typename TIn>
 __global__ void __launch_bounds__(kFoldWarps * 32)
 fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gain, int n_seg, int n_samples, int pad,
                       int mode, int n_fft, int hop, int n_frames, int groups_per_seg, __half* __restrict__ a_hi,
@@ -208,22 +206,15 @@ fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gai
     const int t = t0 + warp;
     if (t >= n_frames) continue;                           // warp-uniform; the barriers above are reached by all
     const float* fr = span_s + warp * hop;                 // fr[i + 3] = p[i] of frame t
-    constexpr int kR = kIters > 0 ? kIters : 1;
-    float ev[kR][4], ov[kR][4];
+    // two passes over the staged samples (max, then scale + split): keeping the 64 folded values of a lane in
+    // registers instead costs 95 registers, halves the occupancy and is slower (64 us vs 52 us): the kernel is
+    // latency-bound on the staging loads, not instruction-bound
+    float ev[4], ov[4];
     float mx = 0.f;
-    if constexpr (kIters > 0) {
+    for (int c = lane << 2; c < half; c += 128) {
+      fold4(fr, n_fft, half, c, ev, ov);
 #pragma unroll
-      for (int it = 0; it < kIters; ++it) {
-        fold4(fr, n_fft, half, (lane << 2) + it * 128, ev[it], ov[it]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(ev[it][i]), fabsf(ov[it][i])));
-      }
-    } else {
-      for (int c = lane << 2; c < half; c += 128) {
-        fold4(fr, n_fft, half, c, ev[0], ov[0]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(ev[0][i]), fabsf(ov[0][i])));   // fmaxf drops NaN
-      }
+      for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(ev[i]), fabsf(ov[i])));   // fmaxf drops NaN: s stays finite
     }
     mx = warp_max(mx);
     // floor(log2(mx)) from the exponent field (subnormal rows: treated as 2^-126); all-zero rows: s = 0
@@ -248,21 +239,11 @@ fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gai
       hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
       lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
     };
-    if constexpr (kIters > 0) {
-#pragma unroll
-      for (int it = 0; it < kIters; ++it) {
-        const int q = lane + it * 32;
-        uint2 h, l;
-        split4(ev[it], h, l); e_hi[q] = h; e_lo[q] = l;
-        split4(ov[it], h, l); o_hi[q] = h; o_lo[q] = l;
-      }
-    } else {
-      for (int c = lane << 2; c < half; c += 128) {
-        fold4(fr, n_fft, half, c, ev[0], ov[0]);
-        uint2 h, l;
-        split4(ev[0], h, l); e_hi[c >> 2] = h; e_lo[c >> 2] = l;
-        split4(ov[0], h, l); o_hi[c >> 2] = h; o_lo[c >> 2] = l;
-      }
+    for (int c = lane << 2; c < half; c += 128) {
+      fold4(fr, n_fft, half, c, ev, ov);
+      uint2 h, l;
+      split4(ev, h, l); e_hi[c >> 2] = h; e_lo[c >> 2] = l;
+      split4(ov, h, l); o_hi[c >> 2] = h; o_lo[c >> 2] = l;
     }
     if (lane == 0) {
       row_scale_inv[f] = __uint_as_float((unsigned)(127 - s) << 23);      // 2^-s
@@ -641,12 +622,7 @@ static int launch_fold_split_f16(const char* who, const TIn* audio, int64_t audi
   RVB_REQUIRE(hop % 4 == 0, "%s: hop %d must be a multiple of 4", who, hop);
   const size_t smem = (size_t)(n_fft + (kFoldWarps - 1) * (int64_t)hop + 8) * sizeof(float);
   RVB_REQUIRE(smem <= 200 * 1024, "%s: n_fft %d with hop %d needs %zu bytes of shared memory", who, n_fft, hop, smem);
-  static const bool regs = getenv("RVB_FOLD_REGS") != nullptr;      // A/B switch for measurements
-  auto kernel = !regs ? fold_split_f16_kernel<TIn, 0>
-              : (n_fft == 2048) ? fold_split_f16_kernel<TIn, 8>
-              : (n_fft == 1024) ? fold_split_f16_kernel<TIn, 4>
-              : (n_fft == 512)  ? fold_split_f16_kernel<TIn, 2>
-                                : fold_split_f16_kernel<TIn, 0>;
+  auto kernel = fold_split_f16_kernel<TIn>;
   if (smem > 48 * 1024)
     RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int groups_per_seg = (n_frames + kFoldWarps - 1) / kFoldWarps;

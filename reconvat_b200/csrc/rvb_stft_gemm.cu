@@ -344,7 +344,6 @@ struct FoldParams {
   float* out0;
   const float* row_scale_inv;   // fp16 operands only: per-frame 2^-s_row
   float basis_scale_inv;        // fp16 operands only: 2^-s_basis
-  int dbg;                      // RVB_DBG experiments (timing only, results invalid): 1 alt acc, 2 no stores, 4 no TMA
   // fused Mel projection (K1m, kernels instantiated with a MelTable): the epilogue does not store the spectrum
   float* mel_out;               // [n_seg][n_mels][n_frames], zeroed before the launch, accumulated with RED.ADD
   int n_mels;
@@ -443,13 +442,13 @@ __device__ __forceinline__ void mel_unit(const FoldParams& p, uint32_t taddr /* 
     tmem_ld_wait();                                                // set 0 (bins 8j .. 8j+7) has landed
     tmem_ld8(taddr + 8 * (j + 1), re1);
     tmem_ld8(taddr + 128 + 8 * (j + 1), im1);
-    if (!(p.dbg & 32) || re0[0] == 0x7fc12345u) mel_bins8<kEpi, kFast>(p, re0, im0, tab + 8 * j, col, f_ok, scale, re_add, a);
+    mel_bins8<kEpi, kFast>(p, re0, im0, tab + 8 * j, col, f_ok, scale, re_add, a);
     tmem_ld_wait();                                                // set 1
     if (j + 2 < n_trips) {
       tmem_ld8(taddr + 8 * (j + 2), re0);
       tmem_ld8(taddr + 128 + 8 * (j + 2), im0);
     }
-    if (!(p.dbg & 32) || re1[0] == 0x7fc12345u) mel_bins8<kEpi, kFast>(p, re1, im1, tab + 8 * (j + 1), col, f_ok, scale, re_add, a);
+    mel_bins8<kEpi, kFast>(p, re1, im1, tab + 8 * (j + 1), col, f_ok, scale, re_add, a);
   }
   const float s2 = kFast ? scale * scale : 1.f;
   mel_flush(a.cur, a.b0, p.n_mels, a.acc0 * s2, f_ok);
@@ -463,7 +462,6 @@ __device__ __forceinline__ void fold_epilogue_unit(const FoldParams& p, const Ta
                                                    int n_tile, int c_begin, int c_end, int b, int t, float scale,
                                                    float re0) {
   if constexpr (std::is_same<TabT, MelTable>::value) {
-    if (p.dbg & 16) return;
     const float4* tt = tab.e + n_tile * 128 + c_begin * 32;
     const uint32_t ta = taddr + (uint32_t)(c_begin * 32);
     const int trips = (c_end - c_begin) * 4;
@@ -481,7 +479,7 @@ __device__ __forceinline__ void fold_epilogue_unit(const FoldParams& p, const Ta
     tmem_ld32(taddr + 128 + c * 32, im);
     tmem_ld_wait();
     const int k0 = n_tile * 128 + c * 32;
-    if (f_ok && !((p.dbg & 2) && re[0] != 0x7fc12345u))
+    if (f_ok)
       stft_store_chunk(p.epilogue, p.power, re, im, scale, re0, p.out0, b, k0, t, p.n_out_bins, p.n_store_bins,
                        p.n_frames);
   }
@@ -549,7 +547,6 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
           const int a_row = (int)(chain * p.m_rows) + m_tile * BLOCK_M;
           const int b_row = chain * p.n_bins_pad + n_tile * F_BLOCK_N;
           mbar_wait(bar_empty(stage), phase ^ 1u, nullptr, 1);
-          if (p.dbg & 4) { mbar_arrive(bar_full(stage)); if (++stage == F_STAGES) { stage = 0; phase ^= 1u; } continue; }
           mbar_expect_tx(bar_full(stage), F_STAGE_BYTES);
           tma_load_2d(&tm_a_hi, s_tile(stage, 0), bar_full(stage), kk, a_row);
           tma_load_2d(&tm_a_lo, s_tile(stage, 1), bar_full(stage), kk, a_row);
@@ -583,10 +580,9 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
             const uint64_t adv = (uint64_t)(k * UMMA_K * 4 >> 4);     // one MMA consumes 32 bytes of the row
             // small cross terms first: while the accumulator is still small their truncation costs nothing
             if constexpr (kF16) {
-              const uint32_t d_x = (p.dbg & 1) ? (d_tmem ^ 256u) : d_tmem;
-              umma_f16(d_x, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
+              umma_f16(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
               umma_f16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
-              umma_f16(d_x, da_hi + adv, db_hi + adv, idesc, 1u);
+              umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
             } else {
               umma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
               umma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
@@ -1060,7 +1056,6 @@ static int launch_folded(const char* who, const void* a_hi, const void* a_lo, co
   p.n_store_bins = n_out_bins < n_bins_pad ? n_out_bins : n_bins_pad;
   p.power = power; p.w0 = w0; p.p0 = (w0 != 0.f) ? p0 : nullptr; p.out0 = out0;
   p.row_scale_inv = row_scale_inv; p.basis_scale_inv = basis_scale_inv;
-  { const char* d = getenv("RVB_DBG"); p.dbg = d ? atoi(d) : 0; }
   p.mel_out = mel ? mel->out : nullptr;
   p.n_mels = mel ? mel->n_mels : 0;
 

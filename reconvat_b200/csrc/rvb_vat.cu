@@ -410,7 +410,7 @@ extern "C" int rvb_div_mean(int kind, const float* p, const float* y, int64_t n,
                             float* workspace, rvb_stream_t stream) {
   RVB_REQUIRE(p && y && loss && workspace, "rvb_div_mean: null pointer");
   RVB_REQUIRE(n > 0 && denom > 0, "rvb_div_mean: empty input (the reference returns NaN for an empty mean)");
-  unsigned grid = flat_grid(n, 16);
+  unsigned grid = flat_grid(n, 8);                      // two float4 pairs per thread: enough warps to hide the logs
   if (grid > (unsigned)kBceMaxBlocks) grid = kBceMaxBlocks;
   const int vec = aligned16(p) && aligned16(y);
   return dispatch_kind(kind, "rvb_div_mean", [&](auto k) {
