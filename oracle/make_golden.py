@@ -175,6 +175,36 @@ def main():
                         imagewise=ref.utils.Normalization("imagewise").transform(l).numpy(),
                         framewise=ref.utils.Normalization("framewise").transform(l.clone()).numpy())
 
+    # ---- 9. local-window attention of the U-Net: the reference class, forward and backward.
+    # Weights come from the integer hash (no framework RNG), so only inputs' seeds and the outputs are stored.
+    from reconvat_b200.standin import _hash_normal
+    out = {}
+    for tag, (B_, L_, fin, cout, W_, G_, pos) in {"small": (2, 37, 20, 48, 7, 4, True),
+                                                  "nopos": (1, 19, 12, 24, 5, 2, False),
+                                                  "unet": (1, 70, 229, 916, 31, 4, True)}.items():
+        att_mod = ref.self_attention_VAT.MutliHeadAttention1D(fin, cout, W_, position=pos, groups=G_)
+        hn = lambda n, seed, shape: torch.tensor(_hash_normal(n, seed).reshape(shape), dtype=torch.float32)
+        with torch.no_grad():
+            att_mod.W_q.weight.copy_(hn(cout * fin, 301, (cout, fin)) / np.sqrt(fin))
+            att_mod.W_k.weight.copy_(hn(cout * fin, 302, (cout, fin)) / np.sqrt(fin))
+            att_mod.W_v.weight.copy_(hn(cout * fin, 303, (cout, fin)) / np.sqrt(fin))
+            if pos:
+                att_mod.rel.copy_(hn(cout * W_, 304, (1, cout, W_)))
+        xa = hn(B_ * L_ * fin, 305, (B_, L_, fin)).requires_grad_(True)
+        o, a = att_mod(xa)
+        go = hn(B_ * L_ * cout, 306, (B_, L_, cout))
+        o.backward(go)
+        out[tag + "_dims"] = np.array([B_, L_, fin, cout, W_, G_, int(pos)])
+        out[tag + "_out"] = o.detach().numpy()
+        out[tag + "_att"] = a.detach().numpy()
+        out[tag + "_dx"] = xa.grad.numpy()
+        if pos:
+            out[tag + "_drel"] = att_mod.rel.grad.numpy()
+        if tag != "unet":
+            for nm in ("W_q", "W_k", "W_v"):
+                out[tag + "_d" + nm] = getattr(att_mod, nm).weight.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "attention.npz"), **out)
+
     for f in sorted(os.listdir(OUT)):
         print("%-28s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
 

@@ -1,0 +1,92 @@
+"""Drop-in for the reference's ``MutliHeadAttention1D`` (model/self_attention_VAT.py:22-91; the same class is repeated in
+model/UNet_onset.py:22, model/onset_frame_VAT.py:16 and model/self_attention.py:6): 1-D local-window multi-head
+attention with a relative position term, the sequence model of the ReconVAT U-Net (Spec2Roll.lstm1 / Roll2Spec.lstm2,
+:934,:953).  SURVEY.md 8f row f2: it is the CALLER of the hot path, and the worst memory amplifier in it -- the
+reference unfolds k and v to (B, L, C, W), 73 MB per 20 s segment each at C = 916, W = 31, and autograd keeps both.
+
+Same constructor, parameters (``W_q``, ``W_k``, ``W_v``, ``rel`` -> state_dict compatible) and return values
+``(out (B, L, C), attention (B, L, groups, W))``.  The three projections stay ``nn.Linear`` (cuBLAS); everything after
+them is one kernel forward and two backward (librvb.so, rvb_attention.cu); d rel is a batched GEMM (torch).
+Scope cuts, raising: ``stride != 1`` and ``bias=True`` (no reference model uses them; with a bias the zero padding
+rows would become the bias vector).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.init as init
+
+from . import _lib
+
+
+class _LocalAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, rel, groups, window):
+        for t in (q, k, v, rel):
+            if not t.is_cuda or t.dtype != torch.float32:
+                raise _lib.RvbError("reconvat_b200 attention needs CUDA float32 tensors (got %s, %s); there is no CPU "
+                                    "path" % (t.device, t.dtype))
+        q, k, v, rel = q.contiguous(), k.contiguous(), v.contiguous(), rel.contiguous()
+        B, L, C = q.shape
+        D = C // groups
+        out = torch.empty_like(q)
+        att = torch.empty((B, L, groups, window), dtype=torch.float32, device=q.device)
+        _lib.call("rvb_local_attn_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), rel.data_ptr(), B, L, groups, D, window,
+                  out.data_ptr(), att.data_ptr())
+        ctx.save_for_backward(q, k, v, rel, att)
+        ctx.dims = (B, L, groups, D, window)
+        ctx.mark_non_differentiable(att)          # the reference only plots it (model/self_attention_VAT.py:938)
+        return out, att
+
+    @staticmethod
+    def backward(ctx, dout, _datt):
+        q, k, v, rel, att = ctx.saved_tensors
+        B, L, G, D, W = ctx.dims
+        dout = dout.contiguous()
+        relT = rel.view(G, D, W).transpose(1, 2).contiguous()            # [G][W][D]: coalesced for lanes <-> channels
+        dE = torch.empty_like(att)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        _lib.call("rvb_local_attn_bwd_q", dout.data_ptr(), att.data_ptr(), k.data_ptr(), v.data_ptr(), relT.data_ptr(),
+                  B, L, G, D, W, dE.data_ptr(), dq.data_ptr())
+        _lib.call("rvb_local_attn_bwd_kv", q.data_ptr(), dout.data_ptr(), att.data_ptr(), dE.data_ptr(), B, L, G, D, W,
+                  dk.data_ptr(), dv.data_ptr())
+        # d rel[h,c,w] = sum_{b,l} q[b,l,h,c] dE[b,l,h,w]: one batched GEMM over the heads
+        drel = torch.einsum("nhc,nhw->hcw", q.view(B * L, G, D), dE.view(B * L, G, W)).reshape(G * D, W)
+        return dq, dk, dv, drel, None, None
+
+
+class MutliHeadAttention1D(nn.Module):
+    def __init__(self, in_features, out_features, kernel_size, stride=1, groups=1, position=True, bias=False):
+        """kernel_size is the 1D local attention window size"""
+        super().__init__()
+        if stride != 1:
+            raise NotImplementedError("reconvat_b200 MutliHeadAttention1D: stride=%r (every reference model uses 1)" % stride)
+        if bias:
+            raise NotImplementedError("reconvat_b200 MutliHeadAttention1D: bias=True (never used by the reference)")
+        self.out_features = out_features
+        self.kernel_size = kernel_size
+        self.stride = stride
+        self.position = position
+        self.padding = (kernel_size - 1) // 2
+        self.groups = groups
+        assert self.out_features % self.groups == 0, (
+            f"out_channels should be divided by groups. (example: out_channels: 40, groups: 4). "
+            f"Now out_channels={self.out_features}, groups={self.groups}")
+        assert (kernel_size - 1) % 2 == 0, "kernal size must be odd number"
+        if self.position:
+            self.rel = nn.Parameter(torch.randn(1, out_features, kernel_size), requires_grad=True)
+        self.W_k = nn.Linear(in_features, out_features, bias=bias)
+        self.W_q = nn.Linear(in_features, out_features, bias=bias)
+        self.W_v = nn.Linear(in_features, out_features, bias=bias)
+        self.reset_parameters()
+
+    def forward(self, x):
+        q, k, v = self.W_q(x), self.W_k(x), self.W_v(x)                  # zero padding rows project to zero (no bias)
+        rel = self.rel[0] if self.position else torch.zeros((self.out_features, self.kernel_size), dtype=q.dtype,
+                                                             device=q.device)
+        return _LocalAttention.apply(q, k, v, rel, self.groups, self.kernel_size)
+
+    def reset_parameters(self):
+        init.kaiming_normal_(self.W_k.weight, mode='fan_out', nonlinearity='relu')
+        init.kaiming_normal_(self.W_v.weight, mode='fan_out', nonlinearity='relu')
+        init.kaiming_normal_(self.W_q.weight, mode='fan_out', nonlinearity='relu')
+        if self.position:
+            init.normal_(self.rel, 0, 1)

@@ -59,10 +59,22 @@ def install_nnaudio():
     return pkg
 
 
-def patch_reference():
+_ATTENTION_MODULES = ("model.self_attention_VAT", "model.UNet_onset", "model.onset_frame_VAT", "model.self_attention")
+
+
+def patch_reference(attention=False):
     """Rebind VAT classes, Normalization and the Spectrogram module in every imported reference module.
+    ``attention=True`` also rebinds ``MutliHeadAttention1D`` (the U-Net's sequence model) to the
+    fused local-window attention: same parameters and outputs, no (B, L, C, W) unfolded tensors.
     Returns the list of (module, name) pairs that were rebound."""
     done = []
+    if attention:
+        from . import attention as _att
+        for modname in _ATTENTION_MODULES:
+            mod = sys.modules.get(modname)
+            if mod is not None and hasattr(mod, "MutliHeadAttention1D"):
+                mod.MutliHeadAttention1D = _att.MutliHeadAttention1D
+                done.append((modname, "MutliHeadAttention1D"))
     for modname, names in _VAT_BINDINGS.items():
         mod = sys.modules.get(modname)
         if mod is None:
@@ -89,6 +101,6 @@ def patch_reference():
     return done
 
 
-def install():
+def install(attention=False):
     install_nnaudio()
-    return patch_reference()
+    return patch_reference(attention=attention)

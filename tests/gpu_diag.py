@@ -1,5 +1,5 @@
 """Verbose per-kernel diagnostics for a GPU box (writes human-readable text; not a test).
-Usage: python tools/gpu_diag.py [stage ...]   stages: vat pad mel gemm frontend timing"""
+Usage: python tests/gpu_diag.py [stage ...]   stages: vat pad mel gemm frontend timing"""
 import os
 import sys
 import time

@@ -1,0 +1,115 @@
+"""Local-window attention of the U-Net: oracle restatement pinned to the unmodified reference's
+outputs (CPU), and the CUDA kernels (forward + backward) against both."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention as OA
+from reconvat_b200.standin import _hash_normal
+
+CASES = ["small", "nopos", "unet"]
+
+
+def _inputs(g, tag):
+    B, L, fin, cout, W, G, pos = [int(v) for v in g[tag + "_dims"]]
+    hn = lambda n, seed, shape: torch.tensor(_hash_normal(n, seed).reshape(shape), dtype=torch.float32)
+    w = [hn(cout * fin, s, (cout, fin)) / np.sqrt(fin) for s in (301, 302, 303)]
+    rel = hn(cout * W, 304, (1, cout, W)) if pos else None
+    x = hn(B * L * fin, 305, (B, L, fin))
+    go = hn(B * L * cout, 306, (B, L, cout))
+    return (B, L, fin, cout, W, G, pos), w, rel, x, go
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_oracle_attention_matches_reference_golden(golden, tag):
+    g = golden["attention"]
+    (B, L, fin, cout, W, G, pos), w, rel, x, go = _inputs(g, tag)
+    x = x.requires_grad_(True)
+    if rel is not None:
+        rel = rel.requires_grad_(True)
+    out, att = OA.local_attention(x, w[0], w[1], w[2], rel, G, W)
+    assert out.shape == (B, L, cout) and att.shape == (B, L, G, W)
+    assert np.abs(out.detach().numpy() - g[tag + "_out"]).max() < 1e-5 * np.abs(g[tag + "_out"]).max()
+    assert np.abs(att.detach().numpy() - g[tag + "_att"]).max() < 1e-6
+    out.backward(go)
+    assert np.abs(x.grad.numpy() - g[tag + "_dx"]).max() < 1e-5 * np.abs(g[tag + "_dx"]).max()
+    if pos:
+        assert np.abs(rel.grad.numpy() - g[tag + "_drel"]).max() < 1e-5 * np.abs(g[tag + "_drel"]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", CASES)
+def test_attention_kernels_match_reference_golden(golden, tag):
+    """reconvat_b200.attention.MutliHeadAttention1D (forward, and backward to x, the projections and rel) against the
+    outputs the UNMODIFIED reference class produced for the same weights and input."""
+    import reconvat_b200.attention as A
+    dev = torch.device("cuda:0")
+    g = golden["attention"]
+    (B, L, fin, cout, W, G, pos), w, rel, x, go = _inputs(g, tag)
+    m = A.MutliHeadAttention1D(fin, cout, W, position=pos, groups=G).to(dev)
+    with torch.no_grad():
+        m.W_q.weight.copy_(w[0]); m.W_k.weight.copy_(w[1]); m.W_v.weight.copy_(w[2])
+        if pos:
+            m.rel.copy_(rel)
+    xd = x.to(dev).requires_grad_(True)
+    out, att = m(xd)
+    rel_err = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    assert out.shape == (B, L, cout) and att.shape == (B, L, G, W) and not att.requires_grad
+    assert rel_err(out.detach().cpu().numpy(), g[tag + "_out"]) < 2e-5
+    # energies reach +-50 at the U-Net's head size: their fp32 summation-order rounding (~1e-5) passes through exp
+    assert np.abs(att.cpu().numpy() - g[tag + "_att"]).max() < 5e-5
+    assert torch.allclose(att.sum(-1), torch.ones_like(att[..., 0]), atol=1e-5)
+    out.backward(go.to(dev))
+    assert rel_err(xd.grad.cpu().numpy(), g[tag + "_dx"]) < 5e-5
+    if pos:
+        assert rel_err(m.rel.grad.cpu().numpy(), g[tag + "_drel"]) < 5e-5
+    if tag != "unet":
+        for nm in ("W_q", "W_k", "W_v"):
+            assert rel_err(getattr(m, nm).weight.grad.cpu().numpy(), g[tag + "_d" + nm]) < 5e-5
+    # state_dict interchange with the reference class: same parameter names and shapes
+    assert sorted(m.state_dict()) == sorted(["W_k.weight", "W_q.weight", "W_v.weight"] + (["rel"] if pos else []))
+
+
+@pytest.mark.gpu
+def test_attention_full_size_against_oracle_and_memory():
+    """Spec2Roll.lstm1 at full size (B=2, L=640, 229 -> 916, W=31, 4 heads): forward/backward against the oracle run on
+    the CPU, and the point of the kernel -- no (B, L, C, W) tensor: peak memory stays a small multiple of q/k/v."""
+    import reconvat_b200.attention as A
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    m = A.MutliHeadAttention1D(229, 916, 31, position=True, groups=4)
+    x = torch.rand(2, 640, 229)
+    go = torch.randn(2, 640, 916)
+    xr = x.clone().requires_grad_(True)
+    rel = m.rel.detach().clone().requires_grad_(True)
+    o_ref, a_ref = OA.local_attention(xr, m.W_q.weight.detach(), m.W_k.weight.detach(), m.W_v.weight.detach(), rel, 4, 31)
+    o_ref.backward(go)
+    m = m.to(dev)
+    xd = x.to(dev).requires_grad_(True)
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    out, att = m(xd)
+    out.backward(go.to(dev))
+    torch.cuda.synchronize()
+    peak = torch.cuda.max_memory_allocated() - base
+    rel_err = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    assert rel_err(out.detach().cpu(), o_ref.detach()) < 2e-5
+    assert float((att.cpu() - a_ref.detach()).abs().max()) < 5e-5
+    assert rel_err(xd.grad.cpu(), xr.grad) < 5e-5
+    assert rel_err(m.rel.grad.cpu(), rel.grad) < 5e-5
+    unfolded = 2 * 640 * 916 * 31 * 4                        # ONE of the reference's unfolded k / v tensors: 145 MB
+    assert peak < 0.5 * unfolded, (peak, unfolded)
+
+
+@pytest.mark.gpu
+def test_attention_rejects_what_it_does_not_implement():
+    import reconvat_b200.attention as A
+    from reconvat_b200 import _lib
+    with pytest.raises(NotImplementedError):
+        A.MutliHeadAttention1D(8, 16, 3, stride=2)
+    with pytest.raises(NotImplementedError):
+        A.MutliHeadAttention1D(8, 16, 3, bias=True)
+    with pytest.raises(AssertionError):
+        A.MutliHeadAttention1D(8, 16, 4)                      # even window, like the reference
+    with pytest.raises(_lib.RvbError):
+        A.MutliHeadAttention1D(8, 16, 3)(torch.zeros(1, 5, 8))   # CPU tensor: no fallback
