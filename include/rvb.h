@@ -316,6 +316,15 @@ int rvb_local_attn_bwd_q(const float* dout, const float* att, const float* k, co
 int rvb_local_attn_bwd_kv(const float* q, const float* dout, const float* att, const float* dE, int B, int L, int G,
                           int D, int W, float* dk, float* dv, rvb_stream_t stream);
 
+/*
+ * D1  note decoding (model/decoding.py:4-55, extract_notes_wo_velocity; driven by transcribe_files.py:12-40):
+ * onsets, frames: [n_frames][n_pitches] posteriors.  start[t][p] = 1 where a note begins (thresholded onset roll rises;
+ * rule1: and the frame roll is on), offset[t][p] = first frame u >= t where neither thresholded roll is on (n_frames
+ * if none).  The note list is then nonzero(start) with intervals (t, offset[t][p]) -- integer work, bit-exact.
+ */
+int rvb_note_offsets(const float* onsets, const float* frames, int n_frames, int n_pitches, float onset_threshold,
+                     float frame_threshold, int rule1, uint8_t* start, int32_t* offset, rvb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

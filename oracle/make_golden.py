@@ -205,6 +205,31 @@ def main():
                 out[tag + "_d" + nm] = getattr(att_mod, nm).weight.grad.numpy()
     np.savez_compressed(os.path.join(OUT, "attention.npz"), **out)
 
+    # ---- 10. note decoding (model/decoding.py:4-55), both rules, on run-structured random posteriors
+    T_, P_ = 300, 88
+    u = synth.uniform01(T_ * P_, 401).reshape(T_, P_)
+    fr_roll = np.zeros((T_, P_), np.float32)
+    on_roll = np.zeros((T_, P_), np.float32)
+    starts = np.argwhere(u > 0.985)
+    lens = (synth.uniform01(len(starts), 402) * 40).astype(int) + 1
+    for (t0, p0), n in zip(starts, lens):
+        fr_roll[t0:t0 + n, p0] = 0.9
+        on_roll[t0:t0 + 1 + n // 8, p0] = 0.8
+    fr_roll[-5:, 3] = 0.9; on_roll[-5, 3] = 0.8                       # a note that runs into the end of the file
+    on_roll[10, 7] = 0.8                                               # an onset without a frame (rule1 drops it)
+    noise = (synth.uniform01(T_ * P_, 403).reshape(T_, P_) * 0.45).astype(np.float32)
+    on_roll = np.maximum(on_roll, noise); fr_roll = np.maximum(fr_roll, noise[::-1].copy())
+    out = {"onsets": on_roll, "frames": fr_roll}
+    for rule in ("rule1", "rule2"):
+        pch, itv = ref.decoding.extract_notes_wo_velocity(torch.from_numpy(on_roll), torch.from_numpy(fr_roll), 0.5, 0.5, rule=rule)
+        out[rule + "_pitches"], out[rule + "_intervals"] = pch, itv
+        tt, ff = ref.decoding.notes_to_frames(pch, itv, (T_, P_))
+        out[rule + "_frame_counts"] = np.array([len(f) for f in ff])
+        out[rule + "_frame_bins"] = np.concatenate(ff) if len(ff) else np.array([])
+    pch, itv = ref.decoding.extract_notes_wo_velocity(torch.from_numpy(on_roll), torch.from_numpy(fr_roll), 0.95, 0.95)
+    out["none_pitches"], out["none_intervals"] = pch, itv              # thresholds nothing reaches: empty arrays
+    np.savez_compressed(os.path.join(OUT, "decoding.npz"), **out)
+
     for f in sorted(os.listdir(OUT)):
         print("%-28s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
 

@@ -74,7 +74,8 @@ def load_reference():
         ns.Spectrogram = importlib.import_module("model.Spectrogram")
         nna.Spectrogram = ns.Spectrogram
         sys.modules["nnAudio.Spectrogram"] = ns.Spectrogram
-        for name in ("constants", "utils", "VAT", "self_attention_VAT", "UNet_onset", "onset_frame_VAT", "Segmentation"):
+        for name in ("constants", "utils", "VAT", "self_attention_VAT", "UNet_onset", "onset_frame_VAT", "Segmentation",
+                     "decoding"):
             setattr(ns, name, importlib.import_module("model." + name))
     finally:
         # leave sys.modules as we found it: the product installs its own

@@ -748,3 +748,40 @@ extern "C" int rvb_normalise_framewise(const float* x, float* y, int n_seg, int 
   count_launch();
   return check_launch("normalise_framewise_kernel");
 }
+
+// ------------------------------------------------------------------ D1: note decoding (caller side)
+// model/decoding.py:4-55 extract_notes_wo_velocity: a note starts where the thresholded onset roll rises (and, rule1,
+// the frame roll is on) and ends at the first later frame where neither roll is on.  The reference walks every note
+// with a Python while loop and two .item() calls per frame.  Here one thread per pitch scans its column backwards
+// (rows are contiguous over the pitches: coalesced), carrying "first inactive frame at or after t".
+namespace rvb {
+__global__ void __launch_bounds__(128)
+note_offsets_kernel(const float* __restrict__ onsets, const float* __restrict__ frames, int T, int P, float onset_thr,
+                    float frame_thr, int rule1, uint8_t* __restrict__ start, int32_t* __restrict__ offset) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int next_inactive = T;
+  bool on_t = __ldg(onsets + (int64_t)(T - 1) * P + p) > onset_thr;
+  for (int t = T - 1; t >= 0; --t) {
+    const bool fr_t = __ldg(frames + (int64_t)t * P + p) > frame_thr;
+    const bool on_prev = (t > 0) ? (__ldg(onsets + (int64_t)(t - 1) * P + p) > onset_thr) : false;
+    if (!(on_t || fr_t)) next_inactive = t;
+    // uint8 arithmetic of the reference: onsets[t] - onsets[t-1] == 1  <=>  on now and off before (row 0: on now)
+    const bool rises = on_t && !on_prev;
+    start[(int64_t)t * P + p] = (rises && (!rule1 || fr_t)) ? 1 : 0;
+    offset[(int64_t)t * P + p] = next_inactive;
+    on_t = on_prev;
+  }
+}
+}  // namespace rvb
+
+extern "C" int rvb_note_offsets(const float* onsets, const float* frames, int n_frames, int n_pitches,
+                                float onset_threshold, float frame_threshold, int rule1, uint8_t* start,
+                                int32_t* offset, rvb_stream_t stream) {
+  RVB_REQUIRE(onsets && frames && start && offset, "rvb_note_offsets: null pointer");
+  RVB_REQUIRE(n_frames > 0 && n_pitches > 0, "rvb_note_offsets: bad shape");
+  rvb::note_offsets_kernel<<<(unsigned)((n_pitches + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      onsets, frames, n_frames, n_pitches, onset_threshold, frame_threshold, rule1, start, offset);
+  rvb::count_launch();
+  return rvb::check_launch("note_offsets_kernel");
+}
