@@ -62,12 +62,34 @@ def install_nnaudio():
 _ATTENTION_MODULES = ("model.self_attention_VAT", "model.UNet_onset", "model.onset_frame_VAT", "model.self_attention")
 
 
-def patch_reference(attention=False):
+def _rebind_everywhere(name, new, defining_module):
+    """Replace ``name`` in every loaded module that holds the reference's own object (scripts copy the names with
+    ``from model import *``, transcribe_files.py:4, so the defining module is not the only holder)."""
+    src = sys.modules.get(defining_module)
+    old = getattr(src, name, None) if src is not None else None
+    done = []
+    if old is None or old is new:
+        return done
+    for modname, mod in list(sys.modules.items()):
+        if mod is not None and getattr(mod, name, None) is old:
+            setattr(mod, name, new)
+            done.append((modname, name))
+    return done
+
+
+def patch_reference(attention=False, decoding=False):
     """Rebind VAT classes, Normalization and the Spectrogram module in every imported reference module.
     ``attention=True`` also rebinds ``MutliHeadAttention1D`` (the U-Net's sequence model) to the
     fused local-window attention: same parameters and outputs, no (B, L, C, W) unfolded tensors.
+    ``decoding=True`` rebinds ``extract_notes_wo_velocity`` / ``notes_to_frames`` (model/decoding.py) wherever the
+    reference's functions are held; they then expect the posteriors on the GPU, which is where ``UNet.transcribe``
+    leaves them.
     Returns the list of (module, name) pairs that were rebound."""
     done = []
+    if decoding:
+        from . import decoding as _dec
+        done += _rebind_everywhere("extract_notes_wo_velocity", _dec.extract_notes_wo_velocity, "model.decoding")
+        done += _rebind_everywhere("notes_to_frames", _dec.notes_to_frames, "model.decoding")
     if attention:
         from . import attention as _att
         for modname in _ATTENTION_MODULES:
@@ -101,6 +123,6 @@ def patch_reference(attention=False):
     return done
 
 
-def install(attention=False):
+def install(attention=False, decoding=False):
     install_nnaudio()
-    return patch_reference(attention=attention)
+    return patch_reference(attention=attention, decoding=decoding)

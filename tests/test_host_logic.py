@@ -240,6 +240,33 @@ def test_install_rebinds_the_reference_modules(monkeypatch):
     assert create_fourier_kernels(512, freq_scale="no")[0].shape == (257, 1, 512) and mel(16000, 512).shape == (128, 257)
 
 
+def test_install_opt_in_attention_and_decoding(monkeypatch):
+    """install(attention=True, decoding=True): the U-Net's sequence model and the note decoder are rebound too --
+    the decoder in every module that copied the reference's function with `from model import *`."""
+    import reconvat_b200.attention as A
+    import reconvat_b200.decoding as D
+    fake = {}
+    for name in ("model", "model.self_attention_VAT", "model.UNet_onset", "model.decoding", "some_script"):
+        fake[name] = types.ModuleType(name)
+        monkeypatch.setitem(sys.modules, name, fake[name])
+    ref_attention, ref_extract, ref_frames = object(), (lambda *a: None), (lambda *a: None)
+    fake["model.self_attention_VAT"].MutliHeadAttention1D = ref_attention
+    fake["model.UNet_onset"].MutliHeadAttention1D = ref_attention
+    for m in ("model.decoding", "model", "some_script"):
+        fake[m].extract_notes_wo_velocity = ref_extract
+        fake[m].notes_to_frames = ref_frames
+    for k in ("nnAudio", "nnAudio.Spectrogram", "nnAudio.utils", "nnAudio.librosa_functions"):
+        monkeypatch.delitem(sys.modules, k, raising=False)
+    assert R.install() is not None and fake["model.UNet_onset"].MutliHeadAttention1D is ref_attention   # opt-in only
+    done = R.install(attention=True, decoding=True)
+    assert fake["model.self_attention_VAT"].MutliHeadAttention1D is A.MutliHeadAttention1D
+    assert fake["model.UNet_onset"].MutliHeadAttention1D is A.MutliHeadAttention1D
+    for m in ("model.decoding", "model", "some_script"):
+        assert fake[m].extract_notes_wo_velocity is D.extract_notes_wo_velocity
+        assert fake[m].notes_to_frames is D.notes_to_frames
+    assert ("some_script", "extract_notes_wo_velocity") in done
+
+
 def test_vat_constructor_signatures_mirror_the_reference():
     V = R.VAT
     assert V.stepwise_VAT_vatpy(1e-6, 2, 1).epsilon == 2
