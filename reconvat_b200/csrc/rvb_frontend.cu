@@ -138,19 +138,46 @@ fold_split_kernel(const float* __restrict__ audio, int64_t audio_ld, int n_seg, 
 // |v 2^s| >= 2^-3, i.e. over 18 binades below the row maximum; under that it rounds on the fp16 subnormal grid,
 // an absolute 2^-25 (2^-39 of the row maximum).  row_scale_inv[frame] = 2^-s is applied by the GEMM epilogue.
 //
-// Block = kFoldWarps consecutive frames of one segment: their n_fft + (kFoldWarps-1) hop samples are staged once in
-// smem (each sample is used by n_fft/hop frames), then one WARP owns one frame: fold, warp-shuffle max, scale,
-// split, 8-byte stores -- no block barrier after the staging.  smem index = sample index + 3 so that the forward
-// run p[c+1..c+4] is one aligned LDS.128; the mirrored run p[N-c-4..N-c-1] straddles two aligned quads.
+// Block = kFoldWarps consecutive frames of one segment.  Their n_fft + (kFoldWarps-1) hop RAW samples (float or PCM16)
+// are staged in shared memory by ONE bulk async copy (cp.async.bulk + mbarrier: the TMA engine moves the 11-22 KB, no
+// thread holds staging registers); blocks are persistent and double-buffered, so the copy of the next group is in
+// flight while the warps fold this one.  Then one WARP owns one frame: fold, warp-shuffle max, scale, split, 8-byte
+// stores -- no block barrier between staging and use, one per group to recycle the buffer.  Groups that touch the
+// reflect padding (or are not 16-byte aligned) are filled by the threads instead.
+// smem index = sample index: the mirrored run p[N-c-4..N-c-1] is one aligned vector load, the forward run
+// p[c+1..c+4] straddles two.
 constexpr int kFoldWarps = 8;
 
-__device__ __forceinline__ void fold4(const float* __restrict__ fr /* fr[i + 3] = p[i] */, int n_fft, int half, int c,
+__device__ __forceinline__ uint32_t fs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool fs_mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
+template <typename TIn>
+__device__ __forceinline__ void fold4(const TIn* __restrict__ fr /* fr[i] = p[i] */, float gain, int n_fft, int half, int c,
                                       float (&e)[4], float (&o)[4]) {
-  const float4 x = *reinterpret_cast<const float4*>(fr + c + 4);                 // p[c+1 .. c+4]
-  const float4 g0 = *reinterpret_cast<const float4*>(fr + n_fft - c - 4);        // .w = p[N-c-4]
-  const float4 g1 = *reinterpret_cast<const float4*>(fr + n_fft - c);            // p[N-c-3], p[N-c-2], p[N-c-1], -
-  const float xs[4] = {x.x, x.y, x.z, x.w};
-  const float ys[4] = {g1.z, g1.y, g1.x, g0.w};                                  // p[N-n], n = c+1 .. c+4
+  float xs[4], ys[4];
+  if constexpr (sizeof(TIn) == 4) {
+    const float4 q0 = *reinterpret_cast<const float4*>(fr + c);                  // p[c .. c+3]
+    const float4 q1 = *reinterpret_cast<const float4*>(fr + c + 4);              // p[c+4 .. c+7]
+    const float4 m = *reinterpret_cast<const float4*>(fr + n_fft - c - 4);       // p[N-c-4 .. N-c-1]
+    xs[0] = q0.y; xs[1] = q0.z; xs[2] = q0.w; xs[3] = q1.x;                      // p[n], n = c+1 .. c+4
+    ys[0] = m.w; ys[1] = m.z; ys[2] = m.y; ys[3] = m.x;                          // p[N-n]
+  } else {
+    const short4 q0 = *reinterpret_cast<const short4*>(fr + c);
+    const short4 q1 = *reinterpret_cast<const short4*>(fr + c + 4);
+    const short4 m = *reinterpret_cast<const short4*>(fr + n_fft - c - 4);
+    xs[0] = (float)q0.y * gain; xs[1] = (float)q0.z * gain; xs[2] = (float)q0.w * gain; xs[3] = (float)q1.x * gain;
+    ys[0] = (float)m.w * gain; ys[1] = (float)m.z * gain; ys[2] = (float)m.y * gain; ys[3] = (float)m.x * gain;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     e[i] = xs[i] + ys[i];
@@ -166,89 +193,125 @@ __global__ void __launch_bounds__(kFoldWarps * 32)
 fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gain, int n_seg, int n_samples, int pad,
                       int mode, int n_fft, int hop, int n_frames, int groups_per_seg, __half* __restrict__ a_hi,
                       __half* __restrict__ a_lo, float* __restrict__ row_scale_inv, float* __restrict__ p0) {
-  extern __shared__ __align__(16) float span_s[];          // span_s[i + 3] = padded signal at start + i
+  extern __shared__ __align__(128) uint8_t fs_raw[];
+  __shared__ __align__(8) uint64_t fs_bar[2];
   const int half = n_fft >> 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n_rows = (int64_t)n_seg * n_frames;
   const int64_t padded = (mode == RVB_PAD_NONE) ? n_samples : (int64_t)n_samples + 2 * pad;
   const int off = (mode == RVB_PAD_NONE) ? 0 : pad;
   const int span = n_fft + (kFoldWarps - 1) * hop;
+  const int buf_elems = (span + 8 + 31) & ~31;             // + slack for the forward straddle of the last quad
   const int n_groups = n_seg * groups_per_seg;
-  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+  TIn* const buf0 = reinterpret_cast<TIn*>(fs_raw);
+  const uint32_t bar0 = fs_smem_u32(&fs_bar[0]);           // buffer / barrier `which` = base + which * stride
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // where a group's samples start, and whether one aligned bulk copy can fetch them
+  auto locate = [&](int grp, const TIn*& src) -> bool {
     const int b = grp / groups_per_seg;
     const int t0 = (grp - b * groups_per_seg) * kFoldWarps;
     const TIn* a = audio + (int64_t)b * audio_ld;
-    const int64_t start = (int64_t)t0 * hop;               // index of the group's first sample in the padded signal
-    const int64_t j0 = start - off;                        // ... and in the audio row
-    __syncthreads();                                       // the previous group's readers are done
-    const bool interior = j0 >= 0 && j0 + span <= n_samples && ((j0 & 3) == 0) && ((span & 3) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(a) & (4 * sizeof(TIn) - 1)) == 0);
-    if (interior) {
-      for (int i = threadIdx.x; i < (span >> 2); i += blockDim.x) {
-        float* d = span_s + 3 + 4 * i;
-        if constexpr (sizeof(TIn) == 4) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(a + j0) + i);
-          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        } else {
-          const short4 v = __ldg(reinterpret_cast<const short4*>(a + j0) + i);
-          d[0] = (float)v.x * gain; d[1] = (float)v.y * gain; d[2] = (float)v.z * gain; d[3] = (float)v.w * gain;
-        }
-      }
+    const int64_t j0 = (int64_t)t0 * hop - off;
+    src = a + j0;
+    return j0 >= 0 && j0 + span <= n_samples && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) &&
+           (((size_t)span * sizeof(TIn)) & 15u) == 0;
+  };
+  auto issue = [&](int grp, int which) {                     // thread 0 only
+    const TIn* src;
+    if (locate(grp, src)) {
+      const uint32_t bytes = (uint32_t)((size_t)span * sizeof(TIn));
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * which), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(fs_smem_u32(buf0 + which * buf_elems)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes),
+                     "r"(bar0 + 8 * which)
+                   : "memory");
+    }
+  };
+
+  uint32_t phases = 0u;                                    // bit `which` = parity the next wait on that barrier expects
+  if (threadIdx.x == 0 && (int)blockIdx.x < n_groups) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++it) {
+    const int cur = it & 1;
+    const int nxt = grp + gridDim.x;
+    if (threadIdx.x == 0 && nxt < n_groups) issue(nxt, cur ^ 1);   // its previous readers passed the barrier below
+    const int b = grp / groups_per_seg;
+    const int t0 = (grp - b * groups_per_seg) * kFoldWarps;
+    const TIn* src;
+    TIn* S = buf0 + cur * buf_elems;
+    if (locate(grp, src)) {
+      while (!fs_mbar_try_wait(bar0 + 8 * cur, (phases >> cur) & 1u)) {}
+      phases ^= 1u << cur;
     } else {
+      const TIn* a = audio + (int64_t)b * audio_ld;
+      const int64_t start = (int64_t)t0 * hop;
       for (int i = threadIdx.x; i < span; i += blockDim.x) {
         const int64_t pi = start + i;
-        float v = (pi < padded) ? padded_sample(a, pi, n_samples, pad, mode) : 0.f;
-        if constexpr (sizeof(TIn) != 4) v *= gain;
-        span_s[3 + i] = v;
+        TIn v = (TIn)0;
+        if (pi < padded) {
+          int64_t j = (mode == RVB_PAD_NONE) ? pi : pi - pad;
+          bool zero = false;
+          if (j < 0) { if (mode == RVB_PAD_REFLECT) j = -j; else zero = true; }
+          else if (j >= n_samples) { if (mode == RVB_PAD_REFLECT) j = 2 * (int64_t)(n_samples - 1) - j; else zero = true; }
+          if (!zero) v = __ldg(a + j);
+        }
+        S[i] = v;
+      }
+      __syncthreads();
+    }
+    const int t = t0 + warp;
+    if (t < n_frames) {                                      // warp-uniform
+      const TIn* fr = S + warp * hop;                        // fr[i] = p[i] of frame t
+      // two passes over the staged samples (max, then scale + split): keeping the 64 folded values of a lane in
+      // registers instead costs 95 registers, halves the occupancy and is slower
+      float ev[4], ov[4];
+      float mx = 0.f;
+      for (int c = lane << 2; c < half; c += 128) {
+        fold4<TIn>(fr, gain, n_fft, half, c, ev, ov);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(ev[i]), fabsf(ov[i])));   // fmaxf drops NaN: s stays finite
+      }
+      mx = warp_max(mx);
+      // floor(log2(mx)) from the exponent field (subnormal rows: treated as 2^-126); all-zero rows: s = 0
+      int s = 0;
+      if (mx > 0.f) {
+        int ex = (int)((__float_as_uint(mx) >> 23) & 0xff) - 127;
+        ex = max(-126, min(ex, 127));
+        s = max(-126, min(14 - ex, 126));
+      }
+      const float sc = __uint_as_float((unsigned)(s + 127) << 23);          // 2^s, exact
+      const int64_t f = (int64_t)b * n_frames + t;
+      uint2* e_hi = reinterpret_cast<uint2*>(a_hi + f * half);
+      uint2* e_lo = reinterpret_cast<uint2*>(a_lo + f * half);
+      uint2* o_hi = reinterpret_cast<uint2*>(a_hi + (n_rows + f) * half);
+      uint2* o_lo = reinterpret_cast<uint2*>(a_lo + (n_rows + f) * half);
+      // hi = fp16(v 2^s), lo = fp16(v 2^s - hi), two values per cvt.rn.f16x2
+      auto split4 = [sc](const float (&v)[4], uint2& hi, uint2& lo) {
+        const float a0 = v[0] * sc, a1 = v[1] * sc, a2 = v[2] * sc, a3 = v[3] * sc;
+        const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
+        hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+      };
+      for (int c = lane << 2; c < half; c += 128) {
+        fold4<TIn>(fr, gain, n_fft, half, c, ev, ov);
+        uint2 h, l;
+        split4(ev, h, l); e_hi[c >> 2] = h; e_lo[c >> 2] = l;
+        split4(ov, h, l); o_hi[c >> 2] = h; o_lo[c >> 2] = l;
+      }
+      if (lane == 0) {
+        row_scale_inv[f] = __uint_as_float((unsigned)(127 - s) << 23);      // 2^-s
+        if (p0) p0[f] = (float)fr[0] * (sizeof(TIn) == 4 ? 1.f : gain);
       }
     }
-    __syncthreads();
-    const int t = t0 + warp;
-    if (t >= n_frames) continue;                           // warp-uniform; the barriers above are reached by all
-    const float* fr = span_s + warp * hop;                 // fr[i + 3] = p[i] of frame t
-    // two passes over the staged samples (max, then scale + split): keeping the 64 folded values of a lane in
-    // registers instead costs 95 registers, halves the occupancy and is slower (64 us vs 52 us): the kernel is
-    // latency-bound on the staging loads, not instruction-bound
-    float ev[4], ov[4];
-    float mx = 0.f;
-    for (int c = lane << 2; c < half; c += 128) {
-      fold4(fr, n_fft, half, c, ev, ov);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(ev[i]), fabsf(ov[i])));   // fmaxf drops NaN: s stays finite
-    }
-    mx = warp_max(mx);
-    // floor(log2(mx)) from the exponent field (subnormal rows: treated as 2^-126); all-zero rows: s = 0
-    int s = 0;
-    if (mx > 0.f) {
-      int ex = (int)((__float_as_uint(mx) >> 23) & 0xff) - 127;
-      ex = max(-126, min(ex, 127));
-      s = max(-126, min(14 - ex, 126));
-    }
-    const float sc = __uint_as_float((unsigned)(s + 127) << 23);          // 2^s, exact
-    const int64_t f = (int64_t)b * n_frames + t;
-    uint2* e_hi = reinterpret_cast<uint2*>(a_hi + f * half);
-    uint2* e_lo = reinterpret_cast<uint2*>(a_lo + f * half);
-    uint2* o_hi = reinterpret_cast<uint2*>(a_hi + (n_rows + f) * half);
-    uint2* o_lo = reinterpret_cast<uint2*>(a_lo + (n_rows + f) * half);
-    // hi = fp16(v 2^s), lo = fp16(v 2^s - hi), two values per cvt.rn.f16x2
-    auto split4 = [sc](const float (&v)[4], uint2& hi, uint2& lo) {
-      const float a0 = v[0] * sc, a1 = v[1] * sc, a2 = v[2] * sc, a3 = v[3] * sc;
-      const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
-      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-      const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
-      hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
-      lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
-    };
-    for (int c = lane << 2; c < half; c += 128) {
-      fold4(fr, n_fft, half, c, ev, ov);
-      uint2 h, l;
-      split4(ev, h, l); e_hi[c >> 2] = h; e_lo[c >> 2] = l;
-      split4(ov, h, l); o_hi[c >> 2] = h; o_lo[c >> 2] = l;
-    }
-    if (lane == 0) {
-      row_scale_inv[f] = __uint_as_float((unsigned)(127 - s) << 23);      // 2^-s
-      if (p0) p0[f] = fr[3];
-    }
+    __syncthreads();                                         // everyone is done with bufs[cur]: it may be refilled
   }
 }
 
@@ -620,7 +683,8 @@ static int launch_fold_split_f16(const char* who, const TIn* audio, int64_t audi
   RVB_REQUIRE((int64_t)(n_frames - 1) * hop + n_fft <= padded, "%s: %d frames do not fit %lld samples", who, n_frames,
               (long long)padded);
   RVB_REQUIRE(hop % 4 == 0, "%s: hop %d must be a multiple of 4", who, hop);
-  const size_t smem = (size_t)(n_fft + (kFoldWarps - 1) * (int64_t)hop + 8) * sizeof(float);
+  const int64_t span = n_fft + (kFoldWarps - 1) * (int64_t)hop;
+  const size_t smem = 2 * (size_t)((span + 8 + 31) & ~31) * sizeof(TIn);     // two raw staging buffers
   RVB_REQUIRE(smem <= 200 * 1024, "%s: n_fft %d with hop %d needs %zu bytes of shared memory", who, n_fft, hop, smem);
   auto kernel = fold_split_f16_kernel<TIn>;
   if (smem > 48 * 1024)
@@ -628,7 +692,10 @@ static int launch_fold_split_f16(const char* who, const TIn* audio, int64_t audi
   const int groups_per_seg = (n_frames + kFoldWarps - 1) / kFoldWarps;
   const int64_t n_groups = (int64_t)n_seg * groups_per_seg;
   RVB_REQUIRE(n_groups < (1ll << 31), "%s: too many frames", who);
-  const int64_t cap = 148 * 8 * 4;
+  // persistent blocks: as many as stay resident (8 x 256 threads or the shared memory, whichever binds)
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  const int64_t cap = (int64_t)148 * per_sm;
   const unsigned grid = (unsigned)(n_groups < cap ? n_groups : cap);
   kernel<<<grid, kFoldWarps * 32, smem, (cudaStream_t)stream>>>(
       audio, audio_ld, gain, n_seg, n_samples, pad, pad_mode, n_fft, hop, n_frames, groups_per_seg,
