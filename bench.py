@@ -170,7 +170,9 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     import reconvat_b200 as R
+    from reconvat_b200 import parallel
     from reconvat_b200.pipeline import HotPathStep
+    numa_cores = parallel.bind_to_gpu_numa(local_rank) if world > 1 else 0     # before the pinned buffers exist
 
     B = args.batch
     pcm16 = args.input == "pcm16"
@@ -356,7 +358,9 @@ def run_ours(args, rank, local_rank, world):
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": B * SEG_SAMPLES * (2 if pcm16 else 4),
                 "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / n_done,
                 "api": "reconvat_b200.pipeline.HotPathStep.run_host (pinned host audio in, (vat_loss, r_norm) out; "
-                       "copy of batch i+1 overlapped with the kernels of batch i%s)" % ("" if args.no_graphs else "; graph replay")},
+                       "copy of batch i+1 overlapped with the kernels of batch i%s)%s"
+                       % ("" if args.no_graphs else "; graph replay",
+                          "; each rank bound to its GPU's %d NUMA-local cores" % numa_cores if numa_cores else "")},
         "gpu_launches": launches,
         "eager_ms_per_step": eager_ms_step,
         # an event pair around nothing costs this much on the stream; the per-kernel times below INCLUDE it (they

@@ -9,6 +9,26 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin the calling process to the CPU cores NVML reports as local to GPU ``device_index`` (same NUMA node / PCIe
+    root), BEFORE it allocates pinned host buffers: first touch then places them in local memory, and eight ranks
+    feeding eight GPUs stop sharing one socket's memory controllers.  Returns the number of cores, or 0 when NVML
+    is unavailable (nothing is changed then)."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def segment_shard(n_segments, rank, world_size):
     """Contiguous, balanced slice [start, stop) of the batch dimension owned by ``rank``."""
     if not (0 <= rank < world_size):
