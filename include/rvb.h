@@ -300,19 +300,19 @@ int rvb_vat_finalize_binwise(const float* g, const float* d, const float* x, flo
 /*
  * A1-A3  MutliHeadAttention1D.forward (model/self_attention_VAT.py:22-91; same class in model/UNet_onset.py:22,
  * model/self_attention.py:6) after the three nn.Linear projections, and its backward:
- *   energy[b,l,h,w] = sum_c q[b,l,h,c] (k[b,l+w-P,h,c] + rel[h,c,w]),  P = (W-1)/2, rows outside [0,L) are zero
+ *   energy[b,l,h,w] = sum_c q[b,l,h,c] k[b,l+w-P,h,c] + bias[b,l,h,w],  P = (W-1)/2, rows outside [0,L) are zero
  *   att = softmax_w(energy);  out[b,l,h,c] = sum_w att[b,l,h,w] v[b,l+w-P,h,c]
- * Replaces F.pad / unfold / + rel / (q*k).sum / softmax / (att*v).sum (:64-88) without materialising the
- * (B, L, C, W) unfolded k and v.  q, k, v, out, dq, dk, dv, dout: [B][L][G*D];  rel: [G*D][W];  relT: [G][W][D];
- * att, dE: [B][L][G][W].  W odd, <= 32;  D <= 512.
- *   rvb_local_attn_bwd_q   dE = softmax backward of (dout . v), dq = dE . (k + rel)
+ * Replaces F.pad / unfold / (q*k).sum / softmax / (att*v).sum (:64-88) without materialising the (B, L, C, W) unfolded
+ * k and v.  The relative-position term of :76 does not depend on k: bias = q . rel (and dq += dE . rel^T,
+ * d rel = q^T dE in the backward) are plain batched GEMMs left to the caller; bias may be NULL (position=False).
+ * q, k, v, out, dq, dk, dv, dout: [B][L][G*D];  att, dE, bias: [B][L][G][W].  W odd, <= 32;  D <= 508.
+ *   rvb_local_attn_bwd_q   dE = softmax backward of (dout . v), dq = dE . k
  *   rvb_local_attn_bwd_kv  dk[m] = sum_w dE[m-w+P][w] q[m-w+P],  dv[m] = sum_w att[m-w+P][w] dout[m-w+P]
- * (d rel = sum_{b,l} dE (x) q is a plain batched GEMM and is left to the caller.)
  */
-int rvb_local_attn_fwd(const float* q, const float* k, const float* v, const float* rel, int B, int L, int G, int D,
+int rvb_local_attn_fwd(const float* q, const float* k, const float* v, const float* bias, int B, int L, int G, int D,
                        int W, float* out, float* att, rvb_stream_t stream);
-int rvb_local_attn_bwd_q(const float* dout, const float* att, const float* k, const float* v, const float* relT, int B,
-                         int L, int G, int D, int W, float* dE, float* dq, rvb_stream_t stream);
+int rvb_local_attn_bwd_q(const float* dout, const float* att, const float* k, const float* v, int B, int L, int G,
+                         int D, int W, float* dE, float* dq, rvb_stream_t stream);
 int rvb_local_attn_bwd_kv(const float* q, const float* dout, const float* att, const float* dE, int B, int L, int G,
                           int D, int W, float* dk, float* dv, rvb_stream_t stream);
 

@@ -6,7 +6,8 @@ reference unfolds k and v to (B, L, C, W), 73 MB per 20 s segment each at C = 91
 
 Same constructor, parameters (``W_q``, ``W_k``, ``W_v``, ``rel`` -> state_dict compatible) and return values
 ``(out (B, L, C), attention (B, L, groups, W))``.  The three projections stay ``nn.Linear`` (cuBLAS); everything after
-them is one kernel forward and two backward (librvb.so, rvb_attention.cu); d rel is a batched GEMM (torch).
+them is one kernel forward and two backward (librvb.so, rvb_attention.cu); the relative-position terms (q . rel,
+dE . rel^T, d rel) do not involve k and are batched GEMMs (torch / cuBLAS).
 Scope cuts, raising: ``stride != 1`` and ``bias=True`` (no reference model uses them; with a bias the zero padding
 rows would become the bias vector).
 """
@@ -20,17 +21,21 @@ from . import _lib
 class _LocalAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, rel, groups, window):
-        for t in (q, k, v, rel):
+        for t in (q, k, v):
             if not t.is_cuda or t.dtype != torch.float32:
                 raise _lib.RvbError("reconvat_b200 attention needs CUDA float32 tensors (got %s, %s); there is no CPU "
                                     "path" % (t.device, t.dtype))
-        q, k, v, rel = q.contiguous(), k.contiguous(), v.contiguous(), rel.contiguous()
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         B, L, C = q.shape
         D = C // groups
+        bias = None
+        if rel is not None:
+            # q . rel does not involve k: one batched GEMM over the heads (cuBLAS), added to the energies in the kernel
+            bias = torch.einsum("nhc,hcw->nhw", q.view(B * L, groups, D), rel.view(groups, D, window)).contiguous()
         out = torch.empty_like(q)
         att = torch.empty((B, L, groups, window), dtype=torch.float32, device=q.device)
-        _lib.call("rvb_local_attn_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), rel.data_ptr(), B, L, groups, D, window,
-                  out.data_ptr(), att.data_ptr())
+        _lib.call("rvb_local_attn_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), None if bias is None else bias.data_ptr(),
+                  B, L, groups, D, window, out.data_ptr(), att.data_ptr())
         ctx.save_for_backward(q, k, v, rel, att)
         ctx.dims = (B, L, groups, D, window)
         ctx.mark_non_differentiable(att)          # the reference only plots it (model/self_attention_VAT.py:938)
@@ -41,15 +46,17 @@ class _LocalAttention(torch.autograd.Function):
         q, k, v, rel, att = ctx.saved_tensors
         B, L, G, D, W = ctx.dims
         dout = dout.contiguous()
-        relT = rel.view(G, D, W).transpose(1, 2).contiguous()            # [G][W][D]: coalesced for lanes <-> channels
         dE = torch.empty_like(att)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        _lib.call("rvb_local_attn_bwd_q", dout.data_ptr(), att.data_ptr(), k.data_ptr(), v.data_ptr(), relT.data_ptr(),
-                  B, L, G, D, W, dE.data_ptr(), dq.data_ptr())
+        _lib.call("rvb_local_attn_bwd_q", dout.data_ptr(), att.data_ptr(), k.data_ptr(), v.data_ptr(), B, L, G, D, W,
+                  dE.data_ptr(), dq.data_ptr())
         _lib.call("rvb_local_attn_bwd_kv", q.data_ptr(), dout.data_ptr(), att.data_ptr(), dE.data_ptr(), B, L, G, D, W,
                   dk.data_ptr(), dv.data_ptr())
-        # d rel[h,c,w] = sum_{b,l} q[b,l,h,c] dE[b,l,h,w]: one batched GEMM over the heads
-        drel = torch.einsum("nhc,nhw->hcw", q.view(B * L, G, D), dE.view(B * L, G, W)).reshape(G * D, W)
+        drel = None
+        if rel is not None:
+            dE2, rel3 = dE.view(B * L, G, W), rel.view(G, D, W)
+            dq = dq + torch.einsum("nhw,hcw->nhc", dE2, rel3).reshape(B, L, G * D)      # dE . rel^T
+            drel = torch.einsum("nhc,nhw->hcw", q.view(B * L, G, D), dE2).reshape(G * D, W)
         return dq, dk, dv, drel, None, None
 
 
@@ -80,9 +87,7 @@ class MutliHeadAttention1D(nn.Module):
 
     def forward(self, x):
         q, k, v = self.W_q(x), self.W_k(x), self.W_v(x)                  # zero padding rows project to zero (no bias)
-        rel = self.rel[0] if self.position else torch.zeros((self.out_features, self.kernel_size), dtype=q.dtype,
-                                                             device=q.device)
-        return _LocalAttention.apply(q, k, v, rel, self.groups, self.kernel_size)
+        return _LocalAttention.apply(q, k, v, self.rel[0] if self.position else None, self.groups, self.kernel_size)
 
     def reset_parameters(self):
         init.kaiming_normal_(self.W_k.weight, mode='fan_out', nonlinearity='relu')
