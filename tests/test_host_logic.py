@@ -202,13 +202,22 @@ def test_no_cpu_fallback_anywhere():
         R.VAT.UNet_VAT(1e-6, 2.0, 1, False)(None, torch.zeros(1, 1, 4, 229))
     with pytest.raises(ValueError):
         m(torch.zeros(1, 1, 1, 4096))
-    # the product never imports the oracle
+    from reconvat_b200 import attention, decoding
+    with pytest.raises(R._lib.RvbError, match="no CPU path"):
+        attention.MutliHeadAttention1D(8, 16, 3)(torch.zeros(1, 5, 8))
+    with pytest.raises(R._lib.RvbError, match="no CPU path"):
+        decoding.extract_notes_wo_velocity(torch.zeros(4, 88), torch.zeros(4, 88))
+    with pytest.raises(R._lib.RvbError, match="no CPU path"):
+        R.utils.Normalization("framewise").transform(torch.zeros(1, 4, 4))
+    # the product never imports the oracle (nor do the tools)
     import os
     pkg = os.path.dirname(R.__file__)
-    for root, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                assert "oracle" not in open(os.path.join(root, f)).read().replace("oracle/cpu_path", ""), f
+    for top in (pkg, os.path.join(os.path.dirname(pkg), "tools"), os.path.join(os.path.dirname(pkg), "include")):
+        for root, _, files in os.walk(top):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    text = open(os.path.join(root, f)).read().replace("oracle/cpu_path", "").replace("oracle/vat.py", "")
+                    assert "oracle" not in text, os.path.join(root, f)
 
 
 def test_install_rebinds_the_reference_modules(monkeypatch):
