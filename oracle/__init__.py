@@ -21,6 +21,10 @@ frontend.py          reflect pad -> STFT contraction -> power -> Mel -> log ->
                      model/utils.py, model/self_attention_VAT.py:1100-1104)
 vat.py               the VAT perturbation loop, closed form and autograd form
                      (model/self_attention_VAT.py:101-255 and siblings)
+attention.py         MutliHeadAttention1D.forward (model/self_attention_VAT.py:61-88)
+decoding.py          extract_notes_wo_velocity / notes_to_frames (model/decoding.py)
+cpu_path.py          the whole step as the reference's ATen op sequence: the timed
+                     CPU baseline of bench.py
 reference_loader.py  imports the *unmodified* reference modules (build
                      container only; /root/reference is absent on the GPU box)
 make_golden.py       regenerates tests/golden/*.npz from the reference

@@ -4,8 +4,11 @@ the classes on the hot path: ``STFT`` (model/Spectrogram.py:22-316) and ``MelSpe
 (``wsin``, ``wcos``, ``window_mask``, ``mel_basis`` -- checkpoint compatible, transcribe_files.py:71
 loads strictly), same output shapes and formats; the arithmetic runs in librvb.so:
 
-    pad + hop-block + tf32 split  ->  tcgen05 3xTF32 contraction (+ magnitude / power / complex /
-    phase epilogue)  ->  banded Mel  [-> log -> per-segment min/max -> normalise, fused extension]
+    MelSpectrogram:  pad + frame + fold + block-scaled fp16 hi/lo split (float or PCM16 in)  ->  folded 3xFP16
+                     contraction on tcgen05 CTA pairs with |.|^2 and the banded Mel projection in its epilogue
+                     [-> log -> per-segment min/max -> normalise -> transpose: ``normalised_log_mel``]
+    STFT:            the same contraction with a magnitude / complex / phase epilogue (+ a scalar Nyquist-bin kernel)
+    other bases:     3xTF32 folded / unfolded contractions, separate banded Mel kernel (see ``_spectrum``)
 
 Scope cuts, all raising instead of silently computing something else: ``trainable*=True`` (no
 config of the reference uses it), ``STFT.inverse`` / the other nnAudio transforms,
@@ -70,7 +73,7 @@ class STFT(nn.Module):
         self._tables = None          # device operand planes, rebuilt lazily from wsin/wcos
         self._tables_key = None
         if verbose:
-            print("STFT kernels created (reconvat_b200, tcgen05 3xTF32 contraction)")
+            print("STFT kernels created (reconvat_b200, tcgen05 split-precision contraction)")
 
     # -- device tables ------------------------------------------------------------------
     def _device_tables(self):
