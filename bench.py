@@ -381,7 +381,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="segments per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=8, help="segments per CPU-baseline step")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=100,
+                    help="steps of the CPU baseline (8 segments each: ~10 s of host work at the default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--input", default="pcm16", choices=["pcm16", "f32"],
                     help="audio format handed to the front-end: the dataset's PCM int16 (default) or float32")
