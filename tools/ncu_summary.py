@@ -2,6 +2,7 @@
 
   python tools/ncu_summary.py rep   <file.ncu-rep> <out.txt>      key counters of every kernel in a --set full report
   python tools/ncu_summary.py list  <launches.csv> <out.txt>      per-kernel device time and share of one step
+                                                                  (or of the whole list when it holds no hot-path step)
 """
 import collections
 import csv
@@ -47,9 +48,10 @@ def launch_list(path, out):
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
     seq = [(r[ki], float(r[vi].replace(",", ""))) for r in rows[hi + 1:] if len(r) > vi and r[vi] not in ("", "Metric Value")
            and r[0] != ""]
+    # one steady-state step = from the last-but-one framing kernel to the last one; any other launch list (e.g.
+    # tools/attn_bench.py) is summarised whole
     idx = [i for i, (n, _) in enumerate(seq) if "pad_split" in n or "fold_split" in n]
-    s, e = idx[-2], idx[-1]
-    step = seq[s:e]
+    step = seq[idx[-2]:idx[-1]] if len(idx) >= 2 else seq
     tot = sum(v for _, v in step)
     agg = collections.OrderedDict()
     for n, v in step:
