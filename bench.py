@@ -33,12 +33,14 @@ HBM_BYTES_PER_SEG = {
     "rvb_mel_project": 1020 * 640 * 4 + N4,
     "rvb_logmel_minmax": N4,
     "rvb_logmel_transpose": 2 * N4,
+    "rvb_logmel_normalise": 2 * N4,                        # fused min/max + normalise + transpose: R mel, W spec
     "rvb_normalise": 2 * N4,
     "rvb_vat_perturb": 3 * N4,
     "rvb_bce_grad": 3 * P4,
     "rvb_div_grad": 3 * P4,                                # what the VAT modules call (kind = BCE here)
     "rvb_div_mean": 2 * P4,
     "rvb_vat_finalize": 6 * N4,
+    "rvb_vat_finalize_stats": 6 * N4,
     "rvb_bce_mean": 2 * P4,
 }
 
@@ -227,10 +229,7 @@ def run_ours(args, rank, local_rank, world):
     ms_step = ms_total / args.steps
     value = world * B * SEG_SECONDS / (ms_step * 1e-3)
 
-    # per-kernel durations: the same K steps launched eagerly with CUDA events around every entry point, on the
-    # launching stream (events cannot be read back from inside a replayed graph)
-    kernel_names = ["rvb_stft_gemm", "rvb_stft_gemm_folded", "rvb_stft_gemm_folded_f16",
-                    "rvb_stft_mel_folded_f16"] + list(HBM_BYTES_PER_SEG)
+    # eager launches of the same K steps (host-bound: what the CUDA graphs remove)
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
@@ -240,27 +239,48 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     step.vat_loss.check()
     eager_ms_step = ev2.elapsed_time(ev3) / args.steps
-    # Eager launches are host-bound (eager_ms_step > ms_step): an event pair around a kernel would then also time the
-    # idle gap before its launch arrives.  A spin kernel holds the stream while the host enqueues k_steps steps, so
-    # the events bracket back-to-back kernels.
-    k_steps = max(1, min(args.steps, 16))
-    log = R._lib.record_events(kernel_names)
-    torch.cuda._sleep(int(k_steps * max(eager_ms_step, 0.3) * 3e-3 * 1.9e9))      # 3x the eager enqueue time
-    for i in range(k_steps):
-        step(dev_audio[i % n_rot])
-    # an event pair around nothing, queued behind the same spin: what the pair itself costs on the stream
-    empty = []
-    for _ in range(64):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        e1.record()
-        empty.append((e0, e1))
+
+    # per-kernel durations: every entry point of the step re-launched `reps` times BACK TO BACK between one CUDA-event
+    # pair on the launching stream.  The calls are recorded from n_rot eager steps, each run inside its own memory
+    # pool, so that step i's tensors (inputs, intermediates, outputs) have their own addresses: consecutive launches
+    # rotate over n_rot working sets (> L2) and every launch streams from / to HBM.  A spin kernel holds the stream
+    # while the host enqueues, so the events bracket kernels, not launch gaps; no per-launch event overhead.
+    recorded, pools = [], []
+    for i in range(n_rot):
+        pool = torch.cuda.MemPool()
+        pools.append(pool)                                   # keeps the recorded addresses reserved
+        with torch.cuda.use_mem_pool(pool):
+            log = []
+            R._lib.record_calls(log)
+            try:
+                step(dev_audio[i])
+            finally:
+                R._lib.record_calls(None)
+        recorded.append(log)
     barrier()
-    R._lib.record_events(None)
     step.vat_loss.check()
-    ev_overhead_ms = statistics.median(a.elapsed_time(b) for a, b in empty)
-    kms = {n: [s.elapsed_time(e) for s, e in v] for n, v in log.items() if v}
-    kavg = {n: sum(v) / len(v) for n, v in kms.items()}
+    names = [n for n, _ in recorded[0]]
+    reps = max(n_rot * 3, 20)
+    kavg, kcalls = {}, {}
+    for idx, name in enumerate(names):
+        if name in kavg:                                     # an entry point called twice per step: first use only
+            kcalls[name] += 1
+            continue
+        kcalls[name] = 1
+        calls = [recorded[i][idx][1] for i in range(n_rot)]
+        for c in calls:                                      # warm-up (and first-launch attribute calls)
+            R._lib.raw_call(name, c)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(int(reps * 12e-6 * 1.9e9))         # ~12 us of spin per launch the host has to enqueue
+        e0.record()
+        for r in range(reps):
+            R._lib.raw_call(name, calls[r % n_rot])
+        e1.record()
+        torch.cuda.synchronize()
+        kavg[name] = e0.elapsed_time(e1) / reps
+    barrier()
+    del pools
 
     # ---------------- end to end from pinned host memory ("e2e") ----------------
     results = torch.zeros((args.steps, 2), dtype=torch.float32).pin_memory()
@@ -316,9 +336,8 @@ def run_ours(args, rank, local_rank, world):
     hbm = {}
     for n, per_seg in HBM_BYTES_PER_SEG.items():
         if n in kavg:
-            calls_per_step = len(kms[n]) / k_steps
             gbs = B * per_seg / (kavg[n] * 1e-3) / 1e9
-            hbm[n] = {"ms_per_launch": kavg[n], "launches_per_step": calls_per_step, "achieved_gbs": gbs,
+            hbm[n] = {"ms_per_launch": kavg[n], "launches_per_step": kcalls[n], "achieved_gbs": gbs,
                       "frac_of_measured_hbm": gbs / peaks["hbm"]}
 
     cpu = None
@@ -363,9 +382,9 @@ def run_ours(args, rank, local_rank, world):
                           "; each rank bound to its GPU's %d NUMA-local cores" % numa_cores if numa_cores else "")},
         "gpu_launches": launches,
         "eager_ms_per_step": eager_ms_step,
-        # an event pair around nothing costs this much on the stream; the per-kernel times below INCLUDE it (they
-        # are upper bounds: the ncu durations in profiles/ are tighter, e.g. 11 us for vat_perturb)
-        "event_pair_overhead_us": ev_overhead_ms * 1e3,
+        "kernel_timing": "each entry point re-launched %d times back to back between one CUDA-event pair, rotating over "
+                         "%d recorded working sets (> L2); the contraction's entry point includes its 19 MB memset of "
+                         "the Mel accumulator" % (reps, n_rot),
         "roofline": roofline,
         "hbm_kernels": hbm,
         "cpu_baseline": cpu,

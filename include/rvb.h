@@ -180,6 +180,17 @@ int rvb_logmel_minmax(const float* mel, int n_seg, int64_t n_per_seg, float log_
                       rvb_stream_t stream);
 int rvb_logmel_transpose(const float* mel, int n_seg, int n_mels, int n_frames, float log_offset,
                          const uint32_t* minmax, float* out, rvb_stream_t stream);
+/*
+ * K2m + K3m in one pass: out[b][t][m] = (log(mel[b][m][t] + log_offset) - min_b) / (max_b - min_b).  A thread-block
+ * cluster of 8 CTAs owns one segment: its log-Mel values stay in shared memory between the min/max reduction
+ * (exchanged through distributed shared memory) and the normalised, transposed write -- mel is read once.
+ * Replaces `torch.log(spec + 1e-5)`, Normalization('imagewise').transform and `.transpose(-1,-2)`
+ * (model/self_attention_VAT.py:1102-1104, model/utils.py:93-100).  Bit-identical to rvb_logmel_minmax +
+ * rvb_logmel_transpose, which it falls back to when a segment does not fit the cluster's shared memory
+ * (or RVB_NO_NORM_FUSION=1).  minmax: uint32 [n_seg][2], receives the keys (required).
+ */
+int rvb_logmel_normalise(const float* mel, int n_seg, int n_mels, int n_frames, float log_offset, uint32_t* minmax,
+                         float* out, rvb_stream_t stream);
 
 #define RVB_LAYOUT_BINS_MAJOR 0 /* out[b][m][t]  -- what MelSpectrogram.forward returns (:460) */
 #define RVB_LAYOUT_TIME_MAJOR 1 /* out[b][t][m]  -- after `.transpose(-1,-2)` (self_attention_VAT.py:1104) */
@@ -260,6 +271,20 @@ int rvb_vat_finalize(const float* g, const float* d, const float* x, float* r_ad
  */
 int rvb_vat_direct(const float* d, const float* x, float* r_adv, float* x_adv, float* d_hat, int64_t n_rows,
                    int row_len, float eps, int do_clamp, int32_t* status_flag, rvb_stream_t stream);
+
+/*
+ * V3 / V3b with the step's by-products folded in: the same kernels, but the per-block NaN / Inf bits and sum |dhat|
+ * go to a workspace and the last block to finish WRITES status_flag (no zeroing by the caller) and
+ *   dhat_abs_mean = mean |dhat|     -- the `r_norm.abs().mean()` that run_on_batch logs after every VAT call
+ *                                      (model/self_attention_VAT.py:1149-1150), summed in a fixed order in double.
+ * g == NULL selects V3b (n_power == 0).  workspace: rvb_vat_stats_workspace_bytes(n_rows) bytes, zeroed once by the
+ * caller (self-cleaning); one workspace per stream that may run the kernel concurrently.
+ */
+int64_t rvb_vat_stats_workspace_bytes(int64_t n_rows);
+int rvb_vat_finalize_stats(const float* g, const float* d, const float* x, float* r_adv, float* x_adv, float* d_hat,
+                           int64_t n_rows, int row_len, float xi, float eps, float scale, int do_clamp,
+                           int32_t* status_flag, float* dhat_abs_mean, void* workspace, int64_t workspace_bytes,
+                           rvb_stream_t stream);
 
 /*
  * V4  loss = mean( -(y*max(log p,-100) + (1-y)*max(log1p(-p),-100)) ), deterministic two-level sum.

@@ -393,13 +393,19 @@ class MelSpectrogram(nn.Module):
             B, n_mels = mel.shape[0], mel.shape[1]
             out = torch.empty((B, n_frames, n_mels), dtype=torch.float32, device=x.device)
             minmax = None
-            if normalise:
+            if normalise and reduce_minmax is None:
+                # one pass: a cluster per segment keeps the log-Mel values in shared memory across the min/max
                 minmax = torch.empty((B, 2), dtype=torch.int32, device=x.device)
-                _lib.call("rvb_logmel_minmax", mel.data_ptr(), B, n_mels * n_frames, float(log_offset), minmax.data_ptr())
-                if reduce_minmax is not None:
-                    minmax = reduce_minmax(minmax)
-            _lib.call("rvb_logmel_transpose", mel.data_ptr(), B, n_mels, n_frames, float(log_offset),
-                      None if minmax is None else minmax.data_ptr(), out.data_ptr())
+                _lib.call("rvb_logmel_normalise", mel.data_ptr(), B, n_mels, n_frames, float(log_offset),
+                          minmax.data_ptr(), out.data_ptr())
+            else:
+                if normalise:
+                    minmax = torch.empty((B, 2), dtype=torch.int32, device=x.device)
+                    _lib.call("rvb_logmel_minmax", mel.data_ptr(), B, n_mels * n_frames, float(log_offset),
+                              minmax.data_ptr())
+                    minmax = reduce_minmax(minmax)                  # e.g. all-reduce over the ranks of a sharded file
+                _lib.call("rvb_logmel_transpose", mel.data_ptr(), B, n_mels, n_frames, float(log_offset),
+                          None if minmax is None else minmax.data_ptr(), out.data_ptr())
             out = out.unsqueeze(1) if channel_dim else out
             return (out, minmax) if return_minmax else out
         power, n_frames, bands = self._power_spectrogram(x, prepadded)

@@ -39,7 +39,7 @@ from . import _lib
 
 __all__ = ["stepwise_VAT_vatpy", "stepwise_VAT", "UNet_VAT", "onset_frame_VAT", "UNet_VAT_onset",
            "stepwise_VAT_onf", "stepwise_VAT_frame_stack", "Seg_VAT", "bce_mean", "binary_kl_div", "mse_mean",
-           "l2_normalize"]
+           "l2_normalize", "Scratch"]
 
 
 def _rows(x):
@@ -98,11 +98,35 @@ def _denom(p, kind):
     return p.shape[0] if kind == _lib.DIV_BKL else p.numel()
 
 
-def _divergence(p, y, kind):
+def _divergence(p, y, kind, workspace=None):
     if p.shape != y.shape:
         raise ValueError("Using a target size ({}) that is different to the input size ({}) is deprecated. "
                          "Please ensure they have the same size.".format(y.shape, p.shape))
-    return _DivMean.apply(p, y.detach(), _workspace(p.device), kind, _denom(p, kind))
+    ws = _workspace(p.device) if workspace is None else workspace
+    return _DivMean.apply(p, y.detach(), ws, kind, _denom(p, kind))
+
+
+class Scratch:
+    """Reduction workspaces of ONE in-flight VAT call chain.  The divergence and the finalisation kernels finish with
+    a last-block reduction over a small workspace (ticket + per-block partials); two calls that may run concurrently
+    -- CUDA graphs replayed on different streams -- must not share it.  ``vat.scratch = Scratch(device)`` also
+    switches the module to ``rvb_vat_finalize_stats``: the NaN flag is written (not OR-ed into a zeroed one) and
+    ``vat.last_r_norm_mean`` receives mean |d_hat| (the ``r_norm.abs().mean()`` of model/self_attention_VAT.py:1149)
+    without another pass over d_hat."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.div = torch.zeros(_lib.BCE_WORKSPACE_FLOATS, dtype=torch.float32, device=self.device)
+        self._stats = None
+
+    def stats(self, n_rows):
+        need = _lib.vat_stats_workspace_bytes(n_rows)
+        if self._stats is None or self._stats.numel() * 4 < need:
+            if torch.cuda.is_current_stream_capturing():
+                raise _lib.RvbError("reconvat_b200 VAT: the Scratch of a captured step must be sized before the capture "
+                                    "(run the step once eagerly with the same scratch)")
+            self._stats = torch.zeros((need + 3) // 4, dtype=torch.int32, device=self.device)
+        return self._stats
 
 
 def bce_mean(p, y):
@@ -162,6 +186,8 @@ class _VATCore(nn.Module):
         self._pending = None       # (pinned host copy of the NaN flag, event) of the previous eager call
         self._host_flag = None     # persistent pinned int32 (allocated once: no per-call cudaHostAlloc)
         self.last_flag = None      # device flag of the latest call (what a captured CUDA graph leaves behind)
+        self.scratch = None        # a Scratch: private reduction workspaces + fused flag / mean |d_hat| (see Scratch)
+        self.last_r_norm_mean = None   # device scalar, mean |d_hat| of the latest call (only with a Scratch)
         if KL_Div and len(self._heads) > 1:
             raise NotImplementedError("reconvat_b200 VAT: KL_Div=True with two heads -- the reference itself fails "
                                       "there (NameError: y_pred, model/UNet_onset.py:133-134)")
@@ -205,7 +231,14 @@ class _VATCore(nn.Module):
             y_ref = [y.detach() for y in self._model_outputs(model, x)]   # labels, no grad (…:163-164)
 
         d = torch.randn_like(x)                                           # same global Philox stream (…:172)
-        flag = torch.zeros((), dtype=torch.int32, device=x.device)
+        sc = self.scratch if not self.binwise else None
+        div_ws = None if self.scratch is None else self.scratch.div
+        if sc is not None:
+            flag = torch.empty((), dtype=torch.int32, device=x.device)    # written by the kernel's last block
+            r_norm_mean = torch.empty((), dtype=torch.float32, device=x.device)
+            stats_ws = sc.stats(n_rows)
+        else:
+            flag = torch.zeros((), dtype=torch.int32, device=x.device)
         r_adv = torch.empty_like(x)
         x_adv2 = torch.empty_like(x)
         d_hat = torch.empty_like(x)
@@ -228,6 +261,11 @@ class _VATCore(nn.Module):
                 _lib.call("rvb_vat_finalize_binwise", g.contiguous().data_ptr(), d.data_ptr(), x.data_ptr(),
                           r_adv.data_ptr(), x_adv2.data_ptr(), d_hat.data_ptr(), x.numel(), float(self.XI),
                           float(self.epsilon), float(self._scale), int(self._clamp), flag.data_ptr())
+            elif sc is not None:
+                _lib.call("rvb_vat_finalize_stats", g.contiguous().data_ptr(), d.data_ptr(), x.data_ptr(),
+                          r_adv.data_ptr(), x_adv2.data_ptr(), d_hat.data_ptr(), n_rows, row_len, float(self.XI),
+                          float(self.epsilon), float(self._scale), int(self._clamp), flag.data_ptr(),
+                          r_norm_mean.data_ptr(), stats_ws.data_ptr(), stats_ws.numel() * 4)
             else:
                 _lib.call("rvb_vat_finalize", g.contiguous().data_ptr(), d.data_ptr(), x.data_ptr(), r_adv.data_ptr(),
                           x_adv2.data_ptr(), d_hat.data_ptr(), n_rows, row_len, float(self.XI), float(self.epsilon),
@@ -236,11 +274,16 @@ class _VATCore(nn.Module):
             _lib.call("rvb_vat_finalize_binwise", None, d.data_ptr(), x.data_ptr(), r_adv.data_ptr(), x_adv2.data_ptr(),
                       d_hat.data_ptr(), x.numel(), float(self.XI), float(self.epsilon), 1.0, int(self._clamp),
                       flag.data_ptr())
+        elif sc is not None:
+            _lib.call("rvb_vat_finalize_stats", None, d.data_ptr(), x.data_ptr(), r_adv.data_ptr(), x_adv2.data_ptr(),
+                      d_hat.data_ptr(), n_rows, row_len, 0.0, float(self.epsilon), 1.0, int(self._clamp),
+                      flag.data_ptr(), r_norm_mean.data_ptr(), stats_ws.data_ptr(), stats_ws.numel() * 4)
         else:
             _lib.call("rvb_vat_direct", d.data_ptr(), x.data_ptr(), r_adv.data_ptr(), x_adv2.data_ptr(),
                       d_hat.data_ptr(), n_rows, row_len, float(self.epsilon), int(self._clamp), flag.data_ptr())
 
         self.last_flag = flag
+        self.last_r_norm_mean = r_norm_mean if sc is not None else None
         if not torch.cuda.is_current_stream_capturing():
             # inside a CUDA-graph capture there is no host round trip: the owner of the graph tests last_flag
             if self._host_flag is None:
@@ -253,7 +296,7 @@ class _VATCore(nn.Module):
                 self.check()
 
         y_pred = self._model_outputs(model, x_adv2)                       # graph to the parameters kept (…:195)
-        losses = [_divergence(p, y, k) for p, y, k in zip(y_pred, y_ref, kinds)]   # (…:200)
+        losses = [_divergence(p, y, k, div_ws) for p, y, k in zip(y_pred, y_ref, kinds)]   # (…:200)
         if self._dict_loss is not None:
             vat_loss = dict(zip(self._dict_loss, losses))
         else:

@@ -30,6 +30,7 @@ SIGNATURES = {
                                 _i32, _c_p, _c_p],
     "rvb_logmel_minmax": [_c_p, _i32, _i64, _f32, _c_p, _c_p],
     "rvb_logmel_transpose": [_c_p, _i32, _i32, _i32, _f32, _c_p, _c_p, _c_p],
+    "rvb_logmel_normalise": [_c_p, _i32, _i32, _i32, _f32, _c_p, _c_p, _c_p],
     "rvb_stft_bin_folded_f16": [_c_p, _c_p, _c_p, _i32, _i32, _i32, _c_p, _c_p, _c_p, _f32, _i32, _i32, _f32, _c_p, _i32,
                                 _c_p],
     "rvb_stft_bin": [_c_p, _c_p, _i32, _i32, _i32, _i32, _c_p, _c_p, _i32, _i32, _i32, _f32, _c_p, _i32, _c_p],
@@ -49,6 +50,8 @@ SIGNATURES = {
     "rvb_local_attn_bwd_kv": [_c_p, _c_p, _c_p, _c_p, _i32, _i32, _i32, _i32, _i32, _c_p, _c_p, _c_p],
     "rvb_note_offsets": [_c_p, _c_p, _i32, _i32, _f32, _f32, _i32, _c_p, _c_p, _c_p],
     "rvb_vat_direct": [_c_p, _c_p, _c_p, _c_p, _c_p, _i64, _i32, _f32, _i32, _c_p, _c_p],
+    "rvb_vat_finalize_stats": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i64, _i32, _f32, _f32, _f32, _i32, _c_p, _c_p, _c_p,
+                               _i64, _c_p],
     "rvb_bce_mean": [_c_p, _c_p, _i64, _c_p, _c_p, _c_p],
 }
 ABI_VERSION = 1
@@ -80,6 +83,8 @@ def load():
     lib.rvb_abi_version.restype = ctypes.c_int
     lib.rvb_last_error.restype = ctypes.c_char_p
     lib.rvb_launch_count.restype = ctypes.c_int64
+    lib.rvb_vat_stats_workspace_bytes.restype = ctypes.c_int64
+    lib.rvb_vat_stats_workspace_bytes.argtypes = [_i64]
     if lib.rvb_abi_version() != ABI_VERSION:
         raise ImportError("reconvat_b200: librvb.so has ABI %d, the Python side expects %d -- rebuild"
                           % (lib.rvb_abi_version(), ABI_VERSION))
@@ -94,6 +99,10 @@ def load():
 def launch_count():
     """Kernels launched by librvb.so in this process so far (bench.py reports the delta)."""
     return int(load().rvb_launch_count())
+
+
+def vat_stats_workspace_bytes(n_rows):
+    return int(load().rvb_vat_stats_workspace_bytes(int(n_rows)))
 
 
 def _stream():
@@ -124,9 +133,29 @@ def record_events(names):
     return _event_log
 
 
+# Optional call recording (bench.py re-launches single entry points back to back): [(name, args), ...]
+_call_log = None
+
+
+def record_calls(log):
+    """Append (name, args) of every entry-point call to ``log`` (a list) until ``record_calls(None)``.  The arguments
+    are raw pointers: whoever replays them with :func:`raw_call` keeps the memory they point to alive."""
+    global _call_log
+    _call_log = log
+
+
+def raw_call(name, args):
+    """Re-issue a recorded call on the current stream."""
+    rc = getattr(load(), name)(*args, _stream())
+    if rc != 0:
+        raise RvbError("%s failed (%d): %s" % (name, rc, load().rvb_last_error().decode("utf-8", "replace")))
+
+
 def call(name, *args):
     """Invoke an entry point on the current PyTorch stream; raise RvbError on a non-zero status."""
     lib = load()
+    if _call_log is not None:
+        _call_log.append((name, args))
     log = _event_log.get(name) if _event_log is not None else None
     if log is not None:
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

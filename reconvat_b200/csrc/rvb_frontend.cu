@@ -3,6 +3,8 @@
 //   K1b single frequency bin in fp32       (Nyquist bin of model/Spectrogram.py:219-220)
 //   K2 banded Mel + log + min/max          (model/Spectrogram.py:460, self_attention_VAT.py:1102, utils.py:96-97)
 //   K3 imagewise normalise                 (model/utils.py:100)
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "rvb_common.cuh"
@@ -552,6 +554,104 @@ logmel_transpose_kernel(const float* __restrict__ mel, int n_mels, int n_frames,
   }
 }
 
+// ------------------------------------------------------------------ K2m + K3m in ONE pass: a cluster per segment
+// The imagewise min/max (model/utils.py:96-97) is the only step of the front-end that couples a whole segment, and it
+// is why the two kernels above read the Mel spectrogram twice.  Here a thread-block CLUSTER owns one segment: CTA r
+// keeps frames [r*fpc, (r+1)*fpc) of log(mel + offset) in shared memory, already transposed into output order
+// (229 x 80 floats = 73 KB per CTA for a 640-frame segment on 8 CTAs), the CTAs exchange their min/max keys through
+// distributed shared memory (one remote store per peer + one cluster barrier), and every CTA then normalises its slab
+// on the way out.  mel is read once, out is written once: 2 x N4 bytes per segment instead of 3 x N4, one launch
+// instead of two (+ a memset).  Same fast_log, same keys, same (v - min) / (max - min) as the two-pass kernels:
+// bit-identical results.
+constexpr int kNormCluster = 8;              // portable cluster size
+constexpr int kNormThreads = 512;
+constexpr int kNormRows = 4;                 // band rows per warp and trip ...
+constexpr int kNormChunks = 4;               // ... times 32-frame chunks: a CTA holds at most 128 frames
+
+__global__ void __launch_bounds__(kNormThreads)
+logmel_normalise_cluster_kernel(const float* __restrict__ mel, int n_mels, int n_frames, int frames_per_cta, int pitch,
+                                float log_offset, uint32_t* __restrict__ minmax_out, float* __restrict__ out) {
+  extern __shared__ __align__(16) float slab[];            // [frames_per_cta][pitch], pitch odd: conflict-free
+  __shared__ unsigned red[2][kNormThreads / 32];
+  __shared__ unsigned peer_keys[2][kNormCluster];          // [min|max][rank], written by the peers (DSMEM)
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const int b = blockIdx.x / kNormCluster;
+  const int t0 = (int)rank * frames_per_cta;
+  const int nt = max(0, min(frames_per_cta, n_frames - t0));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kNormThreads / 32;
+
+  // pass 1: one warp-wide load = 32 consecutive frames of one band (128 bytes).  A warp takes kNormRows band rows per
+  // trip and all of their (up to kNormChunks) 32-frame chunks: 16 independent loads in flight, no index division.
+  const float* src = mel + (int64_t)b * n_mels * n_frames + t0;
+  float vmax = -INFINITY, vmin = INFINITY;
+  bool seen_nan = false;
+  for (int m0 = warp; m0 < n_mels; m0 += kWarps * kNormRows) {
+    float v[kNormRows][kNormChunks];
+#pragma unroll
+    for (int u = 0; u < kNormRows; ++u) {
+      const int m = m0 + u * kWarps;
+      const float* row = src + (int64_t)m * n_frames + lane;
+#pragma unroll
+      for (int c = 0; c < kNormChunks; ++c) v[u][c] = (m < n_mels && c * 32 + lane < nt) ? __ldg(row + c * 32) : 1.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kNormRows; ++u) {
+      const int m = m0 + u * kWarps;
+#pragma unroll
+      for (int c = 0; c < kNormChunks; ++c) {
+        const int t = c * 32 + lane;
+        if (m < n_mels && t < nt) {
+          const float w = fast_log(v[u][c] + log_offset);
+          vmax = fmaxf(vmax, w); vmin = fminf(vmin, w); seen_nan |= isnan(w);
+          slab[t * pitch + m] = w;                         // bank = (t * pitch + m) % 32, lanes <-> t, pitch odd
+        }
+      }
+    }
+  }
+  // block -> cluster reduction of the order-preserving keys (NaN = largest key on both sides, as torch.max / min)
+  unsigned kmax = warp_max_u32(seen_nan ? 0xffffffffu : f2key(vmax));
+  unsigned kmin = warp_max_u32(seen_nan ? 0xffffffffu : f2key(-vmin));
+  if (lane == 0) { red[0][warp] = kmin; red[1][warp] = kmax; }
+  __syncthreads();
+  if (threadIdx.x < kNormCluster) {                        // thread r hands this CTA's keys to peer r
+    unsigned k0 = 0, k1 = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < kWarps; ++w2) { k0 = max(k0, red[0][w2]); k1 = max(k1, red[1][w2]); }
+    unsigned* peer = cluster.map_shared_rank(&peer_keys[0][0], threadIdx.x);
+    peer[rank] = k0;
+    peer[kNormCluster + rank] = k1;
+  }
+  cluster.sync();                                          // release / acquire: the remote stores are visible
+  unsigned gmin = 0, gmax = 0;
+#pragma unroll
+  for (int r = 0; r < kNormCluster; ++r) { gmin = max(gmin, peer_keys[0][r]); gmax = max(gmax, peer_keys[1][r]); }
+  if (minmax_out && rank == 0 && threadIdx.x == 0) { minmax_out[2 * b] = gmin; minmax_out[2 * b + 1] = gmax; }
+  float mn, mx;
+  if (gmin == 0xffffffffu || gmax == 0xffffffffu) mn = mx = __int_as_float(0x7fc00000);
+  else { mn = -key2f(gmin); mx = key2f(gmax); }
+  const float den = mx - mn;                               // (x_max - x_min), utils.py:100
+
+  // pass 2: the slab is one contiguous run of the output
+  float* dst = out + ((int64_t)b * n_frames + t0) * n_mels;
+  const int n = nt * n_mels;
+  if (pitch == n_mels && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    for (int i = threadIdx.x; i < (n >> 2); i += kNormThreads) {
+      float4 q = reinterpret_cast<const float4*>(slab)[i];
+      q.x = (q.x - mn) / den; q.y = (q.y - mn) / den; q.z = (q.z - mn) / den; q.w = (q.w - mn) / den;
+      reinterpret_cast<float4*>(dst)[i] = q;
+    }
+    for (int i = (n & ~3) + threadIdx.x; i < n; i += kNormThreads) dst[i] = (slab[i] - mn) / den;
+  } else {
+    for (int i = threadIdx.x; i < n; i += kNormThreads) {
+      const int t = i / n_mels, m = i - t * n_mels;
+      dst[i] = (slab[t * pitch + m] - mn) / den;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ K3
 __device__ __forceinline__ void decode_minmax(const uint32_t* __restrict__ minmax, int b, float& mn, float& mx) {
   const unsigned kmin = __ldg(minmax + 2 * b), kmax = __ldg(minmax + 2 * b + 1);
@@ -778,6 +878,41 @@ extern "C" int rvb_logmel_transpose(const float* mel, int n_seg, int n_mels, int
   logmel_transpose_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(mel, n_mels, n_frames, log_offset, minmax, out);
   count_launch();
   return check_launch("logmel_transpose_kernel");
+}
+
+extern "C" int rvb_logmel_normalise(const float* mel, int n_seg, int n_mels, int n_frames, float log_offset,
+                                    uint32_t* minmax, float* out, rvb_stream_t stream) {
+  RVB_REQUIRE(mel && minmax && out, "rvb_logmel_normalise: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_mels > 0 && n_frames > 0 && n_seg <= 65535 && log_offset >= 0.f,
+              "rvb_logmel_normalise: bad argument");
+  // frames per CTA: a multiple of 4 keeps every slab of the output 16-byte aligned
+  const int fpc = (((n_frames + kNormCluster - 1) / kNormCluster) + 3) & ~3;
+  const int pitch = n_mels | 1;
+  const size_t smem = (size_t)fpc * pitch * sizeof(float);
+  static const bool no_fusion = [] { const char* e = getenv("RVB_NO_NORM_FUSION"); return e && *e && *e != '0'; }();
+  if (smem > 200 * 1024 || fpc > 32 * kNormChunks || no_fusion) {   // a segment that does not fit 8 SMs: two passes
+    int rc = rvb_logmel_minmax(mel, n_seg, (int64_t)n_mels * n_frames, log_offset, minmax, stream);
+    if (rc != RVB_OK) return rc;
+    return rvb_logmel_transpose(mel, n_seg, n_mels, n_frames, log_offset, minmax, out, stream);
+  }
+  if (smem > 48 * 1024)
+    RVB_CUDA(cudaFuncSetAttribute(logmel_normalise_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)n_seg * kNormCluster);
+  cfg.blockDim = dim3(kNormThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kNormCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RVB_CUDA(cudaLaunchKernelEx(&cfg, logmel_normalise_cluster_kernel, mel, n_mels, n_frames, fpc, pitch, log_offset,
+                              minmax, out));
+  count_launch();
+  return check_launch("logmel_normalise_cluster_kernel");
 }
 
 extern "C" int rvb_minmax(const float* x, int n_seg, int64_t n_per_seg, uint32_t* minmax, rvb_stream_t stream) {

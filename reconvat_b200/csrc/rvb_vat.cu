@@ -66,20 +66,31 @@ vat_perturb_kernel(const float* __restrict__ x, const float* __restrict__ d, flo
 }
 
 // ---- V3: power-iteration backward + finalisation ----------------------------------------
+// Per-row result of the finalisation: NaN / Inf bits of r_adv and sum |dhat| (the `r_norm.abs().mean()` the reference's
+// run_on_batch logs, model/self_attention_VAT.py:1149).
+struct RowStat {
+  unsigned bad;
+  float abs_sum;
+};
+
 template <int NPL>
-__device__ __forceinline__ void finalize_row(RowRegs<NPL>& dp /* in: d' ; out: dhat' */, RowRegs<NPL>& rx,
-                                             float* __restrict__ r_adv, float* __restrict__ x_adv,
-                                             float* __restrict__ d_hat, int64_t off, int row_len, int lane,
-                                             float eps, int do_clamp, int32_t* status_flag) {
+__device__ __forceinline__ RowStat finalize_row(RowRegs<NPL>& dp /* in: d' ; out: dhat' */, RowRegs<NPL>& rx,
+                                                float* __restrict__ r_adv, float* __restrict__ x_adv,
+                                                float* __restrict__ d_hat, int64_t off, int row_len, int lane,
+                                                float eps, int do_clamp) {
   const float n2 = sqrtf(row_sumsq(dp));
   RowRegs<NPL> rr;
   unsigned bad = 0;
+  float asum = 0.f;
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
     const bool in = lane + i * kWarp < row_len;
     float dh = dp.v[i] / n2;                  // _l2_normalize(d)
     float r = eps * dh;                       // r_adv
-    if (in) bad |= (isnan(r) ? 1u : 0u) | (isinf(r) ? 2u : 0u);
+    if (in) {
+      bad |= (isnan(r) ? 1u : 0u) | (isinf(r) ? 2u : 0u);
+      asum += fabsf(dh);
+    }
     float s = rx.v[i] + r;
     dp.v[i] = dh;
     rr.v[i] = r;
@@ -88,8 +99,64 @@ __device__ __forceinline__ void finalize_row(RowRegs<NPL>& dp /* in: d' ; out: d
   store_row(rr, r_adv + off, row_len, lane);
   store_row(rx, x_adv + off, row_len, lane);
   store_row(dp, d_hat + off, row_len, lane);
-  bad = __reduce_or_sync(kFull, bad);
-  if (bad && lane == 0 && status_flag) atomicOr(status_flag, (int)bad);
+  RowStat st;
+  st.bad = __reduce_or_sync(kFull, bad);
+  st.abs_sum = warp_sum(asum);
+  return st;
+}
+
+// Where the per-row results go.  Plain flavour: OR the bits into a flag the caller zeroed.  Stats flavour (workspace
+// != nullptr): per-block partials, and the LAST block to finish adds them in a fixed order (double), WRITES the flag
+// and the mean |dhat| -- nobody has to zero the flag, and the logged metric costs no extra pass over d_hat.
+// workspace: [n_blocks] float partial sums | [n_blocks] uint32 bits | uint32 ticket (zero once; self-cleaning).
+__device__ __forceinline__ void finalize_block_stats(RowStat st, bool valid, int32_t* __restrict__ status_flag,
+                                                     float* __restrict__ dhat_abs_mean, float* __restrict__ workspace,
+                                                     double n_elems) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (!workspace) {
+    if (valid && st.bad && lane == 0 && status_flag) atomicOr(status_flag, (int)st.bad);
+    return;
+  }
+  __shared__ float s_abs[kRowsPerBlock];
+  __shared__ unsigned s_bad[kRowsPerBlock];
+  __shared__ bool is_last;
+  if (lane == 0) { s_abs[warp] = valid ? st.abs_sum : 0.f; s_bad[warp] = valid ? st.bad : 0u; }
+  __syncthreads();
+  float* part = workspace;
+  unsigned* bits = reinterpret_cast<unsigned*>(workspace) + gridDim.x;
+  unsigned* ticket = bits + gridDim.x;
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    unsigned bd = 0;
+#pragma unroll
+    for (int w = 0; w < kRowsPerBlock; ++w) { a += s_abs[w]; bd |= s_bad[w]; }
+    part[blockIdx.x] = a;
+    bits[blockIdx.x] = bd;
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double s = 0.0;
+  unsigned bd = 0;
+  for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) { s += (double)__ldcg(part + j); bd |= __ldcg(bits + j); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+  bd = __reduce_or_sync(kFull, bd);
+  __shared__ double d_part[kRowsPerBlock];
+  __syncthreads();                                         // s_bad is reused below
+  if (lane == 0) { d_part[warp] = s; s_bad[warp] = bd; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    unsigned all = 0;
+#pragma unroll
+    for (int w = 0; w < kRowsPerBlock; ++w) { tot += d_part[w]; all |= s_bad[w]; }
+    if (dhat_abs_mean) *dhat_abs_mean = (float)(tot / n_elems);
+    if (status_flag) *status_flag = (int)all;
+    *ticket = 0u;
+  }
 }
 
 template <int NPL>
@@ -97,10 +164,12 @@ __global__ void __launch_bounds__(kRowsPerBlock* kWarp)
 vat_finalize_kernel(const float* __restrict__ g, const float* __restrict__ d, const float* __restrict__ x,
                     float* __restrict__ r_adv, float* __restrict__ x_adv, float* __restrict__ d_hat,
                     int64_t n_rows, int row_len, float xi, float eps, float scale, int do_clamp,
-                    int32_t* status_flag) {
+                    int32_t* status_flag, float* __restrict__ dhat_abs_mean, float* __restrict__ workspace) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
+  const bool valid = row < n_rows;                         // warp-uniform
+  RowStat st = {0u, 0.f};
+  if (valid) {
   const int64_t off = row * row_len;
   RowRegs<NPL> rd, rx, rg;
   load_row(rd, d + off, row_len, lane);
@@ -124,22 +193,28 @@ vat_finalize_kernel(const float* __restrict__ g, const float* __restrict__ d, co
   const float c = dot / (n * n * n);
 #pragma unroll
   for (int i = 0; i < NPL; ++i) rd.v[i] = (rg.v[i] / n - rd.v[i] * c) * scale;   // d.grad * scale
-  finalize_row(rd, rx, r_adv, x_adv, d_hat, off, row_len, lane, eps, do_clamp, status_flag);
+  st = finalize_row(rd, rx, r_adv, x_adv, d_hat, off, row_len, lane, eps, do_clamp);
+  }
+  finalize_block_stats(st, valid, status_flag, dhat_abs_mean, workspace, (double)n_rows * row_len);
 }
 
 template <int NPL>
 __global__ void __launch_bounds__(kRowsPerBlock* kWarp)
 vat_direct_kernel(const float* __restrict__ d, const float* __restrict__ x, float* __restrict__ r_adv,
                   float* __restrict__ x_adv, float* __restrict__ d_hat, int64_t n_rows, int row_len, float eps,
-                  int do_clamp, int32_t* status_flag) {
+                  int do_clamp, int32_t* status_flag, float* __restrict__ dhat_abs_mean, float* __restrict__ workspace) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
-  const int64_t off = row * row_len;
-  RowRegs<NPL> rd, rx;
-  load_row(rd, d + off, row_len, lane);
-  load_row(rx, x + off, row_len, lane);
-  finalize_row(rd, rx, r_adv, x_adv, d_hat, off, row_len, lane, eps, do_clamp, status_flag);
+  const bool valid = row < n_rows;                         // warp-uniform
+  RowStat st = {0u, 0.f};
+  if (valid) {
+    const int64_t off = row * row_len;
+    RowRegs<NPL> rd, rx;
+    load_row(rd, d + off, row_len, lane);
+    load_row(rx, x + off, row_len, lane);
+    st = finalize_row(rd, rx, r_adv, x_adv, d_hat, off, row_len, lane, eps, do_clamp);
+  }
+  finalize_block_stats(st, valid, status_flag, dhat_abs_mean, workspace, (double)n_rows * row_len);
 }
 
 // ---- binwise=True flavour of _l2_normalize: d / (|d| + 1e-8), no row coupling (self_attention_VAT.py:242-243) ----
@@ -345,34 +420,59 @@ extern "C" int rvb_vat_perturb(const float* x, const float* d, float* x_adv, int
   });
 }
 
-extern "C" int rvb_vat_finalize(const float* g, const float* d, const float* x, float* r_adv, float* x_adv,
-                                float* d_hat, int64_t n_rows, int row_len, float xi, float eps, float scale,
-                                int do_clamp, int32_t* status_flag, rvb_stream_t stream) {
-  RVB_REQUIRE(g && d && x && r_adv && x_adv && d_hat, "rvb_vat_finalize: null pointer");
-  RVB_REQUIRE(n_rows >= 0 && row_len > 0, "rvb_vat_finalize: bad shape (%lld, %d)", (long long)n_rows, row_len);
+static int launch_vat_finalize(const char* who, const float* g, const float* d, const float* x, float* r_adv,
+                               float* x_adv, float* d_hat, int64_t n_rows, int row_len, float xi, float eps, float scale,
+                               int do_clamp, int32_t* status_flag, float* dhat_abs_mean, float* workspace,
+                               rvb_stream_t stream) {
+  RVB_REQUIRE(d && x && r_adv && x_adv && d_hat, "%s: null pointer", who);
+  RVB_REQUIRE(n_rows >= 0 && row_len > 0, "%s: bad shape (%lld, %d)", who, (long long)n_rows, row_len);
+  RVB_REQUIRE(n_rows < (int64_t)kRowsPerBlock * 0x7fffffff, "%s: too many rows", who);
   if (n_rows == 0) return RVB_OK;
   const unsigned grid = (unsigned)((n_rows + kRowsPerBlock - 1) / kRowsPerBlock);
   return dispatch_npl(row_len, [&](auto npl) {
-    vat_finalize_kernel<decltype(npl)::value><<<grid, kRowsPerBlock * kWarp, 0, (cudaStream_t)stream>>>(
-        g, d, x, r_adv, x_adv, d_hat, n_rows, row_len, xi, eps, scale, do_clamp, status_flag);
+    constexpr int N = decltype(npl)::value;
+    if (g)
+      vat_finalize_kernel<N><<<grid, kRowsPerBlock * kWarp, 0, (cudaStream_t)stream>>>(
+          g, d, x, r_adv, x_adv, d_hat, n_rows, row_len, xi, eps, scale, do_clamp, status_flag, dhat_abs_mean, workspace);
+    else
+      vat_direct_kernel<N><<<grid, kRowsPerBlock * kWarp, 0, (cudaStream_t)stream>>>(
+          d, x, r_adv, x_adv, d_hat, n_rows, row_len, eps, do_clamp, status_flag, dhat_abs_mean, workspace);
     count_launch();
-    return check_launch("vat_finalize_kernel");
+    return check_launch(g ? "vat_finalize_kernel" : "vat_direct_kernel");
   });
+}
+
+extern "C" int rvb_vat_finalize(const float* g, const float* d, const float* x, float* r_adv, float* x_adv,
+                                float* d_hat, int64_t n_rows, int row_len, float xi, float eps, float scale,
+                                int do_clamp, int32_t* status_flag, rvb_stream_t stream) {
+  RVB_REQUIRE(g, "rvb_vat_finalize: null pointer");
+  return launch_vat_finalize("rvb_vat_finalize", g, d, x, r_adv, x_adv, d_hat, n_rows, row_len, xi, eps, scale, do_clamp,
+                             status_flag, nullptr, nullptr, stream);
 }
 
 extern "C" int rvb_vat_direct(const float* d, const float* x, float* r_adv, float* x_adv, float* d_hat,
                               int64_t n_rows, int row_len, float eps, int do_clamp, int32_t* status_flag,
                               rvb_stream_t stream) {
-  RVB_REQUIRE(d && x && r_adv && x_adv && d_hat, "rvb_vat_direct: null pointer");
-  RVB_REQUIRE(n_rows >= 0 && row_len > 0, "rvb_vat_direct: bad shape (%lld, %d)", (long long)n_rows, row_len);
-  if (n_rows == 0) return RVB_OK;
-  const unsigned grid = (unsigned)((n_rows + kRowsPerBlock - 1) / kRowsPerBlock);
-  return dispatch_npl(row_len, [&](auto npl) {
-    vat_direct_kernel<decltype(npl)::value><<<grid, kRowsPerBlock * kWarp, 0, (cudaStream_t)stream>>>(
-        d, x, r_adv, x_adv, d_hat, n_rows, row_len, eps, do_clamp, status_flag);
-    count_launch();
-    return check_launch("vat_direct_kernel");
-  });
+  return launch_vat_finalize("rvb_vat_direct", nullptr, d, x, r_adv, x_adv, d_hat, n_rows, row_len, 0.f, eps, 1.f,
+                             do_clamp, status_flag, nullptr, nullptr, stream);
+}
+
+extern "C" int64_t rvb_vat_stats_workspace_bytes(int64_t n_rows) {
+  const int64_t blocks = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
+  return (2 * blocks + 1) * 4;
+}
+
+extern "C" int rvb_vat_finalize_stats(const float* g, const float* d, const float* x, float* r_adv, float* x_adv,
+                                      float* d_hat, int64_t n_rows, int row_len, float xi, float eps, float scale,
+                                      int do_clamp, int32_t* status_flag, float* dhat_abs_mean, void* workspace,
+                                      int64_t workspace_bytes, rvb_stream_t stream) {
+  RVB_REQUIRE(status_flag && dhat_abs_mean && workspace, "rvb_vat_finalize_stats: null pointer");
+  RVB_REQUIRE(n_rows > 0, "rvb_vat_finalize_stats: empty input (the reference's mean of nothing is NaN)");
+  RVB_REQUIRE(workspace_bytes >= rvb_vat_stats_workspace_bytes(n_rows),
+              "rvb_vat_finalize_stats: workspace of %lld bytes, %lld needed", (long long)workspace_bytes,
+              (long long)rvb_vat_stats_workspace_bytes(n_rows));
+  return launch_vat_finalize("rvb_vat_finalize_stats", g, d, x, r_adv, x_adv, d_hat, n_rows, row_len, xi, eps, scale,
+                             do_clamp, status_flag, dhat_abs_mean, static_cast<float*>(workspace), stream);
 }
 
 static unsigned flat_grid(int64_t n, int per_thread) {

@@ -24,6 +24,9 @@ class HotPathStep:
         self.model = model
         self.spectrogram = Spectrogram.MelSpectrogram(**MEL_KW).to(self.device)
         self.vat_loss = (vat_cls or VAT.UNet_VAT)(xi, eps, 1, False)
+        # private reduction workspaces + the fused NaN flag / mean |d_hat| (VAT.Scratch); every captured graph gets
+        # its own, because graphs replayed on different streams run the last-block reductions concurrently
+        self._eager_scratch = VAT.Scratch(self.device)
         self._copy_stream = None
         self._graphs = []              # [(graph, input buffer, outputs, device flag)]
         self._lanes = []               # side streams of replay_many
@@ -32,8 +35,13 @@ class HotPathStep:
     def __call__(self, audio):
         """audio: (B, L) float32 on the device.  Returns (vat_loss, r_norm_mean, spec, r_adv)."""
         spec = self.spectrogram.normalised_log_mel(audio)
+        self._n_rows = spec.numel() // spec.shape[-1]
+        if self.vat_loss.scratch is None:
+            self.vat_loss.scratch = self._eager_scratch
         vat_loss, r_adv, r_norm = self.vat_loss(self.model, spec)
-        return vat_loss, r_norm.abs().mean(), spec, r_adv
+        # r_norm.abs().mean() (model/self_attention_VAT.py:1149) comes out of the finalisation kernel
+        r_norm_mean = self.vat_loss.last_r_norm_mean
+        return vat_loss, (r_norm.abs().mean() if r_norm_mean is None else r_norm_mean), spec, r_adv
 
     # -- CUDA graphs ------------------------------------------------------------------------
     def capture(self, buffers, warmup=3):
@@ -49,20 +57,26 @@ class HotPathStep:
         torch.cuda.synchronize(self.device)
         self.vat_loss.check()
         self._graphs = []
-        for buf in buffers:
-            g = torch.cuda.CUDAGraph()
-            n0 = _lib.launch_count()
-            with torch.cuda.graph(g):
-                out = self(buf)
-                packed = torch.stack((out[0].detach(), out[1]))      # (vat_loss, r_norm_mean): one 8-byte result
-            self.kernels_per_graph = _lib.launch_count() - n0
-            self._graphs.append((g, buf, out + (packed,), self.vat_loss.last_flag))
+        try:
+            for buf in buffers:
+                scratch = VAT.Scratch(self.device)
+                scratch.stats(self._n_rows)               # sized before the capture (row count of the warm-up step)
+                self.vat_loss.scratch = scratch
+                g = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
+                with torch.cuda.graph(g):
+                    out = self(buf)
+                    out = (out[0].detach(),) + out[1:]
+                self.kernels_per_graph = _lib.launch_count() - n0
+                self._graphs.append((g, buf, out, self.vat_loss.last_flag, scratch))
+        finally:
+            self.vat_loss.scratch = self._eager_scratch
         return len(self._graphs)
 
     def replay(self, i):
-        """Re-launch graph i on the current stream.  Returns (vat_loss, r_norm_mean, spec, r_adv, packed): static
-        tensors that the next replay of the same graph overwrites."""
-        g, _, out, _ = self._graphs[i]
+        """Re-launch graph i on the current stream.  Returns (vat_loss, r_norm_mean, spec, r_adv): static tensors that
+        the next replay of the same graph overwrites."""
+        g, out = self._graphs[i][0], self._graphs[i][2]
         g.replay()
         return out
 
@@ -86,8 +100,8 @@ class HotPathStep:
         """NaN/Inf assertion of the reference (model/self_attention_VAT.py:189-190) for the eager path and for every
         captured graph (synchronises)."""
         self.vat_loss.check()
-        for _, _, _, flag in self._graphs:
-            self.vat_loss.check(flag)
+        for entry in self._graphs:
+            self.vat_loss.check(entry[3])
 
     # -- host-fed loop ----------------------------------------------------------------------
     def run_host(self, host_batches, results_host, use_graphs=True):
@@ -128,12 +142,9 @@ class HotPathStep:
             if nxt is not None:
                 stage(slot ^ 1, nxt)
             main.wait_event(ready[slot])
-            if graphs:
-                packed = self.replay(slot)[4]
-            else:
-                vat_loss, r_norm, _, _ = self(bufs[slot])
-                packed = torch.stack((vat_loss.detach(), r_norm))
-            results_host[i].copy_(packed, non_blocking=True)
+            vat_loss, r_norm = (self.replay(slot) if graphs else self(bufs[slot]))[:2]
+            results_host[i, 0].copy_(vat_loss.detach(), non_blocking=True)     # two 4-byte reads, no packing kernel
+            results_host[i, 1].copy_(r_norm, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(main)
             freed[slot] = ev

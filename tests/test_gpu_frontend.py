@@ -316,6 +316,36 @@ def test_mel_variants_golden(R, dev, golden, tag, kw):
     assert relerr(np.log(out + 1e-5), np.log(g[tag] + 1e-5)) < LOGMEL_TOL
 
 
+@pytest.mark.parametrize("B,M,T", [(3, 229, 640), (32, 229, 640), (2, 229, 37), (2, 128, 100), (1, 229, 1), (2, 80, 3001)])
+def test_fused_normalise_is_bit_identical_to_the_two_pass_kernels(R, dev, B, M, T):
+    """rvb_logmel_normalise (one cluster per segment, min/max exchanged through distributed shared memory) against
+    rvb_logmel_minmax + rvb_logmel_transpose: same keys, same output bits -- including ragged frame counts, an even
+    band count (padded smem pitch), a NaN segment and a constant segment (0/0 = NaN, as model/utils.py:100)."""
+    torch.manual_seed(B * 1000 + T)
+    mel = (torch.rand(B, M, T, device=dev) ** 4) * 50.0
+    if B >= 2:
+        mel[1] = 0.25                                             # constant image -> NaN everywhere
+    if B >= 3:
+        mel[2, M // 2, T // 3] = float("nan")                    # torch.max / min propagate NaN
+    want = torch.empty(B, T, M, device=dev)
+    keys = torch.empty(B, 2, dtype=torch.int32, device=dev)
+    R._lib.call("rvb_logmel_minmax", mel.data_ptr(), B, M * T, 1e-5, keys.data_ptr())
+    R._lib.call("rvb_logmel_transpose", mel.data_ptr(), B, M, T, 1e-5, keys.data_ptr(), want.data_ptr())
+    got = torch.full((B, T, M), -7.0, device=dev)
+    keys2 = torch.zeros(B, 2, dtype=torch.int32, device=dev)
+    R._lib.call("rvb_logmel_normalise", mel.data_ptr(), B, M, T, 1e-5, keys2.data_ptr(), got.data_ptr())
+    assert torch.equal(keys, keys2)
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32))           # bit pattern, NaNs included
+    ref = torch.log(mel[0] + 1e-5)
+    ref = ((ref - ref.min()) / (ref.max() - ref.min())).T
+    assert float((got[0] - ref).abs().max()) < 2e-6
+    assert float(got[0].min()) == 0.0 and float(got[0].max()) == 1.0
+    if B >= 2:
+        assert torch.isnan(got[1]).all()
+    if B >= 3:
+        assert torch.isnan(got[2]).all()
+
+
 def test_normalization_golden_bit_exact(R, dev, golden):
     g = golden["normalization"]
     out = R.utils.Normalization("imagewise").transform(torch.from_numpy(g["x"]).to(dev)).cpu().numpy()

@@ -92,6 +92,75 @@ def test_finalize_flags_nan_like_the_reference_assert(R, dev):
     assert torch.isnan(r[0, 0, 2]).all() and not torch.isnan(r[0, 0, :2]).any()
 
 
+@pytest.mark.parametrize("B,T,F", [(2, 24, 229), (32, 640, 229), (1, 3, 88), (3, 7, 400)])
+@pytest.mark.parametrize("have_g", [True, False])
+def test_finalize_stats_flavour(R, dev, B, T, F, have_g):
+    """rvb_vat_finalize_stats: same r_adv / x_adv / d_hat bits as rvb_vat_finalize (rvb_vat_direct when g is NULL),
+    the flag is WRITTEN by the last block (no zeroing, repeated calls on one workspace), and dhat_abs_mean is the
+    reference's r_norm.abs().mean() (model/self_attention_VAT.py:1149) of the returned d_hat."""
+    x = _spec_like(B, T, F, 6).to(dev)
+    torch.manual_seed(7)
+    d = torch.randn_like(x)
+    g = torch.randn_like(x) * 1e-7
+    n_rows = B * T
+    outs = [[torch.empty_like(x) for _ in range(3)] for _ in range(2)]
+    flag0 = torch.zeros((), dtype=torch.int32, device=dev)
+    if have_g:
+        R._lib.call("rvb_vat_finalize", g.data_ptr(), d.data_ptr(), x.data_ptr(), *[o.data_ptr() for o in outs[0]],
+                    n_rows, F, 1e-6, 2.0, 1e10, 1, flag0.data_ptr())
+    else:
+        R._lib.call("rvb_vat_direct", d.data_ptr(), x.data_ptr(), *[o.data_ptr() for o in outs[0]], n_rows, F, 2.0, 1,
+                    flag0.data_ptr())
+    ws = torch.zeros((R._lib.vat_stats_workspace_bytes(n_rows) + 3) // 4, dtype=torch.int32, device=dev)
+    mean = torch.full((), -1.0, device=dev)
+    flag = torch.full((), 77, dtype=torch.int32, device=dev)          # garbage: the kernel must overwrite it
+    vals = set()
+    for rep in range(3):
+        R._lib.call("rvb_vat_finalize_stats", g.data_ptr() if have_g else None, d.data_ptr(), x.data_ptr(),
+                    *[o.data_ptr() for o in outs[1]], n_rows, F, 1e-6, 2.0, 1e10, 1, flag.data_ptr(), mean.data_ptr(),
+                    ws.data_ptr(), ws.numel() * 4)
+        assert flag.item() == 0 == flag0.item()
+        vals.add(mean.item())
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    assert len(vals) == 1                                             # fixed-order sum: run-to-run identical
+    want = outs[0][2].double().abs().mean().item()
+    assert abs(vals.pop() - want) <= 2e-7 * want
+    # NaN row: flag bit 0 is set, then cleared again by the next clean call on the same workspace
+    if have_g:
+        g2 = g.clone(); g2[0, 0, 1] = 0.0
+        R._lib.call("rvb_vat_finalize_stats", g2.data_ptr(), d.data_ptr(), x.data_ptr(), *[o.data_ptr() for o in outs[1]],
+                    n_rows, F, 1e-6, 2.0, 1e10, 1, flag.data_ptr(), mean.data_ptr(), ws.data_ptr(), ws.numel() * 4)
+        assert flag.item() & 1 and torch.isnan(mean)
+        R._lib.call("rvb_vat_finalize_stats", g.data_ptr(), d.data_ptr(), x.data_ptr(), *[o.data_ptr() for o in outs[1]],
+                    n_rows, F, 1e-6, 2.0, 1e10, 1, flag.data_ptr(), mean.data_ptr(), ws.data_ptr(), ws.numel() * 4)
+        assert flag.item() == 0
+    with pytest.raises(R._lib.RvbError, match="workspace"):
+        R._lib.call("rvb_vat_finalize_stats", g.data_ptr(), d.data_ptr(), x.data_ptr(), *[o.data_ptr() for o in outs[1]],
+                    n_rows, F, 1e-6, 2.0, 1e10, 1, flag.data_ptr(), mean.data_ptr(), ws.data_ptr(), 4)
+
+
+def test_module_with_scratch_matches_module_without(R, dev):
+    """vat.scratch = Scratch(dev) switches to the stats kernel and private workspaces: same r_adv, d_hat, loss; the
+    deferred NaN assertion still fires."""
+    from reconvat_b200.standin import StandInTranscriber
+    gm = StandInTranscriber("unet", seed=2).to(dev)
+    x = _spec_like(2, 16, 229, 8).unsqueeze(1).to(dev)
+    res = []
+    for use in (False, True):
+        vat = R.VAT.UNet_VAT(0.1, 2.0, 1, False)
+        if use:
+            vat.scratch = R.VAT.Scratch(dev)
+        torch.manual_seed(11)
+        loss, r_adv, d_hat = vat(gm, x)
+        res.append((loss.item(), r_adv.clone(), d_hat.clone(), vat.last_r_norm_mean))
+        vat.check()
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    assert res[0][3] is None
+    want = res[1][2].double().abs().mean().item()
+    assert abs(res[1][3].item() - want) <= 2e-7 * want
+
+
 def test_bce_grad_and_mean(R, dev):
     import torch.nn.functional as F
     torch.manual_seed(5)
