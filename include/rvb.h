@@ -176,6 +176,30 @@ int rvb_stft_mel_folded_f16(const void* a_hi, const void* a_lo, const float* row
                             int n_fft, const void* basis_hi, const void* basis_lo, float basis_scale_inv, int n_bins_pad,
                             const float* p0, float w0, int spectrum, float power, const float* mel_tab, int n_mels,
                             float* mel_out, rvb_stream_t stream);
+/*
+ * K0q / K1q  the TWICE-folded contraction (same references as K0h / K1m).  For integer bins the basis has a second
+ * symmetry, cos(2 pi (N/2-k) n/N) = (-1)^n cos(2 pi k n/N), sin likewise with a minus sign: splitting the folded sums by
+ * the parity of n yields bin k and bin N/2-k from the same four partial sums (one radix-2 decimation step), so the
+ * contraction runs over k = 1 .. N/4 only -- half the multiply-adds of K1m.  Bins 0 and N/2 are not produced.
+ *   rvb_fold_split2_f16[_pcm16]: as rvb_fold_split_f16[_pcm16], but a row's columns are ordered even n first
+ *     (n = 2, 4, .., N/2), then odd n (n = 1, 3, .., N/2-1); no p0 output (the n = 0 term must vanish: w0 == 0).
+ *   rvb_stft_mel_folded2_f16: power spectrum + Mel projection.
+ *     basis_hi/lo  [4 * N/4][N/4] fp16: chains Ce | Co | Se | So, row r <-> k = r + 1, columns in increasing n of the
+ *                  chain's parity (basis.fold2_operand), block-scaled by 2^s (basis_scale_inv = 2^-s)
+ *     mel_tab      HOST pointer, [2 * N/4][4] float (basis.mel_epilogue_table2): rows [0, N/4) the ascending stream
+ *                  (row q <-> bin q + 1), rows [N/4, N/2) the mirrored stream (row q <-> bin N/2 - 1 - q) in
+ *                  reversed band coordinates; n_fft <= 2048
+ *     mel_out      [n_seg][n_mels][n_frames]; zeroed by the call, accumulated with RED.ADD (<= 2 partial sums each)
+ */
+int rvb_fold_split2_f16(const float* audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int pad_mode,
+                        int n_fft, int hop, int n_frames, void* a_hi, void* a_lo, float* row_scale_inv,
+                        rvb_stream_t stream);
+int rvb_fold_split2_f16_pcm16(const int16_t* audio, int64_t audio_ld, float gain, int n_seg, int n_samples, int pad,
+                              int pad_mode, int n_fft, int hop, int n_frames, void* a_hi, void* a_lo,
+                              float* row_scale_inv, rvb_stream_t stream);
+int rvb_stft_mel_folded2_f16(const void* a_hi, const void* a_lo, const float* row_scale_inv, int n_seg, int n_frames,
+                             int n_fft, const void* basis_hi, const void* basis_lo, float basis_scale_inv,
+                             const float* mel_tab, int n_mels, float* mel_out, rvb_stream_t stream);
 int rvb_logmel_minmax(const float* mel, int n_seg, int64_t n_per_seg, float log_offset, uint32_t* minmax,
                       rvb_stream_t stream);
 int rvb_logmel_transpose(const float* mel, int n_seg, int n_mels, int n_frames, float log_offset,

@@ -85,7 +85,7 @@ class STFT(nn.Module):
             wcos = self.wcos[:, 0, :].detach().cpu().numpy()
             wsin = self.wsin[:, 0, :].detach().cpu().numpy()
             dev = self.wsin.device
-            tb = dict(n_bins=wcos.shape[0], fold=None, direct=None)
+            tb = dict(n_bins=wcos.shape[0], fold=None, fold2=None, direct=None)
             # RVB_STFT_OPERAND=tf32 keeps the 3xTF32 planes (half the MMA rate; kept for A/B measurements)
             operand = os.environ.get("RVB_STFT_OPERAND", "f16")
             fold = None if os.environ.get("RVB_NO_FOLD") else basis.fold_operand(wcos, wsin, operand=operand)
@@ -95,6 +95,13 @@ class STFT(nn.Module):
                 for k in ("basis_hi", "basis_lo", "left_cos", "left_sin"):
                     fold[k] = torch.from_numpy(np.ascontiguousarray(fold[k])).to(dev)
                 tb["fold"] = fold
+                # the twice-folded operand of the fused Mel path (RVB_NO_FOLD2=1: keep the once-folded contraction)
+                if fold["operand"] == "f16" and not os.environ.get("RVB_NO_FOLD2"):
+                    f2 = basis.fold2_operand(wcos, wsin)
+                    if f2 is not None:
+                        for k in ("basis_hi", "basis_lo"):
+                            f2[k] = torch.from_numpy(np.ascontiguousarray(f2[k])).to(dev)
+                        tb["fold2"] = f2
             else:
                 hi, lo, n_gemm, leftover = basis.gemm_operand(wcos, wsin)
                 tb["direct"] = dict(basis_hi=torch.from_numpy(hi).to(dev), basis_lo=torch.from_numpy(lo).to(dev),
@@ -145,7 +152,7 @@ class STFT(nn.Module):
     def n_frames(self, num_samples):
         return self._geometry(num_samples)[1]
 
-    def _spectrum(self, x, epilogue, power, make_out, mel_tab=None, prepadded=False):
+    def _spectrum(self, x, epilogue, power, make_out, mel_tab=None, prepadded=False, mel_tab2=None):
         """x: (B,1,L) CUDA float32.  Runs pad/frame/split + the tcgen05 contraction with the given epilogue.
         ``make_out(B, n_frames)`` -> (out tensor, n_out_bins).  Returns (out, n_frames).
         ``mel_tab`` (only with the folded fp16 contraction, see :meth:`fused_mel_ok`): fuse the Mel projection;
@@ -168,6 +175,20 @@ class STFT(nn.Module):
             if fd["operand"] == "f16":
                 planes = torch.empty((2, 2, M, half), dtype=torch.float16, device=x.device)  # [hi|lo][e|o][frame][c]
                 row_inv = torch.empty((M,), dtype=torch.float32, device=x.device)
+                if mel_tab2 is not None:
+                    # twice-folded contraction: planes with the even-n columns first, four chains over k = 1 .. N/4
+                    f2 = tb["fold2"]
+                    if pcm16:
+                        _lib.call("rvb_fold_split2_f16_pcm16", _lib.ptr(x2, torch.int16), ld, 1.0 / 32768.0, B, L,
+                                  self.pad_amount, mode, self.n_fft, self.stride, n_frames, planes[0].data_ptr(),
+                                  planes[1].data_ptr(), row_inv.data_ptr())
+                    else:
+                        _lib.call("rvb_fold_split2_f16", _lib.ptr(x2), ld, B, L, self.pad_amount, mode, self.n_fft,
+                                  self.stride, n_frames, planes[0].data_ptr(), planes[1].data_ptr(), row_inv.data_ptr())
+                    _lib.call("rvb_stft_mel_folded2_f16", planes[0].data_ptr(), planes[1].data_ptr(), row_inv.data_ptr(),
+                              B, n_frames, self.n_fft, f2["basis_hi"].data_ptr(), f2["basis_lo"].data_ptr(),
+                              f2["scale_inv"], mel_tab2.ctypes.data, n_out_bins, _lib.ptr(out))
+                    return out, n_frames
                 if pcm16:
                     _lib.call("rvb_fold_split_f16_pcm16", _lib.ptr(x2, torch.int16), ld, 1.0 / 32768.0, B, L,
                               self.pad_amount, mode, self.n_fft, self.stride, n_frames, planes[0].data_ptr(),
@@ -289,12 +310,15 @@ class MelSpectrogram(nn.Module):
         self._bands_key = None
         self._fused = None
         self._fused_key = None
+        self._fused2 = None
+        self._fused2_key = None
         if verbose:
             print("Mel filter created (reconvat_b200, banded projection)")
 
     def _apply(self, fn, *args, **kwargs):
         self._bands = None
         self._fused = None
+        self._fused2 = None
         return super()._apply(fn, *args, **kwargs)
 
     def _band_tables(self):
@@ -322,6 +346,18 @@ class MelSpectrogram(nn.Module):
             self._fused_key = key
         return self._fused[0]
 
+    def _fused2_table(self):
+        """Host table of the twice-folded contraction's Mel epilogue (power spectrogram only), or None."""
+        key = (self.mel_basis.device, self.mel_basis._version, self.mel_basis.data_ptr())
+        if self._fused2 is None or self._fused2_key != key:
+            tab = None
+            if self._fused_table() is not None and float(self.power) == 2.0 and \
+                    self.stft._device_tables().get("fold2") is not None:
+                tab = basis.mel_epilogue_table2(self.mel_basis.detach().cpu().numpy(), self.n_fft)
+            self._fused2 = (None if tab is None else np.ascontiguousarray(tab),)
+            self._fused2_key = key
+        return self._fused2[0]
+
     def _spectrum_epilogue(self):
         if float(self.power) == 2.0:
             return _lib.EPI_POWER
@@ -334,7 +370,7 @@ class MelSpectrogram(nn.Module):
         n_mels, dev = self.mel_basis.shape[0], x.device
         return self.stft._spectrum(x, self._spectrum_epilogue(), self.power,
                                    lambda B, T: (torch.empty((B, n_mels, T), dtype=torch.float32, device=dev), n_mels),
-                                   mel_tab=tab, prepadded=prepadded)
+                                   mel_tab=tab, prepadded=prepadded, mel_tab2=self._fused2_table())
 
     def _power_spectrogram(self, x, prepadded=False):
         """(B,1,L) -> power (B, T, n_pow_bins), time-major, holding (sqrt(re^2+im^2))**power for every bin the

@@ -306,3 +306,94 @@ def fold_operand(wcos, wsin, tol=2.5e-7, operand="tf32"):
     return dict(basis_hi=hi, basis_lo=lo, n_bins_pad=n_bins_pad, n_gemm_bins=n_gemm, leftover=leftover, w0=w0,
                 left_cos=bc[n_gemm:].astype(np.float32), left_sin=bs[n_gemm:].astype(np.float32),
                 scale_inv=scale_inv, operand=operand)
+
+
+FOLD2_TILE_K = 64             # k-values per tile of the twice-folded contraction (rvb_stft_gemm.cu)
+
+
+def fold2_operand(wcos, wsin, tol=2.5e-7):
+    """Operand of the TWICE-folded contraction, or None when the basis does not have the second symmetry.
+
+    On top of :func:`fold_operand` (n <-> N-n), a full-resolution basis (integer bins k = 0 .. N/2) satisfies
+        cos(2 pi (N/2 - k) n / N) = (-1)^n cos(2 pi k n / N),   sin(2 pi (N/2 - k) n / N) = -(-1)^n sin(2 pi k n / N)
+    for ANY window, so with the folded sums split by the parity of n,
+        Ce[k] = sum_{n even} Bc[k][n] e[n]   Co[k] = sum_{n odd} Bc[k][n] e[n]
+        Se[k] = sum_{n even} Bs[k][n] o[n]   So[k] = sum_{n odd} Bs[k][n] o[n]          (n = 1 .. N/2)
+    bin k has re = Ce + Co, im = Se + So and bin N/2 - k has re = Ce - Co, im = -(Se - So): one radix-2 decimation
+    step of the FFT.  The contraction then needs k = 1 .. N/4 only -- four chains of length N/4 over N/4 rows, HALF the
+    multiply-adds of the once-folded form.  Bins 0 and N/2 are not produced (the caller checks that nothing reads
+    them), and the n = 0 term must vanish (w0 == 0: every window that starts at zero, e.g. periodic Hann).
+
+    Returns dict(basis_hi, basis_lo: float16 [4 * n_k, N/4] planes, chains Ce | Co | Se | So, row r <-> k = r + 1;
+    columns of a chain ordered by increasing n of its parity; n_k = N/4; scale_inv).  The matching frame planes
+    carry the even-n columns first, then the odd-n ones (``rvb_fold_split2_f16``)."""
+    F, N = wcos.shape
+    if N % 256 != 0 or F != N // 2 + 1:
+        return None
+    half, quarter = N // 2, N // 4
+    if quarter % FOLD2_TILE_K != 0:
+        return None
+    first = fold_operand(wcos, wsin, tol=tol, operand="tf32")
+    if first is None or first["w0"] != 0.0:
+        return None
+    c64, s64 = wcos.astype(np.float64), wsin.astype(np.float64)
+    bc = np.empty((F, half), np.float64)               # column c <-> n = c + 1 (as fold_operand, float64 mirror average)
+    bs = np.zeros((F, half), np.float64)
+    bc[:, :half - 1] = 0.5 * (c64[:, 1:half] + c64[:, N - 1:half:-1])
+    bc[:, half - 1] = c64[:, half]
+    bs[:, :half - 1] = 0.5 * (s64[:, 1:half] - s64[:, N - 1:half:-1])
+    n = np.arange(1, half + 1)
+    sgn = np.where(n % 2 == 0, 1.0, -1.0)              # (-1)^n
+    k = np.arange(1, quarter + 1)
+    scale = max(float(np.abs(c64).max()), 1e-30)
+    if np.abs(bc[half - k] - sgn * bc[k]).max() > tol * scale or np.abs(bs[half - k] + sgn * bs[k]).max() > tol * scale:
+        return None
+    C = 0.5 * (bc[k] + sgn * bc[half - k])             # float64 average of the two mirror rows (<= 1 fp32 ulp apart)
+    S = 0.5 * (bs[k] - sgn * bs[half - k])
+    even, odd = np.flatnonzero(n % 2 == 0), np.flatnonzero(n % 2 == 1)
+    mat = np.concatenate([C[:, even], C[:, odd], S[:, even], S[:, odd]], axis=0)     # [4 * n_k, N/4]
+    hi, lo, scale_inv = f16_split64(mat)
+    return dict(basis_hi=hi, basis_lo=lo, n_k=quarter, scale_inv=scale_inv, even_cols=even, odd_cols=odd)
+
+
+def mel_epilogue_table2(mel_basis, n_fft, chunk=EPILOGUE_CHUNK_BINS):
+    """Tables for the Mel epilogue of the twice-folded contraction: float32 [2 * n_k, 4], n_k = n_fft / 4.
+
+    Rows [0, n_k): the ASCENDING stream, row q <-> bin q + 1: (w0, w1, band0) as in :func:`mel_epilogue_table`.
+    Rows [n_k, 2 n_k): the MIRRORED stream, row q <-> bin n_fft/2 - 1 - q, walked downwards in frequency.  In
+    reversed band coordinates band' = n_mels - 1 - band the walk is again non-decreasing, so the same rotating
+    accumulators serve: the row holds (w1, w0, band0' = n_mels - 2 - band0) -- it adds w1 P to band' band0' and w0 P
+    to band0' + 1.  The mirrored row of bin n_fft/4 (q = n_k - 1) is zero: the ascending stream owns that bin.
+    None when the bank cannot be represented: see :func:`mel_epilogue_table`; in addition bins 0 and n_fft/2 must
+    carry no weight."""
+    mb = np.asarray(mel_basis, dtype=np.float32)
+    n_mels, F = mb.shape
+    half, n_k = n_fft // 2, n_fft // 4
+    if F != half + 1 or np.any(mb[:, 0] != 0) or np.any(mb[:, half] != 0):
+        return None
+    try:
+        band0, w0, w1, k_begin, k_end = banded_filterbank(mb)
+    except ValueError:
+        return None
+    b = band0.copy()
+    b[:k_begin] = band0[k_begin]
+    b[k_end:] = band0[k_end - 1]
+    # bit-reproducibility: a band may receive at most two partial sums.  Streams are cut into chunks of `chunk` rows.
+    row_of = np.empty(F, np.int64)
+    row_of[1:n_k + 1] = np.arange(n_k)                                  # ascending rows
+    row_of[n_k + 1:half] = n_k + (half - 1 - np.arange(n_k + 1, half))  # mirrored rows
+    for m in range(n_mels):
+        nz = np.flatnonzero(mb[m])
+        if len(nz) and len(np.unique(row_of[nz] // chunk)) > 2:
+            return None
+    tab = np.zeros((2 * n_k, 4), np.float32)
+    bins_up = np.arange(1, n_k + 1)
+    tab[:n_k, 0], tab[:n_k, 1] = w0[bins_up], w1[bins_up]
+    tab[:n_k, 2] = b[bins_up].astype(np.int32).view(np.float32)
+    bins_dn = half - 1 - np.arange(n_k)
+    tab[n_k:, 0], tab[n_k:, 1] = w1[bins_dn], w0[bins_dn]
+    tab[2 * n_k - 1, :2] = 0.0                                          # bin n_fft/4 belongs to the ascending stream
+    bd = (n_mels - 2 - b[bins_dn]).astype(np.int32)
+    assert np.all(np.diff(b[bins_up]) >= 0) and np.all(np.diff(bd) >= 0)
+    tab[n_k:, 2] = bd.view(np.float32)
+    return tab

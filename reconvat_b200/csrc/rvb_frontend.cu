@@ -190,7 +190,10 @@ __device__ __forceinline__ void fold4(const TIn* __restrict__ fr /* fr[i] = p[i]
 
 // TIn = float, or int16_t for PCM16 audio as the dataset stores it (sample = pcm * gain, gain = 1/32768:
 // model/dataset.py:62 `audio.float().div_(32768.0)`; both steps are exact in fp32).
-template <typename TIn>
+// kPerm (planes of the TWICE-folded contraction, rvb_stft_mel_folded2_f16): the columns of a row are ordered by the
+// parity of n = c + 1 -- even n first (n = 2, 4, .., N/2 -> columns 0 .. N/4-1), then odd n (columns N/4 .. N/2-1).  A
+// lane's four consecutive n are two even and two odd ones: two 4-byte stores per plane instead of one 8-byte store.
+template <typename TIn, bool kPerm>
 __global__ void __launch_bounds__(kFoldWarps * 32)
 fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gain, int n_seg, int n_samples, int pad,
                       int mode, int n_fft, int hop, int n_frames, int groups_per_seg, __half* __restrict__ a_hi,
@@ -305,8 +308,21 @@ fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gai
       for (int c = lane << 2; c < half; c += 128) {
         fold4<TIn>(fr, gain, n_fft, half, c, ev, ov);
         uint2 h, l;
-        split4(ev, h, l); e_hi[c >> 2] = h; e_lo[c >> 2] = l;
-        split4(ov, h, l); o_hi[c >> 2] = h; o_lo[c >> 2] = l;
+        if constexpr (kPerm) {
+          // n = c+1 .. c+4: (ev[1], ev[3]) are the even n -> pair c/2 of the first half of the row, (ev[0], ev[2]) the
+          // odd n -> pair c/2 of the second half
+          const int pe = c >> 2, po = (half >> 2) + (c >> 2);                 // in units of two halves (4 bytes)
+          const float e2[4] = {ev[1], ev[3], ev[0], ev[2]}, o2[4] = {ov[1], ov[3], ov[0], ov[2]};
+          split4(e2, h, l);
+          reinterpret_cast<uint32_t*>(e_hi)[pe] = h.x; reinterpret_cast<uint32_t*>(e_hi)[po] = h.y;
+          reinterpret_cast<uint32_t*>(e_lo)[pe] = l.x; reinterpret_cast<uint32_t*>(e_lo)[po] = l.y;
+          split4(o2, h, l);
+          reinterpret_cast<uint32_t*>(o_hi)[pe] = h.x; reinterpret_cast<uint32_t*>(o_hi)[po] = h.y;
+          reinterpret_cast<uint32_t*>(o_lo)[pe] = l.x; reinterpret_cast<uint32_t*>(o_lo)[po] = l.y;
+        } else {
+          split4(ev, h, l); e_hi[c >> 2] = h; e_lo[c >> 2] = l;
+          split4(ov, h, l); o_hi[c >> 2] = h; o_lo[c >> 2] = l;
+        }
       }
       if (lane == 0) {
         row_scale_inv[f] = __uint_as_float((unsigned)(127 - s) << 23);      // 2^-s
@@ -767,7 +783,7 @@ extern "C" int rvb_fold_split(const float* audio, int64_t audio_ld, int n_seg, i
   return check_launch("fold_split_kernel");
 }
 
-template <typename TIn>
+template <typename TIn, bool kPerm = false>
 static int launch_fold_split_f16(const char* who, const TIn* audio, int64_t audio_ld, float gain, int n_seg,
                                  int n_samples, int pad, int pad_mode, int n_fft, int hop, int n_frames, void* a_hi,
                                  void* a_lo, float* row_scale_inv, float* p0, rvb_stream_t stream) {
@@ -786,7 +802,8 @@ static int launch_fold_split_f16(const char* who, const TIn* audio, int64_t audi
   const int64_t span = n_fft + (kFoldWarps - 1) * (int64_t)hop;
   const size_t smem = 2 * (size_t)((span + 8 + 31) & ~31) * sizeof(TIn);     // two raw staging buffers
   RVB_REQUIRE(smem <= 200 * 1024, "%s: n_fft %d with hop %d needs %zu bytes of shared memory", who, n_fft, hop, smem);
-  auto kernel = fold_split_f16_kernel<TIn>;
+  RVB_REQUIRE(!kPerm || n_fft % 256 == 0, "%s: n_fft %d must be a multiple of 256", who, n_fft);
+  auto kernel = fold_split_f16_kernel<TIn, kPerm>;
   if (smem > 48 * 1024)
     RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int groups_per_seg = (n_frames + kFoldWarps - 1) / kFoldWarps;
@@ -816,6 +833,20 @@ extern "C" int rvb_fold_split_f16_pcm16(const int16_t* audio, int64_t audio_ld, 
                                         void* a_lo, float* row_scale_inv, float* p0, rvb_stream_t stream) {
   return launch_fold_split_f16<int16_t>("rvb_fold_split_f16_pcm16", audio, audio_ld, gain, n_seg, n_samples, pad,
                                         pad_mode, n_fft, hop, n_frames, a_hi, a_lo, row_scale_inv, p0, stream);
+}
+
+extern "C" int rvb_fold_split2_f16(const float* audio, int64_t audio_ld, int n_seg, int n_samples, int pad,
+                                   int pad_mode, int n_fft, int hop, int n_frames, void* a_hi, void* a_lo,
+                                   float* row_scale_inv, rvb_stream_t stream) {
+  return launch_fold_split_f16<float, true>("rvb_fold_split2_f16", audio, audio_ld, 1.f, n_seg, n_samples, pad, pad_mode,
+                                            n_fft, hop, n_frames, a_hi, a_lo, row_scale_inv, nullptr, stream);
+}
+
+extern "C" int rvb_fold_split2_f16_pcm16(const int16_t* audio, int64_t audio_ld, float gain, int n_seg, int n_samples,
+                                         int pad, int pad_mode, int n_fft, int hop, int n_frames, void* a_hi,
+                                         void* a_lo, float* row_scale_inv, rvb_stream_t stream) {
+  return launch_fold_split_f16<int16_t, true>("rvb_fold_split2_f16_pcm16", audio, audio_ld, gain, n_seg, n_samples, pad,
+                                              pad_mode, n_fft, hop, n_frames, a_hi, a_lo, row_scale_inv, nullptr, stream);
 }
 
 extern "C" int rvb_stft_bin(const float* sig_hi, const float* sig_lo, int n_seg, int rows_per_seg, int hop,

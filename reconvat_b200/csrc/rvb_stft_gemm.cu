@@ -856,6 +856,267 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
   }
 }
 
+// ---------------------------------------------------------------- twice-folded kernel, CTA pairs (K1q)
+// One more symmetry than K1f2.  For integer bins, cos(2 pi (N/2-k) n / N) = (-1)^n cos(2 pi k n / N) and
+// sin(2 pi (N/2-k) n / N) = -(-1)^n sin(2 pi k n / N), whatever the window.  Splitting the folded sums by the parity of n,
+//     Ce = sum_{n even} Bc[k][n] e[n],  Co = sum_{n odd} Bc[k][n] e[n],  Se, So likewise with Bs and o,
+// gives BOTH bin k (re = Ce + Co, im = Se + So) and bin N/2 - k (re = Ce - Co, im = -(Se - So)): one radix-2
+// decimation step of the FFT.  The contraction runs over k = 1 .. N/4 only: four chains of length N/4 per tile
+// instead of two of length N/2 over twice as many rows -- HALF the multiply-adds of K1f2 for the same 1022 bins (bins 0
+// and N/2 are not produced; the Mel bank does not read them -- checked on the host).
+//  * A planes: [hi|lo][e|o][frame][N/2] with the even-n columns first (rvb_fold_split2_f16); chain c reads plane
+//    c >> 1 at column offset (c & 1) N/4.  B planes: [hi|lo][Ce|Co|Se|So][N/4 rows][N/4], row r <-> k = r + 1.
+//  * tile = 256 frames x 64 k-values; MMAs are M256 N64 K16 (cta_group::2), each CTA stages 128 frame rows and 32
+//    basis rows per 64-column K-block: 40 KB per stage, 5 stages.  TMEM: 4 accumulators x 64 columns per stage, 2 stages.
+//  * epilogue: four groups of four warps.  Group g = (stream g >> 1, half g & 1) walks 32 of the tile's k-values in
+//    ascending order and feeds P = (Ce +- Co)^2 + (Se +- So)^2 to the rotating band accumulators.  Stream 0 is the
+//    ascending bins k; stream 1 is bins N/2 - k, DEscending in frequency -- in reversed band coordinates
+//    (band' = n_mels - 1 - band) that walk is ascending again, so both streams run the SAME code with a different sign,
+//    table half and output stride (basis.mel_epilogue_table2).  A band receives at most two partial sums (32-row
+//    chunks; checked on the host), so the result stays bit-reproducible.
+constexpr int Q_BLOCK_N = 64;
+constexpr int Q_STAGES = 5;
+constexpr int Q_B_BYTES = 32 * 128;                     // this CTA's half of the 64 basis rows
+constexpr int Q_STAGE_BYTES = 2 * P_A_BYTES + 2 * Q_B_BYTES;     // A_hi A_lo B_hi B_lo = 40 KB
+constexpr int Q_SMEM_BYTES = Q_STAGES * Q_STAGE_BYTES + BAR_BYTES + 1024;
+constexpr int Q_CHUNK = 32;                             // k-values per epilogue group and tile
+
+struct Fold2Params {
+  int n_frames;               // frames per segment (T)
+  int64_t m_rows;             // n_seg * n_frames
+  int n_k, quarter;           // basis rows per chain (N/4), contraction length per chain (N/4)
+  int m_tiles, n_tiles;
+  const float* row_scale_inv;
+  float basis_scale_inv;
+  float* mel_out;             // [n_seg][n_mels][n_frames], zeroed before the launch
+  int n_mels;
+};
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+
+struct Mel2Acc {
+  int b0;
+  float acc0, acc1;
+  float* cur;        // row of band b0 (stream 1: of band n_mels - 1 - b0); advanced by `stride` per rotation
+};
+
+// Four consecutive k-values of one frame.  (ce, co, se, so): the four accumulators; sgn = +1 / -1 selects bin k / N/2-k.
+__device__ __forceinline__ void mel2_bins4(const uint32_t (&ce)[4], const uint32_t (&co)[4], const uint32_t (&se)[4],
+                                           const uint32_t (&so)[4], const float4* tab, float sgn, int n_mels,
+                                           int64_t stride, bool f_ok, float scale2, Mel2Acc& a) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 e = tab[i];                                       // constant bank, same index in every lane
+    const float r = fmaf(sgn, __uint_as_float(co[i]), __uint_as_float(ce[i]));
+    const float m = fmaf(sgn, __uint_as_float(so[i]), __uint_as_float(se[i]));
+    const float v = fmaf(r, r, m * m);
+    const int band = __float_as_int(e.z);
+#pragma unroll 1
+    while (a.b0 < band) {                                          // warp-uniform; rolled (instruction cache, see K1m)
+      const float out = a.acc0 * scale2;
+      if (f_ok && out != 0.f && (unsigned)a.b0 < (unsigned)n_mels) atomicAdd(a.cur, out);
+      a.cur += stride;
+      a.acc0 = a.acc1;
+      a.acc1 = 0.f;
+      ++a.b0;
+    }
+    a.acc0 = fmaf(e.x, v, a.acc0);
+    a.acc1 = fmaf(e.y, v, a.acc1);
+  }
+}
+
+__device__ __forceinline__ void mel2_unit(const Fold2Params& p, uint32_t taddr /* column of the first k-value in Ce */,
+                                          const float4* tab, int stream, float* __restrict__ col, bool f_ok, float scale) {
+  const float sgn = stream ? -1.f : 1.f;
+  const int64_t stride = stream ? -(int64_t)p.n_frames : (int64_t)p.n_frames;
+  Mel2Acc a{__float_as_int(tab[0].z), 0.f, 0.f, nullptr};
+  a.cur = col + (int64_t)(stream ? p.n_mels - 1 - a.b0 : a.b0) * p.n_frames;
+  const float scale2 = scale * scale;
+  uint32_t ce0[4], co0[4], se0[4], so0[4], ce1[4], co1[4], se1[4], so1[4];
+  tmem_ld4(taddr, ce0);
+  tmem_ld4(taddr + Q_BLOCK_N, co0);
+  tmem_ld4(taddr + 2 * Q_BLOCK_N, se0);
+  tmem_ld4(taddr + 3 * Q_BLOCK_N, so0);
+#pragma unroll 1
+  for (int j = 0; j < Q_CHUNK / 4; j += 2) {
+    tmem_ld_wait();                                                // set 0 (k-values 4j .. 4j+3) has landed
+    tmem_ld4(taddr + 4 * (j + 1), ce1);
+    tmem_ld4(taddr + Q_BLOCK_N + 4 * (j + 1), co1);
+    tmem_ld4(taddr + 2 * Q_BLOCK_N + 4 * (j + 1), se1);
+    tmem_ld4(taddr + 3 * Q_BLOCK_N + 4 * (j + 1), so1);
+    mel2_bins4(ce0, co0, se0, so0, tab + 4 * j, sgn, p.n_mels, stride, f_ok, scale2, a);
+    tmem_ld_wait();                                                // set 1
+    if (j + 2 < Q_CHUNK / 4) {
+      tmem_ld4(taddr + 4 * (j + 2), ce0);
+      tmem_ld4(taddr + Q_BLOCK_N + 4 * (j + 2), co0);
+      tmem_ld4(taddr + 2 * Q_BLOCK_N + 4 * (j + 2), se0);
+      tmem_ld4(taddr + 3 * Q_BLOCK_N + 4 * (j + 2), so0);
+    }
+    mel2_bins4(ce1, co1, se1, so1, tab + 4 * (j + 1), sgn, p.n_mels, stride, f_ok, scale2, a);
+  }
+  float out = a.acc0 * scale2;
+  if (f_ok && out != 0.f && (unsigned)a.b0 < (unsigned)p.n_mels) atomicAdd(a.cur, out);
+  out = a.acc1 * scale2;
+  if (f_ok && out != 0.f && (unsigned)(a.b0 + 1) < (unsigned)p.n_mels) atomicAdd(a.cur + stride, out);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_NUM_THREADS, 1)
+stft_gemm_fold2_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                            const Fold2Params p, const __grid_constant__ MelTable tab) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Q_STAGES * Q_STAGE_BYTES;
+  auto s_a = [&](int s, int lo) { return smem_base + s * Q_STAGE_BYTES + lo * P_A_BYTES; };
+  auto s_b = [&](int s, int lo) { return smem_base + s * Q_STAGE_BYTES + 2 * P_A_BYTES + lo * Q_B_BYTES; };
+  auto bar_full = [&](int s) { return bar_base + 8 * s; };
+  auto bar_empty = [&](int s) { return bar_base + 8 * (Q_STAGES + s); };
+  auto bar_tmem_full = [&](int a) { return bar_base + 8 * (2 * Q_STAGES + a); };
+  auto bar_tmem_empty = [&](int a) { return bar_base + 8 * (2 * Q_STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8 * (2 * Q_STAGES + 4);
+  static_assert(8 * (2 * Q_STAGES + 4) + 4 <= BAR_BYTES, "barrier block too small");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b_hi);
+    tma_prefetch_desc(&tm_b_lo);
+    for (int s = 0; s < Q_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tmem_full(a), 1);
+      mbar_init(bar_tmem_empty(a), 8 * P_EPI_GROUPS);   // epilogue warps of both CTAs (only the leader's copy is used)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  constexpr int kBlockK = 2 * BLOCK_K;            // 64 halves per 128-byte swizzle row
+  const int n_units = p.m_tiles * p.n_tiles;      // 256-frame x 64-k tiles
+  const int kb_per_chain = p.quarter / kBlockK;
+  const int num_kb = 4 * kb_per_chain;
+  const int unit0 = (int)(blockIdx.x >> 1), unit_step = (int)(gridDim.x >> 1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t leader_full0 = map_to_rank(bar_full(0), 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
+        const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
+        int chain = 0, kbi = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int a_row = (int)((chain >> 1) * p.m_rows) + m_tile * 256 + (int)rank * 128;
+          const int a_col = (chain & 1) * p.quarter + kbi * kBlockK;
+          const int b_row = chain * p.n_k + n_tile * Q_BLOCK_N + (int)rank * 32;
+          mbar_wait(bar_empty(stage), phase ^ 1u, nullptr, 1);
+          if (leader) mbar_expect_tx(bar_full(stage), 2 * Q_STAGE_BYTES);
+          const uint32_t fb = leader_full0 + 8 * stage;
+          tma_load_2d_pair(&tm_a_hi, s_a(stage, 0), fb, a_col, a_row);
+          tma_load_2d_pair(&tm_a_lo, s_a(stage, 1), fb, a_col, a_row);
+          tma_load_2d_pair(&tm_b_hi, s_b(stage, 0), fb, kbi * kBlockK, b_row);
+          tma_load_2d_pair(&tm_b_lo, s_b(stage, 1), fb, kbi * kBlockK, b_row);
+          if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
+          if (++kbi == kb_per_chain) { kbi = 0; ++chain; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(256, Q_BLOCK_N, FMT_F16);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
+        mbar_wait(bar_tmem_empty(acc), acc_phase ^ 1u, nullptr, 2);
+        tc_fence_after();
+        int chain = 0, kbi = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + chain * Q_BLOCK_N);
+          const bool first_kb = kbi == 0;
+          mbar_wait(bar_full(stage), phase, nullptr, 3);
+          tc_fence_after();
+          const uint64_t da_hi = make_sw128_desc(s_a(stage, 0));
+          const uint64_t da_lo = make_sw128_desc(s_a(stage, 1));
+          const uint64_t db_hi = make_sw128_desc(s_b(stage, 0));
+          const uint64_t db_lo = make_sw128_desc(s_b(stage, 1));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);             // one MMA consumes 32 bytes of the row
+            umma_f16_pair(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
+            umma_f16_pair(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+            umma_f16_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+          }
+          umma_commit_pair(bar_empty(stage));
+          if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
+          if (++kbi == kb_per_chain) { kbi = 0; ++chain; }
+        }
+        umma_commit_pair(bar_tmem_full(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int group = (warp - EPI_WARP0) >> 2;      // 0 .. 3
+    const int stream = group >> 1, hhalf = group & 1;
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const uint32_t leader_tmem_empty0 = map_to_rank(bar_tmem_empty(0), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = unit0; unit < n_units; unit += unit_step) {
+      const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
+      const int64_t f = (int64_t)m_tile * 256 + (int64_t)rank * 128 + row;       // flattened frame index
+      const bool f_ok = f < p.m_rows;
+      const int b = f_ok ? (int)(f / p.n_frames) : 0;
+      const int t = f_ok ? (int)(f - (int64_t)b * p.n_frames) : 0;
+      const float scale = f_ok ? __ldg(p.row_scale_inv + f) * p.basis_scale_inv : 1.f;
+      float* col = p.mel_out + (int64_t)b * p.n_mels * p.n_frames + t;
+      const float4* tt = tab.e + stream * p.n_k + n_tile * Q_BLOCK_N + hhalf * Q_CHUNK;
+      mbar_wait(bar_tmem_full(acc), acc_phase, nullptr, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + hhalf * Q_CHUNK);
+      mel2_unit(p, taddr, tt, stream, col, f_ok, scale);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // Single bin from the folded planes (Nyquist bin of the STFT module): warp per frame, fp32 FMA.
 // T = float (tf32 planes) or __half (fp16 planes, row-scaled: row_scale_inv undoes the scaling).
 template <typename T>
@@ -1133,6 +1394,57 @@ extern "C" int rvb_stft_mel_folded_f16(const void* a_hi, const void* a_lo, const
   return launch_folded<true>("rvb_stft_mel_folded_f16", a_hi, a_lo, row_scale_inv, n_seg, n_frames, n_fft, basis_hi,
                              basis_lo, basis_scale_inv, n_bins_pad, p0, w0, spectrum, power, nullptr, n_bins_pad, stream,
                              &mel);
+}
+
+extern "C" int rvb_stft_mel_folded2_f16(const void* a_hi, const void* a_lo, const float* row_scale_inv, int n_seg,
+                                        int n_frames, int n_fft, const void* basis_hi, const void* basis_lo,
+                                        float basis_scale_inv, const float* mel_tab, int n_mels, float* mel_out,
+                                        rvb_stream_t stream) {
+  const char* who = "rvb_stft_mel_folded2_f16";
+  RVB_REQUIRE(a_hi && a_lo && row_scale_inv && basis_hi && basis_lo && mel_tab && mel_out, "%s: null pointer", who);
+  RVB_REQUIRE(n_seg > 0 && n_frames > 0 && n_mels > 0, "%s: bad shape", who);
+  RVB_REQUIRE(n_fft >= 256 && n_fft % 256 == 0 && 2 * (n_fft / 4) <= kMelTableBins,
+              "%s: n_fft %d must be a multiple of 256 and at most %d", who, n_fft, 2 * kMelTableBins);
+  for (const void* ptr : {a_hi, a_lo, basis_hi, basis_lo})
+    RVB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 127u) == 0, "%s: operands must be 128-byte aligned", who);
+  const int half = n_fft / 2, quarter = n_fft / 4;
+  const int64_t m_rows = (int64_t)n_seg * n_frames;
+  RVB_REQUIRE(2 * m_rows < (1ll << 31), "%s: too many frames", who);
+  RVB_CUDA(cudaMemsetAsync(mel_out, 0, sizeof(float) * (size_t)n_seg * n_mels * n_frames, (cudaStream_t)stream));
+
+  CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+  int rc;
+  if ((rc = make_map_2d(&tm_a_hi, a_hi, half, 2 * m_rows, 64, 128, 2)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_a_lo, a_lo, half, 2 * m_rows, 64, 128, 2)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_b_hi, basis_hi, quarter, 4 * (uint64_t)quarter, 64, 32, 2)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_b_lo, basis_lo, quarter, 4 * (uint64_t)quarter, 64, 32, 2)) != RVB_OK) return rc;
+
+  Fold2Params p;
+  p.n_frames = n_frames; p.m_rows = m_rows; p.n_k = quarter; p.quarter = quarter;
+  p.m_tiles = (int)((m_rows + 255) / 256);
+  p.n_tiles = quarter / Q_BLOCK_N;
+  p.row_scale_inv = row_scale_inv; p.basis_scale_inv = basis_scale_inv;
+  p.mel_out = mel_out; p.n_mels = n_mels;
+
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
+    cudaLaunchConfig_t qc = {};
+    qc.gridDim = dim3(num_sms() & ~1u); qc.blockDim = dim3(P_NUM_THREADS); qc.dynamicSmemBytes = Q_SMEM_BYTES;
+    int nc = 0;
+    RVB_CUDA(cudaOccupancyMaxActiveClusters(&nc, stft_gemm_fold2_pair_kernel, &qc));
+    RVB_REQUIRE(nc > 0, "%s: no CTA pair fits on this device", who);
+    max_clusters = nc < num_sms() / 2 ? nc : num_sms() / 2;
+  }
+  const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
+  const int n_clusters = (int)(n_units < max_clusters ? n_units : max_clusters);
+  static thread_local MelTable tab;
+  std::memset(&tab, 0, sizeof(tab));
+  std::memcpy(tab.e, mel_tab, sizeof(float4) * (size_t)(2 * quarter));
+  stft_gemm_fold2_pair_kernel<<<2 * n_clusters, P_NUM_THREADS, Q_SMEM_BYTES, (cudaStream_t)stream>>>(
+      tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p, tab);
+  count_launch();
+  return check_launch("stft_gemm_fold2_pair_kernel");
 }
 
 template <typename T>

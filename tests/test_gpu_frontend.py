@@ -27,13 +27,15 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.fixture(scope="module", params=["fused_f16", "folded_f16", "folded_tf32", "direct"])
+@pytest.fixture(scope="module", params=["fused2_f16", "fused_f16", "folded_f16", "folded_tf32", "direct"])
 def mel(R, dev, request):
-    """Every front-end path: folded 3xFP16 contraction with the Mel projection fused into its epilogue (symmetric
-    window + triangular bank: the default), the same contraction followed by the separate Mel kernel, folded
-    3xTF32, and the unfolded 3xTF32 contraction."""
+    """Every front-end path: the twice-folded 3xFP16 contraction with the Mel projection in its epilogue (symmetric
+    window + integer bins + triangular bank: the default), the once-folded one with the same epilogue, the once-folded
+    contraction followed by the separate Mel kernel, folded 3xTF32, and the unfolded 3xTF32 contraction."""
     import os
     m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    if request.param == "fused_f16":
+        os.environ["RVB_NO_FOLD2"] = "1"
     if request.param == "direct":
         os.environ["RVB_NO_FOLD"] = "1"
     if request.param == "folded_tf32":
@@ -43,13 +45,15 @@ def mel(R, dev, request):
     try:
         tb = m.stft._device_tables()                          # tables are built here, under the env switches
         fused = m._fused_table()
+        fused2 = m._fused2_table()
     finally:
-        for k in ("RVB_NO_FOLD", "RVB_STFT_OPERAND", "RVB_NO_MEL_FUSION"):
+        for k in ("RVB_NO_FOLD", "RVB_STFT_OPERAND", "RVB_NO_MEL_FUSION", "RVB_NO_FOLD2"):
             os.environ.pop(k, None)
     assert (tb["fold"] is None) == (request.param == "direct")
     if tb["fold"] is not None:
         assert tb["fold"]["operand"] == request.param.split("_")[1]
-    assert (fused is not None) == (request.param == "fused_f16")
+    assert (fused is not None) == (request.param in ("fused_f16", "fused2_f16"))
+    assert (fused2 is not None) == (request.param == "fused2_f16")
     return m
 
 
@@ -151,14 +155,16 @@ def test_fused_mel_epilogue_matches_separate_kernel_and_is_reproducible(R, dev):
     import os
     from reconvat_b200 import synth
     a = torch.from_numpy(synth.segments(3, "mixed", seed=9)).to(dev)
-    fused = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
-    os.environ["RVB_NO_MEL_FUSION"] = "1"
+    os.environ["RVB_NO_FOLD2"] = "1"
     try:
+        fused = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+        assert fused._fused_table() is not None and fused._fused2_table() is None
+        os.environ["RVB_NO_MEL_FUSION"] = "1"
         plain = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
         assert plain._fused_table() is None
     finally:
         os.environ.pop("RVB_NO_MEL_FUSION", None)
-    assert fused._fused_table() is not None
+        os.environ.pop("RVB_NO_FOLD2", None)
     f1, f2, p1 = fused(a[:, :-1]), fused(a[:, :-1]), plain(a[:, :-1])
     assert f1.shape == p1.shape == (3, 229, 640) and f1.is_contiguous()
     assert torch.equal(f1, f2)
@@ -171,6 +177,70 @@ def test_fused_mel_epilogue_matches_separate_kernel_and_is_reproducible(R, dev):
     odd.mel_basis[5, 60] = 1e-3
     assert odd._fused_table() is None
     assert odd(a[:, :-1]).shape == (3, 229, 640)
+
+
+def test_fold_split2_is_the_parity_permutation_of_fold_split(R, dev):
+    """rvb_fold_split2_f16[_pcm16]: same values and row scales as rvb_fold_split_f16, columns reordered even n first
+    (n = 2, 4, .., N/2), then odd n (n = c + 1)."""
+    from reconvat_b200 import synth
+    a16 = np.stack([synth.white_int16(16385, 1), synth.music_int16(16385, 2), synth.white_int16(16385, 3)])
+    a16[2, :9000] = 0
+    nb, L, N, hop, T = 3, 16384, 2048, 512, 33
+    n = np.arange(1, N // 2 + 1)
+    order = torch.from_numpy(np.concatenate([np.flatnonzero(n % 2 == 0), np.flatnonzero(n % 2 == 1)])).to(dev)
+    for pcm in (False, True):
+        x = torch.from_numpy(a16 if pcm else synth.to_float(a16)).to(dev)[:, :-1]
+        p1 = torch.full((2, 2, nb * T, N // 2), float("nan"), dtype=torch.float16, device=dev)
+        p2 = torch.full_like(p1, float("nan"))
+        i1, i2 = torch.empty(nb * T, device=dev), torch.empty(nb * T, device=dev)
+        if pcm:
+            R._lib.call("rvb_fold_split_f16_pcm16", x.data_ptr(), x.stride(0), 1 / 32768.0, nb, L, 1024, 0, N, hop, T,
+                        p1[0].data_ptr(), p1[1].data_ptr(), i1.data_ptr(), None)
+            R._lib.call("rvb_fold_split2_f16_pcm16", x.data_ptr(), x.stride(0), 1 / 32768.0, nb, L, 1024, 0, N, hop, T,
+                        p2[0].data_ptr(), p2[1].data_ptr(), i2.data_ptr())
+        else:
+            R._lib.call("rvb_fold_split_f16", x.data_ptr(), x.stride(0), nb, L, 1024, 0, N, hop, T, p1[0].data_ptr(),
+                        p1[1].data_ptr(), i1.data_ptr(), None)
+            R._lib.call("rvb_fold_split2_f16", x.data_ptr(), x.stride(0), nb, L, 1024, 0, N, hop, T, p2[0].data_ptr(),
+                        p2[1].data_ptr(), i2.data_ptr())
+        assert torch.equal(i1, i2)
+        assert torch.equal(p1[..., order].view(torch.int16), p2.view(torch.int16))
+
+
+def test_twice_folded_contraction_against_once_folded_and_float64(R, dev):
+    """The radix-2 split (bin k and bin N/2 - k from the parity-split sums over k = 1 .. N/4) against the once-folded
+    contraction and the float64 oracle: log-Mel within the 1e-4 budget with the same margin, bit-reproducible from run
+    to run (at most two partial sums per Mel element), and it really is the kernel that runs by default."""
+    import os
+    from oracle.frontend import FrontEndOracle
+    from reconvat_b200 import synth
+    a = synth.segments(3, "mixed", seed=9)
+    ad = torch.from_numpy(a).to(dev)
+    m2 = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    assert m2._fused2_table() is not None
+    os.environ["RVB_NO_FOLD2"] = "1"
+    try:
+        m1 = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+        assert m1._fused2_table() is None and m1._fused_table() is not None
+    finally:
+        os.environ.pop("RVB_NO_FOLD2", None)
+    log = []
+    R._lib.record_calls(log)
+    y2 = m2(ad[:, :-1])
+    R._lib.record_calls(None)
+    assert [n for n, _ in log] == ["rvb_fold_split2_f16", "rvb_stft_mel_folded2_f16"]
+    assert torch.equal(y2, m2(ad[:, :-1]))
+    y1 = m1(ad[:, :-1])
+    l1, l2 = torch.log(y1 + 1e-5).cpu().numpy(), torch.log(y2 + 1e-5).cpu().numpy()
+    ref = FrontEndOracle().log_mel(a[:, :-1].astype(np.float64), np.float64)
+    e1, e2 = relerr(l1, ref), relerr(l2, ref)
+    assert e2 < LOGMEL_TOL and e2 < 2 * e1 + 1e-5, (e1, e2)
+    assert relerr(l2, l1) < LOGMEL_TOL
+    # a bank that reads bin 0 (fmin = 0 with htk) cannot use the split: it falls back to the once-folded kernel
+    kw = dict(MEL_KW, fmin=0, htk=True)
+    m0 = R.Spectrogram.MelSpectrogram(**kw).to(dev)
+    if m0.mel_basis[:, 0].abs().max() > 0:
+        assert m0._fused2_table() is None
 
 
 def test_pad_split_bit_exact(R, dev):
