@@ -181,6 +181,7 @@ int rvb_stft_mel_folded_f16(const void* a_hi, const void* a_lo, const float* row
  * symmetry, cos(2 pi (N/2-k) n/N) = (-1)^n cos(2 pi k n/N), sin likewise with a minus sign: splitting the folded sums by
  * the parity of n yields bin k and bin N/2-k from the same four partial sums (one radix-2 decimation step), so the
  * contraction runs over k = 1 .. N/4 only -- half the multiply-adds of K1m.  Bins 0 and N/2 are not produced.
+ * n_fft: a multiple of 512, at most 2048.
  *   rvb_fold_split2_f16[_pcm16]: as rvb_fold_split_f16[_pcm16], but a row's columns are ordered even n first
  *     (n = 2, 4, .., N/2), then odd n (n = 1, 3, .., N/2-1); no p0 output (the n = 0 term must vanish: w0 == 0).
  *   rvb_stft_mel_folded2_f16: power spectrum + Mel projection.
@@ -189,7 +190,10 @@ int rvb_stft_mel_folded_f16(const void* a_hi, const void* a_lo, const float* row
  *     mel_tab      HOST pointer, [2 * N/4][4] float (basis.mel_epilogue_table2): rows [0, N/4) the ascending stream
  *                  (row q <-> bin q + 1), rows [N/4, N/2) the mirrored stream (row q <-> bin N/2 - 1 - q) in
  *                  reversed band coordinates; n_fft <= 2048
- *     mel_out      [n_seg][n_mels][n_frames]; zeroed by the call, accumulated with RED.ADD (<= 2 partial sums each)
+ *     mel_out      [2][n_seg][n_mels][n_frames]: the cos^2 and the sin^2 part of the Mel power spectrogram (the
+ *                  projection is linear in P = re^2 + im^2, so a unit of the kernel handles ONE component: half the
+ *                  L2 -> SM operand traffic per multiply-add); the consumer adds the planes (rvb_logmel_normalise
+ *                  does).  Zeroed by the call, accumulated with RED.ADD, at most two partial sums per element
  */
 int rvb_fold_split2_f16(const float* audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int pad_mode,
                         int n_fft, int hop, int n_frames, void* a_hi, void* a_lo, float* row_scale_inv,
@@ -212,9 +216,10 @@ int rvb_logmel_transpose(const float* mel, int n_seg, int n_mels, int n_frames, 
  * (model/self_attention_VAT.py:1102-1104, model/utils.py:93-100).  Bit-identical to rvb_logmel_minmax +
  * rvb_logmel_transpose, which it falls back to when a segment does not fit the cluster's shared memory
  * (or RVB_NO_NORM_FUSION=1).  minmax: uint32 [n_seg][2], receives the keys (required).
+ * mel_b: NULL, or the second plane of rvb_stft_mel_folded2_f16 -- the kernel then reads mel + mel_b (fused path only).
  */
-int rvb_logmel_normalise(const float* mel, int n_seg, int n_mels, int n_frames, float log_offset, uint32_t* minmax,
-                         float* out, rvb_stream_t stream);
+int rvb_logmel_normalise(const float* mel, const float* mel_b, int n_seg, int n_mels, int n_frames, float log_offset,
+                         uint32_t* minmax, float* out, rvb_stream_t stream);
 
 #define RVB_LAYOUT_BINS_MAJOR 0 /* out[b][m][t]  -- what MelSpectrogram.forward returns (:460) */
 #define RVB_LAYOUT_TIME_MAJOR 1 /* out[b][t][m]  -- after `.transpose(-1,-2)` (self_attention_VAT.py:1104) */

@@ -366,11 +366,17 @@ class MelSpectrogram(nn.Module):
         return _lib.EPI_POWER_P
 
     def _mel_fused(self, x, tab, prepadded=False):
-        """(B,1,L) -> Mel spectrogram (B, n_mels, T) through the contraction with the fused Mel epilogue."""
+        """(B,1,L) -> Mel spectrogram through the contraction with the fused Mel epilogue: (mel, None, T) with mel
+        (B, n_mels, T), or -- twice-folded contraction -- (mel_c, mel_s, T), the cos^2 and sin^2 parts whose sum is
+        the Mel spectrogram."""
         n_mels, dev = self.mel_basis.shape[0], x.device
-        return self.stft._spectrum(x, self._spectrum_epilogue(), self.power,
-                                   lambda B, T: (torch.empty((B, n_mels, T), dtype=torch.float32, device=dev), n_mels),
-                                   mel_tab=tab, prepadded=prepadded, mel_tab2=self._fused2_table())
+        tab2 = self._fused2_table()
+        lead = (2,) if tab2 is not None else ()
+        out, n_frames = self.stft._spectrum(
+            x, self._spectrum_epilogue(), self.power,
+            lambda B, T: (torch.empty(lead + (B, n_mels, T), dtype=torch.float32, device=dev), n_mels),
+            mel_tab=tab, prepadded=prepadded, mel_tab2=tab2)
+        return (out[0], out[1], n_frames) if tab2 is not None else (out, None, n_frames)
 
     def _power_spectrogram(self, x, prepadded=False):
         """(B,1,L) -> power (B, T, n_pow_bins), time-major, holding (sqrt(re^2+im^2))**power for every bin the
@@ -397,7 +403,8 @@ class MelSpectrogram(nn.Module):
         x = basis.broadcast_dim(x)
         tab = self._fused_table()
         if tab is not None:
-            return self._mel_fused(x, tab)[0]
+            mel, mel_b, _ = self._mel_fused(x, tab)
+            return mel if mel_b is None else torch.add(mel, mel_b)
         power, n_frames, bands = self._power_spectrogram(x)
         out = torch.empty((power.shape[0], self.mel_basis.shape[0], n_frames), dtype=torch.float32, device=x.device)
         self._project(power, n_frames, bands, -1.0, _lib.LAYOUT_BINS_MAJOR, out, None)
@@ -425,15 +432,19 @@ class MelSpectrogram(nn.Module):
             x = x[:, :, :-1]                                  # a view; the kernel takes the row stride
         tab = self._fused_table()
         if tab is not None:
-            mel, n_frames = self._mel_fused(x, tab, prepadded)
+            mel, mel_b, n_frames = self._mel_fused(x, tab, prepadded)
             B, n_mels = mel.shape[0], mel.shape[1]
             out = torch.empty((B, n_frames, n_mels), dtype=torch.float32, device=x.device)
             minmax = None
+            fpc = (-(-n_frames // 8) + 3) // 4 * 4                   # frames per CTA of the 8-CTA cluster kernel
+            fits = fpc <= 128 and fpc * (n_mels | 1) * 4 <= 200 * 1024 and not os.environ.get("RVB_NO_NORM_FUSION")
+            if mel_b is not None and not (normalise and reduce_minmax is None and fits):
+                mel, mel_b = torch.add(mel, mel_b), None              # the two-pass kernels take one plane
             if normalise and reduce_minmax is None:
                 # one pass: a cluster per segment keeps the log-Mel values in shared memory across the min/max
                 minmax = torch.empty((B, 2), dtype=torch.int32, device=x.device)
-                _lib.call("rvb_logmel_normalise", mel.data_ptr(), B, n_mels, n_frames, float(log_offset),
-                          minmax.data_ptr(), out.data_ptr())
+                _lib.call("rvb_logmel_normalise", mel.data_ptr(), None if mel_b is None else mel_b.data_ptr(), B, n_mels,
+                          n_frames, float(log_offset), minmax.data_ptr(), out.data_ptr())
             else:
                 if normalise:
                     minmax = torch.empty((B, 2), dtype=torch.int32, device=x.device)

@@ -33,7 +33,7 @@ SIGNATURES = {
     "rvb_stft_mel_folded2_f16": [_c_p, _c_p, _c_p, _i32, _i32, _i32, _c_p, _c_p, _f32, _c_p, _i32, _c_p, _c_p],
     "rvb_logmel_minmax": [_c_p, _i32, _i64, _f32, _c_p, _c_p],
     "rvb_logmel_transpose": [_c_p, _i32, _i32, _i32, _f32, _c_p, _c_p, _c_p],
-    "rvb_logmel_normalise": [_c_p, _i32, _i32, _i32, _f32, _c_p, _c_p, _c_p],
+    "rvb_logmel_normalise": [_c_p, _c_p, _i32, _i32, _i32, _f32, _c_p, _c_p, _c_p],
     "rvb_stft_bin_folded_f16": [_c_p, _c_p, _c_p, _i32, _i32, _i32, _c_p, _c_p, _c_p, _f32, _i32, _i32, _f32, _c_p, _i32,
                                 _c_p],
     "rvb_stft_bin": [_c_p, _c_p, _i32, _i32, _i32, _i32, _c_p, _c_p, _i32, _i32, _i32, _f32, _c_p, _i32, _c_p],

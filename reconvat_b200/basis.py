@@ -308,7 +308,7 @@ def fold_operand(wcos, wsin, tol=2.5e-7, operand="tf32"):
                 scale_inv=scale_inv, operand=operand)
 
 
-FOLD2_TILE_K = 64             # k-values per tile of the twice-folded contraction (rvb_stft_gemm.cu)
+FOLD2_TILE_K = 128            # k-values per tile of the twice-folded contraction (rvb_stft_gemm.cu)
 
 
 def fold2_operand(wcos, wsin, tol=2.5e-7):
@@ -328,7 +328,7 @@ def fold2_operand(wcos, wsin, tol=2.5e-7):
     columns of a chain ordered by increasing n of its parity; n_k = N/4; scale_inv).  The matching frame planes
     carry the even-n columns first, then the odd-n ones (``rvb_fold_split2_f16``)."""
     F, N = wcos.shape
-    if N % 256 != 0 or F != N // 2 + 1:
+    if N % 512 != 0 or N > 2048 or F != N // 2 + 1:
         return None
     half, quarter = N // 2, N // 4
     if quarter % FOLD2_TILE_K != 0:

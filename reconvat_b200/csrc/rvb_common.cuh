@@ -60,6 +60,22 @@ __device__ __forceinline__ unsigned warp_max_u32(unsigned v) {
   return v;
 }
 
+// a / b for a divisor shared by a whole row: q = a * (1/b), one residual correction.  With the correctly rounded
+// reciprocal this is the correctly rounded quotient except for a vanishing set of operands (Markstein), where it is
+// one ulp off -- three instructions instead of the ~10 of the IEEE sequence with its slow-path check, which made
+// these kernels issue-bound (16 M warp instructions for 20 480 VAT rows, profiles/r01e).  Rows whose divisor is 0, inf,
+// NaN or so small that 1/b overflows take the real division (kFast = false) under a warp-uniform branch.
+__device__ __forceinline__ bool rcp_usable(float rcp_b) { return fabsf(rcp_b) <= 3.0e38f && rcp_b != 0.f; }
+template <bool kFast>
+__device__ __forceinline__ float div_by(float a, float b, float rcp_b) {
+  if constexpr (kFast) {
+    const float q = a * rcp_b;
+    return fmaf(fmaf(-q, b, a), rcp_b, q);
+  } else {
+    return a / b;
+  }
+}
+
 // torch.clamp(v, 0, 1): NaN propagates (fminf/fmaxf would drop it).
 __device__ __forceinline__ float clamp01(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
 

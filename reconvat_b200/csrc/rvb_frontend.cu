@@ -5,7 +5,9 @@
 //   K3 imagewise normalise                 (model/utils.py:100)
 #include <cooperative_groups.h>
 
+#include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "rvb_common.cuh"
 
@@ -163,9 +165,10 @@ __device__ __forceinline__ bool fs_mbar_try_wait(uint32_t bar, uint32_t parity) 
   return done != 0;
 }
 
-template <typename TIn>
+template <typename TIn, bool kRaw = false>
 __device__ __forceinline__ void fold4(const TIn* __restrict__ fr /* fr[i] = p[i] */, float gain, int n_fft, int half, int c,
                                       float (&e)[4], float (&o)[4]) {
+  if constexpr (kRaw) gain = 1.f;                                                // integer PCM units: the multiply folds away
   float xs[4], ys[4];
   if constexpr (sizeof(TIn) == 4) {
     const float4 q0 = *reinterpret_cast<const float4*>(fr + c);                  // p[c .. c+3]
@@ -193,7 +196,11 @@ __device__ __forceinline__ void fold4(const TIn* __restrict__ fr /* fr[i] = p[i]
 // kPerm (planes of the TWICE-folded contraction, rvb_stft_mel_folded2_f16): the columns of a row are ordered by the
 // parity of n = c + 1 -- even n first (n = 2, 4, .., N/2 -> columns 0 .. N/4-1), then odd n (columns N/4 .. N/2-1).  A
 // lane's four consecutive n are two even and two odd ones: two 4-byte stores per plane instead of one 8-byte store.
-template <typename TIn, bool kPerm>
+// kFixed (PCM16 with a power-of-two gain): no max pass.  e = x +- y of two int16 samples is an integer of at most 17
+// bits; e / 4 lies inside the fp16 range and hi = fp16(e/4), lo = fp16(e/4 - hi) hold it EXACTLY (11 + 6 bits, the
+// residual never below 2^-2), whatever the level of the frame -- so every row takes the same scale 4 * gain.  The
+// planes differ from the block-scaled ones by an exact power of two per row, the contraction's result not at all.
+template <typename TIn, bool kPerm, bool kFixed = false>
 __global__ void __launch_bounds__(kFoldWarps * 32)
 fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gain, int n_seg, int n_samples, int pad,
                       int mode, int n_fft, int hop, int n_frames, int groups_per_seg, __half* __restrict__ a_hi,
@@ -276,21 +283,24 @@ fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gai
       // two passes over the staged samples (max, then scale + split): keeping the 64 folded values of a lane in
       // registers instead costs 95 registers, halves the occupancy and is slower
       float ev[4], ov[4];
-      float mx = 0.f;
-      for (int c = lane << 2; c < half; c += 128) {
-        fold4<TIn>(fr, gain, n_fft, half, c, ev, ov);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(ev[i]), fabsf(ov[i])));   // fmaxf drops NaN: s stays finite
-      }
-      mx = warp_max(mx);
-      // floor(log2(mx)) from the exponent field (subnormal rows: treated as 2^-126); all-zero rows: s = 0
       int s = 0;
-      if (mx > 0.f) {
-        int ex = (int)((__float_as_uint(mx) >> 23) & 0xff) - 127;
-        ex = max(-126, min(ex, 127));
-        s = max(-126, min(14 - ex, 126));
+      float sc = 0.25f;
+      if constexpr (!kFixed) {
+        float mx = 0.f;
+        for (int c = lane << 2; c < half; c += 128) {
+          fold4<TIn>(fr, gain, n_fft, half, c, ev, ov);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(ev[i]), fabsf(ov[i])));   // fmaxf drops NaN: s stays finite
+        }
+        mx = warp_max(mx);
+        // floor(log2(mx)) from the exponent field (subnormal rows: treated as 2^-126); all-zero rows: s = 0
+        if (mx > 0.f) {
+          int ex = (int)((__float_as_uint(mx) >> 23) & 0xff) - 127;
+          ex = max(-126, min(ex, 127));
+          s = max(-126, min(14 - ex, 126));
+        }
+        sc = __uint_as_float((unsigned)(s + 127) << 23);                    // 2^s, exact
       }
-      const float sc = __uint_as_float((unsigned)(s + 127) << 23);          // 2^s, exact
       const int64_t f = (int64_t)b * n_frames + t;
       uint2* e_hi = reinterpret_cast<uint2*>(a_hi + f * half);
       uint2* e_lo = reinterpret_cast<uint2*>(a_lo + f * half);
@@ -306,7 +316,7 @@ fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gai
         lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
       };
       for (int c = lane << 2; c < half; c += 128) {
-        fold4<TIn>(fr, gain, n_fft, half, c, ev, ov);
+        fold4<TIn, kFixed>(fr, gain, n_fft, half, c, ev, ov);
         uint2 h, l;
         if constexpr (kPerm) {
           // n = c+1 .. c+4: (ev[1], ev[3]) are the even n -> pair c/2 of the first half of the row, (ev[0], ev[2]) the
@@ -325,7 +335,7 @@ fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gai
         }
       }
       if (lane == 0) {
-        row_scale_inv[f] = __uint_as_float((unsigned)(127 - s) << 23);      // 2^-s
+        row_scale_inv[f] = kFixed ? 4.f * gain : __uint_as_float((unsigned)(127 - s) << 23);      // 2^-s
         if (p0) p0[f] = (float)fr[0] * (sizeof(TIn) == 4 ? 1.f : gain);
       }
     }
@@ -540,6 +550,8 @@ logmel_transpose_kernel(const float* __restrict__ mel, int n_mels, int n_frames,
     decode_minmax(minmax, b, mn, mx);
     den = mx - mn;                                         // (x_max - x_min), utils.py:100
   }
+  const float rden = 1.f / den;
+  const bool rcp_ok = rcp_usable(rden);                    // block-uniform: constant / NaN segments take the real division
   const float* src = mel + (int64_t)b * n_mels * n_frames + t0;
   // one warp per band row (32 consecutive frames = 128 bytes); four rows in flight per warp to cover DRAM latency
   for (int m4 = warp; m4 < n_mels; m4 += 32) {
@@ -554,7 +566,7 @@ logmel_transpose_kernel(const float* __restrict__ mel, int n_mels, int n_frames,
       const int m = m4 + 8 * u;
       float w = v[u];
       if (log_offset >= 0.f) w = fast_log(w + log_offset);
-      if (minmax) w = (w - mn) / den;
+      if (minmax) w = rcp_ok ? div_by<true>(w - mn, den, rden) : (w - mn) / den;
       if (m < n_mels && lane < nt) tile[lane * n_mels + m] = w;   // bank = (lane * n_mels + m) % 32: conflict-free, odd n_mels
     }
   }
@@ -581,12 +593,14 @@ logmel_transpose_kernel(const float* __restrict__ mel, int n_mels, int n_frames,
 // bit-identical results.
 constexpr int kNormCluster = 8;              // portable cluster size
 constexpr int kNormThreads = 512;
-constexpr int kNormRows = 4;                 // band rows per warp and trip ...
+constexpr int kNormItems = 4;                // vector path: (8 rows x 4 float4) items per warp and trip
+constexpr int kNormRows = 4;                 // scalar path: band rows per warp and trip ...
 constexpr int kNormChunks = 4;               // ... times 32-frame chunks: a CTA holds at most 128 frames
 
 __global__ void __launch_bounds__(kNormThreads)
-logmel_normalise_cluster_kernel(const float* __restrict__ mel, int n_mels, int n_frames, int frames_per_cta, int pitch,
-                                float log_offset, uint32_t* __restrict__ minmax_out, float* __restrict__ out) {
+logmel_normalise_cluster_kernel(const float* __restrict__ mel, const float* __restrict__ mel_b, int n_mels, int n_frames,
+                                int frames_per_cta, int pitch, float log_offset, uint32_t* __restrict__ minmax_out,
+                                float* __restrict__ out) {
   extern __shared__ __align__(16) float slab[];            // [frames_per_cta][pitch], pitch odd: conflict-free
   __shared__ unsigned red[2][kNormThreads / 32];
   __shared__ unsigned peer_keys[2][kNormCluster];          // [min|max][rank], written by the peers (DSMEM)
@@ -599,31 +613,73 @@ logmel_normalise_cluster_kernel(const float* __restrict__ mel, int n_mels, int n
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kWarps = kNormThreads / 32;
 
-  // pass 1: one warp-wide load = 32 consecutive frames of one band (128 bytes).  A warp takes kNormRows band rows per
-  // trip and all of their (up to kNormChunks) 32-frame chunks: 16 independent loads in flight, no index division.
-  const float* src = mel + (int64_t)b * n_mels * n_frames + t0;
+  // mel_b (optional): second plane of the twice-folded contraction (sin^2 part); the Mel spectrogram is mel + mel_b
+  const int64_t seg_off = (int64_t)b * n_mels * n_frames + t0;
+  const float* src = mel + seg_off;
   float vmax = -INFINITY, vmin = INFINITY;
   bool seen_nan = false;
-  for (int m0 = warp; m0 < n_mels; m0 += kWarps * kNormRows) {
-    float v[kNormRows][kNormChunks];
+  auto take = [&](float x, int t, int m) {                 // one value: log, extrema, transposed store
+    const float w = fast_log(x + log_offset);
+    vmax = fmaxf(vmax, w); vmin = fminf(vmin, w); seen_nan |= isnan(w);
+    slab[t * pitch + m] = w;
+  };
+  const bool vec = (n_frames & 3) == 0 && (reinterpret_cast<uintptr_t>(mel) & 15u) == 0 &&
+                   (mel_b == nullptr || (reinterpret_cast<uintptr_t>(mel_b) & 15u) == 0);
+  if (vec) {
+    // pass 1, 16-byte loads: a warp item is 8 band rows x 4 consecutive float4 (64 contiguous bytes per row: whole
+    // sectors); lane = (row, quad).  kNormItems items per trip: up to 8 independent LDG.128 in flight per lane.
+    const int nq = nt >> 2;                                // float4 per row (t0 and n_frames are multiples of 4)
+    const int q_groups = (nq + 3) >> 2, r_groups = (n_mels + 7) >> 3;
+    const int n_items = q_groups * r_groups;
+    const int lr = lane >> 2, lq = lane & 3;
+    for (int i0 = warp; i0 < n_items; i0 += kWarps * kNormItems) {
+      float4 va[kNormItems], vb[kNormItems];
+      int mm[kNormItems], qq[kNormItems];
 #pragma unroll
-    for (int u = 0; u < kNormRows; ++u) {
-      const int m = m0 + u * kWarps;
-      const float* row = src + (int64_t)m * n_frames + lane;
+      for (int u = 0; u < kNormItems; ++u) {
+        const int i = i0 + u * kWarps;
+        const int rg = i / q_groups, qg = i - rg * q_groups;
+        mm[u] = rg * 8 + lr;
+        qq[u] = qg * 4 + lq;
+        const bool ok = i < n_items && mm[u] < n_mels && qq[u] < nq;
+        if (!ok) mm[u] = -1;
+        const int64_t o = (int64_t)mm[u] * n_frames + 4 * qq[u];
+        va[u] = ok ? __ldg(reinterpret_cast<const float4*>(src + o)) : make_float4(1.f, 1.f, 1.f, 1.f);
+        vb[u] = (ok && mel_b) ? __ldg(reinterpret_cast<const float4*>(mel_b + seg_off + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
-      for (int c = 0; c < kNormChunks; ++c) v[u][c] = (m < n_mels && c * 32 + lane < nt) ? __ldg(row + c * 32) : 1.f;
-    }
-#pragma unroll
-    for (int u = 0; u < kNormRows; ++u) {
-      const int m = m0 + u * kWarps;
-#pragma unroll
-      for (int c = 0; c < kNormChunks; ++c) {
-        const int t = c * 32 + lane;
-        if (m < n_mels && t < nt) {
-          const float w = fast_log(v[u][c] + log_offset);
-          vmax = fmaxf(vmax, w); vmin = fminf(vmin, w); seen_nan |= isnan(w);
-          slab[t * pitch + m] = w;                         // bank = (t * pitch + m) % 32, lanes <-> t, pitch odd
+      for (int u = 0; u < kNormItems; ++u) {
+        if (mm[u] >= 0) {
+          float4 x = va[u];
+          if (mel_b) { x.x = __fadd_rn(x.x, vb[u].x); x.y = __fadd_rn(x.y, vb[u].y); x.z = __fadd_rn(x.z, vb[u].z); x.w = __fadd_rn(x.w, vb[u].w); }
+          const int t = 4 * qq[u];
+          take(x.x, t, mm[u]); take(x.y, t + 1, mm[u]); take(x.z, t + 2, mm[u]); take(x.w, t + 3, mm[u]);
         }
+      }
+    }
+  } else {
+    // pass 1, any frame count: one warp-wide load = 32 consecutive frames of one band (128 bytes); a warp takes
+    // kNormRows band rows per trip and all of their (up to kNormChunks) 32-frame chunks
+    for (int m0 = warp; m0 < n_mels; m0 += kWarps * kNormRows) {
+      float v[kNormRows][kNormChunks];
+#pragma unroll
+      for (int u = 0; u < kNormRows; ++u) {
+        const int m = m0 + u * kWarps;
+        const float* row = src + (int64_t)m * n_frames + lane;
+        const float* row_b = mel_b ? mel_b + seg_off + (int64_t)m * n_frames + lane : nullptr;
+#pragma unroll
+        for (int c = 0; c < kNormChunks; ++c) {
+          const bool ok = m < n_mels && c * 32 + lane < nt;
+          v[u][c] = ok ? __ldg(row + c * 32) : 1.f;
+          if (ok && row_b) v[u][c] = __fadd_rn(v[u][c], __ldg(row_b + c * 32));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kNormRows; ++u) {
+        const int m = m0 + u * kWarps;
+#pragma unroll
+        for (int c = 0; c < kNormChunks; ++c)
+          if (m < n_mels && c * 32 + lane < nt) take(v[u][c], c * 32 + lane, m);
       }
     }
   }
@@ -649,23 +705,29 @@ logmel_normalise_cluster_kernel(const float* __restrict__ mel, int n_mels, int n
   if (gmin == 0xffffffffu || gmax == 0xffffffffu) mn = mx = __int_as_float(0x7fc00000);
   else { mn = -key2f(gmin); mx = key2f(gmax); }
   const float den = mx - mn;                               // (x_max - x_min), utils.py:100
+  const float rden = 1.f / den;
 
   // pass 2: the slab is one contiguous run of the output
   float* dst = out + ((int64_t)b * n_frames + t0) * n_mels;
   const int n = nt * n_mels;
-  if (pitch == n_mels && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-    for (int i = threadIdx.x; i < (n >> 2); i += kNormThreads) {
-      float4 q = reinterpret_cast<const float4*>(slab)[i];
-      q.x = (q.x - mn) / den; q.y = (q.y - mn) / den; q.z = (q.z - mn) / den; q.w = (q.w - mn) / den;
-      reinterpret_cast<float4*>(dst)[i] = q;
+  auto write = [&](auto fast) {
+    constexpr bool kFast = decltype(fast)::value;
+    if (pitch == n_mels && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+      for (int i = threadIdx.x; i < (n >> 2); i += kNormThreads) {
+        float4 q = reinterpret_cast<const float4*>(slab)[i];
+        q.x = div_by<kFast>(q.x - mn, den, rden); q.y = div_by<kFast>(q.y - mn, den, rden);
+        q.z = div_by<kFast>(q.z - mn, den, rden); q.w = div_by<kFast>(q.w - mn, den, rden);
+        reinterpret_cast<float4*>(dst)[i] = q;
+      }
+      for (int i = (n & ~3) + threadIdx.x; i < n; i += kNormThreads) dst[i] = div_by<kFast>(slab[i] - mn, den, rden);
+    } else {
+      for (int i = threadIdx.x; i < n; i += kNormThreads) {
+        const int t = i / n_mels, m = i - t * n_mels;
+        dst[i] = div_by<kFast>(slab[t * pitch + m] - mn, den, rden);
+      }
     }
-    for (int i = (n & ~3) + threadIdx.x; i < n; i += kNormThreads) dst[i] = (slab[i] - mn) / den;
-  } else {
-    for (int i = threadIdx.x; i < n; i += kNormThreads) {
-      const int t = i / n_mels, m = i - t * n_mels;
-      dst[i] = (slab[t * pitch + m] - mn) / den;
-    }
-  }
+  };
+  if (rcp_usable(rden)) write(std::true_type{}); else write(std::false_type{});   // constant / NaN segment: real division
 }
 
 // ------------------------------------------------------------------ K3
@@ -803,7 +865,11 @@ static int launch_fold_split_f16(const char* who, const TIn* audio, int64_t audi
   const size_t smem = 2 * (size_t)((span + 8 + 31) & ~31) * sizeof(TIn);     // two raw staging buffers
   RVB_REQUIRE(smem <= 200 * 1024, "%s: n_fft %d with hop %d needs %zu bytes of shared memory", who, n_fft, hop, smem);
   RVB_REQUIRE(!kPerm || n_fft % 256 == 0, "%s: n_fft %d must be a multiple of 256", who, n_fft);
-  auto kernel = fold_split_f16_kernel<TIn, kPerm>;
+  // PCM16 with a power-of-two gain (1/32768): fixed-scale planes, no max pass
+  int gexp = 0;
+  const bool fixed = sizeof(TIn) == 2 && gain > 0.f && std::frexp(gain, &gexp) == 0.5f && gexp > -100 && gexp < 100 &&
+                     !getenv("RVB_NO_FIXED_SCALE");
+  auto kernel = fixed ? fold_split_f16_kernel<TIn, kPerm, sizeof(TIn) == 2> : fold_split_f16_kernel<TIn, kPerm, false>;
   if (smem > 48 * 1024)
     RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int groups_per_seg = (n_frames + kFoldWarps - 1) / kFoldWarps;
@@ -911,8 +977,8 @@ extern "C" int rvb_logmel_transpose(const float* mel, int n_seg, int n_mels, int
   return check_launch("logmel_transpose_kernel");
 }
 
-extern "C" int rvb_logmel_normalise(const float* mel, int n_seg, int n_mels, int n_frames, float log_offset,
-                                    uint32_t* minmax, float* out, rvb_stream_t stream) {
+extern "C" int rvb_logmel_normalise(const float* mel, const float* mel_b, int n_seg, int n_mels, int n_frames,
+                                    float log_offset, uint32_t* minmax, float* out, rvb_stream_t stream) {
   RVB_REQUIRE(mel && minmax && out, "rvb_logmel_normalise: null pointer");
   RVB_REQUIRE(n_seg > 0 && n_mels > 0 && n_frames > 0 && n_seg <= 65535 && log_offset >= 0.f,
               "rvb_logmel_normalise: bad argument");
@@ -922,12 +988,16 @@ extern "C" int rvb_logmel_normalise(const float* mel, int n_seg, int n_mels, int
   const size_t smem = (size_t)fpc * pitch * sizeof(float);
   static const bool no_fusion = [] { const char* e = getenv("RVB_NO_NORM_FUSION"); return e && *e && *e != '0'; }();
   if (smem > 200 * 1024 || fpc > 32 * kNormChunks || no_fusion) {   // a segment that does not fit 8 SMs: two passes
+    RVB_REQUIRE(!mel_b, "rvb_logmel_normalise: the two-pass path takes one plane (add the planes first)");
     int rc = rvb_logmel_minmax(mel, n_seg, (int64_t)n_mels * n_frames, log_offset, minmax, stream);
     if (rc != RVB_OK) return rc;
     return rvb_logmel_transpose(mel, n_seg, n_mels, n_frames, log_offset, minmax, out, stream);
   }
-  if (smem > 48 * 1024)
+  static size_t smem_set = 48 * 1024;                      // the attribute call is not free: once per new maximum
+  if (smem > smem_set) {
     RVB_CUDA(cudaFuncSetAttribute(logmel_normalise_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)n_seg * kNormCluster);
   cfg.blockDim = dim3(kNormThreads);
@@ -940,8 +1010,8 @@ extern "C" int rvb_logmel_normalise(const float* mel, int n_seg, int n_mels, int
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  RVB_CUDA(cudaLaunchKernelEx(&cfg, logmel_normalise_cluster_kernel, mel, n_mels, n_frames, fpc, pitch, log_offset,
-                              minmax, out));
+  RVB_CUDA(cudaLaunchKernelEx(&cfg, logmel_normalise_cluster_kernel, mel, mel_b, n_mels, n_frames, fpc, pitch,
+                              log_offset, minmax, out));
   count_launch();
   return check_launch("logmel_normalise_cluster_kernel");
 }

@@ -678,6 +678,9 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* tm, uint32_t smem_dst, uint32_t leader_bar, int c0,
                                                  int c1) {
   asm volatile(
@@ -888,8 +891,10 @@ struct Fold2Params {
   int m_tiles, n_tiles;
   const float* row_scale_inv;
   float basis_scale_inv;
-  float* mel_out;             // [n_seg][n_mels][n_frames], zeroed before the launch
+  float* mel_out;             // [2][n_seg][n_mels][n_frames] (cos^2 part | sin^2 part), zeroed before the launch
+  int64_t plane_stride;       // n_seg * n_mels * n_frames
   int n_mels;
+  int exp;                    // RVB_EXP: measurement switches (1: no RED.ADD, 2: no epilogue work, 4: relaxed hand-back)
 };
 
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
@@ -1103,6 +1108,227 @@ stft_gemm_fold2_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- twice-folded kernel, one component per unit (K1q)
+// stft_gemm_fold2_pair_kernel above moves 40 KB of operands per CTA for twelve M256 N64 MMAs: at the tensor pipe's pace
+// that is 17 TB/s of L2 -> SM traffic over the chip, more than the L2 delivers (~12 TB/s): it runs L2-bound.  The Mel
+// projection is LINEAR in the power P = re^2 + im^2, so the two components never have to meet in one thread: this
+// kernel's unit is (256 frames, 128 k-values, ONE component): two chains (even n, odd n) of the e plane against the
+// cos rows -- or of the o plane against the sin rows -- into two 128-column accumulators, exactly the shape of K1f2
+// (48 KB per twelve M256 N128 MMAs, 4 stages) at half its contraction length.  The epilogue forms r = E +- O, adds
+// w r^2 to the band accumulators and flushes them into the component's OWN Mel plane (mel_out[comp]); a plane
+// element receives at most two partial sums, so both planes -- and their sum, taken by the consumer -- are
+// bit-reproducible.  L2 -> SM traffic: 0.98 GB per 32 segments instead of 1.64 GB.
+// scale2 == 0 for rows past the end (their accumulators are finite: the flush then adds nothing).
+__device__ __forceinline__ void mel2c_bins8(const uint32_t (&ev)[8], const uint32_t (&od)[8], const float4* tab, float sgn,
+                                            int n_mels, int64_t stride, float scale2, Mel2Acc& a) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 e = tab[i];                                       // constant bank, same index in every lane
+    const float r = fmaf(sgn, __uint_as_float(od[i]), __uint_as_float(ev[i]));
+    const float v = r * r;
+    const int band = __float_as_int(e.z);
+#pragma unroll 1
+    while (a.b0 < band) {                                          // warp-uniform; rolled (instruction cache, see K1m)
+      const float out = a.acc0 * scale2;
+      if (out != 0.f && (unsigned)a.b0 < (unsigned)n_mels) atomicAdd(a.cur, out);
+      a.cur += stride;
+      a.acc0 = a.acc1;
+      a.acc1 = 0.f;
+      ++a.b0;
+    }
+    a.acc0 = fmaf(e.x, v, a.acc0);
+    a.acc1 = fmaf(e.y, v, a.acc1);
+  }
+}
+
+constexpr int C_CHUNK = 64;                             // k-values per epilogue group and tile
+
+__device__ __forceinline__ void mel2c_unit(const Fold2Params& p, uint32_t taddr /* column of the first k-value in E */,
+                                           const float4* tab, int stream, float* __restrict__ col, bool f_ok, float scale) {
+  const float sgn = stream ? -1.f : 1.f;
+  int n_mels = p.n_mels;
+  asm volatile("" : "+r"(n_mels));                                 // keep it in a register (not an LDC per flush)
+  const int64_t stride = stream ? -(int64_t)p.n_frames : (int64_t)p.n_frames;
+  Mel2Acc a{__float_as_int(tab[0].z), 0.f, 0.f, nullptr};
+  a.cur = col + (int64_t)(stream ? n_mels - 1 - a.b0 : a.b0) * p.n_frames;
+  const float scale2 = f_ok ? scale * scale : 0.f;
+  uint32_t e0[8], o0[8], e1[8], o1[8];
+  tmem_ld8(taddr, e0);
+  tmem_ld8(taddr + F_BLOCK_N, o0);
+#pragma unroll 1
+  for (int j = 0; j < C_CHUNK / 8; j += 2) {
+    tmem_ld_wait();                                                // set 0 (k-values 8j .. 8j+7) has landed
+    tmem_ld8(taddr + 8 * (j + 1), e1);
+    tmem_ld8(taddr + F_BLOCK_N + 8 * (j + 1), o1);
+    mel2c_bins8(e0, o0, tab + 8 * j, sgn, n_mels, stride, scale2, a);
+    tmem_ld_wait();                                                // set 1
+    if (j + 2 < C_CHUNK / 8) {
+      tmem_ld8(taddr + 8 * (j + 2), e0);
+      tmem_ld8(taddr + F_BLOCK_N + 8 * (j + 2), o0);
+    }
+    mel2c_bins8(e1, o1, tab + 8 * (j + 1), sgn, n_mels, stride, scale2, a);
+  }
+  float out = a.acc0 * scale2;
+  if (out != 0.f && (unsigned)a.b0 < (unsigned)n_mels) atomicAdd(a.cur, out);
+  out = a.acc1 * scale2;
+  if (out != 0.f && (unsigned)(a.b0 + 1) < (unsigned)n_mels) atomicAdd(a.cur + stride, out);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_NUM_THREADS, 1)
+stft_gemm_fold2c_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                             const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                             const Fold2Params p, const __grid_constant__ MelTable tab) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + P_STAGES * P_STAGE_BYTES;
+  auto s_a = [&](int s, int lo) { return smem_base + s * P_STAGE_BYTES + lo * P_A_BYTES; };
+  auto s_b = [&](int s, int lo) { return smem_base + s * P_STAGE_BYTES + 2 * P_A_BYTES + lo * P_B_BYTES; };
+  auto bar_full = [&](int s) { return bar_base + 8 * s; };
+  auto bar_empty = [&](int s) { return bar_base + 8 * (P_STAGES + s); };
+  auto bar_tmem_full = [&](int a) { return bar_base + 8 * (2 * P_STAGES + a); };
+  auto bar_tmem_empty = [&](int a) { return bar_base + 8 * (2 * P_STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8 * (2 * P_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b_hi);
+    tma_prefetch_desc(&tm_b_lo);
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tmem_full(a), 1);
+      mbar_init(bar_tmem_empty(a), 8 * P_EPI_GROUPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  constexpr int kBlockK = 2 * BLOCK_K;            // 64 halves per 128-byte swizzle row
+  const int units_per_m = 2 * p.n_tiles;          // (component, 128-k tile)
+  const int n_units = p.m_tiles * units_per_m;
+  const int kb_per_chain = p.quarter / kBlockK;
+  const int num_kb = 2 * kb_per_chain;            // even-n chain, odd-n chain
+  const int unit0 = (int)(blockIdx.x >> 1), unit_step = (int)(gridDim.x >> 1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t leader_full0 = map_to_rank(bar_full(0), 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
+        const int m_tile = unit / units_per_m, rest = unit - m_tile * units_per_m;
+        const int comp = rest / p.n_tiles, n_tile = rest - comp * p.n_tiles;
+        const int a_row = (int)(comp * p.m_rows) + m_tile * 256 + (int)rank * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int chain = kb >= kb_per_chain;
+          const int kk = (kb - chain * kb_per_chain) * kBlockK;
+          const int b_row = (2 * comp + chain) * p.n_k + n_tile * F_BLOCK_N + (int)rank * 64;
+          mbar_wait(bar_empty(stage), phase ^ 1u, nullptr, 1);
+          if (leader) mbar_expect_tx(bar_full(stage), 2 * P_STAGE_BYTES);
+          const uint32_t fb = leader_full0 + 8 * stage;
+          tma_load_2d_pair(&tm_a_hi, s_a(stage, 0), fb, chain * p.quarter + kk, a_row);
+          tma_load_2d_pair(&tm_a_lo, s_a(stage, 1), fb, chain * p.quarter + kk, a_row);
+          tma_load_2d_pair(&tm_b_hi, s_b(stage, 0), fb, kk, b_row);
+          tma_load_2d_pair(&tm_b_lo, s_b(stage, 1), fb, kk, b_row);
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(256, F_BLOCK_N, FMT_F16);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
+        mbar_wait(bar_tmem_empty(acc), acc_phase ^ 1u, nullptr, 2);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int chain = kb >= kb_per_chain;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + chain * F_BLOCK_N);
+          const bool first_kb = (kb == 0) || (kb == kb_per_chain);
+          mbar_wait(bar_full(stage), phase, nullptr, 3);
+          tc_fence_after();
+          const uint64_t da_hi = make_sw128_desc(s_a(stage, 0));
+          const uint64_t da_lo = make_sw128_desc(s_a(stage, 1));
+          const uint64_t db_hi = make_sw128_desc(s_b(stage, 0));
+          const uint64_t db_lo = make_sw128_desc(s_b(stage, 1));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);             // one MMA consumes 32 bytes of the row
+            umma_f16_pair(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
+            umma_f16_pair(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+            umma_f16_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+          }
+          umma_commit_pair(bar_empty(stage));
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(bar_tmem_full(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int group = (warp - EPI_WARP0) >> 2;      // 0 .. 3
+    const int stream = group >> 1, hhalf = group & 1;
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const uint32_t leader_tmem_empty0 = map_to_rank(bar_tmem_empty(0), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = unit0; unit < n_units; unit += unit_step) {
+      const int m_tile = unit / units_per_m, rest = unit - m_tile * units_per_m;
+      const int comp = rest / p.n_tiles, n_tile = rest - comp * p.n_tiles;
+      const int64_t f = (int64_t)m_tile * 256 + (int64_t)rank * 128 + row;       // flattened frame index
+      const bool f_ok = f < p.m_rows;
+      const int b = f_ok ? (int)(f / p.n_frames) : 0;
+      const int t = f_ok ? (int)(f - (int64_t)b * p.n_frames) : 0;
+      const float scale = f_ok ? __ldg(p.row_scale_inv + f) * p.basis_scale_inv : 1.f;
+      float* col = p.mel_out + comp * p.plane_stride + (int64_t)b * p.n_mels * p.n_frames + t;
+      const float4* tt = tab.e + stream * p.n_k + n_tile * F_BLOCK_N + hhalf * C_CHUNK;
+      mbar_wait(bar_tmem_full(acc), acc_phase, nullptr, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + hhalf * C_CHUNK);
+      if (!(p.exp & 2)) mel2c_unit(p, taddr, tt, stream, col, f_ok && !(p.exp & 1), scale);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (p.exp & 4) mbar_arrive_cluster_relaxed(leader_tmem_empty0 + 8 * acc);
+        else mbar_arrive_cluster(leader_tmem_empty0 + 8 * acc);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -1403,48 +1629,54 @@ extern "C" int rvb_stft_mel_folded2_f16(const void* a_hi, const void* a_lo, cons
   const char* who = "rvb_stft_mel_folded2_f16";
   RVB_REQUIRE(a_hi && a_lo && row_scale_inv && basis_hi && basis_lo && mel_tab && mel_out, "%s: null pointer", who);
   RVB_REQUIRE(n_seg > 0 && n_frames > 0 && n_mels > 0, "%s: bad shape", who);
-  RVB_REQUIRE(n_fft >= 256 && n_fft % 256 == 0 && 2 * (n_fft / 4) <= kMelTableBins,
-              "%s: n_fft %d must be a multiple of 256 and at most %d", who, n_fft, 2 * kMelTableBins);
+  RVB_REQUIRE(n_fft >= 512 && n_fft % 512 == 0 && 2 * (n_fft / 4) <= kMelTableBins,
+              "%s: n_fft %d must be a multiple of 512 and at most %d", who, n_fft, 2 * kMelTableBins);
   for (const void* ptr : {a_hi, a_lo, basis_hi, basis_lo})
     RVB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 127u) == 0, "%s: operands must be 128-byte aligned", who);
   const int half = n_fft / 2, quarter = n_fft / 4;
   const int64_t m_rows = (int64_t)n_seg * n_frames;
   RVB_REQUIRE(2 * m_rows < (1ll << 31), "%s: too many frames", who);
-  RVB_CUDA(cudaMemsetAsync(mel_out, 0, sizeof(float) * (size_t)n_seg * n_mels * n_frames, (cudaStream_t)stream));
+  const int64_t plane = (int64_t)n_seg * n_mels * n_frames;
+  RVB_CUDA(cudaMemsetAsync(mel_out, 0, sizeof(float) * 2 * (size_t)plane, (cudaStream_t)stream));
+  // A/B switch for measurements: RVB_FOLD2_N64=1 runs the four-chain kernel (both components per unit, L2-bound)
+  static const bool n64 = [] { const char* e = getenv("RVB_FOLD2_N64"); return e && *e && *e != '0'; }();
 
   CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
   int rc;
+  const uint32_t b_box_rows = n64 ? 32 : 64;
   if ((rc = make_map_2d(&tm_a_hi, a_hi, half, 2 * m_rows, 64, 128, 2)) != RVB_OK) return rc;
   if ((rc = make_map_2d(&tm_a_lo, a_lo, half, 2 * m_rows, 64, 128, 2)) != RVB_OK) return rc;
-  if ((rc = make_map_2d(&tm_b_hi, basis_hi, quarter, 4 * (uint64_t)quarter, 64, 32, 2)) != RVB_OK) return rc;
-  if ((rc = make_map_2d(&tm_b_lo, basis_lo, quarter, 4 * (uint64_t)quarter, 64, 32, 2)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_b_hi, basis_hi, quarter, 4 * (uint64_t)quarter, 64, b_box_rows, 2)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_b_lo, basis_lo, quarter, 4 * (uint64_t)quarter, 64, b_box_rows, 2)) != RVB_OK) return rc;
 
   Fold2Params p;
   p.n_frames = n_frames; p.m_rows = m_rows; p.n_k = quarter; p.quarter = quarter;
   p.m_tiles = (int)((m_rows + 255) / 256);
-  p.n_tiles = quarter / Q_BLOCK_N;
+  p.n_tiles = quarter / (n64 ? Q_BLOCK_N : F_BLOCK_N);
   p.row_scale_inv = row_scale_inv; p.basis_scale_inv = basis_scale_inv;
-  p.mel_out = mel_out; p.n_mels = n_mels;
+  p.mel_out = mel_out; p.plane_stride = plane; p.n_mels = n_mels;
+  { const char* e = getenv("RVB_EXP"); p.exp = e ? atoi(e) : 0; }
 
-  static int max_clusters = 0;
-  if (max_clusters == 0) {
-    RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
+  static int max_clusters[2] = {0, 0};
+  const int smem = n64 ? Q_SMEM_BYTES : P_SMEM_BYTES;
+  auto kernel = n64 ? stft_gemm_fold2_pair_kernel : stft_gemm_fold2c_pair_kernel;
+  if (max_clusters[n64] == 0) {
+    RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaLaunchConfig_t qc = {};
-    qc.gridDim = dim3(num_sms() & ~1u); qc.blockDim = dim3(P_NUM_THREADS); qc.dynamicSmemBytes = Q_SMEM_BYTES;
+    qc.gridDim = dim3(num_sms() & ~1u); qc.blockDim = dim3(P_NUM_THREADS); qc.dynamicSmemBytes = smem;
     int nc = 0;
-    RVB_CUDA(cudaOccupancyMaxActiveClusters(&nc, stft_gemm_fold2_pair_kernel, &qc));
+    RVB_CUDA(cudaOccupancyMaxActiveClusters(&nc, kernel, &qc));
     RVB_REQUIRE(nc > 0, "%s: no CTA pair fits on this device", who);
-    max_clusters = nc < num_sms() / 2 ? nc : num_sms() / 2;
+    max_clusters[n64] = nc < num_sms() / 2 ? nc : num_sms() / 2;
   }
-  const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
-  const int n_clusters = (int)(n_units < max_clusters ? n_units : max_clusters);
+  const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles * (n64 ? 1 : 2);
+  const int n_clusters = (int)(n_units < max_clusters[n64] ? n_units : max_clusters[n64]);
   static thread_local MelTable tab;
   std::memset(&tab, 0, sizeof(tab));
   std::memcpy(tab.e, mel_tab, sizeof(float4) * (size_t)(2 * quarter));
-  stft_gemm_fold2_pair_kernel<<<2 * n_clusters, P_NUM_THREADS, Q_SMEM_BYTES, (cudaStream_t)stream>>>(
-      tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p, tab);
+  kernel<<<2 * n_clusters, P_NUM_THREADS, smem, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p, tab);
   count_launch();
-  return check_launch("stft_gemm_fold2_pair_kernel");
+  return check_launch(n64 ? "stft_gemm_fold2_pair_kernel" : "stft_gemm_fold2c_pair_kernel");
 }
 
 template <typename T>

@@ -6,6 +6,8 @@
 // A row (916 B for 229 mels) is only 4-byte aligned, so each lane owns elements lane, lane+32, ...
 // (every warp-wide access is one fully coalesced 128-byte request) and keeps them in registers:
 // each tensor is read or written exactly once.
+#include <type_traits>
+
 #include "rvb_common.cuh"
 
 namespace rvb {
@@ -57,11 +59,15 @@ vat_perturb_kernel(const float* __restrict__ x, const float* __restrict__ d, flo
   load_row(rd, d + off, row_len, lane);
   load_row(rx, x + off, row_len, lane);
   const float n = sqrtf(row_sumsq(rd));       // torch.norm(d, dim=-1)
+  const float rn = 1.f / n;
+  auto body = [&](auto fast) {
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    float s = rx.v[i] + xi * (rd.v[i] / n);   // x + XI * (d / n)
-    rx.v[i] = do_clamp ? clamp01(s) : s;
-  }
+    for (int i = 0; i < NPL; ++i) {
+      float s = rx.v[i] + xi * div_by<decltype(fast)::value>(rd.v[i], n, rn);   // x + XI * (d / n)
+      rx.v[i] = do_clamp ? clamp01(s) : s;
+    }
+  };
+  if (rcp_usable(rn)) body(std::true_type{}); else body(std::false_type{});
   store_row(rx, x_adv + off, row_len, lane);
 }
 
@@ -79,23 +85,27 @@ __device__ __forceinline__ RowStat finalize_row(RowRegs<NPL>& dp /* in: d' ; out
                                                 float* __restrict__ d_hat, int64_t off, int row_len, int lane,
                                                 float eps, int do_clamp) {
   const float n2 = sqrtf(row_sumsq(dp));
+  const float rn2 = 1.f / n2;
   RowRegs<NPL> rr;
   unsigned bad = 0;
   float asum = 0.f;
+  auto body = [&](auto fast) {
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    const bool in = lane + i * kWarp < row_len;
-    float dh = dp.v[i] / n2;                  // _l2_normalize(d)
-    float r = eps * dh;                       // r_adv
-    if (in) {
-      bad |= (isnan(r) ? 1u : 0u) | (isinf(r) ? 2u : 0u);
-      asum += fabsf(dh);
+    for (int i = 0; i < NPL; ++i) {
+      const bool in = lane + i * kWarp < row_len;
+      float dh = div_by<decltype(fast)::value>(dp.v[i], n2, rn2);      // _l2_normalize(d)
+      float r = eps * dh;                     // r_adv
+      if (in) {
+        bad |= (isnan(r) ? 1u : 0u) | (isinf(r) ? 2u : 0u);
+        asum += fabsf(dh);
+      }
+      float s = rx.v[i] + r;
+      dp.v[i] = dh;
+      rr.v[i] = r;
+      rx.v[i] = do_clamp ? clamp01(s) : s;
     }
-    float s = rx.v[i] + r;
-    dp.v[i] = dh;
-    rr.v[i] = r;
-    rx.v[i] = do_clamp ? clamp01(s) : s;
-  }
+  };
+  if (rcp_usable(rn2)) body(std::true_type{}); else body(std::false_type{});
   store_row(rr, r_adv + off, row_len, lane);
   store_row(rx, x_adv + off, row_len, lane);
   store_row(dp, d_hat + off, row_len, lane);
@@ -159,8 +169,10 @@ __device__ __forceinline__ void finalize_block_stats(RowStat st, bool valid, int
   }
 }
 
+// (256 threads, 5 blocks per SM: <= 48 registers, so that a block fits beside a resident contraction CTA of another
+// stream -- 576 threads x 80 registers leave 14 K registers per SM)
 template <int NPL>
-__global__ void __launch_bounds__(kRowsPerBlock* kWarp)
+__global__ void __launch_bounds__(kRowsPerBlock* kWarp, NPL <= 8 ? 5 : 1)
 vat_finalize_kernel(const float* __restrict__ g, const float* __restrict__ d, const float* __restrict__ x,
                     float* __restrict__ r_adv, float* __restrict__ x_adv, float* __restrict__ d_hat,
                     int64_t n_rows, int row_len, float xi, float eps, float scale, int do_clamp,
@@ -176,23 +188,28 @@ vat_finalize_kernel(const float* __restrict__ g, const float* __restrict__ d, co
   load_row(rx, x + off, row_len, lane);
   load_row(rg, g + off, row_len, lane);
   const float n = sqrtf(row_sumsq(rd));
+  const float rn = 1.f / n;
   // gd = xi * g * [0 <= x + xi*d/n <= 1]   (clamp passes the gradient on the closed interval)
-  float dot = 0.f;
+  auto body = [&](auto fast) {
+    constexpr bool kFast = decltype(fast)::value;
+    float dot = 0.f;
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    float gm = rg.v[i];
-    if (do_clamp) {
-      float s = rx.v[i] + xi * (rd.v[i] / n);
-      gm = (s >= 0.f && s <= 1.f) ? gm : 0.f;
+    for (int i = 0; i < NPL; ++i) {
+      float gm = rg.v[i];
+      if (do_clamp) {
+        float s = rx.v[i] + xi * div_by<kFast>(rd.v[i], n, rn);
+        gm = (s >= 0.f && s <= 1.f) ? gm : 0.f;
+      }
+      float gd = xi * gm;
+      rg.v[i] = gd;
+      dot = fmaf(gd, rd.v[i], dot);
     }
-    float gd = xi * gm;
-    rg.v[i] = gd;
-    dot = fmaf(gd, rd.v[i], dot);
-  }
-  dot = warp_sum(dot);
-  const float c = dot / (n * n * n);
+    dot = warp_sum(dot);
+    const float c = dot / (n * n * n);
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) rd.v[i] = (rg.v[i] / n - rd.v[i] * c) * scale;   // d.grad * scale
+    for (int i = 0; i < NPL; ++i) rd.v[i] = (div_by<kFast>(rg.v[i], n, rn) - rd.v[i] * c) * scale;   // d.grad * scale
+  };
+  if (rcp_usable(rn)) body(std::true_type{}); else body(std::false_type{});
   st = finalize_row(rd, rx, r_adv, x_adv, d_hat, off, row_len, lane, eps, do_clamp);
   }
   finalize_block_stats(st, valid, status_flag, dhat_abs_mean, workspace, (double)n_rows * row_len);
@@ -350,9 +367,23 @@ div_mean_kernel(const float* __restrict__ p, const float* __restrict__ y, int64_
     const int64_t n4 = n >> 2;
     const float4* p4 = reinterpret_cast<const float4*>(p);
     const float4* y4 = reinterpret_cast<const float4*>(y);
-    for (int64_t j = i; j < n4; j += stride) {
-      float4 a = __ldg(p4 + j), b = __ldg(y4 + j);
-      acc += (bce_one<kKind>(a.x, b.x) + bce_one<kKind>(a.y, b.y)) + (bce_one<kKind>(a.z, b.z) + bce_one<kKind>(a.w, b.w));
+    // four float4 pairs per trip, all eight loads issued before the first logarithm: the kernel is latency-bound
+    // (14 MB over 148 SMs), what counts is bytes in flight per thread
+    constexpr int kU = 4;
+    for (int64_t j0 = i; j0 < n4; j0 += stride * kU) {
+      float4 a[kU], b[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t j = j0 + u * stride;
+        const bool ok = j < n4;
+        a[u] = ok ? __ldg(p4 + j) : make_float4(1.f, 1.f, 1.f, 1.f);     // (p, y) = (1, 1) contributes exactly 0 to
+        b[u] = ok ? __ldg(y4 + j) : make_float4(1.f, 1.f, 1.f, 1.f);     // every divergence
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (j0 + u * stride < n4)
+          acc += (bce_one<kKind>(a[u].x, b[u].x) + bce_one<kKind>(a[u].y, b[u].y)) +
+                 (bce_one<kKind>(a[u].z, b[u].z) + bce_one<kKind>(a[u].w, b[u].w));
     }
     for (int64_t j = (n4 << 2) + i; j < n; j += stride) acc += bce_one<kKind>(__ldg(p + j), __ldg(y + j));
   } else {
@@ -377,15 +408,16 @@ div_mean_kernel(const float* __restrict__ p, const float* __restrict__ y, int64_
     // fixed-order final sum in double: the result does not depend on block scheduling
     double s = 0.0;
     for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) s += (double)__ldcg(workspace + j);
-    __shared__ double dsum[256];
-    dsum[threadIdx.x] = s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    __shared__ double dsum[8];
+    if ((threadIdx.x & 31) == 0) dsum[threadIdx.x >> 5] = s;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if ((int)threadIdx.x < o) dsum[threadIdx.x] += dsum[threadIdx.x + o];
-      __syncthreads();
-    }
     if (threadIdx.x == 0) {
-      *loss = (float)(dsum[0] / denom);
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += dsum[w];
+      *loss = (float)(tot / denom);
       *ticket = 0u;   // self-cleaning for the next call on this stream
     }
   }

@@ -403,7 +403,17 @@ def test_fused_normalise_is_bit_identical_to_the_two_pass_kernels(R, dev, B, M, 
     R._lib.call("rvb_logmel_transpose", mel.data_ptr(), B, M, T, 1e-5, keys.data_ptr(), want.data_ptr())
     got = torch.full((B, T, M), -7.0, device=dev)
     keys2 = torch.zeros(B, 2, dtype=torch.int32, device=dev)
-    R._lib.call("rvb_logmel_normalise", mel.data_ptr(), B, M, T, 1e-5, keys2.data_ptr(), got.data_ptr())
+    R._lib.call("rvb_logmel_normalise", mel.data_ptr(), None, B, M, T, 1e-5, keys2.data_ptr(), got.data_ptr())
+    if T <= 1024:                                                 # two planes: the kernel reads their fp32 sum
+        part = mel * torch.rand_like(mel)
+        rest = mel - part
+        keys3 = torch.zeros(B, 2, dtype=torch.int32, device=dev)
+        got3 = torch.empty_like(got)
+        R._lib.call("rvb_logmel_normalise", part.data_ptr(), rest.data_ptr(), B, M, T, 1e-5, keys3.data_ptr(), got3.data_ptr())
+        summed = part + rest
+        R._lib.call("rvb_logmel_normalise", summed.data_ptr(), None, B, M, T, 1e-5, keys2.data_ptr(), got.data_ptr())
+        assert torch.equal(keys3, keys2) and torch.equal(got3.view(torch.int32), got.view(torch.int32))
+        R._lib.call("rvb_logmel_normalise", mel.data_ptr(), None, B, M, T, 1e-5, keys2.data_ptr(), got.data_ptr())
     assert torch.equal(keys, keys2)
     assert torch.equal(got.view(torch.int32), want.view(torch.int32))           # bit pattern, NaNs included
     ref = torch.log(mel[0] + 1e-5)
