@@ -233,6 +233,17 @@ def run_ours(args, rank, local_rank, world):
     step.check()
     ms_step = ms_total / args.steps
     value = world * B * SEG_SECONDS / (ms_step * 1e-3)
+    # the same K steps on ONE stream (kernels strictly one after the other): the denominator of share_of_step, so
+    # that the share can be compared with the serialised ncu launch list in profiles/
+    ms_step_serial = ms_step
+    if not args.no_graphs and args.streams > 1:
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            step.replay(i % n_rot)
+        ev1.record()
+        barrier()
+        ms_step_serial = ev0.elapsed_time(ev1) / args.steps
 
     # eager launches of the same K steps (host-bound: what the CUDA graphs remove)
     barrier()
@@ -337,7 +348,7 @@ def run_ours(args, rank, local_rank, world):
                                       2048 // k_len, "two symmetry folds" if fold2 else "one fold" if folded else "unfolded",
                                       "4/3" if fold2 else "2/3" if f16 else ("1/3" if folded else "1/6")),
                     "issued_tflops": issued, "issued_frac_of_pipe_peak": issued / pipe_peak,
-                    "ms_per_launch": gemm_ms, "share_of_step": gemm_ms / ms_step}
+                    "ms_per_launch": gemm_ms, "share_of_step": gemm_ms / ms_step_serial}
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 roofline["traffic"] = json.load(f).get(kname)
@@ -392,6 +403,7 @@ def run_ours(args, rank, local_rank, world):
                        % ("" if args.no_graphs else "; graph replay",
                           "; each rank bound to its GPU's %d NUMA-local cores" % numa_cores if numa_cores else "")},
         "gpu_launches": launches,
+        "ms_per_step_one_stream": ms_step_serial,
         "eager_ms_per_step": eager_ms_step,
         "kernel_timing": "each entry point re-launched %d times back to back between one CUDA-event pair, rotating over "
                          "%d recorded working sets (> L2); the contraction's entry point includes its 19 MB memset of "

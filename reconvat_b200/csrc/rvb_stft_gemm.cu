@@ -1188,20 +1188,21 @@ __device__ __forceinline__ void mel2c_unit(const Fold2Params& p, uint32_t taddr 
   if (out != 0.f && (unsigned)(a.b0 + 1) < (unsigned)n_mels) atomicAdd(a.cur + stride, out);
 }
 
+template <int kStages>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_NUM_THREADS, 1)
 stft_gemm_fold2c_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                              const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                              const Fold2Params p, const __grid_constant__ MelTable tab) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + P_STAGES * P_STAGE_BYTES;
+  const uint32_t bar_base = smem_base + kStages * P_STAGE_BYTES;
   auto s_a = [&](int s, int lo) { return smem_base + s * P_STAGE_BYTES + lo * P_A_BYTES; };
   auto s_b = [&](int s, int lo) { return smem_base + s * P_STAGE_BYTES + 2 * P_A_BYTES + lo * P_B_BYTES; };
   auto bar_full = [&](int s) { return bar_base + 8 * s; };
-  auto bar_empty = [&](int s) { return bar_base + 8 * (P_STAGES + s); };
-  auto bar_tmem_full = [&](int a) { return bar_base + 8 * (2 * P_STAGES + a); };
-  auto bar_tmem_empty = [&](int a) { return bar_base + 8 * (2 * P_STAGES + 2 + a); };
-  const uint32_t tmem_ptr_addr = bar_base + 8 * (2 * P_STAGES + 4);
+  auto bar_empty = [&](int s) { return bar_base + 8 * (kStages + s); };
+  auto bar_tmem_full = [&](int a) { return bar_base + 8 * (2 * kStages + a); };
+  auto bar_tmem_empty = [&](int a) { return bar_base + 8 * (2 * kStages + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8 * (2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1213,7 +1214,7 @@ stft_gemm_fold2c_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const 
     tma_prefetch_desc(&tm_a_lo);
     tma_prefetch_desc(&tm_b_hi);
     tma_prefetch_desc(&tm_b_lo);
-    for (int s = 0; s < P_STAGES; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), 1);
     }
@@ -1263,7 +1264,7 @@ stft_gemm_fold2c_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const 
           tma_load_2d_pair(&tm_a_lo, s_a(stage, 1), fb, chain * p.quarter + kk, a_row);
           tma_load_2d_pair(&tm_b_hi, s_b(stage, 0), fb, kk, b_row);
           tma_load_2d_pair(&tm_b_lo, s_b(stage, 1), fb, kk, b_row);
-          if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -1294,7 +1295,7 @@ stft_gemm_fold2c_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const 
             umma_f16_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
           }
           umma_commit_pair(bar_empty(stage));
-          if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit_pair(bar_tmem_full(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -1657,9 +1658,13 @@ extern "C" int rvb_stft_mel_folded2_f16(const void* a_hi, const void* a_lo, cons
   p.mel_out = mel_out; p.plane_stride = plane; p.n_mels = n_mels;
   { const char* e = getenv("RVB_EXP"); p.exp = e ? atoi(e) : 0; }
 
+  // RVB_FOLD2_STAGES=3: a 3-stage operand ring (144 KB of shared memory instead of 192 KB leaves room for blocks of the
+  // HBM kernels of other streams beside a resident CTA)
+  static const bool three = [] { const char* e = getenv("RVB_FOLD2_STAGES"); return e && atoi(e) == 3; }();
   static int max_clusters[2] = {0, 0};
-  const int smem = n64 ? Q_SMEM_BYTES : P_SMEM_BYTES;
-  auto kernel = n64 ? stft_gemm_fold2_pair_kernel : stft_gemm_fold2c_pair_kernel;
+  const int smem = n64 ? Q_SMEM_BYTES : (three ? 3 : P_STAGES) * P_STAGE_BYTES + BAR_BYTES + 1024;
+  auto kernel = n64 ? stft_gemm_fold2_pair_kernel
+                    : (three ? stft_gemm_fold2c_pair_kernel<3> : stft_gemm_fold2c_pair_kernel<P_STAGES>);
   if (max_clusters[n64] == 0) {
     RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaLaunchConfig_t qc = {};

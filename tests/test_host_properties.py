@@ -80,3 +80,60 @@ def test_notes_to_frames_vectorised_equals_the_loop(T, P, seed):
     t2, f2 = OD.notes_to_frames(pit if n else np.array([]), iv, (T, P))
     assert np.array_equal(t1, t2) and len(f1) == len(f2)
     assert all(np.array_equal(a, b) for a, b in zip(f1, f2))
+
+
+def test_twice_folded_operand_and_tables():
+    """basis.fold2_operand + basis.mel_epilogue_table2 in float64 on the CPU, emulating what the GPU path does: planes
+    with the even-n columns first, four chains over k = 1 .. N/4, bins k and N/2 - k from (Ce +- Co, Se +- So), the
+    rotating band accumulators walked over 64-row chunks -- the mirrored stream in reversed band coordinates --
+    against the direct windowed-DFT + dense Mel matmul of model/Spectrogram.py:219-231, :458-460."""
+    import torch
+    from reconvat_b200 import basis
+    N, n_mels = 2048, 229
+    ks, kc, _, _, wm = basis.fourier_basis(N, win_length=N, window="hann", freq_scale="no", sr=16000)
+    wcos = (torch.from_numpy(kc) * torch.from_numpy(wm)).numpy()           # float32 product, as the reference
+    wsin = (torch.from_numpy(ks) * torch.from_numpy(wm)).numpy()
+    mb = basis.mel_filterbank(16000, N, n_mels, 30, 8000, htk=False, norm=1)
+    f2 = basis.fold2_operand(wcos, wsin)
+    tab = basis.mel_epilogue_table2(mb, N)
+    assert f2 is not None and tab is not None and f2["n_k"] == 512 and tab.shape == (1024, 4)
+    nk, half = f2["n_k"], N // 2
+    Bm = (f2["basis_hi"].astype(np.float64) + f2["basis_lo"].astype(np.float64)) * f2["scale_inv"]
+    rng = np.random.default_rng(0)
+    T = 5
+    p = rng.standard_normal((T, N))
+    P = (p @ wcos.astype(np.float64).T) ** 2 + (p @ wsin.astype(np.float64).T) ** 2
+    mel_ref = P @ mb.astype(np.float64).T
+    c = np.arange(half)
+    mirror = np.where(c < half - 1, p[:, (N - c - 1) % N], 0.0)
+    e, o = p[:, c + 1] + mirror, np.where(c < half - 1, p[:, c + 1] - mirror, 0.0)
+    ev, od = f2["even_cols"], f2["odd_cols"]
+    assert np.array_equal((ev + 1) % 2, np.zeros_like(ev)) and np.array_equal((od + 1) % 2, np.ones_like(od))
+    Ce, Co = e[:, ev] @ Bm[:nk].T, e[:, od] @ Bm[nk:2 * nk].T
+    Se, So = o[:, ev] @ Bm[2 * nk:3 * nk].T, o[:, od] @ Bm[3 * nk:].T
+    planes = np.zeros((2, T, n_mels))                                       # cos^2 part | sin^2 part
+
+    def walk(rows, vals, reverse, plane):
+        for ch in range(0, nk, 64):
+            b0, acc0, acc1 = int(rows[ch, 2].view(np.int32)), np.zeros(T), np.zeros(T)
+            partial = []
+            for r in range(ch, ch + 64):
+                band = int(rows[r, 2].view(np.int32))
+                while b0 < band:
+                    partial.append((b0, acc0)); acc0, acc1, b0 = acc1, np.zeros(T), b0 + 1
+                acc0 = acc0 + rows[r, 0] * vals[:, r]
+                acc1 = acc1 + rows[r, 1] * vals[:, r]
+            partial += [(b0, acc0), (b0 + 1, acc1)]
+            for band, v in partial:
+                if 0 <= band < n_mels:
+                    plane[:, n_mels - 1 - band if reverse else band] += v
+    for comp, (E, O) in enumerate(((Ce, Co), (Se, So))):
+        walk(tab[:nk], (E + O) ** 2, False, planes[comp])
+        walk(tab[nk:], (E - O) ** 2, True, planes[comp])
+    mel = planes[0] + planes[1]
+    assert np.abs(mel - mel_ref).max() <= 2e-7 * np.abs(mel_ref).max()
+    assert np.abs(np.log(mel + 1e-5) - np.log(mel_ref + 1e-5)).max() < 2e-6
+    # banks the split cannot serve: weight on bin 0 / N/2, or a basis without the second symmetry
+    mb0 = mb.copy(); mb0[0, 0] = 1e-3
+    assert basis.mel_epilogue_table2(mb0, N) is None
+    assert basis.fold2_operand(wcos[:513], wsin[:513]) is None             # freq_bins != N/2 + 1

@@ -15,7 +15,7 @@ warmup = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 dev = torch.device("cuda:0")
-audio = [torch.from_numpy(a).to(dev) for a in make_audio(2, B, 0)]
+audio = [torch.from_numpy(a).to(dev) for a in make_audio(2, B, 0, pcm16=True)]      # PCM16, as bench.py
 step = HotPathStep(InjectedTranscriber(B, seed=7).to(dev), dev)
 for i in range(warmup + steps):
     step(audio[i % 2])
