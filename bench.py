@@ -172,6 +172,9 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL writes its "NCCL version ..." banner (and any warning) to stdout: send them to a file, stdout carries
+        # ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/rvb_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
     import reconvat_b200 as R
     from reconvat_b200 import parallel
@@ -406,8 +409,8 @@ def run_ours(args, rank, local_rank, world):
         "ms_per_step_one_stream": ms_step_serial,
         "eager_ms_per_step": eager_ms_step,
         "kernel_timing": "each entry point re-launched %d times back to back between one CUDA-event pair, rotating over "
-                         "%d recorded working sets (> L2); the contraction's entry point includes its 19 MB memset of "
-                         "the Mel accumulator" % (reps, n_rot),
+                         "%d recorded working sets (> L2); the contraction's entry point includes the memset of "
+                         "its Mel accumulator (38 MB for the two planes of the twice-folded kernel)" % (reps, n_rot),
         "roofline": roofline,
         "hbm_kernels": hbm,
         "cpu_baseline": cpu,
