@@ -592,11 +592,12 @@ logmel_transpose_kernel(const float* __restrict__ mel, int n_mels, int n_frames,
 // instead of two (+ a memset).  Same fast_log, same keys, same (v - min) / (max - min) as the two-pass kernels:
 // bit-identical results.
 constexpr int kNormCluster = 8;              // portable cluster size
-constexpr int kNormThreads = 512;
+constexpr int kNormThreadsMax = 512;
 constexpr int kNormItems = 4;                // vector path: (8 rows x 4 float4) items per warp and trip
 constexpr int kNormRows = 4;                 // scalar path: band rows per warp and trip ...
 constexpr int kNormChunks = 4;               // ... times 32-frame chunks: a CTA holds at most 128 frames
 
+template <int kNormThreads>
 __global__ void __launch_bounds__(kNormThreads)
 logmel_normalise_cluster_kernel(const float* __restrict__ mel, const float* __restrict__ mel_b, int n_mels, int n_frames,
                                 int frames_per_cta, int pitch, float log_offset, uint32_t* __restrict__ minmax_out,
@@ -993,14 +994,18 @@ extern "C" int rvb_logmel_normalise(const float* mel, const float* mel_b, int n_
     if (rc != RVB_OK) return rc;
     return rvb_logmel_transpose(mel, n_seg, n_mels, n_frames, log_offset, minmax, out, stream);
   }
+  // RVB_NORM_THREADS=256: 8 warps per CTA (16 K registers): a CTA then fits beside a resident contraction CTA of
+  // another stream (with RVB_FOLD2_STAGES=3 leaving it 82 KB of shared memory)
+  static const int n_threads = [] { const char* e = getenv("RVB_NORM_THREADS"); return (e && atoi(e) == 256) ? 256 : kNormThreadsMax; }();
+  auto kernel = n_threads == 256 ? logmel_normalise_cluster_kernel<256> : logmel_normalise_cluster_kernel<kNormThreadsMax>;
   static size_t smem_set = 48 * 1024;                      // the attribute call is not free: once per new maximum
   if (smem > smem_set) {
-    RVB_CUDA(cudaFuncSetAttribute(logmel_normalise_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)n_seg * kNormCluster);
-  cfg.blockDim = dim3(kNormThreads);
+  cfg.blockDim = dim3(n_threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
@@ -1010,8 +1015,7 @@ extern "C" int rvb_logmel_normalise(const float* mel, const float* mel_b, int n_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  RVB_CUDA(cudaLaunchKernelEx(&cfg, logmel_normalise_cluster_kernel, mel, mel_b, n_mels, n_frames, fpc, pitch,
-                              log_offset, minmax, out));
+  RVB_CUDA(cudaLaunchKernelEx(&cfg, kernel, mel, mel_b, n_mels, n_frames, fpc, pitch, log_offset, minmax, out));
   count_launch();
   return check_launch("logmel_normalise_cluster_kernel");
 }

@@ -1679,6 +1679,8 @@ extern "C" int rvb_stft_mel_folded2_f16(const void* a_hi, const void* a_lo, cons
   static thread_local MelTable tab;
   std::memset(&tab, 0, sizeof(tab));
   std::memcpy(tab.e, mel_tab, sizeof(float4) * (size_t)(2 * quarter));
+  // (Tried: highest launch priority for this kernel, so that freed SMs go to its CTAs before another stream's HBM
+  // blocks -- 0.216 instead of 0.209 ms per step on three streams; not kept.)
   kernel<<<2 * n_clusters, P_NUM_THREADS, smem, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p, tab);
   count_launch();
   return check_launch(n64 ? "stft_gemm_fold2_pair_kernel" : "stft_gemm_fold2c_pair_kernel");
