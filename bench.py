@@ -35,7 +35,7 @@ HBM_BYTES_PER_SEG = {
     "rvb_mel_project": 1020 * 640 * 4 + N4,
     "rvb_logmel_minmax": N4,
     "rvb_logmel_transpose": 2 * N4,
-    "rvb_logmel_normalise": 2 * N4,                        # fused min/max + normalise + transpose: R mel, W spec
+    "rvb_logmel_normalise": 3 * N4,                        # fused min/max + normalise + transpose: R two Mel planes, W spec
     "rvb_normalise": 2 * N4,
     "rvb_vat_perturb": 3 * N4,
     "rvb_bce_grad": 3 * P4,
