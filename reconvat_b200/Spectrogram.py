@@ -351,9 +351,12 @@ class MelSpectrogram(nn.Module):
         key = (self.mel_basis.device, self.mel_basis._version, self.mel_basis.data_ptr())
         if self._fused2 is None or self._fused2_key != key:
             tab = None
-            if self._fused_table() is not None and float(self.power) == 2.0 and \
+            if self.stft.fused_mel_ok() and float(self.power) == 2.0 and \
                     self.stft._device_tables().get("fold2") is not None:
-                tab = basis.mel_epilogue_table2(self.mel_basis.detach().cpu().numpy(), self.n_fft)
+                # 64 rows per epilogue group (32 in the four-chain A/B kernel): bands up to 65 bins wide stay at two
+                # partial sums per element
+                tab = basis.mel_epilogue_table2(self.mel_basis.detach().cpu().numpy(), self.n_fft,
+                                                chunk=32 if os.environ.get("RVB_FOLD2_N64") else 64)
             self._fused2 = (None if tab is None else np.ascontiguousarray(tab),)
             self._fused2_key = key
         return self._fused2[0]
@@ -402,7 +405,7 @@ class MelSpectrogram(nn.Module):
     def forward(self, x):
         x = basis.broadcast_dim(x)
         tab = self._fused_table()
-        if tab is not None:
+        if tab is not None or self._fused2_table() is not None:
             mel, mel_b, _ = self._mel_fused(x, tab)
             return mel if mel_b is None else torch.add(mel, mel_b)
         power, n_frames, bands = self._power_spectrogram(x)
@@ -431,7 +434,7 @@ class MelSpectrogram(nn.Module):
         if trim_last:
             x = x[:, :, :-1]                                  # a view; the kernel takes the row stride
         tab = self._fused_table()
-        if tab is not None:
+        if tab is not None or self._fused2_table() is not None:
             mel, mel_b, n_frames = self._mel_fused(x, tab, prepadded)
             B, n_mels = mel.shape[0], mel.shape[1]
             out = torch.empty((B, n_frames, n_mels), dtype=torch.float32, device=x.device)

@@ -243,6 +243,30 @@ def test_twice_folded_contraction_against_once_folded_and_float64(R, dev):
         assert m0._fused2_table() is None
 
 
+@pytest.mark.parametrize("n_fft,hop,n_mels,B,L", [(512, 128, 40, 3, 8192), (1024, 256, 128, 2, 20001), (2048, 512, 229, 1, 2048 + 7 * 512)])
+def test_twice_folded_contraction_other_sizes(R, dev, n_fft, hop, n_mels, B, L):
+    """The radix-2 split with one, two and four 128-k tiles (n_fft = 512 / 1024 / 2048), ragged frame counts (the last
+    256-frame tile is partly empty, frames of different segments share a tile) against the float64 oracle."""
+    from oracle.frontend import FrontEndOracle
+    from reconvat_b200 import synth
+    kw = dict(sr=16000, n_fft=n_fft, n_mels=n_mels, hop_length=hop, fmin=30, fmax=7600, verbose=False)
+    a = synth.to_float(np.stack([synth.music_int16(L, 40 + i) if i % 2 else synth.white_int16(L, 40 + i) for i in range(B)]))
+    m = R.Spectrogram.MelSpectrogram(**kw).to(dev)
+    assert m._fused2_table() is not None
+    log = []
+    R._lib.record_calls(log)
+    y = m(torch.from_numpy(a).to(dev))
+    R._lib.record_calls(None)
+    assert [n for n, _ in log] == ["rvb_fold_split2_f16", "rvb_stft_mel_folded2_f16"]
+    ref = FrontEndOracle(sr=16000, n_fft=n_fft, n_mels=n_mels, hop_length=hop, fmin=30, fmax=7600).log_mel(
+        a.astype(np.float64), np.float64)
+    assert y.shape == ref.shape
+    assert relerr(torch.log(y + 1e-5).cpu().numpy(), ref) < LOGMEL_TOL
+    spec = m.normalised_log_mel(torch.from_numpy(a).to(dev), trim_last=False)
+    want = (ref - ref.min(axis=(1, 2), keepdims=True)) / (ref.max(axis=(1, 2), keepdims=True) - ref.min(axis=(1, 2), keepdims=True))
+    assert float(np.abs(spec[:, 0].cpu().numpy() - want.transpose(0, 2, 1)).max()) < 2e-5
+
+
 def test_pad_split_bit_exact(R, dev):
     from reconvat_b200 import basis, synth
     a = torch.from_numpy(synth.to_float(np.stack([synth.white_int16(16385, 1), synth.music_int16(16385, 2)])))
@@ -381,9 +405,15 @@ def test_mel_variants_golden(R, dev, golden, tag, kw):
     from reconvat_b200 import synth
     g = golden["mel_variants"]
     a = torch.from_numpy(synth.to_float(g["audio_int16"])).to(dev)
-    out = R.Spectrogram.MelSpectrogram(**kw).to(dev)(a).cpu().numpy()
+    m = R.Spectrogram.MelSpectrogram(**kw).to(dev)
+    out = m(a).cpu().numpy()
     assert out.shape == g[tag].shape
     assert relerr(np.log(out + 1e-5), np.log(g[tag] + 1e-5)) < LOGMEL_TOL
+    # which kernels serve these banks: librosa_default has bands up to 53 bins wide -- too wide for the once-folded
+    # epilogue's 32-bin chunks, fine for the 64-row chunks of the twice-folded one; htk_128 puts a 6e-17 weight on the
+    # Nyquist bin, which neither fused epilogue produces (separate Mel kernel); power = 1 stays on the once-folded kernel
+    assert (m._fused2_table() is not None) == (tag == "librosa_default")
+    assert (m._fused_table() is not None) == (tag == "power1")
 
 
 @pytest.mark.parametrize("B,M,T", [(3, 229, 640), (32, 229, 640), (2, 229, 37), (2, 128, 100), (1, 229, 1), (2, 80, 3001)])
