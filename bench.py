@@ -172,8 +172,10 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL writes its "NCCL version ..." banner (and any warning) to stdout: send them to a file, stdout carries
-        # ONE JSON line
+        # stdout carries ONE JSON line: with NCCL_DEBUG=VERSION (set on the GPU boxes) NCCL printf()s its
+        # "NCCL version ..." banner to stdout; at WARN it does not, and whatever it logs goes to a file
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/rvb_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
     import reconvat_b200 as R
