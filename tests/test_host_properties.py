@@ -1,5 +1,6 @@
 """Property tests (hypothesis) of the host-side logic: shard arithmetic, padding slices, operand splits, Mel tables."""
 import numpy as np
+import pytest
 import torch
 from hypothesis import given, settings, strategies as st
 
@@ -137,3 +138,32 @@ def test_twice_folded_operand_and_tables():
     mb0 = mb.copy(); mb0[0, 0] = 1e-3
     assert basis.mel_epilogue_table2(mb0, N) is None
     assert basis.fold2_operand(wcos[:513], wsin[:513]) is None             # freq_bins != N/2 + 1
+
+
+@pytest.mark.parametrize("sr,n_fft,n_mels,fmin,fmax,htk", [
+    (16000, 2048, 229, 30, 8000, False), (22050, 2048, 128, 0.0, None, False), (16000, 1024, 128, 30, 7600, False),
+    (16000, 512, 40, 20, 7000, False), (44100, 2048, 96, 50, 16000, True)])
+def test_mel_epilogue_table2_reconstructs_the_filterbank(sr, n_fft, n_mels, fmin, fmax, htk):
+    """The two streams of basis.mel_epilogue_table2 hold every weight of the bank exactly once: scattering
+    (w0, w1, band0) of the ascending rows and (w1', w0', band0') of the mirrored rows (reversed band coordinates) back
+    into a dense matrix gives mel_basis[:, 1:n_fft/2] bit for bit; band indices are non-decreasing in both streams."""
+    from reconvat_b200 import basis
+    mb = basis.mel_filterbank(sr, n_fft, n_mels, fmin, fmax, htk=htk, norm=1)
+    tab = basis.mel_epilogue_table2(mb, n_fft, chunk=64)
+    if tab is None:
+        assert np.any(mb[:, 0] != 0) or np.any(mb[:, n_fft // 2] != 0) or max(len(np.flatnonzero(r)) for r in mb) > 64
+        return
+    nk, half = n_fft // 4, n_fft // 2
+    dense = np.zeros_like(mb)
+    band_up = tab[:nk, 2].copy().view(np.int32)
+    band_dn = tab[nk:, 2].copy().view(np.int32)
+    assert np.all(np.diff(band_up) >= 0) and np.all(np.diff(band_dn) >= 0)
+    for q in range(nk):
+        for w, band in ((tab[q, 0], band_up[q]), (tab[q, 1], band_up[q] + 1)):
+            if w != 0:
+                dense[band, q + 1] += w
+        for w, bp in ((tab[nk + q, 0], band_dn[q]), (tab[nk + q, 1], band_dn[q] + 1)):
+            if w != 0:
+                dense[n_mels - 1 - bp, half - 1 - q] += w
+    assert np.array_equal(dense[:, 1:half], mb[:, 1:half])
+    assert not dense[:, 0].any() and not dense[:, half].any()
