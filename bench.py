@@ -42,7 +42,7 @@ HBM_BYTES_PER_SEG = {
     "rvb_div_grad": 3 * P4,                                # what the VAT modules call (kind = BCE here)
     "rvb_div_mean": 2 * P4,
     "rvb_vat_finalize": 6 * N4,
-    "rvb_vat_finalize_stats": 6 * N4,
+    "rvb_vat_finalize_stats": 5 * N4,                      # as HotPathStep calls it: d_hat itself is not stored
     "rvb_bce_mean": 2 * P4,
 }
 

@@ -306,7 +306,8 @@ int rvb_vat_direct(const float* d, const float* x, float* r_adv, float* x_adv, f
  * go to a workspace and the last block to finish WRITES status_flag (no zeroing by the caller) and
  *   dhat_abs_mean = mean |dhat|     -- the `r_norm.abs().mean()` that run_on_batch logs after every VAT call
  *                                      (model/self_attention_VAT.py:1149-1150), summed in a fixed order in double.
- * g == NULL selects V3b (n_power == 0).  workspace: rvb_vat_stats_workspace_bytes(n_rows) bytes, zeroed once by the
+ * g == NULL selects V3b (n_power == 0).  d_hat == NULL: the normalised direction itself is not stored (a caller that
+ * only logs its mean saves a sixth of the kernel's traffic).  workspace: rvb_vat_stats_workspace_bytes(n_rows) bytes, zeroed once by the
  * caller (self-cleaning); one workspace per stream that may run the kernel concurrently.
  */
 int64_t rvb_vat_stats_workspace_bytes(int64_t n_rows);

@@ -114,10 +114,13 @@ class Scratch:
     ``vat.last_r_norm_mean`` receives mean |d_hat| (the ``r_norm.abs().mean()`` of model/self_attention_VAT.py:1149)
     without another pass over d_hat."""
 
-    def __init__(self, device):
+    def __init__(self, device, keep_d_hat=True):
         self.device = torch.device(device)
         self.div = torch.zeros(_lib.BCE_WORKSPACE_FLOATS, dtype=torch.float32, device=self.device)
         self._stats = None
+        # False: the module returns None for its third output (the normalised direction) and the kernel does not
+        # store it -- for callers that only log its mean (``last_r_norm_mean``), as run_on_batch does
+        self.keep_d_hat = keep_d_hat
 
     def stats(self, n_rows):
         need = _lib.vat_stats_workspace_bytes(n_rows)
@@ -241,7 +244,8 @@ class _VATCore(nn.Module):
             flag = torch.zeros((), dtype=torch.int32, device=x.device)
         r_adv = torch.empty_like(x)
         x_adv2 = torch.empty_like(x)
-        d_hat = torch.empty_like(x)
+        d_hat = torch.empty_like(x) if (sc is None or sc.keep_d_hat) else None
+        d_hat_ptr = None if d_hat is None else d_hat.data_ptr()
         kinds = self._head_kinds()
         if self.n_power == 1:
             x_adv = torch.empty_like(x)
@@ -263,7 +267,7 @@ class _VATCore(nn.Module):
                           float(self.epsilon), float(self._scale), int(self._clamp), flag.data_ptr())
             elif sc is not None:
                 _lib.call("rvb_vat_finalize_stats", g.contiguous().data_ptr(), d.data_ptr(), x.data_ptr(),
-                          r_adv.data_ptr(), x_adv2.data_ptr(), d_hat.data_ptr(), n_rows, row_len, float(self.XI),
+                          r_adv.data_ptr(), x_adv2.data_ptr(), d_hat_ptr, n_rows, row_len, float(self.XI),
                           float(self.epsilon), float(self._scale), int(self._clamp), flag.data_ptr(),
                           r_norm_mean.data_ptr(), stats_ws.data_ptr(), stats_ws.numel() * 4)
             else:
@@ -276,7 +280,7 @@ class _VATCore(nn.Module):
                       flag.data_ptr())
         elif sc is not None:
             _lib.call("rvb_vat_finalize_stats", None, d.data_ptr(), x.data_ptr(), r_adv.data_ptr(), x_adv2.data_ptr(),
-                      d_hat.data_ptr(), n_rows, row_len, 0.0, float(self.epsilon), 1.0, int(self._clamp),
+                      d_hat_ptr, n_rows, row_len, 0.0, float(self.epsilon), 1.0, int(self._clamp),
                       flag.data_ptr(), r_norm_mean.data_ptr(), stats_ws.data_ptr(), stats_ws.numel() * 4)
         else:
             _lib.call("rvb_vat_direct", d.data_ptr(), x.data_ptr(), r_adv.data_ptr(), x_adv2.data_ptr(),

@@ -108,7 +108,7 @@ __device__ __forceinline__ RowStat finalize_row(RowRegs<NPL>& dp /* in: d' ; out
   if (rcp_usable(rn2)) body(std::true_type{}); else body(std::false_type{});
   store_row(rr, r_adv + off, row_len, lane);
   store_row(rx, x_adv + off, row_len, lane);
-  store_row(dp, d_hat + off, row_len, lane);
+  if (d_hat) store_row(dp, d_hat + off, row_len, lane);    // stats flavour: optional (its mean |.| is reduced here)
   RowStat st;
   st.bad = __reduce_or_sync(kFull, bad);
   st.abs_sum = warp_sum(asum);
@@ -459,7 +459,7 @@ static int launch_vat_finalize(const char* who, const float* g, const float* d, 
                                float* x_adv, float* d_hat, int64_t n_rows, int row_len, float xi, float eps, float scale,
                                int do_clamp, int32_t* status_flag, float* dhat_abs_mean, float* workspace,
                                rvb_stream_t stream) {
-  RVB_REQUIRE(d && x && r_adv && x_adv && d_hat, "%s: null pointer", who);
+  RVB_REQUIRE(d && x && r_adv && x_adv && (d_hat || workspace), "%s: null pointer", who);
   RVB_REQUIRE(n_rows >= 0 && row_len > 0, "%s: bad shape (%lld, %d)", who, (long long)n_rows, row_len);
   RVB_REQUIRE(n_rows < (int64_t)kRowsPerBlock * 0x7fffffff, "%s: too many rows", who);
   if (n_rows == 0) return RVB_OK;

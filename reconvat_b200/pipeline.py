@@ -26,7 +26,7 @@ class HotPathStep:
         self.vat_loss = (vat_cls or VAT.UNet_VAT)(xi, eps, 1, False)
         # private reduction workspaces + the fused NaN flag / mean |d_hat| (VAT.Scratch); every captured graph gets
         # its own, because graphs replayed on different streams run the last-block reductions concurrently
-        self._eager_scratch = VAT.Scratch(self.device)
+        self._eager_scratch = VAT.Scratch(self.device, keep_d_hat=False)     # only mean |d_hat| leaves the step
         self._copy_stream = None
         self._graphs = []              # [(graph, input buffer, outputs, device flag)]
         self._lanes = []               # side streams of replay_many
@@ -59,7 +59,7 @@ class HotPathStep:
         self._graphs = []
         try:
             for buf in buffers:
-                scratch = VAT.Scratch(self.device)
+                scratch = VAT.Scratch(self.device, keep_d_hat=False)
                 scratch.stats(self._n_rows)               # sized before the capture (row count of the warm-up step)
                 self.vat_loss.scratch = scratch
                 g = torch.cuda.CUDAGraph()

@@ -135,6 +135,13 @@ def test_finalize_stats_flavour(R, dev, B, T, F, have_g):
         R._lib.call("rvb_vat_finalize_stats", g.data_ptr(), d.data_ptr(), x.data_ptr(), *[o.data_ptr() for o in outs[1]],
                     n_rows, F, 1e-6, 2.0, 1e10, 1, flag.data_ptr(), mean.data_ptr(), ws.data_ptr(), ws.numel() * 4)
         assert flag.item() == 0
+    # d_hat == NULL: nothing else changes (the mean still comes out of the same registers)
+    r2, x2 = torch.empty_like(x), torch.empty_like(x)
+    mean2 = torch.full((), -1.0, device=dev)
+    R._lib.call("rvb_vat_finalize_stats", g.data_ptr() if have_g else None, d.data_ptr(), x.data_ptr(), r2.data_ptr(),
+                x2.data_ptr(), None, n_rows, F, 1e-6, 2.0, 1e10, 1, flag.data_ptr(), mean2.data_ptr(), ws.data_ptr(),
+                ws.numel() * 4)
+    assert torch.equal(r2, outs[0][0]) and torch.equal(x2, outs[0][1]) and abs(mean2.item() - want) <= 2e-7 * want
     with pytest.raises(R._lib.RvbError, match="workspace"):
         R._lib.call("rvb_vat_finalize_stats", g.data_ptr(), d.data_ptr(), x.data_ptr(), *[o.data_ptr() for o in outs[1]],
                     n_rows, F, 1e-6, 2.0, 1e10, 1, flag.data_ptr(), mean.data_ptr(), ws.data_ptr(), 4)
@@ -159,6 +166,12 @@ def test_module_with_scratch_matches_module_without(R, dev):
     assert res[0][3] is None
     want = res[1][2].double().abs().mean().item()
     assert abs(res[1][3].item() - want) <= 2e-7 * want
+    vat = R.VAT.UNet_VAT(0.1, 2.0, 1, False)
+    vat.scratch = R.VAT.Scratch(dev, keep_d_hat=False)                # the direction itself is not stored
+    torch.manual_seed(11)
+    loss, r_adv, d_hat = vat(gm, x)
+    assert d_hat is None and torch.equal(r_adv, res[1][1]) and loss.item() == res[1][0]
+    assert vat.last_r_norm_mean.item() == res[1][3].item()
 
 
 def test_bce_grad_and_mean(R, dev):
