@@ -894,7 +894,8 @@ struct Fold2Params {
   float* mel_out;             // [2][n_seg][n_mels][n_frames] (cos^2 part | sin^2 part), zeroed before the launch
   int64_t plane_stride;       // n_seg * n_mels * n_frames
   int n_mels;
-  int exp;                    // RVB_EXP: measurement switches (1: no RED.ADD, 2: no epilogue work, 4: relaxed hand-back)
+  int exp;                    // ablation builds only (make ABLATION=1): RVB_EXP bits 1: no RED.ADD, 2: no epilogue work,
+                              // 4: relaxed hand-back; always 0 in the product build
 };
 
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
@@ -1323,6 +1324,7 @@ stft_gemm_fold2c_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const 
       mbar_wait(bar_tmem_full(acc), acc_phase, nullptr, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + hhalf * C_CHUNK);
+#ifdef RVB_ABLATION   // measurement-only build (make ABLATION=1): RVB_EXP switches parts of the epilogue off -- wrong results
       if (!(p.exp & 2)) mel2c_unit(p, taddr, tt, stream, col, f_ok && !(p.exp & 1), scale);
       tc_fence_before();
       __syncwarp();
@@ -1330,6 +1332,12 @@ stft_gemm_fold2c_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const 
         if (p.exp & 4) mbar_arrive_cluster_relaxed(leader_tmem_empty0 + 8 * acc);
         else mbar_arrive_cluster(leader_tmem_empty0 + 8 * acc);
       }
+#else
+      mel2c_unit(p, taddr, tt, stream, col, f_ok, scale);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8 * acc);
+#endif
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -1656,7 +1664,10 @@ extern "C" int rvb_stft_mel_folded2_f16(const void* a_hi, const void* a_lo, cons
   p.n_tiles = quarter / (n64 ? Q_BLOCK_N : F_BLOCK_N);
   p.row_scale_inv = row_scale_inv; p.basis_scale_inv = basis_scale_inv;
   p.mel_out = mel_out; p.plane_stride = plane; p.n_mels = n_mels;
+  p.exp = 0;
+#ifdef RVB_ABLATION
   { const char* e = getenv("RVB_EXP"); p.exp = e ? atoi(e) : 0; }
+#endif
 
   // RVB_FOLD2_STAGES=3: a 3-stage operand ring (144 KB of shared memory instead of 192 KB leaves room for blocks of the
   // HBM kernels of other streams beside a resident CTA)

@@ -1,7 +1,7 @@
 """Times the front-end entry points one by one: each is re-launched back to back between one CUDA-event pair, rotating
 over recorded working sets (> L2), behind a spin kernel so that the events bracket kernels and not launch gaps.
 Usage: python tools/gemm_bench.py [B] [reps]
-Switches: RVB_NO_FOLD2=1 (once-folded contraction), RVB_FOLD2_N64=1 (four-chain twice-folded kernel), RVB_EXP=<bits>."""
+Switches: RVB_NO_FOLD2=1 (once-folded contraction), RVB_FOLD2_N64=1 (four-chain twice-folded kernel), RVB_EXP=<bits> (ablation build, make ABLATION=1)."""
 import os
 import sys
 
