@@ -167,3 +167,41 @@ def test_mel_epilogue_table2_reconstructs_the_filterbank(sr, n_fft, n_mels, fmin
                 dense[n_mels - 1 - bp, half - 1 - q] += w
     assert np.array_equal(dense[:, 1:half], mb[:, 1:half])
     assert not dense[:, 0].any() and not dense[:, half].any()
+
+
+@pytest.mark.parametrize("n_fft,window,win_length,expect", [
+    (512, "hann", None, True), (1024, "hann", None, True), (2048, "hann", None, True),
+    (2048, "hamming", None, False),       # w[0] != 0: the n = 0 term does not vanish (p0 path of the once-folded kernel)
+    (2048, "hann", 1600, True),           # a short window, centre-padded: still symmetric, still starts at zero
+    (256, "hann", None, False),           # N/4 = 64 is less than one 128-k tile
+    (4096, "hann", None, False),          # the Mel table is a 1024-row kernel parameter
+])
+def test_fold2_operand_availability_and_exactness(n_fft, window, win_length, expect):
+    """Which bases get the twice-folded operand, and that it reproduces the windowed DFT: for random frames, bins k and
+    N/2 - k rebuilt from the four parity chains equal the direct contraction to 1e-7 of scale (float64)."""
+    import torch
+    from reconvat_b200 import basis
+    ks, kc, _, _, wm = basis.fourier_basis(n_fft, win_length=win_length or n_fft, window=window, freq_scale="no", sr=16000)
+    wcos = (torch.from_numpy(kc) * torch.from_numpy(wm)).numpy()
+    wsin = (torch.from_numpy(ks) * torch.from_numpy(wm)).numpy()
+    f2 = basis.fold2_operand(wcos, wsin)
+    assert (f2 is not None) == expect
+    if f2 is None:
+        return
+    nk, half = f2["n_k"], n_fft // 2
+    assert nk == n_fft // 4 and f2["basis_hi"].shape == (4 * nk, nk) and f2["basis_hi"].dtype == np.float16
+    Bm = (f2["basis_hi"].astype(np.float64) + f2["basis_lo"].astype(np.float64)) * f2["scale_inv"]
+    rng = np.random.default_rng(n_fft)
+    p = rng.standard_normal((3, n_fft))
+    re, im = p @ wcos.astype(np.float64).T, p @ wsin.astype(np.float64).T
+    c = np.arange(half)
+    mirror = np.where(c < half - 1, p[:, (n_fft - c - 1) % n_fft], 0.0)
+    e, o = p[:, c + 1] + mirror, np.where(c < half - 1, p[:, c + 1] - mirror, 0.0)
+    ev, od = f2["even_cols"], f2["odd_cols"]
+    Ce, Co = e[:, ev] @ Bm[:nk].T, e[:, od] @ Bm[nk:2 * nk].T
+    Se, So = o[:, ev] @ Bm[2 * nk:3 * nk].T, o[:, od] @ Bm[3 * nk:].T
+    k = np.arange(1, nk + 1)
+    scale = np.abs(re).max()
+    assert np.abs((Ce + Co) - re[:, k]).max() < 1e-7 * scale and np.abs((Se + So) - im[:, k]).max() < 1e-7 * scale
+    assert np.abs((Ce - Co) - re[:, half - k]).max() < 1e-7 * scale
+    assert np.abs(-(Se - So) - im[:, half - k]).max() < 1e-7 * scale
