@@ -607,6 +607,9 @@ logmel_normalise_cluster_kernel(const float* __restrict__ mel, const float* __re
   __shared__ unsigned peer_keys[2][kNormCluster];          // [min|max][rank], written by the peers (DSMEM)
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
+  // A CTA may only be written through distributed shared memory once it has started executing: every CTA arrives
+  // here, and waits for the others right before its remote stores (a split barrier: no stall in practice).
+  cluster.barrier_arrive();
   const unsigned rank = cluster.block_rank();
   const int b = blockIdx.x / kNormCluster;
   const int t0 = (int)rank * frames_per_cta;
@@ -689,6 +692,7 @@ logmel_normalise_cluster_kernel(const float* __restrict__ mel, const float* __re
   unsigned kmin = warp_max_u32(seen_nan ? 0xffffffffu : f2key(-vmin));
   if (lane == 0) { red[0][warp] = kmin; red[1][warp] = kmax; }
   __syncthreads();
+  cluster.barrier_wait();                                  // completes the arrive at the top: all peers are running
   if (threadIdx.x < kNormCluster) {                        // thread r hands this CTA's keys to peer r
     unsigned k0 = 0, k1 = 0;
 #pragma unroll
