@@ -125,18 +125,30 @@ def make_model(args, batch, dev):
     return m if dev is None else m.to(dev)
 
 
+def cpu_path():
+    """The CPU implementation of the step that is timed as the baseline: the reference's OWN modules when its tree is
+    there (/root/reference in the build container, the oracle/_ref snapshot made by build() on the GPU box), else the
+    oracle's port of the same ATen op sequence.  Returns (object with .step(model, audio), kind, description)."""
+    from oracle import reference_path
+    if reference_path.available():
+        path = reference_path.ReferenceHotPath("cpu")
+        src = os.path.relpath(path.source, ROOT) if path.source.startswith(ROOT) else path.source
+        return path, "reference", "the unmodified reference modules (MelSpectrogram, Normalization, UNet_VAT) from " + src
+    from oracle.cpu_path import CpuHotPath
+    return CpuHotPath(), "port", "oracle/cpu_path.py (the reference's ATen op sequence; no reference tree found)"
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port) on the host cores, rank 0 only."""
+    """--impl reference: the reference's own CPU path on the host cores, rank 0 only."""
     if rank != 0:
         return
     import torch
-    from oracle.cpu_path import CpuHotPath
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sample = min(args.batch, args.cpu_batch)
     audio = torch.from_numpy(make_audio(1, sample, 0, pcm16=args.input == "pcm16")[0])
     model = make_model(args, sample, None)
-    path = CpuHotPath()
+    path, kind, what = cpu_path()
     torch.manual_seed(0)
     for _ in range(max(1, min(args.warmup, 2))):
         path.step(model, to_float_cpu(audio))
@@ -154,9 +166,8 @@ def run_reference(args, rank, world):
         "config": {"workload": "Mel+VAT step (front-end + UNet_VAT, network = %s), CPU, %d x 20.48 s "
                                "segments per step (bounded sample of the B=%d workload), input %s"
                                % (args.model, sample, args.batch, args.input)},
-        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                         "sample": "%d segments x %d steps, oracle/cpu_path.py (the reference's ATen op sequence; the "
-                                   "reference is Python and /root/reference does not travel)" % (sample, steps)},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": kind,
+                         "sample": "%d segments x %d steps, %s" % (sample, steps, what)},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -261,6 +272,80 @@ def run_ours(args, rank, local_rank, world):
     step.vat_loss.check()
     eager_ms_step = ev2.elapsed_time(ev3) / args.steps
 
+    # ---------------- sustained: the same replay loop for >= 2 s, with its own clock samples ----------------
+    sustained = None
+    if not args.no_graphs and args.sustain_s > 0:
+        n_sus = max(args.steps, int(args.sustain_s * 1e3 / ms_step) + 1)
+        sus_sampler = ClockSampler(local_rank)
+        barrier()
+        sus_sampler.start()
+        ev0.record()
+        done = 0
+        while done < n_sus:                                  # bounded bursts: the launch queue never holds > 2000 graphs
+            n = min(2000, n_sus - done)
+            step.replay_many([(done + i) % n_rot for i in range(n)], streams=args.streams)
+            done += n
+        ev1.record()
+        barrier()
+        sus_ms = max_over_ranks(ev0.elapsed_time(ev1))
+        step.check()
+        sustained = {"seconds": sus_ms * 1e-3, "steps": n_sus, "ms_per_step": sus_ms / n_sus,
+                     "value": world * B * SEG_SECONDS / (sus_ms / n_sus * 1e-3), "unit": "audio-s/s",
+                     "clocks": sus_sampler.summary()}
+
+    # ---------------- the zero-edit module surface and the reference's eager path on the same GPU ----------------
+    surface = gpu_eager = None
+    if not args.no_gpu_baselines:
+        f32_audio = [a.float().div_(32768.0) if a.dtype == torch.int16 else a for a in dev_audio[:min(n_rot, 4)]]
+        k_b = max(3, min(args.steps, 20))
+
+        def time_steps(fn, sync_each=False):
+            for i in range(2):
+                fn(f32_audio[i % len(f32_audio)])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(k_b):
+                fn(f32_audio[i % len(f32_audio)])
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / k_b
+
+        # (1) what an UNCHANGED run_on_batch executes after install(): MelSpectrogram.forward -> the caller's torch.log
+        # -> Normalization.transform -> transposed view -> UNet_VAT.forward (synchronous NaN assert, as the reference)
+        mel, norm = step.spectrogram, R.utils.Normalization("imagewise")
+        vat_eager = R.VAT.UNet_VAT(1e-6, 2.0, 1, False)
+
+        def surface_step(audio):
+            spec = mel(audio.reshape(-1, audio.shape[-1])[:, :-1])
+            spec = torch.log(spec + 1e-5)
+            spec = norm.transform(spec)
+            lds, _, r_norm = vat_eager(model, spec.transpose(-1, -2).unsqueeze(1))
+            return lds, r_norm.abs().mean()
+        surface = {"ms_per_step": time_steps(surface_step), "steps": k_b,
+                   "what": "reconvat_b200 behind the reference's unchanged call sequence (model/self_attention_VAT.py:"
+                           "1100-1106), eager launches, float32 audio, synchronous NaN assert"}
+        surface["value"] = B * SEG_SECONDS / (surface["ms_per_step"] * 1e-3)
+
+        # (2) the kernel-for-kernel bar: the reference's own modules, eager PyTorch on this GPU
+        from oracle import reference_path
+        if reference_path.available():
+            ref_path = reference_path.ReferenceHotPath(dev)
+            gpu_eager = {"what": "unmodified reference modules (cuDNN conv1d STFT, cuBLAS Mel matmul, ATen VAT ops, "
+                                 "autograd) on the same GPU, same B, same injected network, float32 audio", "steps": k_b}
+            saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            for tf32 in (True, False):
+                torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = tf32
+                ms = time_steps(lambda a: ref_path.step(model, a))
+                gpu_eager["allow_tf32=%s" % tf32] = {"ms_per_step": ms, "value": B * SEG_SECONDS / (ms * 1e-3),
+                                                     "unit": "audio-s/s"}
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+            del ref_path
+        else:
+            gpu_eager = {"unavailable": "no reference tree (oracle/_ref is made by __graft_entry__.build())"}
+        del f32_audio
+        torch.cuda.empty_cache()
+
     # per-kernel durations: every entry point of the step re-launched `reps` times BACK TO BACK between one CUDA-event
     # pair on the launching stream.  The calls are recorded from n_rot eager steps, each run inside its own memory
     # pool, so that step i's tensors (inputs, intermediates, outputs) have their own addresses: consecutive launches
@@ -339,7 +424,7 @@ def run_ours(args, rank, local_rank, world):
         k_len = 512 if fold2 else 1024 if folded else 2048
         achieved = B * STFT_FLOP_PER_SEG / (gemm_ms * 1e-3) / 1e12
         issued = 3 * B * 2 * 640 * 2048 * k_len / (gemm_ms * 1e-3) / 1e12
-        kname = ("stft_gemm_fold2_pair_kernel + Mel epilogue" if fold2 else
+        kname = ("stft_gemm_fold2c_pair_kernel + Mel epilogue" if fold2 else
                  "stft_gemm_fold_pair_kernel%s" % (" + Mel epilogue" if fused else "") if f16 else
                  "stft_gemm_fold_kernel<tf32>") if folded else "stft_gemm_kernel"
         pipe_peak = peaks["bf16"] if f16 else peaks["bf16"] / 2
@@ -354,11 +439,15 @@ def run_ours(args, rank, local_rank, world):
                                       "4/3" if fold2 else "2/3" if f16 else ("1/3" if folded else "1/6")),
                     "issued_tflops": issued, "issued_frac_of_pipe_peak": issued / pipe_peak,
                     "ms_per_launch": gemm_ms, "share_of_step": gemm_ms / ms_step_serial}
+        # ncu DRAM bytes per launch of the kernel that RAN (profiles/traffic.json, keyed by kernel name); a kernel
+        # without a capture is reported as such, never labelled with another kernel's bytes
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                roofline["traffic"] = json.load(f).get(kname)
-        except Exception:
-            pass
+                roofline["traffic"] = json.load(f)[kname]
+        except (OSError, KeyError, ValueError):
+            roofline["traffic_note"] = "no ncu --set full capture recorded in profiles/traffic.json for %r" % kname
+            print("bench.py: WARNING: profiles/traffic.json has no entry for %r -- roofline.traffic is null" % kname,
+                  file=sys.stderr)
     hbm = {}
     for n, per_seg in HBM_BYTES_PER_SEG.items():
         if n in kavg:
@@ -368,22 +457,20 @@ def run_ours(args, rank, local_rank, world):
 
     cpu = None
     if not args.no_cpu_baseline:
-        from oracle.cpu_path import CpuHotPath
         os.sched_setaffinity(0, all_cpus)                    # the CPU baseline gets every core again
         cores = len(all_cpus) or 1
         torch.set_num_threads(cores)
         cb = min(B, args.cpu_batch)
         audio = host[0][:cb].clone()
         cm = make_model(args, cb, None)
-        path = CpuHotPath()
+        path, cpu_kind, cpu_what = cpu_path()
         path.step(cm, to_float_cpu(audio))
         t0 = time.perf_counter()
         for _ in range(args.cpu_steps):
             path.step(cm, to_float_cpu(audio))[0].item()
         dt = (time.perf_counter() - t0) / args.cpu_steps
-        cpu = {"value": cb * SEG_SECONDS / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
-               "sample": "%d segments x %d steps of the same step on the host CPU (oracle/cpu_path.py: the reference's "
-                         "ATen op sequence)" % (cb, args.cpu_steps)}
+        cpu = {"value": cb * SEG_SECONDS / dt, "unit": "audio-s/s", "cores": cores, "kind": cpu_kind,
+               "sample": "%d segments x %d steps of the same step on the host CPU: %s" % (cb, args.cpu_steps, cpu_what)}
 
     line = {
         "metric": "audio-sec/s", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
@@ -413,6 +500,9 @@ def run_ours(args, rank, local_rank, world):
         "kernel_timing": "each entry point re-launched %d times back to back between one CUDA-event pair, rotating over "
                          "%d recorded working sets (> L2); the contraction's entry point includes the memset of "
                          "its Mel accumulator (38 MB for the two planes of the twice-folded kernel)" % (reps, n_rot),
+        "sustained": sustained,
+        "module_surface": surface,
+        "gpu_eager_baseline": gpu_eager,
         "roofline": roofline,
         "hbm_kernels": hbm,
         "cpu_baseline": cpu,
@@ -427,14 +517,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32, help="segments per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-batch", type=int, default=8, help="segments per CPU-baseline step")
-    ap.add_argument("--cpu-steps", type=int, default=100,
-                    help="steps of the CPU baseline (8 segments each: ~10 s of host work at the default)")
+    ap.add_argument("--cpu-batch", type=int, default=32,
+                    help="segments per CPU-baseline step (default: the same B=32 step as the GPU arm)")
+    ap.add_argument("--cpu-steps", type=int, default=30,
+                    help="steps of the CPU baseline (32 segments each: ~10 s of host work on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--input", default="pcm16", choices=["pcm16", "f32"],
                     help="audio format handed to the front-end: the dataset's PCM int16 (default) or float32")
     ap.add_argument("--streams", type=int, default=3,
                     help="replay the per-buffer graphs on this many alternating streams (device-resident run)")
+    ap.add_argument("--sustain-s", type=float, default=2.0,
+                    help="seconds of back-to-back graph replays for the `sustained` block (0: skip)")
+    ap.add_argument("--no-gpu-baselines", action="store_true",
+                    help="skip the module-surface leg and the reference's eager GPU path")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--model", default="injected", choices=["injected", "standin"],
                     help="the black-box network the VAT loop calls (see make_model)")

@@ -1,9 +1,10 @@
-"""Import the UNMODIFIED reference hot-path modules from /root/reference.
+"""Import the UNMODIFIED reference hot-path modules.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  Build-container only: the GPU
-box has no /root/reference, so nothing that runs there may call this; it is
-used by ``oracle/make_golden.py`` and by CPU tests that skip when the tree is
-absent.
+TEST INFRASTRUCTURE (see oracle/__init__.py).  The tree is looked for at ``$RECONVAT_REFERENCE``, then
+``/root/reference`` (build container), then ``oracle/_ref/reference`` -- the byte-for-byte snapshot that
+``__graft_entry__.build()`` makes with ``oracle/ref_snapshot.py`` so that the reference's own Python travels to
+the GPU box (git-ignored build output, never committed).  Used by ``oracle/make_golden.py``, by the tests
+(which skip when no tree is found) and by ``bench.py``'s reference legs.
 
 ``import model`` fails in this image because ``model/__init__.py:2-7`` pulls in
 sacred / mir_eval / mido / soundfile / matplotlib.  The hot-path modules
@@ -20,11 +21,26 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("RECONVAT_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    for cand in (os.environ.get("RECONVAT_REFERENCE"), "/root/reference", os.path.join(_HERE, "_ref", "reference")):
+        if cand and os.path.isdir(os.path.join(cand, "model")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "model"))
+
+
+def is_snapshot():
+    """True when the tree in use is the shipped oracle/_ref copy (GPU box), not /root/reference itself."""
+    return os.path.realpath(REFERENCE_ROOT).startswith(os.path.realpath(os.path.join(_HERE, "_ref")))
 
 
 _cached = None
@@ -89,4 +105,58 @@ def load_reference():
             if saved.get("model") is None:
                 ns.__dict__.setdefault("_mods", {})[k] = sys.modules.pop(k)
     _cached = ns
+    return ns
+
+
+_MODEL_MODULES = ("constants", "utils", "VAT", "self_attention_VAT", "UNet_onset", "onset_frame_VAT", "Segmentation",
+                  "decoding")
+_patched = {}
+
+
+def load_patched(attention=False, decoding=False):
+    """The same UNMODIFIED reference modules, imported a second time behind the product's seams: the package
+    ``reconvat_b200`` registered as ``nnAudio`` before the import and ``reconvat_b200.install()`` rebinding the VAT
+    classes / Normalization afterwards -- what a user's ``sitecustomize`` does.  Returns a namespace
+    like :func:`load_reference`, whose ``UNet`` / ``UNet_Onset`` / ``OnsetsAndFrames_VAT_full`` then run on librvb.so.
+    The module objects are distinct from the unpatched ones, so both flavours can live in one process."""
+    key = (bool(attention), bool(decoding))
+    if key in _patched:
+        return _patched[key]
+    if not available():
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    import reconvat_b200
+
+    names = ["model", "nnAudio", "nnAudio.utils", "nnAudio.librosa_functions", "nnAudio.Spectrogram", "matplotlib",
+             "matplotlib.pyplot"]
+    saved = {k: sys.modules.get(k) for k in names}
+    saved_model = {k: v for k, v in sys.modules.items() if k.startswith("model.")}
+    for k in saved_model:
+        del sys.modules[k]
+    try:
+        import matplotlib.pyplot  # noqa: F401
+    except Exception:
+        mpl = types.ModuleType("matplotlib")
+        mpl.__path__ = []
+        mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+        sys.modules.update({"matplotlib": mpl, "matplotlib.pyplot": mpl.pyplot})
+    pkg = types.ModuleType("model")
+    pkg.__path__ = [os.path.join(REFERENCE_ROOT, "model")]
+    sys.modules["model"] = pkg
+    sys.modules.pop("nnAudio", None)
+    ns = types.SimpleNamespace()
+    try:
+        reconvat_b200.install_nnaudio()                           # seam 1: before `import model`
+        for name in _MODEL_MODULES:
+            setattr(ns, name, importlib.import_module("model." + name))
+        ns.rebound = reconvat_b200.patch_reference(attention=attention, decoding=decoding)   # seam 2: after it
+        ns.Spectrogram = reconvat_b200.Spectrogram
+    finally:
+        ns._mods = {k: sys.modules.pop(k) for k in [k for k in sys.modules if k.startswith("model.")]}
+        sys.modules.update(saved_model)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _patched[key] = ns
     return ns

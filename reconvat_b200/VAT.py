@@ -26,9 +26,13 @@ What changes relative to the reference's op sequence (results identical within t
 * the chain rule through the row normalisation and the clamp mask, the ``*1e10``, the second
   normalisation, ``eps`` scaling, the clamp of ``x + r_adv`` and the recomputed ``_l2_normalize(d)``
   are one kernel (``rvb_vat_finalize``);
-* the two host-synchronising NaN asserts (:189-190) become a device flag: it is checked (and raises
-  the reference's AssertionError) at the next call, on ``check()``, or immediately with
-  ``strict=True`` / ``RVB_STRICT_NAN=1``.
+* the two host-synchronising NaN asserts (:189-190) become ONE device flag written by the finalisation kernel.
+  Eager calls test it synchronously, like the reference (one 4-byte read before the loss is handed back: a NaN
+  ``r_adv`` never reaches ``loss.backward()`` / ``optimizer.step()``).  ``strict=False`` (or ``RVB_STRICT_NAN=0``)
+  defers the test to the next call or an explicit ``check()`` -- for loops that must not synchronise every step and
+  call ``vat.check()`` before ``optimizer.step()`` themselves; inside a CUDA-graph capture there is no host round
+  trip at all and the owner of the graph tests ``last_flag`` (``pipeline.HotPathStep.check``).  The flavours whose
+  reference has no assert (model/VAT.py, self_attention_VAT.stepwise_VAT / onset_frame_VAT) never raise.
 """
 import os
 
@@ -53,6 +57,17 @@ def _check_input(x):
     if x.dtype != torch.float32:
         raise _lib.RvbError("reconvat_b200 VAT needs float32, got %s" % x.dtype)
     return x if x.is_contiguous() else x.contiguous()     # the reference hands over a transposed view
+
+
+def _draw_direction(x_in, x):
+    """``torch.randn_like(x)`` of the reference (model/self_attention_VAT.py:172) for the contiguous ``x`` the kernels
+    read.  The reference draws on the tensor it was handed -- a transposed view in ``run_on_batch`` (:1104) --, and
+    ``randn_like`` keeps those strides and fills in MEMORY order, so the element <-> noise mapping depends on them.
+    Drawing with the incoming strides and copying afterwards reproduces the reference's ``d`` bit for bit under the
+    same seed (the copy is one extra pass; contiguous inputs, what our own front-end hands over, take no copy)."""
+    if x_in.is_contiguous():
+        return torch.randn_like(x)
+    return torch.randn_like(x_in).contiguous()
 
 
 class _DivMean(torch.autograd.Function):
@@ -85,10 +100,18 @@ _workspaces = {}
 
 
 def _workspace(device):
-    ws = _workspaces.get(device)
+    """Default reduction workspace (ticket + per-block partials) of the divergence kernels: one per (device, current
+    stream).  Calls on one stream are ordered, so they may share it; calls in flight on different streams (side
+    streams, DataParallel threads) must not -- they would race on the ticket.  A zero-filled workspace is allocated
+    on the calling stream, so its memset is ordered before the first kernel that uses it."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
     if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.RvbError("reconvat_b200: the first divergence call on a stream allocates its reduction workspace; "
+                                "run the step once eagerly on this stream (or attach a VAT.Scratch) before capturing")
         ws = torch.zeros(_lib.BCE_WORKSPACE_FLOATS, dtype=torch.float32, device=device)
-        _workspaces[device] = ws
+        _workspaces[key] = ws
     return ws
 
 
@@ -177,6 +200,7 @@ class _VATCore(nn.Module):
     _clamp = True                  # (x + r).clamp(0, 1)
     _n_returns = 3
     _dict_loss = None              # names of the per-head losses when the loss is returned as a dict
+    _asserts = True                # the reference flavour asserts on NaN / Inf in r_adv (False: it never looks)
     _nan_message = ("r_adv has nan, d min={dmin} d max={dmax} d mean={dmean} please debug tune down the XI for VAT")
 
     def _init_common(self, XI, epsilon, n_power, KL_Div=False, binwise=False, strict=None):
@@ -185,7 +209,7 @@ class _VATCore(nn.Module):
         self.epsilon = epsilon
         self.KL_Div = KL_Div
         self.binwise = binwise
-        self.strict = bool(int(os.environ.get("RVB_STRICT_NAN", "0"))) if strict is None else strict
+        self.strict = bool(int(os.environ.get("RVB_STRICT_NAN", "1"))) if strict is None else bool(strict)
         self._pending = None       # (pinned host copy of the NaN flag, event) of the previous eager call
         self._host_flag = None     # persistent pinned int32 (allocated once: no per-call cudaHostAlloc)
         self.last_flag = None      # device flag of the latest call (what a captured CUDA graph leaves behind)
@@ -204,6 +228,9 @@ class _VATCore(nn.Module):
         """Raise the reference's AssertionError if the previous call produced NaN/Inf in r_adv.
         ``flag``: a device flag to test instead (e.g. ``last_flag`` after replaying a captured graph; this
         synchronises with the device)."""
+        if not self._asserts:
+            self._pending = None
+            return
         if flag is not None:
             bad = int(flag.item()) != 0
         elif self._pending is not None:
@@ -226,6 +253,7 @@ class _VATCore(nn.Module):
         return (_lib.DIV_BKL if self.KL_Div else _lib.DIV_BCE,) * len(self._heads)
 
     def forward(self, model, x):
+        x_in = x
         x = _check_input(x).detach()
         if not torch.cuda.is_current_stream_capturing():
             self.check()
@@ -233,7 +261,7 @@ class _VATCore(nn.Module):
         with torch.no_grad():
             y_ref = [y.detach() for y in self._model_outputs(model, x)]   # labels, no grad (…:163-164)
 
-        d = torch.randn_like(x)                                           # same global Philox stream (…:172)
+        d = _draw_direction(x_in, x)                                      # same global Philox stream (…:172)
         sc = self.scratch if not self.binwise else None
         div_ws = None if self.scratch is None else self.scratch.div
         if sc is not None:
@@ -288,7 +316,7 @@ class _VATCore(nn.Module):
 
         self.last_flag = flag
         self.last_r_norm_mean = r_norm_mean if sc is not None else None
-        if not torch.cuda.is_current_stream_capturing():
+        if self._asserts and not torch.cuda.is_current_stream_capturing():
             # inside a CUDA-graph capture there is no host round trip: the owner of the graph tests last_flag
             if self._host_flag is None:
                 self._host_flag = torch.empty((), dtype=torch.int32, pin_memory=True)
@@ -313,9 +341,10 @@ class _VATCore(nn.Module):
 
 
 class stepwise_VAT_vatpy(_VATCore):
-    """model/VAT.py:9-40 -- ``stepwise_VAT(XI, epsilon, n_power)``; no clamp, returns (vat_loss, r_adv)."""
+    """model/VAT.py:9-40 -- ``stepwise_VAT(XI, epsilon, n_power)``; no clamp, no assert, returns (vat_loss, r_adv)."""
     _clamp = False
     _n_returns = 2
+    _asserts = False
 
     def __init__(self, XI, epsilon, n_power, strict=None):
         super().__init__()
@@ -323,7 +352,9 @@ class stepwise_VAT_vatpy(_VATCore):
 
 
 class stepwise_VAT(_VATCore):
-    """model/self_attention_VAT.py:101-145 -- ``stepwise_VAT(XI, epsilon, n_power, KL_Div, binwise=False)``."""
+    """model/self_attention_VAT.py:101-145 -- ``stepwise_VAT(XI, epsilon, n_power, KL_Div, binwise=False)``; the
+    reference has no NaN assert in this flavour."""
+    _asserts = False
 
     def __init__(self, XI, epsilon, n_power, KL_Div, binwise=False, strict=None):
         super().__init__()
@@ -343,8 +374,9 @@ class UNet_VAT(_VATCore):
 
 class onset_frame_VAT(_VATCore):
     """model/self_attention_VAT.py:204-238 -- ``onset_frame_VAT(XI, epsilon, n_power)``; the model returns a
-    3-tuple whose first element is the posterior; returns (vat_loss, r_adv)."""
+    3-tuple whose first element is the posterior; returns (vat_loss, r_adv); no NaN assert in the reference."""
     _n_returns = 2
+    _asserts = False
 
     def __init__(self, XI, epsilon, n_power, strict=None):
         super().__init__()

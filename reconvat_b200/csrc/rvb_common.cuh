@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 
 #include "../../include/rvb.h"
 
@@ -16,6 +17,13 @@ namespace rvb {
 // ---- host-side error plumbing (thread-local last-error string, see rvb_last_error) ----
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);           // cudaGetLastError -> RVB_ERR_LAUNCH
+
+// Function attributes (opt-in dynamic shared memory, cluster occupancy) and the SM count belong to a DEVICE, not to the
+// process: host-side caches of them are arrays indexed by device_slot() and are read / written under attr_mutex()
+// (one process may drive several GPUs from several threads -- nn.DataParallel).
+constexpr int kMaxDevices = 64;
+int device_slot();                            // cudaGetDevice(), folded into [0, kMaxDevices)
+std::mutex& attr_mutex();
 
 #define RVB_REQUIRE(cond, ...)                              \
   do {                                                      \
@@ -78,6 +86,10 @@ __device__ __forceinline__ float div_by(float a, float b, float rcp_b) {
 
 // torch.clamp(v, 0, 1): NaN propagates (fminf/fmaxf would drop it).
 __device__ __forceinline__ float clamp01(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
+
+// std::max(v, lo) / torch.clamp(v, lo, hi) as ATen evaluates them: a NaN in `v` comes out as NaN.
+__device__ __forceinline__ float max_nan(float v, float lo) { return v < lo ? lo : v; }
+__device__ __forceinline__ float clamp_nan(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // Monotone float -> uint32 key (works with a zero-initialised atomicMax target:
 // every finite/inf float maps above 0).  NaN (positive payload) maps above +inf.

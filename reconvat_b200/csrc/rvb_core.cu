@@ -25,6 +25,17 @@ int check_launch(const char* what) {
   return RVB_OK;
 }
 
+int device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 ? 0 : dev % kMaxDevices;
+}
+
+std::mutex& attr_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 }  // namespace rvb

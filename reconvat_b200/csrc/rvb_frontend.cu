@@ -1002,10 +1002,14 @@ extern "C" int rvb_logmel_normalise(const float* mel, const float* mel_b, int n_
   // another stream (with RVB_FOLD2_STAGES=3 leaving it 82 KB of shared memory)
   static const int n_threads = [] { const char* e = getenv("RVB_NORM_THREADS"); return (e && atoi(e) == 256) ? 256 : kNormThreadsMax; }();
   auto kernel = n_threads == 256 ? logmel_normalise_cluster_kernel<256> : logmel_normalise_cluster_kernel<kNormThreadsMax>;
-  static size_t smem_set = 48 * 1024;                      // the attribute call is not free: once per new maximum
-  if (smem > smem_set) {
-    RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  {
+    static size_t smem_set[kMaxDevices] = {};              // the attribute call is not free: once per device and new maximum
+    const int slot = device_slot();
+    std::lock_guard<std::mutex> g(attr_mutex());
+    if (smem > 48 * 1024 && smem > smem_set[slot]) {
+      RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set[slot] = smem;
+    }
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)n_seg * kNormCluster);

@@ -1440,14 +1440,16 @@ static int make_map_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64
 }
 
 static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
+  static int n[kMaxDevices] = {};
+  const int slot = device_slot();
+  std::lock_guard<std::mutex> g(attr_mutex());
+  if (n[slot] == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cudaDeviceGetAttribute(&n[slot], cudaDevAttrMultiProcessorCount, dev);
+    if (n[slot] <= 0) n[slot] = 148;
   }
-  return n;
+  return n[slot];
 }
 
 }  // namespace rvb
@@ -1488,10 +1490,14 @@ extern "C" int rvb_stft_gemm(const float* sig_hi, const float* sig_lo, int n_seg
   p.n_store_bins = n_out_bins < n_basis_rows / 2 ? n_out_bins : n_basis_rows / 2;
   p.power = power; p.out0 = out0; p.dbg_status = nullptr;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    RVB_CUDA(cudaFuncSetAttribute(stft_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+  {
+    static bool attr_set[kMaxDevices] = {};
+    const int slot = device_slot();
+    std::lock_guard<std::mutex> g(attr_mutex());
+    if (!attr_set[slot]) {
+      RVB_CUDA(cudaFuncSetAttribute(stft_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_set[slot] = true;
+    }
   }
   const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
   const int grid = (int)(n_units < num_sms() ? n_units : num_sms());
@@ -1562,16 +1568,22 @@ static int launch_folded(const char* who, const void* a_hi, const void* a_lo, co
       if ((rc = make_map_2d(&tm_b_hi, basis_hi, half, 2 * (uint64_t)n_bins_pad, kBlockK, 64, kElem)) != RVB_OK) return rc;
       if ((rc = make_map_2d(&tm_b_lo, basis_lo, half, 2 * (uint64_t)n_bins_pad, kBlockK, 64, kElem)) != RVB_OK) return rc;
       p.m_tiles = (int)((m_rows + 255) / 256);
-      static int max_clusters = 0;
-      if (max_clusters == 0) {
-        RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_pair_kernel<NoTable>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-        RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_pair_kernel<MelTable>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-        cudaLaunchConfig_t qc = {};
-        qc.gridDim = dim3(num_sms() & ~1u); qc.blockDim = dim3(P_NUM_THREADS); qc.dynamicSmemBytes = P_SMEM_BYTES;
-        int nc = 0;
-        RVB_CUDA(cudaOccupancyMaxActiveClusters(&nc, stft_gemm_fold_pair_kernel<MelTable>, &qc));
-        RVB_REQUIRE(nc > 0, "%s: no CTA pair fits on this device", who);
-        max_clusters = nc < num_sms() / 2 ? nc : num_sms() / 2;
+      static int max_clusters_dev[kMaxDevices] = {};
+      const int sms = num_sms(), slot = device_slot();
+      int max_clusters;
+      {
+        std::lock_guard<std::mutex> g(attr_mutex());
+        if (max_clusters_dev[slot] == 0) {
+          RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_pair_kernel<NoTable>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+          RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_pair_kernel<MelTable>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+          cudaLaunchConfig_t qc = {};
+          qc.gridDim = dim3(sms & ~1u); qc.blockDim = dim3(P_NUM_THREADS); qc.dynamicSmemBytes = P_SMEM_BYTES;
+          int nc = 0;
+          RVB_CUDA(cudaOccupancyMaxActiveClusters(&nc, stft_gemm_fold_pair_kernel<MelTable>, &qc));
+          RVB_REQUIRE(nc > 0, "%s: no CTA pair fits on this device", who);
+          max_clusters_dev[slot] = nc < sms / 2 ? nc : sms / 2;
+        }
+        max_clusters = max_clusters_dev[slot];
       }
       const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
       const int n_clusters = (int)(n_units < max_clusters ? n_units : max_clusters);
@@ -1591,10 +1603,14 @@ static int launch_folded(const char* who, const void* a_hi, const void* a_lo, co
     }
   }
   RVB_REQUIRE(!mel, "%s: the Mel epilogue lives in the CTA-pair kernel (unset RVB_GEMM_1CTA)", who);
-  static bool attr_set = false;
-  if (!attr_set) {
-    RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_kernel<kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
-    attr_set = true;
+  {
+    static bool attr_set[kMaxDevices] = {};
+    const int slot = device_slot();
+    std::lock_guard<std::mutex> g(attr_mutex());
+    if (!attr_set[slot]) {
+      RVB_CUDA(cudaFuncSetAttribute(stft_gemm_fold_kernel<kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+      attr_set[slot] = true;
+    }
   }
   const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
   const int grid = (int)(n_units < num_sms() ? n_units : num_sms());
@@ -1672,21 +1688,27 @@ extern "C" int rvb_stft_mel_folded2_f16(const void* a_hi, const void* a_lo, cons
   // RVB_FOLD2_STAGES=3: a 3-stage operand ring (144 KB of shared memory instead of 192 KB leaves room for blocks of the
   // HBM kernels of other streams beside a resident CTA)
   static const bool three = [] { const char* e = getenv("RVB_FOLD2_STAGES"); return e && atoi(e) == 3; }();
-  static int max_clusters[2] = {0, 0};
+  static int max_clusters_dev[kMaxDevices][2] = {};
   const int smem = n64 ? Q_SMEM_BYTES : (three ? 3 : P_STAGES) * P_STAGE_BYTES + BAR_BYTES + 1024;
   auto kernel = n64 ? stft_gemm_fold2_pair_kernel
                     : (three ? stft_gemm_fold2c_pair_kernel<3> : stft_gemm_fold2c_pair_kernel<P_STAGES>);
-  if (max_clusters[n64] == 0) {
-    RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    cudaLaunchConfig_t qc = {};
-    qc.gridDim = dim3(num_sms() & ~1u); qc.blockDim = dim3(P_NUM_THREADS); qc.dynamicSmemBytes = smem;
-    int nc = 0;
-    RVB_CUDA(cudaOccupancyMaxActiveClusters(&nc, kernel, &qc));
-    RVB_REQUIRE(nc > 0, "%s: no CTA pair fits on this device", who);
-    max_clusters[n64] = nc < num_sms() / 2 ? nc : num_sms() / 2;
+  const int sms = num_sms(), slot = device_slot();
+  int max_clusters;
+  {
+    std::lock_guard<std::mutex> g(attr_mutex());
+    if (max_clusters_dev[slot][n64] == 0) {
+      RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(sms & ~1u); qc.blockDim = dim3(P_NUM_THREADS); qc.dynamicSmemBytes = smem;
+      int nc = 0;
+      RVB_CUDA(cudaOccupancyMaxActiveClusters(&nc, kernel, &qc));
+      RVB_REQUIRE(nc > 0, "%s: no CTA pair fits on this device", who);
+      max_clusters_dev[slot][n64] = nc < sms / 2 ? nc : sms / 2;
+    }
+    max_clusters = max_clusters_dev[slot][n64];
   }
   const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles * (n64 ? 1 : 2);
-  const int n_clusters = (int)(n_units < max_clusters[n64] ? n_units : max_clusters[n64]);
+  const int n_clusters = (int)(n_units < max_clusters ? n_units : max_clusters);
   static thread_local MelTable tab;
   std::memset(&tab, 0, sizeof(tab));
   std::memcpy(tab.e, mel_tab, sizeof(float4) * (size_t)(2 * quarter));

@@ -296,14 +296,14 @@ vat_finalize_binwise_kernel(const float* __restrict__ g, const float* __restrict
 template <int kKind>
 __device__ __forceinline__ float div_grad_one(float p, float y, float s) {
   if constexpr (kKind == RVB_DIV_BCE) {
-    return (p - y) / fmaxf((1.f - p) * p, 1e-12f) * s;                    // ATen's binary_cross_entropy_backward
+    return (p - y) / max_nan((1.f - p) * p, 1e-12f) * s;                  // ATen's binary_cross_entropy_backward
   } else if constexpr (kKind == RVB_DIV_BKL) {
     // d/dq0 [q0 (log q0 - log p0) + q1 (log q1 - log p1)], q1 = 1 - q0; torch.clamp passes the gradient on the
     // closed interval only
-    const float q0 = fminf(fmaxf(p, 1e-4f), 0.9999f), p0 = fminf(fmaxf(y, 1e-4f), 0.9999f);
+    const float q0 = clamp_nan(p, 1e-4f, 0.9999f), p0 = clamp_nan(y, 1e-4f, 0.9999f);
     const float q1 = 1.f - q0, p1 = 1.f - p0;
     const float g = (logf(q0) - logf(p0)) - (logf(q1) - logf(p1));
-    return (p >= 1e-4f && p <= 0.9999f) ? g * s : 0.f;
+    return (p >= 1e-4f && p <= 0.9999f) ? g * s : (p != p ? p : 0.f);    // NaN in -> NaN out, as autograd does
   } else {
     return 2.f * (p - y) * s;
   }
@@ -343,10 +343,12 @@ __device__ __forceinline__ float bce_one(float p, float y) {
     // outside [0.5, 2], 1 ulp inside): libm's logf + log1pf are ~80 instructions per element and made this 14 MB
     // reduction compute-bound (4.7 M warp instructions, profiles/r01f); the per-element error is unbiased and four
     // orders below the 1e-3 budget of the VAT loss.  log(0) = -inf and the -100 clamp behave as in ATen.
-    return (y - 1.f) * fmaxf(__logf(1.f - p), -100.f) - y * fmaxf(__logf(p), -100.f);
+    // max_nan / clamp_nan: like ATen's std::max and torch.clamp, a NaN posterior gives a NaN loss (fmaxf would turn it
+    // into a finite 100 and hide a diverged network from the logged VAT loss)
+    return (y - 1.f) * max_nan(__logf(1.f - p), -100.f) - y * max_nan(__logf(p), -100.f);
   } else if constexpr (kKind == RVB_DIV_BKL) {
     // kl_div(input = log [p0, p1], target = [q0, q1]) pointwise: q log q - q input, summed over the pair
-    const float q0 = fminf(fmaxf(p, 1e-4f), 0.9999f), p0 = fminf(fmaxf(y, 1e-4f), 0.9999f);
+    const float q0 = clamp_nan(p, 1e-4f, 0.9999f), p0 = clamp_nan(y, 1e-4f, 0.9999f);
     const float q1 = 1.f - q0, p1 = 1.f - p0;
     return (q0 * logf(q0) - q0 * logf(p0)) + (q1 * logf(q1) - q1 * logf(p1));
   } else {
