@@ -1,6 +1,7 @@
 """CPU tests of the host-side logic: basis builders (bit-exact against the reference-generated golden
 tables), banded filterbank, tf32 split, module surface / state dict, geometry and error behaviour,
 the install() seam, the no-CPU-fallback rule, the injected transcriber."""
+import os
 import sys
 import types
 
@@ -247,6 +248,50 @@ def test_install_rebinds_the_reference_modules(monkeypatch):
     from nnAudio.utils import create_fourier_kernels
     from nnAudio.librosa_functions import mel
     assert create_fourier_kernels(512, freq_scale="no")[0].shape == (257, 1, 512) and mel(16000, 512).shape == (128, 257)
+
+
+def test_install_on_the_real_reference_classes():
+    """The seam on the reference's OWN modules (not fakes): imported behind install(), ``UNet`` / ``UNet_Onset`` /
+    ``OnsetsAndFrames_VAT_full`` construct our MelSpectrogram / VAT / Normalization, their state_dicts are
+    interchangeable with the unpatched models' (transcribe_files.py:71 loads strictly) and, built from the same seed,
+    bit-identical -- buffers (wsin, wcos, window_mask, mel_basis) included."""
+    import torch
+    from oracle import reference_loader as RL
+    if not RL.available():
+        pytest.skip("no reference tree (/root/reference or the oracle/_ref snapshot made by build())")
+    ref, pat = RL.load_reference(), RL.load_patched()
+    assert ("model.self_attention_VAT", "UNet_VAT") in pat.rebound and ("model.UNet_onset", "UNet_VAT") in pat.rebound
+    assert sys.modules.get("model") is None or not hasattr(sys.modules["model"], "__reconvat_test__")
+    cases = [("self_attention_VAT", "UNet", ((2, 2), (2, 2)), dict(spec="Mel", XI=1e-6, eps=2), R.VAT.UNet_VAT),
+             ("UNet_onset", "UNet_Onset", ((2, 2), (2, 2)), dict(spec="Mel"), R.VAT.UNet_VAT_onset),
+             ("onset_frame_VAT", "OnsetsAndFrames_VAT_full", (229, 88), {}, R.VAT.stepwise_VAT_onf)]
+    for mod, cls, args, kw, vat_cls in cases:
+        torch.manual_seed(0)
+        a = getattr(getattr(ref, mod), cls)(*args, **kw)
+        torch.manual_seed(0)
+        b = getattr(getattr(pat, mod), cls)(*args, **kw)
+        assert type(b.spectrogram) is R.Spectrogram.MelSpectrogram and type(b.vat_loss) is vat_cls
+        assert type(b.normalize) is R.utils.Normalization
+        assert type(a.spectrogram).__module__ == "model.Spectrogram"          # the unpatched flavour stays unpatched
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb)
+        assert all(torch.equal(sa[k], sb[k]) for k in sa), cls
+        b.load_state_dict(sa, strict=True)
+        a.load_state_dict(sb, strict=True)
+        assert b.vat_loss.XI == a.vat_loss.XI and b.vat_loss.epsilon == a.vat_loss.epsilon
+
+
+def test_reference_snapshot_recipe(tmp_path):
+    """oracle/ref_snapshot.py copies byte for byte and verifies by sha256 (what build() ships to the GPU box)."""
+    from oracle import ref_snapshot, reference_loader as RL
+    if not RL.available():
+        pytest.skip("no reference tree")
+    dest = str(tmp_path / "reference")
+    manifest = ref_snapshot.materialise(source=RL.REFERENCE_ROOT, dest=dest, quiet=True)
+    assert manifest and "model/self_attention_VAT.py" in manifest["files"] and ref_snapshot.verify(dest)
+    with open(os.path.join(dest, "model", "VAT.py"), "a") as f:
+        f.write("# tampered\n")
+    assert not ref_snapshot.verify(dest)
 
 
 def test_install_opt_in_attention_and_decoding(monkeypatch):
