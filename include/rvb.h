@@ -204,6 +204,26 @@ int rvb_fold_split2_f16_pcm16(const int16_t* audio, int64_t audio_ld, float gain
 int rvb_stft_mel_folded2_f16(const void* a_hi, const void* a_lo, const float* row_scale_inv, int n_seg, int n_frames,
                              int n_fft, const void* basis_hi, const void* basis_lo, float basis_scale_inv,
                              const float* mel_tab, int n_mels, float* mel_out, rvb_stream_t stream);
+/*
+ * K0x / K1x  the twice-folded contraction WITHOUT materialised frame planes (PCM16 input, the dataset's storage format,
+ * model/dataset.py:19-62; same references as K0q / K1q: model/Spectrogram.py:209-231, :458, :460).  K0q writes every
+ * sample four times as fp16 hi/lo of e and o (16 bytes per sample of the hop) and K1q reads that back; here
+ *   rvb_pad_parity_pcm16: reflect-pads the signal (or constant / none, as rvb_fold_split*) and stores it ONCE, split by
+ *     sample parity, in offset binary: planes[q][b][i] = padded sample 2 i + q of segment b, + 32768 (uint16; 32768
+ *     past the end).  plane_len: rvb_parity_plane_len(...) elements (a multiple of 8), planes 128-byte aligned.
+ *   rvb_stft_mel_fused_pcm16: converter warps inside the tcgen05 kernel read those planes, form e = p[n] + p[N-n] /
+ *     o = p[n] - p[N-n] exactly, split them into fp16 hi + lo and write the swizzled operand tiles in shared memory;
+ *     contraction, epilogue, basis layout, Mel table and mel_out exactly as rvb_stft_mel_folded2_f16, except that the
+ *     basis carries HALF the weight in the centre column of the even-n cos chain (the centre sample is its own
+ *     partner: e = 2 p[N/2]; basis.fold2_operand(centre_doubled=True)).  gain: the PCM scale (1/32768), a power of two.
+ *     hop: a multiple of 16.
+ */
+int64_t rvb_parity_plane_len(int n_samples, int pad, int pad_mode, int n_fft, int hop, int n_frames);
+int rvb_pad_parity_pcm16(const int16_t* audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int pad_mode,
+                         uint16_t* planes, int64_t plane_len, rvb_stream_t stream);
+int rvb_stft_mel_fused_pcm16(const uint16_t* planes, int64_t plane_len, int n_seg, int n_frames, int n_fft, int hop,
+                             float gain, const void* basis_hi, const void* basis_lo, float basis_scale_inv,
+                             const float* mel_tab, int n_mels, float* mel_out, rvb_stream_t stream);
 int rvb_logmel_minmax(const float* mel, int n_seg, int64_t n_per_seg, float log_offset, uint32_t* minmax,
                       rvb_stream_t stream);
 int rvb_logmel_transpose(const float* mel, int n_seg, int n_mels, int n_frames, float log_offset,

@@ -85,7 +85,7 @@ class STFT(nn.Module):
             wcos = self.wcos[:, 0, :].detach().cpu().numpy()
             wsin = self.wsin[:, 0, :].detach().cpu().numpy()
             dev = self.wsin.device
-            tb = dict(n_bins=wcos.shape[0], fold=None, fold2=None, direct=None)
+            tb = dict(n_bins=wcos.shape[0], fold=None, fold2=None, fold2x=None, direct=None)
             # RVB_STFT_OPERAND=tf32 keeps the 3xTF32 planes (half the MMA rate; kept for A/B measurements)
             operand = os.environ.get("RVB_STFT_OPERAND", "f16")
             fold = None if os.environ.get("RVB_NO_FOLD") else basis.fold_operand(wcos, wsin, operand=operand)
@@ -102,6 +102,12 @@ class STFT(nn.Module):
                         for k in ("basis_hi", "basis_lo"):
                             f2[k] = torch.from_numpy(np.ascontiguousarray(f2[k])).to(dev)
                         tb["fold2"] = f2
+                        # ... and its twin for the contraction that folds in-kernel (PCM16 input): half the weight in
+                        # the centre column, where the converter's e = p[n] + p[N-n] counts the sample twice
+                        fx = basis.fold2_operand(wcos, wsin, centre_doubled=True)
+                        for k in ("basis_hi", "basis_lo"):
+                            fx[k] = torch.from_numpy(np.ascontiguousarray(fx[k])).to(dev)
+                        tb["fold2x"] = fx
             else:
                 hi, lo, n_gemm, leftover = basis.gemm_operand(wcos, wsin)
                 tb["direct"] = dict(basis_hi=torch.from_numpy(hi).to(dev), basis_lo=torch.from_numpy(lo).to(dev),
@@ -173,6 +179,20 @@ class STFT(nn.Module):
             p0 = torch.empty((M,), dtype=torch.float32, device=x.device) if fd["w0"] != 0.0 else None
             p0_ptr = None if p0 is None else p0.data_ptr()
             if fd["operand"] == "f16":
+                if mel_tab2 is not None and pcm16 and tb["fold2x"] is not None and self.stride % 16 == 0 \
+                        and 2 * B * (n_frames * self.stride + self.n_fft) < 2 ** 31 \
+                        and not os.environ.get("RVB_NO_FUSED_FOLD"):
+                    # K0x / K1x: no materialised frame planes.  The padded PCM16 signal is stored once, split by sample
+                    # parity (2 bytes per sample); the contraction's converter warps fold / scale / split in-kernel
+                    fx = tb["fold2x"]
+                    plane_len = _lib.parity_plane_len(L, self.pad_amount, mode, self.n_fft, self.stride, n_frames)
+                    sig = torch.empty((2, B, plane_len), dtype=torch.int16, device=x.device)
+                    _lib.call("rvb_pad_parity_pcm16", _lib.ptr(x2, torch.int16), ld, B, L, self.pad_amount, mode,
+                              sig.data_ptr(), plane_len)
+                    _lib.call("rvb_stft_mel_fused_pcm16", sig.data_ptr(), plane_len, B, n_frames, self.n_fft,
+                              self.stride, 1.0 / 32768.0, fx["basis_hi"].data_ptr(), fx["basis_lo"].data_ptr(),
+                              fx["scale_inv"], mel_tab2.ctypes.data, n_out_bins, _lib.ptr(out))
+                    return out, n_frames
                 planes = torch.empty((2, 2, M, half), dtype=torch.float16, device=x.device)  # [hi|lo][e|o][frame][c]
                 row_inv = torch.empty((M,), dtype=torch.float32, device=x.device)
                 if mel_tab2 is not None:

@@ -31,6 +31,8 @@ SIGNATURES = {
     "rvb_fold_split2_f16": [_c_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _c_p, _c_p, _c_p, _c_p],
     "rvb_fold_split2_f16_pcm16": [_c_p, _i64, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _c_p, _c_p, _c_p, _c_p],
     "rvb_stft_mel_folded2_f16": [_c_p, _c_p, _c_p, _i32, _i32, _i32, _c_p, _c_p, _f32, _c_p, _i32, _c_p, _c_p],
+    "rvb_pad_parity_pcm16": [_c_p, _i64, _i32, _i32, _i32, _i32, _c_p, _i64],
+    "rvb_stft_mel_fused_pcm16": [_c_p, _i64, _i32, _i32, _i32, _i32, _f32, _c_p, _c_p, _f32, _c_p, _i32, _c_p],
     "rvb_logmel_minmax": [_c_p, _i32, _i64, _f32, _c_p, _c_p],
     "rvb_logmel_transpose": [_c_p, _i32, _i32, _i32, _f32, _c_p, _c_p, _c_p],
     "rvb_logmel_normalise": [_c_p, _c_p, _i32, _i32, _i32, _f32, _c_p, _c_p, _c_p],
@@ -88,6 +90,8 @@ def load():
     lib.rvb_launch_count.restype = ctypes.c_int64
     lib.rvb_vat_stats_workspace_bytes.restype = ctypes.c_int64
     lib.rvb_vat_stats_workspace_bytes.argtypes = [_i64]
+    lib.rvb_parity_plane_len.restype = ctypes.c_int64
+    lib.rvb_parity_plane_len.argtypes = [_i32, _i32, _i32, _i32, _i32, _i32]
     if lib.rvb_abi_version() != ABI_VERSION:
         raise ImportError("reconvat_b200: librvb.so has ABI %d, the Python side expects %d -- rebuild"
                           % (lib.rvb_abi_version(), ABI_VERSION))
@@ -102,6 +106,10 @@ def load():
 def launch_count():
     """Kernels launched by librvb.so in this process so far (bench.py reports the delta)."""
     return int(load().rvb_launch_count())
+
+
+def parity_plane_len(n_samples, pad, pad_mode, n_fft, hop, n_frames):
+    return int(load().rvb_parity_plane_len(int(n_samples), int(pad), int(pad_mode), int(n_fft), int(hop), int(n_frames)))
 
 
 def vat_stats_workspace_bytes(n_rows):

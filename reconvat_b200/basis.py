@@ -311,7 +311,7 @@ def fold_operand(wcos, wsin, tol=2.5e-7, operand="tf32"):
 FOLD2_TILE_K = 128            # k-values per tile of the twice-folded contraction (rvb_stft_gemm.cu)
 
 
-def fold2_operand(wcos, wsin, tol=2.5e-7):
+def fold2_operand(wcos, wsin, tol=2.5e-7, centre_doubled=False):
     """Operand of the TWICE-folded contraction, or None when the basis does not have the second symmetry.
 
     On top of :func:`fold_operand` (n <-> N-n), a full-resolution basis (integer bins k = 0 .. N/2) satisfies
@@ -326,7 +326,12 @@ def fold2_operand(wcos, wsin, tol=2.5e-7):
 
     Returns dict(basis_hi, basis_lo: float16 [4 * n_k, N/4] planes, chains Ce | Co | Se | So, row r <-> k = r + 1;
     columns of a chain ordered by increasing n of its parity; n_k = N/4; scale_inv).  The matching frame planes
-    carry the even-n columns first, then the odd-n ones (``rvb_fold_split2_f16``)."""
+    carry the even-n columns first, then the odd-n ones (``rvb_fold_split2_f16``).
+
+    ``centre_doubled=True``: the operand of the contraction that folds in-kernel (``rvb_stft_mel_fused_pcm16``).  Its
+    converter forms e[n] = p[n] + p[N-n] for EVERY column, so the centre sample n = N/2 (its own partner; last column
+    of the even-n chain) arrives as 2 p[N/2]: that column of the cos rows carries half the weight (exact: a power of
+    two).  The sin rows are zero there either way."""
     F, N = wcos.shape
     if N % 512 != 0 or N > 2048 or F != N // 2 + 1:
         return None
@@ -352,6 +357,9 @@ def fold2_operand(wcos, wsin, tol=2.5e-7):
     S = 0.5 * (bs[k] - sgn * bs[half - k])
     even, odd = np.flatnonzero(n % 2 == 0), np.flatnonzero(n % 2 == 1)
     mat = np.concatenate([C[:, even], C[:, odd], S[:, even], S[:, odd]], axis=0)     # [4 * n_k, N/4]
+    if centre_doubled:
+        assert n[even[-1]] == half
+        mat[:quarter, quarter - 1] *= 0.5
     hi, lo, scale_inv = f16_split64(mat)
     return dict(basis_hi=hi, basis_lo=lo, n_k=quarter, scale_inv=scale_inv, even_cols=even, odd_cols=odd)
 

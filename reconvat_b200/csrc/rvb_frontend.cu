@@ -1100,3 +1100,87 @@ extern "C" int rvb_note_offsets(const float* onsets, const float* frames, int n_
   rvb::count_launch();
   return rvb::check_launch("note_offsets_kernel");
 }
+
+// ---------------------------------------------------------------- K0x: pad + parity split of the raw PCM16 signal
+// The fused contraction (rvb_stft_mel_fused_pcm16, rvb_stft_gemm.cu) folds, scales and hi/lo-splits the frame rows
+// itself.  What it reads is the reflect-padded signal (model/Spectrogram.py:209-218) split by SAMPLE PARITY -- the
+// twice-folded contraction runs one chain over the even n and one over the odd n of a frame, and frames start at even
+// samples -- and stored in OFFSET BINARY (u = x + 32768): the converter turns a sample into a float with one byte
+// permute (0x4AC00000 | u is the float 1.5 * 2^22 + u / 2).  2 bytes per sample: the materialised fp16 frame planes of
+// K0q are 16.  planes: [2][n_seg][plane_len] uint16, plane q element i = padded sample 2 i + q (32768 past the end).
+namespace rvb {
+
+__global__ void __launch_bounds__(256)
+pad_parity_pcm16_kernel(const int16_t* __restrict__ audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int mode,
+                        uint16_t* __restrict__ planes, int64_t plane_len) {
+  const int64_t groups_per_seg = plane_len >> 3;           // 8 plane elements of each parity = 16 padded samples
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= groups_per_seg * n_seg) return;
+  const int b = (int)(g / groups_per_seg);
+  const int64_t i0 = (g - (int64_t)b * groups_per_seg) << 3;
+  const int64_t padded = (mode == RVB_PAD_NONE) ? n_samples : (int64_t)n_samples + 2 * pad;
+  const int off = (mode == RVB_PAD_NONE) ? 0 : pad;
+  const int16_t* a = audio + (int64_t)b * audio_ld;
+  const int64_t j0 = 2 * i0 - off;                          // source index of the first of the 16 samples
+  uint4 even, odd;
+  if (j0 >= 0 && j0 + 16 <= n_samples && ((reinterpret_cast<uintptr_t>(a + j0) & 15u) == 0)) {
+    const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(a + j0));
+    const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(a + j0) + 1);
+    // (s0 s1)(s2 s3) -> even (s0 s2), odd (s1 s3); x ^ 0x8000 = x + 32768 mod 2^16
+    even.x = __byte_perm(v0.x, v0.y, 0x5410) ^ 0x80008000u; odd.x = __byte_perm(v0.x, v0.y, 0x7632) ^ 0x80008000u;
+    even.y = __byte_perm(v0.z, v0.w, 0x5410) ^ 0x80008000u; odd.y = __byte_perm(v0.z, v0.w, 0x7632) ^ 0x80008000u;
+    even.z = __byte_perm(v1.x, v1.y, 0x5410) ^ 0x80008000u; odd.z = __byte_perm(v1.x, v1.y, 0x7632) ^ 0x80008000u;
+    even.w = __byte_perm(v1.z, v1.w, 0x5410) ^ 0x80008000u; odd.w = __byte_perm(v1.z, v1.w, 0x7632) ^ 0x80008000u;
+  } else {
+    uint32_t w[8];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int64_t pi = 2 * i0 + e;
+      int v = 0;
+      if (pi < padded) {
+        int64_t j = pi - off;
+        bool zero = false;
+        if (j < 0) { if (mode == RVB_PAD_REFLECT) j = -j; else zero = true; }
+        else if (j >= n_samples) { if (mode == RVB_PAD_REFLECT) j = 2 * (int64_t)(n_samples - 1) - j; else zero = true; }
+        if (!zero && j >= 0 && j < n_samples) v = a[j];
+      }
+      const uint32_t u = (uint32_t)(v + 32768) & 0xffffu;
+      // e = 2 m + q: element m of parity q; two elements per 32-bit word
+      const int q = e & 1, m = e >> 1;
+      uint32_t& word = w[q * 4 + (m >> 1)];
+      word = (m & 1) ? (word | (u << 16)) : u;
+    }
+    even = make_uint4(w[0], w[1], w[2], w[3]);
+    odd = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+  uint16_t* pe = planes + (int64_t)b * plane_len + i0;
+  uint16_t* po = planes + ((int64_t)n_seg + b) * plane_len + i0;
+  *reinterpret_cast<uint4*>(pe) = even;
+  *reinterpret_cast<uint4*>(po) = odd;
+}
+
+}  // namespace rvb
+
+extern "C" int64_t rvb_parity_plane_len(int n_samples, int pad, int pad_mode, int n_fft, int hop, int n_frames) {
+  const int64_t padded = (pad_mode == RVB_PAD_NONE) ? n_samples : (int64_t)n_samples + 2 * pad;
+  int64_t need = (int64_t)(hop / 2) * (n_frames > 0 ? n_frames - 1 : 0) + n_fft / 2 + 8;   // + the converter's look-ahead
+  if ((padded + 1) / 2 > need) need = (padded + 1) / 2;
+  return (need + 7) & ~(int64_t)7;
+}
+
+extern "C" int rvb_pad_parity_pcm16(const int16_t* audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int pad_mode,
+                                    uint16_t* planes, int64_t plane_len, rvb_stream_t stream) {
+  RVB_REQUIRE(audio && planes, "rvb_pad_parity_pcm16: null pointer");
+  RVB_REQUIRE(n_seg > 0 && n_samples > 0 && pad >= 0 && plane_len > 0 && (plane_len & 7) == 0,
+              "rvb_pad_parity_pcm16: bad shape (plane_len must be a positive multiple of 8)");
+  RVB_REQUIRE(pad_mode == RVB_PAD_REFLECT || pad_mode == RVB_PAD_CONSTANT || pad_mode == RVB_PAD_NONE,
+              "rvb_pad_parity_pcm16: bad pad mode %d", pad_mode);
+  RVB_REQUIRE(pad_mode != RVB_PAD_REFLECT || pad < n_samples, "rvb_pad_parity_pcm16: reflect padding needs pad < n_samples");
+  RVB_REQUIRE((reinterpret_cast<uintptr_t>(planes) & 15u) == 0, "rvb_pad_parity_pcm16: planes must be 16-byte aligned");
+  const int64_t groups = (plane_len >> 3) * n_seg;
+  RVB_REQUIRE(groups < (1ll << 31) * 256, "rvb_pad_parity_pcm16: too many samples");
+  rvb::pad_parity_pcm16_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      audio, audio_ld, n_seg, n_samples, pad, pad_mode, planes, plane_len);
+  rvb::count_launch();
+  return rvb::check_launch("pad_parity_pcm16_kernel");
+}

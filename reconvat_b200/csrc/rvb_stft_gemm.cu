@@ -99,6 +99,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* db
     }
   }
 }
+// The same with cluster-scope acquire: the arrivals come from threads of the peer CTA that wrote ITS shared memory.
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* dbg_status, int code) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  uint64_t t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    if ((it & 0x3ff) == 0x3ff) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) {     // 4 s
+        if (dbg_status) atomicExch(dbg_status, code);
+        __threadfence_system();
+        __trap();
+      }
+    }
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -1352,6 +1380,292 @@ stft_gemm_fold2c_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const 
   }
 }
 
+// ---------------------------------------------------------------- twice-folded kernel with the fold done IN the kernel (K1x)
+// K1q re-reads 168 MB of materialised frame planes (every sample stored 4 times as fp16 hi/lo of e and o) that K0q
+// has to write first.  Here the A operand is produced on the fly: eight CONVERTER warps per CTA read the raw padded
+// PCM16 signal (parity planes of rvb_pad_parity_pcm16, 2 bytes per sample, L2-resident after the first touch), form
+//     e[n] = p[n] + p[N-n]   or   o[n] = p[n] - p[N-n]          (this unit's component)
+// exactly, split the value into fp16 hi + lo (exact: 17-bit integers) and store the two 128-row x 64-column tiles of
+// a stage straight into the 128-byte-swizzled layout the MMA descriptors expect -- what the TMA did in K1q.  The
+// even-n and the odd-n chain of a 128-sample block come from the same loads, so stages alternate between the chains:
+// stage 2i = even chain, block i; stage 2i+1 = odd chain, block i.  The TMA warp only fetches the basis tiles.
+//   full[s]   (leader)  1 arrive.expect_tx of the leader's producer (basis bytes of both CTAs) + one arrival per
+//                       converter warp of BOTH CTAs (remote for rank 1), each after fence.proxy.async: the generic-
+//                       proxy stores to shared memory are ordered before the async-proxy reads of tcgen05.mma
+//   empty[s]  (per CTA) as in K1q (multicast commit); the converter warps wait on it like the producer does
+// Sample -> float without a conversion instruction: the planes hold u = x + 32768; PRMT glues the 16 bits under the
+// constant 0x4AC0: the float 1.5 * 2^22 + u / 2.  o / 2 = f(ux) - f(uy) exactly; e / 2 = f(ux) - f(~uy) - 1/2
+// (~u = 65535 - u).  Column j of the even chain is n = 2 j + 2 (x = even-plane element 256 t + j + 1, one element past
+// the 16-byte alignment: taken from the neighbouring lane), of the odd chain n = 2 j + 1; the partner p[N-n] is element
+// 256 t + 1023 - j of the same plane for both.  The centre sample (n = N/2, even chain, last column) has no partner:
+// e = 2 p[N/2] here, and the basis carries HALF the weight in that column (basis.fold2_operand(centre_doubled=True)).
+constexpr int X_CONV_WARPS = 8;
+constexpr int X_NUM_THREADS = P_NUM_THREADS + 32 * X_CONV_WARPS;      // 832
+constexpr int X_CONV_WARP0 = P_NUM_THREADS / 32;                      // first converter warp
+
+struct FusedParams {
+  int n_frames;               // frames per segment (T)
+  int64_t m_rows;             // n_seg * n_frames
+  int n_k, quarter;           // basis rows per chain (N/4), contraction length per chain (N/4)
+  int m_tiles, n_tiles;
+  const uint16_t* sig;        // [2][n_seg][plane_len] parity planes, offset binary
+  int64_t plane_len;
+  int n_seg, hop2;            // hop / 2: plane elements between the starts of consecutive frames
+  float scale;                // 2 * gain * basis_scale_inv: undoes the e/2 representation and the block scaling of the basis
+  float* mel_out;             // [2][n_seg][n_mels][n_frames]
+  int64_t plane_stride;
+  int n_mels;
+};
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Two columns (x elements in xr, low half first; partner elements in yr, HIGH half first) -> packed fp16 hi and lo.
+__device__ __forceinline__ void fold_pair(uint32_t xr, uint32_t yr, float bias, uint32_t& hi, uint32_t& lo) {
+  constexpr uint32_t kMagic = 0x4AC00000u;                 // 1.5 * 2^22: the low 16 mantissa bits weigh 1/2 .. 2^14
+  const float x0 = __uint_as_float(__byte_perm(xr, kMagic, 0x7610));
+  const float x1 = __uint_as_float(__byte_perm(xr, kMagic, 0x7632));
+  const float y0 = __uint_as_float(__byte_perm(yr, kMagic, 0x7632));
+  const float y1 = __uint_as_float(__byte_perm(yr, kMagic, 0x7610));
+  const float v0 = (x0 - y0) - bias, v1 = (x1 - y1) - bias;           // exact: multiples of 1/2 below 2^16
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);          // exact: |v - hi| <= 16
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X_NUM_THREADS, 1)
+stft_gemm_fold2x_pair_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                             const FusedParams p, const __grid_constant__ MelTable tab) {
+  static_assert(kStages % 2 == 0, "stages are filled in (even chain, odd chain) pairs");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * P_STAGE_BYTES;
+  auto s_a = [&](int s, int lo) { return smem_base + s * P_STAGE_BYTES + lo * P_A_BYTES; };
+  auto s_b = [&](int s, int lo) { return smem_base + s * P_STAGE_BYTES + 2 * P_A_BYTES + lo * P_B_BYTES; };
+  auto bar_full = [&](int s) { return bar_base + 8 * s; };
+  auto bar_empty = [&](int s) { return bar_base + 8 * (kStages + s); };
+  auto bar_tmem_full = [&](int a) { return bar_base + 8 * (2 * kStages + a); };
+  auto bar_tmem_empty = [&](int a) { return bar_base + 8 * (2 * kStages + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8 * (2 * kStages + 4) + 16;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_b_hi);
+    tma_prefetch_desc(&tm_b_lo);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full(s), 1 + 2 * X_CONV_WARPS);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tmem_full(a), 1);
+      mbar_init(bar_tmem_empty(a), 8 * P_EPI_GROUPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();                                     // barriers initialised before the allocator touches its slot
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  constexpr int kBlockK = 2 * BLOCK_K;            // 64 halves per 128-byte swizzle row
+  const int units_per_m = 2 * p.n_tiles;          // (component, 128-k tile)
+  const int n_units = p.m_tiles * units_per_m;
+  const int n_blocks = p.quarter / kBlockK;       // 128-sample blocks per frame half = stage pairs per unit
+  const int num_kb = 2 * n_blocks;
+  const int unit0 = (int)(blockIdx.x >> 1), unit_step = (int)(gridDim.x >> 1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t leader_full0 = map_to_rank(bar_full(0), 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
+        const int rest = unit % units_per_m;
+        const int comp = rest / p.n_tiles, n_tile = rest - comp * p.n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int chain = kb & 1;
+          const int kk = (kb >> 1) * kBlockK;
+          const int b_row = (2 * comp + chain) * p.n_k + n_tile * F_BLOCK_N + (int)rank * 64;
+          mbar_wait(bar_empty(stage), phase ^ 1u, nullptr, 1);
+          if (leader) mbar_expect_tx(bar_full(stage), 2 * 2 * P_B_BYTES);
+          const uint32_t fb = leader_full0 + 8 * stage;
+          tma_load_2d_pair(&tm_b_hi, s_b(stage, 0), fb, kk, b_row);
+          tma_load_2d_pair(&tm_b_lo, s_b(stage, 1), fb, kk, b_row);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(256, F_BLOCK_N, FMT_F16);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
+        mbar_wait(bar_tmem_empty(acc), acc_phase ^ 1u, nullptr, 2);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int chain = kb & 1;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + chain * F_BLOCK_N);
+          mbar_wait_cluster(bar_full(stage), phase, nullptr, 3);
+          tc_fence_after();
+          const uint64_t da_hi = make_sw128_desc(s_a(stage, 0));
+          const uint64_t da_lo = make_sw128_desc(s_a(stage, 1));
+          const uint64_t db_hi = make_sw128_desc(s_b(stage, 0));
+          const uint64_t db_lo = make_sw128_desc(s_b(stage, 1));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);             // one MMA consumes 32 bytes of the row
+            umma_f16_pair(d_tmem, da_hi + adv, db_lo + adv, idesc, (kb < 2 && k == 0) ? 0u : 1u);
+            umma_f16_pair(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+            umma_f16_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+          }
+          umma_commit_pair(bar_empty(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(bar_tmem_full(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= X_CONV_WARP0) {
+    // ---- converter warps: raw samples -> folded, split, swizzled A tiles of a stage pair
+    const int cw = warp - X_CONV_WARP0;
+    const int q = lane >> 3, sub = lane & 7;              // quarter-warp = (row, chain); lane = 16-byte chunk of the row
+    const int chain = q & 1;
+    const int sh = chain ? 0 : 16;                        // even chain: x starts one element past the chunk
+    const uint32_t leader_full0 = map_to_rank(bar_full(0), 0);
+    const uint16_t* plane = p.sig + (int64_t)chain * p.n_seg * p.plane_len;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int unit = unit0; unit < n_units; unit += unit_step) {
+      const int m_tile = unit / units_per_m, rest = unit - m_tile * units_per_m;
+      const int comp = rest / p.n_tiles;
+      const uint32_t ymask = comp ? 0u : 0xffffffffu;     // e: partner complemented (f(ux) - f(~uy) = (x + y + 1) / 2)
+      const float bias = comp ? 0.f : 0.5f;
+      int32_t off[8];                                     // plane offset of the frame start of this lane's 8 rows
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 16 + cw * 2 + (q >> 1);
+        int64_t f = (int64_t)m_tile * 256 + (int64_t)rank * 128 + row;
+        if (f >= p.m_rows) f = p.m_rows - 1;              // rows past the end: any valid frame (the epilogue drops them)
+        const int b = (int)(f / p.n_frames);
+        const int t = (int)(f - (int64_t)b * p.n_frames);
+        off[it] = (int32_t)((int64_t)b * p.plane_len + (int64_t)t * p.hop2);
+      }
+      for (int blk = 0; blk < n_blocks; ++blk) {
+        mbar_wait(bar_empty(stage), phase ^ 1u, nullptr, 5);
+        mbar_wait(bar_empty(stage + 1), phase ^ 1u, nullptr, 5);
+        const int st = stage + chain;                     // this quarter-warp's stage of the pair
+        const uint32_t a_hi = s_a(st, 0), a_lo = s_a(st, 1);
+        const int xo = blk * kBlockK + sub * 8, yo = p.quarter * 2 - 8 - xo;     // N/2 - 8 - xo
+        uint4 X, Y;
+        uint32_t XN;
+        {
+          const uint16_t* base = plane + off[0];
+          X = ldg_nc_v4(base + xo);
+          Y = ldg_nc_v4(base + yo);
+          XN = (sub == 7) ? __ldg(reinterpret_cast<const uint32_t*>(base + xo + 8)) : 0u;
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          uint4 Xn = X, Yn = Y;
+          uint32_t XNn = XN;
+          if (it + 1 < 8) {                               // next row's loads in flight while this row is converted
+            const uint16_t* base = plane + off[it + 1];
+            Xn = ldg_nc_v4(base + xo);
+            Yn = ldg_nc_v4(base + yo);
+            XNn = (sub == 7) ? __ldg(reinterpret_cast<const uint32_t*>(base + xo + 8)) : 0u;
+          }
+          // element 8 of this chunk = element 0 of the next lane's chunk (same row for sub < 7)
+          uint32_t nx = __shfl_down_sync(kFull, X.x, 1);
+          if (sub == 7) nx = XN;
+          const uint32_t x0 = __funnelshift_r(X.x, X.y, sh), x1 = __funnelshift_r(X.y, X.z, sh);
+          const uint32_t x2 = __funnelshift_r(X.z, X.w, sh), x3 = __funnelshift_r(X.w, nx, sh);
+          uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+          fold_pair(x0, Y.w ^ ymask, bias, h0, l0);      // columns 8 sub + 0, 1  <->  partner elements 7, 6
+          fold_pair(x1, Y.z ^ ymask, bias, h1, l1);
+          fold_pair(x2, Y.y ^ ymask, bias, h2, l2);
+          fold_pair(x3, Y.x ^ ymask, bias, h3, l3);
+          const int row = it * 16 + cw * 2 + (q >> 1);
+          const uint32_t dst = (uint32_t)(row * 128 + ((sub ^ (row & 7)) << 4));
+          sts_v4(a_hi + dst, h0, h1, h2, h3);
+          sts_v4(a_lo + dst, l0, l1, l2, l3);
+          X = Xn; Y = Yn; XN = XNn;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(leader_full0 + 8 * stage);
+          mbar_arrive_cluster(leader_full0 + 8 * (stage + 1));
+        }
+        stage += 2;
+        if (stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    const int group = (warp - EPI_WARP0) >> 2;      // 0 .. 3
+    const int stream = group >> 1, hhalf = group & 1;
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const uint32_t leader_tmem_empty0 = map_to_rank(bar_tmem_empty(0), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    Fold2Params ep;                                  // the epilogue of K1q, fed with this kernel's geometry
+    ep.n_frames = p.n_frames; ep.n_mels = p.n_mels;
+    for (int unit = unit0; unit < n_units; unit += unit_step) {
+      const int m_tile = unit / units_per_m, rest = unit - m_tile * units_per_m;
+      const int comp = rest / p.n_tiles, n_tile = rest - comp * p.n_tiles;
+      const int64_t f = (int64_t)m_tile * 256 + (int64_t)rank * 128 + row;       // flattened frame index
+      const bool f_ok = f < p.m_rows;
+      const int b = f_ok ? (int)(f / p.n_frames) : 0;
+      const int t = f_ok ? (int)(f - (int64_t)b * p.n_frames) : 0;
+      float* col = p.mel_out + comp * p.plane_stride + (int64_t)b * p.n_mels * p.n_frames + t;
+      const float4* tt = tab.e + stream * p.n_k + n_tile * F_BLOCK_N + hhalf * C_CHUNK;
+      mbar_wait(bar_tmem_full(acc), acc_phase, nullptr, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + hhalf * C_CHUNK);
+      mel2c_unit(ep, taddr, tt, stream, col, f_ok, p.scale);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // Single bin from the folded planes (Nyquist bin of the STFT module): warp per frame, fp32 FMA.
 // T = float (tf32 planes) or __half (fp16 planes, row-scaled: row_scale_inv undoes the scaling).
 template <typename T>
@@ -1717,6 +2031,68 @@ extern "C" int rvb_stft_mel_folded2_f16(const void* a_hi, const void* a_lo, cons
   kernel<<<2 * n_clusters, P_NUM_THREADS, smem, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p, tab);
   count_launch();
   return check_launch(n64 ? "stft_gemm_fold2_pair_kernel" : "stft_gemm_fold2c_pair_kernel");
+}
+
+extern "C" int rvb_stft_mel_fused_pcm16(const uint16_t* planes, int64_t plane_len, int n_seg, int n_frames, int n_fft,
+                                        int hop, float gain, const void* basis_hi, const void* basis_lo,
+                                        float basis_scale_inv, const float* mel_tab, int n_mels, float* mel_out,
+                                        rvb_stream_t stream) {
+  const char* who = "rvb_stft_mel_fused_pcm16";
+  RVB_REQUIRE(planes && basis_hi && basis_lo && mel_tab && mel_out, "%s: null pointer", who);
+  RVB_REQUIRE(n_seg > 0 && n_frames > 0 && n_mels > 0, "%s: bad shape", who);
+  RVB_REQUIRE(n_fft >= 512 && n_fft % 512 == 0 && 2 * (n_fft / 4) <= kMelTableBins,
+              "%s: n_fft %d must be a multiple of 512 and at most %d", who, n_fft, 2 * kMelTableBins);
+  RVB_REQUIRE(hop > 0 && hop % 16 == 0, "%s: hop %d must be a multiple of 16 (16-byte loads from the parity planes)", who, hop);
+  RVB_REQUIRE(plane_len % 8 == 0 && plane_len >= (int64_t)(hop / 2) * (n_frames - 1) + n_fft / 2 + 8,
+              "%s: plane_len %lld too short for %d frames (rvb_parity_plane_len)", who, (long long)plane_len, n_frames);
+  RVB_REQUIRE(2 * (int64_t)n_seg * plane_len < (1ll << 31), "%s: signal too long for 32-bit plane offsets", who);
+  for (const void* ptr : {(const void*)planes, basis_hi, basis_lo})
+    RVB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 127u) == 0, "%s: operands must be 128-byte aligned", who);
+  const int quarter = n_fft / 4;
+  const int64_t m_rows = (int64_t)n_seg * n_frames;
+  RVB_REQUIRE(2 * m_rows < (1ll << 31), "%s: too many frames", who);
+  const int64_t plane = (int64_t)n_seg * n_mels * n_frames;
+  RVB_CUDA(cudaMemsetAsync(mel_out, 0, sizeof(float) * 2 * (size_t)plane, (cudaStream_t)stream));
+
+  CUtensorMap tm_b_hi, tm_b_lo;
+  int rc;
+  if ((rc = make_map_2d(&tm_b_hi, basis_hi, quarter, 4 * (uint64_t)quarter, 64, 64, 2)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_b_lo, basis_lo, quarter, 4 * (uint64_t)quarter, 64, 64, 2)) != RVB_OK) return rc;
+
+  FusedParams p;
+  p.n_frames = n_frames; p.m_rows = m_rows; p.n_k = quarter; p.quarter = quarter;
+  p.m_tiles = (int)((m_rows + 255) / 256);
+  p.n_tiles = quarter / F_BLOCK_N;
+  p.sig = planes; p.plane_len = plane_len; p.n_seg = n_seg; p.hop2 = hop / 2;
+  p.scale = 2.f * gain * basis_scale_inv;              // A holds e / 2 (o / 2) in units of one PCM step
+  p.mel_out = mel_out; p.plane_stride = plane; p.n_mels = n_mels;
+
+  constexpr int smem = P_STAGES * P_STAGE_BYTES + BAR_BYTES + 1024;
+  auto kernel = stft_gemm_fold2x_pair_kernel<P_STAGES>;
+  static int max_clusters_dev[kMaxDevices] = {};
+  const int sms = num_sms(), slot = device_slot();
+  int max_clusters;
+  {
+    std::lock_guard<std::mutex> g(attr_mutex());
+    if (max_clusters_dev[slot] == 0) {
+      RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(sms & ~1u); qc.blockDim = dim3(X_NUM_THREADS); qc.dynamicSmemBytes = smem;
+      int nc = 0;
+      RVB_CUDA(cudaOccupancyMaxActiveClusters(&nc, kernel, &qc));
+      RVB_REQUIRE(nc > 0, "%s: no CTA pair fits on this device", who);
+      max_clusters_dev[slot] = nc < sms / 2 ? nc : sms / 2;
+    }
+    max_clusters = max_clusters_dev[slot];
+  }
+  const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles * 2;
+  const int n_clusters = (int)(n_units < max_clusters ? n_units : max_clusters);
+  static thread_local MelTable tab;
+  std::memset(&tab, 0, sizeof(tab));
+  std::memcpy(tab.e, mel_tab, sizeof(float4) * (size_t)(2 * quarter));
+  kernel<<<2 * n_clusters, X_NUM_THREADS, smem, (cudaStream_t)stream>>>(tm_b_hi, tm_b_lo, p, tab);
+  count_launch();
+  return check_launch("stft_gemm_fold2x_pair_kernel");
 }
 
 template <typename T>

@@ -129,15 +129,21 @@ def test_frontend_amplitude_range(R, dev):
 
 def test_pcm16_input_is_bit_identical_to_float_input(R, dev):
     """int16 audio (the dataset's storage format, model/dataset.py:62) through rvb_fold_split_f16_pcm16 gives the same
-    bits as the float path fed pcm/32768; the other contraction paths convert with torch and must agree too."""
+    bits as the float path fed pcm/32768; the other contraction paths convert with torch and must agree too.  (The
+    default PCM16 route folds inside the contraction -- test_fused_fold_pcm16_* -- so the materialised route is
+    selected with RVB_NO_FUSED_FOLD here.)"""
     import os
     from reconvat_b200 import synth
     a16 = np.stack([synth.white_int16(16385, 21), synth.music_int16(16385, 22)])
     ai = torch.from_numpy(a16).to(dev)
     af = torch.from_numpy(synth.to_float(a16)).to(dev)
     m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
-    assert torch.equal(m.normalised_log_mel(ai), m.normalised_log_mel(af))
-    assert torch.equal(m(ai[:, :-1]), m(af[:, :-1]))
+    os.environ["RVB_NO_FUSED_FOLD"] = "1"
+    try:
+        assert torch.equal(m.normalised_log_mel(ai), m.normalised_log_mel(af))
+        assert torch.equal(m(ai[:, :-1]), m(af[:, :-1]))
+    finally:
+        os.environ.pop("RVB_NO_FUSED_FOLD", None)
     os.environ["RVB_STFT_OPERAND"] = "tf32"
     try:
         m2 = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
@@ -147,6 +153,90 @@ def test_pcm16_input_is_bit_identical_to_float_input(R, dev):
     assert torch.equal(m2.normalised_log_mel(ai), m2.normalised_log_mel(af))
     with pytest.raises(R._lib.RvbError):
         m(ai.to(torch.int32))
+
+
+@pytest.mark.parametrize("mode,n,pad,ld_extra", [(0, 16385, 1024, 0), (0, 5000, 1024, 37), (1, 4097, 512, 3),
+                                                  (2, 9000, 0, 0), (0, 1025, 1024, 0)])
+def test_pad_parity_planes_bit_exact(R, dev, mode, n, pad, ld_extra):
+    """K0x: padded (reflect / constant / none) signal, split by sample parity, offset binary; any row stride."""
+    rng = np.random.default_rng(n)
+    B = 3
+    raw = rng.integers(-32768, 32768, size=(B, n + ld_extra)).astype(np.int16)
+    raw[0, :5] = [-32768, 32767, 0, -1, 1]
+    x = torch.from_numpy(raw).to(dev)[:, :n]
+    n_fft, hop = 2048, 512
+    padded = n if mode == 2 else n + 2 * pad
+    T = max(1, (padded - n_fft) // hop + 1)
+    plane_len = R._lib.parity_plane_len(n, pad, mode, n_fft, hop, T)
+    assert plane_len % 8 == 0 and 2 * plane_len >= padded and plane_len >= 256 * (T - 1) + 1024 + 8
+    planes = torch.full((2, B, plane_len), 7, dtype=torch.int16, device=dev)
+    R._lib.call("rvb_pad_parity_pcm16", x.data_ptr(), x.stride(0), B, n, pad, mode, planes.data_ptr(), plane_len)
+    sig = raw[:, :n].astype(np.int64)
+    if mode == 0:
+        sig = np.pad(sig, [(0, 0), (pad, pad)], mode="reflect")
+    elif mode == 1:
+        sig = np.pad(sig, [(0, 0), (pad, pad)])
+    want = np.zeros((B, 2 * plane_len), np.int64)
+    want[:, :sig.shape[1]] = sig
+    want = (want + 32768).astype(np.uint16)
+    got = planes.cpu().numpy().view(np.uint16)
+    assert np.array_equal(got[0], want[:, 0::2]) and np.array_equal(got[1], want[:, 1::2])
+
+
+def test_fused_fold_pcm16_golden_and_against_the_materialised_route(R, dev, golden):
+    """K0x + K1x (PCM16 input, the fold done by converter warps inside the tcgen05 kernel) against the reference's
+    golden log-Mel, against the materialised route (K0q + K1q) and against itself (bit-reproducible)."""
+    import os
+    from reconvat_b200 import synth
+    g = golden["frontend_full"]
+    a16 = np.stack([synth.white_int16(synth.SEGMENT_SAMPLES, int(g["seeds"][0])),
+                    synth.music_int16(synth.SEGMENT_SAMPLES, int(g["seeds"][1]))])
+    ai = torch.from_numpy(a16).to(dev)
+    m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    calls = []
+    R._lib.record_calls(calls)
+    try:
+        mel_x = m(ai[:, :-1])
+    finally:
+        R._lib.record_calls(None)
+    assert [n for n, _ in calls] == ["rvb_pad_parity_pcm16", "rvb_stft_mel_fused_pcm16"]
+    assert mel_x.shape == (2, 229, 640)
+    assert relerr(torch.log(mel_x + 1e-5).cpu().numpy(), g["log_mel"]) < LOGMEL_TOL
+    assert torch.equal(mel_x, m(ai[:, :-1]))
+    os.environ["RVB_NO_FUSED_FOLD"] = "1"
+    try:
+        calls = []
+        R._lib.record_calls(calls)
+        mel_q = m(ai[:, :-1])
+        R._lib.record_calls(None)
+    finally:
+        os.environ.pop("RVB_NO_FUSED_FOLD", None)
+    assert [n for n, _ in calls] == ["rvb_fold_split2_f16_pcm16", "rvb_stft_mel_folded2_f16"]
+    # same exact operand values, split at a different bit: the two routes differ by the dropped lo*lo products only
+    assert float(((mel_x - mel_q).abs() / (mel_q.abs() + 1e-7)).max()) < 2e-5
+    spec = m.normalised_log_mel(ai).cpu().numpy()
+    assert np.abs(spec.reshape(2, -1)[:, ::7] - g["spec_stride7"]).max() < LOGMEL_TOL
+    assert spec.min() == 0.0 and spec.max() == 1.0
+
+
+def test_fused_fold_pcm16_edges(R, dev):
+    """Ragged batch sizes (rows past the last frame in a tile), the shortest legal signal, full-scale and silent
+    input, a non-contiguous batch view -- against the float64 oracle."""
+    from oracle.frontend import FrontEndOracle
+    from reconvat_b200 import synth
+    m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    orc = FrontEndOracle()
+    for B, L in ((1, 1026), (3, 8 * 512 + 1), (5, 77 * 512 + 1)):
+        a16 = np.stack([synth.music_int16(L, 70 + b) if b % 2 else synth.white_int16(L, 70 + b) for b in range(B)])
+        a16[0, :] = np.where(np.arange(L) % 2 == 0, 32767, -32768)            # full-scale Nyquist-rate square wave
+        if B > 2:
+            a16[2, :] //= 512                                                 # -54 dB
+        wide = torch.from_numpy(np.concatenate([a16, a16[:, :13]], axis=1)).to(dev)
+        x = wide[:, :L]                                                       # row stride L + 13
+        lm = torch.log(m(x[:, :-1]) + 1e-5).cpu().numpy()
+        ref = orc.log_mel(synth.to_float(a16)[:, :-1], np.float64)
+        assert lm.shape == ref.shape
+        assert relerr(lm, ref) < LOGMEL_TOL, (B, L)
 
 
 def test_fused_mel_epilogue_matches_separate_kernel_and_is_reproducible(R, dev):

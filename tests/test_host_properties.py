@@ -140,6 +140,82 @@ def test_twice_folded_operand_and_tables():
     assert basis.fold2_operand(wcos[:513], wsin[:513]) is None             # freq_bins != N/2 + 1
 
 
+def _emulate_fused_operand(pcm, n_fft, hop, pad, comp):
+    """What K0x + the converter warps of K1x do (csrc/rvb_frontend.cu pad_parity_pcm16_kernel, csrc/rvb_stft_gemm.cu
+    stft_gemm_fold2x_pair_kernel), restated with numpy in the kernel's own fp32 / fp16 arithmetic: offset-binary parity
+    planes, x / partner element indices, the 0x4AC00000 byte-permute float, the complement + 1/2 bias of the e
+    component, the fp16 hi/lo split.  Returns (hi, lo) as float64 [frames][chain][N/4]."""
+    half, quarter = n_fft // 2, n_fft // 4
+    padded = np.pad(pcm.astype(np.int64), (pad, pad), mode="reflect")
+    u = (padded + 32768).astype(np.uint32)
+    assert u.max() < 65536
+    planes = [u[0::2], u[1::2]]
+    n_frames = (len(padded) - n_fft) // hop + 1
+    magic = np.uint32(0x4AC00000)
+    hi = np.zeros((n_frames, 2, quarter)); lo = np.zeros_like(hi)
+    j = np.arange(quarter)
+    for t in range(n_frames):
+        for chain in range(2):                                   # 0: even n = 2j + 2, 1: odd n = 2j + 1
+            pl = planes[chain]
+            ux = pl[(hop // 2) * t + j + (1 if chain == 0 else 0)]
+            uy = pl[(hop // 2) * t + half - 1 - j]
+            if comp == 0:
+                uy = (~uy) & np.uint32(0xFFFF)
+            fx = (magic | ux).view(np.float32)
+            fy = (magic | uy).view(np.float32)
+            v = (fx - fy) - np.float32(0.5 if comp == 0 else 0.0)
+            h = v.astype(np.float16)
+            l = (v - h.astype(np.float32)).astype(np.float16)
+            hi[t, chain], lo[t, chain] = h, l
+    return hi, lo, padded, n_frames
+
+
+def test_fused_fold_converter_arithmetic_is_exact_and_matches_the_stft():
+    """The in-kernel fold of the PCM16 contraction: hi + lo equals (p[n] +- p[N-n]) / 2 EXACTLY for every column --
+    extremes of the int16 range included --, and contracted with fold2_operand(centre_doubled=True) it reproduces the
+    windowed DFT of model/Spectrogram.py:219-231 for the bins k = 1 .. N/2 - 1."""
+    N, hop, pad = 2048, 512, 1024
+    ks, kc, _, _, wm = basis.fourier_basis(N, win_length=N, window="hann", freq_scale="no", sr=16000)
+    wcos = (torch.from_numpy(kc) * torch.from_numpy(wm)).numpy()
+    wsin = (torch.from_numpy(ks) * torch.from_numpy(wm)).numpy()
+    fx = basis.fold2_operand(wcos, wsin, centre_doubled=True)
+    f2 = basis.fold2_operand(wcos, wsin)
+    nk = fx["n_k"]
+    Bx = (fx["basis_hi"].astype(np.float64) + fx["basis_lo"].astype(np.float64)) * fx["scale_inv"]
+    B2 = (f2["basis_hi"].astype(np.float64) + f2["basis_lo"].astype(np.float64)) * f2["scale_inv"]
+    assert np.allclose(Bx[:nk, nk - 1], 0.5 * B2[:nk, nk - 1], rtol=1e-6) and np.all(Bx[2 * nk:3 * nk, nk - 1] == 0)
+    # every other column is the same basis (to the 2^-22 of the fp16 hi/lo split: the block scale of the twin differs,
+    # its largest element no longer being the centre weight)
+    assert np.abs(np.delete(Bx, nk - 1, axis=1) - np.delete(B2, nk - 1, axis=1)).max() < 5e-7
+    rng = np.random.default_rng(3)
+    pcm = rng.integers(-32768, 32768, size=4 * hop + 77).astype(np.int16)
+    pcm[:40] = 32767; pcm[40:80] = -32768; pcm[100:140:2] = -32768; pcm[101:140:2] = 32767   # range extremes, both signs
+    T = None
+    acc = {}
+    for comp in (0, 1):
+        hi, lo, padded, T = _emulate_fused_operand(pcm, N, hop, pad, comp)
+        a = hi + lo                                              # the A operand, in units of 2 PCM steps
+        for t in range(T):
+            fr = padded[hop * t: hop * t + N].astype(np.float64)
+            n_even, n_odd = 2 * np.arange(nk) + 2, 2 * np.arange(nk) + 1
+            for chain, n in ((0, n_even), (1, n_odd)):
+                mirror = fr[(N - n) % N]
+                want = (fr[n] + mirror) / 2 if comp == 0 else (fr[n] - mirror) / 2
+                assert np.array_equal(a[t, chain], want), (comp, t, chain)
+                assert np.abs(lo[t, chain]).max() <= 16.5
+        rows = slice(2 * comp * nk, (2 * comp + 1) * nk), slice((2 * comp + 1) * nk, (2 * comp + 2) * nk)
+        acc[comp] = (a[:, 0] @ Bx[rows[0]].T, a[:, 1] @ Bx[rows[1]].T)      # even chain, odd chain: [T][n_k]
+    scale = 2.0 / 32768.0
+    frames = np.stack([padded[hop * t: hop * t + N] for t in range(T)]).astype(np.float64) / 32768.0
+    re_ref, im_ref = frames @ wcos.astype(np.float64).T, frames @ wsin.astype(np.float64).T
+    k = np.arange(1, nk + 1)
+    tol = 3e-7 * np.abs(re_ref).max()
+    assert np.abs((acc[0][0] + acc[0][1]) * scale - re_ref[:, k]).max() < tol              # bin k
+    assert np.abs((acc[1][0] + acc[1][1]) * scale - im_ref[:, k]).max() < tol
+    assert np.abs((acc[0][0] - acc[0][1]) * scale - re_ref[:, N // 2 - k]).max() < tol     # bin N/2 - k
+    assert np.abs(-(acc[1][0] - acc[1][1]) * scale - im_ref[:, N // 2 - k]).max() < tol
+
+
 @pytest.mark.parametrize("sr,n_fft,n_mels,fmin,fmax,htk", [
     (16000, 2048, 229, 30, 8000, False), (22050, 2048, 128, 0.0, None, False), (16000, 1024, 128, 30, 7600, False),
     (16000, 512, 40, 20, 7000, False), (44100, 2048, 96, 50, 16000, True)])
