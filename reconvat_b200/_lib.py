@@ -31,8 +31,8 @@ SIGNATURES = {
     "rvb_fold_split2_f16": [_c_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _c_p, _c_p, _c_p, _c_p],
     "rvb_fold_split2_f16_pcm16": [_c_p, _i64, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _c_p, _c_p, _c_p, _c_p],
     "rvb_stft_mel_folded2_f16": [_c_p, _c_p, _c_p, _i32, _i32, _i32, _c_p, _c_p, _f32, _c_p, _i32, _c_p, _c_p],
-    "rvb_pad_parity_pcm16": [_c_p, _i64, _i32, _i32, _i32, _i32, _c_p, _i64],
-    "rvb_stft_mel_fused_pcm16": [_c_p, _i64, _i32, _i32, _i32, _i32, _f32, _c_p, _c_p, _f32, _c_p, _i32, _c_p],
+    "rvb_pad_parity_pcm16": [_c_p, _i64, _i32, _i32, _i32, _i32, _c_p, _i64, _c_p],
+    "rvb_stft_mel_fused_pcm16": [_c_p, _i64, _i32, _i32, _i32, _i32, _f32, _c_p, _c_p, _f32, _c_p, _i32, _c_p, _c_p],
     "rvb_logmel_minmax": [_c_p, _i32, _i64, _f32, _c_p, _c_p],
     "rvb_logmel_transpose": [_c_p, _i32, _i32, _i32, _f32, _c_p, _c_p, _c_p],
     "rvb_logmel_normalise": [_c_p, _c_p, _i32, _i32, _i32, _f32, _c_p, _c_p, _c_p],

@@ -44,7 +44,8 @@ def test_header_and_library_agree(lib):
 def test_ctypes_table_mirrors_header(lib):
     import ctypes
     decls = _declared()
-    plumbing = {"rvb_abi_version", "rvb_last_error", "rvb_launch_count", "rvb_vat_stats_workspace_bytes"}
+    plumbing = {"rvb_abi_version", "rvb_last_error", "rvb_launch_count", "rvb_vat_stats_workspace_bytes",
+                "rvb_parity_plane_len"}
     assert set(lib.SIGNATURES) == set(decls) - plumbing
     kinds = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_int64: "int64_t", ctypes.c_float: "float",
              ctypes.c_double: "double"}
