@@ -29,6 +29,17 @@ def _ceil_div(a, b):
     return -(-a // b)
 
 
+def _fused_fold_enabled():
+    """PCM16 input: fold inside the contraction (K0x + K1x, no materialised frame planes) or materialise the folded
+    fp16 planes first (K0q + K1q)?  RVB_FUSED_FOLD=1 / 0 selects; the default is the faster of the two on B200 at
+    the benchmark shape (profiles/r02_experiments.md)."""
+    v = os.environ.get("RVB_FUSED_FOLD")
+    return _FUSED_FOLD_DEFAULT if v is None else v not in ("0", "")
+
+
+_FUSED_FOLD_DEFAULT = False
+
+
 class STFT(nn.Module):
     """model/Spectrogram.py:22-237.  ``forward(x, output_format=None)``:
     ``Magnitude`` -> (B, F, T); ``Complex`` -> (B, F, T, 2) holding (re, -im); ``Phase`` -> (B, F, T)."""
@@ -181,7 +192,7 @@ class STFT(nn.Module):
             if fd["operand"] == "f16":
                 if mel_tab2 is not None and pcm16 and tb["fold2x"] is not None and self.stride % 16 == 0 \
                         and 2 * B * (n_frames * self.stride + self.n_fft) < 2 ** 31 \
-                        and not os.environ.get("RVB_NO_FUSED_FOLD"):
+                        and _fused_fold_enabled():
                     # K0x / K1x: no materialised frame planes.  The padded PCM16 signal is stored once, split by sample
                     # parity (2 bytes per sample); the contraction's converter warps fold / scale / split in-kernel
                     fx = tb["fold2x"]

@@ -1576,45 +1576,52 @@ stft_gemm_fold2x_pair_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const 
         const int t = (int)(f - (int64_t)b * p.n_frames);
         off[it] = (int32_t)((int64_t)b * p.plane_len + (int64_t)t * p.hop2);
       }
+      // The loads of a row are issued kPrefetch rows ahead of its conversion, across the block (stage pair) boundary:
+      // they do not depend on the empty barrier, only the shared-memory stores do.  Little's law: 8 warps x 3 rows x
+      // 1.1 KB in flight per SM (27 KB) cover ~600 cycles of L2 latency at the 26 bytes/clock the MMA pace asks for;
+      // one row ahead (the first version) left the converters latency-bound at half that rate.
+      constexpr int kPrefetch = 3;
+      uint4 X[4], Y[4];
+      uint32_t XN[4];
+      const int n_rows_unit = 8 * n_blocks;
+      auto issue = [&](int slot, int it, int blk) {
+        const int xo = blk * kBlockK + sub * 8, yo = p.quarter * 2 - 8 - xo;     // N/2 - 8 - xo
+        const uint16_t* base = plane + off[it];
+        X[slot] = ldg_nc_v4(base + xo);
+        Y[slot] = ldg_nc_v4(base + yo);
+        XN[slot] = (sub == 7) ? __ldg(reinterpret_cast<const uint32_t*>(base + xo + 8)) : 0u;
+      };
+#pragma unroll
+      for (int j = 0; j < kPrefetch; ++j) issue(j, j, 0);
       for (int blk = 0; blk < n_blocks; ++blk) {
         mbar_wait(bar_empty(stage), phase ^ 1u, nullptr, 5);
         mbar_wait(bar_empty(stage + 1), phase ^ 1u, nullptr, 5);
         const int st = stage + chain;                     // this quarter-warp's stage of the pair
         const uint32_t a_hi = s_a(st, 0), a_lo = s_a(st, 1);
-        const int xo = blk * kBlockK + sub * 8, yo = p.quarter * 2 - 8 - xo;     // N/2 - 8 - xo
-        uint4 X, Y;
-        uint32_t XN;
-        {
-          const uint16_t* base = plane + off[0];
-          X = ldg_nc_v4(base + xo);
-          Y = ldg_nc_v4(base + yo);
-          XN = (sub == 7) ? __ldg(reinterpret_cast<const uint32_t*>(base + xo + 8)) : 0u;
-        }
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          uint4 Xn = X, Yn = Y;
-          uint32_t XNn = XN;
-          if (it + 1 < 8) {                               // next row's loads in flight while this row is converted
-            const uint16_t* base = plane + off[it + 1];
-            Xn = ldg_nc_v4(base + xo);
-            Yn = ldg_nc_v4(base + yo);
-            XNn = (sub == 7) ? __ldg(reinterpret_cast<const uint32_t*>(base + xo + 8)) : 0u;
+          const int cur = it & 3;
+          const uint4 Xc = X[cur], Yc = Y[cur];
+          const uint32_t XNc = XN[cur];
+          {
+            constexpr int kAhead = kPrefetch;
+            const int itn = (it + kAhead) & 7, blkn = blk + ((it + kAhead) >> 3);
+            if (blk * 8 + it + kAhead < n_rows_unit) issue((it + kAhead) & 3, itn, blkn);
           }
           // element 8 of this chunk = element 0 of the next lane's chunk (same row for sub < 7)
-          uint32_t nx = __shfl_down_sync(kFull, X.x, 1);
-          if (sub == 7) nx = XN;
-          const uint32_t x0 = __funnelshift_r(X.x, X.y, sh), x1 = __funnelshift_r(X.y, X.z, sh);
-          const uint32_t x2 = __funnelshift_r(X.z, X.w, sh), x3 = __funnelshift_r(X.w, nx, sh);
+          uint32_t nx = __shfl_down_sync(kFull, Xc.x, 1);
+          if (sub == 7) nx = XNc;
+          const uint32_t x0 = __funnelshift_r(Xc.x, Xc.y, sh), x1 = __funnelshift_r(Xc.y, Xc.z, sh);
+          const uint32_t x2 = __funnelshift_r(Xc.z, Xc.w, sh), x3 = __funnelshift_r(Xc.w, nx, sh);
           uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-          fold_pair(x0, Y.w ^ ymask, bias, h0, l0);      // columns 8 sub + 0, 1  <->  partner elements 7, 6
-          fold_pair(x1, Y.z ^ ymask, bias, h1, l1);
-          fold_pair(x2, Y.y ^ ymask, bias, h2, l2);
-          fold_pair(x3, Y.x ^ ymask, bias, h3, l3);
+          fold_pair(x0, Yc.w ^ ymask, bias, h0, l0);     // columns 8 sub + 0, 1  <->  partner elements 7, 6
+          fold_pair(x1, Yc.z ^ ymask, bias, h1, l1);
+          fold_pair(x2, Yc.y ^ ymask, bias, h2, l2);
+          fold_pair(x3, Yc.x ^ ymask, bias, h3, l3);
           const int row = it * 16 + cw * 2 + (q >> 1);
           const uint32_t dst = (uint32_t)(row * 128 + ((sub ^ (row & 7)) << 4));
           sts_v4(a_hi + dst, h0, h1, h2, h3);
           sts_v4(a_lo + dst, l0, l1, l2, l3);
-          X = Xn; Y = Yn; XN = XNn;
         }
         fence_proxy_async_smem();
         __syncwarp();

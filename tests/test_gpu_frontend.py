@@ -138,12 +138,12 @@ def test_pcm16_input_is_bit_identical_to_float_input(R, dev):
     ai = torch.from_numpy(a16).to(dev)
     af = torch.from_numpy(synth.to_float(a16)).to(dev)
     m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
-    os.environ["RVB_NO_FUSED_FOLD"] = "1"
+    os.environ["RVB_FUSED_FOLD"] = "0"
     try:
         assert torch.equal(m.normalised_log_mel(ai), m.normalised_log_mel(af))
         assert torch.equal(m(ai[:, :-1]), m(af[:, :-1]))
     finally:
-        os.environ.pop("RVB_NO_FUSED_FOLD", None)
+        os.environ.pop("RVB_FUSED_FOLD", None)
     os.environ["RVB_STFT_OPERAND"] = "tf32"
     try:
         m2 = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
@@ -194,38 +194,41 @@ def test_fused_fold_pcm16_golden_and_against_the_materialised_route(R, dev, gold
     ai = torch.from_numpy(a16).to(dev)
     m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
     calls = []
+    os.environ["RVB_FUSED_FOLD"] = "1"
     R._lib.record_calls(calls)
     try:
         mel_x = m(ai[:, :-1])
+        assert torch.equal(mel_x, m(ai[:, :-1]))
+        spec = m.normalised_log_mel(ai).cpu().numpy()
     finally:
         R._lib.record_calls(None)
-    assert [n for n, _ in calls] == ["rvb_pad_parity_pcm16", "rvb_stft_mel_fused_pcm16"]
+        os.environ.pop("RVB_FUSED_FOLD", None)
+    assert [n for n, _ in calls][:2] == ["rvb_pad_parity_pcm16", "rvb_stft_mel_fused_pcm16"]
     assert mel_x.shape == (2, 229, 640)
     assert relerr(torch.log(mel_x + 1e-5).cpu().numpy(), g["log_mel"]) < LOGMEL_TOL
-    assert torch.equal(mel_x, m(ai[:, :-1]))
-    os.environ["RVB_NO_FUSED_FOLD"] = "1"
+    os.environ["RVB_FUSED_FOLD"] = "0"
     try:
         calls = []
         R._lib.record_calls(calls)
         mel_q = m(ai[:, :-1])
         R._lib.record_calls(None)
     finally:
-        os.environ.pop("RVB_NO_FUSED_FOLD", None)
+        os.environ.pop("RVB_FUSED_FOLD", None)
     assert [n for n, _ in calls] == ["rvb_fold_split2_f16_pcm16", "rvb_stft_mel_folded2_f16"]
     # same exact operand values, split at a different bit: the two routes differ by the dropped lo*lo products only
     assert float(((mel_x - mel_q).abs() / (mel_q.abs() + 1e-7)).max()) < 2e-5
-    spec = m.normalised_log_mel(ai).cpu().numpy()
     assert np.abs(spec.reshape(2, -1)[:, ::7] - g["spec_stride7"]).max() < LOGMEL_TOL
     assert spec.min() == 0.0 and spec.max() == 1.0
 
 
-def test_fused_fold_pcm16_edges(R, dev):
+def test_fused_fold_pcm16_edges(R, dev, monkeypatch):
     """Ragged batch sizes (rows past the last frame in a tile), the shortest legal signal, full-scale and silent
     input, a non-contiguous batch view -- against the float64 oracle."""
     from oracle.frontend import FrontEndOracle
     from reconvat_b200 import synth
     m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
     orc = FrontEndOracle()
+    monkeypatch.setenv("RVB_FUSED_FOLD", "1")
     for B, L in ((1, 1026), (3, 8 * 512 + 1), (5, 77 * 512 + 1)):
         a16 = np.stack([synth.music_int16(L, 70 + b) if b % 2 else synth.white_int16(L, 70 + b) for b in range(B)])
         a16[0, :] = np.where(np.arange(L) % 2 == 0, 32767, -32768)            # full-scale Nyquist-rate square wave
