@@ -291,6 +291,20 @@ int rvb_normalise_framewise(const float* x, float* y, int n_seg, int n_bins, int
  */
 int rvb_vat_perturb(const float* x, const float* d, float* x_adv, int64_t n_rows, int row_len, float xi,
                     int do_clamp, rvb_stream_t stream);
+/*
+ * V0 + V1  rvb_vat_perturb with the direction DRAWN IN THE KERNEL (model/self_attention_VAT.py:172, :176-177):
+ * d = torch.randn_like(x) bit for bit -- Philox4x32-10 keyed by the generator's seed, Box-Muller, ATen's element <->
+ * (thread, call, component) mapping for a contiguous tensor -- then x_adv as rvb_vat_perturb.  No ATen kernel, no
+ * round trip of d through HBM for this step; d_out (nullable) receives d for rvb_vat_finalize.
+ *   seed, offset    the CUDA generator's seed and Philox offset BEFORE the draw (offset % 4 == 0)
+ *   aten_threads   256 * min(#SM * (maxThreadsPerSM / 256), ceil(numel / 256)): ATen's launch geometry
+ *   increment       ((numel - 1) / (4 * aten_threads) + 1) * 4: what the caller adds to the generator's offset
+ *   dev_state       NULL, or device uint64[3] = {seed, offset, 0}: read INSTEAD of (seed, offset), and the offset is
+ *                   advanced by `increment` when the kernel ends -- a captured CUDA graph replays a continuing stream
+ */
+int rvb_vat_perturb_draw(const float* x, float* d_out, float* x_adv, int64_t n_rows, int row_len, float xi, int do_clamp,
+                         uint64_t seed, uint64_t offset, uint32_t aten_threads, uint64_t increment, uint64_t* dev_state,
+                         rvb_stream_t stream);
 
 /*
  * V2  grad = gscale * (p - y) / max((1 - p) * p, 1e-12) / n   (d mean-BCE / d p, ATen's formula).

@@ -70,6 +70,31 @@ def _draw_direction(x_in, x):
     return torch.randn_like(x_in).contiguous()
 
 
+def philox_geometry(numel, device):
+    """ATen's launch geometry for ``normal_`` on a contiguous tensor (DistributionTemplates.h, calc_execution_policy):
+    (total threads TT, what the draw adds to the generator's Philox offset)."""
+    prop = torch.cuda.get_device_properties(device)
+    grid = min(prop.multi_processor_count * (prop.max_threads_per_multi_processor // 256), -(-numel // 256))
+    tt = 256 * grid
+    return tt, ((numel - 1) // (4 * tt) + 1) * 4
+
+
+def _perturb_draw(x, x_adv, d_out, n_rows, row_len, xi, clamp, rng_state=None):
+    """x_adv = clamp(x + XI * d / ||d||_row) with d = torch.randn_like(x) drawn inside the kernel, bit for bit (the
+    same global Philox stream, model/self_attention_VAT.py:172): eager calls read the CUDA generator's (seed, offset)
+    and advance it exactly as ATen would; inside a CUDA-graph capture the stream lives in ``rng_state`` (device
+    uint64[3], see Scratch) and continues from replay to replay."""
+    tt, inc = philox_geometry(x.numel(), x.device)
+    if rng_state is not None:
+        seed, offset, state_ptr = 0, 0, rng_state.data_ptr()
+    else:
+        gen = torch.cuda.default_generators[x.device.index if x.device.index is not None else torch.cuda.current_device()]
+        seed, offset, state_ptr = gen.initial_seed(), gen.get_offset(), None
+        gen.set_offset(offset + inc)
+    _lib.call("rvb_vat_perturb_draw", x.data_ptr(), None if d_out is None else d_out.data_ptr(), x_adv.data_ptr(), n_rows,
+              row_len, float(xi), int(clamp), seed & 0xFFFFFFFFFFFFFFFF, offset, tt, inc, state_ptr)
+
+
 class _DivMean(torch.autograd.Function):
     """A divergence between posteriors with our forward and backward kernels: ``kind`` BCE
     (``F.binary_cross_entropy``), BKL (the reference's ``binary_kl_div``) or MSE (``F.mse_loss``); ``y`` is a label
@@ -141,6 +166,15 @@ class Scratch:
         self.device = torch.device(device)
         self.div = torch.zeros(_lib.BCE_WORKSPACE_FLOATS, dtype=torch.float32, device=self.device)
         self._stats = None
+        # a private Philox stream for the in-kernel draw of d inside captured graphs: {seed, offset, ticket}.  It starts
+        # at the CUDA generator's current position, and the generator skips 2^40 draws so that neither it nor another
+        # Scratch ever revisits this segment (replays advance the device-side offset, never the host generator).
+        gen = torch.cuda.default_generators[self.device.index if self.device.index is not None
+                                            else torch.cuda.current_device()]
+        seed, offset = gen.initial_seed(), gen.get_offset()
+        gen.set_offset(offset + (1 << 40))
+        self.rng_state = torch.tensor([seed - (1 << 64) if seed >= (1 << 63) else seed, offset, 0], dtype=torch.int64,
+                                      device=self.device)
         # False: the module returns None for its third output (the normalised direction) and the kernel does not
         # store it -- for callers that only log its mean (``last_r_norm_mean``), as run_on_batch does
         self.keep_d_hat = keep_d_hat
@@ -261,7 +295,12 @@ class _VATCore(nn.Module):
         with torch.no_grad():
             y_ref = [y.detach() for y in self._model_outputs(model, x)]   # labels, no grad (…:163-164)
 
-        d = _draw_direction(x_in, x)                                      # same global Philox stream (…:172)
+        capturing = torch.cuda.is_current_stream_capturing()
+        # d ~ N(0, 1) from the global Philox stream (…:172): drawn inside the perturb kernel when x is contiguous
+        # (bit-identical to torch.randn_like), by ATen on the caller's strides otherwise
+        fused_draw = (self.n_power == 1 and not self.binwise and x_in.is_contiguous()
+                      and (not capturing or self.scratch is not None) and not os.environ.get("RVB_NO_FUSED_DRAW"))
+        d = torch.empty_like(x) if fused_draw else _draw_direction(x_in, x)
         sc = self.scratch if not self.binwise else None
         div_ws = None if self.scratch is None else self.scratch.div
         if sc is not None:
@@ -280,6 +319,9 @@ class _VATCore(nn.Module):
             if self.binwise:
                 _lib.call("rvb_vat_perturb_binwise", x.data_ptr(), d.data_ptr(), x_adv.data_ptr(), x.numel(),
                           float(self.XI), int(self._clamp))
+            elif fused_draw:
+                _perturb_draw(x, x_adv, d, n_rows, row_len, self.XI, self._clamp,
+                              self.scratch.rng_state if capturing else None)
             else:
                 _lib.call("rvb_vat_perturb", x.data_ptr(), d.data_ptr(), x_adv.data_ptr(), n_rows, row_len,
                           float(self.XI), int(self._clamp))

@@ -8,6 +8,8 @@
 // each tensor is read or written exactly once.
 #include <type_traits>
 
+#include <curand_kernel.h>        // device-side Philox4x32-10 and Box-Muller, the functions ATen's normal_ kernel calls
+
 #include "rvb_common.cuh"
 
 namespace rvb {
@@ -69,6 +71,88 @@ vat_perturb_kernel(const float* __restrict__ x, const float* __restrict__ d, flo
   };
   if (rcp_usable(rn)) body(std::true_type{}); else body(std::false_type{});
   store_row(rx, x_adv + off, row_len, lane);
+}
+
+// ---- V0 + V1: draw d ~ N(0, 1) IN the perturb kernel, bit-identical to torch.randn_like ------------------------
+// ATen's normal_ on a contiguous float tensor of n elements (aten/src/ATen/native/cuda/DistributionTemplates.h):
+// grid = min(#SM * (maxThreadsPerSM / 256), ceil(n / 256)) blocks of 256 threads, TT = 256 * grid threads in total;
+// thread idx owns the Philox4x32-10 stream (key = seed, subsequence = idx, offset = the generator's offset) and its
+// j-th curand_normal4 call fills elements idx + TT * (4 j + ii), ii = 0 .. 3; afterwards the generator's offset has
+// advanced by ((n - 1) / (4 TT) + 1) * 4.  So element li is component ii of Box-Muller on Philox(key,
+// counter = (offset / 4 + j, idx)) with q = li / TT, idx = li % TT, j = q >> 2, ii = q & 3 -- computable for any
+// element on its own.  A row-wise kernel cannot share a Philox call between its four elements (they lie TT apart), so
+// each element pays a full call: ~95 instructions, the price of bit parity (the separate ATen kernel it replaces cost
+// 13 us per step, one launch and a 19 MB write + read of d).
+struct DrawArgs {
+  unsigned long long seed, offset;      // used when dev_state == nullptr (eager: read from torch's generator)
+  unsigned long long* dev_state;        // [seed, offset, ticket]: CUDA-graph replays carry their own stream
+  unsigned long long increment;         // what ATen would add to the offset
+  unsigned tt;                          // TT
+};
+
+__device__ __forceinline__ float draw_normal(unsigned long long seed, unsigned long long ctr_lo, unsigned idx, unsigned ii) {
+  const uint4 ctr = make_uint4((unsigned)ctr_lo, (unsigned)(ctr_lo >> 32), idx, 0u);
+  const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+  const uint4 r = curand_Philox4x32_10(ctr, key);
+  const float2 n2 = _curand_box_muller((ii & 2) ? r.z : r.x, (ii & 2) ? r.w : r.y);
+  return (ii & 1) ? n2.y : n2.x;
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(kRowsPerBlock* kWarp)
+vat_perturb_draw_kernel(const float* __restrict__ x, float* __restrict__ d_out, float* __restrict__ x_adv,
+                        int64_t n_rows, int row_len, float xi, int do_clamp, DrawArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  unsigned long long seed = a.seed, offset = a.offset;
+  if (a.dev_state) { seed = a.dev_state[0]; offset = a.dev_state[1]; }
+  if (row < n_rows) {
+    const int64_t off = row * row_len;
+    // (q, idx) of the row's first element; a row crosses at most one multiple of TT
+    const unsigned long long q0 = (unsigned long long)off / a.tt;
+    const unsigned rem0 = (unsigned)((unsigned long long)off - q0 * a.tt);
+    RowRegs<NPL> rd, rx;
+    load_row(rx, x + off, row_len, lane);
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int c = lane + i * kWarp;
+      float v = 0.f;
+      if (c < row_len) {
+        unsigned idx = rem0 + (unsigned)c;
+        unsigned long long q = q0;
+        if (idx >= a.tt) { idx -= a.tt; ++q; }
+        v = draw_normal(seed, (offset >> 2) + (q >> 2), idx, (unsigned)(q & 3));
+      }
+      rd.v[i] = v;
+    }
+    if (d_out) store_row(rd, d_out + off, row_len, lane);
+    const float n = sqrtf(row_sumsq(rd));       // torch.norm(d, dim=-1)
+    const float rn = 1.f / n;
+    auto body = [&](auto fast) {
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        float s = rx.v[i] + xi * div_by<decltype(fast)::value>(rd.v[i], n, rn);   // x + XI * (d / n)
+        rx.v[i] = do_clamp ? clamp01(s) : s;
+      }
+    };
+    if (rcp_usable(rn)) body(std::true_type{}); else body(std::false_type{});
+    store_row(rx, x_adv + off, row_len, lane);
+  }
+  if (a.dev_state) {
+    // the last block to finish advances the device-resident offset (every block has read it by then)
+    __shared__ bool is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      is_last = atomicAdd(a.dev_state + 2, 1ull) == (unsigned long long)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+      a.dev_state[1] = offset + a.increment;
+      a.dev_state[2] = 0ull;
+      __threadfence();
+    }
+  }
 }
 
 // ---- V3: power-iteration backward + finalisation ----------------------------------------
@@ -454,6 +538,27 @@ extern "C" int rvb_vat_perturb(const float* x, const float* d, float* x_adv, int
         x, d, x_adv, n_rows, row_len, xi, do_clamp);
     count_launch();
     return check_launch("vat_perturb_kernel");
+  });
+}
+
+extern "C" int rvb_vat_perturb_draw(const float* x, float* d_out, float* x_adv, int64_t n_rows, int row_len, float xi,
+                                    int do_clamp, uint64_t seed, uint64_t offset, uint32_t aten_threads,
+                                    uint64_t increment, uint64_t* dev_state, rvb_stream_t stream) {
+  RVB_REQUIRE(x && x_adv, "rvb_vat_perturb_draw: null pointer");
+  RVB_REQUIRE(n_rows >= 0 && row_len > 0, "rvb_vat_perturb_draw: bad shape (%lld, %d)", (long long)n_rows, row_len);
+  RVB_REQUIRE(aten_threads > 0 && aten_threads % 256 == 0, "rvb_vat_perturb_draw: aten_threads must be 256 * grid");
+  RVB_REQUIRE((offset & 3) == 0 && (increment & 3) == 0, "rvb_vat_perturb_draw: Philox offsets are multiples of 4");
+  RVB_REQUIRE(n_rows * (int64_t)row_len < (int64_t)aten_threads * 0x7fffffffll, "rvb_vat_perturb_draw: tensor too large");
+  if (n_rows == 0) return RVB_OK;
+  const unsigned grid = (unsigned)((n_rows + kRowsPerBlock - 1) / kRowsPerBlock);
+  DrawArgs a;
+  a.seed = seed; a.offset = offset; a.dev_state = reinterpret_cast<unsigned long long*>(dev_state);
+  a.increment = increment; a.tt = aten_threads;
+  return dispatch_npl(row_len, [&](auto npl) {
+    vat_perturb_draw_kernel<decltype(npl)::value><<<grid, kRowsPerBlock * kWarp, 0, (cudaStream_t)stream>>>(
+        x, d_out, x_adv, n_rows, row_len, xi, do_clamp, a);
+    count_launch();
+    return check_launch("vat_perturb_draw_kernel");
   });
 }
 

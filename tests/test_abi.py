@@ -48,7 +48,7 @@ def test_ctypes_table_mirrors_header(lib):
                 "rvb_parity_plane_len"}
     assert set(lib.SIGNATURES) == set(decls) - plumbing
     kinds = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_int64: "int64_t", ctypes.c_float: "float",
-             ctypes.c_double: "double"}
+             ctypes.c_double: "double", ctypes.c_uint64: "uint64_t", ctypes.c_uint32: "uint32_t"}
     for name, argtypes in lib.SIGNATURES.items():
         args = decls[name]
         assert len(args) == len(argtypes), name
@@ -57,6 +57,8 @@ def test_ctypes_table_mirrors_header(lib):
                 assert kinds[t] == "ptr", (name, a)
             elif a.startswith("int64_t"):
                 assert kinds[t] == "int64_t", (name, a)
+            elif a.startswith("uint64_t") or a.startswith("uint32_t"):
+                assert kinds[t] == a.split()[0], (name, a)
             elif a.startswith("int"):
                 assert kinds[t] == "int", (name, a)
             elif a.startswith("float"):

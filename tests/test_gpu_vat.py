@@ -463,3 +463,68 @@ def test_l2_normalize_and_n_power_zero(R, dev):
     loss, r_adv, d_hat = vat(m, x)
     assert torch.allclose(r_adv.norm(dim=-1), torch.full_like(r_adv[..., 0], 2.0), rtol=1e-5)
     assert torch.allclose(r_adv, 2.0 * d_hat)
+
+
+@pytest.mark.parametrize("shape,warm", [((32, 1, 640, 229), 0), ((8, 640, 229), 3), ((2, 1, 33, 229), 1), ((3, 1, 7, 100), 0),
+                                        ((1, 1, 1324, 229), 2)])
+def test_in_kernel_direction_draw_is_torch_randn_like(R, dev, shape, warm):
+    """a11 (model/self_attention_VAT.py:172): rvb_vat_perturb_draw draws d inside the kernel -- Philox4x32-10 +
+    Box-Muller with ATen's element <-> (thread, call, component) mapping.  Same seed and generator position in, the
+    SAME BITS as torch.randn_like out, the generator advanced by the same amount, x_adv as rvb_vat_perturb on that d.
+    Shapes: the benchmark tensor (16 Philox bands), the O&F 3-D input, a tensor smaller than ATen's grid, a row length
+    that is not 229, and one whose rows straddle a band boundary."""
+    from reconvat_b200 import VAT
+    gen = torch.cuda.default_generators[dev.index or 0]
+    torch.manual_seed(1234 + warm)
+    for _ in range(warm):
+        torch.randn(1000 + 77 * warm, device=dev)            # the draw does not start at offset 0
+    x = torch.rand(shape, device=dev)
+    state = gen.get_state()
+    d_ref = torch.randn_like(x)
+    after = gen.get_offset()
+    gen.set_state(state)
+    n_rows, row_len = x.numel() // x.shape[-1], x.shape[-1]
+    d, x_adv = torch.full_like(x, float("nan")), torch.empty_like(x)
+    VAT._perturb_draw(x, x_adv, d, n_rows, row_len, 0.1, True)
+    assert gen.get_offset() == after
+    assert torch.equal(d, d_ref)
+    want = torch.empty_like(x)
+    R._lib.call("rvb_vat_perturb", x.data_ptr(), d_ref.data_ptr(), want.data_ptr(), n_rows, row_len, 0.1, 1)
+    assert torch.equal(x_adv, want)
+    nxt = torch.randn(5, device=dev)                         # ... and the stream continues where ATen's would
+    gen.set_state(state)
+    torch.randn_like(x)
+    assert torch.equal(nxt, torch.randn(5, device=dev))
+
+
+def test_module_with_fused_draw_equals_module_with_aten_draw(R, dev, monkeypatch):
+    """The whole module, same seed: d drawn in the kernel vs by torch.randn_like -- identical r_adv, d_hat and loss
+    bits; and a device-resident stream (CUDA-graph mode) that advances from call to call."""
+    from reconvat_b200 import VAT
+    from reconvat_b200.standin import StandInTranscriber
+    m = StandInTranscriber("unet", seed=4).to(dev)
+    x = _spec_like(3, 40).to(dev)
+    vat = R.VAT.UNet_VAT(0.1, 2.0, 1, False)
+    torch.manual_seed(8)
+    a = vat(m, x)
+    monkeypatch.setenv("RVB_NO_FUSED_DRAW", "1")
+    torch.manual_seed(8)
+    b = vat(m, x)
+    monkeypatch.delenv("RVB_NO_FUSED_DRAW")
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and float(a[0]) == float(b[0])
+    sc = VAT.Scratch(dev)
+    n_rows = x.numel() // 229
+    outs = []
+    for _ in range(3):
+        d, xa = torch.empty_like(x), torch.empty_like(x)
+        VAT._perturb_draw(x, xa, d, n_rows, 229, 0.1, True, rng_state=sc.rng_state)
+        outs.append(d)
+    st = sc.rng_state.cpu()
+    _, inc = VAT.philox_geometry(x.numel(), dev)
+    assert int(st[2]) == 0 and not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
+    # replay i of the device stream == torch.randn_like at offset0 + i * increment
+    gen = torch.cuda.default_generators[dev.index or 0]
+    saved = gen.get_state()
+    gen.set_offset(int(st[1]) - inc)
+    assert torch.equal(torch.randn_like(x), outs[2])
+    gen.set_state(saved)
