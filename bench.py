@@ -32,6 +32,9 @@ HBM_BYTES_PER_SEG = {
     "rvb_fold_split_f16_pcm16": 1310716 // 2 + 4 * 640 * 1024 * 2 + 640 * 4,
     "rvb_fold_split2_f16": 1310716 + 4 * 640 * 1024 * 2 + 640 * 4,  # the same planes, even-n columns first
     "rvb_fold_split2_f16_pcm16": 1310716 // 2 + 4 * 640 * 1024 * 2 + 640 * 4,
+    "rvb_pad_parity_pcm16": 327679 * 2 + 2 * 164864 * 2,           # R PCM16, W the two parity planes (K0x)
+    "rvb_randn_like": N4,                                           # W d (the draw, ATen's amortisation)
+    "rvb_vat_perturb_draw": 3 * N4,                                 # R x, W d (for the finalisation), W x_adv
     "rvb_mel_project": 1020 * 640 * 4 + N4,
     "rvb_logmel_minmax": N4,
     "rvb_logmel_transpose": 2 * N4,
@@ -410,11 +413,12 @@ def run_ours(args, rank, local_rank, world):
     if rank != 0:
         return
     peaks = load_peaks()
-    fold2 = "rvb_stft_mel_folded2_f16" in kavg
+    fold2x = "rvb_stft_mel_fused_pcm16" in kavg
+    fold2 = fold2x or "rvb_stft_mel_folded2_f16" in kavg
     fused = fold2 or "rvb_stft_mel_folded_f16" in kavg
     f16 = fused or "rvb_stft_gemm_folded_f16" in kavg
     folded = f16 or "rvb_stft_gemm_folded" in kavg
-    gemm_name = ("rvb_stft_mel_folded2_f16" if fold2 else "rvb_stft_mel_folded_f16" if fused else
+    gemm_name = ("rvb_stft_mel_fused_pcm16" if fold2x else "rvb_stft_mel_folded2_f16" if fold2 else "rvb_stft_mel_folded_f16" if fused else
                  "rvb_stft_gemm_folded_f16" if f16 else "rvb_stft_gemm_folded" if folded else "rvb_stft_gemm")
     gemm_ms = kavg.get(gemm_name)
     roofline = None
@@ -424,7 +428,8 @@ def run_ours(args, rank, local_rank, world):
         k_len = 512 if fold2 else 1024 if folded else 2048
         achieved = B * STFT_FLOP_PER_SEG / (gemm_ms * 1e-3) / 1e12
         issued = 3 * B * 2 * 640 * 2048 * k_len / (gemm_ms * 1e-3) / 1e12
-        kname = ("stft_gemm_fold2c_pair_kernel + Mel epilogue" if fold2 else
+        kname = ("stft_gemm_fold2x_pair_kernel + Mel epilogue" if fold2x else
+                 "stft_gemm_fold2c_pair_kernel + Mel epilogue" if fold2 else
                  "stft_gemm_fold_pair_kernel%s" % (" + Mel epilogue" if fused else "") if f16 else
                  "stft_gemm_fold_kernel<tf32>") if folded else "stft_gemm_kernel"
         pipe_peak = peaks["bf16"] if f16 else peaks["bf16"] / 2

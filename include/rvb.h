@@ -305,6 +305,14 @@ int rvb_vat_perturb(const float* x, const float* d, float* x_adv, int64_t n_rows
 int rvb_vat_perturb_draw(const float* x, float* d_out, float* x_adv, int64_t n_rows, int row_len, float xi, int do_clamp,
                          uint64_t seed, uint64_t offset, uint32_t aten_threads, uint64_t increment, uint64_t* dev_state,
                          rvb_stream_t stream);
+/*
+ * V0  d = torch.randn_like(x) (model/self_attention_VAT.py:172) as a kernel of this library: the same bits as ATen's
+ * normal_ kernel for a contiguous float tensor of n elements (arguments as rvb_vat_perturb_draw), one Philox call per
+ * four elements like ATen, all trips of a thread issued at once.  For steps that run beside a tensor-bound kernel of
+ * another stream, where the 4x Philox work of the fused draw costs more than a round trip of d through HBM.
+ */
+int rvb_randn_like(float* out, int64_t n, uint64_t seed, uint64_t offset, uint32_t aten_threads, uint64_t increment,
+                   uint64_t* dev_state, rvb_stream_t stream);
 
 /*
  * V2  grad = gscale * (p - y) / max((1 - p) * p, 1e-12) / n   (d mean-BCE / d p, ATen's formula).

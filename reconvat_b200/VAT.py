@@ -43,7 +43,7 @@ from . import _lib
 
 __all__ = ["stepwise_VAT_vatpy", "stepwise_VAT", "UNet_VAT", "onset_frame_VAT", "UNet_VAT_onset",
            "stepwise_VAT_onf", "stepwise_VAT_frame_stack", "Seg_VAT", "bce_mean", "binary_kl_div", "mse_mean",
-           "l2_normalize", "Scratch"]
+           "l2_normalize", "randn_like", "Scratch"]
 
 
 def _rows(x):
@@ -70,29 +70,48 @@ def _draw_direction(x_in, x):
     return torch.randn_like(x_in).contiguous()
 
 
+_ATEN_RANDN_LIKE = torch.randn_like      # whoever rebinds torch.randn_like (tests injecting d) keeps getting called
+_max_aten_blocks = {}
+
+
 def philox_geometry(numel, device):
     """ATen's launch geometry for ``normal_`` on a contiguous tensor (DistributionTemplates.h, calc_execution_policy):
     (total threads TT, what the draw adds to the generator's Philox offset)."""
-    prop = torch.cuda.get_device_properties(device)
-    grid = min(prop.multi_processor_count * (prop.max_threads_per_multi_processor // 256), -(-numel // 256))
-    tt = 256 * grid
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    cap = _max_aten_blocks.get(index)
+    if cap is None:
+        prop = torch.cuda.get_device_properties(index)
+        cap = _max_aten_blocks[index] = prop.multi_processor_count * (prop.max_threads_per_multi_processor // 256)
+    tt = 256 * min(cap, -(-numel // 256))
     return tt, ((numel - 1) // (4 * tt) + 1) * 4
 
 
-def _perturb_draw(x, x_adv, d_out, n_rows, row_len, xi, clamp, rng_state=None):
-    """x_adv = clamp(x + XI * d / ||d||_row) with d = torch.randn_like(x) drawn inside the kernel, bit for bit (the
-    same global Philox stream, model/self_attention_VAT.py:172): eager calls read the CUDA generator's (seed, offset)
-    and advance it exactly as ATen would; inside a CUDA-graph capture the stream lives in ``rng_state`` (device
-    uint64[3], see Scratch) and continues from replay to replay."""
+def _philox_args(x, rng_state):
+    """(seed, offset, TT, increment, device-state pointer) for a draw of x.numel() normals.  Eager calls read the CUDA
+    generator's (seed, offset) and advance it exactly as ATen would; inside a CUDA-graph capture the stream lives in
+    ``rng_state`` (device uint64[3], see Scratch) and continues from replay to replay."""
     tt, inc = philox_geometry(x.numel(), x.device)
     if rng_state is not None:
-        seed, offset, state_ptr = 0, 0, rng_state.data_ptr()
-    else:
-        gen = torch.cuda.default_generators[x.device.index if x.device.index is not None else torch.cuda.current_device()]
-        seed, offset, state_ptr = gen.initial_seed(), gen.get_offset(), None
-        gen.set_offset(offset + inc)
+        return 0, 0, tt, inc, rng_state.data_ptr()
+    gen = torch.cuda.default_generators[x.device.index if x.device.index is not None else torch.cuda.current_device()]
+    seed, offset = gen.initial_seed(), gen.get_offset()
+    gen.set_offset(offset + inc)
+    return seed & 0xFFFFFFFFFFFFFFFF, offset, tt, inc, None
+
+
+def randn_like(x, rng_state=None):
+    """``torch.randn_like(x)`` for a contiguous float32 CUDA tensor, bit for bit, by ``rvb_randn_like`` (same global
+    Philox stream, model/self_attention_VAT.py:172)."""
+    x = _check_input(x)
+    d = torch.empty_like(x)
+    _lib.call("rvb_randn_like", d.data_ptr(), d.numel(), *_philox_args(x, rng_state))
+    return d
+
+
+def _perturb_draw(x, x_adv, d_out, n_rows, row_len, xi, clamp, rng_state=None):
+    """x_adv = clamp(x + XI * d / ||d||_row) with d = torch.randn_like(x) drawn inside the row kernel, bit for bit."""
     _lib.call("rvb_vat_perturb_draw", x.data_ptr(), None if d_out is None else d_out.data_ptr(), x_adv.data_ptr(), n_rows,
-              row_len, float(xi), int(clamp), seed & 0xFFFFFFFFFFFFFFFF, offset, tt, inc, state_ptr)
+              row_len, float(xi), int(clamp), *_philox_args(x, rng_state))
 
 
 class _DivMean(torch.autograd.Function):
@@ -298,9 +317,14 @@ class _VATCore(nn.Module):
         capturing = torch.cuda.is_current_stream_capturing()
         # d ~ N(0, 1) from the global Philox stream (…:172): drawn inside the perturb kernel when x is contiguous
         # (bit-identical to torch.randn_like), by ATen on the caller's strides otherwise
-        fused_draw = (self.n_power == 1 and not self.binwise and x_in.is_contiguous()
-                      and (not capturing or self.scratch is not None) and not os.environ.get("RVB_NO_FUSED_DRAW"))
-        d = torch.empty_like(x) if fused_draw else _draw_direction(x_in, x)
+        # RVB_DRAW = kernel (default): rvb_randn_like, ATen's amortisation; fused: inside rvb_vat_perturb (no round trip
+        # of d, 4x the Philox work: fastest on an otherwise idle GPU); aten: torch.randn_like itself
+        mode = os.environ.get("RVB_DRAW", "kernel")
+        ours = (mode != "aten" and x_in.is_contiguous() and torch.randn_like is _ATEN_RANDN_LIKE
+                and (not capturing or self.scratch is not None))
+        fused_draw = ours and mode == "fused" and self.n_power == 1 and not self.binwise
+        rng_state = self.scratch.rng_state if (capturing and self.scratch is not None) else None
+        d = torch.empty_like(x) if fused_draw else (randn_like(x, rng_state) if ours else _draw_direction(x_in, x))
         sc = self.scratch if not self.binwise else None
         div_ws = None if self.scratch is None else self.scratch.div
         if sc is not None:
@@ -320,8 +344,7 @@ class _VATCore(nn.Module):
                 _lib.call("rvb_vat_perturb_binwise", x.data_ptr(), d.data_ptr(), x_adv.data_ptr(), x.numel(),
                           float(self.XI), int(self._clamp))
             elif fused_draw:
-                _perturb_draw(x, x_adv, d, n_rows, row_len, self.XI, self._clamp,
-                              self.scratch.rng_state if capturing else None)
+                _perturb_draw(x, x_adv, d, n_rows, row_len, self.XI, self._clamp, rng_state)
             else:
                 _lib.call("rvb_vat_perturb", x.data_ptr(), d.data_ptr(), x_adv.data_ptr(), n_rows, row_len,
                           float(self.XI), int(self._clamp))

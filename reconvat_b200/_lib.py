@@ -46,6 +46,7 @@ SIGNATURES = {
     "rvb_vat_perturb": [_c_p, _c_p, _c_p, _i64, _i32, _f32, _i32, _c_p],
     "rvb_vat_perturb_draw": [_c_p, _c_p, _c_p, _i64, _i32, _f32, _i32, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
                              ctypes.c_uint64, _c_p, _c_p],
+    "rvb_randn_like": [_c_p, _i64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, _c_p, _c_p],
     "rvb_bce_grad": [_c_p, _c_p, _c_p, _i64, _c_p, _f32, _c_p],
     "rvb_vat_finalize": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i64, _i32, _f32, _f32, _f32, _i32, _c_p, _c_p],
     "rvb_div_grad": [_i32, _c_p, _c_p, _c_p, _i64, ctypes.c_double, _c_p, _f32, _c_p],

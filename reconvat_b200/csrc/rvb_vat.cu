@@ -49,28 +49,45 @@ __device__ __forceinline__ float row_sumsq(const RowRegs<NPL>& r) {
 }
 
 // ---- V1: x_adv = clamp(x + xi * d/||d||) -------------------------------------------------
+// Persistent: the grid is a few blocks per SM and every warp walks rows with a fixed stride, the loads of its NEXT row
+// issued before the current row is reduced -- a warp always has 2 x NPL x 128 bytes in flight.  One-shot blocks (one row
+// per warp, then exit) ramp up and drain once per 8 rows; beside a resident contraction CTA of another stream, where
+// only one such block fits per SM, that left the memory pipe idle between blocks (144 -> 217 us for the HBM kernels of a
+// step, profiles/r01f_experiments.md).
+constexpr int kPersistBlocksPerSM = 3;
+
 template <int NPL>
-__global__ void __launch_bounds__(kRowsPerBlock* kWarp)
+__global__ void __launch_bounds__(kRowsPerBlock* kWarp) __maxnreg__(NPL <= 8 ? 72 : 128)
 vat_perturb_kernel(const float* __restrict__ x, const float* __restrict__ d, float* __restrict__ x_adv,
                    int64_t n_rows, int row_len, float xi, int do_clamp) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * kRowsPerBlock;
+  int64_t row = (int64_t)blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   if (row >= n_rows) return;
-  const int64_t off = row * row_len;
-  RowRegs<NPL> rd, rx;
-  load_row(rd, d + off, row_len, lane);
-  load_row(rx, x + off, row_len, lane);
-  const float n = sqrtf(row_sumsq(rd));       // torch.norm(d, dim=-1)
-  const float rn = 1.f / n;
-  auto body = [&](auto fast) {
-#pragma unroll
-    for (int i = 0; i < NPL; ++i) {
-      float s = rx.v[i] + xi * div_by<decltype(fast)::value>(rd.v[i], n, rn);   // x + XI * (d / n)
-      rx.v[i] = do_clamp ? clamp01(s) : s;
+  RowRegs<NPL> nd, nx;
+  load_row(nd, d + row * row_len, row_len, lane);
+  load_row(nx, x + row * row_len, row_len, lane);
+  for (;;) {
+    RowRegs<NPL> rd = nd, rx = nx;
+    const int64_t off = row * row_len, next = row + stride;
+    if (next < n_rows) {
+      load_row(nd, d + next * row_len, row_len, lane);
+      load_row(nx, x + next * row_len, row_len, lane);
     }
-  };
-  if (rcp_usable(rn)) body(std::true_type{}); else body(std::false_type{});
-  store_row(rx, x_adv + off, row_len, lane);
+    const float n = sqrtf(row_sumsq(rd));       // torch.norm(d, dim=-1)
+    const float rn = 1.f / n;
+    auto body = [&](auto fast) {
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        float s = rx.v[i] + xi * div_by<decltype(fast)::value>(rd.v[i], n, rn);   // x + XI * (d / n)
+        rx.v[i] = do_clamp ? clamp01(s) : s;
+      }
+    };
+    if (rcp_usable(rn)) body(std::true_type{}); else body(std::false_type{});
+    store_row(rx, x_adv + off, row_len, lane);
+    if (next >= n_rows) break;
+    row = next;
+  }
 }
 
 // ---- V0 + V1: draw d ~ N(0, 1) IN the perturb kernel, bit-identical to torch.randn_like ------------------------
@@ -96,6 +113,56 @@ __device__ __forceinline__ float draw_normal(unsigned long long seed, unsigned l
   const uint4 r = curand_Philox4x32_10(ctr, key);
   const float2 n2 = _curand_box_muller((ii & 2) ? r.z : r.x, (ii & 2) ? r.w : r.y);
   return (ii & 1) ? n2.y : n2.x;
+}
+
+// The same draw as a kernel of its own, with ATen's amortisation: thread <-> Philox stream idx, one Philox call and two
+// Box-Muller evaluations per FOUR elements (idx + TT (4 j + ii)), every store warp-coalesced.  ATen's own kernel spends
+// 13 us on the 4.7 M elements of a B = 32 step (four dependent loop trips with a __syncthreads each); this one issues
+// all trips of a thread at once.  What the fused row kernel above cannot do -- share a call between its elements --
+// costs it 4x the Philox work, which matters when the kernel runs beside the tensor-bound contraction of another
+// stream: there issue slots are scarce and HBM bytes are cheap.
+template <int kTrips>
+__global__ void __launch_bounds__(256)
+randn_like_kernel(float* __restrict__ out, int64_t n, DrawArgs a) {
+  unsigned long long seed = a.seed, offset = a.offset;
+  if (a.dev_state) { seed = a.dev_state[0]; offset = a.dev_state[1]; }
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < a.tt) {
+    const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+    const int64_t n_trips = (n + 4ll * a.tt - 1) / (4ll * a.tt);
+    for (int64_t j0 = 0; j0 < n_trips; j0 += kTrips) {
+      float4 v[kTrips];
+#pragma unroll
+      for (int t = 0; t < kTrips; ++t) {
+        const unsigned long long c = (offset >> 2) + (unsigned long long)(j0 + t);
+        const uint4 r = curand_Philox4x32_10(make_uint4((unsigned)c, (unsigned)(c >> 32), idx, 0u), key);
+        const float2 lo = _curand_box_muller(r.x, r.y), hi = _curand_box_muller(r.z, r.w);
+        v[t] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      }
+#pragma unroll
+      for (int t = 0; t < kTrips; ++t) {
+        const int64_t base = (int64_t)idx + 4ll * a.tt * (j0 + t);
+        if (base < n) out[base] = v[t].x;
+        if (base + a.tt < n) out[base + a.tt] = v[t].y;
+        if (base + 2ll * a.tt < n) out[base + 2ll * a.tt] = v[t].z;
+        if (base + 3ll * a.tt < n) out[base + 3ll * a.tt] = v[t].w;
+      }
+    }
+  }
+  if (a.dev_state) {
+    __shared__ bool is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      is_last = atomicAdd(a.dev_state + 2, 1ull) == (unsigned long long)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+      a.dev_state[1] = offset + a.increment;
+      a.dev_state[2] = 0ull;
+      __threadfence();
+    }
+  }
 }
 
 template <int NPL>
@@ -173,13 +240,18 @@ __device__ __forceinline__ RowStat finalize_row(RowRegs<NPL>& dp /* in: d' ; out
   RowRegs<NPL> rr;
   unsigned bad = 0;
   float asum = 0.f;
+  // NaN / Inf in r_adv = eps d'/||d'|| needs a NaN, an Inf or an all-zero row in d' -- and each of those makes the
+  // reciprocal of the norm unusable (0, Inf or NaN).  Rows on the fast path (usable reciprocal: every d' finite, norm
+  // finite and positive) cannot raise a bit, so only the slow path looks at the elements.  (Padding lanes hold 0.)
   auto body = [&](auto fast) {
+    constexpr bool kFast = decltype(fast)::value;
 #pragma unroll
     for (int i = 0; i < NPL; ++i) {
-      const bool in = lane + i * kWarp < row_len;
-      float dh = div_by<decltype(fast)::value>(dp.v[i], n2, rn2);      // _l2_normalize(d)
+      float dh = div_by<kFast>(dp.v[i], n2, rn2);                      // _l2_normalize(d)
       float r = eps * dh;                     // r_adv
-      if (in) {
+      if constexpr (kFast) {
+        asum += fabsf(dh);
+      } else if (lane + i * kWarp < row_len) {
         bad |= (isnan(r) ? 1u : 0u) | (isinf(r) ? 2u : 0u);
         asum += fabsf(dh);
       }
@@ -253,50 +325,65 @@ __device__ __forceinline__ void finalize_block_stats(RowStat st, bool valid, int
   }
 }
 
-// (256 threads, 5 blocks per SM: <= 48 registers, so that a block fits beside a resident contraction CTA of another
-// stream -- 576 threads x 80 registers leave 14 K registers per SM)
+// Persistent like vat_perturb_kernel: a warp walks rows with a fixed stride, the three loads of its next row in flight
+// while the current row goes through its three reductions; the per-row results (NaN / Inf bits, sum |dhat|) accumulate
+// in the warp and enter the block reduction once.
+// (<= 72 registers: 256 x 72 fit into the 19 K registers a resident contraction CTA leaves free on its SM)
 template <int NPL>
-__global__ void __launch_bounds__(kRowsPerBlock* kWarp, NPL <= 8 ? 5 : 1)
+__global__ void __launch_bounds__(kRowsPerBlock* kWarp) __maxnreg__(NPL <= 8 ? 72 : 168)
 vat_finalize_kernel(const float* __restrict__ g, const float* __restrict__ d, const float* __restrict__ x,
                     float* __restrict__ r_adv, float* __restrict__ x_adv, float* __restrict__ d_hat,
                     int64_t n_rows, int row_len, float xi, float eps, float scale, int do_clamp,
                     int32_t* status_flag, float* __restrict__ dhat_abs_mean, float* __restrict__ workspace) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
-  const bool valid = row < n_rows;                         // warp-uniform
+  const int64_t stride = (int64_t)gridDim.x * kRowsPerBlock;
+  int64_t row = (int64_t)blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  bool valid = row < n_rows;                               // warp-uniform
   RowStat st = {0u, 0.f};
+  RowRegs<NPL> nd, nx, ng;
   if (valid) {
-  const int64_t off = row * row_len;
-  RowRegs<NPL> rd, rx, rg;
-  load_row(rd, d + off, row_len, lane);
-  load_row(rx, x + off, row_len, lane);
-  load_row(rg, g + off, row_len, lane);
-  const float n = sqrtf(row_sumsq(rd));
-  const float rn = 1.f / n;
-  // gd = xi * g * [0 <= x + xi*d/n <= 1]   (clamp passes the gradient on the closed interval)
-  auto body = [&](auto fast) {
-    constexpr bool kFast = decltype(fast)::value;
-    float dot = 0.f;
-#pragma unroll
-    for (int i = 0; i < NPL; ++i) {
-      float gm = rg.v[i];
-      if (do_clamp) {
-        float s = rx.v[i] + xi * div_by<kFast>(rd.v[i], n, rn);
-        gm = (s >= 0.f && s <= 1.f) ? gm : 0.f;
-      }
-      float gd = xi * gm;
-      rg.v[i] = gd;
-      dot = fmaf(gd, rd.v[i], dot);
-    }
-    dot = warp_sum(dot);
-    const float c = dot / (n * n * n);
-#pragma unroll
-    for (int i = 0; i < NPL; ++i) rd.v[i] = (div_by<kFast>(rg.v[i], n, rn) - rd.v[i] * c) * scale;   // d.grad * scale
-  };
-  if (rcp_usable(rn)) body(std::true_type{}); else body(std::false_type{});
-  st = finalize_row(rd, rx, r_adv, x_adv, d_hat, off, row_len, lane, eps, do_clamp);
+    load_row(nd, d + row * row_len, row_len, lane);
+    load_row(nx, x + row * row_len, row_len, lane);
+    load_row(ng, g + row * row_len, row_len, lane);
   }
-  finalize_block_stats(st, valid, status_flag, dhat_abs_mean, workspace, (double)n_rows * row_len);
+  while (valid) {
+    RowRegs<NPL> rd = nd, rx = nx, rg = ng;
+    const int64_t off = row * row_len, next = row + stride;
+    valid = next < n_rows;
+    if (valid) {
+      load_row(nd, d + next * row_len, row_len, lane);
+      load_row(nx, x + next * row_len, row_len, lane);
+      load_row(ng, g + next * row_len, row_len, lane);
+    }
+    const float n = sqrtf(row_sumsq(rd));
+    const float rn = 1.f / n;
+    // gd = xi * g * [0 <= x + xi*d/n <= 1]   (clamp passes the gradient on the closed interval)
+    auto body = [&](auto fast) {
+      constexpr bool kFast = decltype(fast)::value;
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        float gm = rg.v[i];
+        if (do_clamp) {
+          float s = rx.v[i] + xi * div_by<kFast>(rd.v[i], n, rn);
+          gm = (s >= 0.f && s <= 1.f) ? gm : 0.f;
+        }
+        float gd = xi * gm;
+        rg.v[i] = gd;
+        dot = fmaf(gd, rd.v[i], dot);
+      }
+      dot = warp_sum(dot);
+      const float c = dot / (n * n * n);
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) rd.v[i] = (div_by<kFast>(rg.v[i], n, rn) - rd.v[i] * c) * scale;   // d.grad * scale
+    };
+    if (rcp_usable(rn)) body(std::true_type{}); else body(std::false_type{});
+    const RowStat one = finalize_row(rd, rx, r_adv, x_adv, d_hat, off, row_len, lane, eps, do_clamp);
+    st.bad |= one.bad;
+    st.abs_sum += one.abs_sum;
+    row = next;
+  }
+  finalize_block_stats(st, true, status_flag, dhat_abs_mean, workspace, (double)n_rows * row_len);
 }
 
 template <int NPL>
@@ -521,6 +608,25 @@ static int dispatch_npl(int row_len, F&& f) {
   return RVB_ERR_ARG;
 }
 
+// Grid of the persistent row kernels: every warp gets at least one row, at most kPersistBlocksPerSM blocks per SM.
+static unsigned persistent_grid(int64_t n_rows) {
+  static int sms[kMaxDevices] = {};
+  const int slot = device_slot();
+  int n;
+  {
+    std::lock_guard<std::mutex> g(attr_mutex());
+    if (sms[slot] == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms[slot], cudaDevAttrMultiProcessorCount, dev);
+      if (sms[slot] <= 0) sms[slot] = 148;
+    }
+    n = sms[slot];
+  }
+  const int64_t need = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock, cap = (int64_t)n * kPersistBlocksPerSM;
+  return (unsigned)(need < cap ? need : cap);
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace rvb
@@ -532,13 +638,28 @@ extern "C" int rvb_vat_perturb(const float* x, const float* d, float* x_adv, int
   RVB_REQUIRE(x && d && x_adv, "rvb_vat_perturb: null pointer");
   RVB_REQUIRE(n_rows >= 0 && row_len > 0, "rvb_vat_perturb: bad shape (%lld, %d)", (long long)n_rows, row_len);
   if (n_rows == 0) return RVB_OK;
-  const unsigned grid = (unsigned)((n_rows + kRowsPerBlock - 1) / kRowsPerBlock);
+  const unsigned grid = persistent_grid(n_rows);
   return dispatch_npl(row_len, [&](auto npl) {
     vat_perturb_kernel<decltype(npl)::value><<<grid, kRowsPerBlock * kWarp, 0, (cudaStream_t)stream>>>(
         x, d, x_adv, n_rows, row_len, xi, do_clamp);
     count_launch();
     return check_launch("vat_perturb_kernel");
   });
+}
+
+extern "C" int rvb_randn_like(float* out, int64_t n, uint64_t seed, uint64_t offset, uint32_t aten_threads,
+                              uint64_t increment, uint64_t* dev_state, rvb_stream_t stream) {
+  RVB_REQUIRE(out, "rvb_randn_like: null pointer");
+  RVB_REQUIRE(n >= 0, "rvb_randn_like: negative size");
+  RVB_REQUIRE(aten_threads > 0 && aten_threads % 256 == 0, "rvb_randn_like: aten_threads must be 256 * grid");
+  RVB_REQUIRE((offset & 3) == 0 && (increment & 3) == 0, "rvb_randn_like: Philox offsets are multiples of 4");
+  if (n == 0) return RVB_OK;
+  DrawArgs a;
+  a.seed = seed; a.offset = offset; a.dev_state = reinterpret_cast<unsigned long long*>(dev_state);
+  a.increment = increment; a.tt = aten_threads;
+  randn_like_kernel<4><<<aten_threads / 256, 256, 0, (cudaStream_t)stream>>>(out, n, a);
+  count_launch();
+  return check_launch("randn_like_kernel");
 }
 
 extern "C" int rvb_vat_perturb_draw(const float* x, float* d_out, float* x_adv, int64_t n_rows, int row_len, float xi,
@@ -574,7 +695,7 @@ static int launch_vat_finalize(const char* who, const float* g, const float* d, 
   return dispatch_npl(row_len, [&](auto npl) {
     constexpr int N = decltype(npl)::value;
     if (g)
-      vat_finalize_kernel<N><<<grid, kRowsPerBlock * kWarp, 0, (cudaStream_t)stream>>>(
+      vat_finalize_kernel<N><<<persistent_grid(n_rows), kRowsPerBlock * kWarp, 0, (cudaStream_t)stream>>>(
           g, d, x, r_adv, x_adv, d_hat, n_rows, row_len, xi, eps, scale, do_clamp, status_flag, dhat_abs_mean, workspace);
     else
       vat_direct_kernel<N><<<grid, kRowsPerBlock * kWarp, 0, (cudaStream_t)stream>>>(

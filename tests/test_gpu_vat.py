@@ -488,6 +488,8 @@ def test_in_kernel_direction_draw_is_torch_randn_like(R, dev, shape, warm):
     VAT._perturb_draw(x, x_adv, d, n_rows, row_len, 0.1, True)
     assert gen.get_offset() == after
     assert torch.equal(d, d_ref)
+    gen.set_state(state)
+    assert torch.equal(VAT.randn_like(x), d_ref) and gen.get_offset() == after      # the stand-alone kernel
     want = torch.empty_like(x)
     R._lib.call("rvb_vat_perturb", x.data_ptr(), d_ref.data_ptr(), want.data_ptr(), n_rows, row_len, 0.1, 1)
     assert torch.equal(x_adv, want)
@@ -507,11 +509,12 @@ def test_module_with_fused_draw_equals_module_with_aten_draw(R, dev, monkeypatch
     vat = R.VAT.UNet_VAT(0.1, 2.0, 1, False)
     torch.manual_seed(8)
     a = vat(m, x)
-    monkeypatch.setenv("RVB_NO_FUSED_DRAW", "1")
-    torch.manual_seed(8)
-    b = vat(m, x)
-    monkeypatch.delenv("RVB_NO_FUSED_DRAW")
-    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and float(a[0]) == float(b[0])
+    for mode in ("aten", "fused"):
+        monkeypatch.setenv("RVB_DRAW", mode)
+        torch.manual_seed(8)
+        b = vat(m, x)
+        assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and float(a[0]) == float(b[0]), mode
+    monkeypatch.delenv("RVB_DRAW")
     sc = VAT.Scratch(dev)
     n_rows = x.numel() // 229
     outs = []
