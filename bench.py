@@ -515,6 +515,113 @@ def run_ours(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_transcribe(args, rank, local_rank, world):
+    """--workload transcribe (BASELINE config 5): one file of --file-seconds of synthetic 16 kHz
+    PCM16 through whole-file inference, sharded by TIME over the ranks: Mel front-end with the file-global min / max
+    (ONE NCCL MAX all-reduce of two keys per file, reconvat_b200.parallel.global_minmax_keys) and, with --model unet,
+    the reference's own UNet (oracle/_ref snapshot, patched by install(attention=True)) on overlapping 640-frame
+    windows (reconvat_b200.transcribe.transcribe_file).  The work per file is fixed: strong scaling.  Before timing,
+    the sharded front-end is compared bit for bit with the one-rank result."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/rvb_nccl.%h.%p.log")
+        dist.init_process_group("nccl", device_id=dev)
+    import reconvat_b200 as R
+    from reconvat_b200 import parallel, synth, transcribe
+    from reconvat_b200.pipeline import MEL_KW
+    parallel.bind_to_gpu_numa(local_rank)
+    seconds = args.file_seconds
+    L = int(seconds * 16000)
+    minute = synth.music_int16(16000 * 60, 77)
+    a16 = torch.from_numpy(np.tile(minute, -(-L // len(minute)))[:L].copy())
+    a16[L // 2:] //= 4
+    a16 = a16.pin_memory()
+    mel = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    n_frames = (L - 1 + 2048 - 2048) // 512 + 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity of the sharded front-end: all ranks' pieces == the one-rank image, bit for bit
+    piece, (f0, f1) = transcribe.whole_file_frontend(mel, a16, rank, world)
+    identical = None
+    if world > 1:
+        whole, _ = transcribe.whole_file_frontend(mel, a16, 0, 1)            # every rank can afford the whole file
+        identical = torch.tensor([int(torch.equal(piece, whole[:, :, f0:f1]))], device=dev)
+        dist.all_reduce(identical, op=dist.ReduceOp.MIN)
+        identical = bool(identical.item())
+        del whole
+    del piece
+    torch.cuda.empty_cache()
+
+    model = None
+    if args.model == "unet":
+        from oracle import reference_loader as RL
+        if RL.available():
+            ns = RL.load_patched(attention=True)
+            torch.manual_seed(0)
+            model = ns.self_attention_VAT.UNet((2, 2), (2, 2), log=True, reconstruction=True, mode="imagewise", spec="Mel",
+                                               XI=1e-6, eps=1.3).to(dev).eval()           # transcribe_files.py:63-64
+
+    def one_pass():
+        if model is None:
+            return transcribe.whole_file_frontend(mel, a16, rank, world)[0]
+        return transcribe.transcribe_file(model, a16, mel=mel, batch=args.batch, rank=rank, world_size=world)[0]["frame"]
+
+    for _ in range(max(1, args.warmup)):
+        out = one_pass()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        out = one_pass()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.summary()
+    assert torch.isfinite(out).all()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    ms_step = ms / args.steps
+    line = {
+        "metric": "audio-sec/s", "value": seconds / (ms_step * 1e-3), "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 (STFT: 3xFP16 split operands, f32 accumulate in TMEM)",
+        "data": "synthetic",
+        "config": {"workload": "transcribe: one %d s file (%d frames) per step, whole-file inference sharded by time over "
+                               "%d rank(s): %s" % (seconds, n_frames, world,
+                                                    "Mel front-end + the reference's UNet (random init, eval) on "
+                                                    "overlapping 640-frame windows, batch %d" % args.batch
+                                                    if model is not None else "Mel front-end (log-Mel, file-global min/max)"),
+                   "collective": "one MAX all-reduce of the two min/max keys per file (NCCL)" if world > 1 else "none",
+                   "input": "PCM int16 in pinned host memory; every rank copies its own slice (+ halo) per step"},
+        "sharded_equals_single_rank_bit_for_bit": identical,
+        "clocks": clocks,
+        "e2e": {"value": seconds / (ms_step * 1e-3), "unit": "audio-s/s",
+                "h2d_bytes_per_step": int(2 * (L / world)), "d2h_bytes_per_step": 0,
+                "api": "reconvat_b200.transcribe.%s" % ("transcribe_file" if model is not None else "whole_file_frontend")},
+        "gpu_launches": None,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -536,8 +643,12 @@ def main():
     ap.add_argument("--no-gpu-baselines", action="store_true",
                     help="skip the module-surface leg and the reference's eager GPU path")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
-    ap.add_argument("--model", default="injected", choices=["injected", "standin"],
-                    help="the black-box network the VAT loop calls (see make_model)")
+    ap.add_argument("--model", default="injected", choices=["injected", "standin", "unet"],
+                    help="the black-box network the VAT loop calls (see make_model); 'unet': the reference's UNet from the "
+                         "oracle/_ref snapshot (--workload transcribe only)")
+    ap.add_argument("--workload", default="step", choices=["step", "transcribe"],
+                    help="step: the Mel+VAT training step (BASELINE metric); transcribe: whole-file inference (config 5)")
+    ap.add_argument("--file-seconds", type=int, default=3600, help="--workload transcribe: length of the file")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -551,7 +662,13 @@ def main():
         raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "transcribe":
+        if args.steps == 200:
+            args.steps = 5
+        run_transcribe(args, rank, local_rank, world)
     else:
+        if args.model == "unet":
+            raise SystemExit("bench.py: --model unet belongs to --workload transcribe")
         run_ours(args, rank, local_rank, world)
 
 

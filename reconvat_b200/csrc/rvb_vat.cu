@@ -773,7 +773,11 @@ extern "C" int rvb_div_mean(int kind, const float* p, const float* y, int64_t n,
                             float* workspace, rvb_stream_t stream) {
   RVB_REQUIRE(p && y && loss && workspace, "rvb_div_mean: null pointer");
   RVB_REQUIRE(n > 0 && denom > 0, "rvb_div_mean: empty input (the reference returns NaN for an empty mean)");
-  unsigned grid = flat_grid(n, 8);                      // two float4 pairs per thread: enough warps to hide the logs
+  // one wave: at most two 256-thread blocks per SM, every thread looping over trips of four float4 pairs -- the last-
+  // block reduction then reads ~300 partials instead of ~900, and the grid has no tail
+  unsigned grid = flat_grid(n, 16);
+  const unsigned cap = 2 * persistent_grid(1ll << 40) / kPersistBlocksPerSM;
+  if (grid > cap) grid = cap;
   if (grid > (unsigned)kBceMaxBlocks) grid = kBceMaxBlocks;
   const int vec = aligned16(p) && aligned16(y);
   return dispatch_kind(kind, "rvb_div_mean", [&](auto k) {

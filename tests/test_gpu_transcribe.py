@@ -73,3 +73,48 @@ def test_padded_slice_matches_reflection_pad():
     assert np.array_equal(transcribe.padded_slice(a.numpy(), 5, 60, 8), want[5:60].numpy())
     with pytest.raises(AssertionError):
         transcribe.padded_slice(a[:5], 0, 21, 8)
+
+
+def test_chunked_batched_transcription_matches_the_whole_file_pass():
+    """f3 driver (transcribe_files.py:12-40): the reference's real ``UNet`` (random init, eval) on one file --
+    ``UNet.transcribe`` in one batch-1 piece vs ``transcribe_file``: overlapping 640-frame windows through the network
+    as a batch, interior frames stitched.  Then the same file over three emulated ranks (contiguous runs of windows,
+    min / max keys MAX-reduced): identical to the one-rank result bit for bit.  And the decoded notes agree."""
+    import refmodels as RM
+    from reconvat_b200 import synth, transcribe
+    _, pat = RM.namespaces()
+    dev = torch.device("cuda:0")
+    frames = 2100
+    L = frames * 512
+    a16 = np.concatenate([synth.music_int16(L // 2, 41), synth.white_int16(L - L // 2, 42) // 16])
+    audio = torch.from_numpy(synth.to_float(a16))
+    with RM.deterministic(), torch.no_grad():
+        m = RM.build(pat, "unet", dev, 1e-6, 1.3, seed=3).eval()
+        whole = m.transcribe({"audio": audio.to(dev)[None, :]})["frame"][0]            # (T, 88), one piece
+        pred, (f0, f1) = transcribe.transcribe_file(m, audio, batch=4)
+        assert (f0, f1) == (0, frames) and pred["frame"].shape == whole.shape == (frames, 88)
+        err = float((pred["frame"] - whole).abs().max())
+        assert err < 2e-5, err                                # halo 128 >= the network's receptive field
+        narrow = transcribe.transcribe_file(m, audio, halo=16, batch=4)[0]["frame"]
+        assert float((narrow - whole).abs().max()) > err      # ... and a halo that is too small shows
+        # PCM16 input takes the same path
+        pcm, _ = transcribe.transcribe_file(m, torch.from_numpy(a16), batch=4)
+        assert float((pcm["frame"] - whole).abs().max()) < 2e-5
+        # three ranks, emulated: pass 1 collects the keys, the reduction is a MAX
+        world, keys = 3, []
+        for r in range(world):
+            transcribe.transcribe_file(m, audio, batch=4, rank=r, world_size=world, network=lambda s: s.new_zeros(s.shape[0], s.shape[2], 88),
+                                       reduce_keys=lambda k: (keys.append(k.clone()), k)[1])
+        wide = torch.stack([k.to(torch.int64) & 0xFFFFFFFF for k in keys]).max(0).values
+        glob = torch.where(wide >= 2 ** 31, wide - 2 ** 32, wide).to(torch.int32)
+        parts, at = [], 0
+        for r in range(world):
+            p, (g0, g1) = transcribe.transcribe_file(m, audio, batch=4, rank=r, world_size=world, reduce_keys=lambda k: glob)
+            assert g0 == at
+            at = g1
+            parts.append(p["frame"])
+        assert at == frames and torch.equal(torch.cat(parts), pred["frame"])
+    from reconvat_b200 import decoding
+    n_whole = decoding.extract_notes_wo_velocity(whole, whole)
+    n_chunk = decoding.extract_notes_wo_velocity(pred["onset"], pred["frame"])
+    assert len(n_whole[0]) == len(n_chunk[0]) and np.array_equal(n_whole[1], n_chunk[1])

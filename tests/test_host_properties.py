@@ -281,3 +281,26 @@ def test_fold2_operand_availability_and_exactness(n_fft, window, win_length, exp
     assert np.abs((Ce + Co) - re[:, k]).max() < 1e-7 * scale and np.abs((Se + So) - im[:, k]).max() < 1e-7 * scale
     assert np.abs((Ce - Co) - re[:, half - k]).max() < 1e-7 * scale
     assert np.abs(-(Se - So) - im[:, half - k]).max() < 1e-7 * scale
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 30000), st.sampled_from([(640, 128), (640, 64), (320, 32), (1024, 256)]), st.integers(1, 9))
+def test_window_plan_tiles_the_file_and_shards_over_ranks(n_frames, seg_halo, world):
+    """transcribe.window_plan: kept ranges tile [0, T); every kept frame is at least `halo` away from a cut (file ends
+    excepted); window starts are multiples of 16; contiguous runs of windows per rank cover the file in order."""
+    segment, halo = seg_halo
+    plan = transcribe.window_plan(n_frames, segment, halo)
+    assert plan[0][2] == 0 and plan[-1][3] == n_frames
+    for a, b in zip(plan, plan[1:]):
+        assert a[3] == b[2]
+    for w0, w1, k0, k1 in plan:
+        assert w0 % 16 == 0 and 0 < w1 - w0 <= segment and w0 <= k0 < k1 <= w1
+        assert (w0 == 0 and k0 == 0) or k0 - w0 >= halo
+        assert (w1 == n_frames and k1 == n_frames) or w1 - k1 >= halo
+    at = 0
+    for r in range(world):
+        lo, hi = parallel.segment_shard(len(plan), r, world)
+        for w in plan[lo:hi]:
+            assert w[2] == at
+            at = w[3]
+    assert at == n_frames
