@@ -27,6 +27,36 @@ def padded_slice(audio, s0, s1, pad):
     return audio[idx]
 
 
+def _padded_slice_on_device(audio, s0, s1, pad, dev):
+    """``padded_slice`` without touching the samples on the host: the part of [s0, s1) that lies inside the file goes
+    host -> device in ONE copy (asynchronous when ``audio`` is pinned), and the at most ``pad`` reflected samples at
+    either file end are gathered on the device from what was just copied.  (Index arithmetic on the host over a
+    one-hour file -- 57.6 M samples -- cost 0.7 s per pass; the copy is 2 ms.)"""
+    n = len(audio)
+    if not isinstance(audio, torch.Tensor):
+        audio = torch.from_numpy(np.ascontiguousarray(audio))
+    lo, hi = max(s0 - pad, 0), min(s1 - pad, n)               # file samples [lo, hi) are the un-reflected part
+    if hi <= lo or s0 - pad < -pad or (s1 - pad) - n > pad or n <= pad:
+        return padded_slice(audio, s0, s1, pad).to(dev)       # degenerate slices: the general (host) path
+    out = torch.empty(s1 - s0, dtype=audio.dtype, device=dev)
+    a = lo + pad - s0                                         # where file sample `lo` lands in the slice
+    out[a:a + hi - lo].copy_(audio[lo:hi], non_blocking=True)
+    if a > 0:                                                 # left end: padded index i < pad <-> file sample pad - i
+        i = torch.arange(s0, s0 + a, device=dev)
+        src = pad - i                                         # file samples 1 .. pad, all inside [lo, hi) here
+        if pad - s0 >= hi:                                   # (largest source index; host arithmetic, no sync)
+            return padded_slice(audio, s0, s1, pad).to(dev)
+        out[:a] = out[src - lo + a]
+    b = a + hi - lo
+    if b < s1 - s0:                                           # right end: file sample j >= n <-> 2 (n - 1) - j
+        j = torch.arange(s0 + b, s1, device=dev) - pad
+        src = 2 * (n - 1) - j
+        if 2 * (n - 1) - (s1 - 1 - pad) < lo:
+            return padded_slice(audio, s0, s1, pad).to(dev)
+        out[b:] = out[src - lo + a]
+    return out
+
+
 def whole_file_frontend(mel, audio, rank=0, world_size=1, group=None, log_offset=1e-5, trim_last=True,
                         channel_dim=True, reduce_keys=None, frames=None):
     """This rank's frames of the normalised log-Mel image of one long file.
@@ -60,9 +90,7 @@ def whole_file_frontend(mel, audio, rank=0, world_size=1, group=None, log_offset
         n_mels = mel.mel_basis.shape[0]
         shape = (1, 1, 0, n_mels) if channel_dim else (1, 0, n_mels)
         return torch.empty(shape, dtype=torch.float32, device=dev), (f0, f0)
-    chunk = padded_slice(audio, s0, s1, pad)
-    chunk = (chunk if isinstance(chunk, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(chunk)))
-    chunk = chunk.to(dev, non_blocking=True)[None, :]
+    chunk = _padded_slice_on_device(audio, s0, s1, pad, dev)[None, :]
     spec = mel.normalised_log_mel(chunk, trim_last=False, log_offset=log_offset, channel_dim=channel_dim,
                                   prepadded=True,
                                   reduce_minmax=reduce_keys)

@@ -64,6 +64,20 @@ def test_one_hour_file_over_8_ranks_is_bit_identical():
     assert f == 112500
 
 
+def test_padded_slice_on_device_equals_the_host_version():
+    from reconvat_b200 import transcribe
+    dev = torch.device("cuda:0")
+    a = torch.randint(-32768, 32767, (5000,), dtype=torch.int16)
+    for pinned in (a, a.pin_memory()):
+        for s0, s1 in ((0, 5000 + 2 * 64), (0, 700), (10, 900), (64, 3000), (3000, 5000 + 2 * 64), (4000, 5100), (100, 5127)):
+            want = transcribe.padded_slice(pinned, s0, s1, 64)
+            got = transcribe._padded_slice_on_device(pinned, s0, s1, 64, dev)
+            torch.cuda.synchronize()
+            assert torch.equal(got.cpu(), want), (s0, s1)
+    f = torch.randn(300)
+    assert torch.equal(transcribe._padded_slice_on_device(f, 0, 300 + 16, 8, dev).cpu(), transcribe.padded_slice(f, 0, 316, 8))
+
+
 def test_padded_slice_matches_reflection_pad():
     from reconvat_b200 import transcribe
     a = torch.arange(50, dtype=torch.float32)
@@ -113,7 +127,9 @@ def test_chunked_batched_transcription_matches_the_whole_file_pass():
             assert g0 == at
             at = g1
             parts.append(p["frame"])
-        assert at == frames and torch.equal(torch.cat(parts), pred["frame"])
+        # (windows are independent, but cuDNN's choice of kernel depends on the batch a window runs in: the front-end
+        # pieces are bit-identical -- tested above --, the network's posteriors agree to rounding)
+        assert at == frames and float((torch.cat(parts) - pred["frame"]).abs().max()) < 1e-5
     from reconvat_b200 import decoding
     n_whole = decoding.extract_notes_wo_velocity(whole, whole)
     n_chunk = decoding.extract_notes_wo_velocity(pred["onset"], pred["frame"])
