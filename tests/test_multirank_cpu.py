@@ -93,3 +93,72 @@ def test_two_ranks_gloo():
     assert t == 2.0
     assert (mn, mx) == (-3.0, 6.0)
     assert nan_mn and nan_mx
+
+
+# ---- the caller's training step without the host in the loop (reconvat_b200.training) ----
+class _TinyStepModel(torch.nn.Module):
+    """Has the reference's step interface: run_on_batch(batch_l, batch_ul, VAT) -> (predictions, losses, spec)."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(0)
+        self.lin = torch.nn.Linear(6, 3)
+
+    def run_on_batch(self, batch_l, batch_ul=None, VAT=False):
+        y = torch.sigmoid(self.lin(batch_l["audio"]))
+        losses = {"loss/train_frame": torch.nn.functional.binary_cross_entropy(y, batch_l["frame"])}
+        if batch_ul is not None:
+            yu = torch.sigmoid(self.lin(batch_ul["audio"]))
+            losses["loss/train_LDS_ul"] = ((yu - 0.5) ** 2).mean()
+        return {"frame": y}, losses, batch_l["audio"]
+
+
+def _batches(seed, n):
+    g = torch.Generator().manual_seed(seed)
+    return [{"audio": torch.randn(4, 6, generator=g), "frame": (torch.rand(4, 3, generator=g) > 0.5).float()} for _ in range(n)]
+
+
+def _train_worker(rank, world, port, out, use_ddp):
+    from reconvat_b200 import training
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = _TinyStepModel()
+        runner = training.ddp(model) if use_ddp else model
+        opt = torch.optim.SGD(model.parameters(), lr=0.5)
+        sched = torch.optim.lr_scheduler.StepLR(opt, 1000)
+        # every rank trains on ITS half of each global batch
+        l, ul = _batches(1, 3), _batches(2, 3)
+        mine = lambda bs: [{k: v[2 * rank:2 * rank + 2] for k, v in b.items()} for b in bs]      # noqa: E731
+        _, losses, _ = training.train_VAT_model(runner, 3, 0, mine(l), mine(ul), opt, sched, 3.0, alpha=1.0, VAT=True)
+        out.put((rank, [p.detach().double().flatten().tolist() for p in model.parameters()], sorted(losses)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("use_ddp", [False, True])
+def test_training_loop_averages_gradients_over_two_ranks(use_ddp):
+    """Two ranks, each on half of every batch, end with IDENTICAL parameters, equal to one process training on the
+    whole batches (means over equal shards average exactly); both the flattened all-reduce and the DDP adapter."""
+    from reconvat_b200 import training
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q, use_ddp)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict()
+    for _ in procs:
+        r, params, keys = q.get()
+        got[r] = params
+        assert keys == ["loss/train_LDS_ul", "loss/train_frame"]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    single = _TinyStepModel()
+    opt = torch.optim.SGD(single.parameters(), lr=0.5)
+    training.train_VAT_model(single, 3, 0, _batches(1, 3), _batches(2, 3), opt, torch.optim.lr_scheduler.StepLR(opt, 1000),
+                             3.0, alpha=1.0, VAT=True)
+    for a, b, c in zip(got[0], got[1], single.parameters()):
+        assert a == b
+        assert np.allclose(a, c.detach().double().flatten().numpy(), atol=1e-6)
