@@ -77,15 +77,21 @@ def _rebind_everywhere(name, new, defining_module):
     return done
 
 
-def patch_reference(attention=False, decoding=False):
+def patch_reference(attention=False, decoding=False, training=False):
     """Rebind VAT classes, Normalization and the Spectrogram module in every imported reference module.
     ``attention=True`` also rebinds ``MutliHeadAttention1D`` (the U-Net's sequence model) to the
     fused local-window attention: same parameters and outputs, no (B, L, C, W) unfolded tensors.
     ``decoding=True`` rebinds ``extract_notes_wo_velocity`` / ``notes_to_frames`` (model/decoding.py) wherever the
     reference's functions are held; they then expect the posteriors on the GPU, which is where ``UNet.transcribe``
     leaves them.
+    ``training=True`` rebinds ``train_VAT_model`` (model/helper_functions.py:570-615) to ``reconvat_b200.training``'s:
+    same arguments and arithmetic, no per-iteration host synchronisation, gradients averaged over the ranks when
+    ``torch.distributed`` is initialised.
     Returns the list of (module, name) pairs that were rebound."""
     done = []
+    if training:
+        from . import training as _tr
+        done += _rebind_everywhere("train_VAT_model", _tr.train_VAT_model, "model.helper_functions")
     if decoding:
         from . import decoding as _dec
         done += _rebind_everywhere("extract_notes_wo_velocity", _dec.extract_notes_wo_velocity, "model.decoding")
@@ -123,6 +129,6 @@ def patch_reference(attention=False, decoding=False):
     return done
 
 
-def install(attention=False, decoding=False):
+def install(attention=False, decoding=False, training=False):
     install_nnaudio()
-    return patch_reference(attention=attention, decoding=decoding)
+    return patch_reference(attention=attention, decoding=decoding, training=training)

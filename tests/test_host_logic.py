@@ -319,6 +319,21 @@ def test_install_opt_in_attention_and_decoding(monkeypatch):
         assert fake[m].extract_notes_wo_velocity is D.extract_notes_wo_velocity
         assert fake[m].notes_to_frames is D.notes_to_frames
     assert ("some_script", "extract_notes_wo_velocity") in done
+    # training=True: the step driver (model/helper_functions.py:570), also where a script star-imported it
+    import inspect
+    import reconvat_b200.training as T
+    ref_train = (lambda *a, **k: None)
+    fake["model.helper_functions"] = types.ModuleType("model.helper_functions")
+    monkeypatch.setitem(sys.modules, "model.helper_functions", fake["model.helper_functions"])
+    fake["model.helper_functions"].train_VAT_model = ref_train
+    fake["some_script"].train_VAT_model = ref_train
+    assert R.install() is not None and fake["some_script"].train_VAT_model is ref_train
+    R.install(training=True)
+    assert fake["model.helper_functions"].train_VAT_model is T.train_VAT_model
+    assert fake["some_script"].train_VAT_model is T.train_VAT_model
+    assert list(inspect.signature(T.train_VAT_model).parameters)[:11] == [
+        "model", "iteration", "ep", "l_loader", "ul_loader", "optimizer", "scheduler", "clip_gradient_norm", "alpha",
+        "VAT", "VAT_start"]
 
 
 def test_vat_constructor_signatures_mirror_the_reference():
