@@ -407,6 +407,40 @@ def run_ours(args, rank, local_rank, world):
     e2e_value = world * B * SEG_SECONDS / (e2e_ms * 1e-3)
     assert torch.isfinite(results).all(), "non-finite VAT loss in the e2e run"
 
+    # ---------------- the reference's own data path: corpus resident on the device (model/dataset.py:19-62) --------
+    # PianoRollAudioDataset pre-loads every recording to `device` as int16 and cuts random 327 680-sample crops there
+    # (:40-55); a step never crosses PCIe.  Same here: B random crops are gathered from a device-resident corpus into
+    # the captured input buffer, the graph is replayed, two 4-byte results go back to the host.
+    dev_corpus = None
+    if not args.no_graphs:
+        corpus = torch.cat([a.reshape(-1) for a in dev_audio[:2]])                    # 64 segments' worth of samples
+        starts = [torch.randint(0, corpus.numel() - SEG_SAMPLES, (B,), generator=torch.Generator().manual_seed(i)).to(dev)
+                  for i in range(8)]
+        windows = corpus.unfold(0, SEG_SAMPLES, 1)                                    # every crop, as a view
+        res2 = torch.zeros((args.steps, 2), dtype=torch.float32).pin_memory()
+
+        def corpus_step(i):
+            slot = i % 2
+            buf = step._graphs[slot][1]
+            torch.index_select(windows, 0, starts[i % 8], out=buf)                    # the random crops (device gather)
+            out = step.replay(slot)
+            res2[i, 0].copy_(out[0].detach(), non_blocking=True)
+            res2[i, 1].copy_(out[1], non_blocking=True)
+        for i in range(3):
+            corpus_step(i)
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            corpus_step(i)
+        ev1.record()
+        barrier()
+        dc_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+        dev_corpus = {"value": world * B * SEG_SECONDS / (dc_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": dc_ms,
+                      "what": "as the reference feeds its step (model/dataset.py:19-62): int16 corpus resident on the "
+                              "device, B random 327680-sample crops gathered per step, graph replay, (vat_loss, r_norm) "
+                              "read back -- no host->device copy of audio"}
+        del corpus
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -505,6 +539,7 @@ def run_ours(args, rank, local_rank, world):
         "kernel_timing": "each entry point re-launched %d times back to back between one CUDA-event pair, rotating over "
                          "%d recorded working sets (> L2); the contraction's entry point includes the memset of "
                          "its Mel accumulator (38 MB for the two planes of the twice-folded kernel)" % (reps, n_rot),
+        "e2e_device_corpus": dev_corpus,
         "sustained": sustained,
         "module_surface": surface,
         "gpu_eager_baseline": gpu_eager,
