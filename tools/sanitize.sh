@@ -10,8 +10,9 @@ for tool in memcheck racecheck synccheck initcheck; do
   out=gpurun_out/sanitizer_${tool}.txt
   extra=""
   [ "$tool" = memcheck ] && extra="--leak-check no"
-  [ "$tool" = racecheck ] && extra="--racecheck-report all --print-limit 1000000"
-  timeout 1500 compute-sanitizer --tool $tool --error-exitcode 7 --print-limit 40 $extra \
+  limit=40
+  [ "$tool" = racecheck ] && extra="--racecheck-report all" && limit=1000000
+  timeout 1500 compute-sanitizer --tool $tool --error-exitcode 7 --print-limit $limit $extra \
       python tools/sanitize_target.py > $out 2>&1
   code=$?
   echo "== $tool exit $code" | tee -a $out
