@@ -228,6 +228,7 @@ stft_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     }
     fence_barrier_init();
   }
+  __syncthreads();                                     // mbarrier words initialised before the allocator (another warp) writes beside them
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
                  "r"((uint32_t)TMEM_COLS)
@@ -546,6 +547,7 @@ stft_gemm_fold_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     }
     fence_barrier_init();
   }
+  __syncthreads();                                     // mbarrier words initialised before the allocator (another warp) writes beside them
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
                  "r"((uint32_t)TMEM_COLS)
@@ -768,6 +770,7 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
     }
     fence_barrier_init();
   }
+  __syncthreads();                                     // mbarrier words initialised before the allocator (another warp) writes beside them
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
                  "r"((uint32_t)TMEM_COLS)
@@ -1035,6 +1038,7 @@ stft_gemm_fold2_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
     }
     fence_barrier_init();
   }
+  __syncthreads();                                     // mbarrier words initialised before the allocator (another warp) writes beside them
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
                  "r"((uint32_t)TMEM_COLS)
@@ -1253,6 +1257,7 @@ stft_gemm_fold2c_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const 
     }
     fence_barrier_init();
   }
+  __syncthreads();                                     // mbarrier words initialised before the allocator (another warp) writes beside them
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
                  "r"((uint32_t)TMEM_COLS)

@@ -33,6 +33,10 @@ def main():
     s_f = mel.normalised_log_mel(a_f)
     s_i = mel.normalised_log_mel(a_i)
     assert torch.equal(s_f, s_i), "PCM16 and float input differ"
+    os.environ["RVB_FUSED_FOLD"] = "1"                      # K0x + K1x: the fold done inside the contraction
+    s_x = mel.normalised_log_mel(a_i)
+    os.environ.pop("RVB_FUSED_FOLD")
+    assert float((s_x - s_i).abs().max()) < 1e-5, "fused-fold path differs"
     assert bool(torch.isfinite(s_f).all()) and float(s_f.min()) == 0.0 and float(s_f.max()) == 1.0
     # module surface (forward -> log -> Normalization) = the two-pass kernels
     spec = torch.log(mel(a_f[:, :-1]) + 1e-5)
