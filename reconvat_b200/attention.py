@@ -5,17 +5,21 @@ attention with a relative position term, the sequence model of the ReconVAT U-Ne
 reference unfolds k and v to (B, L, C, W), 73 MB per 20 s segment each at C = 916, W = 31, and autograd keeps both.
 
 Same constructor, parameters (``W_q``, ``W_k``, ``W_v``, ``rel`` -> state_dict compatible) and return values
-``(out (B, L, C), attention (B, L, groups, W))``.  The three projections stay ``nn.Linear`` (cuBLAS); everything after
-them is one kernel forward and two backward (librvb.so, rvb_attention.cu); the relative-position terms (q . rel,
-dE . rel^T, d rel) do not involve k and are batched GEMMs (torch / cuBLAS).
+``(out (B, L, C), attention (B, L, groups, W))``.  The three projections keep their ``nn.Linear`` parameters but run as
+3xTF32 tcgen05 contractions (``reconvat_b200.linear.projections``: PyTorch's fp32 SGEMMs were 61 % of the layer;
+``RVB_ATTN_PROJ=torch`` restores ``nn.Linear``); everything after them is one kernel forward and two backward
+(librvb.so, rvb_attention.cu); the relative-position terms (q . rel, dE . rel^T, d rel) do not involve k and are small
+batched GEMMs (torch / cuBLAS).
 Scope cuts, raising: ``stride != 1`` and ``bias=True`` (no reference model uses them; with a bias the zero padding
 rows would become the bias vector).
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.init as init
 
-from . import _lib
+from . import _lib, linear
 
 
 class _LocalAttention(torch.autograd.Function):
@@ -86,7 +90,10 @@ class MutliHeadAttention1D(nn.Module):
         self.reset_parameters()
 
     def forward(self, x):
-        q, k, v = self.W_q(x), self.W_k(x), self.W_v(x)                  # zero padding rows project to zero (no bias)
+        if os.environ.get("RVB_ATTN_PROJ", "tc") == "torch":
+            q, k, v = self.W_q(x), self.W_k(x), self.W_v(x)              # zero padding rows project to zero (no bias)
+        else:
+            q, k, v = linear.projections(x, [self.W_q.weight, self.W_k.weight, self.W_v.weight])
         return _LocalAttention.apply(q, k, v, self.rel[0] if self.position else None, self.groups, self.kernel_size)
 
     def reset_parameters(self):

@@ -244,3 +244,74 @@ extern "C" int rvb_local_attn_bwd_kv(const float* q, const float* dout, const fl
   count_launch();
   return check_launch("local_attn_bwd_kv_kernel");
 }
+
+
+// ---------------------------------------------------------------- operand planes of rvb_gemm_nt_tf32x3
+// x [rows][cols] (row stride ld)  ->  tf32 hi / lo planes, hi = tf32(x), lo = tf32(x - hi):
+//   transpose == 0:  planes[r][col0 + c] = split(x[r][c])      plane row stride out_ld; columns [col0 + cols, out_ld) of the
+//                    LAST block written by a call are the caller's to zero (rvb_split_tf32 zeroes [col0 + cols, zero_to))
+//   transpose == 1:  planes[c][row0 + r] = split(x[r][c])      (the contraction runs over x's ROWS: dW = dY^T X)
+namespace rvb {
+
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ld, float* __restrict__ hi,
+                  float* __restrict__ lo, int64_t out_ld, int col0, int zero_to) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= zero_to - col0) return;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    const float v = (c < cols) ? __ldg(x + r * ld + c) : 0.f;
+    const float h = to_tf32(v);
+    hi[r * out_ld + col0 + c] = h;
+    lo[r * out_ld + col0 + c] = to_tf32(v - h);
+  }
+}
+
+// 32 x 32 tiles through shared memory: coalesced reads along x's columns, coalesced writes along x's rows
+__global__ void __launch_bounds__(256)
+split_tf32_transpose_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ld, float* __restrict__ hi,
+                            float* __restrict__ lo, int64_t out_ld, int64_t row0, int64_t zero_to) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32;
+  const int c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int64_t r = r0 + ty + j;
+    const int c = c0 + tx;
+    tile[ty + j][tx] = (r < rows && c < cols) ? __ldg(x + r * ld + c) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int c = c0 + ty + j;                                      // output row
+    const int64_t r = r0 + tx;                                      // output column (before row0)
+    if (c < cols && row0 + r < zero_to) {
+      const float v = tile[tx][ty + j];                             // zero past `rows`
+      const float h = to_tf32(v);
+      hi[(int64_t)c * out_ld + row0 + r] = h;
+      lo[(int64_t)c * out_ld + row0 + r] = to_tf32(v - h);
+    }
+  }
+}
+
+}  // namespace rvb
+
+extern "C" int rvb_split_tf32(const float* x, int64_t rows, int cols, int64_t ld, int transpose, float* hi, float* lo,
+                              int64_t out_ld, int64_t offset, int64_t zero_to, rvb_stream_t stream) {
+  RVB_REQUIRE(x && hi && lo, "rvb_split_tf32: null pointer");
+  RVB_REQUIRE(rows > 0 && cols > 0 && ld >= cols && offset >= 0, "rvb_split_tf32: bad shape");
+  const int64_t extent = transpose ? rows : cols;                   // what runs along the plane's columns
+  RVB_REQUIRE(zero_to >= offset + extent && zero_to <= out_ld, "rvb_split_tf32: need offset + extent <= zero_to <= out_ld");
+  if (!transpose) {
+    RVB_REQUIRE(zero_to - offset < (1ll << 31), "rvb_split_tf32: too wide");
+    dim3 grid((unsigned)((zero_to - offset + 255) / 256), (unsigned)(rows < 65535 ? rows : 65535));
+    rvb::split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, hi, lo, out_ld, (int)offset, (int)zero_to);
+  } else {
+    const int64_t r_tiles = (zero_to - offset + 31) / 32;
+    RVB_REQUIRE(r_tiles <= 65535, "rvb_split_tf32: too many rows for one launch");
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)r_tiles);
+    rvb::split_tf32_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, hi, lo, out_ld, offset, zero_to);
+  }
+  rvb::count_launch();
+  return rvb::check_launch("split_tf32_kernel");
+}

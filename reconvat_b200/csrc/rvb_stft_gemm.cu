@@ -45,7 +45,10 @@ constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 192;
 constexpr int EPI_WARP0 = 2;
 
+constexpr int kEpiRawGemm = 0x100;                // internal epilogue code: store the accumulator (plain GEMM)
+
 struct GemmParams {
+  int64_t ldc;                                    // kEpiRawGemm: row stride of C
   int n_seg, rows_per_seg, hop, n_frames, n_fft;
   int tiles_per_seg, m_tiles, n_tiles;
   int epilogue, n_out_bins, n_store_bins;
@@ -314,6 +317,30 @@ stft_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       mbar_wait(bar_tmem_full(acc), acc_phase, p.dbg_status, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+      if (p.epilogue == kEpiRawGemm) {
+        // plain GEMM (rvb_gemm_nt_tf32x3): C[t][n_tile * 256 + j] = accumulator column j; n_out_bins = N, power = ldc
+        float* crow = p.out0 + (int64_t)t * p.ldc + n_tile * BLOCK_N;
+        const bool vec = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out0) & 15u) == 0;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int n0 = n_tile * BLOCK_N + c * 32;
+          if (t_ok && n0 < p.n_out_bins) {
+            if (vec && n0 + 32 <= p.n_out_bins) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                reinterpret_cast<float4*>(crow + c * 32)[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                                          __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n0 + i < p.n_out_bins) crow[c * 32 + i] = __uint_as_float(v[i]);
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t re[32], im[32];
@@ -323,6 +350,7 @@ stft_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         const int k0 = n_tile * 128 + c * 32;
         if (t_ok)
           stft_store_chunk(p.epilogue, p.power, re, im, 1.f, 0.f, p.out0, b, k0, t, p.n_out_bins, p.n_store_bins, p.n_frames);
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -1782,6 +1810,24 @@ static int num_sms() {
 
 using namespace rvb;
 
+static int launch_stft_gemm(const CUtensorMap& tm_a_hi, const CUtensorMap& tm_a_lo, const CUtensorMap& tm_b_hi,
+                            const CUtensorMap& tm_b_lo, const GemmParams& p, rvb_stream_t stream) {
+  {
+    static bool attr_set[kMaxDevices] = {};
+    const int slot = device_slot();
+    std::lock_guard<std::mutex> g(attr_mutex());
+    if (!attr_set[slot]) {
+      RVB_CUDA(cudaFuncSetAttribute(stft_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_set[slot] = true;
+    }
+  }
+  const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
+  const int grid = (int)(n_units < num_sms() ? n_units : num_sms());
+  stft_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p);
+  count_launch();
+  return check_launch("stft_gemm_kernel");
+}
+
 extern "C" int rvb_stft_gemm(const float* sig_hi, const float* sig_lo, int n_seg, int rows_per_seg, int hop,
                              int n_frames, const float* basis_hi, const float* basis_lo, int n_basis_rows, int n_fft,
                              int epilogue, float power, float* out0, int n_out_bins, rvb_stream_t stream) {
@@ -1814,22 +1860,36 @@ extern "C" int rvb_stft_gemm(const float* sig_hi, const float* sig_lo, int n_seg
   p.n_tiles = n_basis_rows / BLOCK_N;
   p.epilogue = epilogue; p.n_out_bins = n_out_bins;
   p.n_store_bins = n_out_bins < n_basis_rows / 2 ? n_out_bins : n_basis_rows / 2;
-  p.power = power; p.out0 = out0; p.dbg_status = nullptr;
+  p.power = power; p.out0 = out0; p.dbg_status = nullptr; p.ldc = 0;
+  return launch_stft_gemm(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p, stream);
+}
 
-  {
-    static bool attr_set[kMaxDevices] = {};
-    const int slot = device_slot();
-    std::lock_guard<std::mutex> g(attr_mutex());
-    if (!attr_set[slot]) {
-      RVB_CUDA(cudaFuncSetAttribute(stft_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      attr_set[slot] = true;
-    }
-  }
-  const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
-  const int grid = (int)(n_units < num_sms() ? n_units : num_sms());
-  stft_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p);
-  count_launch();
-  return check_launch("stft_gemm_kernel");
+// C[M][N] = A[M][K] . B[N][K]^T in 3xTF32 (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM): the dense projections of
+// the caller's sequence model (nn.Linear of MutliHeadAttention1D, model/self_attention_VAT.py:54-56, 70-71), which
+// PyTorch runs as SIMT SGEMMs (TF32 is off by default for matmul).  Operands: tf32 hi / lo planes [rows][k_pad] from
+// rvb_split_tf32, k_pad a multiple of 32, zero beyond K.  Rows past M / N are zero-filled by the TMA and never stored.
+extern "C" int rvb_gemm_nt_tf32x3(const float* a_hi, const float* a_lo, int64_t m, const float* b_hi, const float* b_lo,
+                                  int n, int k_pad, float* c, int64_t ldc, rvb_stream_t stream) {
+  RVB_REQUIRE(a_hi && a_lo && b_hi && b_lo && c, "rvb_gemm_nt_tf32x3: null pointer");
+  RVB_REQUIRE(m > 0 && n > 0 && k_pad >= BLOCK_K && k_pad % BLOCK_K == 0 && ldc >= n,
+              "rvb_gemm_nt_tf32x3: bad shape (m=%lld n=%d k_pad=%d ldc=%lld)", (long long)m, n, k_pad, (long long)ldc);
+  RVB_REQUIRE(m < (1ll << 31) - BLOCK_M, "rvb_gemm_nt_tf32x3: too many rows");
+  for (const void* ptr : {(const void*)a_hi, (const void*)a_lo, (const void*)b_hi, (const void*)b_lo})
+    RVB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 127u) == 0, "rvb_gemm_nt_tf32x3: operands must be 128-byte aligned");
+  CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+  int rc;
+  if ((rc = make_map_2d(&tm_a_hi, a_hi, k_pad, (uint64_t)m, BLOCK_K, BLOCK_M)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_a_lo, a_lo, k_pad, (uint64_t)m, BLOCK_K, BLOCK_M)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_b_hi, b_hi, k_pad, (uint64_t)n, BLOCK_K, BLOCK_N)) != RVB_OK) return rc;
+  if ((rc = make_map_2d(&tm_b_lo, b_lo, k_pad, (uint64_t)n, BLOCK_K, BLOCK_N)) != RVB_OK) return rc;
+  GemmParams p;
+  p.n_seg = 1; p.rows_per_seg = (int)m; p.hop = k_pad; p.n_frames = (int)m; p.n_fft = k_pad;
+  p.tiles_per_seg = (int)((m + BLOCK_M - 1) / BLOCK_M);
+  p.m_tiles = p.tiles_per_seg;
+  p.n_tiles = (n + BLOCK_N - 1) / BLOCK_N;
+  p.epilogue = kEpiRawGemm; p.n_out_bins = n; p.n_store_bins = n;
+  p.power = 0.f; p.out0 = c; p.dbg_status = nullptr; p.ldc = ldc;
+  return launch_stft_gemm(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p, stream);
 }
 
 struct MelArgs {

@@ -113,3 +113,61 @@ def test_attention_rejects_what_it_does_not_implement():
         A.MutliHeadAttention1D(8, 16, 4)                      # even window, like the reference
     with pytest.raises(_lib.RvbError):
         A.MutliHeadAttention1D(8, 16, 3)(torch.zeros(1, 5, 8))   # CPU tensor: no fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,k,n", [(640, 229, 916), (300, 64, 40), (20480, 229, 916), (129, 33, 257)])
+def test_tensor_core_projections_match_float64(m, k, n):
+    """reconvat_b200.linear.projections (3xTF32 tcgen05 GEMM + tf32 split / transpose kernels): forward and the
+    autograd backward (dx, dW) against float64 products; the error of a 3xTF32 contraction is ~2^-21 of the operand
+    scale, like fp32 SGEMM's own accumulation rounding.  Shapes: one segment, ragged everything, the B = 32 layer, and
+    sizes one past the tile edges."""
+    from reconvat_b200 import linear
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(m + k + n)
+    x = torch.randn(m, k, generator=g)
+    ws = [torch.randn(n, k, generator=g) / np.sqrt(k), torch.randn(n // 2 + 1, k, generator=g) / np.sqrt(k)]
+    gos = [torch.randn(m, w.shape[0], generator=g) for w in ws]
+    xd = x.to(dev).requires_grad_(True)
+    wd = [w.to(dev).requires_grad_(True) for w in ws]
+    ys = linear.projections(xd, wd)
+    torch.autograd.backward(ys, [go.to(dev) for go in gos])
+    x64 = x.double().requires_grad_(True)
+    w64 = [w.double().requires_grad_(True) for w in ws]
+    y64 = [x64 @ w.t() for w in w64]
+    torch.autograd.backward(y64, [go.double() for go in gos])
+    rel = lambda a, b: float((a.double().cpu() - b).abs().max() / b.abs().max())
+    for y, yr in zip(ys, y64):
+        assert y.shape == yr.shape and rel(y.detach(), yr.detach()) < 2e-6
+    assert rel(xd.grad, x64.grad) < 2e-6
+    for a, b in zip(wd, w64):
+        assert rel(a.grad, b.grad) < 2e-6
+    # the planes: hi is a tf32 number, hi + lo reconstructs x to 2^-21, padding columns are zero
+    hi, lo = linear._split(xd.detach())
+    assert hi.shape == (m, (k + 31) // 32 * 32) and (hi.view(torch.int32) & 0x1FFF).abs().max() == 0
+    assert float((hi[:, :k] + lo[:, :k] - xd.detach()).abs().max()) <= 2.0 ** -20 * float(x.abs().max())
+    assert float(hi[:, k:].abs().max() if hi.shape[1] > k else 0) == 0
+    ht, lt = linear._split(xd.detach(), transpose=True)
+    assert ht.shape[0] == k and torch.equal(ht[:, :m], hi[:, :k].t()) and torch.equal(lt[:, :m], lo[:, :k].t())
+
+
+@pytest.mark.gpu
+def test_attention_projection_paths_agree(monkeypatch):
+    """MutliHeadAttention1D with the tensor-core projections vs with nn.Linear: same outputs and gradients to fp32
+    rounding; a 3-D (B, L, C) input and the zero rows of the padding project to zero either way."""
+    import reconvat_b200.attention as A
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    m = A.MutliHeadAttention1D(229, 916, 31, position=True, groups=4).to(dev)
+    x = torch.randn(2, 70, 229, device=dev)
+    go = torch.randn(2, 70, 916, device=dev)
+    res = {}
+    for mode in ("tc", "torch"):
+        monkeypatch.setenv("RVB_ATTN_PROJ", mode)
+        m.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        out, att = m(xi)
+        out.backward(go)
+        res[mode] = (out.detach(), att, xi.grad, m.W_q.weight.grad.clone(), m.W_v.weight.grad.clone(), m.rel.grad.clone())
+    for a, b in zip(res["tc"], res["torch"]):
+        assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
