@@ -402,12 +402,14 @@ int rvb_vat_finalize_binwise(const float* g, const float* d, const float* x, flo
  *   rvb_split_tf32: x [rows][cols] (row stride ld) -> tf32 hi / lo planes.  transpose == 0: planes[r][offset + c];
  *     transpose == 1: planes[c][offset + r] (for contractions over x's rows: dW = dY^T X).  Plane row stride out_ld; the
  *     columns [offset + extent, zero_to) are zero-filled (pad the contraction length to a multiple of 32).
- *   rvb_gemm_nt_tf32x3: C[m][n] = A[m][k] . B[n][k]^T from such planes ([rows][k_pad], 128-byte aligned).
+ *   rvb_gemm_nt_tf32x3: C[m][n] = A[m][k] . B[n][k]^T from such planes ([rows][k_pad], 128-byte aligned).  k_split > 1
+ *     cuts the contraction into k_split slices of whole 32-element blocks (none empty); slice s writes its partial
+ *     product to c + s * split_stride and the caller adds the partials (few output tiles, long contraction: dW).
  */
 int rvb_split_tf32(const float* x, int64_t rows, int cols, int64_t ld, int transpose, float* hi, float* lo, int64_t out_ld,
                    int64_t offset, int64_t zero_to, rvb_stream_t stream);
 int rvb_gemm_nt_tf32x3(const float* a_hi, const float* a_lo, int64_t m, const float* b_hi, const float* b_lo, int n,
-                       int k_pad, float* c, int64_t ldc, rvb_stream_t stream);
+                       int k_pad, float* c, int64_t ldc, int k_split, int64_t split_stride, rvb_stream_t stream);
 /*
  * A1-A3  MutliHeadAttention1D.forward (model/self_attention_VAT.py:22-91; same class in model/UNet_onset.py:22,
  * model/self_attention.py:6) after the three nn.Linear projections, and its backward:

@@ -54,7 +54,7 @@ SIGNATURES = {
     "rvb_vat_perturb_binwise": [_c_p, _c_p, _c_p, _i64, _f32, _i32, _c_p],
     "rvb_vat_finalize_binwise": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i64, _f32, _f32, _f32, _i32, _c_p, _c_p],
     "rvb_split_tf32": [_c_p, _i64, _i32, _i64, _i32, _c_p, _c_p, _i64, _i64, _i64, _c_p],
-    "rvb_gemm_nt_tf32x3": [_c_p, _c_p, _i64, _c_p, _c_p, _i32, _i32, _c_p, _i64, _c_p],
+    "rvb_gemm_nt_tf32x3": [_c_p, _c_p, _i64, _c_p, _c_p, _i32, _i32, _c_p, _i64, _i32, _i64, _c_p],
     "rvb_local_attn_fwd": [_c_p, _c_p, _c_p, _c_p, _i32, _i32, _i32, _i32, _i32, _c_p, _c_p, _c_p],
     "rvb_local_attn_bwd_q": [_c_p, _c_p, _c_p, _c_p, _i32, _i32, _i32, _i32, _i32, _c_p, _c_p, _c_p],
     "rvb_local_attn_bwd_kv": [_c_p, _c_p, _c_p, _c_p, _i32, _i32, _i32, _i32, _i32, _c_p, _c_p, _c_p],

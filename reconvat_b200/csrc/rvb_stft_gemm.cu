@@ -49,6 +49,8 @@ constexpr int kEpiRawGemm = 0x100;                // internal epilogue code: sto
 
 struct GemmParams {
   int64_t ldc;                                    // kEpiRawGemm: row stride of C
+  int64_t split_stride;                           // kEpiRawGemm: elements between the partial results of a split contraction
+  int k_split;                                    // units per (m, n) tile along the contraction (1 for the STFT)
   int n_seg, rows_per_seg, hop, n_frames, n_fft;
   int tiles_per_seg, m_tiles, n_tiles;
   int epilogue, n_out_bins, n_store_bins;
@@ -244,8 +246,10 @@ stft_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
 
-  const int n_units = p.m_tiles * p.n_tiles;
-  const int num_kb = p.n_fft / BLOCK_K;
+  // unit = (m tile, n tile, slice of the contraction); k_split == 1 everywhere but in the split-K plain GEMM
+  const int n_units = p.m_tiles * p.n_tiles * p.k_split;
+  const int num_kb_all = p.n_fft / BLOCK_K;
+  const int kb_per = (num_kb_all + p.k_split - 1) / p.k_split;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -253,11 +257,13 @@ stft_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
+        const int ks = unit % p.k_split, mn = unit / p.k_split;
+        const int m_tile = mn / p.n_tiles, n_tile = mn - m_tile * p.n_tiles;
         const int b = m_tile / p.tiles_per_seg;
         const int t0 = (m_tile - b * p.tiles_per_seg) * BLOCK_M;
         const int row0 = b * p.rows_per_seg + t0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_end = min(num_kb_all, (ks + 1) * kb_per);
+        for (int kb = ks * kb_per; kb < kb_end; ++kb) {
           mbar_wait(bar_empty(stage), phase ^ 1u, p.dbg_status, 1);
           mbar_expect_tx(bar_full(stage), STAGE_BYTES);
           const int kk = kb * BLOCK_K;
@@ -281,6 +287,8 @@ stft_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         mbar_wait(bar_tmem_empty(acc), acc_phase ^ 1u, p.dbg_status, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+        const int kb0 = (unit % p.k_split) * kb_per;
+        const int num_kb = min(num_kb_all, kb0 + kb_per) - kb0;      // >= 1: the host never makes empty slices
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_full(stage), phase, p.dbg_status, 3);
           tc_fence_after();
@@ -310,7 +318,8 @@ stft_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-      const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
+      const int ks = unit % p.k_split, mn = unit / p.k_split;
+      const int m_tile = mn / p.n_tiles, n_tile = mn - m_tile * p.n_tiles;
       const int b = m_tile / p.tiles_per_seg;
       const int t = (m_tile - b * p.tiles_per_seg) * BLOCK_M + row;
       const bool t_ok = t < p.n_frames;
@@ -319,7 +328,7 @@ stft_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
       if (p.epilogue == kEpiRawGemm) {
         // plain GEMM (rvb_gemm_nt_tf32x3): C[t][n_tile * 256 + j] = accumulator column j; n_out_bins = N, power = ldc
-        float* crow = p.out0 + (int64_t)t * p.ldc + n_tile * BLOCK_N;
+        float* crow = p.out0 + (int64_t)ks * p.split_stride + (int64_t)t * p.ldc + n_tile * BLOCK_N;
         const bool vec = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out0) & 15u) == 0;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -1860,7 +1869,7 @@ extern "C" int rvb_stft_gemm(const float* sig_hi, const float* sig_lo, int n_seg
   p.n_tiles = n_basis_rows / BLOCK_N;
   p.epilogue = epilogue; p.n_out_bins = n_out_bins;
   p.n_store_bins = n_out_bins < n_basis_rows / 2 ? n_out_bins : n_basis_rows / 2;
-  p.power = power; p.out0 = out0; p.dbg_status = nullptr; p.ldc = 0;
+  p.power = power; p.out0 = out0; p.dbg_status = nullptr; p.ldc = 0; p.split_stride = 0; p.k_split = 1;
   return launch_stft_gemm(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p, stream);
 }
 
@@ -1868,12 +1877,24 @@ extern "C" int rvb_stft_gemm(const float* sig_hi, const float* sig_lo, int n_seg
 // the caller's sequence model (nn.Linear of MutliHeadAttention1D, model/self_attention_VAT.py:54-56, 70-71), which
 // PyTorch runs as SIMT SGEMMs (TF32 is off by default for matmul).  Operands: tf32 hi / lo planes [rows][k_pad] from
 // rvb_split_tf32, k_pad a multiple of 32, zero beyond K.  Rows past M / N are zero-filled by the TMA and never stored.
+// k_split > 1: the contraction is cut into k_split slices of whole 32-element blocks and slice s writes its partial product
+// to c + s * split_stride -- for products with few output tiles and a long contraction (dW = dY^T X: 916 x 229 outputs,
+// 20 480 terms); the caller adds the partials in a fixed order (deterministic, unlike atomics).
 extern "C" int rvb_gemm_nt_tf32x3(const float* a_hi, const float* a_lo, int64_t m, const float* b_hi, const float* b_lo,
-                                  int n, int k_pad, float* c, int64_t ldc, rvb_stream_t stream) {
+                                  int n, int k_pad, float* c, int64_t ldc, int k_split, int64_t split_stride,
+                                  rvb_stream_t stream) {
   RVB_REQUIRE(a_hi && a_lo && b_hi && b_lo && c, "rvb_gemm_nt_tf32x3: null pointer");
   RVB_REQUIRE(m > 0 && n > 0 && k_pad >= BLOCK_K && k_pad % BLOCK_K == 0 && ldc >= n,
               "rvb_gemm_nt_tf32x3: bad shape (m=%lld n=%d k_pad=%d ldc=%lld)", (long long)m, n, k_pad, (long long)ldc);
   RVB_REQUIRE(m < (1ll << 31) - BLOCK_M, "rvb_gemm_nt_tf32x3: too many rows");
+  RVB_REQUIRE(k_split >= 1 && k_split <= k_pad / BLOCK_K && (k_split == 1 || split_stride >= m * ldc),
+              "rvb_gemm_nt_tf32x3: bad split (k_split=%d of %d blocks, stride %lld)", k_split, k_pad / BLOCK_K,
+              (long long)split_stride);
+  {
+    // no empty slice: with kb_per = ceil(blocks / k_split), slice k_split - 1 must still start inside the contraction
+    const int blocks = k_pad / BLOCK_K, kb_per = (blocks + k_split - 1) / k_split;
+    RVB_REQUIRE((k_split - 1) * kb_per < blocks, "rvb_gemm_nt_tf32x3: k_split %d leaves an empty slice of %d blocks", k_split, blocks);
+  }
   for (const void* ptr : {(const void*)a_hi, (const void*)a_lo, (const void*)b_hi, (const void*)b_lo})
     RVB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 127u) == 0, "rvb_gemm_nt_tf32x3: operands must be 128-byte aligned");
   CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
@@ -1888,7 +1909,7 @@ extern "C" int rvb_gemm_nt_tf32x3(const float* a_hi, const float* a_lo, int64_t 
   p.m_tiles = p.tiles_per_seg;
   p.n_tiles = (n + BLOCK_N - 1) / BLOCK_N;
   p.epilogue = kEpiRawGemm; p.n_out_bins = n; p.n_store_bins = n;
-  p.power = 0.f; p.out0 = c; p.dbg_status = nullptr; p.ldc = ldc;
+  p.power = 0.f; p.out0 = c; p.dbg_status = nullptr; p.ldc = ldc; p.k_split = k_split; p.split_stride = split_stride;
   return launch_stft_gemm(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p, stream);
 }
 

@@ -44,12 +44,37 @@ def _split(x, planes=None, transpose=False, offset=0, zero_to=None):
     return planes
 
 
+_N_SM = {}
+
+
+def _sm_count(device):
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    if index not in _N_SM:
+        _N_SM[index] = torch.cuda.get_device_properties(index).multi_processor_count
+    return _N_SM[index]
+
+
 def _gemm_nt(a, b, m, n, out):
-    """out[m][n] = A . B^T from (hi, lo) planes with the same padded contraction length."""
+    """out[m][n] = A . B^T from (hi, lo) planes with the same padded contraction length.  Products with fewer output
+    tiles (128 x 256) than SMs and a long contraction are cut along it: every slice writes its own partial product and
+    the partials are added in a fixed order."""
     k_pad = a[0].shape[1]
     assert b[0].shape[1] == k_pad and out.stride(1) == 1
+    tiles = -(-m // 128) * -(-n // 256)
+    blocks = k_pad // 32
+    k_split = 1
+    if tiles < _sm_count(out.device) and blocks >= 16:
+        k_split = max(1, min(blocks // 8, -(-2 * _sm_count(out.device) // tiles)))
+        per = -(-blocks // k_split)
+        k_split = -(-blocks // per)                           # no empty slice
+    if k_split == 1:
+        _lib.call("rvb_gemm_nt_tf32x3", a[0].data_ptr(), a[1].data_ptr(), m, b[0].data_ptr(), b[1].data_ptr(), n, k_pad,
+                  out.data_ptr(), out.stride(0), 1, 0)
+        return out
+    part = torch.empty((k_split, m, n), dtype=torch.float32, device=out.device)
     _lib.call("rvb_gemm_nt_tf32x3", a[0].data_ptr(), a[1].data_ptr(), m, b[0].data_ptr(), b[1].data_ptr(), n, k_pad,
-              out.data_ptr(), out.stride(0))
+              part.data_ptr(), n, k_split, m * n)
+    torch.sum(part, dim=0, out=out)
     return out
 
 
