@@ -60,7 +60,16 @@ class _LocalAttention(torch.autograd.Function):
         if rel is not None:
             dE2, rel3 = dE.view(B * L, G, W), rel.view(G, D, W)
             dq = dq + torch.einsum("nhw,hcw->nhc", dE2, rel3).reshape(B, L, G * D)      # dE . rel^T
-            drel = torch.einsum("nhc,nhw->hcw", q.view(B * L, G, D), dE2).reshape(G * D, W)
+            if os.environ.get("RVB_ATTN_PROJ", "tc") == "torch":
+                drel = torch.einsum("nhc,nhw->hcw", q.view(B * L, G, D), dE2).reshape(G * D, W)
+            else:
+                # d rel[h] = q_h^T . dE_h: 229 x 31 outputs, 20 480 terms -- cuBLAS picks a 464 us kernel for this shape;
+                # here it is the split-K tensor-core contraction (operands transposed while they are split)
+                q2, drel = q.view(B * L, G * D), torch.empty((G * D, W), dtype=torch.float32, device=q.device)
+                for h in range(G):
+                    qt = linear._split(q2[:, h * D:(h + 1) * D], transpose=True)            # (D, n_pad)
+                    et = linear._split(dE2[:, h, :], transpose=True)                         # (W, n_pad)
+                    linear._gemm_nt(qt, et, D, W, drel[h * D:(h + 1) * D])
         return dq, dk, dv, drel, None, None
 
 

@@ -255,7 +255,27 @@ namespace rvb {
 
 __global__ void __launch_bounds__(256)
 split_tf32_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ld, float* __restrict__ hi,
-                  float* __restrict__ lo, int64_t out_ld, int col0, int zero_to) {
+                  float* __restrict__ lo, int64_t out_ld, int col0, int zero_to, int vec) {
+  // vec: 16-byte loads and stores (every row start, col0 and the widths are multiples of four floats)
+  if (vec) {
+    const int c4 = blockIdx.x * blockDim.x + threadIdx.x;           // quad index inside [col0, zero_to)
+    if (c4 >= (zero_to - col0) >> 2) return;
+    const int c = c4 << 2;
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c + 4 <= cols) v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+      else {
+        if (c < cols) v.x = __ldg(x + r * ld + c);
+        if (c + 1 < cols) v.y = __ldg(x + r * ld + c + 1);
+        if (c + 2 < cols) v.z = __ldg(x + r * ld + c + 2);
+      }
+      const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      *reinterpret_cast<float4*>(hi + r * out_ld + col0 + c) = h;
+      *reinterpret_cast<float4*>(lo + r * out_ld + col0 + c) =
+          make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+    }
+    return;
+  }
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= zero_to - col0) return;
   for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
@@ -304,8 +324,15 @@ extern "C" int rvb_split_tf32(const float* x, int64_t rows, int cols, int64_t ld
   RVB_REQUIRE(zero_to >= offset + extent && zero_to <= out_ld, "rvb_split_tf32: need offset + extent <= zero_to <= out_ld");
   if (!transpose) {
     RVB_REQUIRE(zero_to - offset < (1ll << 31), "rvb_split_tf32: too wide");
-    dim3 grid((unsigned)((zero_to - offset + 255) / 256), (unsigned)(rows < 65535 ? rows : 65535));
-    rvb::split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, hi, lo, out_ld, (int)offset, (int)zero_to);
+    const auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    const int vec = a16(x) && a16(hi) && a16(lo) && (ld & 3) == 0 && (out_ld & 3) == 0 && (offset & 3) == 0 &&
+                    ((zero_to - offset) & 3) == 0;
+    const int64_t width = vec ? (zero_to - offset) >> 2 : zero_to - offset;
+    const unsigned bx = (unsigned)((width + 255) / 256);
+    // few, fat blocks along the rows: every thread streams a column quad down its share of the rows
+    const int64_t by = rows < 2048 ? rows : 2048;
+    dim3 grid(bx, (unsigned)by);
+    rvb::split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, hi, lo, out_ld, (int)offset, (int)zero_to, vec);
   } else {
     const int64_t r_tiles = (zero_to - offset + 31) / 32;
     RVB_REQUIRE(r_tiles <= 65535, "rvb_split_tf32: too many rows for one launch");

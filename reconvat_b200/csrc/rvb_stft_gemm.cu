@@ -1830,7 +1830,7 @@ static int launch_stft_gemm(const CUtensorMap& tm_a_hi, const CUtensorMap& tm_a_
       attr_set[slot] = true;
     }
   }
-  const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles;
+  const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles * p.k_split;
   const int grid = (int)(n_units < num_sms() ? n_units : num_sms());
   stft_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p);
   count_launch();

@@ -62,9 +62,12 @@ def _gemm_nt(a, b, m, n, out):
     assert b[0].shape[1] == k_pad and out.stride(1) == 1
     tiles = -(-m // 128) * -(-n // 256)
     blocks = k_pad // 32
+    sms = _sm_count(out.device)
     k_split = 1
-    if tiles < _sm_count(out.device) and blocks >= 16:
-        k_split = max(1, min(blocks // 8, -(-2 * _sm_count(out.device) // tiles)))
+    if tiles < 4 * sms and blocks >= 16:
+        # fewer than four rounds of tiles: cut the contraction until there are ~six (no tail of half-empty rounds),
+        # slices of at least eight 32-element blocks
+        k_split = max(1, min(blocks // 8, -(-6 * sms // tiles)))
         per = -(-blocks // k_split)
         k_split = -(-blocks // per)                           # no empty slice
     if k_split == 1:
