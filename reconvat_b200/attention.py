@@ -22,6 +22,17 @@ import torch.nn.init as init
 from . import _lib, linear
 
 
+def _projection_path(x):
+    """'tc' (3xTF32 tcgen05 contractions, reconvat_b200.linear) or 'torch' (nn.Linear / einsum on cuBLAS SGEMM).
+    RVB_ATTN_PROJ forces one; by default the tensor-core path takes over from 16 384 rows (B >= 26 segments of 640
+    frames): below that its operand-split passes and extra launches cost more than the SIMT GEMMs they replace
+    (B = 8: 1.8 vs 1.3 ms per layer call; B = 32: 3.3 vs 4.4 ms, profiles/r02_attention.txt)."""
+    forced = os.environ.get("RVB_ATTN_PROJ")
+    if forced in ("tc", "torch"):
+        return forced
+    return "tc" if x.numel() // x.shape[-1] >= 16384 else "torch"
+
+
 class _LocalAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, rel, groups, window):
@@ -60,7 +71,7 @@ class _LocalAttention(torch.autograd.Function):
         if rel is not None:
             dE2, rel3 = dE.view(B * L, G, W), rel.view(G, D, W)
             dq = dq + torch.einsum("nhw,hcw->nhc", dE2, rel3).reshape(B, L, G * D)      # dE . rel^T
-            if os.environ.get("RVB_ATTN_PROJ", "tc") == "torch":
+            if _projection_path(q) == "torch":
                 drel = torch.einsum("nhc,nhw->hcw", q.view(B * L, G, D), dE2).reshape(G * D, W)
             else:
                 # d rel[h] = q_h^T . dE_h: 229 x 31 outputs, 20 480 terms -- cuBLAS picks a 464 us kernel for this shape;
@@ -99,7 +110,7 @@ class MutliHeadAttention1D(nn.Module):
         self.reset_parameters()
 
     def forward(self, x):
-        if os.environ.get("RVB_ATTN_PROJ", "tc") == "torch":
+        if _projection_path(x) == "torch":
             q, k, v = self.W_q(x), self.W_k(x), self.W_v(x)              # zero padding rows project to zero (no bias)
         else:
             q, k, v = linear.projections(x, [self.W_q.weight, self.W_k.weight, self.W_v.weight])

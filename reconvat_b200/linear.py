@@ -119,17 +119,27 @@ class _Projections(torch.autograd.Function):
                 off += w.shape[0]
             dx = _gemm_nt(da, wt, m, k, torch.empty((m, k), dtype=torch.float32, device=dev))
             del da, wt
-        dws = []
-        xt = None
-        for i, (d, w) in enumerate(zip(dys, weights)):
-            if d is None or not ctx.needs_input_grad[1 + i]:
-                dws.append(None)
-                continue
-            if xt is None:
-                xt = _split(x, transpose=True)                                   # (k, m_pad)
-            dt = _split(d, transpose=True)                                       # (n_i, m_pad)
-            dws.append(_gemm_nt(dt, xt, w.shape[0], k, torch.empty_like(w)))
-            del dt
+        # dW_i = dy_i^T . x for all i in ONE contraction: A = [dy_1 | dy_2 | ...]^T stacked along the rows (each dy_i^T
+        # written by a transposing split into its row block), B = x^T; the contraction runs over the m rows
+        want = [i for i, d in enumerate(dys) if d is not None and ctx.needs_input_grad[1 + i]]
+        dws = [None] * len(weights)
+        if want:
+            n_rows = sum(weights[i].shape[0] for i in want)
+            m_pad = _pad32(m)
+            dt = _planes(n_rows, m_pad, dev)
+            xt = _split(x, transpose=True)                                       # (k, m_pad)
+            off = 0
+            for i in want:
+                n_i = weights[i].shape[0]
+                _split(dys[i], (dt[0][off:off + n_i], dt[1][off:off + n_i]), True, 0, m_pad)
+                off += n_i
+            dw_cat = _gemm_nt(dt, xt, n_rows, k, torch.empty((n_rows, k), dtype=torch.float32, device=dev))
+            off = 0
+            for i in want:
+                n_i = weights[i].shape[0]
+                dws[i] = dw_cat[off:off + n_i]
+                off += n_i
+            del dt, xt
         return (dx,) + tuple(dws)
 
 
