@@ -615,3 +615,49 @@ def test_state_dict_interchange(R, dev):
     m2.load_state_dict(sd, strict=True)
     x = torch.rand(1, 8192, device=dev)
     assert torch.equal(m2(x), m.to(dev)(x))
+
+
+def test_headline_shape_b32_against_the_oracle(R, dev):
+    """The benchmark's own shape -- B = 32 segments of 327 680 samples, PCM16 -- against the CPU oracle on all 32
+    segments (the headline shape was pinned by invariance properties and B <= 8 oracle runs only)."""
+    from oracle.frontend import FrontEndOracle
+    from reconvat_b200 import synth
+    a16 = np.stack([synth.music_int16(synth.SEGMENT_SAMPLES, 900 + b) if b % 2 else synth.white_int16(synth.SEGMENT_SAMPLES, 900 + b)
+                    for b in range(32)])
+    m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    spec = m.normalised_log_mel(torch.from_numpy(a16).to(dev)).cpu().numpy()
+    lm = torch.log(m(torch.from_numpy(a16).to(dev)[:, :-1]) + 1e-5).cpu().numpy()
+    orc = FrontEndOracle()
+    ref_lm = np.concatenate([orc.log_mel(synth.to_float(a16[i:i + 8])[:, :-1]) for i in range(0, 32, 8)])
+    assert lm.shape == ref_lm.shape == (32, 229, 640)
+    assert relerr(lm, ref_lm) < LOGMEL_TOL
+    ref_spec = np.swapaxes(orc.normalise_imagewise(ref_lm), -1, -2)[:, None]
+    assert spec.shape == (32, 1, 640, 229) and np.abs(spec - ref_spec).max() < LOGMEL_TOL
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_logmel_error_budget_on_hard_signals(R, dev, fused, monkeypatch):
+    """The 1e-4 log-Mel budget on signals chosen to stress the split-precision contraction, against float64: pure tones
+    on and between bin centres (weak bins next to a full-scale partial), a full-scale square wave, a chirp, an
+    impulse train, noise 80 dB below a tone, near-silence (2 LSB of noise).  Records the worst case."""
+    from oracle.frontend import FrontEndOracle
+    monkeypatch.setenv("RVB_FUSED_FOLD", "1" if fused else "0")
+    n = 64 * 512 + 1
+    t = np.arange(n) / 16000.0
+    rng = np.random.default_rng(7)
+    sigs = {
+        "tone_on_bin": 0.98 * np.sin(2 * np.pi * 1000.0 * t),                      # 1000 Hz = bin 128 exactly
+        "tone_between_bins": 0.98 * np.sin(2 * np.pi * 1003.90625 * t),            # bin 128.5
+        "two_tones_80dB": 0.9 * np.sin(2 * np.pi * 440.0 * t) + 0.9e-4 * np.sin(2 * np.pi * 3520.0 * t),
+        "square_full_scale": 0.999 * np.sign(np.sin(2 * np.pi * 220.0 * t)),
+        "chirp": 0.7 * np.sin(2 * np.pi * (50.0 + 3800.0 * t / t[-1]) * t),
+        "impulses": np.where(np.arange(n) % 4001 == 0, 0.9, 0.0),
+        "tone_over_noise_floor": 0.5 * np.sin(2 * np.pi * 2000.0 * t) + 5e-5 * rng.standard_normal(n),
+        "near_silence": 6e-5 * rng.standard_normal(n),
+    }
+    a16 = np.stack([np.clip(np.round(s * 32768.0), -32768, 32767).astype(np.int16) for s in sigs.values()])
+    m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    lm = torch.log(m(torch.from_numpy(a16).to(dev)[:, :-1]) + 1e-5).cpu().numpy()
+    ref = FrontEndOracle().log_mel(a16[:, :-1].astype(np.float64) / 32768.0, np.float64)
+    errs = {k: relerr(lm[i], ref[i]) for i, k in enumerate(sigs)}
+    assert max(errs.values()) < LOGMEL_TOL, errs
