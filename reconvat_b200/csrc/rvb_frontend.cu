@@ -201,7 +201,7 @@ __device__ __forceinline__ void fold4(const TIn* __restrict__ fr /* fr[i] = p[i]
 // residual never below 2^-2), whatever the level of the frame -- so every row takes the same scale 4 * gain.  The
 // planes differ from the block-scaled ones by an exact power of two per row, the contraction's result not at all.
 template <typename TIn, bool kPerm, bool kFixed = false>
-__global__ void __launch_bounds__(kFoldWarps * 32, 4)
+__global__ void __launch_bounds__(kFoldWarps * 32)
 fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gain, int n_seg, int n_samples, int pad,
                       int mode, int n_fft, int hop, int n_frames, int groups_per_seg, __half* __restrict__ a_hi,
                       __half* __restrict__ a_lo, float* __restrict__ row_scale_inv, float* __restrict__ p0) {
@@ -315,73 +315,6 @@ fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gai
         hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
         lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
       };
-      bool fast_done = false;
-      if constexpr (kPerm && kFixed && sizeof(TIn) == 2) {
-        // PCM16, parity-ordered planes, fixed scale (the benchmark's route): 16 consecutive n per lane and trip, every
-        // plane row written with 16-byte stores, and no integer -> float conversion: the 16 sample bits (offset
-        // binary) are glued under the exponent of 1.5 * 2^21 -- the float 1.5 * 2^21 + u / 4 -- so that
-        //   o / 4 = f(ux) - f(uy)                 e / 4 = f(ux) - f(~uy) - 1/4        (~u = 65535 - u)
-        // exactly.  The same values v = e / 4, o / 4 as the generic loop below, hence the same hi / lo bits.
-        if ((hop & 7) == 0 && (n_fft & 15) == 0) {
-          constexpr uint32_t kMagic = 0x4A400000u;           // 1.5 * 2^21: the low 16 mantissa bits weigh 1/4 .. 2^13
-          const uint32_t* fw = reinterpret_cast<const uint32_t*>(fr);
-          for (int c = lane << 4; c < half; c += 512) {
-            const uint4 f0 = *reinterpret_cast<const uint4*>(fr + c), f1 = *reinterpret_cast<const uint4*>(fr + c + 8);
-            const uint4 b0 = *reinterpret_cast<const uint4*>(fr + n_fft - c - 16);
-            const uint4 b1 = *reinterpret_cast<const uint4*>(fr + n_fft - c - 8);
-            const uint32_t xw[9] = {f0.x ^ 0x80008000u, f0.y ^ 0x80008000u, f0.z ^ 0x80008000u, f0.w ^ 0x80008000u,
-                                    f1.x ^ 0x80008000u, f1.y ^ 0x80008000u, f1.z ^ 0x80008000u, f1.w ^ 0x80008000u,
-                                    fw[(c >> 1) + 8] ^ 0x80008000u};
-            const uint32_t yw[8] = {b0.x ^ 0x80008000u, b0.y ^ 0x80008000u, b0.z ^ 0x80008000u, b0.w ^ 0x80008000u,
-                                    b1.x ^ 0x80008000u, b1.y ^ 0x80008000u, b1.z ^ 0x80008000u, b1.w ^ 0x80008000u};
-            uint32_t eh[8], el[8], oh[8], ol[8];             // [0,4): even n, [4,8): odd n; two columns per word
-            auto split2 = [](float v0, float v1, uint32_t& hi, uint32_t& lo) {
-              const __half2 h = __floats2half2_rn(v0, v1);
-              const float2 hf = __half22float2(h);
-              const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-              hi = *reinterpret_cast<const uint32_t*>(&h);
-              lo = *reinterpret_cast<const uint32_t*>(&l);
-            };
-#pragma unroll
-            for (int m = 0; m < 8; m += 2) {
-              float ve[2], vo[2], we[2], wo[2];              // (e, o) of the even n, of the odd n
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                const uint32_t ywd = yw[7 - (m + k)];
-                // odd n = c + 1 + 2 (m + k): x = high half of word m + k, partner = high half of word 7 - (m + k)
-                const float xo = __uint_as_float(__byte_perm(xw[m + k], kMagic, 0x7632));
-                const float yo = __uint_as_float(__byte_perm(ywd, kMagic, 0x7632));
-                const float yoc = __uint_as_float(__byte_perm(~ywd, kMagic, 0x7632));
-                wo[k] = xo - yo;
-                we[k] = (xo - yoc) - 0.25f;
-                // even n = c + 2 + 2 (m + k): x = low half of word m + k + 1, partner = low half of word 7 - (m + k)
-                const float xe = __uint_as_float(__byte_perm(xw[m + k + 1], kMagic, 0x7610));
-                const float ye = __uint_as_float(__byte_perm(ywd, kMagic, 0x7610));
-                const float yec = __uint_as_float(__byte_perm(~ywd, kMagic, 0x7610));
-                vo[k] = xe - ye;
-                ve[k] = (xe - yec) - 0.25f;
-                if (c + 2 + 2 * (m + k) == half) { ve[k] = (xe - __uint_as_float(kMagic)) - 8192.f; vo[k] = 0.f; }   // n == N/2: e = x
-              }
-              split2(ve[0], ve[1], eh[m >> 1], el[m >> 1]);
-              split2(vo[0], vo[1], oh[m >> 1], ol[m >> 1]);
-              split2(we[0], we[1], eh[4 + (m >> 1)], el[4 + (m >> 1)]);
-              split2(wo[0], wo[1], oh[4 + (m >> 1)], ol[4 + (m >> 1)]);
-            }
-            const int qe = c >> 4, qo = (half >> 4) + (c >> 4);             // in units of eight halves (16 bytes)
-            reinterpret_cast<uint4*>(e_hi)[qe] = make_uint4(eh[0], eh[1], eh[2], eh[3]);
-            reinterpret_cast<uint4*>(e_hi)[qo] = make_uint4(eh[4], eh[5], eh[6], eh[7]);
-            reinterpret_cast<uint4*>(e_lo)[qe] = make_uint4(el[0], el[1], el[2], el[3]);
-            reinterpret_cast<uint4*>(e_lo)[qo] = make_uint4(el[4], el[5], el[6], el[7]);
-            reinterpret_cast<uint4*>(o_hi)[qe] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-            reinterpret_cast<uint4*>(o_hi)[qo] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
-            reinterpret_cast<uint4*>(o_lo)[qe] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-            reinterpret_cast<uint4*>(o_lo)[qo] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
-          }
-          if (lane == 0) row_scale_inv[f] = 4.f * gain;
-          fast_done = true;
-        }
-      }
-      if (!fast_done) {
       for (int c = lane << 2; c < half; c += 128) {
         fold4<TIn, kFixed>(fr, gain, n_fft, half, c, ev, ov);
         uint2 h, l;
@@ -404,7 +337,6 @@ fold_split_f16_kernel(const TIn* __restrict__ audio, int64_t audio_ld, float gai
       if (lane == 0) {
         row_scale_inv[f] = kFixed ? 4.f * gain : __uint_as_float((unsigned)(127 - s) << 23);      // 2^-s
         if (p0) p0[f] = (float)fr[0] * (sizeof(TIn) == 4 ? 1.f : gain);
-      }
       }
     }
     __syncthreads();                                         // everyone is done with bufs[cur]: it may be refilled
@@ -948,9 +880,9 @@ static int launch_fold_split_f16(const char* who, const TIn* audio, int64_t audi
   const int groups_per_seg = (n_frames + kFoldWarps - 1) / kFoldWarps;
   const int64_t n_groups = (int64_t)n_seg * groups_per_seg;
   RVB_REQUIRE(n_groups < (1ll << 31), "%s: too many frames", who);
-  // persistent blocks: as many as stay resident (4 x 256 threads x 64 registers or the shared memory, whichever binds)
+  // persistent blocks: as many as stay resident (8 x 256 threads or the shared memory, whichever binds)
   int per_sm = (int)((220 * 1024) / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
   const int64_t cap = (int64_t)148 * per_sm;
   const unsigned grid = (unsigned)(n_groups < cap ? n_groups : cap);
   kernel<<<grid, kFoldWarps * 32, smem, (cudaStream_t)stream>>>(
