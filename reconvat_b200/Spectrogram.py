@@ -315,13 +315,29 @@ class MelSpectrogram(nn.Module):
 
     Extension (not in the reference): :meth:`normalised_log_mel` runs the rest of the front-end of
     ``UNet.run_on_batch`` (model/self_attention_VAT.py:1100-1104) fused on the device.
+
+    ``precision`` (extension; default ``$RVB_PRECISION`` or ``"fast"``) picks the contraction:
+
+    * ``"fast"``: the TWICE-folded contraction -- bins k and N/2-k from the parity-split sums Ce +- Co, a quarter of
+      the dense contraction's multiply-adds.  The partial sums carry the energy of BOTH bins and are accumulated in
+      fp32 (TMEM), so a bin inherits an absolute error of ~1e-7 of the amplitude of its mirror bin N/2-k (-140 dB).
+      On white, music-like and PCM-quantised input (the BASELINE signals) log-Mel stays within 4.3e-5 of float64; a
+      band that lies more than ~75 dB below the content at its mirror frequency (a full-scale 7 kHz tone over silent
+      low bands) can miss the 1e-4 budget by up to 9x -- still closer to the truth than the reference's own GPU run with
+      PyTorch's default ``cudnn.allow_tf32=True`` (1.3e-4 .. 5.6e-4 on the same signals, profiles/r02_precision.md).
+    * ``"strict"``: the once-folded contraction (every bin accumulated on its own, twice the multiply-adds): <= 2.8e-5
+      on every stress signal, the accuracy class of the reference's fp32 path.
     """
 
     def __init__(self, sr=22050, n_fft=2048, n_mels=128, hop_length=512,
                  window='hann', center=True, pad_mode='reflect', power=2.0, htk=False,
                  fmin=0.0, fmax=None, norm=1, trainable_mel=False, trainable_STFT=False,
-                 verbose=True, **kwargs):
+                 verbose=True, precision=None, **kwargs):
         super().__init__()
+        precision = precision or os.environ.get("RVB_PRECISION", "fast")
+        if precision not in ("fast", "strict"):
+            raise ValueError("precision must be 'fast' or 'strict', got %r" % (precision,))
+        self.precision = precision
         if trainable_mel or trainable_STFT:
             raise NotImplementedError("reconvat_b200.MelSpectrogram: trainable_mel / trainable_STFT "
                                       "(model/Spectrogram.py:430-433) are outside the accelerated hot path")
@@ -382,7 +398,7 @@ class MelSpectrogram(nn.Module):
         key = (self.mel_basis.device, self.mel_basis._version, self.mel_basis.data_ptr())
         if self._fused2 is None or self._fused2_key != key:
             tab = None
-            if self.stft.fused_mel_ok() and float(self.power) == 2.0 and \
+            if self.precision == "fast" and self.stft.fused_mel_ok() and float(self.power) == 2.0 and \
                     self.stft._device_tables().get("fold2") is not None:
                 # 64 rows per epilogue group (32 in the four-chain A/B kernel): bands up to 65 bins wide stay at two
                 # partial sums per element
