@@ -296,6 +296,29 @@ def run_ours(args, rank, local_rank, world):
                      "value": world * B * SEG_SECONDS / (sus_ms / n_sus * 1e-3), "unit": "audio-s/s",
                      "clocks": sus_sampler.summary()}
 
+    # ---------------- precision="strict": the once-folded contraction (every bin accumulated on its own) ------------
+    strict = None
+    if not args.no_graphs and not args.no_gpu_baselines:
+        step_s = HotPathStep(model, dev, precision="strict")
+        for i in range(3):
+            step_s(dev_audio[i % n_rot])
+        step_s.capture(dev_audio)
+        for i in range(args.warmup):
+            step_s.replay(i % n_rot)
+        barrier()
+        ev0.record()
+        step_s.replay_many([i % n_rot for i in range(args.steps)], streams=args.streams)
+        ev1.record()
+        barrier()
+        step_s.check()
+        s_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+        strict = {"ms_per_step": s_ms, "value": world * B * SEG_SECONDS / (s_ms * 1e-3), "unit": "audio-s/s",
+                  "what": "the same step with MelSpectrogram(precision='strict'): once-folded contraction, twice the "
+                          "multiply-adds, log-Mel within 2.8e-5 of float64 on every stress signal "
+                          "(profiles/r02_precision.md); the headline `value` is precision='fast'"}
+        del step_s
+        torch.cuda.empty_cache()
+
     # ---------------- the zero-edit module surface and the reference's eager path on the same GPU ----------------
     surface = gpu_eager = None
     if not args.no_gpu_baselines:
@@ -567,6 +590,7 @@ def run_ours(args, rank, local_rank, world):
                          "%d recorded working sets (> L2); the contraction's entry point includes the memset of "
                          "its Mel accumulator (38 MB for the two planes of the twice-folded kernel)" % (reps, n_rot),
         "e2e_device_corpus": dev_corpus,
+        "precision_strict": strict,
         "sustained": sustained,
         "module_surface": surface,
         "gpu_eager_baseline": gpu_eager,

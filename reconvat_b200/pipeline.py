@@ -19,10 +19,10 @@ MEL_KW = dict(sr=16000, win_length=2048, n_mels=229, hop_length=512, fmin=30, fm
 
 
 class HotPathStep:
-    def __init__(self, model, device, xi=1e-6, eps=2.0, vat_cls=None):
+    def __init__(self, model, device, xi=1e-6, eps=2.0, vat_cls=None, precision=None):
         self.device = torch.device(device)
         self.model = model
-        self.spectrogram = Spectrogram.MelSpectrogram(**MEL_KW).to(self.device)
+        self.spectrogram = Spectrogram.MelSpectrogram(precision=precision, **MEL_KW).to(self.device)
         # strict=False: the step never synchronises; check() tests the NaN flags (eager and per graph) on demand
         self.vat_loss = (vat_cls or VAT.UNet_VAT)(xi, eps, 1, False, strict=False)
         # private reduction workspaces + the fused NaN flag / mean |d_hat| (VAT.Scratch); every captured graph gets
