@@ -313,8 +313,9 @@ def run_ours(args, rank, local_rank, world):
         step_s.check()
         s_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
         strict = {"ms_per_step": s_ms, "value": world * B * SEG_SECONDS / (s_ms * 1e-3), "unit": "audio-s/s",
-                  "what": "the same step with MelSpectrogram(precision='strict'): once-folded contraction, twice the "
-                          "multiply-adds, log-Mel within 2.8e-5 of float64 on every stress signal "
+                  "what": "the same step with MelSpectrogram(precision='strict'): once-folded contraction (twice the "
+                          "multiply-adds), correction terms accumulated before the leading one (1.5x the operand "
+                          "traffic); log-Mel within 3.2e-5 of float64 on every stress signal "
                           "(profiles/r02_precision.md); the headline `value` is precision='fast'"}
         del step_s
         torch.cuda.empty_cache()

@@ -413,6 +413,7 @@ struct FoldParams {
   // fused Mel projection (K1m, kernels instantiated with a MelTable): the epilogue does not store the spectrum
   float* mel_out;               // [n_seg][n_mels][n_frames], zeroed before the launch, accumulated with RED.ADD
   int n_mels;
+  int corr_first;               // CTA-pair kernel: order of the three MMAs of the split product, see the kernel
 };
 
 // ---- epilogue of one unit (128 frames x 128 bins), shared by the one-CTA and the CTA-pair folded kernels ----
@@ -824,7 +825,15 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
   constexpr int kBlockK = 2 * BLOCK_K;            // 64 halves per 128-byte swizzle row
   const int n_units = p.m_tiles * p.n_tiles;      // m_tiles counts 256-frame pair tiles here
   const int kb_per_chain = p.half / kBlockK;
-  const int num_kb = 2 * kb_per_chain;
+  // Order of the split product's three MMAs.  The tensor core adds every MMA into the fp32 accumulator with
+  // TRUNCATION, not round-to-nearest: each of the 3 * half / 16 additions of a chain loses up to an ulp of the running
+  // sum, always in the same direction, so a weak bin whose partial sums carry a strong partial's energy ends up biased
+  // by ~(number of additions) * ulp(partial sum) / 2 (profiles/r02_precision.md).  corr_first: the chain runs twice --
+  // first hi*lo + lo*hi over the whole contraction (partial sums 2^-11 of the product's: their truncation is
+  // negligible), then hi*hi on top -- one truncation at full magnitude per 16 terms instead of three.  The second
+  // pass streams the hi planes again: 1.5x the operand traffic, the same MMAs.
+  const int steps_per_chain = p.corr_first ? 2 * kb_per_chain : kb_per_chain;
+  const int n_steps = 2 * steps_per_chain;
   const int unit0 = (int)(blockIdx.x >> 1), unit_step = (int)(gridDim.x >> 1);     // cluster id / count (cluster = 2 CTAs)
 
   if (warp == 0) {
@@ -834,18 +843,22 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
       uint32_t phase = 0;
       for (int unit = unit0; unit < n_units; unit += unit_step) {
         const int m_tile = unit / p.n_tiles, n_tile = unit - m_tile * p.n_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int chain = kb >= kb_per_chain;
-          const int kk = (kb - chain * kb_per_chain) * kBlockK;
+        for (int step = 0; step < n_steps; ++step) {
+          const int chain = step >= steps_per_chain;
+          const int in_chain = step - chain * steps_per_chain;
+          const bool hi_only = in_chain >= kb_per_chain;          // second pass of a corrections-first chain
+          const int kk = (in_chain - (hi_only ? kb_per_chain : 0)) * kBlockK;
           const int a_row = (int)(chain * p.m_rows) + m_tile * 256 + (int)rank * 128;
           const int b_row = chain * p.n_bins_pad + n_tile * F_BLOCK_N + (int)rank * 64;
           mbar_wait(bar_empty(stage), phase ^ 1u, nullptr, 1);
-          if (leader) mbar_expect_tx(bar_full(stage), 2 * P_STAGE_BYTES);
+          if (leader) mbar_expect_tx(bar_full(stage), hi_only ? 2 * (P_A_BYTES + P_B_BYTES) : 2 * P_STAGE_BYTES);
           const uint32_t fb = leader_full0 + 8 * stage;
           tma_load_2d_pair(&tm_a_hi, s_a(stage, 0), fb, kk, a_row);
-          tma_load_2d_pair(&tm_a_lo, s_a(stage, 1), fb, kk, a_row);
           tma_load_2d_pair(&tm_b_hi, s_b(stage, 0), fb, kk, b_row);
-          tma_load_2d_pair(&tm_b_lo, s_b(stage, 1), fb, kk, b_row);
+          if (!hi_only) {
+            tma_load_2d_pair(&tm_a_lo, s_a(stage, 1), fb, kk, a_row);
+            tma_load_2d_pair(&tm_b_lo, s_b(stage, 1), fb, kk, b_row);
+          }
           if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -859,10 +872,12 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
       for (int unit = unit0; unit < n_units; unit += unit_step) {
         mbar_wait(bar_tmem_empty(acc), acc_phase ^ 1u, nullptr, 2);
         tc_fence_after();
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int chain = kb >= kb_per_chain;
+        for (int step = 0; step < n_steps; ++step) {
+          const int chain = step >= steps_per_chain;
+          const int in_chain = step - chain * steps_per_chain;
+          const bool hi_only = in_chain >= kb_per_chain;
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + chain * F_BLOCK_N);
-          const bool first_kb = (kb == 0) || (kb == kb_per_chain);
+          const bool first_kb = in_chain == 0;
           mbar_wait(bar_full(stage), phase, nullptr, 3);
           tc_fence_after();
           const uint64_t da_hi = make_sw128_desc(s_a(stage, 0));
@@ -872,9 +887,11 @@ stft_gemm_fold_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);             // one MMA consumes 32 bytes of the row
-            umma_f16_pair(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
-            umma_f16_pair(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
-            umma_f16_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+            if (!hi_only) {
+              umma_f16_pair(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
+              umma_f16_pair(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+            }
+            if (hi_only || !p.corr_first) umma_f16_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
           }
           umma_commit_pair(bar_empty(stage));       // frees the slot in both CTAs
           if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
@@ -1967,6 +1984,8 @@ static int launch_folded(const char* who, const void* a_hi, const void* a_lo, co
   p.row_scale_inv = row_scale_inv; p.basis_scale_inv = basis_scale_inv;
   p.mel_out = mel ? mel->out : nullptr;
   p.n_mels = mel ? mel->n_mels : 0;
+  static const bool one_pass = getenv("RVB_FOLD_ONE_PASS") != nullptr;    // A/B switch for measurements
+  p.corr_first = one_pass ? 0 : 1;
 
   if constexpr (kF16) {
     static const bool one_cta = getenv("RVB_GEMM_1CTA") != nullptr;       // A/B switch for measurements

@@ -645,10 +645,12 @@ def test_logmel_error_budget_on_hard_signals(R, dev, precision):
     train, noise 80 dB below a tone, near-silence -- and the MIRROR-STRESS family (a chirp to 7.6 kHz, a full-scale
     7 kHz tone alone / over lows 60 dB down, a 500 Hz tone over highs 80 dB down): strong content at the mirror
     frequency N/2 - k of a nearly silent band.
-    precision="strict" (once-folded contraction) meets the budget on ALL of them.  precision="fast" (twice-folded, the
-    default) meets it on everything but the mirror-stress family, where fp32 accumulation of sums that carry the
-    mirror bin's energy leaves ~1e-7 of that bin's amplitude in the weak one: bounded here by 1e-3 (measured <= 8.7e-4;
-    the reference's own default-flag GPU run is at 1.3e-4 .. 5.6e-4 on these signals, profiles/r02_precision.md)."""
+    precision="strict" (once-folded contraction, correction terms accumulated before the leading one) meets the budget
+    on ALL of them (measured <= 3.2e-5; the fp32 numpy oracle and the reference's CPU conv1d are at 4.2e-5 .. 4.7e-5 on
+    the worst one).  precision="fast" (twice-folded, the default) meets it on everything but the mirror-stress family:
+    the tensor core adds into its fp32 accumulator with truncation (profiles/r02_tc_accumulate_probe.txt), which leaves
+    ~1e-7 of the mirror bin's amplitude in the weak one: bounded here by 1e-3 (measured <= 8.7e-4; the reference's own
+    default-flag GPU run is at 1.3e-4 .. 5.6e-4 on these signals, profiles/r02_precision.md)."""
     from oracle.frontend import FrontEndOracle
     n = 64 * 512 + 1
     t = np.arange(n) / 16000.0
