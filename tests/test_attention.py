@@ -175,3 +175,26 @@ def test_attention_projection_paths_agree(monkeypatch):
         res[mode] = (out.detach(), att, xi.grad, m.W_q.weight.grad.clone(), m.W_v.weight.grad.clone(), m.rel.grad.clone())
     for a, b in zip(res["tc"], res["torch"]):
         assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
+
+
+@pytest.mark.gpu
+def test_tf32x3_gemm_equals_the_tensor_core_model_bit_for_bit():
+    """rvb_gemm_nt_tf32x3 (one accumulator per element: k_split = 1) on random split operands against the CPU model of
+    the tensor core's accumulation (oracle/tc_accumulate.py; hh, hl, lh per block of 8 terms): every bit."""
+    from oracle import tc_accumulate as TC
+    from reconvat_b200 import _lib, linear
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    m, n, k = 37, 70, 224
+    x = torch.randn(m, k, generator=g) * torch.exp(2 * torch.randn(m, 1, generator=g))
+    w = torch.randn(n, k, generator=g)
+    xa, wb = linear._split(x.to(dev)), linear._split(w.to(dev))
+    out = torch.empty((m, n), dtype=torch.float32, device=dev)
+    _lib.call("rvb_gemm_nt_tf32x3", xa[0].data_ptr(), xa[1].data_ptr(), m, wb[0].data_ptr(), wb[1].data_ptr(), n, 224,
+              out.data_ptr(), n, 1, 0)
+    torch.cuda.synchronize()
+    f64 = lambda t: t.cpu().numpy().astype(np.float64)
+    want = TC.split_product(f64(xa[0]), f64(xa[1]), f64(wb[0]), f64(wb[1]), k_per_mma=8, order=("hh", "hl", "lh"))
+    assert np.array_equal(out.cpu().numpy(), want.astype(np.float32))
+    exact = (f64(xa[0]) + f64(xa[1])) @ (f64(wb[0]) + f64(wb[1])).T - f64(xa[1]) @ f64(wb[1]).T
+    assert not np.array_equal(out.cpu().numpy(), exact.astype(np.float32))       # round-to-nearest would differ

@@ -694,3 +694,80 @@ def test_logmel_error_budget_on_hard_signals(R, dev, precision):
         finally:
             os.environ.pop("RVB_FUSED_FOLD")
         assert np.array_equal(lm_x, lm)
+
+
+def test_once_folded_contraction_equals_the_tensor_core_model_bit_for_bit(R, dev):
+    """The STFT module's complex output (once-folded 3xFP16 contraction, correction terms first) against the CPU model
+    of the tensor core's arithmetic (oracle/tc_accumulate.py) fed with the operand planes the GPU produced: EVERY bit
+    of re and im.  The contraction kernel is then fully characterised: its distance from float64 is the model's."""
+    from oracle import tc_accumulate as TC
+    from reconvat_b200 import _lib, synth
+    stft = R.Spectrogram.STFT(n_fft=2048, hop_length=512, window='hann', freq_scale='no', center=True,
+                              pad_mode='reflect', sr=16000, trainable=False, output_format='Complex', verbose=False).to(dev)
+    L = 5 * 512
+    a16 = torch.from_numpy(synth.music_int16(L, 5)[None].copy()).to(dev)
+    out = stft(a16).cpu().numpy()                                   # (1, 1025, T, 2) = (re, -im)
+    fd = stft._device_tables()["fold"]
+    assert fd["operand"] == "f16" and fd["w0"] == 0.0
+    mode, n_frames, _ = stft._geometry(L)
+    half, M = 1024, n_frames
+    planes = torch.empty((2, 2, M, half), dtype=torch.float16, device=dev)
+    row_inv = torch.empty((M,), dtype=torch.float32, device=dev)
+    _lib.call("rvb_fold_split_f16_pcm16", _lib.ptr(a16, torch.int16), L, 1.0 / 32768.0, 1, L, stft.pad_amount, mode,
+              2048, 512, n_frames, planes[0].data_ptr(), planes[1].data_ptr(), row_inv.data_ptr(), None)
+    torch.cuda.synchronize()
+    pl = planes.cpu().numpy().astype(np.float64)
+    bh, bl = fd["basis_hi"].cpu().numpy().astype(np.float64), fd["basis_lo"].cpu().numpy().astype(np.float64)
+    ng, nb = fd["n_gemm_bins"], fd["n_bins_pad"]
+    scale = (row_inv.cpu().numpy() * np.float32(fd["scale_inv"]))[:, None]          # powers of two: exact
+    kw = dict(k_per_mma=16, order=("hl", "lh", "hh"), corrections_first=True)       # as stft_gemm_fold_pair_kernel issues them
+    re = TC.split_product(pl[0, 0], pl[1, 0], bh[:ng], bl[:ng], **kw).astype(np.float32) * scale
+    im = TC.split_product(pl[0, 1], pl[1, 1], bh[nb:nb + ng], bl[nb:nb + ng], **kw).astype(np.float32) * scale
+    assert out.shape == (1, 1025, n_frames, 2)
+    assert np.array_equal(out[0, :ng, :, 0].T, re)
+    assert np.array_equal(out[0, :ng, :, 1].T, -im)
+    # and the model is needed: round-to-nearest accumulation of the same planes gives other bits
+    rn = ((pl[0, 0] + pl[1, 0]) @ (bh[:ng] + bl[:ng]).T - pl[1, 0] @ bl[:ng].T).astype(np.float32) * scale
+    assert not np.array_equal(out[0, :ng, :, 0].T, rn)
+
+
+def test_fast_route_error_is_the_tensor_core_models_error(R, dev):
+    """Where the default (twice-folded) route leaves the 1e-4 budget -- a full-scale 7 kHz tone over silence -- its
+    log-Mel is reproduced by the CPU model of the tensor core's truncating accumulation run over the same schedule
+    (four parity chains, hl / lh / hh per 16 terms): the measured error IS the accumulator's, not the operand split's,
+    the epilogue's or the Mel table's."""
+    from oracle import tc_accumulate as TC
+    from oracle.frontend import FrontEndOracle
+    from reconvat_b200 import _lib
+    n = 16 * 512 + 1
+    t = np.arange(n) / 16000.0
+    a16 = np.clip(np.round(0.9 * np.sin(2 * np.pi * 7000.0 * t) * 32768.0), -32768, 32767).astype(np.int16)[None]
+    m = R.Spectrogram.MelSpectrogram(precision="fast", **MEL_KW).to(dev)
+    x = torch.from_numpy(a16).to(dev)
+    lm = torch.log(m(x[:, :-1]) + 1e-5).cpu().numpy()[0]                             # (229, T)
+    ref = FrontEndOracle().log_mel(a16[:, :-1].astype(np.float64) / 32768.0, np.float64)[0]
+    tb = m.stft._device_tables()
+    f2 = tb["fold2"]
+    L = n - 1
+    mode, n_frames, _ = m.stft._geometry(L)
+    planes = torch.empty((2, 2, n_frames, 1024), dtype=torch.float16, device=dev)
+    row_inv = torch.empty((n_frames,), dtype=torch.float32, device=dev)
+    _lib.call("rvb_fold_split2_f16_pcm16", _lib.ptr(x[:, :-1], torch.int16), n, 1.0 / 32768.0, 1, L, m.stft.pad_amount,
+              mode, 2048, 512, n_frames, planes[0].data_ptr(), planes[1].data_ptr(), row_inv.data_ptr())
+    torch.cuda.synchronize()
+    pl = planes.cpu().numpy().astype(np.float64)
+    bh, bl = f2["basis_hi"].cpu().numpy().astype(np.float64), f2["basis_lo"].cpu().numpy().astype(np.float64)
+    nk, q = 512, 512
+    kw = dict(k_per_mma=16, order=("hl", "lh", "hh"))
+    ch = [TC.split_product(pl[0, c >> 1][:, (c & 1) * q:(c & 1) * q + q], pl[1, c >> 1][:, (c & 1) * q:(c & 1) * q + q],
+                           bh[c * nk:(c + 1) * nk], bl[c * nk:(c + 1) * nk], **kw) for c in range(4)]
+    f32 = lambda v: v.astype(np.float32).astype(np.float64)
+    scale = (row_inv.cpu().numpy().astype(np.float64) * f2["scale_inv"])[:, None]
+    P = np.zeros((n_frames, 1025))
+    k = np.arange(1, nk + 1)
+    P[:, k] = (f32(ch[0] + ch[1]) ** 2 + f32(ch[2] + ch[3]) ** 2) * scale ** 2
+    P[:, 1024 - k[:-1]] = ((f32(ch[0] - ch[1]) ** 2 + f32(ch[2] - ch[3]) ** 2) * scale ** 2)[:, :-1]
+    model = np.log(P @ FrontEndOracle().mel_basis.astype(np.float64).T + 1e-5).T
+    err_true, err_model = relerr(lm, ref), relerr(lm, model)
+    assert err_true > 3e-4                                          # the documented excursion is there ...
+    assert err_model < 0.02 * err_true and err_model < 1e-5, (err_true, err_model)   # ... and it is the model's

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small-shape pass over every hot-path kernel, meant to run UNDER compute-sanitizer (tools/sanitize.sh):
 front-end on float and PCM16 input (fold/split or the fused contraction, tcgen05 contraction with the Mel epilogue,
-cluster normalise, two-pass normalise), the VAT kernels through the module (eager and stats flavours), the divergence
+cluster normalise, two-pass normalise; the strict route, the STFT module, the 3xTF32 GEMM), the VAT kernels through the module (eager and stats flavours), the divergence
 kernels, a CUDA-graph capture + replay of the whole step.  ``__graft_entry__.smoke()`` runs first (it checks the
 results against the CPU checker), so a sanitizer run is also a correctness run."""
 import os
@@ -42,6 +42,18 @@ def main():
     spec = torch.log(mel(a_f[:, :-1]) + 1e-5)
     spec = R.utils.Normalization("imagewise").transform(spec).transpose(-1, -2).unsqueeze(1)
     assert float((spec - s_f).abs().max()) < 1e-5
+    # precision="strict": the once-folded CTA-pair contraction (two passes per chain) with the Mel epilogue, the same
+    # kernel with the plain epilogue (STFT module), and the raw 3xTF32 GEMM with and without a split contraction
+    mel_s = R.Spectrogram.MelSpectrogram(sr=16000, win_length=2048, n_mels=229, hop_length=512, fmin=30, fmax=8000,
+                                         verbose=False, precision="strict").to(dev)
+    assert float((mel_s.normalised_log_mel(a_i) - s_i).abs().max()) < 1e-3
+    stft = R.Spectrogram.STFT(n_fft=2048, hop_length=512, sr=16000, output_format="Complex", verbose=False).to(dev)
+    assert bool(torch.isfinite(stft(a_i[:, :8192])).all())
+    from reconvat_b200 import linear
+    xw = torch.randn(700, 229, device=dev, requires_grad=True)
+    ws = [torch.randn(916, 229, device=dev, requires_grad=True) for _ in range(2)]
+    sum(y.square().sum() for y in linear.projections(xw, ws)).backward()
+    assert bool(torch.isfinite(xw.grad).all())
     # VAT flavours
     for conv, cls, kw in (("unet", "UNet_VAT", dict(KL_Div=False)), ("unet_onset", "UNet_VAT_onset", dict(KL_Div=False)),
                           ("stepwise", "stepwise_VAT", dict(KL_Div=True)), ("stepwise", "stepwise_VAT", dict(KL_Div=False, binwise=True))):

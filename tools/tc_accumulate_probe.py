@@ -22,10 +22,13 @@ from reconvat_b200 import _lib  # noqa: E402
 U = 2.0 ** -26
 
 
-def main():
-    dev = torch.device("cuda:0")
+K = 512
+N_TERMS = {"cross": 1, "intra": 1, "intra7": 7, "chain": 63}
+
+
+def problem():
+    """(a (rows, K), b (len(ms), K), rows [(kind, V)], ms): out[i][j] = sum_k a[i][k] b[j][k]."""
     ms = np.arange(-12, 13)
-    K = 512
     kinds = ["cross", "intra", "intra7", "chain"]
     rows = [(kind, v) for kind in kinds for v in (1.0, -1.0)]
     a = np.zeros((len(rows), K), np.float32)
@@ -42,14 +45,30 @@ def main():
     b = np.zeros((len(ms), K), np.float32)
     b[:, 0] = 1.0
     b[:, 1:] = (ms * U)[:, None]
-    n_terms = {"cross": 1, "intra": 1, "intra7": 7, "chain": 63}
+    return a, b, rows, ms
+
+
+def run(dev):
+    """The probe through rvb_gemm_nt_tf32x3 on `dev`: float32 (rows, len(ms))."""
+    a, b, rows, ms = problem()
     ah = torch.from_numpy(a).to(dev); bh = torch.from_numpy(b).to(dev)
     out = torch.empty((len(rows), len(ms)), dtype=torch.float32, device=dev)
     al, bl = torch.zeros_like(ah), torch.zeros_like(bh)
     _lib.call("rvb_gemm_nt_tf32x3", ah.data_ptr(), al.data_ptr(), len(rows), bh.data_ptr(), bl.data_ptr(), len(ms), K,
               out.data_ptr(), out.stride(0), 1, 0)           # k_split = 1: ONE accumulator per element, 64 k-blocks of 8
     torch.cuda.synchronize()
-    res = out.cpu().numpy().astype(np.float64)
+    return out.cpu().numpy()
+
+
+def main():
+    a, b, rows, ms = problem()
+    n_terms = N_TERMS
+    res = run(torch.device("cuda:0")).astype(np.float64)
+    if len(sys.argv) > 1:                                      # golden vector for the CPU model test
+        import json
+        with open(sys.argv[1], "w") as f:
+            json.dump({"rows": [[k, v] for k, v in rows], "m": ms.tolist(),
+                       "result_minus_v_in_units_of_2^-26": ((res - np.array([v for _, v in rows])[:, None]) / U).tolist()}, f)
 
     def grid(x, mode):
         f = np.float32(x)
@@ -67,7 +86,7 @@ def main():
             for mode in ("rn", "rz", "floor"):
                 print("               %-9s: " % mode + " ".join("%4g" % ((grid(v + m * U, mode) - v) / U) for m in ms))
         if kind == "chain":
-            def run(mode):
+            def chain_of(mode):
                 vals = []
                 for m in ms:
                     acc = v
@@ -76,7 +95,7 @@ def main():
                     vals.append((acc - v) / U)
                 return vals
             for mode in ("rn", "rz", "floor"):
-                print("               %-9s: " % mode + " ".join("%4g" % x for x in run(mode)))
+                print("               %-9s: " % mode + " ".join("%4g" % x for x in chain_of(mode)))
 
 
 if __name__ == "__main__":
