@@ -2134,6 +2134,10 @@ extern "C" int rvb_stft_mel_folded2_f16(const void* a_hi, const void* a_lo, cons
     max_clusters = max_clusters_dev[slot][n64];
   }
   const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles * (n64 ? 1 : 2);
+  // RVB_FOLD2_CLUSTERS=<n>: fewer CTA pairs than fit (A/B: the kernel is bound by L2 -> SM operand traffic, not by the
+  // number of tensor pipes, so SMs left free go to the HBM kernels of other streams)
+  static const int cap = [] { const char* e = getenv("RVB_FOLD2_CLUSTERS"); return e ? atoi(e) : 0; }();
+  if (cap > 0 && cap < max_clusters) max_clusters = cap;
   const int n_clusters = (int)(n_units < max_clusters ? n_units : max_clusters);
   static thread_local MelTable tab;
   std::memset(&tab, 0, sizeof(tab));
