@@ -1439,6 +1439,200 @@ stft_gemm_fold2c_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const 
   }
 }
 
+// ---------------------------------------------------------------- K1q with the frame tiles shared across a cluster (K1qm)
+// stft_gemm_fold2c_pair_kernel reads every 128-row frame tile from the L2 once per (k tile): four times per component.
+// Here a cluster holds kPairs CTA pairs that work on the SAME 256 frames and component and on kPairs DIFFERENT k tiles:
+// rank = 2 * pair + half.  The frame tile of the CTAs with the same `half` is the same, so each of them fetches
+// 128 / kPairs of its rows and TMA-multicasts them to all kPairs CTAs of that half: the L2 -> SM traffic of the frame
+// operand drops by kPairs (48 KB -> 16 + 32 / kPairs KB per CTA and stage).  Protocol changes against K1q:
+//   full[s]   (leader of each pair) still one arrive.expect_tx for the pair's 96 KB; the bytes now come from the
+//             pair's own basis loads and from the multicast frame slices of ALL pairs (complete_tx lands on the leader
+//             of every destination pair: mbarrier address with the peer bit cleared, relative to the destination CTA)
+//   empty[s]  (every CTA) kPairs arrivals: the MMA thread of EVERY pair commits to the barrier of EVERY CTA of the
+//             cluster, because any CTA's producer writes into every same-half CTA's stage s
+//   tmem_*    per pair, as in K1q
+__device__ __forceinline__ void tma_load_2d_pair_mc(const CUtensorMap* tm, uint32_t smem_dst, uint32_t bar_local, int c0,
+                                                    int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_local & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mask(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
+
+template <int kStages, int kPairs>
+__global__ void __launch_bounds__(P_NUM_THREADS, 1)
+stft_gemm_fold2c_mc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                           const Fold2Params p, const __grid_constant__ MelTable tab) {
+  constexpr int kSliceRows = 128 / kPairs;
+  constexpr int kSliceBytes = kSliceRows * 128;
+  static_assert(kSliceBytes % 1024 == 0, "a slice must be whole swizzle atoms");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * P_STAGE_BYTES;
+  auto s_a = [&](int s, int lo) { return smem_base + s * P_STAGE_BYTES + lo * P_A_BYTES; };
+  auto s_b = [&](int s, int lo) { return smem_base + s * P_STAGE_BYTES + 2 * P_A_BYTES + lo * P_B_BYTES; };
+  auto bar_full = [&](int s) { return bar_base + 8 * s; };
+  auto bar_empty = [&](int s) { return bar_base + 8 * (kStages + s); };
+  auto bar_tmem_full = [&](int a) { return bar_base + 8 * (2 * kStages + a); };
+  auto bar_tmem_empty = [&](int a) { return bar_base + 8 * (2 * kStages + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8 * (2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t half_id = rank & 1u, pair = rank >> 1;
+  const bool leader = half_id == 0;
+  const uint32_t leader_rank = rank & ~1u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b_hi);
+    tma_prefetch_desc(&tm_b_lo);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), kPairs);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tmem_full(a), 1);
+      mbar_init(bar_tmem_empty(a), 8 * P_EPI_GROUPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                             // every CTA's barriers are initialised before any remote signal
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  constexpr int kBlockK = 2 * BLOCK_K;            // 64 halves per 128-byte swizzle row
+  const int groups_per_comp = p.n_tiles / kPairs; // host: n_tiles % kPairs == 0
+  const int units_per_m = 2 * groups_per_comp;    // (component, group of kPairs k tiles)
+  const int n_units = p.m_tiles * units_per_m;
+  const int kb_per_chain = p.quarter / kBlockK;
+  const int num_kb = 2 * kb_per_chain;            // even-n chain, odd-n chain
+  const int unit0 = (int)(blockIdx.x / (2 * kPairs)), unit_step = (int)(gridDim.x / (2 * kPairs));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t leader_full0 = map_to_rank(bar_full(0), leader_rank);
+      uint16_t same_half = 0;
+#pragma unroll
+      for (int j = 0; j < kPairs; ++j) same_half |= (uint16_t)(1u << (2 * j + (int)half_id));
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
+        const int m_tile = unit / units_per_m, rest = unit - m_tile * units_per_m;
+        const int comp = rest / groups_per_comp, n_tile = (rest - comp * groups_per_comp) * kPairs + (int)pair;
+        const int a_row = (int)(comp * p.m_rows) + m_tile * 256 + (int)half_id * 128 + (int)pair * kSliceRows;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int chain = kb >= kb_per_chain;
+          const int kk = (kb - chain * kb_per_chain) * kBlockK;
+          const int b_row = (2 * comp + chain) * p.n_k + n_tile * F_BLOCK_N + (int)half_id * 64;
+          mbar_wait_cluster(bar_empty(stage), phase ^ 1u, nullptr, 1);
+          if (leader) mbar_expect_tx(bar_full(stage), 2 * P_STAGE_BYTES);
+          const uint32_t fb = leader_full0 + 8 * stage;
+          tma_load_2d_pair_mc(&tm_a_hi, s_a(stage, 0) + pair * kSliceBytes, bar_full(stage), chain * p.quarter + kk, a_row,
+                              same_half);
+          tma_load_2d_pair_mc(&tm_a_lo, s_a(stage, 1) + pair * kSliceBytes, bar_full(stage), chain * p.quarter + kk, a_row,
+                              same_half);
+          tma_load_2d_pair(&tm_b_hi, s_b(stage, 0), fb, kk, b_row);
+          tma_load_2d_pair(&tm_b_lo, s_b(stage, 1), fb, kk, b_row);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(256, F_BLOCK_N, FMT_F16);
+      constexpr uint16_t kAll = (uint16_t)((1u << (2 * kPairs)) - 1u);
+      const uint16_t own_pair = (uint16_t)(3u << leader_rank);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
+        mbar_wait(bar_tmem_empty(acc), acc_phase ^ 1u, nullptr, 2);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int chain = kb >= kb_per_chain;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + chain * F_BLOCK_N);
+          const bool first_kb = (kb == 0) || (kb == kb_per_chain);
+          mbar_wait(bar_full(stage), phase, nullptr, 3);
+          tc_fence_after();
+          const uint64_t da_hi = make_sw128_desc(s_a(stage, 0));
+          const uint64_t da_lo = make_sw128_desc(s_a(stage, 1));
+          const uint64_t db_hi = make_sw128_desc(s_b(stage, 0));
+          const uint64_t db_lo = make_sw128_desc(s_b(stage, 1));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);             // one MMA consumes 32 bytes of the row
+            umma_f16_pair(d_tmem, da_hi + adv, db_lo + adv, idesc, (first_kb && k == 0) ? 0u : 1u);
+            umma_f16_pair(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+            umma_f16_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+          }
+          umma_commit_mask(bar_empty(stage), kAll);          // this pair is done with stage s: tell every producer
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_mask(bar_tmem_full(acc), own_pair);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int group = (warp - EPI_WARP0) >> 2;      // 0 .. 3
+    const int stream = group >> 1, hhalf = group & 1;
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const uint32_t leader_tmem_empty0 = map_to_rank(bar_tmem_empty(0), leader_rank);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = unit0; unit < n_units; unit += unit_step) {
+      const int m_tile = unit / units_per_m, rest = unit - m_tile * units_per_m;
+      const int comp = rest / groups_per_comp, n_tile = (rest - comp * groups_per_comp) * kPairs + (int)pair;
+      const int64_t f = (int64_t)m_tile * 256 + (int64_t)half_id * 128 + row;    // flattened frame index
+      const bool f_ok = f < p.m_rows;
+      const int b = f_ok ? (int)(f / p.n_frames) : 0;
+      const int t = f_ok ? (int)(f - (int64_t)b * p.n_frames) : 0;
+      const float scale = f_ok ? __ldg(p.row_scale_inv + f) * p.basis_scale_inv : 1.f;
+      float* col = p.mel_out + comp * p.plane_stride + (int64_t)b * p.n_mels * p.n_frames + t;
+      const float4* tt = tab.e + stream * p.n_k + n_tile * F_BLOCK_N + hhalf * C_CHUNK;
+      mbar_wait(bar_tmem_full(acc), acc_phase, nullptr, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + hhalf * C_CHUNK);
+      mel2c_unit(p, taddr, tt, stream, col, f_ok, scale);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                             // peers may still be writing our smem / signalling our barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- twice-folded kernel with the fold done IN the kernel (K1x)
 // K1q re-reads 168 MB of materialised frame planes (every sample stored 4 times as fp16 hi/lo of e and o) that K0q
 // has to write first.  Here the A operand is produced on the fly: eight CONVERTER warps per CTA read the raw padded
@@ -2132,6 +2326,46 @@ extern "C" int rvb_stft_mel_folded2_f16(const void* a_hi, const void* a_lo, cons
       max_clusters_dev[slot][n64] = nc < sms / 2 ? nc : sms / 2;
     }
     max_clusters = max_clusters_dev[slot][n64];
+  }
+  // RVB_FOLD2_MC=<2|4>: K1qm, <n> CTA pairs per cluster share the frame tiles through TMA multicast
+  const int mc_pairs = [] { const char* e = getenv("RVB_FOLD2_MC"); return e ? atoi(e) : 0; }();   // read per launch (tests)
+  if (!n64 && !three && (mc_pairs == 2 || mc_pairs == 4) && p.n_tiles % mc_pairs == 0) {
+    const uint32_t slice_rows = 128 / mc_pairs;
+    if ((rc = make_map_2d(&tm_a_hi, a_hi, half, 2 * m_rows, 64, slice_rows, 2)) != RVB_OK) return rc;
+    if ((rc = make_map_2d(&tm_a_lo, a_lo, half, 2 * m_rows, 64, slice_rows, 2)) != RVB_OK) return rc;
+    auto mc_kernel = mc_pairs == 4 ? stft_gemm_fold2c_mc_kernel<P_STAGES, 4> : stft_gemm_fold2c_mc_kernel<P_STAGES, 2>;
+    static int mc_clusters_dev[kMaxDevices][2] = {};
+    const int slot2 = device_slot();
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2 * mc_pairs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(P_NUM_THREADS); cfg.dynamicSmemBytes = P_SMEM_BYTES; cfg.stream = (cudaStream_t)stream;
+    int mc_clusters;
+    {
+      std::lock_guard<std::mutex> g(attr_mutex());
+      if (mc_clusters_dev[slot2][mc_pairs == 4] == 0) {
+        RVB_CUDA(cudaFuncSetAttribute(mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+        cfg.gridDim = dim3((sms / (2 * mc_pairs)) * 2 * mc_pairs);   // (num_sms() takes attr_mutex itself)
+        int nc = 0;
+        RVB_CUDA(cudaOccupancyMaxActiveClusters(&nc, mc_kernel, &cfg));
+        RVB_REQUIRE(nc > 0, "%s: no cluster of %d CTAs fits on this device", who, 2 * mc_pairs);
+        mc_clusters_dev[slot2][mc_pairs == 4] = nc;
+      }
+      mc_clusters = mc_clusters_dev[slot2][mc_pairs == 4];
+    }
+    static const int mc_cap = [] { const char* e = getenv("RVB_FOLD2_CLUSTERS"); return e ? atoi(e) : 0; }();
+    if (mc_cap > 0 && mc_cap < mc_clusters) mc_clusters = mc_cap;
+    const int64_t g_units = (int64_t)p.m_tiles * 2 * (p.n_tiles / mc_pairs);
+    const int n_cl = (int)(g_units < mc_clusters ? g_units : mc_clusters);
+    static thread_local MelTable mtab;
+    std::memset(&mtab, 0, sizeof(mtab));
+    std::memcpy(mtab.e, mel_tab, sizeof(float4) * (size_t)(2 * quarter));
+    cfg.gridDim = dim3(n_cl * 2 * mc_pairs);
+    RVB_CUDA(cudaLaunchKernelEx(&cfg, mc_kernel, tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p, mtab));
+    count_launch();
+    return check_launch("stft_gemm_fold2c_mc_kernel");
   }
   const int64_t n_units = (int64_t)p.m_tiles * p.n_tiles * (n64 ? 1 : 2);
   // RVB_FOLD2_CLUSTERS=<n>: fewer CTA pairs than fit (A/B: the kernel is bound by L2 -> SM operand traffic, not by the

@@ -771,3 +771,19 @@ def test_fast_route_error_is_the_tensor_core_models_error(R, dev):
     err_true, err_model = relerr(lm, ref), relerr(lm, model)
     assert err_true > 3e-4                                          # the documented excursion is there ...
     assert err_model < 0.02 * err_true and err_model < 1e-5, (err_true, err_model)   # ... and it is the model's
+
+
+@pytest.mark.parametrize("pairs", [2, 4])
+def test_multicast_cluster_contraction_is_bit_identical(R, dev, monkeypatch, pairs):
+    """RVB_FOLD2_MC: the twice-folded contraction with the frame tiles TMA-multicast across a cluster of 2 / 4 CTA pairs
+    (stft_gemm_fold2c_mc_kernel; an A/B variant, slower on B200 -- profiles/r02_experiments.md) gives the default
+    kernel's bits, ragged last tile included."""
+    from reconvat_b200 import synth
+    a16 = torch.from_numpy(np.stack([synth.music_int16(40 * 512 + 1, 70 + b) for b in range(3)])).to(dev)
+    m = R.Spectrogram.MelSpectrogram(**MEL_KW).to(dev)
+    want = m(a16[:, :-1])
+    n0 = R._lib.launch_count()
+    monkeypatch.setenv("RVB_FOLD2_MC", str(pairs))
+    got = m(a16[:, :-1])
+    torch.cuda.synchronize()
+    assert R._lib.launch_count() > n0 and torch.equal(got, want)
