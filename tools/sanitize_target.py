@@ -37,6 +37,11 @@ def main():
     s_x = mel.normalised_log_mel(a_i)
     os.environ.pop("RVB_FUSED_FOLD")
     assert float((s_x - s_i).abs().max()) < 1e-5, "fused-fold path differs"
+    for pairs in ("2", "4"):                                # K1qm: frame tiles multicast across a cluster
+        os.environ["RVB_FOLD2_MC"] = pairs
+        s_m = mel.normalised_log_mel(a_i)
+        os.environ.pop("RVB_FOLD2_MC")
+        assert torch.equal(s_m, s_i), "multicast contraction differs"
     assert bool(torch.isfinite(s_f).all()) and float(s_f.min()) == 0.0 and float(s_f.max()) == 1.0
     # module surface (forward -> log -> Normalization) = the two-pass kernels
     spec = torch.log(mel(a_f[:, :-1]) + 1e-5)
