@@ -787,3 +787,73 @@ def test_multicast_cluster_contraction_is_bit_identical(R, dev, monkeypatch, pai
     got = m(a16[:, :-1])
     torch.cuda.synchronize()
     assert R._lib.launch_count() > n0 and torch.equal(got, want)
+
+
+def test_headline_contraction_equals_its_cpu_model_bit_for_bit(R, dev):
+    """The DEFAULT route's kernel (twice-folded 3xFP16 contraction + Mel epilogue, rvb_stft_mel_folded2_f16), both Mel
+    planes, against a CPU emulation made of (1) the tensor-core accumulation model over the GPU's operand planes --
+    four parity chains, hl / lh / hh per 16 terms -- and (2) the epilogue's fp32 operation sequence: r = fma(+-1, O, E),
+    v = r r, the two rotating band accumulators fed by fma over 64-row chunks, flush = acc * scale^2, at most two
+    partial sums per plane element.  Every bit: nothing in the kernel's arithmetic is left unexplained."""
+    from oracle import tc_accumulate as TC
+    from reconvat_b200 import _lib, basis, synth
+    L = 5 * 512
+    a16 = torch.from_numpy(synth.music_int16(L + 1, 21)[None].copy()).to(dev)
+    m = R.Spectrogram.MelSpectrogram(precision="fast", **MEL_KW).to(dev)
+    x = a16[:, :-1]
+    mel_c, mel_s, T = m._mel_fused(basis.broadcast_dim(x), m._fused_table())
+    assert mel_s is not None
+    got = torch.stack([mel_c, mel_s]).cpu().numpy()[:, 0]                              # (2, n_mels, T)
+    f2 = m.stft._device_tables()["fold2"]
+    tab = m._fused2_table()
+    mode, n_frames, _ = m.stft._geometry(L)
+    assert n_frames == T
+    planes = torch.empty((2, 2, T, 1024), dtype=torch.float16, device=dev)
+    row_inv = torch.empty((T,), dtype=torch.float32, device=dev)
+    _lib.call("rvb_fold_split2_f16_pcm16", _lib.ptr(x, torch.int16), L + 1, 1.0 / 32768.0, 1, L, m.stft.pad_amount,
+              mode, 2048, 512, T, planes[0].data_ptr(), planes[1].data_ptr(), row_inv.data_ptr())
+    torch.cuda.synchronize()
+    pl = planes.cpu().numpy().astype(np.float64)
+    bh, bl = f2["basis_hi"].cpu().numpy().astype(np.float64), f2["basis_lo"].cpu().numpy().astype(np.float64)
+    nk, n_mels = 512, 229
+    ch = [TC.split_product(pl[0, c >> 1][:, (c & 1) * nk:(c & 1) * nk + nk], pl[1, c >> 1][:, (c & 1) * nk:(c & 1) * nk + nk],
+                           bh[c * nk:(c + 1) * nk], bl[c * nk:(c + 1) * nk], k_per_mma=16, order=("hl", "lh", "hh"))
+          for c in range(4)]
+    f32 = lambda v: np.asarray(v, dtype=np.float64).astype(np.float32).astype(np.float64)
+    scale = row_inv.cpu().numpy() * np.float32(f2["scale_inv"])
+    scale2 = (scale * scale).astype(np.float64)                                        # powers of two: exact
+    band_of = tab[:, 2].copy().view(np.int32)
+    partial = [[[[] for _ in range(T)] for _ in range(n_mels)] for _ in range(2)]
+
+    def flush(comp, stream, b0, acc):
+        if 0 <= b0 < n_mels:
+            out = f32(acc * scale2)
+            band = n_mels - 1 - b0 if stream else b0
+            for t in range(T):
+                if out[t] != 0.0:
+                    partial[comp][band][t].append(out[t])
+
+    for comp in range(2):
+        ev, od = ch[2 * comp], ch[2 * comp + 1]
+        for stream in range(2):
+            sgn = -1.0 if stream else 1.0
+            for kk0 in range(0, nk, 64):
+                b0, acc0, acc1 = int(band_of[stream * nk + kk0]), np.zeros(T), np.zeros(T)
+                for kk in range(kk0, kk0 + 64):
+                    w0, w1 = float(tab[stream * nk + kk, 0]), float(tab[stream * nk + kk, 1])
+                    r = f32(ev[:, kk] + sgn * od[:, kk])
+                    v = f32(r * r)
+                    while b0 < int(band_of[stream * nk + kk]):
+                        flush(comp, stream, b0, acc0)
+                        acc0, acc1, b0 = acc1, np.zeros(T), b0 + 1
+                    acc0, acc1 = f32(w0 * v + acc0), f32(w1 * v + acc1)
+                flush(comp, stream, b0, acc0)
+                flush(comp, stream, b0 + 1, acc1)
+    want = np.zeros((2, n_mels, T), np.float32)
+    for comp in range(2):
+        for band in range(n_mels):
+            for t in range(T):
+                ps = partial[comp][band][t]
+                assert len(ps) <= 2
+                want[comp, band, t] = np.float32(sum(ps)) if ps else 0.0
+    assert np.array_equal(got, want), (int((got != want).sum()), got.size)
