@@ -709,6 +709,84 @@ def run_transcribe(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_train_step(args, rank, local_rank, world):
+    """--workload train_step (the CALLER's step, SURVEY.md 8f rows f2 / f4 -- context for the hot-path numbers, not the
+    headline): the reference's own ``UNet`` (oracle/_ref snapshot, random init) through one iteration of
+    ``train_VAT_model`` (model/helper_functions.py:570-615: run_on_batch with VAT on a labelled + an unlabelled batch
+    of --batch segments each, backward, Adam step), three ways on the same GPU: the unmodified reference, the same
+    scripts behind ``reconvat_b200.install()`` (hot path only), and behind ``install(attention=True)`` (plus the
+    caller-side attention kernels).  One rank (the reference's scripts are single-GPU)."""
+    import numpy as np
+    import torch
+    if rank != 0:
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    from oracle import reference_loader as RL
+    from reconvat_b200 import synth
+    if not RL.available():
+        print(json.dumps({"workload": "train_step", "unavailable": "no reference snapshot (oracle/_ref) on this box"}))
+        return
+    B = args.batch if args.batch != 32 else 8                                   # train_UNet_VAT.py: batch_size = 8
+    frames = 640
+    L = frames * 512
+
+    def batch(seed):
+        audio = np.stack([(synth.music_int16 if (b & 1) else synth.white_int16)(L, seed * 100 + b) for b in range(B)])
+        g = torch.Generator().manual_seed(seed)
+        return {"audio": torch.from_numpy(synth.to_float(audio)).to(dev),
+                "onset": (torch.rand(B, frames, 88, generator=g) > 0.99).float().to(dev),
+                "frame": (torch.rand(B, frames, 88, generator=g) > 0.95).float().to(dev)}
+    batches = [(batch(2 * i + 1), batch(2 * i + 2)) for i in range(3)]
+    arms = (("reference", lambda: RL.load_reference()),
+            ("install()", lambda: RL.load_patched()),
+            ("install(attention=True)", lambda: RL.load_patched(attention=True)))
+    res = {}
+    steps, warm = (args.steps if args.steps != 200 else 10), max(2, min(args.warmup, 3))
+    for name, load in arms:
+        ns = load()
+        torch.manual_seed(0)
+        model = ns.self_attention_VAT.UNet((2, 2), (2, 2), log=True, reconstruction=True, mode="imagewise", spec="Mel",
+                                           XI=1e-6, eps=2).to(dev)                 # train_UNet_VAT.py:126
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), 1e-3)
+
+        def one(i):
+            opt.zero_grad()
+            bl, bu = batches[i % len(batches)]
+            _, losses, _ = model.run_on_batch(bl, bu, True)
+            loss = 0
+            for k, v in losses.items():
+                loss = loss + (v / 2 if k.startswith("loss/train_LDS") else v)
+            loss.backward()
+            opt.step()
+            return loss
+        for i in range(warm):
+            last = one(i)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.reset_peak_memory_stats()
+        ev0.record()
+        for i in range(steps):
+            last = one(i)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / steps
+        assert bool(torch.isfinite(last))
+        res[name] = {"ms_per_step": ms, "value": 2 * B * SEG_SECONDS / (ms * 1e-3), "unit": "audio-s/s",
+                     "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        del model, opt
+        torch.cuda.empty_cache()
+    line = {"metric": "audio-sec/s", "workload": "train_step", "n_gpus": 1, "steps": steps, "warmup": warm,
+            "higher_is_better": True, "data": "synthetic",
+            "config": {"workload": "the reference's UNet (random init, train mode), one train_VAT_model iteration: "
+                                   "run_on_batch(labelled B=%d, unlabelled B=%d, VAT=True) + backward + Adam step; "
+                                   "PyTorch default flags" % (B, B)},
+            "value": res["install(attention=True)"]["value"], "unit": "audio-s/s",
+            "ms_per_step": res["install(attention=True)"]["ms_per_step"], "arms": res}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -733,7 +811,7 @@ def main():
     ap.add_argument("--model", default="injected", choices=["injected", "standin", "unet"],
                     help="the black-box network the VAT loop calls (see make_model); 'unet': the reference's UNet from the "
                          "oracle/_ref snapshot (--workload transcribe only)")
-    ap.add_argument("--workload", default="step", choices=["step", "transcribe"],
+    ap.add_argument("--workload", default="step", choices=["step", "transcribe", "train_step"],
                     help="step: the Mel+VAT training step (BASELINE metric); transcribe: whole-file inference (config 5)")
     ap.add_argument("--file-seconds", type=int, default=3600, help="--workload transcribe: length of the file")
     args = ap.parse_args()
@@ -753,6 +831,8 @@ def main():
         if args.steps == 200:
             args.steps = 5
         run_transcribe(args, rank, local_rank, world)
+    elif args.workload == "train_step":
+        run_train_step(args, rank, local_rank, world)
     else:
         if args.model == "unet":
             raise SystemExit("bench.py: --model unet belongs to --workload transcribe")
