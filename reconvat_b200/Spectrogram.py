@@ -319,14 +319,16 @@ class MelSpectrogram(nn.Module):
     ``precision`` (extension; default ``$RVB_PRECISION`` or ``"fast"``) picks the contraction:
 
     * ``"fast"``: the TWICE-folded contraction -- bins k and N/2-k from the parity-split sums Ce +- Co, a quarter of
-      the dense contraction's multiply-adds.  The partial sums carry the energy of BOTH bins and are accumulated in
-      fp32 (TMEM), so a bin inherits an absolute error of ~1e-7 of the amplitude of its mirror bin N/2-k (-140 dB).
-      On white, music-like and PCM-quantised input (the BASELINE signals) log-Mel stays within 4.3e-5 of float64; a
-      band that lies more than ~75 dB below the content at its mirror frequency (a full-scale 7 kHz tone over silent
-      low bands) can miss the 1e-4 budget by up to 9x -- still closer to the truth than the reference's own GPU run with
-      PyTorch's default ``cudnn.allow_tf32=True`` (1.3e-4 .. 5.6e-4 on the same signals, profiles/r02_precision.md).
-    * ``"strict"``: the once-folded contraction (every bin accumulated on its own, twice the multiply-adds): <= 2.8e-5
-      on every stress signal, the accuracy class of the reference's fp32 path.
+      the dense contraction's multiply-adds.  The partial sums carry the energy of BOTH bins, and the tensor core adds
+      into its fp32 accumulator (TMEM) with truncation, not rounding: a bin inherits an absolute
+      error of ~1e-7 of the amplitude of its mirror bin N/2-k (-140 dB).  On white, music-like and PCM-quantised input
+      (the BASELINE signals) log-Mel stays within 4.3e-5 of float64; a band that lies more than ~75 dB below the content
+      at its mirror frequency (a full-scale 7 kHz tone over silent low bands) can miss the 1e-4 budget by up to 9x --
+      still closer to the truth than the reference's own GPU run with PyTorch's default ``cudnn.allow_tf32=True``
+      (1.3e-4 .. 5.6e-4 on the same signals, profiles/r02_precision.md).
+    * ``"strict"``: the once-folded contraction (every bin accumulated on its own, twice the multiply-adds, the split
+      product's small terms accumulated before the leading one): <= 3.2e-5 on every stress signal, the accuracy class
+      of the reference's fp32 path, at about twice the front-end time.
     """
 
     def __init__(self, sr=22050, n_fft=2048, n_mels=128, hop_length=512,
