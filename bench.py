@@ -714,8 +714,8 @@ def run_train_step(args, rank, local_rank, world):
     headline): the reference's own ``UNet`` (oracle/_ref snapshot, random init) through one iteration of
     ``train_VAT_model`` (model/helper_functions.py:570-615: run_on_batch with VAT on a labelled + an unlabelled batch
     of --batch segments each, backward, Adam step), three ways on the same GPU: the unmodified reference, the same
-    scripts behind ``reconvat_b200.install()`` (hot path only), and behind ``install(attention=True)`` (plus the
-    caller-side attention kernels).  One rank (the reference's scripts are single-GPU)."""
+    scripts behind ``reconvat_b200.install()`` (hot path only), behind ``install(attention=True)`` (plus the caller-side
+    attention kernels) and behind ``install(attention=True, batchnorm=True)`` (plus the U-Net's BatchNorm2d).  One rank (the reference's scripts are single-GPU)."""
     import numpy as np
     import torch
     if rank != 0:
@@ -740,7 +740,8 @@ def run_train_step(args, rank, local_rank, world):
     batches = [(batch(2 * i + 1), batch(2 * i + 2)) for i in range(3)]
     arms = (("reference", lambda: RL.load_reference()),
             ("install()", lambda: RL.load_patched()),
-            ("install(attention=True)", lambda: RL.load_patched(attention=True)))
+            ("install(attention=True)", lambda: RL.load_patched(attention=True)),
+            ("install(attention=True, batchnorm=True)", lambda: RL.load_patched(attention=True, batchnorm=True)))
     res = {}
     steps, warm = (args.steps if args.steps != 200 else 10), max(2, min(args.warmup, 3))
     for name, load in arms:
@@ -782,8 +783,8 @@ def run_train_step(args, rank, local_rank, world):
             "config": {"workload": "the reference's UNet (random init, train mode), one train_VAT_model iteration: "
                                    "run_on_batch(labelled B=%d, unlabelled B=%d, VAT=True) + backward + Adam step; "
                                    "PyTorch default flags" % (B, B)},
-            "value": res["install(attention=True)"]["value"], "unit": "audio-s/s",
-            "ms_per_step": res["install(attention=True)"]["ms_per_step"], "arms": res}
+            "value": res["install(attention=True, batchnorm=True)"]["value"], "unit": "audio-s/s",
+            "ms_per_step": res["install(attention=True, batchnorm=True)"]["ms_per_step"], "arms": res}
     print(json.dumps(line), flush=True)
 
 

@@ -134,7 +134,8 @@ int rvb_stft_bin_folded(const float* a_hi, const float* a_lo, int n_seg, int n_f
  * Accumulation order (rvb_stft_gemm_folded_f16, rvb_stft_mel_folded_f16): hi*lo + lo*hi over the WHOLE contraction
  * first, hi*hi on top -- tcgen05.mma truncates when it adds into the fp32 accumulator, and this order keeps two of
  * the three truncations per 16 terms away from the large partial sums (log-Mel <= 3.2e-5 of float64 on every stress
- * signal).  The results are bit-identical to oracle/tc_accumulate.py run over the same planes.
+ * signal).  The results are bit-identical to the CPU model of the tensor core's accumulation
+ * (tests/test_gpu_frontend.py) run over the same planes.
  */
 int rvb_fold_split_f16(const float* audio, int64_t audio_ld, int n_seg, int n_samples, int pad, int pad_mode,
                        int n_fft, int hop, int n_frames, void* a_hi, void* a_lo, float* row_scale_inv, float* p0,
@@ -441,6 +442,34 @@ int rvb_local_attn_bwd_kv(const float* q, const float* dout, const float* att, c
  */
 int rvb_note_offsets(const float* onsets, const float* frames, int n_frames, int n_pitches, float onset_threshold,
                      float frame_threshold, int rule1, uint8_t* start, int32_t* offset, rvb_stream_t stream);
+
+/*
+ * B1-B4  nn.BatchNorm2d of the caller's U-Net (model/self_attention_VAT.py:848-850, :865-869; the same blocks in
+ * model/UNet_onset.py:190-211), fp32 NCHW, forward and backward (consumer side of the hot path).  Replaces
+ * aten::cudnn_batch_norm / aten::cudnn_batch_norm_backward (train) and the eval-mode native_batch_norm.
+ *   x, y, dy, dx   [n][c][hw] contiguous
+ *   splits         slices per channel, from rvb_bn_splits(n, c, hw) (the same value in the calls of one pass)
+ *   partials       float64 [c][splits][2] workspace
+ *   rvb_bn_reduce    dy == NULL: partial sums of (x - K), (x - K)^2 with K = x[0][ch][0] (shifted: no cancellation);
+ *                    else partial sums of dy, dy (x - mean[ch])
+ *   rvb_bn_forward   mean, biased variance from the partials; y = (x - mean) / sqrt(var + eps) * gamma + beta;
+ *                    save_mean / save_invstd for the backward; running_mean / running_var (NULL: not tracked) updated
+ *                    with `momentum` and the UNBIASED variance, as nn.BatchNorm2d does.  gamma / beta NULL: 1 / 0
+ *   rvb_bn_apply     eval mode: the same formula with the given mean / invstd
+ *   rvb_bn_backward  training: dx = (dy - mean(dy) - xhat mean(dy xhat)) invstd gamma; eval (training = 0):
+ *                    dx = dy invstd gamma; dgamma = sum(dy xhat), dbeta = sum(dy); any of dx / dgamma / dbeta may be NULL
+ */
+int rvb_bn_splits(int n, int c, int64_t hw);
+int rvb_bn_reduce(const float* x, const float* dy, const float* mean, int n, int c, int64_t hw, int splits,
+                  double* partials, rvb_stream_t stream);
+int rvb_bn_forward(const float* x, int n, int c, int64_t hw, int splits, const double* partials, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                   float* save_mean, float* save_invstd, float* y, rvb_stream_t stream);
+int rvb_bn_apply(const float* x, int n, int c, int64_t hw, const float* mean, const float* invstd, const float* gamma,
+                 const float* beta, float* y, rvb_stream_t stream);
+int rvb_bn_backward(const float* x, const float* dy, int n, int c, int64_t hw, int splits, const double* partials,
+                    const float* gamma, const float* mean, const float* invstd, int training, float* dx, float* dgamma,
+                    float* dbeta, rvb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -113,13 +113,13 @@ _MODEL_MODULES = ("constants", "utils", "VAT", "self_attention_VAT", "UNet_onset
 _patched = {}
 
 
-def load_patched(attention=False, decoding=False):
+def load_patched(attention=False, decoding=False, batchnorm=False):
     """The same UNMODIFIED reference modules, imported a second time behind the product's seams: the package
     ``reconvat_b200`` registered as ``nnAudio`` before the import and ``reconvat_b200.install()`` rebinding the VAT
     classes / Normalization afterwards -- what a user's ``sitecustomize`` does.  Returns a namespace
     like :func:`load_reference`, whose ``UNet`` / ``UNet_Onset`` / ``OnsetsAndFrames_VAT_full`` then run on librvb.so.
     The module objects are distinct from the unpatched ones, so both flavours can live in one process."""
-    key = (bool(attention), bool(decoding))
+    key = (bool(attention), bool(decoding), bool(batchnorm))
     if key in _patched:
         return _patched[key]
     if not available():
@@ -148,7 +148,7 @@ def load_patched(attention=False, decoding=False):
         reconvat_b200.install_nnaudio()                           # seam 1: before `import model`
         for name in _MODEL_MODULES:
             setattr(ns, name, importlib.import_module("model." + name))
-        ns.rebound = reconvat_b200.patch_reference(attention=attention, decoding=decoding)   # seam 2: after it
+        ns.rebound = reconvat_b200.patch_reference(attention=attention, decoding=decoding, batchnorm=batchnorm)   # seam 2
         ns.Spectrogram = reconvat_b200.Spectrogram
     finally:
         ns._mods = {k: sys.modules.pop(k) for k in [k for k in sys.modules if k.startswith("model.")]}

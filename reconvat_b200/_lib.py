@@ -63,6 +63,10 @@ SIGNATURES = {
     "rvb_vat_finalize_stats": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i64, _i32, _f32, _f32, _f32, _i32, _c_p, _c_p, _c_p,
                                _i64, _c_p],
     "rvb_bce_mean": [_c_p, _c_p, _i64, _c_p, _c_p, _c_p],
+    "rvb_bn_reduce": [_c_p, _c_p, _c_p, _i32, _i32, _i64, _i32, _c_p, _c_p],
+    "rvb_bn_forward": [_c_p, _i32, _i32, _i64, _i32, _c_p, _c_p, _c_p, _f32, _f32, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p],
+    "rvb_bn_apply": [_c_p, _i32, _i32, _i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p],
+    "rvb_bn_backward": [_c_p, _c_p, _i32, _i32, _i64, _i32, _c_p, _c_p, _c_p, _c_p, _i32, _c_p, _c_p, _c_p, _c_p],
 }
 ABI_VERSION = 1
 BCE_WORKSPACE_FLOATS = 1032
@@ -97,6 +101,8 @@ def load():
     lib.rvb_vat_stats_workspace_bytes.argtypes = [_i64]
     lib.rvb_parity_plane_len.restype = ctypes.c_int64
     lib.rvb_parity_plane_len.argtypes = [_i32, _i32, _i32, _i32, _i32, _i32]
+    lib.rvb_bn_splits.restype = ctypes.c_int
+    lib.rvb_bn_splits.argtypes = [_i32, _i32, _i64]
     if lib.rvb_abi_version() != ABI_VERSION:
         raise ImportError("reconvat_b200: librvb.so has ABI %d, the Python side expects %d -- rebuild"
                           % (lib.rvb_abi_version(), ABI_VERSION))
@@ -115,6 +121,10 @@ def launch_count():
 
 def parity_plane_len(n_samples, pad, pad_mode, n_fft, hop, n_frames):
     return int(load().rvb_parity_plane_len(int(n_samples), int(pad), int(pad_mode), int(n_fft), int(hop), int(n_frames)))
+
+
+def bn_splits(n, c, hw):
+    return int(load().rvb_bn_splits(int(n), int(c), int(hw)))
 
 
 def vat_stats_workspace_bytes(n_rows):

@@ -1,0 +1,120 @@
+"""``nn.BatchNorm2d`` of the caller's U-Net on hand-written kernels (consumer side of the hot path).
+
+The reference puts an ``nn.BatchNorm2d(C)`` with C = 16 .. 128 behind every convolution of its two U-Nets
+(model/self_attention_VAT.py:848-850, :865-869; model/UNet_onset.py:190-211): 30 modules, three forward and two backward
+passes per training iteration.  cuDNN runs that layout with one block per channel; on a B200 the two kernels take half of
+the iteration (profiles/r02_train_step.md).  :class:`BatchNorm2d` is the same module -- same constructor, parameters,
+buffers (``state_dict`` interchange), train / eval semantics, running-statistics update -- over ``rvb_bn_*``: every
+channel cut into slices so that the whole chip works on it, two launches per direction, float64 partial sums.
+
+``convert(model)`` swaps the class of every ``nn.BatchNorm2d`` in place (parameters untouched);
+``install(batchnorm=True)`` makes the reference's model files construct this class without editing them.
+There is no CPU path: a CPU tensor raises.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+__all__ = ["BatchNorm2d", "convert", "batch_norm"]
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class _BatchNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps):
+        x = x.contiguous()
+        n, c = x.shape[0], x.shape[1]
+        hw = x.numel() // (n * c)
+        y = torch.empty_like(x)
+        if training:
+            if n * hw <= 1:
+                raise ValueError("Expected more than 1 value per channel when training, got input size %s" % (tuple(x.shape),))
+            splits = _lib.bn_splits(n, c, hw)
+            partials = torch.empty((c, splits, 2), dtype=torch.float64, device=x.device)
+            mean = torch.empty((c,), dtype=torch.float32, device=x.device)
+            invstd = torch.empty((c,), dtype=torch.float32, device=x.device)
+            _lib.call("rvb_bn_reduce", x.data_ptr(), None, None, n, c, hw, splits, partials.data_ptr())
+            _lib.call("rvb_bn_forward", x.data_ptr(), n, c, hw, splits, partials.data_ptr(), _ptr(weight), _ptr(bias),
+                      float(eps), float(momentum), _ptr(running_mean), _ptr(running_var), mean.data_ptr(),
+                      invstd.data_ptr(), y.data_ptr())
+        else:
+            mean = running_mean
+            invstd = torch.rsqrt(running_var + eps)
+            _lib.call("rvb_bn_apply", x.data_ptr(), n, c, hw, mean.data_ptr(), invstd.data_ptr(), _ptr(weight), _ptr(bias),
+                      y.data_ptr())
+        ctx.save_for_backward(x, weight, mean, invstd)
+        ctx.training = training
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, invstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        n, c = x.shape[0], x.shape[1]
+        hw = x.numel() // (n * c)
+        need_x, need_w, need_b = ctx.needs_input_grad[0], weight is not None and ctx.needs_input_grad[1], \
+            ctx.has_bias and ctx.needs_input_grad[2]
+        if not (need_x or need_w or need_b):
+            return (None,) * 8
+        splits = _lib.bn_splits(n, c, hw)
+        partials = torch.empty((c, splits, 2), dtype=torch.float64, device=x.device)
+        dx = torch.empty_like(x) if need_x else None
+        dgamma = torch.empty((c,), dtype=torch.float32, device=x.device) if need_w else None
+        dbeta = torch.empty((c,), dtype=torch.float32, device=x.device) if need_b else None
+        _lib.call("rvb_bn_reduce", x.data_ptr(), dy.data_ptr(), mean.data_ptr(), n, c, hw, splits, partials.data_ptr())
+        _lib.call("rvb_bn_backward", x.data_ptr(), dy.data_ptr(), n, c, hw, splits, partials.data_ptr(), _ptr(weight),
+                  mean.data_ptr(), invstd.data_ptr(), int(ctx.training), _ptr(dx), _ptr(dgamma), _ptr(dbeta))
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+def batch_norm(x, running_mean, running_var, weight=None, bias=None, training=False, momentum=0.1, eps=1e-5):
+    """``F.batch_norm`` for (N, C, ...) float32 CUDA tensors."""
+    for t in (x, weight, bias, running_mean, running_var):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise _lib.RvbError("reconvat_b200 batch_norm needs CUDA float32 tensors (got %s, %s); there is no CPU path"
+                                % (t.device, t.dtype))
+    if not training and (running_mean is None or running_var is None):
+        raise ValueError("batch_norm in eval mode needs running_mean and running_var")
+    return _BatchNormFn.apply(x, weight, bias, running_mean, running_var, bool(training), momentum, eps)
+
+
+class BatchNorm2d(nn.BatchNorm2d):
+    """torch.nn.BatchNorm2d (as used by model/self_attention_VAT.py:848) over the rvb_bn_* kernels."""
+
+    def forward(self, input):
+        self._check_input_dim(input)
+        # torch/nn/modules/batchnorm.py, _BatchNorm.forward: the exponential-average factor and the counter
+        factor = 0.0 if self.momentum is None else self.momentum
+        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+            factor = 1.0 / float(self.num_batches_tracked) if self.momentum is None else self.momentum
+        bn_training = self.training or (self.running_mean is None and self.running_var is None)
+        use_running = not self.training or self.track_running_stats
+        return batch_norm(input, self.running_mean if use_running else None, self.running_var if use_running else None,
+                          self.weight, self.bias, bn_training, factor, self.eps)
+
+
+def convert(module):
+    """Swap the class of every ``nn.BatchNorm2d`` inside ``module`` (in place; parameters and buffers untouched)."""
+    for m in module.modules():
+        if type(m) is nn.BatchNorm2d:
+            m.__class__ = BatchNorm2d
+    return module
+
+
+class _NNProxy:
+    """What ``install(batchnorm=True)`` binds to the name ``nn`` inside the reference's model files: torch.nn with
+    BatchNorm2d replaced."""
+
+    BatchNorm2d = BatchNorm2d
+
+    def __getattr__(self, name):
+        return getattr(nn, name)
+
+
+nn_proxy = _NNProxy()

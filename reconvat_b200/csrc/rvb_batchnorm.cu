@@ -1,0 +1,318 @@
+// Train-mode BatchNorm2d of the caller's U-Net (SURVEY.md 8f, row f5 -- consumer side of the hot path).
+//
+// model/self_attention_VAT.py:848-850, :865-869 put an nn.BatchNorm2d(C = 16 .. 128) behind every convolution of the
+// two U-Nets: 30 modules, three forward and two backward passes per training iteration.  cuDNN's spatial kernels for
+// this layout (bn_fw_tr_1C11_kernel_NCHW / bn_bw_1C11_kernel_new) launch ONE block per channel -- 16 blocks on 148
+// SMs for the (8, 16, 640, 229) tensors -- and take 52 % of the iteration on a B200 (profiles/r02_train_step.md).  The
+// op is two reductions and an elementwise pass over 75 MB: an HBM problem.  Here every channel is cut into `splits`
+// slices so that ~4 blocks per SM run, partial sums go through a small float64 workspace, and the pass that applies
+// the result re-derives the channel statistics from those partials in its prologue -- two launches per direction.
+//
+//   forward  (training)  rvb_bn_reduce(x)              partial sums of (x - K), (x - K)^2, K = first element of the channel
+//                        rvb_bn_forward                mean, biased var, y = (x - mean) invstd gamma + beta, running stats
+//   forward  (eval)      rvb_bn_apply                  y = (x - mean) invstd gamma + beta with the given statistics
+//   backward             rvb_bn_reduce(x, dy, mean)    partial sums of dy, dy (x - mean)
+//                        rvb_bn_backward               dx, dgamma, dbeta   (ATen: native_batch_norm_backward)
+#include "rvb_common.cuh"
+
+namespace rvb {
+
+extern void count_launch();
+
+constexpr int kBnThreads = 256;
+constexpr int kBnMaxSplits = 64;
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// Block-wide sum of two doubles; the result is valid in thread 0.
+__device__ __forceinline__ void block_sum2(double& a, double& b) {
+  __shared__ double s_part[kBnThreads / kWarp][2];
+  a = warp_sum_f64(a);
+  b = warp_sum_f64(b);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_part[warp][0] = a; s_part[warp][1] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = 0.0; b = 0.0;
+#pragma unroll
+    for (int w = 0; w < kBnThreads / kWarp; ++w) { a += s_part[w][0]; b += s_part[w][1]; }
+  }
+}
+
+// grid (splits, C).  Block (s, ch) covers elements [s chunk, min(hw, (s + 1) chunk)) of every sample's channel ch.
+template <bool kBackward>
+__global__ void __launch_bounds__(kBnThreads)
+bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean, int n, int c,
+                 int64_t hw, int64_t chunk, int vec, double* __restrict__ partials) {
+  const int ch = blockIdx.y, s = blockIdx.x;
+  const int64_t j0 = (int64_t)s * chunk;
+  const int64_t j1 = j0 + chunk < hw ? j0 + chunk : hw;
+  const float K = kBackward ? __ldg(mean + ch) : __ldg(x + (int64_t)ch * hw);
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = 0; i < n; ++i) {
+    const int64_t base = ((int64_t)i * c + ch) * hw;
+    if (vec) {
+      for (int64_t j = j0 + 4 * (int64_t)threadIdx.x; j < j1; j += 4 * kBnThreads) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + base + j));
+        const float d[4] = {v.x - K, v.y - K, v.z - K, v.w - K};
+        if constexpr (kBackward) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(dy + base + j));
+          const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { a[q] += gg[q]; b[q] = fmaf(gg[q], d[q], b[q]); }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { a[q] += d[q]; b[q] = fmaf(d[q], d[q], b[q]); }
+        }
+      }
+    } else {
+      for (int64_t j = j0 + threadIdx.x; j < j1; j += kBnThreads) {
+        const float d = __ldg(x + base + j) - K;
+        const int q = (int)((j - j0) / kBnThreads) & 3;
+        if constexpr (kBackward) {
+          const float g = __ldg(dy + base + j);
+          a[q] += g; b[q] = fmaf(g, d, b[q]);
+        } else {
+          a[q] += d; b[q] = fmaf(d, d, b[q]);
+        }
+      }
+    }
+  }
+  double sa = ((double)a[0] + (double)a[1]) + ((double)a[2] + (double)a[3]);
+  double sb = ((double)b[0] + (double)b[1]) + ((double)b[2] + (double)b[3]);
+  block_sum2(sa, sb);
+  if (threadIdx.x == 0) {
+    partials[2 * ((int64_t)ch * gridDim.x + s)] = sa;
+    partials[2 * ((int64_t)ch * gridDim.x + s) + 1] = sb;
+  }
+}
+
+// Sum of this channel's partials, by warp 0; valid in lane 0.
+__device__ __forceinline__ void channel_sums(const double* __restrict__ partials, int ch, int splits, double& s1, double& s2) {
+  const int lane = threadIdx.x & 31;
+  s1 = 0.0; s2 = 0.0;
+  for (int i = lane; i < splits; i += kWarp) {
+    s1 += partials[2 * ((int64_t)ch * splits + i)];
+    s2 += partials[2 * ((int64_t)ch * splits + i) + 1];
+  }
+  s1 = warp_sum_f64(s1);
+  s2 = warp_sum_f64(s2);
+}
+
+// y = (x - mean) * scale + shift over this block's slice
+__device__ __forceinline__ void apply_slice(const float* __restrict__ x, float* __restrict__ y, int n, int c, int ch,
+                                            int64_t hw, int64_t j0, int64_t j1, int vec, float mean, float scale, float shift) {
+  for (int i = 0; i < n; ++i) {
+    const int64_t base = ((int64_t)i * c + ch) * hw;
+    if (vec) {
+      for (int64_t j = j0 + 4 * (int64_t)threadIdx.x; j < j1; j += 4 * kBnThreads) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + base + j));
+        float4 o;
+        o.x = fmaf(v.x - mean, scale, shift); o.y = fmaf(v.y - mean, scale, shift);
+        o.z = fmaf(v.z - mean, scale, shift); o.w = fmaf(v.w - mean, scale, shift);
+        *reinterpret_cast<float4*>(y + base + j) = o;
+      }
+    } else {
+      for (int64_t j = j0 + threadIdx.x; j < j1; j += kBnThreads) y[base + j] = fmaf(__ldg(x + base + j) - mean, scale, shift);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBnThreads)
+bn_forward_kernel(const float* __restrict__ x, int n, int c, int64_t hw, int64_t chunk, int vec,
+                  const double* __restrict__ partials, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float eps, float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                  float* __restrict__ save_mean, float* __restrict__ save_invstd, float* __restrict__ y) {
+  const int ch = blockIdx.y, s = blockIdx.x, splits = gridDim.x;
+  __shared__ float s_stat[3];
+  if (threadIdx.x < kWarp) {
+    double s1, s2;
+    channel_sums(partials, ch, splits, s1, s2);
+    if (threadIdx.x == 0) {
+      const double cnt = (double)n * (double)hw;
+      const double K = (double)__ldg(x + (int64_t)ch * hw);
+      const double m_sh = s1 / cnt;
+      double var = s2 / cnt - m_sh * m_sh;
+      if (var < 0.0) var = 0.0;
+      const float mean = (float)(K + m_sh);
+      const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float g = gamma ? __ldg(gamma + ch) : 1.f;
+      s_stat[0] = mean;
+      s_stat[1] = invstd * g;
+      s_stat[2] = beta ? __ldg(beta + ch) : 0.f;
+      if (s == 0) {
+        save_mean[ch] = mean;
+        save_invstd[ch] = invstd;
+        if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
+        if (running_var) {
+          const float unbiased = (float)(var * (cnt / (cnt - 1.0)));
+          running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * unbiased;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int64_t j0 = (int64_t)s * chunk;
+  const int64_t j1 = j0 + chunk < hw ? j0 + chunk : hw;
+  apply_slice(x, y, n, c, ch, hw, j0, j1, vec, s_stat[0], s_stat[1], s_stat[2]);
+}
+
+__global__ void __launch_bounds__(kBnThreads)
+bn_apply_kernel(const float* __restrict__ x, int n, int c, int64_t hw, int64_t chunk, int vec, const float* __restrict__ mean,
+                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float* __restrict__ y) {
+  const int ch = blockIdx.y, s = blockIdx.x;
+  const float g = gamma ? __ldg(gamma + ch) : 1.f;
+  const int64_t j0 = (int64_t)s * chunk;
+  const int64_t j1 = j0 + chunk < hw ? j0 + chunk : hw;
+  apply_slice(x, y, n, c, ch, hw, j0, j1, vec, __ldg(mean + ch), __ldg(invstd + ch) * g, beta ? __ldg(beta + ch) : 0.f);
+}
+
+__global__ void __launch_bounds__(kBnThreads)
+bn_backward_kernel(const float* __restrict__ x, const float* __restrict__ dy, int n, int c, int64_t hw, int64_t chunk, int vec,
+                   const double* __restrict__ partials, const float* __restrict__ gamma, const float* __restrict__ mean,
+                   const float* __restrict__ invstd, int training, float* __restrict__ dx, float* __restrict__ dgamma,
+                   float* __restrict__ dbeta) {
+  const int ch = blockIdx.y, s = blockIdx.x, splits = gridDim.x;
+  __shared__ float s_k[3];
+  const float mu = __ldg(mean + ch), is = __ldg(invstd + ch);
+  if (threadIdx.x < kWarp) {
+    double sdy, sdyx;
+    channel_sums(partials, ch, splits, sdy, sdyx);
+    if (threadIdx.x == 0) {
+      const double cnt = (double)n * (double)hw;
+      const float g = gamma ? __ldg(gamma + ch) : 1.f;
+      s_k[0] = training ? (float)(sdy / cnt) : 0.f;
+      s_k[1] = training ? (float)(sdyx * (double)is * (double)is / cnt) : 0.f;
+      s_k[2] = is * g;
+      if (s == 0) {
+        if (dgamma) dgamma[ch] = (float)(sdyx * (double)is);
+        if (dbeta) dbeta[ch] = (float)sdy;
+      }
+    }
+  }
+  __syncthreads();
+  if (dx == nullptr) return;
+  const float k1 = s_k[0], k2 = s_k[1], sc = s_k[2];
+  const int64_t j0 = (int64_t)s * chunk;
+  const int64_t j1 = j0 + chunk < hw ? j0 + chunk : hw;
+  for (int i = 0; i < n; ++i) {
+    const int64_t base = ((int64_t)i * c + ch) * hw;
+    if (vec) {
+      for (int64_t j = j0 + 4 * (int64_t)threadIdx.x; j < j1; j += 4 * kBnThreads) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + base + j));
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dy + base + j));
+        float4 o;
+        o.x = (g.x - k1 - (v.x - mu) * k2) * sc; o.y = (g.y - k1 - (v.y - mu) * k2) * sc;
+        o.z = (g.z - k1 - (v.z - mu) * k2) * sc; o.w = (g.w - k1 - (v.w - mu) * k2) * sc;
+        *reinterpret_cast<float4*>(dx + base + j) = o;
+      }
+    } else {
+      for (int64_t j = j0 + threadIdx.x; j < j1; j += kBnThreads)
+        dx[base + j] = (__ldg(dy + base + j) - k1 - (__ldg(x + base + j) - mu) * k2) * sc;
+    }
+  }
+}
+
+static bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int bn_geometry(const char* who, int n, int c, int64_t hw, int splits, int64_t* chunk) {
+  RVB_REQUIRE(n > 0 && c > 0 && c <= 65535 && hw > 0, "%s: bad shape (n %d, c %d, hw %lld)", who, n, c, (long long)hw);
+  RVB_REQUIRE(splits >= 1 && splits <= kBnMaxSplits, "%s: splits %d outside [1, %d]", who, splits, kBnMaxSplits);
+  const int64_t per = (hw + splits - 1) / splits;
+  *chunk = (per + 3) / 4 * 4;
+  RVB_REQUIRE((int64_t)(splits - 1) * *chunk < hw, "%s: %d splits leave an empty slice for hw %lld (use rvb_bn_splits)", who,
+              splits, (long long)hw);
+  return RVB_OK;
+}
+
+}  // namespace rvb
+
+using namespace rvb;
+
+extern "C" int rvb_bn_splits(int n, int c, int64_t hw) {
+  if (n <= 0 || c <= 0 || hw <= 0) return 1;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t want = (4 * (int64_t)sms + c - 1) / c;                 // ~4 blocks per SM
+  const int64_t most = hw / 1024 > 1 ? hw / 1024 : 1;            // slices of at least 1 024 elements per sample
+  if (want > most) want = most;
+  if (want > kBnMaxSplits) want = kBnMaxSplits;
+  if (want < 1) want = 1;
+  // no empty last slice: chunk = roundup4(ceil(hw / splits)) must leave (splits - 1) * chunk < hw
+  while (want > 1) {
+    const int64_t chunk = ((hw + want - 1) / want + 3) / 4 * 4;
+    if ((want - 1) * chunk < hw) break;
+    --want;
+  }
+  return (int)want;
+}
+
+extern "C" int rvb_bn_reduce(const float* x, const float* dy, const float* mean, int n, int c, int64_t hw, int splits,
+                             double* partials, rvb_stream_t stream) {
+  const char* who = "rvb_bn_reduce";
+  RVB_REQUIRE(x && partials, "%s: null pointer", who);
+  RVB_REQUIRE((dy == nullptr) == (mean == nullptr), "%s: dy and mean go together (backward sums)", who);
+  int64_t chunk;
+  int rc = bn_geometry(who, n, c, hw, splits, &chunk);
+  if (rc != RVB_OK) return rc;
+  const int vec = (hw % 4 == 0) && aligned16(x) && aligned16(dy);
+  const dim3 grid(splits, c);
+  if (dy)
+    bn_reduce_kernel<true><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>(x, dy, mean, n, c, hw, chunk, vec, partials);
+  else
+    bn_reduce_kernel<false><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>(x, nullptr, nullptr, n, c, hw, chunk, vec, partials);
+  count_launch();
+  return check_launch("bn_reduce_kernel");
+}
+
+extern "C" int rvb_bn_forward(const float* x, int n, int c, int64_t hw, int splits, const double* partials,
+                              const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                              float* running_var, float* save_mean, float* save_invstd, float* y, rvb_stream_t stream) {
+  const char* who = "rvb_bn_forward";
+  RVB_REQUIRE(x && partials && save_mean && save_invstd && y, "%s: null pointer", who);
+  RVB_REQUIRE((int64_t)n * hw > 1, "%s: more than one value per channel is needed in training mode", who);
+  int64_t chunk;
+  int rc = bn_geometry(who, n, c, hw, splits, &chunk);
+  if (rc != RVB_OK) return rc;
+  const int vec = (hw % 4 == 0) && aligned16(x) && aligned16(y);
+  bn_forward_kernel<<<dim3(splits, c), kBnThreads, 0, (cudaStream_t)stream>>>(
+      x, n, c, hw, chunk, vec, partials, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_invstd, y);
+  count_launch();
+  return check_launch("bn_forward_kernel");
+}
+
+extern "C" int rvb_bn_apply(const float* x, int n, int c, int64_t hw, const float* mean, const float* invstd,
+                            const float* gamma, const float* beta, float* y, rvb_stream_t stream) {
+  const char* who = "rvb_bn_apply";
+  RVB_REQUIRE(x && mean && invstd && y, "%s: null pointer", who);
+  const int splits = rvb_bn_splits(n, c, hw);
+  int64_t chunk;
+  int rc = bn_geometry(who, n, c, hw, splits, &chunk);
+  if (rc != RVB_OK) return rc;
+  const int vec = (hw % 4 == 0) && aligned16(x) && aligned16(y);
+  bn_apply_kernel<<<dim3(splits, c), kBnThreads, 0, (cudaStream_t)stream>>>(x, n, c, hw, chunk, vec, mean, invstd, gamma,
+                                                                             beta, y);
+  count_launch();
+  return check_launch("bn_apply_kernel");
+}
+
+extern "C" int rvb_bn_backward(const float* x, const float* dy, int n, int c, int64_t hw, int splits, const double* partials,
+                               const float* gamma, const float* mean, const float* invstd, int training, float* dx,
+                               float* dgamma, float* dbeta, rvb_stream_t stream) {
+  const char* who = "rvb_bn_backward";
+  RVB_REQUIRE(x && dy && partials && mean && invstd, "%s: null pointer", who);
+  RVB_REQUIRE(dx || dgamma || dbeta, "%s: nothing to compute", who);
+  int64_t chunk;
+  int rc = bn_geometry(who, n, c, hw, splits, &chunk);
+  if (rc != RVB_OK) return rc;
+  const int vec = (hw % 4 == 0) && aligned16(x) && aligned16(dy) && aligned16(dx);
+  bn_backward_kernel<<<dim3(splits, c), kBnThreads, 0, (cudaStream_t)stream>>>(x, dy, n, c, hw, chunk, vec, partials, gamma,
+                                                                                mean, invstd, training, dx, dgamma, dbeta);
+  count_launch();
+  return check_launch("bn_backward_kernel");
+}

@@ -77,7 +77,7 @@ def _rebind_everywhere(name, new, defining_module):
     return done
 
 
-def patch_reference(attention=False, decoding=False, training=False):
+def patch_reference(attention=False, decoding=False, training=False, batchnorm=False):
     """Rebind VAT classes, Normalization and the Spectrogram module in every imported reference module.
     ``attention=True`` also rebinds ``MutliHeadAttention1D`` (the U-Net's sequence model) to the
     fused local-window attention: same parameters and outputs, no (B, L, C, W) unfolded tensors.
@@ -87,8 +87,19 @@ def patch_reference(attention=False, decoding=False, training=False):
     ``training=True`` rebinds ``train_VAT_model`` (model/helper_functions.py:570-615) to ``reconvat_b200.training``'s:
     same arguments and arithmetic, no per-iteration host synchronisation, gradients averaged over the ranks when
     ``torch.distributed`` is initialised.
+    ``batchnorm=True`` rebinds the name ``nn`` inside the reference's model files to a view of ``torch.nn`` whose
+    ``BatchNorm2d`` is ``reconvat_b200.batchnorm.BatchNorm2d`` (same parameters, buffers and semantics; cuDNN's
+    one-block-per-channel kernels are half of the U-Net's training iteration on a B200): models constructed afterwards
+    use it, existing ones are converted with ``reconvat_b200.batchnorm.convert(model)``.
     Returns the list of (module, name) pairs that were rebound."""
     done = []
+    if batchnorm:
+        import torch.nn as _nn
+        from . import batchnorm as _bn
+        for modname, mod in list(sys.modules.items()):
+            if mod is not None and modname.startswith("model.") and getattr(mod, "nn", None) is _nn:
+                mod.nn = _bn.nn_proxy
+                done.append((modname, "nn.BatchNorm2d"))
     if training:
         from . import training as _tr
         done += _rebind_everywhere("train_VAT_model", _tr.train_VAT_model, "model.helper_functions")
@@ -129,6 +140,6 @@ def patch_reference(attention=False, decoding=False, training=False):
     return done
 
 
-def install(attention=False, decoding=False, training=False):
+def install(attention=False, decoding=False, training=False, batchnorm=False):
     install_nnaudio()
-    return patch_reference(attention=attention, decoding=decoding, training=training)
+    return patch_reference(attention=attention, decoding=decoding, training=training, batchnorm=batchnorm)

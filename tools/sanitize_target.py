@@ -59,6 +59,13 @@ def main():
     ws = [torch.randn(916, 229, device=dev, requires_grad=True) for _ in range(2)]
     sum(y.square().sum() for y in linear.projections(xw, ws)).backward()
     assert bool(torch.isfinite(xw.grad).all())
+    # the caller's BatchNorm2d: train forward / backward (vector and scalar paths), eval forward
+    from reconvat_b200 import batchnorm
+    for shape in ((2, 16, 64, 36), (3, 5, 17, 13)):
+        bn = batchnorm.BatchNorm2d(shape[1]).to(dev)
+        xb = torch.randn(shape, device=dev, requires_grad=True)
+        bn(xb).square().sum().backward()
+        assert bool(torch.isfinite(xb.grad).all()) and bool(torch.isfinite(bn.eval()(xb)).all())
     # VAT flavours
     for conv, cls, kw in (("unet", "UNet_VAT", dict(KL_Div=False)), ("unet_onset", "UNet_VAT_onset", dict(KL_Div=False)),
                           ("stepwise", "stepwise_VAT", dict(KL_Div=True)), ("stepwise", "stepwise_VAT", dict(KL_Div=False, binwise=True))):
