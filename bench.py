@@ -744,11 +744,13 @@ def run_train_step(args, rank, local_rank, world):
             ("install(attention=True, batchnorm=True)", lambda: RL.load_patched(attention=True, batchnorm=True)))
     res = {}
     steps, warm = (args.steps if args.steps != 200 else 10), max(2, min(args.warmup, 3))
+    import contextlib
     for name, load in arms:
         ns = load()
         torch.manual_seed(0)
-        model = ns.self_attention_VAT.UNet((2, 2), (2, 2), log=True, reconstruction=True, mode="imagewise", spec="Mel",
-                                           XI=1e-6, eps=2).to(dev)                 # train_UNet_VAT.py:126
+        with contextlib.redirect_stdout(sys.stderr):                              # the constructors print
+            model = ns.self_attention_VAT.UNet((2, 2), (2, 2), log=True, reconstruction=True, mode="imagewise",
+                                               spec="Mel", XI=1e-6, eps=2).to(dev)   # train_UNet_VAT.py:126
         model.train()
         opt = torch.optim.Adam(model.parameters(), 1e-3)
 
