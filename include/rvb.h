@@ -460,6 +460,14 @@ int rvb_note_offsets(const float* onsets, const float* frames, int n_frames, int
  *                    dx = dy invstd gamma; dgamma = sum(dy xhat), dbeta = sum(dy); any of dx / dgamma / dbeta may be NULL
  */
 int rvb_bn_splits(int n, int c, int64_t hw);
+/* rvb_bn_train_forward = rvb_bn_reduce + rvb_bn_forward, rvb_bn_train_backward = rvb_bn_reduce + rvb_bn_backward with
+ * splits = rvb_bn_splits(n, c, hw), in ONE host call; partials must hold c * 64 * 2 doubles. */
+int rvb_bn_train_forward(const float* x, int n, int c, int64_t hw, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                         float* y, double* partials, rvb_stream_t stream);
+int rvb_bn_train_backward(const float* x, const float* dy, int n, int c, int64_t hw, const float* gamma, const float* mean,
+                          const float* invstd, int training, float* dx, float* dgamma, float* dbeta, double* partials,
+                          rvb_stream_t stream);
 int rvb_bn_reduce(const float* x, const float* dy, const float* mean, int n, int c, int64_t hw, int splits,
                   double* partials, rvb_stream_t stream);
 int rvb_bn_forward(const float* x, int n, int c, int64_t hw, int splits, const double* partials, const float* gamma,

@@ -65,6 +65,8 @@ SIGNATURES = {
     "rvb_bce_mean": [_c_p, _c_p, _i64, _c_p, _c_p, _c_p],
     "rvb_bn_reduce": [_c_p, _c_p, _c_p, _i32, _i32, _i64, _i32, _c_p, _c_p],
     "rvb_bn_forward": [_c_p, _i32, _i32, _i64, _i32, _c_p, _c_p, _c_p, _f32, _f32, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p],
+    "rvb_bn_train_forward": [_c_p, _i32, _i32, _i64, _c_p, _c_p, _f32, _f32, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p],
+    "rvb_bn_train_backward": [_c_p, _c_p, _i32, _i32, _i64, _c_p, _c_p, _c_p, _i32, _c_p, _c_p, _c_p, _c_p, _c_p],
     "rvb_bn_apply": [_c_p, _i32, _i32, _i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p],
     "rvb_bn_backward": [_c_p, _c_p, _i32, _i32, _i64, _i32, _c_p, _c_p, _c_p, _c_p, _i32, _c_p, _c_p, _c_p, _c_p],
 }

@@ -23,6 +23,23 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_WORKSPACE = {}
+_MAX_SPLITS = 64
+
+
+def _partials(device, c):
+    """float64 [c][64][2] workspace of the two reductions, one per (device, stream): calls on one stream are ordered.
+    Under CUDA-graph capture every call gets its own (graphs captured on one stream may be replayed side by side)."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty((c * _MAX_SPLITS * 2,), dtype=torch.float64, device=device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACE.get(key)
+    if ws is None or ws.numel() < c * _MAX_SPLITS * 2:
+        ws = torch.empty((max(c, 256) * _MAX_SPLITS * 2,), dtype=torch.float64, device=device)
+        _WORKSPACE[key] = ws
+    return ws
+
+
 class _BatchNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps):
@@ -33,14 +50,11 @@ class _BatchNormFn(torch.autograd.Function):
         if training:
             if n * hw <= 1:
                 raise ValueError("Expected more than 1 value per channel when training, got input size %s" % (tuple(x.shape),))
-            splits = _lib.bn_splits(n, c, hw)
-            partials = torch.empty((c, splits, 2), dtype=torch.float64, device=x.device)
-            mean = torch.empty((c,), dtype=torch.float32, device=x.device)
-            invstd = torch.empty((c,), dtype=torch.float32, device=x.device)
-            _lib.call("rvb_bn_reduce", x.data_ptr(), None, None, n, c, hw, splits, partials.data_ptr())
-            _lib.call("rvb_bn_forward", x.data_ptr(), n, c, hw, splits, partials.data_ptr(), _ptr(weight), _ptr(bias),
-                      float(eps), float(momentum), _ptr(running_mean), _ptr(running_var), mean.data_ptr(),
-                      invstd.data_ptr(), y.data_ptr())
+            stats = torch.empty((2, c), dtype=torch.float32, device=x.device)
+            mean, invstd = stats[0], stats[1]
+            _lib.call("rvb_bn_train_forward", x.data_ptr(), n, c, hw, _ptr(weight), _ptr(bias), float(eps), float(momentum),
+                      _ptr(running_mean), _ptr(running_var), mean.data_ptr(), invstd.data_ptr(), y.data_ptr(),
+                      _partials(x.device, c).data_ptr())
         else:
             mean = running_mean
             invstd = torch.rsqrt(running_var + eps)
@@ -61,14 +75,12 @@ class _BatchNormFn(torch.autograd.Function):
             ctx.has_bias and ctx.needs_input_grad[2]
         if not (need_x or need_w or need_b):
             return (None,) * 8
-        splits = _lib.bn_splits(n, c, hw)
-        partials = torch.empty((c, splits, 2), dtype=torch.float64, device=x.device)
         dx = torch.empty_like(x) if need_x else None
-        dgamma = torch.empty((c,), dtype=torch.float32, device=x.device) if need_w else None
-        dbeta = torch.empty((c,), dtype=torch.float32, device=x.device) if need_b else None
-        _lib.call("rvb_bn_reduce", x.data_ptr(), dy.data_ptr(), mean.data_ptr(), n, c, hw, splits, partials.data_ptr())
-        _lib.call("rvb_bn_backward", x.data_ptr(), dy.data_ptr(), n, c, hw, splits, partials.data_ptr(), _ptr(weight),
-                  mean.data_ptr(), invstd.data_ptr(), int(ctx.training), _ptr(dx), _ptr(dgamma), _ptr(dbeta))
+        dgb = torch.empty((2, c), dtype=torch.float32, device=x.device) if (need_w or need_b) else None
+        dgamma, dbeta = (dgb[0] if need_w else None), (dgb[1] if need_b else None)
+        _lib.call("rvb_bn_train_backward", x.data_ptr(), dy.data_ptr(), n, c, hw, _ptr(weight), mean.data_ptr(),
+                  invstd.data_ptr(), int(ctx.training), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                  _partials(x.device, c).data_ptr())
         return dx, dgamma, dbeta, None, None, None, None, None
 
 

@@ -236,8 +236,15 @@ using namespace rvb;
 
 extern "C" int rvb_bn_splits(int n, int c, int64_t hw) {
   if (n <= 0 || c <= 0 || hw <= 0) return 1;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sm_count[kMaxDevices] = {};
+  const int slot = device_slot();
+  int sms = sm_count[slot];                                      // benign race: every writer stores the same value
+  if (sms == 0) {
+    int dev = 0;
+    sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sm_count[slot] = sms;
+  }
   int64_t want = (4 * (int64_t)sms + c - 1) / c;                 // ~4 blocks per SM
   const int64_t most = hw / 1024 > 1 ? hw / 1024 : 1;            // slices of at least 1 024 elements per sample
   if (want > most) want = most;
@@ -315,4 +322,25 @@ extern "C" int rvb_bn_backward(const float* x, const float* dy, int n, int c, in
                                                                                 mean, invstd, training, dx, dgamma, dbeta);
   count_launch();
   return check_launch("bn_backward_kernel");
+}
+
+// One host call per direction (the caller's network makes ~240 BatchNorm calls per training iteration: the Python /
+// ctypes cost per call is what is left of them).  `partials` must hold c * 64 * 2 doubles.
+extern "C" int rvb_bn_train_forward(const float* x, int n, int c, int64_t hw, const float* gamma, const float* beta,
+                                    float eps, float momentum, float* running_mean, float* running_var, float* save_mean,
+                                    float* save_invstd, float* y, double* partials, rvb_stream_t stream) {
+  const int splits = rvb_bn_splits(n, c, hw);
+  int rc = rvb_bn_reduce(x, nullptr, nullptr, n, c, hw, splits, partials, stream);
+  if (rc != RVB_OK) return rc;
+  return rvb_bn_forward(x, n, c, hw, splits, partials, gamma, beta, eps, momentum, running_mean, running_var, save_mean,
+                        save_invstd, y, stream);
+}
+
+extern "C" int rvb_bn_train_backward(const float* x, const float* dy, int n, int c, int64_t hw, const float* gamma,
+                                     const float* mean, const float* invstd, int training, float* dx, float* dgamma,
+                                     float* dbeta, double* partials, rvb_stream_t stream) {
+  const int splits = rvb_bn_splits(n, c, hw);
+  int rc = rvb_bn_reduce(x, dy, mean, n, c, hw, splits, partials, stream);
+  if (rc != RVB_OK) return rc;
+  return rvb_bn_backward(x, dy, n, c, hw, splits, partials, gamma, mean, invstd, training, dx, dgamma, dbeta, stream);
 }

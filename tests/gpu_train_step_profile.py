@@ -13,7 +13,7 @@ def batch(seed):
     return {"audio": torch.from_numpy(synth.to_float(audio)).to(dev),
             "onset": (torch.rand(B, frames, 88, generator=g) > 0.99).float().to(dev),
             "frame": (torch.rand(B, frames, 88, generator=g) > 0.95).float().to(dev)}
-ns = RL.load_patched(attention=True)
+ns = RL.load_patched(attention=True, batchnorm=True)
 torch.manual_seed(0)
 model = ns.self_attention_VAT.UNet((2, 2), (2, 2), log=True, reconstruction=True, mode="imagewise", spec="Mel", XI=1e-6, eps=2).to(dev).train()
 opt = torch.optim.Adam(model.parameters(), 1e-3)
