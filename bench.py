@@ -710,22 +710,29 @@ def run_transcribe(args, rank, local_rank, world):
 
 
 def run_train_step(args, rank, local_rank, world):
-    """--workload train_step (the CALLER's step, SURVEY.md 8f rows f2 / f4 -- context for the hot-path numbers, not the
-    headline): the reference's own ``UNet`` (oracle/_ref snapshot, random init) through one iteration of
+    """--workload train_step (the CALLER's step, SURVEY.md 8f rows f2 / f4 / f5 -- context for the hot-path numbers, not
+    the headline): the reference's own ``UNet`` (oracle/_ref snapshot, random init) through one iteration of
     ``train_VAT_model`` (model/helper_functions.py:570-615: run_on_batch with VAT on a labelled + an unlabelled batch
-    of --batch segments each, backward, Adam step), three ways on the same GPU: the unmodified reference, the same
-    scripts behind ``reconvat_b200.install()`` (hot path only), behind ``install(attention=True)`` (plus the caller-side
-    attention kernels) and behind ``install(attention=True, batchnorm=True)`` (plus the U-Net's BatchNorm2d).  One rank (the reference's scripts are single-GPU)."""
+    of --batch segments each, backward, Adam step).  One rank: four arms on the same GPU -- the unmodified reference, the
+    same scripts behind ``reconvat_b200.install()`` (hot path only), behind ``install(attention=True)`` (plus the
+    caller-side attention kernels) and behind ``install(attention=True, batchnorm=True)`` (plus the U-Net's BatchNorm2d).
+    N ranks (the reference's scripts are single-GPU): the last arm, data-parallel -- every rank its own batches, the
+    gradients averaged by ONE flattened NCCL all-reduce per iteration (reconvat_b200.training.allreduce_gradients);
+    weak scaling, time = max over ranks."""
+    import contextlib
     import numpy as np
     import torch
-    if rank != 0:
-        return
+    import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     from oracle import reference_loader as RL
-    from reconvat_b200 import synth
+    from reconvat_b200 import parallel, synth, training
+    parallel.bind_to_gpu_numa(local_rank)
     if not RL.available():
-        print(json.dumps({"workload": "train_step", "unavailable": "no reference snapshot (oracle/_ref) on this box"}))
+        if rank == 0:
+            print(json.dumps({"workload": "train_step", "unavailable": "no reference snapshot (oracle/_ref) on this box"}))
         return
     B = args.batch if args.batch != 32 else 8                                   # train_UNet_VAT.py: batch_size = 8
     frames = 640
@@ -737,17 +744,18 @@ def run_train_step(args, rank, local_rank, world):
         return {"audio": torch.from_numpy(synth.to_float(audio)).to(dev),
                 "onset": (torch.rand(B, frames, 88, generator=g) > 0.99).float().to(dev),
                 "frame": (torch.rand(B, frames, 88, generator=g) > 0.95).float().to(dev)}
-    batches = [(batch(2 * i + 1), batch(2 * i + 2)) for i in range(3)]
+    batches = [(batch(10 * rank + 2 * i + 1), batch(10 * rank + 2 * i + 2)) for i in range(3)]
     arms = (("reference", lambda: RL.load_reference()),
             ("install()", lambda: RL.load_patched()),
             ("install(attention=True)", lambda: RL.load_patched(attention=True)),
             ("install(attention=True, batchnorm=True)", lambda: RL.load_patched(attention=True, batchnorm=True)))
+    if world > 1:
+        arms = arms[-1:]
     res = {}
     steps, warm = (args.steps if args.steps != 200 else 10), max(2, min(args.warmup, 3))
-    import contextlib
     for name, load in arms:
         ns = load()
-        torch.manual_seed(0)
+        torch.manual_seed(0)                                                      # the same parameters on every rank
         with contextlib.redirect_stdout(sys.stderr):                              # the constructors print
             model = ns.self_attention_VAT.UNet((2, 2), (2, 2), log=True, reconstruction=True, mode="imagewise",
                                                spec="Mel", XI=1e-6, eps=2).to(dev)   # train_UNet_VAT.py:126
@@ -762,10 +770,14 @@ def run_train_step(args, rank, local_rank, world):
             for k, v in losses.items():
                 loss = loss + (v / 2 if k.startswith("loss/train_LDS") else v)
             loss.backward()
+            if world > 1:
+                training.allreduce_gradients(model)
             opt.step()
             return loss
         for i in range(warm):
             last = one(i)
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.reset_peak_memory_stats()
@@ -773,20 +785,40 @@ def run_train_step(args, rank, local_rank, world):
         for i in range(steps):
             last = one(i)
         ev1.record()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1) / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
         assert bool(torch.isfinite(last))
-        res[name] = {"ms_per_step": ms, "value": 2 * B * SEG_SECONDS / (ms * 1e-3), "unit": "audio-s/s",
+        res[name] = {"ms_per_step": ms, "value": world * 2 * B * SEG_SECONDS / (ms * 1e-3), "unit": "audio-s/s",
                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        if world > 1:
+            # the ranks still hold the same parameters: the all-reduce did its job
+            flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+            lo, hi = flat.clone(), flat.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            res[name]["parameters_identical_across_ranks"] = bool(torch.equal(lo, hi))
         del model, opt
         torch.cuda.empty_cache()
-    line = {"metric": "audio-sec/s", "workload": "train_step", "n_gpus": 1, "steps": steps, "warmup": warm,
-            "higher_is_better": True, "data": "synthetic",
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    best = "install(attention=True, batchnorm=True)"
+    line = {"metric": "audio-sec/s", "workload": "train_step", "n_gpus": world, "steps": steps, "warmup": warm,
+            "higher_is_better": True, "data": "synthetic", "scaling": "weak",
             "config": {"workload": "the reference's UNet (random init, train mode), one train_VAT_model iteration: "
-                                   "run_on_batch(labelled B=%d, unlabelled B=%d, VAT=True) + backward + Adam step; "
-                                   "PyTorch default flags" % (B, B)},
-            "value": res["install(attention=True, batchnorm=True)"]["value"], "unit": "audio-s/s",
-            "ms_per_step": res["install(attention=True, batchnorm=True)"]["ms_per_step"], "arms": res}
+                                   "run_on_batch(labelled B=%d, unlabelled B=%d, VAT=True) + backward + Adam step per "
+                                   "rank; PyTorch default flags" % (B, B),
+                       "collective": "one flattened NCCL all-reduce of the gradients (11.4 MB) per iteration"
+                       if world > 1 else "none"},
+            "value": res[best]["value"], "unit": "audio-s/s", "ms_per_step": res[best]["ms_per_step"], "arms": res}
     print(json.dumps(line), flush=True)
 
 
