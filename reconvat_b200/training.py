@@ -45,8 +45,7 @@ def allreduce_gradients(model, group=None):
     flat = torch._utils._flatten_dense_tensors(grads)
     dist.all_reduce(flat, group=group)
     flat.div_(world)
-    for g, new in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-        g.copy_(new)
+    torch._foreach_copy_(grads, list(torch._utils._unflatten_dense_tensors(flat, grads)))    # one call, not one per tensor
 
 
 class RunOnBatch(nn.Module):
