@@ -749,8 +749,14 @@ def run_train_step(args, rank, local_rank, world):
             ("install()", lambda: RL.load_patched()),
             ("install(attention=True)", lambda: RL.load_patched(attention=True)),
             ("install(attention=True, batchnorm=True)", lambda: RL.load_patched(attention=True, batchnorm=True)))
+    if os.environ.get("RVB_BENCH_CHANNELS_LAST"):
+        # what a user could do without us: the unmodified reference with channels_last weights (cuDNN's NHWC kernels)
+        arms = arms + (("reference, channels_last", lambda: RL.load_reference()),
+                       ("install(attention=True), channels_last", lambda: RL.load_patched(attention=True)),
+                       ("install(attention=True, batchnorm=True), channels_last",
+                        lambda: RL.load_patched(attention=True, batchnorm=True)))
     if world > 1:
-        arms = arms[-1:]
+        arms = arms[3:4]
     res = {}
     steps, warm = (args.steps if args.steps != 200 else 10), max(2, min(args.warmup, 3))
     for name, load in arms:
@@ -759,6 +765,8 @@ def run_train_step(args, rank, local_rank, world):
         with contextlib.redirect_stdout(sys.stderr):                              # the constructors print
             model = ns.self_attention_VAT.UNet((2, 2), (2, 2), log=True, reconstruction=True, mode="imagewise",
                                                spec="Mel", XI=1e-6, eps=2).to(dev)   # train_UNet_VAT.py:126
+        if name.endswith("channels_last"):
+            model = model.to(memory_format=torch.channels_last)
         model.train()
         opt = torch.optim.Adam(model.parameters(), 1e-3)
 

@@ -468,6 +468,20 @@ int rvb_bn_train_forward(const float* x, int n, int c, int64_t hw, const float* 
 int rvb_bn_train_backward(const float* x, const float* dy, int n, int c, int64_t hw, const float* gamma, const float* mean,
                           const float* invstd, int training, float* dx, float* dgamma, float* dbeta, double* partials,
                           rvb_stream_t stream);
+/* The same three operations for torch.channels_last tensors: x, y, dy, dx in [n][h][w][c] physical order, pixels = n h w,
+ * c % 4 == 0, c <= 1024, all pointers 16-byte aligned.  A block owns a range of pixels and all channels, a thread one
+ * group of four channels; the last block of the reduction (ticket) turns the per-block partial sums into the channel
+ * statistics.  workspace: rvb_bn_nhwc_workspace_bytes(c) bytes whose LAST 16 bytes (the ticket) are zero before the
+ * first use; the kernels leave them zero. */
+int64_t rvb_bn_nhwc_workspace_bytes(int c);
+int rvb_bn_train_forward_nhwc(const float* x, int64_t pixels, int c, const float* gamma, const float* beta, float eps,
+                              float momentum, float* running_mean, float* running_var, float* save_mean,
+                              float* save_invstd, float* y, void* workspace, rvb_stream_t stream);
+int rvb_bn_apply_nhwc(const float* x, int64_t pixels, int c, const float* mean, const float* invstd, const float* gamma,
+                      const float* beta, float* y, rvb_stream_t stream);
+int rvb_bn_train_backward_nhwc(const float* x, const float* dy, int64_t pixels, int c, const float* gamma,
+                               const float* mean, const float* invstd, int training, float* dx, float* dgamma,
+                               float* dbeta, void* workspace, rvb_stream_t stream);
 int rvb_bn_reduce(const float* x, const float* dy, const float* mean, int n, int c, int64_t hw, int splits,
                   double* partials, rvb_stream_t stream);
 int rvb_bn_forward(const float* x, int n, int c, int64_t hw, int splits, const double* partials, const float* gamma,

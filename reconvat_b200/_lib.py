@@ -67,6 +67,9 @@ SIGNATURES = {
     "rvb_bn_forward": [_c_p, _i32, _i32, _i64, _i32, _c_p, _c_p, _c_p, _f32, _f32, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p],
     "rvb_bn_train_forward": [_c_p, _i32, _i32, _i64, _c_p, _c_p, _f32, _f32, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p],
     "rvb_bn_train_backward": [_c_p, _c_p, _i32, _i32, _i64, _c_p, _c_p, _c_p, _i32, _c_p, _c_p, _c_p, _c_p, _c_p],
+    "rvb_bn_train_forward_nhwc": [_c_p, _i64, _i32, _c_p, _c_p, _f32, _f32, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p],
+    "rvb_bn_apply_nhwc": [_c_p, _i64, _i32, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p],
+    "rvb_bn_train_backward_nhwc": [_c_p, _c_p, _i64, _i32, _c_p, _c_p, _c_p, _i32, _c_p, _c_p, _c_p, _c_p, _c_p],
     "rvb_bn_apply": [_c_p, _i32, _i32, _i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p],
     "rvb_bn_backward": [_c_p, _c_p, _i32, _i32, _i64, _i32, _c_p, _c_p, _c_p, _c_p, _i32, _c_p, _c_p, _c_p, _c_p],
 }
@@ -104,6 +107,8 @@ def load():
     lib.rvb_parity_plane_len.restype = ctypes.c_int64
     lib.rvb_parity_plane_len.argtypes = [_i32, _i32, _i32, _i32, _i32, _i32]
     lib.rvb_bn_splits.restype = ctypes.c_int
+    lib.rvb_bn_nhwc_workspace_bytes.restype = ctypes.c_int64
+    lib.rvb_bn_nhwc_workspace_bytes.argtypes = [_i32]
     lib.rvb_bn_splits.argtypes = [_i32, _i32, _i64]
     if lib.rvb_abi_version() != ABI_VERSION:
         raise ImportError("reconvat_b200: librvb.so has ABI %d, the Python side expects %d -- rebuild"
@@ -123,6 +128,10 @@ def launch_count():
 
 def parity_plane_len(n_samples, pad, pad_mode, n_fft, hop, n_frames):
     return int(load().rvb_parity_plane_len(int(n_samples), int(pad), int(pad_mode), int(n_fft), int(hop), int(n_frames)))
+
+
+def bn_nhwc_workspace_bytes(c):
+    return int(load().rvb_bn_nhwc_workspace_bytes(int(c)))
 
 
 def bn_splits(n, c, hw):

@@ -6,6 +6,9 @@ passes per training iteration.  cuDNN runs that layout with one block per channe
 the iteration (profiles/r02_train_step.md).  :class:`BatchNorm2d` is the same module -- same constructor, parameters,
 buffers (``state_dict`` interchange), train / eval semantics, running-statistics update -- over ``rvb_bn_*``: every
 channel cut into slices so that the whole chip works on it, two launches per direction, float64 partial sums.
+Both memory formats have kernels of their own: NCHW (what the reference's unchanged scripts produce) and
+``torch.channels_last`` (what ``model.to(memory_format=torch.channels_last)`` produces; C % 4 == 0), so the module never
+forces a layout conversion on its neighbours.
 
 ``convert(model)`` swaps the class of every ``nn.BatchNorm2d`` in place (parameters untouched);
 ``install(batchnorm=True)`` makes the reference's model files construct this class without editing them.
@@ -40,35 +43,74 @@ def _partials(device, c):
     return ws
 
 
+_WORKSPACE_NHWC = {}
+_NHWC_MAX_C = 1024
+
+
+def _nhwc_workspace(device, c):
+    """Workspace of the channels_last kernels (per-block partial sums, backward coefficients, a ticket that must be
+    zero before the first launch and is left zero by every launch)."""
+    nbytes = _lib.bn_nhwc_workspace_bytes(c)
+    if torch.cuda.is_current_stream_capturing():
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        ws[-16:].zero_()
+        return ws
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream, c)
+    ws = _WORKSPACE_NHWC.get(key)
+    if ws is None:
+        ws = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
+        _WORKSPACE_NHWC[key] = ws
+    return ws
+
+
+def _is_nhwc(x):
+    """4-D, dense in torch.channels_last order but not in NCHW order, with a channel count the NHWC kernels take."""
+    return x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last) \
+        and x.shape[1] % 4 == 0 and x.shape[1] <= _NHWC_MAX_C
+
+
 class _BatchNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps):
-        x = x.contiguous()
+        nhwc = _is_nhwc(x)
+        if not nhwc:
+            x = x.contiguous()
         n, c = x.shape[0], x.shape[1]
         hw = x.numel() // (n * c)
-        y = torch.empty_like(x)
+        y = torch.empty_like(x)                                  # keeps the memory format
         if training:
             if n * hw <= 1:
                 raise ValueError("Expected more than 1 value per channel when training, got input size %s" % (tuple(x.shape),))
             stats = torch.empty((2, c), dtype=torch.float32, device=x.device)
             mean, invstd = stats[0], stats[1]
-            _lib.call("rvb_bn_train_forward", x.data_ptr(), n, c, hw, _ptr(weight), _ptr(bias), float(eps), float(momentum),
-                      _ptr(running_mean), _ptr(running_var), mean.data_ptr(), invstd.data_ptr(), y.data_ptr(),
-                      _partials(x.device, c).data_ptr())
+            if nhwc:
+                _lib.call("rvb_bn_train_forward_nhwc", x.data_ptr(), n * hw, c, _ptr(weight), _ptr(bias), float(eps),
+                          float(momentum), _ptr(running_mean), _ptr(running_var), mean.data_ptr(), invstd.data_ptr(),
+                          y.data_ptr(), _nhwc_workspace(x.device, c).data_ptr())
+            else:
+                _lib.call("rvb_bn_train_forward", x.data_ptr(), n, c, hw, _ptr(weight), _ptr(bias), float(eps),
+                          float(momentum), _ptr(running_mean), _ptr(running_var), mean.data_ptr(), invstd.data_ptr(),
+                          y.data_ptr(), _partials(x.device, c).data_ptr())
         else:
             mean = running_mean
             invstd = torch.rsqrt(running_var + eps)
-            _lib.call("rvb_bn_apply", x.data_ptr(), n, c, hw, mean.data_ptr(), invstd.data_ptr(), _ptr(weight), _ptr(bias),
-                      y.data_ptr())
+            if nhwc:
+                _lib.call("rvb_bn_apply_nhwc", x.data_ptr(), n * hw, c, mean.data_ptr(), invstd.data_ptr(), _ptr(weight),
+                          _ptr(bias), y.data_ptr())
+            else:
+                _lib.call("rvb_bn_apply", x.data_ptr(), n, c, hw, mean.data_ptr(), invstd.data_ptr(), _ptr(weight),
+                          _ptr(bias), y.data_ptr())
         ctx.save_for_backward(x, weight, mean, invstd)
         ctx.training = training
         ctx.has_bias = bias is not None
+        ctx.nhwc = nhwc
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, weight, mean, invstd = ctx.saved_tensors
-        dy = dy.contiguous()
+        dy = dy.contiguous(memory_format=torch.channels_last) if ctx.nhwc else dy.contiguous()
         n, c = x.shape[0], x.shape[1]
         hw = x.numel() // (n * c)
         need_x, need_w, need_b = ctx.needs_input_grad[0], weight is not None and ctx.needs_input_grad[1], \
@@ -78,9 +120,14 @@ class _BatchNormFn(torch.autograd.Function):
         dx = torch.empty_like(x) if need_x else None
         dgb = torch.empty((2, c), dtype=torch.float32, device=x.device) if (need_w or need_b) else None
         dgamma, dbeta = (dgb[0] if need_w else None), (dgb[1] if need_b else None)
-        _lib.call("rvb_bn_train_backward", x.data_ptr(), dy.data_ptr(), n, c, hw, _ptr(weight), mean.data_ptr(),
-                  invstd.data_ptr(), int(ctx.training), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
-                  _partials(x.device, c).data_ptr())
+        if ctx.nhwc:
+            _lib.call("rvb_bn_train_backward_nhwc", x.data_ptr(), dy.data_ptr(), n * hw, c, _ptr(weight), mean.data_ptr(),
+                      invstd.data_ptr(), int(ctx.training), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                      _nhwc_workspace(x.device, c).data_ptr())
+        else:
+            _lib.call("rvb_bn_train_backward", x.data_ptr(), dy.data_ptr(), n, c, hw, _ptr(weight), mean.data_ptr(),
+                      invstd.data_ptr(), int(ctx.training), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                      _partials(x.device, c).data_ptr())
         return dx, dgamma, dbeta, None, None, None, None, None
 
 

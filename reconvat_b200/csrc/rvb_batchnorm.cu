@@ -218,6 +218,172 @@ bn_backward_kernel(const float* __restrict__ x, const float* __restrict__ dy, in
   }
 }
 
+// ---------------------------------------------------------------- channels_last (NHWC) flavour
+// x[p][c], p = pixel (n, h, w), c contiguous.  A block owns a range of pixels and ALL channels; a thread owns one group of
+// four channels (float4) for the whole kernel -- blockDim is a multiple of C / 4 -- so its sums, and later its scale /
+// shift, stay in registers.  Partials: [block][C][2] doubles; the LAST block to finish (ticket) adds them per channel
+// and writes the channel statistics, so the applying kernel starts from 2-3 floats per channel.
+struct BnNhwcWs {                       // workspace layout (doubles first); see rvb_bn_nhwc_workspace_bytes
+  double* partials;                     // [kBnNhwcMaxBlocks][C][2]
+  float* coef;                          // [3][C]: backward k1, k2, invstd * gamma
+  unsigned int* ticket;                 // zero before the first launch; the last block resets it
+};
+constexpr int kBnNhwcMaxBlocks = 1024;
+
+__device__ __forceinline__ BnNhwcWs nhwc_ws(void* ws, int c) {
+  BnNhwcWs w;
+  w.partials = reinterpret_cast<double*>(ws);
+  w.coef = reinterpret_cast<float*>(w.partials + (size_t)kBnNhwcMaxBlocks * c * 2);
+  w.ticket = reinterpret_cast<unsigned int*>(w.coef + 3 * (size_t)c);
+  return w;
+}
+
+template <bool kBackward>
+__global__ void __launch_bounds__(kBnThreads)
+bn_nhwc_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t pixels, int c, int64_t per_block,
+                      void* __restrict__ ws_raw,
+                      // forward finalisation
+                      float eps, float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                      float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                      // backward finalisation
+                      const float* __restrict__ gamma, int training, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ double s_red[];                        // [8][blockDim]
+  const BnNhwcWs ws = nhwc_ws(ws_raw, c);
+  const int cg = c >> 2;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg, rows = blockDim.x / cg;
+  const int64_t p0 = (int64_t)blockIdx.x * per_block;
+  const int64_t p1 = p0 + per_block < pixels ? p0 + per_block : pixels;
+  // shift: forward K = pixel 0 of the tensor; backward K = the saved mean
+  const float4 K = kBackward ? __ldg(reinterpret_cast<const float4*>(save_mean) + g) : __ldg(reinterpret_cast<const float4*>(x) + g);
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t p = p0 + r; p < p1; p += rows) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * c) + g);
+    const float d[4] = {v.x - K.x, v.y - K.y, v.z - K.z, v.w - K.w};
+    if constexpr (kBackward) {
+      const float4 gy = __ldg(reinterpret_cast<const float4*>(dy + p * c) + g);
+      const float gg[4] = {gy.x, gy.y, gy.z, gy.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[q] += gg[q]; b[q] = fmaf(gg[q], d[q], b[q]); }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[q] += d[q]; b[q] = fmaf(d[q], d[q], b[q]); }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    s_red[(2 * q) * blockDim.x + threadIdx.x] = (double)a[q];
+    s_red[(2 * q + 1) * blockDim.x + threadIdx.x] = (double)b[q];
+  }
+  __syncthreads();
+  if (r == 0) {                                            // one thread per channel group adds the rows
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double sa = 0.0, sb = 0.0;
+      for (int rr = 0; rr < rows; ++rr) {
+        sa += s_red[(2 * q) * blockDim.x + rr * cg + g];
+        sb += s_red[(2 * q + 1) * blockDim.x + rr * cg + g];
+      }
+      const int ch = 4 * g + q;
+      ws.partials[2 * ((int64_t)blockIdx.x * c + ch)] = sa;
+      ws.partials[2 * ((int64_t)blockIdx.x * c + ch) + 1] = sb;
+    }
+  }
+  // ---- last block: per-channel totals and statistics
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ws.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double cnt = (double)pixels;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    double s1 = 0.0, s2 = 0.0;
+    for (unsigned blk = 0; blk < gridDim.x; ++blk) {
+      s1 += __ldcg(ws.partials + 2 * ((int64_t)blk * c + ch));
+      s2 += __ldcg(ws.partials + 2 * ((int64_t)blk * c + ch) + 1);
+    }
+    if constexpr (kBackward) {
+      const float is = save_invstd[ch];
+      const float gm = gamma ? gamma[ch] : 1.f;
+      ws.coef[ch] = training ? (float)(s1 / cnt) : 0.f;
+      ws.coef[c + ch] = training ? (float)(s2 * (double)is * (double)is / cnt) : 0.f;
+      ws.coef[2 * c + ch] = is * gm;
+      if (dgamma) dgamma[ch] = (float)(s2 * (double)is);
+      if (dbeta) dbeta[ch] = (float)s1;
+    } else {
+      const double Kc = (double)x[ch];
+      const double m_sh = s1 / cnt;
+      double var = s2 / cnt - m_sh * m_sh;
+      if (var < 0.0) var = 0.0;
+      const float mean = (float)(Kc + m_sh);
+      save_mean[ch] = mean;
+      save_invstd[ch] = (float)(1.0 / sqrt(var + (double)eps));
+      if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
+      if (running_var) running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)(var * (cnt / (cnt - 1.0)));
+    }
+  }
+  if (threadIdx.x == 0) *ws.ticket = 0u;                    // ready for the next launch (stream order)
+}
+
+// kMode 0: y = (x - mean) invstd gamma + beta;  1: dx = (dy - k1 - (x - mean) k2) * (invstd gamma) with coef from the workspace
+template <int kMode>
+__global__ void __launch_bounds__(kBnThreads)
+bn_nhwc_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t pixels, int c, int64_t per_block,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const void* __restrict__ ws_raw, float* __restrict__ out) {
+  const int cg = c >> 2;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg, rows = blockDim.x / cg;
+  const int64_t p0 = (int64_t)blockIdx.x * per_block;
+  const int64_t p1 = p0 + per_block < pixels ? p0 + per_block : pixels;
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + g);
+  float4 sc, sh, k2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (kMode == 0) {
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + g);
+    const float4 gm = gamma ? __ldg(reinterpret_cast<const float4*>(gamma) + g) : make_float4(1.f, 1.f, 1.f, 1.f);
+    sc = make_float4(is.x * gm.x, is.y * gm.y, is.z * gm.z, is.w * gm.w);
+    sh = beta ? __ldg(reinterpret_cast<const float4*>(beta) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    const float* coef = nhwc_ws(const_cast<void*>(ws_raw), c).coef;
+    sh = __ldcg(reinterpret_cast<const float4*>(coef) + g);             // k1
+    k2 = __ldcg(reinterpret_cast<const float4*>(coef + c) + g);
+    sc = __ldcg(reinterpret_cast<const float4*>(coef + 2 * c) + g);
+  }
+  for (int64_t p = p0 + r; p < p1; p += rows) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * c) + g);
+    float4 o;
+    if constexpr (kMode == 0) {
+      o.x = fmaf(v.x - mu.x, sc.x, sh.x); o.y = fmaf(v.y - mu.y, sc.y, sh.y);
+      o.z = fmaf(v.z - mu.z, sc.z, sh.z); o.w = fmaf(v.w - mu.w, sc.w, sh.w);
+    } else {
+      const float4 gy = __ldg(reinterpret_cast<const float4*>(dy + p * c) + g);
+      o.x = (gy.x - sh.x - (v.x - mu.x) * k2.x) * sc.x; o.y = (gy.y - sh.y - (v.y - mu.y) * k2.y) * sc.y;
+      o.z = (gy.z - sh.z - (v.z - mu.z) * k2.z) * sc.z; o.w = (gy.w - sh.w - (v.w - mu.w) * k2.w) * sc.w;
+    }
+    *(reinterpret_cast<float4*>(out + p * c) + g) = o;
+  }
+}
+
+struct NhwcPlan { int threads, blocks; int64_t per_block; };
+
+static int nhwc_plan(const char* who, int64_t pixels, int c, NhwcPlan* plan) {
+  RVB_REQUIRE(pixels > 0 && c > 0 && c % 4 == 0 && c <= 4 * kBnThreads, "%s: the channels_last kernels need c %% 4 == 0 and c <= %d (got %d)",
+              who, 4 * kBnThreads, c);
+  const int cg = c / 4;
+  plan->threads = kBnThreads / cg * cg;
+  const int rows = plan->threads / cg;
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t blocks = 4 * (int64_t)sms;
+  const int64_t most = (pixels + 8 * rows - 1) / (8 * rows);             // at least eight loop trips per thread
+  if (blocks > most) blocks = most;
+  if (blocks > kBnNhwcMaxBlocks) blocks = kBnNhwcMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  plan->per_block = (pixels + blocks - 1) / blocks;
+  plan->blocks = (int)((pixels + plan->per_block - 1) / plan->per_block);
+  return RVB_OK;
+}
+
 static bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int bn_geometry(const char* who, int n, int c, int64_t hw, int splits, int64_t* chunk) {
@@ -343,4 +509,73 @@ extern "C" int rvb_bn_train_backward(const float* x, const float* dy, int n, int
   int rc = rvb_bn_reduce(x, dy, mean, n, c, hw, splits, partials, stream);
   if (rc != RVB_OK) return rc;
   return rvb_bn_backward(x, dy, n, c, hw, splits, partials, gamma, mean, invstd, training, dx, dgamma, dbeta, stream);
+}
+
+// ---- channels_last entry points.  x, y, dy, dx: [n][h][w][c] physical order (torch.channels_last), c % 4 == 0, 16-byte
+// aligned; workspace: rvb_bn_nhwc_workspace_bytes(c) bytes, ZEROED once by the caller before its first use.
+extern "C" int64_t rvb_bn_nhwc_workspace_bytes(int c) {
+  return (int64_t)kBnNhwcMaxBlocks * c * 2 * (int64_t)sizeof(double) + 3 * (int64_t)c * (int64_t)sizeof(float) + 16;
+}
+
+extern "C" int rvb_bn_train_forward_nhwc(const float* x, int64_t pixels, int c, const float* gamma, const float* beta,
+                                         float eps, float momentum, float* running_mean, float* running_var,
+                                         float* save_mean, float* save_invstd, float* y, void* workspace,
+                                         rvb_stream_t stream) {
+  const char* who = "rvb_bn_train_forward_nhwc";
+  RVB_REQUIRE(x && save_mean && save_invstd && y && workspace, "%s: null pointer", who);
+  RVB_REQUIRE(pixels > 1, "%s: more than one value per channel is needed in training mode", who);
+  RVB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && aligned16(save_mean) && aligned16(save_invstd),
+              "%s: pointers must be 16-byte aligned", who);
+  NhwcPlan pl;
+  int rc = nhwc_plan(who, pixels, c, &pl);
+  if (rc != RVB_OK) return rc;
+  const size_t smem = 8 * (size_t)pl.threads * sizeof(double);
+  bn_nhwc_reduce_kernel<false><<<pl.blocks, pl.threads, smem, (cudaStream_t)stream>>>(
+      x, nullptr, pixels, c, pl.per_block, workspace, eps, momentum, running_mean, running_var, save_mean, save_invstd,
+      nullptr, 1, nullptr, nullptr);
+  count_launch();
+  if ((rc = check_launch("bn_nhwc_reduce_kernel")) != RVB_OK) return rc;
+  bn_nhwc_apply_kernel<0><<<pl.blocks, pl.threads, 0, (cudaStream_t)stream>>>(x, nullptr, pixels, c, pl.per_block, save_mean,
+                                                                            save_invstd, gamma, beta, workspace, y);
+  count_launch();
+  return check_launch("bn_nhwc_apply_kernel");
+}
+
+extern "C" int rvb_bn_apply_nhwc(const float* x, int64_t pixels, int c, const float* mean, const float* invstd,
+                                 const float* gamma, const float* beta, float* y, rvb_stream_t stream) {
+  const char* who = "rvb_bn_apply_nhwc";
+  RVB_REQUIRE(x && mean && invstd && y, "%s: null pointer", who);
+  RVB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && aligned16(mean) && aligned16(invstd),
+              "%s: pointers must be 16-byte aligned", who);
+  NhwcPlan pl;
+  int rc = nhwc_plan(who, pixels, c, &pl);
+  if (rc != RVB_OK) return rc;
+  bn_nhwc_apply_kernel<0><<<pl.blocks, pl.threads, 0, (cudaStream_t)stream>>>(x, nullptr, pixels, c, pl.per_block, mean, invstd,
+                                                                            gamma, beta, nullptr, y);
+  count_launch();
+  return check_launch("bn_nhwc_apply_kernel");
+}
+
+extern "C" int rvb_bn_train_backward_nhwc(const float* x, const float* dy, int64_t pixels, int c, const float* gamma,
+                                          const float* mean, const float* invstd, int training, float* dx, float* dgamma,
+                                          float* dbeta, void* workspace, rvb_stream_t stream) {
+  const char* who = "rvb_bn_train_backward_nhwc";
+  RVB_REQUIRE(x && dy && mean && invstd && workspace, "%s: null pointer", who);
+  RVB_REQUIRE(dx || dgamma || dbeta, "%s: nothing to compute", who);
+  RVB_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(mean) && aligned16(invstd),
+              "%s: pointers must be 16-byte aligned", who);
+  NhwcPlan pl;
+  int rc = nhwc_plan(who, pixels, c, &pl);
+  if (rc != RVB_OK) return rc;
+  const size_t smem = 8 * (size_t)pl.threads * sizeof(double);
+  bn_nhwc_reduce_kernel<true><<<pl.blocks, pl.threads, smem, (cudaStream_t)stream>>>(
+      x, dy, pixels, c, pl.per_block, workspace, 0.f, 0.f, nullptr, nullptr, const_cast<float*>(mean),
+      const_cast<float*>(invstd), gamma, training, dgamma, dbeta);
+  count_launch();
+  if ((rc = check_launch("bn_nhwc_reduce_kernel")) != RVB_OK) return rc;
+  if (dx == nullptr) return RVB_OK;
+  bn_nhwc_apply_kernel<1><<<pl.blocks, pl.threads, 0, (cudaStream_t)stream>>>(x, dy, pixels, c, pl.per_block, mean, invstd, gamma,
+                                                                            nullptr, workspace, dx);
+  count_launch();
+  return check_launch("bn_nhwc_apply_kernel");
 }

@@ -45,7 +45,7 @@ def test_ctypes_table_mirrors_header(lib):
     import ctypes
     decls = _declared()
     plumbing = {"rvb_abi_version", "rvb_last_error", "rvb_launch_count", "rvb_vat_stats_workspace_bytes",
-                "rvb_parity_plane_len", "rvb_bn_splits"}
+                "rvb_parity_plane_len", "rvb_bn_splits", "rvb_bn_nhwc_workspace_bytes"}
     assert set(lib.SIGNATURES) == set(decls) - plumbing
     kinds = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_int64: "int64_t", ctypes.c_float: "float",
              ctypes.c_double: "double", ctypes.c_uint64: "uint64_t", ctypes.c_uint32: "uint32_t"}

@@ -60,6 +60,41 @@ def test_train_forward_backward_match_torch_and_float64(shape):
         assert _rel(ours_v, truth) <= max(2.0 * _rel(torch_v, truth), 1e-6)
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 640, 229), (2, 32, 320, 114), (2, 48, 160, 57), (2, 128, 80, 28), (3, 8, 17, 13),
+                                   (1, 4, 3, 5), (2, 1024, 6, 5), (2, 12, 30, 7)])
+def test_channels_last_kernels_match_torch_and_float64(shape):
+    """torch.channels_last tensors go through the NHWC kernels (no layout conversion: the output and the input
+    gradient come back channels_last) -- training and eval, against torch on the same layout and against float64."""
+    from reconvat_b200 import batchnorm
+    dev = torch.device("cuda:0")
+    n, c, h, w = shape
+    ref, ours = _pair(c, dev, momentum=0.1)
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(shape, generator=g) * torch.rand(1, c, 1, 1, generator=g).mul(3).add(0.1) - 4.0).to(dev)
+    x = x.contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(shape, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    assert batchnorm._is_nhwc(x) == (c % 4 == 0 and h * w > 1)
+    res = []
+    for m, dt in ((ref, torch.float32), (ours, torch.float32), (copy.deepcopy(ref).double(), torch.float64)):
+        for step in range(2):
+            xi = x.to(dt).clone(memory_format=torch.preserve_format).requires_grad_(True)
+            m.zero_grad()
+            y = m(xi)
+            y.backward(dy.to(dt))
+        m.eval()
+        ye = m(x.to(dt)).detach()
+        m.train()
+        res.append((y.detach(), xi.grad, m.weight.grad, m.bias.grad, m.running_mean, m.running_var, ye))
+    r, o, t = res
+    if batchnorm._is_nhwc(x):
+        assert o[0].is_contiguous(memory_format=torch.channels_last) and o[1].is_contiguous(memory_format=torch.channels_last)
+        assert o[6].is_contiguous(memory_format=torch.channels_last)
+    for i, tol in ((0, 2e-6), (1, 2e-5), (2, 2e-5), (3, 2e-5), (4, 1e-6), (5, 1e-5), (6, 2e-6)):
+        assert _rel(o[i], r[i]) < tol, (i, _rel(o[i], r[i]))
+    for i in (0, 1, 2, 5):
+        assert _rel(o[i], t[i]) <= max(2.0 * _rel(r[i], t[i]), 1e-6), i
+
+
 def test_eval_mode_affine_off_untracked_and_errors():
     from reconvat_b200 import _lib, batchnorm
     dev = torch.device("cuda:0")

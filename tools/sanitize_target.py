@@ -66,6 +66,11 @@ def main():
         xb = torch.randn(shape, device=dev, requires_grad=True)
         bn(xb).square().sum().backward()
         assert bool(torch.isfinite(xb.grad).all()) and bool(torch.isfinite(bn.eval()(xb)).all())
+    bn = batchnorm.BatchNorm2d(16).to(dev)                   # channels_last kernels (ticketed reduction)
+    xb = torch.randn(2, 16, 64, 36, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    for _ in range(2):
+        bn(xb).square().sum().backward()
+    assert bool(torch.isfinite(xb.grad).all()) and bool(torch.isfinite(bn.eval()(xb)).all())
     # VAT flavours
     for conv, cls, kw in (("unet", "UNet_VAT", dict(KL_Div=False)), ("unet_onset", "UNet_VAT_onset", dict(KL_Div=False)),
                           ("stepwise", "stepwise_VAT", dict(KL_Div=True)), ("stepwise", "stepwise_VAT", dict(KL_Div=False, binwise=True))):
