@@ -44,13 +44,16 @@ def _partials(device, c):
 
 
 _WORKSPACE_NHWC = {}
+_NHWC_BYTES = {}
 _NHWC_MAX_C = 1024
 
 
 def _nhwc_workspace(device, c):
     """Workspace of the channels_last kernels (per-block partial sums, backward coefficients, a ticket that must be
     zero before the first launch and is left zero by every launch)."""
-    nbytes = _lib.bn_nhwc_workspace_bytes(c)
+    nbytes = _NHWC_BYTES.get(c)
+    if nbytes is None:
+        nbytes = _NHWC_BYTES[c] = _lib.bn_nhwc_workspace_bytes(c)
     if torch.cuda.is_current_stream_capturing():
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
         ws[-16:].zero_()

@@ -29,20 +29,21 @@ def timed(fn, n=20):
 def main():
     dev = torch.device("cuda:0")
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    fmt = torch.channels_last if len(sys.argv) > 2 and sys.argv[2] == "channels_last" else torch.contiguous_format
     peak = None
     try:
         peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    print("B = %d; HBM peak %s GB/s" % (B, peak))
+    print("B = %d; HBM peak %s GB/s; memory format %s" % (B, peak, fmt))
     print("%-22s %10s %10s %8s %10s %10s %8s %12s" % ("shape", "fwd ours", "fwd torch", "x", "bwd ours", "bwd torch", "x", "ours GB/s f/b"))
     # several tensors per shape so that consecutive calls do not find their input in the L2
     for c, h, w in ((16, 640, 229), (32, 320, 114), (64, 160, 57), (128, 80, 28), (96, 160, 57), (48, 320, 114)):
         ref = nn.BatchNorm2d(c).to(dev)
         ours = batchnorm.convert(copy.deepcopy(ref))
         n_rot = max(2, int(300e6 // (B * c * h * w * 4)) + 1)
-        xs = [torch.randn(B, c, h, w, device=dev) for _ in range(n_rot)]
-        dys = [torch.randn(B, c, h, w, device=dev) for _ in range(n_rot)]
+        xs = [torch.randn(B, c, h, w, device=dev).contiguous(memory_format=fmt) for _ in range(n_rot)]
+        dys = [torch.randn(B, c, h, w, device=dev).contiguous(memory_format=fmt) for _ in range(n_rot)]
         res = {}
         for name, m in (("torch", ref), ("ours", ours)):
             it = [0]
@@ -53,7 +54,7 @@ def main():
             t_f = timed(fwd)
             ys = []
             for i in range(n_rot):
-                xi = xs[i].clone().requires_grad_(True)
+                xi = xs[i].clone(memory_format=torch.preserve_format).requires_grad_(True)
                 ys.append((m(xi), xi))
 
             def bwd():
