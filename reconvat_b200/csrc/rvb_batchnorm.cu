@@ -256,11 +256,9 @@ bn_nhwc_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy,
   // shift: forward K = pixel 0 of the tensor; backward K = the saved mean
   const float4 K = kBackward ? __ldg(reinterpret_cast<const float4*>(save_mean) + g) : __ldg(reinterpret_cast<const float4*>(x) + g);
   float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t p = p0 + r; p < p1; p += rows) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * c) + g);
+  auto add = [&](const float4& v, const float4& gy) {
     const float d[4] = {v.x - K.x, v.y - K.y, v.z - K.z, v.w - K.w};
     if constexpr (kBackward) {
-      const float4 gy = __ldg(reinterpret_cast<const float4*>(dy + p * c) + g);
       const float gg[4] = {gy.x, gy.y, gy.z, gy.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) { a[q] += gg[q]; b[q] = fmaf(gg[q], d[q], b[q]); }
@@ -268,6 +266,23 @@ bn_nhwc_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy,
 #pragma unroll
       for (int q = 0; q < 4; ++q) { a[q] += d[q]; b[q] = fmaf(d[q], d[q], b[q]); }
     }
+  };
+  int64_t p = p0 + r;
+  for (; p + 3 * rows < p1; p += 4 * rows) {               // four pixels per trip: independent loads in flight
+    float4 v[4], gy[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u] = __ldg(reinterpret_cast<const float4*>(x + (p + u * rows) * c) + g);
+      if constexpr (kBackward) gy[u] = __ldg(reinterpret_cast<const float4*>(dy + (p + u * rows) * c) + g);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) add(v[u], gy[u]);
+  }
+  for (; p < p1; p += rows) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * c) + g);
+    float4 gy = v;
+    if constexpr (kBackward) gy = __ldg(reinterpret_cast<const float4*>(dy + p * c) + g);
+    add(v, gy);
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -297,12 +312,30 @@ bn_nhwc_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy,
   if (!s_last) return;
   __threadfence();
   const double cnt = (double)pixels;
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    double s1 = 0.0, s2 = 0.0;
-    for (unsigned blk = 0; blk < gridDim.x; ++blk) {
-      s1 += __ldcg(ws.partials + 2 * ((int64_t)blk * c + ch));
-      s2 += __ldcg(ws.partials + 2 * ((int64_t)blk * c + ch) + 1);
+  // every thread adds a share of the per-block partials: thread t takes channel t % c' of a window of c' = min(c,
+  // blockDim) channels and every nparts-th block; the shares meet in shared memory
+  const int cw = c < (int)blockDim.x ? c : (int)blockDim.x;
+  const int nparts = (int)blockDim.x / cw;
+  for (int c0 = 0; c0 < c; c0 += cw) {
+    const int chl = threadIdx.x % cw, part = threadIdx.x / cw;
+    double t1 = 0.0, t2 = 0.0;
+    if (part < nparts && c0 + chl < c) {
+      for (unsigned blk = part; blk < gridDim.x; blk += nparts) {
+        t1 += __ldcg(ws.partials + 2 * ((int64_t)blk * c + c0 + chl));
+        t2 += __ldcg(ws.partials + 2 * ((int64_t)blk * c + c0 + chl) + 1);
+      }
     }
+    __syncthreads();
+    s_red[threadIdx.x] = t1;
+    s_red[blockDim.x + threadIdx.x] = t2;
+    __syncthreads();
+    if (threadIdx.x < cw && c0 + threadIdx.x < c) {
+      const int ch = c0 + threadIdx.x;
+      double s1 = 0.0, s2 = 0.0;
+      for (int pp = 0; pp < nparts; ++pp) {
+        s1 += s_red[pp * cw + threadIdx.x];
+        s2 += s_red[blockDim.x + pp * cw + threadIdx.x];
+      }
     if constexpr (kBackward) {
       const float is = save_invstd[ch];
       const float gm = gamma ? gamma[ch] : 1.f;
@@ -321,6 +354,7 @@ bn_nhwc_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy,
       save_invstd[ch] = (float)(1.0 / sqrt(var + (double)eps));
       if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
       if (running_var) running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)(var * (cnt / (cnt - 1.0)));
+    }
     }
   }
   if (threadIdx.x == 0) *ws.ticket = 0u;                    // ready for the next launch (stream order)
@@ -349,18 +383,33 @@ bn_nhwc_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
     k2 = __ldcg(reinterpret_cast<const float4*>(coef + c) + g);
     sc = __ldcg(reinterpret_cast<const float4*>(coef + 2 * c) + g);
   }
-  for (int64_t p = p0 + r; p < p1; p += rows) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * c) + g);
+  auto one = [&](const float4& v, const float4& gy) {
     float4 o;
     if constexpr (kMode == 0) {
       o.x = fmaf(v.x - mu.x, sc.x, sh.x); o.y = fmaf(v.y - mu.y, sc.y, sh.y);
       o.z = fmaf(v.z - mu.z, sc.z, sh.z); o.w = fmaf(v.w - mu.w, sc.w, sh.w);
     } else {
-      const float4 gy = __ldg(reinterpret_cast<const float4*>(dy + p * c) + g);
       o.x = (gy.x - sh.x - (v.x - mu.x) * k2.x) * sc.x; o.y = (gy.y - sh.y - (v.y - mu.y) * k2.y) * sc.y;
       o.z = (gy.z - sh.z - (v.z - mu.z) * k2.z) * sc.z; o.w = (gy.w - sh.w - (v.w - mu.w) * k2.w) * sc.w;
     }
-    *(reinterpret_cast<float4*>(out + p * c) + g) = o;
+    return o;
+  };
+  int64_t p = p0 + r;
+  for (; p + 3 * rows < p1; p += 4 * rows) {               // four pixels per trip
+    float4 v[4], gy[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u] = __ldg(reinterpret_cast<const float4*>(x + (p + u * rows) * c) + g);
+      if constexpr (kMode == 1) gy[u] = __ldg(reinterpret_cast<const float4*>(dy + (p + u * rows) * c) + g);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) *(reinterpret_cast<float4*>(out + (p + u * rows) * c) + g) = one(v[u], gy[u]);
+  }
+  for (; p < p1; p += rows) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * c) + g);
+    float4 gy = v;
+    if constexpr (kMode == 1) gy = __ldg(reinterpret_cast<const float4*>(dy + p * c) + g);
+    *(reinterpret_cast<float4*>(out + p * c) + g) = one(v, gy);
   }
 }
 
