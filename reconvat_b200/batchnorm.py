@@ -7,13 +7,16 @@ the iteration (profiles/r02_train_step.md).  :class:`BatchNorm2d` is the same mo
 buffers (``state_dict`` interchange), train / eval semantics, running-statistics update -- over ``rvb_bn_*``: every
 channel cut into slices so that the whole chip works on it, two launches per direction, float64 partial sums.
 Both memory formats have kernels of their own: NCHW (what the reference's unchanged scripts produce) and
-``torch.channels_last`` (what ``model.to(memory_format=torch.channels_last)`` produces; C % 4 == 0), so the module never
-forces a layout conversion on its neighbours.
+``torch.channels_last`` (C % 4 == 0).  For channels_last input the MODULE hands the call to cuDNN by default -- its NHWC
+kernels are sound and ATen's host cost per call is lower -- and runs the rvb NHWC kernels with ``RVB_BN_NHWC=1``; it
+never forces a layout conversion on its neighbours either way.
 
 ``convert(model)`` swaps the class of every ``nn.BatchNorm2d`` in place (parameters untouched);
 ``install(batchnorm=True)`` makes the reference's model files construct this class without editing them.
 There is no CPU path: a CPU tensor raises.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -65,6 +68,12 @@ def _nhwc_workspace(device, c):
         ws = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
         _WORKSPACE_NHWC[key] = ws
     return ws
+
+
+def _own_nhwc():
+    """RVB_BN_NHWC=1: run the rvb NHWC kernels on channels_last input instead of handing it to cuDNN (1.4-1.7x faster
+    kernels on the U-Net's largest layers; pays off where the host is not the bound, e.g. under CUDA-graph replay)."""
+    return os.environ.get("RVB_BN_NHWC", "0") not in ("", "0")
 
 
 def _is_nhwc(x):
@@ -150,6 +159,11 @@ class BatchNorm2d(nn.BatchNorm2d):
 
     def forward(self, input):
         self._check_input_dim(input)
+        if _is_nhwc(input) and input.is_cuda and not _own_nhwc():
+            # torch.channels_last: cuDNN has real NHWC kernels here (batchnorm_*_nhwc_semiPersist, not the
+            # one-block-per-channel NCHW ones), and in eager mode ATen's per-call host cost is half that of a Python
+            # autograd.Function -- the caller's iteration is host-bound in this layout (profiles/r02_train_step.md)
+            return super().forward(input)
         # torch/nn/modules/batchnorm.py, _BatchNorm.forward: the exponential-average factor and the counter
         factor = 0.0 if self.momentum is None else self.momentum
         if self.training and self.track_running_stats and self.num_batches_tracked is not None:

@@ -62,10 +62,12 @@ def test_train_forward_backward_match_torch_and_float64(shape):
 
 @pytest.mark.parametrize("shape", [(2, 16, 640, 229), (2, 32, 320, 114), (2, 48, 160, 57), (2, 128, 80, 28), (3, 8, 17, 13),
                                    (1, 4, 3, 5), (2, 1024, 6, 5), (2, 12, 30, 7)])
-def test_channels_last_kernels_match_torch_and_float64(shape):
-    """torch.channels_last tensors go through the NHWC kernels (no layout conversion: the output and the input
-    gradient come back channels_last) -- training and eval, against torch on the same layout and against float64."""
-    from reconvat_b200 import batchnorm
+def test_channels_last_kernels_match_torch_and_float64(shape, monkeypatch):
+    """torch.channels_last tensors through the rvb NHWC kernels (RVB_BN_NHWC=1; no layout conversion: the output and
+    the input gradient come back channels_last) -- training and eval, against torch on the same layout and float64."""
+    from reconvat_b200 import _lib, batchnorm
+    monkeypatch.setenv("RVB_BN_NHWC", "1")
+    launches0 = _lib.launch_count()
     dev = torch.device("cuda:0")
     n, c, h, w = shape
     ref, ours = _pair(c, dev, momentum=0.1)
@@ -86,6 +88,7 @@ def test_channels_last_kernels_match_torch_and_float64(shape):
         m.train()
         res.append((y.detach(), xi.grad, m.weight.grad, m.bias.grad, m.running_mean, m.running_var, ye))
     r, o, t = res
+    assert _lib.launch_count() > launches0                      # the rvb kernels ran (not cuDNN)
     if batchnorm._is_nhwc(x):
         assert o[0].is_contiguous(memory_format=torch.channels_last) and o[1].is_contiguous(memory_format=torch.channels_last)
         assert o[6].is_contiguous(memory_format=torch.channels_last)

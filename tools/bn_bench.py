@@ -30,6 +30,7 @@ def main():
     dev = torch.device("cuda:0")
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     fmt = torch.channels_last if len(sys.argv) > 2 and sys.argv[2] == "channels_last" else torch.contiguous_format
+    os.environ["RVB_BN_NHWC"] = "1"                              # measure OUR channels_last kernels, not the delegation
     peak = None
     try:
         peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]

@@ -66,6 +66,7 @@ def main():
         xb = torch.randn(shape, device=dev, requires_grad=True)
         bn(xb).square().sum().backward()
         assert bool(torch.isfinite(xb.grad).all()) and bool(torch.isfinite(bn.eval()(xb)).all())
+    os.environ["RVB_BN_NHWC"] = "1"
     bn = batchnorm.BatchNorm2d(16).to(dev)                   # channels_last kernels (ticketed reduction)
     xb = torch.randn(2, 16, 64, 36, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
     for _ in range(2):
