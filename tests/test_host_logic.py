@@ -364,3 +364,34 @@ def test_injected_transcriber_drives_the_reference_op_sequence_on_cpu():
     loss, r_adv, dhat = CpuHotPath().vat(m, x)
     assert torch.allclose(r_adv.norm(dim=-1), torch.full((1, 1, 6), 2.0), rtol=1e-5)
     assert torch.isfinite(loss)
+
+
+def test_batchnorm_seam_and_convert_on_the_cpu():
+    """install(batchnorm=True) rebinds the name `nn` inside the reference's model files to a view of torch.nn whose
+    BatchNorm2d is ours (everything else falls through); convert() swaps classes in place and keeps the state_dict;
+    the module refuses CPU tensors (no fallback)."""
+    import sys
+    import types
+    import torch
+    import torch.nn as nn
+    import reconvat_b200
+    from reconvat_b200 import _lib, batchnorm
+    fake = types.ModuleType("model.fake_unet")
+    fake.nn = nn
+    sys.modules["model.fake_unet"] = fake
+    try:
+        done = reconvat_b200.patch_reference(batchnorm=True)
+        assert ("model.fake_unet", "nn.BatchNorm2d") in done
+        assert fake.nn.BatchNorm2d is batchnorm.BatchNorm2d and fake.nn.Conv2d is nn.Conv2d and fake.nn.Module is nn.Module
+        bn = fake.nn.BatchNorm2d(8, momentum=0.1)
+        assert isinstance(bn, nn.BatchNorm2d) and sorted(bn.state_dict()) == sorted(nn.BatchNorm2d(8).state_dict())
+        assert reconvat_b200.patch_reference(batchnorm=True).count(("model.fake_unet", "nn.BatchNorm2d")) == 0   # idempotent
+    finally:
+        del sys.modules["model.fake_unet"]
+    net = nn.Sequential(nn.Conv2d(1, 4, 3), nn.BatchNorm2d(4), nn.Sequential(nn.BatchNorm2d(4), nn.BatchNorm1d(4)))
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    batchnorm.convert(net)
+    assert type(net[1]) is batchnorm.BatchNorm2d and type(net[2][0]) is batchnorm.BatchNorm2d and type(net[2][1]) is nn.BatchNorm1d
+    assert all(torch.equal(v, sd[k]) for k, v in net.state_dict().items())
+    with pytest.raises(_lib.RvbError):
+        net[1](torch.zeros(2, 4, 5, 5))
