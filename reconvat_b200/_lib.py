@@ -188,6 +188,16 @@ def raw_call(name, args):
         raise RvbError("%s failed (%d): %s" % (name, rc, load().rvb_last_error().decode("utf-8", "replace")))
 
 
+def call_on(name, stream, *args):
+    """``call`` for callers that already hold the stream handle (saves one stream query per call)."""
+    lib = _lib if _lib is not None else load()
+    if _call_log is not None or _event_log is not None:
+        return call(name, *args)
+    rc = getattr(lib, name)(*args, stream)
+    if rc != 0:
+        raise RvbError("%s failed (%d): %s" % (name, rc, lib.rvb_last_error().decode("utf-8", "replace")))
+
+
 def call(name, *args):
     """Invoke an entry point on the current PyTorch stream; raise RvbError on a non-zero status."""
     lib = load()

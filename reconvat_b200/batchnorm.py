@@ -33,12 +33,12 @@ _WORKSPACE = {}
 _MAX_SPLITS = 64
 
 
-def _partials(device, c):
+def _partials(device, c, stream):
     """float64 [c][64][2] workspace of the two reductions, one per (device, stream): calls on one stream are ordered.
     Under CUDA-graph capture every call gets its own (graphs captured on one stream may be replayed side by side)."""
     if torch.cuda.is_current_stream_capturing():
         return torch.empty((c * _MAX_SPLITS * 2,), dtype=torch.float64, device=device)
-    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+    key = (device.index, stream)
     ws = _WORKSPACE.get(key)
     if ws is None or ws.numel() < c * _MAX_SPLITS * 2:
         ws = torch.empty((max(c, 256) * _MAX_SPLITS * 2,), dtype=torch.float64, device=device)
@@ -51,7 +51,7 @@ _NHWC_BYTES = {}
 _NHWC_MAX_C = 1024
 
 
-def _nhwc_workspace(device, c):
+def _nhwc_workspace(device, c, stream):
     """Workspace of the channels_last kernels (per-block partial sums, backward coefficients, a ticket that must be
     zero before the first launch and is left zero by every launch)."""
     nbytes = _NHWC_BYTES.get(c)
@@ -61,8 +61,7 @@ def _nhwc_workspace(device, c):
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
         ws[-16:].zero_()
         return ws
-    key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream, c)
+    key = (device.index, stream, c)
     ws = _WORKSPACE_NHWC.get(key)
     if ws is None:
         ws = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
@@ -91,19 +90,20 @@ class _BatchNormFn(torch.autograd.Function):
         n, c = x.shape[0], x.shape[1]
         hw = x.numel() // (n * c)
         y = torch.empty_like(x)                                  # keeps the memory format
+        st = torch.cuda.current_stream().cuda_stream
         if training:
             if n * hw <= 1:
                 raise ValueError("Expected more than 1 value per channel when training, got input size %s" % (tuple(x.shape),))
             stats = torch.empty((2, c), dtype=torch.float32, device=x.device)
             mean, invstd = stats[0], stats[1]
             if nhwc:
-                _lib.call("rvb_bn_train_forward_nhwc", x.data_ptr(), n * hw, c, _ptr(weight), _ptr(bias), float(eps),
-                          float(momentum), _ptr(running_mean), _ptr(running_var), mean.data_ptr(), invstd.data_ptr(),
-                          y.data_ptr(), _nhwc_workspace(x.device, c).data_ptr())
+                _lib.call_on("rvb_bn_train_forward_nhwc", st, x.data_ptr(), n * hw, c, _ptr(weight), _ptr(bias), float(eps),
+                             float(momentum), _ptr(running_mean), _ptr(running_var), mean.data_ptr(), invstd.data_ptr(),
+                             y.data_ptr(), _nhwc_workspace(x.device, c, st).data_ptr())
             else:
-                _lib.call("rvb_bn_train_forward", x.data_ptr(), n, c, hw, _ptr(weight), _ptr(bias), float(eps),
-                          float(momentum), _ptr(running_mean), _ptr(running_var), mean.data_ptr(), invstd.data_ptr(),
-                          y.data_ptr(), _partials(x.device, c).data_ptr())
+                _lib.call_on("rvb_bn_train_forward", st, x.data_ptr(), n, c, hw, _ptr(weight), _ptr(bias), float(eps),
+                             float(momentum), _ptr(running_mean), _ptr(running_var), mean.data_ptr(), invstd.data_ptr(),
+                             y.data_ptr(), _partials(x.device, c, st).data_ptr())
         else:
             mean = running_mean
             invstd = torch.rsqrt(running_var + eps)
@@ -132,14 +132,15 @@ class _BatchNormFn(torch.autograd.Function):
         dx = torch.empty_like(x) if need_x else None
         dgb = torch.empty((2, c), dtype=torch.float32, device=x.device) if (need_w or need_b) else None
         dgamma, dbeta = (dgb[0] if need_w else None), (dgb[1] if need_b else None)
+        st = torch.cuda.current_stream().cuda_stream
         if ctx.nhwc:
-            _lib.call("rvb_bn_train_backward_nhwc", x.data_ptr(), dy.data_ptr(), n * hw, c, _ptr(weight), mean.data_ptr(),
-                      invstd.data_ptr(), int(ctx.training), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
-                      _nhwc_workspace(x.device, c).data_ptr())
+            _lib.call_on("rvb_bn_train_backward_nhwc", st, x.data_ptr(), dy.data_ptr(), n * hw, c, _ptr(weight),
+                         mean.data_ptr(), invstd.data_ptr(), int(ctx.training), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                         _nhwc_workspace(x.device, c, st).data_ptr())
         else:
-            _lib.call("rvb_bn_train_backward", x.data_ptr(), dy.data_ptr(), n, c, hw, _ptr(weight), mean.data_ptr(),
-                      invstd.data_ptr(), int(ctx.training), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
-                      _partials(x.device, c).data_ptr())
+            _lib.call_on("rvb_bn_train_backward", st, x.data_ptr(), dy.data_ptr(), n, c, hw, _ptr(weight), mean.data_ptr(),
+                         invstd.data_ptr(), int(ctx.training), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                         _partials(x.device, c, st).data_ptr())
         return dx, dgamma, dbeta, None, None, None, None, None
 
 
@@ -159,20 +160,26 @@ class BatchNorm2d(nn.BatchNorm2d):
 
     def forward(self, input):
         self._check_input_dim(input)
-        if _is_nhwc(input) and input.is_cuda and not _own_nhwc():
+        if not input.is_cuda or input.dtype != torch.float32:
+            raise _lib.RvbError("reconvat_b200 batch_norm needs CUDA float32 tensors (got %s, %s); there is no CPU path"
+                                % (input.device, input.dtype))
+        if not input.is_contiguous() and _is_nhwc(input) and not _own_nhwc():
             # torch.channels_last: cuDNN has real NHWC kernels here (batchnorm_*_nhwc_semiPersist, not the
             # one-block-per-channel NCHW ones), and in eager mode ATen's per-call host cost is half that of a Python
             # autograd.Function -- the caller's iteration is host-bound in this layout (profiles/r02_train_step.md)
             return super().forward(input)
         # torch/nn/modules/batchnorm.py, _BatchNorm.forward: the exponential-average factor and the counter
+        training, track = self.training, self.track_running_stats
         factor = 0.0 if self.momentum is None else self.momentum
-        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+        if training and track and self.num_batches_tracked is not None:
             self.num_batches_tracked.add_(1)
-            factor = 1.0 / float(self.num_batches_tracked) if self.momentum is None else self.momentum
-        bn_training = self.training or (self.running_mean is None and self.running_var is None)
-        use_running = not self.training or self.track_running_stats
-        return batch_norm(input, self.running_mean if use_running else None, self.running_var if use_running else None,
-                          self.weight, self.bias, bn_training, factor, self.eps)
+            if self.momentum is None:
+                factor = 1.0 / float(self.num_batches_tracked)
+        use_running = (not training) or track
+        rm = self.running_mean if use_running else None
+        rv = self.running_var if use_running else None
+        return _BatchNormFn.apply(input, self.weight, self.bias, rm, rv, training or (rm is None and rv is None), factor,
+                                  self.eps)
 
 
 def convert(module):
