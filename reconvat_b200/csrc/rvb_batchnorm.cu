@@ -56,11 +56,9 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
   for (int i = 0; i < n; ++i) {
     const int64_t base = ((int64_t)i * c + ch) * hw;
     if (vec) {
-      for (int64_t j = j0 + 4 * (int64_t)threadIdx.x; j < j1; j += 4 * kBnThreads) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + base + j));
+      auto add = [&](const float4& v, const float4& g) {
         const float d[4] = {v.x - K, v.y - K, v.z - K, v.w - K};
         if constexpr (kBackward) {
-          const float4 g = __ldg(reinterpret_cast<const float4*>(dy + base + j));
           const float gg[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) { a[q] += gg[q]; b[q] = fmaf(gg[q], d[q], b[q]); }
@@ -68,6 +66,21 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
 #pragma unroll
           for (int q = 0; q < 4; ++q) { a[q] += d[q]; b[q] = fmaf(d[q], d[q], b[q]); }
         }
+      };
+      constexpr int64_t kStep = 4 * kBnThreads;
+      int64_t j = j0 + 4 * (int64_t)threadIdx.x;
+      for (; j < j1; j += 4 * kStep) {                       // up to four independent 16-byte loads (eight in the backward)
+        float4 v[4], g[4];                                   // in flight; a slice is only ~4 trips long per sample
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (j + u * kStep < j1) {
+            v[u] = __ldg(reinterpret_cast<const float4*>(x + base + j + u * kStep));
+            if constexpr (kBackward) g[u] = __ldg(reinterpret_cast<const float4*>(dy + base + j + u * kStep));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j + u * kStep < j1) add(v[u], g[u]);
       }
     } else {
       for (int64_t j = j0 + threadIdx.x; j < j1; j += kBnThreads) {
@@ -109,12 +122,22 @@ __device__ __forceinline__ void apply_slice(const float* __restrict__ x, float* 
   for (int i = 0; i < n; ++i) {
     const int64_t base = ((int64_t)i * c + ch) * hw;
     if (vec) {
-      for (int64_t j = j0 + 4 * (int64_t)threadIdx.x; j < j1; j += 4 * kBnThreads) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + base + j));
+      auto one = [&](const float4& v) {
         float4 o;
         o.x = fmaf(v.x - mean, scale, shift); o.y = fmaf(v.y - mean, scale, shift);
         o.z = fmaf(v.z - mean, scale, shift); o.w = fmaf(v.w - mean, scale, shift);
-        *reinterpret_cast<float4*>(y + base + j) = o;
+        return o;
+      };
+      constexpr int64_t kStep = 4 * kBnThreads;
+      int64_t j = j0 + 4 * (int64_t)threadIdx.x;
+      for (; j < j1; j += 4 * kStep) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j + u * kStep < j1) v[u] = __ldg(reinterpret_cast<const float4*>(x + base + j + u * kStep));
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j + u * kStep < j1) *reinterpret_cast<float4*>(y + base + j + u * kStep) = one(v[u]);
       }
     } else {
       for (int64_t j = j0 + threadIdx.x; j < j1; j += kBnThreads) y[base + j] = fmaf(__ldg(x + base + j) - mean, scale, shift);
@@ -203,13 +226,26 @@ bn_backward_kernel(const float* __restrict__ x, const float* __restrict__ dy, in
   for (int i = 0; i < n; ++i) {
     const int64_t base = ((int64_t)i * c + ch) * hw;
     if (vec) {
-      for (int64_t j = j0 + 4 * (int64_t)threadIdx.x; j < j1; j += 4 * kBnThreads) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + base + j));
-        const float4 g = __ldg(reinterpret_cast<const float4*>(dy + base + j));
+      auto one = [&](const float4& v, const float4& g) {
         float4 o;
         o.x = (g.x - k1 - (v.x - mu) * k2) * sc; o.y = (g.y - k1 - (v.y - mu) * k2) * sc;
         o.z = (g.z - k1 - (v.z - mu) * k2) * sc; o.w = (g.w - k1 - (v.w - mu) * k2) * sc;
-        *reinterpret_cast<float4*>(dx + base + j) = o;
+        return o;
+      };
+      constexpr int64_t kStep = 4 * kBnThreads;
+      int64_t j = j0 + 4 * (int64_t)threadIdx.x;
+      for (; j < j1; j += 4 * kStep) {
+        float4 v[4], g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (j + u * kStep < j1) {
+            v[u] = __ldg(reinterpret_cast<const float4*>(x + base + j + u * kStep));
+            g[u] = __ldg(reinterpret_cast<const float4*>(dy + base + j + u * kStep));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j + u * kStep < j1) *reinterpret_cast<float4*>(dx + base + j + u * kStep) = one(v[u], g[u]);
       }
     } else {
       for (int64_t j = j0 + threadIdx.x; j < j1; j += kBnThreads)
