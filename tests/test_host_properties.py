@@ -331,3 +331,21 @@ def test_tensor_core_accumulate_model_reproduces_the_probe():
         assert not np.array_equal(model(other), want)
     rn = (a.astype(np.float64) @ b.astype(np.float64).T).astype(np.float32).astype(np.float64)
     assert not np.array_equal((rn - v) / probe.U, want)
+
+
+def test_batchnorm_slice_plan_never_leaves_an_empty_slice():
+    """rvb_bn_splits (plumbing, no kernel): for any (n, c, hw) the slices of length roundup4(ceil(hw / splits)) cover hw
+    with a non-empty last slice, splits stays within the workspace bound, and large layers get ~4 blocks per SM."""
+    from reconvat_b200 import _lib
+    rng = np.random.default_rng(5)
+    cases = [(8, 16, 640 * 229), (8, 128, 80 * 28), (1, 1, 1), (3, 5, 17 * 13), (2, 1024, 30), (1, 7, 4097), (64, 3, 5)]
+    cases += [(int(rng.integers(1, 9)), int(rng.integers(1, 300)), int(rng.integers(1, 200000))) for _ in range(200)]
+    for n, c, hw in cases:
+        splits = _lib.bn_splits(n, c, hw)
+        assert 1 <= splits <= 64
+        chunk = (-(-hw // splits) + 3) // 4 * 4
+        assert (splits - 1) * chunk < hw <= splits * chunk, (n, c, hw, splits, chunk)
+        if splits > 1:
+            assert hw // splits >= 1000 or splits * c <= 4 * 148 + c      # slices of >= ~1 024 elements
+    assert _lib.bn_splits(8, 16, 640 * 229) == 37                          # 16 x 37 = 592 blocks = 4 per SM
+    assert _lib.bn_nhwc_workspace_bytes(16) == 1024 * 16 * 16 + 3 * 16 * 4 + 16
