@@ -298,7 +298,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---------------- precision="strict": the once-folded contraction (every bin accumulated on its own) ------------
     strict = None
-    if not args.no_graphs and not args.no_gpu_baselines:
+    if not args.no_graphs and not args.no_gpu_baselines and world == 1:      # context legs: at N = 1 only
         step_s = HotPathStep(model, dev, precision="strict")
         for i in range(3):
             step_s(dev_audio[i % n_rot])
@@ -322,7 +322,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---------------- the zero-edit module surface and the reference's eager path on the same GPU ----------------
     surface = gpu_eager = None
-    if not args.no_gpu_baselines:
+    if not args.no_gpu_baselines and world == 1:
         f32_audio = [a.float().div_(32768.0) if a.dtype == torch.int16 else a for a in dev_audio[:min(n_rot, 4)]]
         k_b = max(3, min(args.steps, 20))
 
@@ -546,7 +546,7 @@ def run_ours(args, rank, local_rank, world):
                       "frac_of_size_matched_copy": gbs / copy_gbs[n] if copy_gbs.get(n) else None}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:                               # rank 0 at N = 1 only
         os.sched_setaffinity(0, all_cpus)                    # the CPU baseline gets every core again
         cores = len(all_cpus) or 1
         torch.set_num_threads(cores)
