@@ -606,7 +606,7 @@ def run_transcribe(args, rank, local_rank, world):
     """--workload transcribe (BASELINE config 5): one file of --file-seconds of synthetic 16 kHz
     PCM16 through whole-file inference, sharded by TIME over the ranks: Mel front-end with the file-global min / max
     (ONE NCCL MAX all-reduce of two keys per file, reconvat_b200.parallel.global_minmax_keys) and, with --model unet,
-    the reference's own UNet (oracle/_ref snapshot, patched by install(attention=True)) on overlapping 640-frame
+    the reference's own UNet (oracle/_ref snapshot, patched by install(attention=True, batchnorm=True)) on overlapping 640-frame
     windows (reconvat_b200.transcribe.transcribe_file).  The work per file is fixed: strong scaling.  Before timing,
     the sharded front-end is compared bit for bit with the one-rank result."""
     import numpy as np
@@ -653,7 +653,7 @@ def run_transcribe(args, rank, local_rank, world):
     if args.model == "unet":
         from oracle import reference_loader as RL
         if RL.available():
-            ns = RL.load_patched(attention=True)
+            ns = RL.load_patched(attention=True, batchnorm=os.environ.get("RVB_BENCH_BN", "1") != "0")
             torch.manual_seed(0)
             model = ns.self_attention_VAT.UNet((2, 2), (2, 2), log=True, reconstruction=True, mode="imagewise", spec="Mel",
                                                XI=1e-6, eps=1.3).to(dev).eval()           # transcribe_files.py:63-64
